@@ -1,0 +1,175 @@
+// api.cu — library-wide state and ghf_hypergnn_forward_host, the end-to-end entry point that takes
+// HOST buffers (the shape of the reference's HyperGNN.forward, HG:236-298, at a C boundary).
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "ghf_b200.h"
+#include "graph.cuh"
+
+namespace ghf {
+
+std::atomic<int64_t> g_launches{0};
+
+char* err_buf() {
+  static thread_local char buf[kErrLen] = {0};
+  return buf;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+}  // namespace ghf
+
+using namespace ghf;
+
+extern "C" int ghf_abi_version(void) { return GHF_ABI_VERSION; }
+extern "C" const char* ghf_last_error(void) { return err_buf(); }
+extern "C" int64_t ghf_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+extern "C" int ghf_device_ok(void) {
+  int dev = 0, major = 0;
+  GHF_CUDA(cudaGetDevice(&dev));
+  GHF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  GHF_REQUIRE(major == 10, "ghf_b200 needs a compute-capability 10.x device (sm_100a); current device is %d.x",
+              major);
+  // keep stream-ordered scratch cached in the pool between calls
+  cudaMemPool_t pool;
+  GHF_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t keep = ~0ull;
+  GHF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  return 0;
+}
+
+namespace {
+
+// flat parameter list: 5 global tensors, then per layer
+//   3 MLPs (W_msg, W_self, bias) x (depth+1) x {weight, bias}, 3 log_scales, LayerNorm {weight, bias}
+struct LayerParams {
+  std::vector<const float*> w[3], b[3];
+  const float* log_scale[3];
+  const float *ln_w, *ln_b;
+};
+
+}  // namespace
+
+extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float* const* d_params,
+                                         int64_t n_params, const float* h_node_features, int64_t num_nodes,
+                                         const int64_t* h_edge_index, int64_t E, const uint8_t* h_utf8,
+                                         const int64_t* h_offsets, float* h_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(desc && d_params, "ghf_hypergnn_forward_host: NULL model");
+  const int T = desc->text_dim, F = desc->node_feat_dim, d = desc->hidden_dim, L = desc->num_layers;
+  const int C = desc->char_emb_dim, H = desc->gen_hidden, depth = desc->gen_depth;
+  GHF_REQUIRE(L >= 1, "num_layers must be at least 1");
+  GHF_REQUIRE(T > 0 && F > 0 && d > 0 && C > 0 && depth >= 0 && (H > 0 || depth == 0), "bad model dimensions");
+  const int64_t per_layer = 3 * 2 * (depth + 1) + 3 + 2;
+  GHF_REQUIRE(n_params == 5 + L * per_layer, "expected %lld parameter tensors, got %lld",
+              (long long)(5 + L * per_layer), (long long)n_params);
+  if (int rc = ghf_device_ok()) return rc;
+
+  const float *emb = d_params[0], *Wp = d_params[1], *bp = d_params[2], *Win = d_params[3], *bin = d_params[4];
+  std::vector<LayerParams> layers(L);
+  {
+    int64_t p = 5;
+    for (int l = 0; l < L; ++l) {
+      for (int m = 0; m < 3; ++m)
+        for (int i = 0; i <= depth; ++i) {
+          layers[l].w[m].push_back(d_params[p++]);
+          layers[l].b[m].push_back(d_params[p++]);
+        }
+      for (int m = 0; m < 3; ++m) layers[l].log_scale[m] = d_params[p++];
+      layers[l].ln_w = d_params[p++];
+      layers[l].ln_b = d_params[p++];
+    }
+  }
+
+  const int64_t text_bytes = E > 0 ? h_offsets[E] : 0;
+  TempBuf x, ei, utf8, offs, rel, first, h0, h1, temb;
+  GHF_CUDA(x.alloc(num_nodes * (size_t)F * 4, stream));
+  GHF_CUDA(ei.alloc(2 * E * sizeof(int64_t), stream));
+  GHF_CUDA(utf8.alloc(text_bytes, stream));
+  GHF_CUDA(offs.alloc((E + 1) * sizeof(int64_t), stream));
+  GHF_CUDA(rel.alloc(E * sizeof(int32_t), stream));
+  GHF_CUDA(first.alloc(E * sizeof(int64_t), stream));
+  GHF_CUDA(h0.alloc(num_nodes * (size_t)d * 4, stream));
+  GHF_CUDA(h1.alloc(num_nodes * (size_t)d * 4, stream));
+  GHF_CUDA(cudaMemcpyAsync(x.p, h_node_features, num_nodes * (size_t)F * 4, cudaMemcpyHostToDevice, stream));
+  GHF_CUDA(cudaMemcpyAsync(ei.p, h_edge_index, 2 * E * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  GHF_CUDA(cudaMemcpyAsync(utf8.p, h_utf8, text_bytes, cudaMemcpyHostToDevice, stream));
+  GHF_CUDA(cudaMemcpyAsync(offs.p, h_offsets, (E + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+
+  // HG:261  h = relu(input_proj(x))
+  if (int rc = ghf_linear(x.as<float>(), num_nodes, F, Win, bin, d, 1, nullptr, h0.as<float>(), stream)) return rc;
+  // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
+  int64_t U = 0;
+  if (int rc = ghf_dedup_texts(utf8.as<uint8_t>(), offs.as<int64_t>(), E, rel.as<int32_t>(), first.as<int64_t>(),
+                               &U, stream))
+    return rc;
+  GHF_CUDA(temb.alloc((U > 0 ? U : 1) * (size_t)T * 4, stream));
+  if (int rc = ghf_text_encode(utf8.as<uint8_t>(), offs.as<int64_t>(), first.as<int64_t>(), U, emb, C, Wp, bp, T,
+                               temb.as<float>(), stream))
+    return rc;
+
+  ghf_graph* g = nullptr;
+  if (int rc = ghf_graph_build(ei.as<int64_t>(), rel.as<int32_t>(), E, num_nodes, (int32_t)(U > 0 ? U : 1), d, 0,
+                               num_nodes, 0, 0, &g, stream))
+    return rc;
+  struct Guard {
+    ghf_graph* g;
+    ~Guard() { ghf_graph_free(g); }
+  } guard{g};
+
+  const int prec = (desc->precision == GHF_PREC_TF32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
+                                                                                         : GHF_PREC_FP32;
+  const int64_t Un = U > 0 ? U : 1;
+  TempBuf wmsg, wself, wbias, hid_a, hid_b, ws;
+  GHF_CUDA(wmsg.alloc(Un * (size_t)d * d * 4, stream));
+  GHF_CUDA(wself.alloc(Un * (size_t)d * d * 4, stream));
+  GHF_CUDA(wbias.alloc(Un * (size_t)d * 4, stream));
+  GHF_CUDA(hid_a.alloc(Un * (size_t)(H > 0 ? H : 1) * 4, stream));
+  GHF_CUDA(hid_b.alloc(Un * (size_t)(H > 0 ? H : 1) * 4, stream));
+  GHF_CUDA(ws.alloc(ghf_mp_workspace_bytes(g, d, prec), stream));
+  float* outs[3] = {wmsg.as<float>(), wself.as<float>(), wbias.as<float>()};
+  const int n_out[3] = {d * d, d * d, d};
+
+  float* cur = h0.as<float>();
+  float* nxt = h1.as<float>();
+  for (int l = 0; l < L; ++l) {
+    // WG:137-141 for the U distinct relations
+    for (int m = 0; m < 3 && U > 0; ++m) {
+      const float* in = temb.as<float>();
+      int in_dim = T;
+      for (int i = 0; i < depth; ++i) {
+        float* o = (i & 1) ? hid_b.as<float>() : hid_a.as<float>();
+        if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][i], layers[l].b[m][i], H, 1, nullptr, o, stream))
+          return rc;
+        in = o;
+        in_dim = H;
+      }
+      if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][depth], layers[l].b[m][depth], n_out[m], 0,
+                              layers[l].log_scale[m], outs[m], stream))
+        return rc;
+    }
+    // HG:286-296
+    if (int rc = ghf_mp_layer(g, cur, outs[0], outs[1], outs[2], layers[l].ln_w, layers[l].ln_b, desc->ln_eps, prec,
+                              nxt, nullptr, ws.p, stream))
+      return rc;
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  GHF_CUDA(cudaMemcpyAsync(h_out, cur, num_nodes * (size_t)d * 4, cudaMemcpyDeviceToHost, stream));
+  GHF_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}

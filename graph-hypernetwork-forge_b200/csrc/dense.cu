@@ -1,0 +1,89 @@
+// dense.cu — ghf_linear: Y = alpha * act(X W^T + b), fp32 FFMA.
+// Replaces F.relu(input_proj(x)) (HG:261), the generator MLP Linears (WG:97-107) and the scaled
+// final Linear (WG:138-140: flat * exp(log_scale)).
+#include "ffma_gemm.cuh"
+#include "ghf_b200.h"
+
+namespace ghf {
+namespace {
+
+template <int BN, bool VEC>
+__global__ void __launch_bounds__(kFfmaThreads)
+linear_kernel(const float* __restrict__ X, int64_t M, int K, const float* __restrict__ W,
+              const float* __restrict__ b, int N, int relu, const float* __restrict__ log_scale,
+              float* __restrict__ Y) {
+  __shared__ FfmaSmem<BN> sm;
+  constexpr int TN = BN / 16;
+  const int64_t m0 = (int64_t)blockIdx.x * kFfmaBM;
+  const int n0 = blockIdx.y * BN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  auto loadA = [&](int row, int k) -> float {
+    const int64_t m = m0 + row;
+    return (m < M && k < K) ? X[m * K + k] : 0.f;
+  };
+  auto loadA4 = [&](int row, int k) -> float4 {
+    const int64_t m = m0 + row;
+    return (m < M && k < K) ? *reinterpret_cast<const float4*>(X + m * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto loadB = [&](int k, int n) -> float {
+    const int nn = n0 + n;
+    return (nn < N && k < K) ? W[(int64_t)nn * K + k] : 0.f;
+  };
+  auto loadB4 = [&](int k, int n) -> float4 {
+    const int nn = n0 + n;
+    return (nn < N && k < K) ? *reinterpret_cast<const float4*>(W + (int64_t)nn * K + k)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  ffma_mainloop<BN, VEC, /*B_KMAJOR=*/true>(sm, K, loadA, loadA4, loadB, loadB4, acc);
+
+  const float alpha = log_scale ? expf(*log_scale) : 1.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ffma_row(ty, i);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + ffma_col<BN>(tx, j);
+      if (n >= N) continue;
+      float v = acc[i][j] + (b ? b[n] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      Y[m * N + n] = v * alpha;
+    }
+  }
+}
+
+template <int BN>
+int launch_linear(const float* X, int64_t M, int K, const float* W, const float* b, int N, int relu,
+                  const float* log_scale, float* Y, cudaStream_t stream) {
+  const bool vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) % 16 == 0);
+  dim3 grid((unsigned)cdiv(M, kFfmaBM), (unsigned)cdiv(N, BN));
+  if (vec)
+    linear_kernel<BN, true><<<grid, kFfmaThreads, 0, stream>>>(X, M, K, W, b, N, relu, log_scale, Y);
+  else
+    linear_kernel<BN, false><<<grid, kFfmaThreads, 0, stream>>>(X, M, K, W, b, N, relu, log_scale, Y);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+}  // namespace ghf
+
+using namespace ghf;
+
+extern "C" int ghf_linear(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
+                          int relu, const float* d_log_scale, float* d_Y, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(M >= 0 && K > 0 && N > 0, "ghf_linear: bad dims M=%lld K=%d N=%d", (long long)M, K, N);
+  GHF_REQUIRE(cdiv(N, 32) <= 65535, "ghf_linear: N=%d too large", N);
+  if (M == 0) return 0;
+  if (N <= 32) return launch_linear<32>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
+  if (N <= 64) return launch_linear<64>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
+  return launch_linear<128>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
+}

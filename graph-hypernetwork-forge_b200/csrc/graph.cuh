@@ -1,0 +1,24 @@
+// graph.cuh — device-resident result of ghf_graph_build, shared with the message-passing kernels.
+#pragma once
+
+#include <stdint.h>
+
+struct ghf_graph {
+  int64_t num_edges_in = 0;   // E of the edge_index the graph was built from
+  int64_t num_kept = 0;       // edges whose destination lies in [dst_lo, dst_hi)
+  int64_t num_nodes = 0;      // N (global)
+  int64_t dst_lo = 0, dst_hi = 0;
+  int64_t num_local = 0;      // dst_hi - dst_lo
+  int64_t num_units = 0;
+  int32_t num_rel = 0, hidden_dim = 0, sb_nodes = 0, unit_edges = 0;
+  // all arrays below are device memory owned by the graph
+  int32_t* src_sorted = nullptr;   // [kept]  global source id at each sorted position
+  int32_t* dst_sorted = nullptr;   // [kept]  LOCAL destination id (dst - dst_lo)
+  int64_t* perm = nullptr;         // [kept]  original edge id at each sorted position
+  int32_t* indeg = nullptr;        // [local] in-degree (multi-edges counted)
+  int64_t* rowptr = nullptr;       // [local+1] exclusive scan of indeg (dst-CSR row pointer)
+  int32_t* unit_start = nullptr;   // [units] first sorted position of the unit
+  int32_t* unit_count = nullptr;   // [units] edges in the unit (<= unit_edges)
+  int32_t* unit_rel = nullptr;     // [units] the one relation all its edges share
+  int64_t bytes = 0;
+};

@@ -1,0 +1,226 @@
+// mp.cu — ghf_mp_layer: one relation-typed message-passing layer (HG:160-230 + HG:289-296).
+//
+//   acc_v  = sum_{e:(u->v), r} ( [h_u | h_v] @ [W_msg[r] ; W_self[r]] + bias[r] )      (contraction)
+//   upd_v  = acc_v / max(indeg_v, 1)
+//   out_v  = LayerNorm( relu(upd_v + h_v) )                                            (epilogue)
+//
+// The self-loop of the reference, h_v @ mean_e(W_self[r_e]) (HG:217-228), is the same sum by
+// linearity, which is why it rides along as the second half of K.  Two contraction engines:
+//   GHF_PREC_FP32  this file: CUDA-core FFMA tiles, exact fp32;
+//   GHF_PREC_TF32  mp_umma.cu: tcgen05 kind::tf32 with TMEM accumulators.
+#include "ffma_gemm.cuh"
+#include "ghf_b200.h"
+#include "graph.cuh"
+#include "mp.cuh"
+
+namespace ghf {
+namespace {
+
+template <int BN, bool VEC>
+__global__ void __launch_bounds__(kFfmaThreads)
+mp_fp32_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
+               const int32_t* __restrict__ unit_rel, int64_t num_units,
+               const int32_t* __restrict__ src_sorted, const int32_t* __restrict__ dst_sorted,
+               const float* __restrict__ h, int64_t dst_lo, int d, const float* __restrict__ W_msg,
+               const float* __restrict__ W_self, const float* __restrict__ bias, float* __restrict__ acc_out) {
+  __shared__ FfmaSmem<BN> sm;
+  __shared__ int32_t s_src[kFfmaBM], s_dst[kFfmaBM];
+  constexpr int TN = BN / 16;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+    const int start = unit_start[u], count = unit_count[u];
+    const int64_t r = unit_rel[u];
+    const float* Wm = W_msg + r * d * d;
+    const float* Ws = W_self + r * d * d;
+    for (int t0 = 0; t0 < count; t0 += kFfmaBM) {
+      const int rows = min(kFfmaBM, count - t0);
+      __syncthreads();
+      if (threadIdx.x < kFfmaBM) {
+        const bool ok = (int)threadIdx.x < rows;
+        s_src[threadIdx.x] = ok ? src_sorted[start + t0 + threadIdx.x] : -1;
+        s_dst[threadIdx.x] = ok ? dst_sorted[start + t0 + threadIdx.x] : -1;
+      }
+      __syncthreads();
+      for (int n0 = 0; n0 < d; n0 += BN) {
+        float acc[8][TN];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+        // A row = [ h[src] | h[dst] ]  (K = 2d)
+        auto rowptr = [&](int row, int k) -> const float* {
+          const int s = s_src[row];
+          if (s < 0 || k >= 2 * d) return nullptr;
+          return k < d ? h + (int64_t)s * d + k : h + (dst_lo + s_dst[row]) * d + (k - d);
+        };
+        auto loadA = [&](int row, int k) -> float {
+          const float* p = rowptr(row, k);
+          return p ? *p : 0.f;
+        };
+        auto loadA4 = [&](int row, int k) -> float4 {
+          const float* p = rowptr(row, k);
+          return p ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // B row k = W_msg[r][k][:] for k < d, W_self[r][k-d][:] after
+        auto colptr = [&](int k, int n) -> const float* {
+          const int nn = n0 + n;
+          if (nn >= d || k >= 2 * d) return nullptr;
+          return (k < d ? Wm + (int64_t)k * d : Ws + (int64_t)(k - d) * d) + nn;
+        };
+        auto loadB = [&](int k, int n) -> float {
+          const float* p = colptr(k, n);
+          return p ? *p : 0.f;
+        };
+        auto loadB4 = [&](int k, int n) -> float4 {
+          const float* p = colptr(k, n);
+          return p ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        ffma_mainloop<BN, VEC, /*B_KMAJOR=*/false>(sm, 2 * d, loadA, loadA4, loadB, loadB4, acc);
+
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = ffma_row(ty, i);
+          if (row >= rows) continue;
+          float* out = acc_out + (int64_t)s_dst[row] * d;
+#pragma unroll
+          for (int j = 0; j < TN; ++j) {
+            const int n = n0 + ffma_col<BN>(tx, j);
+            if (n < d) atomicAdd(out + n, acc[i][j] + bias[r * d + n]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// One warp per destination row: upd = acc / max(indeg,1); x = relu(upd + h); LayerNorm(x).
+// MAXV values per lane live in registers (d <= 32*MAXV); larger d re-reads the row.
+constexpr int kLnMaxV = 8;
+__global__ void __launch_bounds__(256)
+mp_epilogue_kernel(const float* __restrict__ acc, const int32_t* __restrict__ indeg,
+                   const float* __restrict__ h, int64_t dst_lo, int64_t num_local, int d,
+                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
+                   float* __restrict__ out, float* __restrict__ upd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (v >= num_local) return;
+  const float inv = 1.f / (float)max(indeg[v], 1);
+  const float* a = acc + v * d;
+  const float* hv = h + (dst_lo + v) * d;
+  float* o = out + v * d;
+  float* up = upd ? upd + v * d : nullptr;
+  float x[kLnMaxV];
+  float sum = 0.f;
+  const bool in_regs = d <= 32 * kLnMaxV;
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = 0.f;
+      if (c < d) {
+        const float u = a[c] * inv;
+        if (up) up[c] = u;
+        x[i] = fmaxf(u + hv[c], 0.f);
+        sum += x[i];
+      }
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) {
+      const float u = a[c] * inv;
+      if (up) up[c] = u;
+      const float xv = fmaxf(u + hv[c], 0.f);
+      o[c] = xv;  // parked in the output row, normalised in place below
+      sum += xv;
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const float mean = sum / (float)d;
+  float var = 0.f;
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i)
+      if (lane + 32 * i < d) var += (x[i] - mean) * (x[i] - mean);
+  } else {
+    for (int c = lane; c < d; c += 32) var += (o[c] - mean) * (o[c] - mean);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+  const float rstd = rsqrtf(var / (float)d + eps);
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d) o[c] = (x[i] - mean) * rstd * ln_w[c] + ln_b[c];
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) o[c] = (o[c] - mean) * rstd * ln_w[c] + ln_b[c];
+  }
+}
+
+template <int BN>
+int launch_mp_fp32(const ghf_graph* g, const float* h, const float* W_msg, const float* W_self,
+                   const float* bias, float* acc, cudaStream_t stream) {
+  const int d = g->hidden_dim;
+  const bool vec = (d % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(W_msg) |
+                     reinterpret_cast<uintptr_t>(W_self)) % 16 == 0);
+  const int64_t grid = g->num_units < (int64_t)sm_count() * 4 ? g->num_units : (int64_t)sm_count() * 4;
+  if (vec)
+    mp_fp32_kernel<BN, true><<<(unsigned)grid, kFfmaThreads, 0, stream>>>(
+        g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo, d,
+        W_msg, W_self, bias, acc);
+  else
+    mp_fp32_kernel<BN, false><<<(unsigned)grid, kFfmaThreads, 0, stream>>>(
+        g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo, d,
+        W_msg, W_self, bias, acc);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+}  // namespace ghf
+
+using namespace ghf;
+
+extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim, int precision) {
+  if (!g) return -1;
+  int64_t bytes = align_up(g->num_local * (int64_t)hidden_dim * 4, 256);
+  if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim);
+  return bytes + 256;
+}
+
+extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, const float* d_W_self,
+                            const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
+                            int precision, float* d_out, float* d_upd, void* d_workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(g != nullptr, "ghf_mp_layer: graph is NULL");
+  GHF_REQUIRE(d_workspace != nullptr, "ghf_mp_layer: workspace is NULL");
+  GHF_REQUIRE(precision == GHF_PREC_FP32 || precision == GHF_PREC_TF32, "ghf_mp_layer: precision=%d", precision);
+  const int d = g->hidden_dim;
+  const int64_t nl = g->num_local;
+  if (nl == 0) return 0;
+  float* acc = reinterpret_cast<float*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
+  const int64_t acc_bytes = align_up(nl * (int64_t)d * 4, 256);
+  GHF_CUDA(cudaMemsetAsync(acc, 0, nl * (size_t)d * 4, stream));
+  if (g->num_units > 0) {
+    if (precision == GHF_PREC_TF32) {
+      GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
+      void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
+      if (int rc = mp_umma_launch(g, d_h, d_W_msg, d_W_self, d_bias, acc, pack, stream)) return rc;
+    } else {
+      int rc;
+      if (d <= 32) rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
+      else if (d <= 64) rc = launch_mp_fp32<64>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
+      else rc = launch_mp_fp32<128>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
+      if (rc) return rc;
+    }
+  }
+  const int threads = 256;
+  mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(
+      acc, g->indeg, d_h, g->dst_lo, nl, d, d_ln_w, d_ln_b, eps, d_out, d_upd);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,257 @@
+"""ctypes binding of libghf_b200.so (C ABI: include/ghf_b200.h).
+
+PyTorch is used for device memory and streams only; every computation on the
+HyperGNN forward path happens inside the library's sm_100a kernels.  There is
+no fallback: a missing library raises ImportError at first use, a non-CUDA
+tensor or a non-Blackwell device raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+PREC_FP32 = 0
+PREC_TF32 = 1
+_PREC = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")
+_lib = None
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("text_dim", c_int32), ("node_feat_dim", c_int32), ("hidden_dim", c_int32),
+                ("num_layers", c_int32), ("char_emb_dim", c_int32), ("gen_hidden", c_int32),
+                ("gen_depth", c_int32), ("precision", c_int32), ("ln_eps", c_float)]
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def lib():
+    """Load the shared library once and declare every prototype of ghf_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  The B200 path has no CPU or eager-PyTorch fallback.")
+    L = ctypes.CDLL(_LIB_PATH)
+    P = c_void_p
+    sig = {
+        "ghf_abi_version": (c_int, []),
+        "ghf_last_error": (c_char_p, []),
+        "ghf_device_ok": (c_int, []),
+        "ghf_dedup_texts": (c_int, [P, P, c_int64, P, P, POINTER(c_int64), P]),
+        "ghf_text_encode": (c_int, [P, P, P, c_int64, P, c_int, P, P, c_int, P, P]),
+        "ghf_linear": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P, P]),
+        "ghf_graph_build": (c_int, [P, P, c_int64, c_int64, c_int32, c_int32, c_int64, c_int64, c_int32,
+                                    c_int32, POINTER(c_void_p), P]),
+        "ghf_graph_free": (None, [P]),
+        "ghf_graph_info": (c_int, [P, POINTER(c_int64)]),
+        "ghf_graph_export": (c_int, [P, P, P, P, P, P, P, P]),
+        "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
+        "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
+        "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
+                                              c_int64, P, P, P, P]),
+        "ghf_launch_count": (c_int64, [c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if L.ghf_abi_version() != 1:
+        raise ImportError(f"{_LIB_PATH}: ABI version {L.ghf_abi_version()} != 1")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_text_encode", "ghf_linear",
+    "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
+    "ghf_mp_layer", "ghf_hypergnn_forward_host", "ghf_launch_count",
+)
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ghf_last_error()
+        raise RuntimeError(f"{what} failed: {msg.decode(errors='replace') if msg else rc}")
+
+
+def precision_code(name: str) -> int:
+    try:
+        return _PREC[name]
+    except KeyError:
+        raise ValueError(f"precision must be one of {sorted(_PREC)}, got {name!r}") from None
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    """All tensors on one CUDA device; the device must be usable by the library."""
+    dev = tensors[0].device
+    for t in tensors:
+        if t.device.type != "cuda":
+            raise RuntimeError(
+                "graph_hypernetwork_forge (B200 build) runs on CUDA tensors only - there is no CPU fallback; "
+                f"got a tensor on {t.device}.  Move the model and inputs to 'cuda'.")
+        if t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {t.device} vs {dev}")
+    with torch.cuda.device(dev):
+        _check(lib().ghf_device_ok(), "ghf_device_ok")
+    return dev
+
+
+def _ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream(dev) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"expected a float32 tensor, got {t.dtype}")
+    return t.detach().contiguous()
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().ghf_launch_count(1 if reset else 0))
+
+
+# ----------------------------------------------------------------------------- ops
+def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_scale=None) -> torch.Tensor:
+    """exp(log_scale) * act(x @ weight.T + bias); x [M,K] float32 CUDA."""
+    x, weight = _f32(x), _f32(weight)
+    dev = x.device
+    M, K = x.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise RuntimeError(f"linear: x is [{M},{K}] but weight is {tuple(weight.shape)}")
+    bias = None if bias is None else _f32(bias)
+    log_scale = None if log_scale is None else _f32(log_scale)
+    y = torch.empty((M, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().ghf_linear(_ptr(x), M, K, _ptr(weight), _ptr(bias), N, int(relu), _ptr(log_scale), _ptr(y),
+                                _stream(dev)), "ghf_linear")
+    return y
+
+
+def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor):
+    """-> (rel_ids int32 [E], first_edge int64 [U]) for packed strings on the device."""
+    dev = utf8.device
+    E = offsets.numel() - 1
+    rel = torch.empty(E, dtype=torch.int32, device=dev)
+    first = torch.empty(max(E, 1), dtype=torch.int64, device=dev)
+    n = c_int64(0)
+    with torch.cuda.device(dev):
+        _check(lib().ghf_dedup_texts(_ptr(utf8), _ptr(offsets), E, _ptr(rel), _ptr(first), ctypes.byref(n),
+                                     _stream(dev)), "ghf_dedup_texts")
+    return rel, first[: n.value]
+
+
+def text_encode(utf8, offsets, index, num, char_emb, proj_w, proj_b) -> torch.Tensor:
+    dev = utf8.device
+    char_emb, proj_w, proj_b = _f32(char_emb), _f32(proj_w), _f32(proj_b)
+    C, T = char_emb.shape[1], proj_w.shape[0]
+    out = torch.empty((num, T), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().ghf_text_encode(_ptr(utf8), _ptr(offsets), _ptr(index), num, _ptr(char_emb), C, _ptr(proj_w),
+                                     _ptr(proj_b), T, _ptr(out), _stream(dev)), "ghf_text_encode")
+    return out
+
+
+class Graph:
+    """Owner of a ghf_graph handle (in-degree, dst-CSR, relation-grouped edge order)."""
+
+    def __init__(self, edge_index: torch.Tensor, rel_ids: torch.Tensor, num_nodes: int, num_rel: int,
+                 hidden_dim: int, dst_lo: int = 0, dst_hi=None, sb_nodes: int = 0, unit_edges: int = 0):
+        dev = edge_index.device
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
+        if rel_ids.dtype != torch.int32:
+            raise RuntimeError("rel_ids must be int32")
+        edge_index = edge_index.contiguous()
+        self.device = dev
+        self.num_nodes, self.hidden_dim, self.num_rel = int(num_nodes), int(hidden_dim), int(num_rel)
+        self.dst_lo = int(dst_lo)
+        self.dst_hi = int(num_nodes if dst_hi is None else dst_hi)
+        self._h = c_void_p()
+        E = edge_index.shape[1]
+        with torch.cuda.device(dev):
+            _check(lib().ghf_graph_build(_ptr(edge_index), _ptr(rel_ids.contiguous()), E, self.num_nodes,
+                                         self.num_rel, self.hidden_dim, self.dst_lo, self.dst_hi, int(sb_nodes),
+                                         int(unit_edges), ctypes.byref(self._h), _stream(dev)), "ghf_graph_build")
+        info = (c_int64 * 6)()
+        _check(lib().ghf_graph_info(self._h, info), "ghf_graph_info")
+        (self.num_kept, self.num_units, self.sb_nodes, self.unit_edges, self.num_local, self.bytes) = map(int, info)
+        self._workspace = {}
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ghf_graph_free(h)
+
+    def export(self):
+        """Integer tables for parity checks (device tensors)."""
+        dev = self.device
+        perm = torch.empty(self.num_kept, dtype=torch.int64, device=dev)
+        indeg = torch.empty(self.num_local, dtype=torch.int32, device=dev)
+        rowptr = torch.empty(self.num_local + 1, dtype=torch.int64, device=dev)
+        us = torch.empty(self.num_units, dtype=torch.int32, device=dev)
+        uc = torch.empty_like(us)
+        ur = torch.empty_like(us)
+        with torch.cuda.device(dev):
+            _check(lib().ghf_graph_export(self._h, _ptr(perm), _ptr(indeg), _ptr(rowptr), _ptr(us), _ptr(uc),
+                                          _ptr(ur), _stream(dev)), "ghf_graph_export")
+        return {"perm": perm, "indeg": indeg, "rowptr": rowptr, "unit_start": us, "unit_count": uc,
+                "unit_rel": ur}
+
+    def workspace(self, precision: int) -> torch.Tensor:
+        ws = self._workspace.get(precision)
+        if ws is None:
+            n = int(lib().ghf_mp_workspace_bytes(self._h, self.hidden_dim, precision))
+            ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._workspace[precision] = ws
+        return ws
+
+    def mp_layer(self, h, W_msg, W_self, bias, ln_w, ln_b, eps: float, precision: int, out=None,
+                 want_upd: bool = False):
+        """One message-passing layer on this graph's destination range -> (out, upd or None)."""
+        dev = self.device
+        h, W_msg, W_self, bias = _f32(h), _f32(W_msg), _f32(W_self), _f32(bias)
+        ln_w, ln_b = _f32(ln_w), _f32(ln_b)
+        d = self.hidden_dim
+        if h.shape != (self.num_nodes, d):
+            raise RuntimeError(f"h must be [{self.num_nodes},{d}], got {tuple(h.shape)}")
+        if W_msg.shape != (self.num_rel, d, d) or W_self.shape != (self.num_rel, d, d) or \
+                bias.shape != (self.num_rel, d):
+            raise RuntimeError("relation weights must be [R,d,d], [R,d,d], [R,d]")
+        if out is None:
+            out = torch.empty((self.num_local, d), dtype=torch.float32, device=dev)
+        elif out.shape != (self.num_local, d) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise RuntimeError("out must be a contiguous float32 [local nodes, d] tensor")
+        upd = torch.empty_like(out) if want_upd else None
+        ws = self.workspace(precision)
+        with torch.cuda.device(dev):
+            _check(lib().ghf_mp_layer(self._h, _ptr(h), _ptr(W_msg), _ptr(W_self), _ptr(bias), _ptr(ln_w),
+                                      _ptr(ln_b), float(eps), precision, _ptr(out), _ptr(upd), _ptr(ws),
+                                      _stream(dev)), "ghf_mp_layer")
+        return out, upd
+
+
+def forward_host(desc: ModelDesc, params, node_features, edge_index, utf8, offsets, out, device):
+    """ghf_hypergnn_forward_host: HOST numpy/pinned buffers in, host buffer out (copies inside)."""
+    arr = (c_void_p * len(params))(*[p.data_ptr() for p in params])
+    N = node_features.shape[0]
+    E = edge_index.shape[1]
+    with torch.cuda.device(device):
+        _check(lib().ghf_hypergnn_forward_host(
+            ctypes.byref(desc), arr, len(params), c_void_p(node_features.data_ptr()), N,
+            c_void_p(edge_index.data_ptr()), E, c_void_p(utf8.data_ptr()), c_void_p(offsets.data_ptr()),
+            c_void_p(out.data_ptr()), _stream(device)), "ghf_hypergnn_forward_host")
+    return out

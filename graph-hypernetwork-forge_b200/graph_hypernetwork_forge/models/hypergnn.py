@@ -1,0 +1,223 @@
+"""HyperGNN forward on B200 - drop-in for the reference `models/hypergnn.py`.
+
+Same public surface as the reference (`TextEncoder` hypergnn.py:39-81, `HyperGNN`
+hypergnn.py:88-322): constructor arguments, attributes, parameter names, the
+three `ValueError`s, `score_triple`, `num_parameters`.  What differs is where the
+work happens.  `HyperGNN.forward` is
+
+    pack strings (host) -> device dedup -> fused char-bag text encoder
+    -> graph build (in-degree, relation-grouped edge order; once per call)
+    -> per layer: generator MLPs -> message passing + self-loop + residual + ReLU + LayerNorm
+
+with every stage a hand-written sm_100a kernel behind the C ABI in
+`include/ghf_b200.h`.  Tensors must live on a CUDA device; there is no CPU or
+eager-PyTorch fallback, and the path is forward-only (no autograd).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _native, _text
+from .weight_generator import WeightGenerator
+
+
+def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if t.numel() > (1 << 16):
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)
+
+
+class PackedTexts:
+    """Relation strings on the device: bytes, offsets, per-edge relation ids, distinct-string index."""
+
+    def __init__(self, texts: List[str], device: torch.device):
+        data, offsets, edge_map = _text.pack_texts(texts)
+        self.num_edges = len(texts)
+        self.utf8 = _to_device(data, device) if data.size else torch.zeros(1, dtype=torch.uint8, device=device)
+        self.offsets = _to_device(offsets, device)
+        ids, first = _native.dedup_texts(self.utf8, self.offsets)   # over the packed strings
+        self.first = first                                          # packed-string index of each distinct text
+        self.num_unique = int(first.numel())
+        if edge_map is None:
+            self.rel_ids = ids
+        else:                                                       # edges -> packed strings -> relation ids
+            self.rel_ids = ids[_to_device(edge_map, device).long()].contiguous()
+
+
+class TextEncoder(nn.Module):
+    """Character-bag relation encoder: ``tanh(mean(Emb[min(ord(c),127)]) @ W^T + b)``."""
+
+    ASCII_VOCAB = 128
+
+    def __init__(self, text_dim: int, char_emb_dim: int = 32) -> None:
+        super().__init__()
+        self.text_dim = text_dim
+        self.char_emb = nn.Embedding(self.ASCII_VOCAB, char_emb_dim)
+        self.proj = nn.Sequential(nn.Linear(char_emb_dim, text_dim), nn.Tanh())
+
+    def _tokenize(self, text: str, device: torch.device) -> torch.Tensor:
+        """Token ids as the reference defines them (kept for API parity; the kernel tokenises UTF-8 itself)."""
+        codes = [min(ord(ch), self.ASCII_VOCAB - 1) for ch in text] or [0]
+        return torch.tensor(codes, dtype=torch.long, device=device)
+
+    def encode_packed(self, packed: PackedTexts, distinct_only: bool = True) -> torch.Tensor:
+        index = packed.first if distinct_only else None
+        num = packed.num_unique if distinct_only else packed.offsets.numel() - 1
+        return _native.text_encode(packed.utf8, packed.offsets, index, num, self.char_emb.weight,
+                                   self.proj[0].weight, self.proj[0].bias)
+
+    def forward(self, texts: List[str], device: torch.device) -> torch.Tensor:
+        """``[len(texts), text_dim]`` - one row per string, in list order (no dedup)."""
+        device = torch.device(device)
+        own = _native.require_cuda(self.char_emb.weight)
+        if device.type != "cuda" or (device.index is not None and device.index != own.index):
+            raise RuntimeError(f"TextEncoder lives on {own}, asked for {device} (no CPU fallback)")
+        device = own
+        data, offsets = _text.pack_utf8(texts)
+        utf8 = _to_device(data, device) if data.size else torch.zeros(1, dtype=torch.uint8, device=device)
+        return _native.text_encode(utf8, _to_device(offsets, device), None, len(texts), self.char_emb.weight,
+                                   self.proj[0].weight, self.proj[0].bias)
+
+    def encode_one(self, text: str, device: torch.device) -> torch.Tensor:
+        return self.forward([text], device)[0]
+
+
+class PreparedGraph:
+    """Everything `HyperGNN.forward` derives from (edge_index, edge_texts) alone; reusable across calls."""
+
+    def __init__(self, packed: PackedTexts, graph: "_native.Graph"):
+        self.packed = packed
+        self.graph = graph
+
+
+class HyperGNN(nn.Module):
+    """Hypernetwork-conditioned relational GNN (forward pass), B200-native.
+
+    ``HyperGNN(text_dim, node_feat_dim, hidden_dim, num_layers=2, dropout=0.0, char_emb_dim=32)``
+    as in the reference.  Extension (keyword-only): ``precision`` - ``"tf32"`` runs the per-edge
+    contraction on tcgen05 tensor cores (hidden_dim 32/64/128), ``"fp32"`` on CUDA cores,
+    ``None``/"auto" picks tf32 when the shape allows (env ``GHF_PRECISION`` overrides).
+    """
+
+    def __init__(self, text_dim: int, node_feat_dim: int, hidden_dim: int, num_layers: int = 2,
+                 dropout: float = 0.0, char_emb_dim: int = 32, *, precision: Optional[str] = None) -> None:
+        super().__init__()
+        if num_layers < 1:
+            raise ValueError("num_layers must be at least 1")
+        self.text_dim, self.node_feat_dim, self.hidden_dim = text_dim, node_feat_dim, hidden_dim
+        self.num_layers, self.dropout = num_layers, dropout
+        self.precision = precision
+
+        self.text_encoder = TextEncoder(text_dim=text_dim, char_emb_dim=char_emb_dim)
+        self.input_proj = nn.Linear(node_feat_dim, hidden_dim)
+        self.weight_generators = nn.ModuleList(
+            WeightGenerator(text_dim=text_dim, d_in=hidden_dim, d_out=hidden_dim,
+                            hidden_dim=max(64, 2 * text_dim), num_hidden=2, dropout=dropout)
+            for _ in range(num_layers))
+        self.layer_norms = nn.ModuleList(nn.LayerNorm(hidden_dim) for _ in range(num_layers))
+
+    # ------------------------------------------------------------------
+    def _precision_code(self) -> int:
+        name = os.environ.get("GHF_PRECISION") or self.precision or "auto"
+        if name == "auto":
+            name = "tf32" if self.hidden_dim in (32, 64, 128) else "fp32"
+        return _native.precision_code(name)
+
+    def prepare(self, edge_index: torch.Tensor, edge_texts: List[str], num_nodes: int,
+                dst_range=None) -> PreparedGraph:
+        """Dedup the relation strings and build the graph tables for (edge_index, edge_texts)."""
+        if edge_index.size(1) != len(edge_texts):
+            raise ValueError(
+                f"edge_index has {edge_index.size(1)} edges but edge_texts has {len(edge_texts)} entries")
+        device = _native.require_cuda(edge_index, self.input_proj.weight)
+        packed = PackedTexts(edge_texts, device)
+        lo, hi = (0, num_nodes) if dst_range is None else dst_range
+        graph = _native.Graph(edge_index, packed.rel_ids, num_nodes, max(packed.num_unique, 1),
+                              self.hidden_dim, dst_lo=lo, dst_hi=hi,
+                              sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
+                              unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")))
+        return PreparedGraph(packed, graph)
+
+    def _message_passing(self, h: torch.Tensor, edge_index: torch.Tensor, rel_weights: dict) -> torch.Tensor:
+        """Reference-shaped entry (hypergnn.py:160-230): per-EDGE weights ``[E,d,d]``/``[E,d]`` in, the
+        pre-residual update ``agg + self_out`` out.  Every edge is its own relation here, so this is the
+        slow way in; `forward` passes per-RELATION weights straight to the kernel instead."""
+        device = _native.require_cuda(h, edge_index)
+        E = edge_index.size(1)
+        rel = torch.arange(E, dtype=torch.int32, device=device)
+        g = _native.Graph(edge_index, rel, h.size(0), max(E, 1), h.size(1))
+        d = h.size(1)
+        ones, zeros = torch.ones(d, device=device), torch.zeros(d, device=device)
+        W_msg, W_self, bias = rel_weights["W_msg"], rel_weights["W_self"], rel_weights["bias"]
+        if E == 0:
+            W_msg = W_self = torch.zeros(1, d, d, device=device)
+            bias = torch.zeros(1, d, device=device)
+        _, upd = g.mp_layer(h, W_msg, W_self, bias, ones, zeros, 1e-5, _native.PREC_FP32, want_upd=True)
+        return upd
+
+    def forward_prepared(self, node_features: torch.Tensor, prepared: PreparedGraph,
+                         taps: Optional[dict] = None) -> torch.Tensor:
+        if self.training and self.dropout > 0.0:
+            raise NotImplementedError("dropout in training mode is outside the forward-only B200 path")
+        _native.require_cuda(node_features, self.input_proj.weight)
+        graph, packed = prepared.graph, prepared.packed
+        if node_features.size(0) != graph.num_nodes:
+            raise RuntimeError(f"graph was prepared for {graph.num_nodes} nodes, got {node_features.size(0)}")
+        if graph.dst_lo != 0 or graph.dst_hi != graph.num_nodes:
+            raise RuntimeError("forward_prepared needs a full-range graph; see distributed.ShardedHyperGNN")
+        prec = self._precision_code()
+        with torch.no_grad():
+            h = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True)
+            text_embs = self.text_encoder.encode_packed(packed)
+            if taps is not None:
+                taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
+                taps["in_degree"] = graph.export()["indeg"]
+            for l in range(self.num_layers):
+                w = self._generate(l, text_embs, packed.num_unique)
+                ln = self.layer_norms[l]
+                h, upd = graph.mp_layer(h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
+                                        want_upd=taps is not None)
+                if taps is not None:
+                    taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
+                    taps[f"upd.{l}"], taps[f"h.{l}"] = upd, h
+        return h
+
+    def _generate(self, layer: int, text_embs: torch.Tensor, num_unique: int) -> dict:
+        d = self.hidden_dim
+        if num_unique == 0:  # no edges: one all-zero relation keeps shapes valid
+            dev = text_embs.device
+            return {"W_msg": torch.zeros(1, d, d, device=dev), "W_self": torch.zeros(1, d, d, device=dev),
+                    "bias": torch.zeros(1, d, device=dev)}
+        return self.weight_generators[layer](text_embs)
+
+    def forward(self, node_features: torch.Tensor, edge_index: torch.Tensor, edge_texts: List[str]) -> torch.Tensor:
+        """``[N, node_feat_dim]``, ``[2, E]`` int64, E strings -> ``[N, hidden_dim]`` (hypergnn.py:236-298)."""
+        prepared = self.prepare(edge_index, edge_texts, node_features.size(0))
+        return self.forward_prepared(node_features, prepared)
+
+    # ------------------------------------------------------------------
+    def score_triple(self, head_emb: torch.Tensor, tail_emb: torch.Tensor) -> torch.Tensor:
+        """Dot-product link score (hypergnn.py:304-318); plain tensor arithmetic, not a kernel target."""
+        return (head_emb * tail_emb).sum(dim=-1)
+
+    def num_parameters(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    # flat parameter list in the order ghf_hypergnn_forward_host expects
+    def flat_parameters(self) -> List[torch.Tensor]:
+        te = self.text_encoder
+        out = [te.char_emb.weight, te.proj[0].weight, te.proj[0].bias, self.input_proj.weight, self.input_proj.bias]
+        for gen, ln in zip(self.weight_generators, self.layer_norms):
+            for kind in ("W_msg", "W_self", "bias"):
+                for m in gen.generators[kind]:
+                    if isinstance(m, nn.Linear):
+                        out += [m.weight, m.bias]
+            out += [gen.log_scales[k] for k in ("W_msg", "W_self", "bias")]
+            out += [ln.weight, ln.bias]
+        return [p.detach().contiguous() for p in out]

@@ -1,0 +1,116 @@
+/* ghf_b200.h — C ABI of the B200-native HyperGNN forward path.
+ *
+ * The reference (danieleschmidt/Graph-Hypernetwork-Forge) has no FFI layer: its hot path is
+ * Python calling stock ATen ops.  Each entry point below replaces one group of those call sites
+ * ("HG" = graph_hypernetwork_forge/models/hypergnn.py, "WG" = .../models/weight_generator.py).
+ * The Python drop-in (graph-hypernetwork-forge_b200/graph_hypernetwork_forge) binds them with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory on the current CUDA device, h_* is HOST memory;
+ *   - tensors are dense row-major; float = IEEE fp32; ids are int32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions enqueue work on `stream` and return without synchronising unless stated;
+ *   - return value 0 = success, non-zero = failure; ghf_last_error() describes the failure
+ *     (thread-local).  There is no CPU fallback: without a usable sm_100 device every
+ *     compute entry point fails.
+ */
+#ifndef GHF_B200_H
+#define GHF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GHF_ABI_VERSION 1
+
+/* precision of the relation-typed contraction in ghf_mp_layer */
+#define GHF_PREC_FP32 0 /* CUDA-core FFMA, fp32 end to end (rtol 1e-5 vs reference)          */
+#define GHF_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM (tolerance: DESIGN.md) */
+
+int ghf_abi_version(void);
+const char* ghf_last_error(void);
+/* 0 when a compute-capability 10.x device is current and usable */
+int ghf_device_ok(void);
+
+/* ---- a4: relation dedup (HG:264-268) -------------------------------------------------------
+ * Strings are packed as UTF-8 bytes + offsets[E+1] (string e = bytes [off[e], off[e+1])).
+ * d_rel_ids[e] = rank of string e among the distinct strings in FIRST-OCCURRENCE order;
+ * d_first_edge[u] = smallest e with d_rel_ids[e] == u (capacity E).  The number of distinct
+ * strings is written to *h_num_unique after an internal stream synchronise. */
+int ghf_dedup_texts(const uint8_t* d_utf8, const int64_t* d_offsets, int64_t E,
+                    int32_t* d_rel_ids, int64_t* d_first_edge, int64_t* h_num_unique,
+                    void* stream);
+
+/* ---- a5+a6: TextEncoder (HG:66-81) ----------------------------------------------------------
+ * out[u,:] = tanh( mean_i Emb[tok_i] @ Wp^T + bp ), tok = code points clamped to 127 recovered
+ * from UTF-8 (lead byte >= 0x80 -> 127, continuation bytes skipped), "" -> [0].
+ * Emb [128,C], Wp [T,C], bp [T], out [U,T].  Row u encodes string d_string_index[u] of the
+ * packed set (pass the d_first_edge of ghf_dedup_texts to encode the distinct strings in
+ * first-occurrence order), or string u itself when d_string_index is NULL. */
+int ghf_text_encode(const uint8_t* d_utf8, const int64_t* d_offsets, const int64_t* d_string_index,
+                    int64_t U, const float* d_emb, int C, const float* d_Wp, const float* d_bp, int T,
+                    float* d_out, void* stream);
+
+/* ---- a3 / a8: Linear (+ReLU) (+exp(log_scale)) (HG:261, WG:97-107, WG:138-140) -------------
+ * Y[M,N] = alpha * act( X[M,K] @ W[N,K]^T + b[N] ), act = ReLU when relu != 0,
+ * alpha = exp(*d_log_scale) when d_log_scale != NULL else 1.  fp32 FFMA. */
+int ghf_linear(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
+               int relu, const float* d_log_scale, float* d_Y, void* stream);
+
+/* ---- graph preprocessing (replaces the per-call gathers HG:281-283, scatter index HG:207-219)
+ * Builds, for destinations dst in [dst_lo, dst_hi):
+ *   in-degree, dst-CSR rowptr, and the edge order (super-block of dst, relation, dst), stable,
+ *   cut into work units of <= unit_edges edges that share one relation.
+ * d_edge_index is the reference's [2,E] int64 tensor.  Edges with dst outside the range are
+ * dropped (1-D destination partition for multi-GPU).  sb_nodes <= 0 / unit_edges <= 0 pick
+ * defaults.  Synchronises `stream` once (to size the unit table). */
+typedef struct ghf_graph ghf_graph;
+int ghf_graph_build(const int64_t* d_edge_index, const int32_t* d_rel_ids, int64_t E,
+                    int64_t num_nodes, int32_t num_rel, int32_t hidden_dim,
+                    int64_t dst_lo, int64_t dst_hi, int32_t sb_nodes, int32_t unit_edges,
+                    ghf_graph** out, void* stream);
+void ghf_graph_free(ghf_graph* g);
+/* sizes: [0]=kept edges, [1]=units, [2]=sb_nodes, [3]=unit_edges, [4]=local nodes, [5]=bytes held */
+int ghf_graph_info(const ghf_graph* g, int64_t info[6]);
+/* device views for parity checks: any pointer may be NULL.  perm[kept] int64 (original edge id
+ * at each sorted position), indeg[local nodes] int32, rowptr[local nodes+1] int64,
+ * unit_start/unit_count/unit_rel [units] int32. */
+int ghf_graph_export(const ghf_graph* g, int64_t* d_perm, int32_t* d_indeg, int64_t* d_rowptr,
+                     int32_t* d_unit_start, int32_t* d_unit_count, int32_t* d_unit_rel,
+                     void* stream);
+
+/* ---- a10-a13: one message-passing layer (HG:160-230, HG:289-296) ---------------------------
+ *   upd_v = (1/c_v) sum_{e:(u->v)} ( h_u W_msg[r_e] + bias[r_e] + h_v W_self[r_e] ),  c_v = max(indeg,1)
+ *   out_v = LayerNorm( relu(upd_v + h_v) ) * ln_w + ln_b            (eps, biased variance)
+ * d_h [num_nodes,d] (all nodes: sources are arbitrary); W_msg/W_self [R,d,d] ([r][in][out]),
+ * bias [R,d]; d_out / d_upd hold rows [dst_lo,dst_hi) only ([local nodes, d]); d_upd may be NULL.
+ * d_workspace: ghf_mp_workspace_bytes(g, d) bytes of scratch (no alignment beyond 256 B). */
+int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim, int precision);
+int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, const float* d_W_self,
+                 const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
+                 int precision, float* d_out, float* d_upd, void* d_workspace, void* stream);
+
+/* ---- whole forward from HOST buffers (HG:236-298): the end-to-end entry point --------------
+ * Parameters are passed as one flat array of DEVICE pointers in reference state_dict order
+ * (see INTEGRATION.md for the exact list); inputs and output are HOST
+ * buffers, copied inside the call.  Synchronises. */
+typedef struct {
+  int32_t text_dim, node_feat_dim, hidden_dim, num_layers, char_emb_dim, gen_hidden, gen_depth;
+  int32_t precision;
+  float ln_eps;
+} ghf_model_desc;
+int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float* const* d_params,
+                              int64_t n_params, const float* h_node_features, int64_t num_nodes,
+                              const int64_t* h_edge_index, int64_t E, const uint8_t* h_utf8,
+                              const int64_t* h_offsets, float* h_out, void* stream);
+
+/* counters for bench.py: kernels launched by this library since the last reset */
+int64_t ghf_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHF_B200_H */
