@@ -8,6 +8,8 @@
 // linearity, which is why it rides along as the second half of K.  Two contraction engines:
 //   GHF_PREC_FP32  this file: CUDA-core FFMA tiles, exact fp32;
 //   GHF_PREC_TF32  mp_umma.cu: tcgen05 kind::tf32 with TMEM accumulators.
+#include <vector>
+
 #include "ffma_gemm.cuh"
 #include "ghf_b200.h"
 #include "graph.cuh"
@@ -185,6 +187,35 @@ int launch_mp_fp32(const ghf_graph* g, const float* h, const float* W_msg, const
 
 using namespace ghf;
 
+// ---- optional per-kernel timing (bench.py roofline): event triples per layer call
+namespace {
+struct ProfRec { cudaEvent_t e[4]; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+extern "C" int ghf_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+
+extern "C" int ghf_profile_read(double ms[3], int64_t* launches) {
+  GHF_REQUIRE(ms != nullptr, "ghf_profile_read: NULL");
+  ms[0] = ms[1] = ms[2] = 0.0;
+  for (auto& r : g_prof) {
+    GHF_CUDA(cudaEventSynchronize(r.e[3]));
+    float a = 0, b = 0, c = 0;
+    GHF_CUDA(cudaEventElapsedTime(&c, r.e[0], r.e[1]));
+    GHF_CUDA(cudaEventElapsedTime(&a, r.e[1], r.e[2]));
+    GHF_CUDA(cudaEventElapsedTime(&b, r.e[2], r.e[3]));
+    ms[0] += a; ms[1] += b; ms[2] += c;
+    for (auto& e : r.e) cudaEventDestroy(e);
+  }
+  if (launches) *launches = (int64_t)g_prof.size();
+  g_prof.clear();
+  return 0;
+}
+
 extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim, int precision) {
   if (!g) return -1;
   int64_t bytes = align_up(g->num_local * (int64_t)hidden_dim * 4, 256);
@@ -204,12 +235,22 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
   if (nl == 0) return 0;
   float* acc = reinterpret_cast<float*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
   const int64_t acc_bytes = align_up(nl * (int64_t)d * 4, 256);
+  ProfRec rec{};
+  const bool prof = g_prof_on;
+  if (prof) {
+    for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
+    GHF_CUDA(cudaEventRecord(rec.e[0], stream));
+  }
   GHF_CUDA(cudaMemsetAsync(acc, 0, nl * (size_t)d * 4, stream));
+  if (precision == GHF_PREC_TF32 && g->num_units > 0) {
+    GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
+    if (int rc = mp_umma_pack(g, d_W_msg, d_W_self, reinterpret_cast<char*>(acc) + acc_bytes, stream)) return rc;
+  }
+  if (prof) GHF_CUDA(cudaEventRecord(rec.e[1], stream));
   if (g->num_units > 0) {
     if (precision == GHF_PREC_TF32) {
-      GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
       void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
-      if (int rc = mp_umma_launch(g, d_h, d_W_msg, d_W_self, d_bias, acc, pack, stream)) return rc;
+      if (int rc = mp_umma_launch(g, d_h, d_bias, acc, pack, stream)) return rc;
     } else {
       int rc;
       if (d <= 32) rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
@@ -218,9 +259,14 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
       if (rc) return rc;
     }
   }
+  if (prof) GHF_CUDA(cudaEventRecord(rec.e[2], stream));
   const int threads = 256;
   mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(
       acc, g->indeg, d_h, g->dst_lo, nl, d, d_ln_w, d_ln_b, eps, d_out, d_upd);
   GHF_LAUNCH_CHECK();
+  if (prof) {
+    GHF_CUDA(cudaEventRecord(rec.e[3], stream));
+    g_prof.push_back(rec);
+  }
   return 0;
 }

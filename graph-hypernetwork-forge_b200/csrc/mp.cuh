@@ -11,8 +11,11 @@ namespace ghf {
 bool mp_umma_supported(int hidden_dim);
 // bytes of scratch for the per-relation operand images [R][2d x d] (tf32, UMMA K-major SW128 layout)
 int64_t mp_umma_pack_bytes(int num_rel, int hidden_dim);
+// operand images: pack[r] = tf32([W_msg[r]; W_self[r]]) in the kernel's shared-memory layout
+int mp_umma_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch,
+                 cudaStream_t stream);
 // acc[dst_local, :] += sum over edges of [h_src | h_dst] @ [W_msg; W_self][rel] + bias[rel]
-int mp_umma_launch(const ghf_graph* g, const float* h, const float* W_msg, const float* W_self,
-                   const float* bias, float* acc, void* pack_scratch, cudaStream_t stream);
+int mp_umma_launch(const ghf_graph* g, const float* h, const float* bias, float* acc, const void* pack_scratch,
+                   cudaStream_t stream);
 
 }  // namespace ghf

@@ -264,17 +264,25 @@ bool mp_umma_supported(int d) { return d == 32 || d == 64 || d == 128; }
 
 int64_t mp_umma_pack_bytes(int num_rel, int d) { return align_up((int64_t)num_rel * 2 * d * d * 4, 256); }
 
-int mp_umma_launch(const ghf_graph* g, const float* h, const float* W_msg, const float* W_self, const float* bias,
-                   float* acc, void* pack_scratch, cudaStream_t stream) {
+int mp_umma_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch,
+                 cudaStream_t stream) {
+  const int d = g->hidden_dim;
+  GHF_REQUIRE(reinterpret_cast<uintptr_t>(pack_scratch) % 16 == 0, "mp_umma: scratch must be 16-byte aligned");
+  const int64_t total = (int64_t)g->num_rel * 2 * d * d;
+  pack_weights_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(W_msg, W_self, g->num_rel, d,
+                                                                    reinterpret_cast<uint8_t*>(pack_scratch));
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+int mp_umma_launch(const ghf_graph* g, const float* h, const float* bias, float* acc, const void* pack_scratch,
+                   cudaStream_t stream) {
   const int d = g->hidden_dim;
   GHF_REQUIRE(g->unit_edges % 128 == 0, "mp_umma: unit_edges=%d must be a multiple of 128", g->unit_edges);
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(acc) |
                reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
               "mp_umma: h / acc / bias / scratch must be 16-byte aligned");
-  uint8_t* pack = reinterpret_cast<uint8_t*>(pack_scratch);
-  const int64_t total = (int64_t)g->num_rel * 2 * d * d;
-  pack_weights_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(W_msg, W_self, g->num_rel, d, pack);
-  GHF_LAUNCH_CHECK();
+  const uint8_t* pack = reinterpret_cast<const uint8_t*>(pack_scratch);
   switch (d) {
     case 32: return launch<32>(g, h, pack, bias, acc, stream);
     case 64: return launch<64>(g, h, pack, bias, acc, stream);

@@ -59,6 +59,8 @@ def lib():
         "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
                                               c_int64, P, P, P, P]),
         "ghf_launch_count": (c_int64, [c_int]),
+        "ghf_profile_enable": (c_int, [c_int]),
+        "ghf_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header and library disagree
@@ -73,7 +75,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_text_encode", "ghf_linear",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_hypergnn_forward_host", "ghf_launch_count",
+    "ghf_mp_layer", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -121,6 +123,18 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().ghf_launch_count(1 if reset else 0))
+
+
+def profile_enable(on: bool) -> None:
+    _check(lib().ghf_profile_enable(int(on)), "ghf_profile_enable")
+
+
+def profile_read():
+    """-> ({"contraction_ms", "epilogue_ms", "prep_ms"} summed since the last read, number of layer calls)."""
+    ms = (ctypes.c_double * 3)()
+    n = c_int64(0)
+    _check(lib().ghf_profile_read(ms, ctypes.byref(n)), "ghf_profile_read")
+    return {"contraction_ms": ms[0], "epilogue_ms": ms[1], "prep_ms": ms[2]}, int(n.value)
 
 
 # ----------------------------------------------------------------------------- ops

@@ -27,7 +27,8 @@ from .weight_generator import WeightGenerator
 
 
 def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
-    t = torch.from_numpy(np.ascontiguousarray(arr))
+    arr = np.ascontiguousarray(arr)
+    t = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
     if t.numel() > (1 << 16):
         t = t.pin_memory()
     return t.to(device, non_blocking=True)

@@ -110,6 +110,14 @@ int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float* const* d_
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t ghf_launch_count(int reset);
 
+/* Per-kernel device timing for the roofline report.  While enabled, ghf_mp_layer brackets its
+ * contraction kernel and its epilogue kernel with CUDA events on the launching stream.
+ * ghf_profile_read synchronises those events, returns the summed milliseconds and launch count
+ * since the last read ([0]=contraction ms, [1]=epilogue ms, [2]=operand-pack + clear ms) and
+ * resets the sums. */
+int ghf_profile_enable(int on);
+int ghf_profile_read(double ms[3], int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,194 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors of the reference and
+against the oracle on the same seeded inputs.  Run with `-m gpu` on a B200."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hypergnn_oracle as O
+from _util import (FORWARD_CASES, FP32_ATOL, FP32_RTOL, TF32_H_ATOL_INIT, TF32_H_ATOL_SCALE1, TF32_UPD_REL,
+                   assert_close, assert_rel_to_max, build_model, load_case, model_params_numpy)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_model(case, precision):
+    model = build_model(case, DEV, precision=precision)
+    x = torch.from_numpy(case["node_features"]).to(DEV)
+    ei = torch.from_numpy(case["edge_index"]).to(DEV)
+    taps = {}
+    prepared = model.prepare(ei, case["edge_texts"], x.size(0))
+    out = model.forward_prepared(x, prepared, taps=taps)
+    torch.cuda.synchronize()
+    return model, out.cpu().numpy(), {k: v.cpu().numpy() for k, v in taps.items()}
+
+
+@pytest.mark.parametrize("name", FORWARD_CASES)
+def test_fp32_path_matches_reference_golden(name):
+    case = load_case(name)
+    model, out, taps = run_model(case, "fp32")
+    ref = case["taps"]
+    L = case["ctor"]["num_layers"]
+    # integer work: bit-exact
+    assert np.array_equal(taps["edge_rel_ids"].astype(np.int64), case["edge_rel_ids"])
+    assert np.array_equal(taps["in_degree"].astype(np.int64), case["in_degree"])
+    # floating point: fp32 path, rtol 1e-5 (atol scaled to the tap's magnitude)
+    assert_close(taps["text_embs"], ref["text_embs"], FP32_RTOL, FP32_ATOL, "text_embs")
+    for l in range(L):
+        for k in ("W_msg", "W_self", "bias"):
+            if f"{k}.{l}" in ref:
+                assert_close(taps[f"{k}.{l}"], ref[f"{k}.{l}"], FP32_RTOL,
+                             2e-6 * float(np.abs(ref[f"{k}.{l}"]).max()), f"{k}.{l}")
+        assert_close(taps[f"upd.{l}"], ref[f"upd.{l}"], 1e-4, 2e-5 * float(np.abs(ref[f"upd.{l}"]).max()),
+                     f"upd.{l}")
+        assert_close(taps[f"h.{l}"], ref[f"h.{l}"], 1e-4, 2e-5, f"h.{l}")
+    assert_close(out, ref["out"], 1e-4, 2e-5, "out")
+
+
+@pytest.mark.parametrize("name", ["toy_c1", "synth_small", "synth_small_scale1", "synth_d64", "synth_d128",
+                                  "synth_d128_scale1"])
+def test_tf32_path_matches_reference_golden(name):
+    """tcgen05 kind::tf32 contraction; tolerance stated in _util.py / DESIGN.md."""
+    case = load_case(name)
+    model, out, taps = run_model(case, "tf32")
+    ref = case["taps"]
+    for l in range(case["ctor"]["num_layers"]):
+        if l == 0:  # layer 0 sees the exact h0, so upd isolates the contraction error
+            assert_rel_to_max(taps[f"upd.{l}"], ref[f"upd.{l}"], TF32_UPD_REL, f"upd.{l}")
+    atol = TF32_H_ATOL_SCALE1 if case["log_scale"] is not None else TF32_H_ATOL_INIT
+    assert_close(out, ref["out"], 0.0, atol, "out")
+    assert np.isfinite(out).all()
+
+
+def test_forward_call_is_drop_in(toy_kg):
+    """model(node_features, edge_index, edge_texts) exactly as the reference is called."""
+    case = load_case("toy_c1")
+    model = build_model(case, DEV)
+    out = model(toy_kg.node_features.to(DEV), toy_kg.edge_index.to(DEV), toy_kg.edge_texts)
+    assert out.shape == (8, 32) and out.device.type == "cuda"
+    assert_close(out.cpu().numpy(), case["taps"]["out"], 0.0, TF32_H_ATOL_INIT, "toy out (auto precision)")
+
+
+@pytest.mark.parametrize("N,E,R,d,L,prec", [
+    (3000, 40000, 37, 128, 2, "tf32"), (3000, 40000, 37, 128, 2, "fp32"),
+    (5000, 60000, 300, 64, 2, "tf32"), (2000, 30000, 11, 32, 3, "tf32"),
+    (1500, 9000, 50, 256, 1, "fp32"), (700, 5000, 9, 48, 2, "fp32"),
+])
+def test_against_oracle_on_seeded_graphs(N, E, R, d, L, prec):
+    """Sizes the numpy oracle finishes in seconds; weights scaled to O(1) so `upd` matters."""
+    from graph_hypernetwork_forge import HyperGNN
+    src, dst, rel, names, feats = O.synthetic_kg(N, E, R, 40, seed=N + d)
+    texts = [names[r] for r in rel]
+    torch.manual_seed(d)
+    model = HyperGNN(32, 40, d, L, precision=prec).eval()
+    with torch.no_grad():
+        for gen in model.weight_generators:
+            for p in gen.log_scales.values():
+                p.fill_(-1.0)
+    params = model_params_numpy(model)
+    ref_taps = {}
+    ref = O.hypergnn_forward(params, feats, np.stack([src, dst]), texts, d, L, dtype=np.float64, taps=ref_taps)
+    model = model.to(DEV)
+    taps = {}
+    prepared = model.prepare(torch.from_numpy(np.stack([src, dst])).to(DEV), texts, N)
+    out = model.forward_prepared(torch.from_numpy(feats).to(DEV), prepared, taps=taps).cpu().numpy()
+    assert np.array_equal(taps["edge_rel_ids"].cpu().numpy().astype(np.int64), ref_taps["edge_rel_ids"])
+    assert np.array_equal(taps["in_degree"].cpu().numpy().astype(np.int64), ref_taps["in_degree"])
+    upd0, ref0 = taps["upd.0"].cpu().numpy(), ref_taps["upd.0"]
+    if prec == "fp32":
+        assert_close(upd0, ref0, 1e-4, 2e-5 * float(np.abs(ref0).max()), "upd.0")
+        assert_close(out, ref, 1e-4, 5e-5, "out")
+    else:
+        assert_rel_to_max(upd0, ref0, TF32_UPD_REL, "upd.0")
+        assert_close(out, ref, 0.0, TF32_H_ATOL_SCALE1, "out")
+
+
+def test_graph_tables_bit_exact():
+    from graph_hypernetwork_forge import _native
+    rng = np.random.default_rng(5)
+    N, E, R = 5000, 100000, 23
+    src = rng.integers(0, N, E)
+    dst = rng.integers(0, N, E)
+    rel = rng.integers(0, R, E)
+    ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+    relt = torch.from_numpy(rel.astype(np.int32)).to(DEV)
+    for lo, hi, sb, ue in ((0, N, 512, 256), (1200, 3700, 300, 128), (0, N, 0, 0)):
+        g = _native.Graph(ei, relt, N, R, 64, dst_lo=lo, dst_hi=hi, sb_nodes=sb, unit_edges=ue)
+        t = {k: v.cpu().numpy() for k, v in g.export().items()}
+        perm, us, uc, ur = O.edge_order(dst, rel, N, R, g.sb_nodes, g.unit_edges, lo, hi)
+        assert np.array_equal(t["perm"], perm)
+        assert np.array_equal(t["unit_start"], us) and np.array_equal(t["unit_count"], uc)
+        assert np.array_equal(t["unit_rel"], ur)
+        deg = O.in_degree(dst, N)[lo:hi]
+        assert np.array_equal(t["indeg"], deg)
+        assert np.array_equal(t["rowptr"], np.concatenate([[0], np.cumsum(deg)]))
+
+
+def test_dedup_and_text_encoder_edge_cases():
+    from graph_hypernetwork_forge import _native
+    from graph_hypernetwork_forge.models.hypergnn import PackedTexts, TextEncoder
+    texts = ["", "a", "é€a", "éa", "ëa", "knows", "knows ", "a", "", "\x7f", "日本語", "knows", "\U0001F600x"] * 3
+    packed = PackedTexts(texts, torch.device(DEV))
+    unique, ids = O.dedup_texts(texts)
+    assert np.array_equal(packed.rel_ids.cpu().numpy().astype(np.int64), ids)
+    assert packed.num_unique == len(unique)
+    torch.manual_seed(3)
+    enc = TextEncoder(24, 16).to(DEV)
+    got = enc.encode_packed(packed).cpu().numpy()
+    want = O.text_encode(unique, enc.char_emb.weight.detach().cpu().numpy(),
+                         enc.proj[0].weight.detach().cpu().numpy(), enc.proj[0].bias.detach().cpu().numpy())
+    assert_close(got, want, FP32_RTOL, FP32_ATOL, "text encoder")
+    # many strings through the identity-collapse path (>= 2048 entries, few distinct objects)
+    names = [f"relation_{i:05d}" for i in range(300)]
+    rng = np.random.default_rng(0)
+    big = [names[i] for i in rng.integers(0, 300, 50000)]
+    big[17] = "relation_00005x"[:-1]   # equal content, different object
+    p2 = PackedTexts(big, torch.device(DEV))
+    u2, i2 = O.dedup_texts(big)
+    assert np.array_equal(p2.rel_ids.cpu().numpy().astype(np.int64), i2) and p2.num_unique == len(u2)
+
+
+def test_empty_graph_and_isolated_nodes():
+    from graph_hypernetwork_forge import HyperGNN
+    torch.manual_seed(0)
+    model = HyperGNN(16, 8, 32, 2).eval()
+    params = model_params_numpy(model)
+    x = np.random.default_rng(0).standard_normal((5, 8)).astype(np.float32)
+    ref = O.hypergnn_forward(params, x, np.zeros((2, 0), dtype=np.int64), [], 32, 2)
+    out = model.to(DEV)(torch.from_numpy(x).to(DEV), torch.zeros(2, 0, dtype=torch.long, device=DEV), [])
+    assert_close(out.cpu().numpy(), ref, 1e-4, 2e-5, "no-edge forward = LN(relu(h))")
+
+
+def test_c_abi_host_forward_matches():
+    """ghf_hypergnn_forward_host: host buffers in, host buffer out."""
+    from graph_hypernetwork_forge import _native, _text
+    case = load_case("synth_small")
+    model = build_model(case, DEV, precision="fp32")
+    c = case["ctor"]
+    desc = _native.ModelDesc(c["text_dim"], c["node_feat_dim"], c["hidden_dim"], c["num_layers"], 32,
+                             max(64, 2 * c["text_dim"]), 2, _native.PREC_FP32, 1e-5)
+    x = torch.from_numpy(case["node_features"]).pin_memory()
+    ei = torch.from_numpy(case["edge_index"]).pin_memory()
+    data, off = _text.pack_utf8(case["edge_texts"])
+    out = torch.empty(x.size(0), c["hidden_dim"]).pin_memory()
+    _native.forward_host(desc, model.flat_parameters(), x, ei, torch.from_numpy(data.copy()),
+                         torch.from_numpy(off), out, torch.device(DEV))
+    assert_close(out.numpy(), case["taps"]["out"], 1e-4, 2e-5, "host forward")
+
+
+def test_message_passing_reference_signature():
+    """_message_passing(h, edge_index, rel_weights) with per-edge weights, as the reference exposes it."""
+    from graph_hypernetwork_forge import HyperGNN
+    rng = np.random.default_rng(1)
+    N, E, d = 40, 150, 16
+    h = rng.standard_normal((N, d)).astype(np.float32)
+    src, dst = rng.integers(0, N, E), rng.integers(0, N, E)
+    Wm = rng.standard_normal((E, d, d)).astype(np.float32) * 0.1
+    Ws = rng.standard_normal((E, d, d)).astype(np.float32) * 0.1
+    b = rng.standard_normal((E, d)).astype(np.float32)
+    want = O.message_passing_literal(h, src, dst, Wm, Ws, b)
+    model = HyperGNN(16, 8, d, 1).to(DEV)
+    got = model._message_passing(torch.from_numpy(h).to(DEV), torch.from_numpy(np.stack([src, dst])).to(DEV),
+                                 {"W_msg": torch.from_numpy(Wm).to(DEV), "W_self": torch.from_numpy(Ws).to(DEV),
+                                  "bias": torch.from_numpy(b).to(DEV)})
+    assert_close(got.cpu().numpy(), want, 1e-4, 1e-5, "_message_passing")

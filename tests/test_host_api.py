@@ -1,0 +1,109 @@
+"""CPU-side checks: drop-in surface, host packing logic, the C-ABI library loads and exports every
+symbol include/ghf_b200.h declares, and the product path refuses CPU tensors (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hypergnn_oracle as O
+from _util import build_model, load_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported():
+    from graph_hypernetwork_forge import _native
+    header = open(os.path.join(ROOT, "include", "ghf_b200.h")).read()
+    declared = set(re.findall(r"\b(ghf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    L = ctypes.CDLL(_native.lib_path())
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _native.lib().ghf_abi_version() == 1
+
+
+def test_state_dict_and_init_stream_match_reference():
+    for name in ("toy_c1", "edge_cases", "synth_small"):
+        c = load_case(name)
+        from graph_hypernetwork_forge import HyperGNN
+        torch.manual_seed(c["seed"])
+        sd = HyperGNN(**c["ctor"]).state_dict()
+        assert list(sd.keys()) == list(c["params"].keys())      # same names, same order
+        for k, v in c["params"].items():
+            assert np.array_equal(sd[k].numpy(), v), k          # same random stream
+
+
+def test_constructor_surface_and_errors():
+    from graph_hypernetwork_forge import HyperGNN, WeightGenerator
+    from graph_hypernetwork_forge.models import TextEncoder
+    m = HyperGNN(text_dim=32, node_feat_dim=16, hidden_dim=16, num_layers=3)
+    assert len(m.weight_generators) == 3 and len(m.layer_norms) == 3 and m.num_layers == 3
+    assert (m.text_dim, m.node_feat_dim, m.hidden_dim, m.dropout) == (32, 16, 16, 0.0)
+    assert m.num_parameters() > 0
+    assert m.weight_generators[0].generators["W_msg"][0].out_features == 64   # max(64, 2*text_dim)
+    with pytest.raises(ValueError):
+        HyperGNN(32, 16, 16, num_layers=0)
+    for bad in (dict(text_dim=0, d_in=4, d_out=4), dict(text_dim=4, d_in=-1, d_out=4), dict(text_dim=4, d_in=4, d_out=0)):
+        with pytest.raises(ValueError):
+            WeightGenerator(**bad)
+    g = WeightGenerator(32, 16, 16, hidden_dim=256)
+    assert (g.text_dim, g.d_in, g.d_out, g.init_scale) == (32, 16, 16, 0.01)
+    assert g.generators["W_msg"][0].out_features == 256
+    assert sum("log_scale" in n for n, _ in g.named_parameters()) == 3
+    assert list(WeightGenerator(8, 4, 4, num_hidden=0).generators["bias"].state_dict()) == ["0.weight", "0.bias"]
+    assert list(WeightGenerator(8, 4, 4, dropout=0.1).generators["bias"].state_dict())[-2:] == ["6.weight", "6.bias"]
+    assert TextEncoder.ASCII_VOCAB == 128
+    assert TextEncoder(8)._tokenize("é€a", "cpu").tolist() == [127, 127, 97]
+    assert TextEncoder(8)._tokenize("", "cpu").tolist() == [0]
+
+
+def test_no_cpu_fallback():
+    c = load_case("toy_c1")
+    m = build_model(c)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.from_numpy(c["node_features"]), torch.from_numpy(c["edge_index"]), c["edge_texts"])
+    with pytest.raises(ValueError):   # count mismatch is checked before anything touches a device
+        m(torch.from_numpy(c["node_features"]), torch.from_numpy(c["edge_index"]), c["edge_texts"][:-1])
+    with pytest.raises(RuntimeError):
+        m.weight_generators[0](torch.randn(64))
+    with pytest.raises(RuntimeError):
+        m.text_encoder(["knows"], torch.device("cpu"))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "graph-hypernetwork-forge_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle.edge_order()", ""), os.path.join(dirpath, f)
+
+
+def test_text_packing_matches_oracle():
+    from graph_hypernetwork_forge import _text
+    texts = ["", "a", "é€a", "knows", "日本語", "a", "\U0001F600", "knows "]
+    d1, o1 = _text.pack_utf8(texts)
+    d2, o2 = O.pack_utf8(texts)
+    assert np.array_equal(d1, d2) and np.array_equal(o1, o2)
+    d1, o1 = _text.pack_utf8(["abc", "", "de"])
+    assert bytes(d1) == b"abcde" and o1.tolist() == [0, 3, 3, 5]
+    assert _text.pack_utf8([])[1].tolist() == [0]
+
+
+def test_identity_collapse_composes_to_first_occurrence_ids():
+    """collapse_by_identity + content dedup of the collapsed list == dict.fromkeys ids."""
+    from graph_hypernetwork_forge import _text
+    names = [f"relation_{i:05d}" for i in range(50)]
+    rng = np.random.default_rng(1)
+    texts = [names[i] for i in rng.integers(0, 50, 10000)]
+    texts[5] = "relation_00007x"[:-1]                      # equal content, distinct object
+    texts[9] = "".join(["relation_", "00007"])
+    data, off, edge_map = _text.pack_texts(texts)
+    assert edge_map is not None and off.size - 1 < 60
+    ids_packed, _ = O.dedup_utf8(np.asarray(data), off)    # what the device kernel computes
+    want_unique, want = O.dedup_texts(texts)
+    assert np.array_equal(ids_packed[edge_map], want)
+    assert len(set(ids_packed.tolist())) == len(want_unique)
