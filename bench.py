@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py - HyperGNN forward, edges/s per layer, on the synthetic wikikg2-shaped KG (BASELINE config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2|c4]
+
+One "step" is one complete forward pass over the workload: relation dedup + text encoder +
+input projection + graph build + L x (weight generation + message passing + LayerNorm epilogue).
+  value  : E * L / step time with inputs resident in HBM (device-timed, CUDA events)
+  e2e    : the same through the C ABI entry ghf_hypergnn_forward_host with HOST buffers
+           (H2D of features / edges / strings and D2H of the embeddings inside the timed region)
+  roofline: the message-passing contraction kernel, algorithmic bytes / its event-timed duration
+  cpu_baseline: the numpy oracle (a port of the reference algorithm) on a bounded sample, host cores
+`--impl reference` times that CPU port alone (the reference is pure Python/torch and cannot travel to
+the GPU box).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "graph-hypernetwork-forge_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # T = 64 (so generator hidden = 128) and F = d for c2-c4
+    "c2": dict(name="fb15k237-shaped", N=14_541, E=272_115, R=237, d=128, L=2, T=64, F=128),
+    "c3": dict(name="wikikg2-shaped", N=2_500_000, E=16_000_000, R=535, d=128, L=3, T=64, F=128),
+    "c4": dict(name="zero-shot-20k-rel", N=100_000, E=2_000_000, R=20_000, d=256, L=2, T=64, F=256),
+}
+NAME_LEN = 14  # len("relation_00000")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        mhz = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(mhz)}
+
+
+def make_device_inputs(w, device, seed=0):
+    """Synthetic KG of the named shape, created on the device (uniform src/dst/rel)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    N, E, R, F = w["N"], w["E"], w["R"], w["F"]
+    edge_index = torch.randint(0, N, (2, E), generator=g, device=device, dtype=torch.int64)
+    rel = torch.randint(0, R, (E,), generator=g, device=device, dtype=torch.int64)
+    x = torch.randn(N, F, generator=g, device=device, dtype=torch.float32)
+    names = np.frombuffer("".join(f"relation_{r:05d}" for r in range(R)).encode(), dtype=np.uint8).reshape(R, NAME_LEN)
+    utf8 = torch.from_numpy(names.copy()).to(device)[rel].reshape(-1).contiguous()
+    offsets = torch.arange(E + 1, device=device, dtype=torch.int64) * NAME_LEN
+    return x, edge_index, rel, utf8, offsets
+
+
+def build_model(w, device, precision):
+    from graph_hypernetwork_forge import HyperGNN
+    torch.manual_seed(0)
+    return HyperGNN(w["T"], w["F"], w["d"], w["L"], precision=precision).eval().to(device)
+
+
+def algorithmic_bytes(w, E, N_local, N):
+    d, R = w["d"], w["R"]
+    contraction = E * (4 * d + 8) + N_local * 4 * d + R * (2 * d * d + d) * 4   # gathers + ids + h[dst] once + weights
+    layer = contraction + N_local * 4 * d + 4 * (N_local + 1)                   # + write h', read rowptr/in-degree
+    return contraction, layer
+
+
+def cpu_port_forward(w, sample_edges, seed=0, threads=None):
+    """The oracle (numpy port of the reference algorithm) on the first `sample_edges` edges of the workload."""
+    from oracle import hypergnn_oracle as O
+    src, dst, rel, names, feats = O.synthetic_kg(w["N"], sample_edges, w["R"], w["F"], seed=seed)
+    texts = [names[r] for r in rel]
+    torch.manual_seed(0)
+    from graph_hypernetwork_forge import HyperGNN
+    params = {k: v.numpy() for k, v in HyperGNN(w["T"], w["F"], w["d"], w["L"]).state_dict().items()}
+    ei = np.stack([src, dst])
+
+    def run():
+        t0 = time.perf_counter()
+        O.hypergnn_forward(params, feats, ei, texts, w["d"], w["L"])
+        return time.perf_counter() - t0
+    return run
+
+
+def run_reference(args, w):
+    """--impl reference: the CPU port of the reference algorithm, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    probe_edges = min(w["E"], 100_000)
+    small = dict(w, N=min(w["N"], 200_000))
+    t_probe = cpu_port_forward(small, probe_edges)()
+    # size the per-step sample so that (warmup + steps) steps finish in ~2 minutes
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    node_cost = t_probe * 0.5 * (w["N"] / small["N"])          # input projection + LayerNorm scale with N
+    edge_rate = probe_edges / max(t_probe * 0.5, 1e-6)
+    sample = int(max(50_000, min(w["E"], (budget - node_cost) * edge_rate))) if budget > node_cost else 50_000
+    run = cpu_port_forward(w, sample)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    ms = 1e3 * sum(times) / len(times)
+    value = sample * w["L"] / (ms / 1e3)
+    line = {"impl": "reference", "metric": "hypergnn_fwd_edges_per_sec_per_layer", "value": value,
+            "unit": "edges/s/layer", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{w['name']} N={w['N']} E={w['E']} R={w['R']} d={w['d']} L={w['L']} T={w['T']}",
+                       "sample": f"first {sample} edges, all {w['N']} nodes, per step"},
+            "cpu_baseline": {"value": value, "unit": "edges/s/layer", "cores": cores, "kind": "port",
+                             "sample": f"{sample} edges x {w['L']} layers per step, numpy oracle"},
+            "e2e": {"value": value, "unit": "edges/s/layer", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink N and E (debugging only; not a bench number)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.scale != 1.0:
+        w["N"], w["E"] = max(64, int(w["N"] * args.scale)), max(64, int(w["E"] * args.scale))
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    from graph_hypernetwork_forge import _native
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    precision = args.precision if w["d"] in (32, 64, 128) else "fp32"
+    model = build_model(w, device, precision)
+    x, edge_index, _rel, utf8, offsets = make_device_inputs(w, device)
+    N, E, L, d = w["N"], w["E"], w["L"], w["d"]
+
+    if world == 1:
+        def step():
+            prepared = model.prepare_packed(edge_index, utf8, offsets, N)
+            return model.forward_prepared(x, prepared)
+        n_local = N
+    else:
+        from graph_hypernetwork_forge.distributed import ShardedForward
+        sharded = ShardedForward(model, N, dist.group.WORLD)
+        n_local = sharded.hi - sharded.lo
+
+        def step():
+            return sharded.forward_packed(x, edge_index, utf8, offsets)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    _native.profile_enable(True)
+    _native.profile_read()
+    _native.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = _native.launch_count()
+    prof, n_layers_timed = _native.profile_read()
+    _native.profile_enable(False)
+    if dist is not None:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = E * L / (ms / 1e3)
+
+    hbm_peak, peak_src = peaks()
+    local_edges = E if world == 1 else sharded.num_kept
+    b_contr, b_layer = algorithmic_bytes(w, local_edges, n_local, N)
+    t_contr = prof["contraction_ms"] / max(n_layers_timed, 1)
+    t_layer = (prof["contraction_ms"] + prof["epilogue_ms"] + prof["prep_ms"]) / max(n_layers_timed, 1)
+    achieved = b_contr / (t_contr * 1e-3) / 1e9 if t_contr > 0 else 0.0
+    traffic = None
+    try:  # per-launch DRAM bytes of the contraction kernel from the committed ncu capture, when present
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{args.workload}:{precision}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "mp_umma_kernel<128>" if precision == "tf32" else "mp_fp32_kernel",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_contr,
+                "ms_per_launch": t_contr,
+                "layer": {"algorithmic_bytes": b_layer, "ms": t_layer,
+                          "achieved": b_layer / (t_layer * 1e-3) / 1e9 if t_layer > 0 else 0.0,
+                          "frac": (b_layer / (t_layer * 1e-3) / 1e9) / hbm_peak if t_layer > 0 else 0.0}}
+
+    # ---- end to end through the C ABI with host buffers (rank 0 of a 1-GPU run)
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        from graph_hypernetwork_forge import _native as nat
+        hx = x.cpu().pin_memory()
+        hei = edge_index.cpu().pin_memory()
+        hutf8 = utf8.cpu().pin_memory()
+        hoff = offsets.cpu().pin_memory()
+        hout = torch.empty(N, d, dtype=torch.float32).pin_memory()
+        desc = nat.ModelDesc(w["T"], w["F"], d, L, 32, max(64, 2 * w["T"]), 2, nat.precision_code(precision), 1e-5)
+        params = model.flat_parameters()
+        del out
+        for _ in range(2):
+            nat.forward_host(desc, params, hx, hei, hutf8, hoff, hout, device)
+        k = max(1, min(args.steps, 3))
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            nat.forward_host(desc, params, hx, hei, hutf8, hoff, hout, device)
+        torch.cuda.synchronize(device)
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / k
+        h2d = hx.numel() * 4 + hei.numel() * 8 + hutf8.numel() + hoff.numel() * 8
+        e2e = {"value": E * L / (e2e_ms / 1e3), "unit": "edges/s/layer", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(hout.numel() * 4),
+               "api": "ghf_hypergnn_forward_host (C ABI, pinned host buffers)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = min(E, 400_000)
+        run = cpu_port_forward(w, sample)
+        run()
+        t = min(run() for _ in range(2))
+        cpu = {"value": sample * L / t, "unit": "edges/s/layer", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {sample} edges of the workload, all {N} nodes, {L} layers (numpy oracle, best of 2)"}
+
+    if rank == 0:
+        line = {"metric": "hypergnn_fwd_edges_per_sec_per_layer", "value": value, "unit": "edges/s/layer",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": precision,
+                "data": "synthetic",
+                "config": {"workload": f"{w['name']} N={N} E={E} R={w['R']} d={d} L={L} T={w['T']} F={w['F']}",
+                           "step": "dedup + text encoder + input projection + graph build + L layers",
+                           "l2": "inputs larger than L2 (h 1.28 GB, edges 0.26 GB); no explicit flush",
+                           "parallelism": "single GPU" if world == 1 else f"dst-range x{world} + all-gather(h) per layer"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

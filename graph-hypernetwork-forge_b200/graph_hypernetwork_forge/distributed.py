@@ -1,0 +1,89 @@
+"""Multi-GPU forward: 1-D destination-range partition + one all-gather of h per layer.
+
+The reference is single-process; this is the scaling design BASELINE.json's
+north_star prescribes.  One process per GPU.  Rank k owns destination rows [lo_k, hi_k): it keeps
+every edge whose destination falls in that range (sources are arbitrary, so each rank holds all
+of h), runs the message-passing layer for its rows, writes them into its slice of the next h and
+all-gathers the slices (NCCL over NVLink; gloo in the CPU tests of the host logic).  Generated
+relation weights are replicated: every rank runs the text encoder and the generators itself.
+
+`plan_partition` is pure host logic (unit-tested on CPU with gloo, world_size 2).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def plan_partition(num_nodes: int, world_size: int) -> Tuple[int, List[Tuple[int, int]]]:
+    """Equal destination ranges, padded so every rank contributes the same number of rows to the
+    all-gather.  -> (rows_per_rank, [(lo, hi)] * world_size); hi - lo may be < rows_per_rank (even 0)
+    on trailing ranks."""
+    if world_size < 1 or num_nodes < 0:
+        raise ValueError("world_size must be >= 1 and num_nodes >= 0")
+    rows = -(-num_nodes // world_size) if num_nodes else 0
+    ranges = []
+    for r in range(world_size):
+        lo = min(r * rows, num_nodes)
+        ranges.append((lo, min(lo + rows, num_nodes)))
+    return rows, ranges
+
+
+def gather_rows(buf: torch.Tensor, rows: int, rank: int, group) -> None:
+    """In-place all-gather: rank r has filled buf[r*rows:(r+1)*rows]; afterwards every rank has all of buf."""
+    dist.all_gather_into_tensor(buf, buf[rank * rows:(rank + 1) * rows], group=group)
+
+
+class ShardedForward:
+    """HyperGNN forward over a destination-partitioned graph (one instance per rank)."""
+
+    def __init__(self, model, num_nodes: int, group=None):
+        self.model, self.group = model, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.num_nodes = num_nodes
+        self.rows, ranges = plan_partition(num_nodes, self.world)
+        self.lo, self.hi = ranges[self.rank]
+        self.num_kept = 0
+        self._bufs: Optional[List[torch.Tensor]] = None
+
+    def _buffers(self, device, d):
+        if self._bufs is None:
+            shape = (self.rows * self.world, d)
+            self._bufs = [torch.zeros(shape, dtype=torch.float32, device=device) for _ in range(2)]
+        return self._bufs
+
+    def forward_packed(self, node_features, edge_index, utf8, offsets) -> torch.Tensor:
+        prepared = self.model.prepare_packed(edge_index, utf8, offsets, self.num_nodes, dst_range=(self.lo, self.hi))
+        return self.forward_prepared(node_features, prepared)
+
+    def forward(self, node_features, edge_index, edge_texts) -> torch.Tensor:
+        prepared = self.model.prepare(edge_index, edge_texts, self.num_nodes, dst_range=(self.lo, self.hi))
+        return self.forward_prepared(node_features, prepared)
+
+    def forward_prepared(self, node_features, prepared) -> torch.Tensor:
+        """-> [num_nodes, hidden] on every rank (the last layer's slices are gathered as well)."""
+        from . import _native
+        m = self.model
+        graph, packed = prepared.graph, prepared.packed
+        self.num_kept = graph.num_kept
+        N, d = self.num_nodes, m.hidden_dim
+        prec = m._precision_code()
+        cur, nxt = self._buffers(node_features.device, d)
+        with torch.no_grad():
+            # every rank projects all nodes (h is needed in full as the gather source)
+            cur[:N] = _native.linear(node_features, m.input_proj.weight, m.input_proj.bias, relu=True)
+            text_embs = m.text_encoder.encode_packed(packed)
+            for l in range(m.num_layers):
+                w = m._generate(l, text_embs, packed.num_unique)
+                ln = m.layer_norms[l]
+                out = nxt[self.lo:self.hi] if self.hi > self.lo else None
+                if out is not None:
+                    graph.mp_layer(cur[:N], w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
+                                   out=out)
+                gather_rows(nxt, self.rows, self.rank, self.group)
+                cur, nxt = nxt, cur
+        self._bufs = [cur, nxt]
+        return cur[:N]

@@ -37,11 +37,18 @@ def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
 class PackedTexts:
     """Relation strings on the device: bytes, offsets, per-edge relation ids, distinct-string index."""
 
-    def __init__(self, texts: List[str], device: torch.device):
-        data, offsets, edge_map = _text.pack_texts(texts)
-        self.num_edges = len(texts)
-        self.utf8 = _to_device(data, device) if data.size else torch.zeros(1, dtype=torch.uint8, device=device)
-        self.offsets = _to_device(offsets, device)
+    def __init__(self, texts: Optional[List[str]], device: torch.device, utf8: Optional[torch.Tensor] = None,
+                 offsets: Optional[torch.Tensor] = None):
+        if texts is None:   # already packed on the device (UTF-8 bytes + int64 offsets[E+1])
+            if utf8.dtype != torch.uint8 or offsets.dtype != torch.int64:
+                raise RuntimeError("packed texts must be uint8 bytes and int64 offsets")
+            self.num_edges = offsets.numel() - 1
+            self.utf8, self.offsets, edge_map = utf8.contiguous(), offsets.contiguous(), None
+        else:
+            data, offs, edge_map = _text.pack_texts(texts)
+            self.num_edges = len(texts)
+            self.utf8 = _to_device(data, device) if data.size else torch.zeros(1, dtype=torch.uint8, device=device)
+            self.offsets = _to_device(offs, device)
         ids, first = _native.dedup_texts(self.utf8, self.offsets)   # over the packed strings
         self.first = first                                          # packed-string index of each distinct text
         self.num_unique = int(first.numel())
@@ -137,7 +144,19 @@ class HyperGNN(nn.Module):
             raise ValueError(
                 f"edge_index has {edge_index.size(1)} edges but edge_texts has {len(edge_texts)} entries")
         device = _native.require_cuda(edge_index, self.input_proj.weight)
-        packed = PackedTexts(edge_texts, device)
+        return self._prepare(edge_index, PackedTexts(edge_texts, device), num_nodes, dst_range)
+
+    def prepare_packed(self, edge_index: torch.Tensor, utf8: torch.Tensor, offsets: torch.Tensor, num_nodes: int,
+                       dst_range=None) -> PreparedGraph:
+        """`prepare` for relation strings that are already packed on the device (UTF-8 + offsets[E+1]);
+        the way in for edge lists too large for a Python list of str."""
+        if edge_index.size(1) != offsets.numel() - 1:
+            raise ValueError(
+                f"edge_index has {edge_index.size(1)} edges but edge_texts has {offsets.numel() - 1} entries")
+        device = _native.require_cuda(edge_index, utf8, offsets, self.input_proj.weight)
+        return self._prepare(edge_index, PackedTexts(None, device, utf8, offsets), num_nodes, dst_range)
+
+    def _prepare(self, edge_index, packed, num_nodes, dst_range) -> PreparedGraph:
         lo, hi = (0, num_nodes) if dst_range is None else dst_range
         graph = _native.Graph(edge_index, packed.rel_ids, num_nodes, max(packed.num_unique, 1),
                               self.hidden_dim, dst_lo=lo, dst_hi=hi,
