@@ -21,4 +21,5 @@ struct ghf_graph {
   int32_t* unit_count = nullptr;   // [units] edges in the unit (<= unit_edges)
   int32_t* unit_rel = nullptr;     // [units] the one relation all its edges share
   int64_t bytes = 0;
+  mutable void* stream = nullptr;  // stream the tables were allocated on / last used on (freed there)
 };

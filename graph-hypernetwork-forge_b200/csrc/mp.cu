@@ -218,7 +218,7 @@ extern "C" int ghf_profile_read(double ms[3], int64_t* launches) {
 
 extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim, int precision) {
   if (!g) return -1;
-  int64_t bytes = align_up(g->num_local * (int64_t)hidden_dim * 4, 256);
+  int64_t bytes = 256 /* work counter */ + align_up(g->num_local * (int64_t)hidden_dim * 4, 256);
   if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim);
   return bytes + 256;
 }
@@ -232,8 +232,11 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
   GHF_REQUIRE(precision == GHF_PREC_FP32 || precision == GHF_PREC_TF32, "ghf_mp_layer: precision=%d", precision);
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
+  g->stream = stream_;
   if (nl == 0) return 0;
-  float* acc = reinterpret_cast<float*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
+  // workspace: [work counter, 256 B][accumulator rows][operand images (tf32 path)]
+  int* counter = reinterpret_cast<int*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
+  float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) + 256);
   const int64_t acc_bytes = align_up(nl * (int64_t)d * 4, 256);
   ProfRec rec{};
   const bool prof = g_prof_on;
@@ -241,7 +244,7 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
     GHF_CUDA(cudaEventRecord(rec.e[0], stream));
   }
-  GHF_CUDA(cudaMemsetAsync(acc, 0, nl * (size_t)d * 4, stream));
+  GHF_CUDA(cudaMemsetAsync(counter, 0, 256 + nl * (size_t)d * 4, stream));
   if (precision == GHF_PREC_TF32 && g->num_units > 0) {
     GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
     if (int rc = mp_umma_pack(g, d_W_msg, d_W_self, reinterpret_cast<char*>(acc) + acc_bytes, stream)) return rc;
@@ -250,7 +253,7 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
   if (g->num_units > 0) {
     if (precision == GHF_PREC_TF32) {
       void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
-      if (int rc = mp_umma_launch(g, d_h, d_bias, acc, pack, stream)) return rc;
+      if (int rc = mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream)) return rc;
     } else {
       int rc;
       if (d <= 32) rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);

@@ -15,7 +15,8 @@ int64_t mp_umma_pack_bytes(int num_rel, int hidden_dim);
 int mp_umma_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch,
                  cudaStream_t stream);
 // acc[dst_local, :] += sum over edges of [h_src | h_dst] @ [W_msg; W_self][rel] + bias[rel]
+// `unit_counter` is one zeroed int in device memory (the shared work counter of the persistent CTAs)
 int mp_umma_launch(const ghf_graph* g, const float* h, const float* bias, float* acc, const void* pack_scratch,
-                   cudaStream_t stream);
+                   int* unit_counter, cudaStream_t stream);
 
 }  // namespace ghf

@@ -15,6 +15,8 @@
 //   warps 4-7  A producers (row gather, cp.async -> full[stage])
 //   warp  8    MMA issuer (lane 0) + TMEM allocator
 //   warp  9    B loader   (lane 0, cp.async.bulk -> b_full)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mp.cuh"
 #include "umma.cuh"
@@ -23,6 +25,13 @@ namespace ghf {
 namespace {
 
 using namespace ptx;
+
+// L2 residency flags (GHF_MP_FLAGS): the destination super-block (h[dst] rows + accumulator rows) should
+// stay in L2 while the source rows stream through once.
+constexpr uint32_t kFlagSrcEvictFirst = 1u, kFlagDstEvictLast = 2u, kFlagRedEvictLast = 4u;
+constexpr uint32_t kFlagStaticSchedule = 8u;
+constexpr uint32_t kFlagWeightsEvictLast = 16u;  // keep the operand images resident across super-block phases  // units round-robin by CTA instead of the shared counter (experiments)
+constexpr uint32_t kDefaultFlags = kFlagSrcEvictFirst | kFlagDstEvictLast | kFlagRedEvictLast;
 
 template <int D>
 struct Cfg {
@@ -36,7 +45,8 @@ struct Cfg {
   static constexpr int kStaging = 4 * 32 * 128;       // 4 epilogue warps x (32 rows x 32 fp32)
   static constexpr int kStages = D == 128 ? 5 : 8;
   static constexpr int kTmemCols = 2 * D;             // two accumulators; 64 / 128 / 256 (powers of two)
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kQueue = 4;                    // unit-id ring between the scheduler and the other roles
   static constexpr int kSmem = 1024 + kBBytes + kStages * kAStage + kStaging + kBarBytes;
   static constexpr int kThreads = 320;
 };
@@ -66,7 +76,7 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
                const int32_t* __restrict__ unit_rel, int64_t num_units,
                const int32_t* __restrict__ src_sorted, const int32_t* __restrict__ dst_sorted,
                const float* __restrict__ h, int64_t dst_lo, const uint8_t* __restrict__ wpack,
-               const float* __restrict__ bias, float* __restrict__ acc) {
+               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter, uint32_t flags) {
   using C = Cfg<D>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -82,9 +92,24 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
   auto acc_empty = [&](int a) { return b_empty + 24u + 8u * a; };
   const uint32_t tmem_slot = b_empty + 40u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // unit queue: the scheduler (warp 9) publishes unit ids; epilogue warps, producer warps and the MMA thread
+  // each consume every entry (9 arrivals free a slot)
+  const uint32_t q_full0 = b_empty + 48u;
+  const uint32_t q_empty0 = q_full0 + 8u * C::kQueue;
+  const uint32_t q_slots = q_empty0 + 8u * C::kQueue;
+  volatile int32_t* q_slot_ptr = reinterpret_cast<volatile int32_t*>(smem_raw + (q_slots - raw));
+  int q_idx = 0;
+  uint32_t q_phase = 0;
+  auto next_unit = [&](bool whole_warp) -> int {
+    mbar_wait(q_full0 + 8u * q_idx, q_phase);
+    const int u = q_slot_ptr[q_idx];
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) mbar_arrive(q_empty0 + 8u * q_idx);
+    if (++q_idx == C::kQueue) { q_idx = 0; q_phase ^= 1u; }
+    return u;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -96,6 +121,10 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full(a), 1);     // tcgen05.commit
       mbar_init(acc_empty(a), 128);  // every epilogue thread
+    }
+    for (int q = 0; q < C::kQueue; ++q) {
+      mbar_init(q_full0 + 8u * q, 1);
+      mbar_init(q_empty0 + 8u * q, 9);
     }
     mbar_fence_init();
   }
@@ -109,8 +138,11 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
     // ------------------------------------------------------------------ epilogue
     float4* stg = reinterpret_cast<float4*>(smem_raw + (sStg - raw) + warp * 4096);
     const int cj = lane & 7;
+    // one code path, policy chosen at run time (a branch between hinted / unhinted forms in the inner
+    // loops cost 35% of the kernel when tried)
+    const uint64_t pol_red = (flags & kFlagRedEvictLast) ? policy_evict_last() : policy_evict_normal();
     uint32_t it = 0;
-    for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (int u = next_unit(true); u >= 0; u = next_unit(true)) {
       const int start = unit_start[u], count = unit_count[u];
       const int64_t rel = unit_rel[u];
       float4 b4[D / 32];
@@ -142,7 +174,8 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
             float4 v = stg[rr * 8 + (cj ^ (rr & 7))];
             if (dsti >= 0) {
               v.x += b4[cc].x; v.y += b4[cc].y; v.z += b4[cc].z; v.w += b4[cc].w;
-              atomicAdd(reinterpret_cast<float4*>(acc + (int64_t)dsti * D + cc * 32 + 4 * cj), v);
+              float* p = acc + (int64_t)dsti * D + cc * 32 + 4 * cj;
+              red_add_v4_hint(p, v, pol_red);
             }
           }
           __syncwarp();
@@ -155,9 +188,11 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
     // ------------------------------------------------------------------ A producers
     const int pw = warp - 4;
     const int cj = lane & 7;
+    const uint64_t pol_src = (flags & kFlagSrcEvictFirst) ? policy_evict_first() : policy_evict_normal();
+    const uint64_t pol_dst = (flags & kFlagDstEvictLast) ? policy_evict_last() : policy_evict_normal();
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (int u = next_unit(true); u >= 0; u = next_unit(true)) {
       const int start = unit_start[u], count = unit_count[u];
       for (int t0 = 0; t0 < count; t0 += C::kTileM) {
         const int rows = min(C::kTileM, count - t0);
@@ -168,15 +203,18 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
 #pragma unroll 1
         for (int c = 0; c < C::kChunks; ++c) {
           mbar_wait(empty(stage), phase ^ 1u);
-          const int64_t mine = c < C::kHalf ? my_src : my_dst;
-          const int col = (c < C::kHalf ? c : c - C::kHalf) * 32 + 4 * cj;
+          const bool from_src = c < C::kHalf;
+          const int64_t mine = from_src ? my_src : my_dst;
+          const int col = (from_src ? c : c - C::kHalf) * 32 + 4 * cj;
           const uint32_t dst_base = sA + stage * C::kAStage;
+          const uint64_t pol = from_src ? pol_src : pol_dst;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + (lane >> 3);
             const int64_t idx = __shfl_sync(0xffffffffu, mine, rr);
             const int row = pw * 32 + rr;
-            if (idx >= 0) cp_async_16(dst_base + row * 128 + ((cj ^ (row & 7)) << 4), h + idx * D + col);
+            const uint32_t to = dst_base + row * 128 + ((cj ^ (row & 7)) << 4);
+            if (idx >= 0) cp_async_16_hint(to, h + idx * D + col, pol);
           }
           cp_async_arrive_noinc(full(stage));
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -189,7 +227,7 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
       constexpr uint32_t idesc = umma_idesc_tf32(C::kTileM, D);
       int stage = 0;
       uint32_t phase = 0, bphase = 0, it = 0;
-      for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+      for (int u = next_unit(false); u >= 0; u = next_unit(false)) {
         const int count = unit_count[u];
         mbar_wait(b_full, bphase);
         tc_fence_after();
@@ -217,10 +255,22 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
       }
     }
   } else {
-    // ------------------------------------------------------------------ B loader
+    // ------------------------------------------------------------------ unit scheduler + B loader
     if (lane == 0) {
-      uint32_t bphase = 0;
-      for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+      uint32_t bphase = 0, sphase = 0;
+      int sq = 0;
+      const uint64_t pol_w = (flags & kFlagWeightsEvictLast) ? policy_evict_last() : policy_evict_normal();
+      int64_t static_next = blockIdx.x;
+      for (;;) {
+        mbar_wait(q_empty0 + 8u * sq, sphase ^ 1u);
+        int64_t u;
+        if (flags & kFlagStaticSchedule) { u = static_next; static_next += gridDim.x; }
+        else u = atomicAdd(unit_counter, 1);
+        const bool done = u >= num_units;
+        q_slot_ptr[sq] = done ? -1 : (int)u;
+        mbar_arrive(q_full0 + 8u * sq);  // release: the slot write is visible to the waiters
+        if (++sq == C::kQueue) { sq = 0; sphase ^= 1u; }
+        if (done) break;
         const int64_t rel = unit_rel[u];
         mbar_wait(b_empty, bphase ^ 1u);
         mbar_arrive_expect_tx(b_full, C::kBBytes);
@@ -229,7 +279,7 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
 #pragma unroll 1
         for (int off = 0; off < C::kBBytes; off += kPiece) {
           const int bytes = min(kPiece, C::kBBytes - off);
-          bulk_g2s(sB + off, src + off, bytes, b_full);
+          bulk_g2s_hint(sB + off, src + off, bytes, b_full, pol_w);
         }
         bphase ^= 1u;
       }
@@ -243,7 +293,7 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
 
 template <int D>
 int launch(const ghf_graph* g, const float* h, const uint8_t* wpack, const float* bias, float* acc,
-           cudaStream_t stream) {
+           int* unit_counter, cudaStream_t stream) {
   using C = Cfg<D>;
   static bool configured = false;
   if (!configured) {
@@ -251,9 +301,11 @@ int launch(const ghf_graph* g, const float* h, const uint8_t* wpack, const float
     configured = true;
   }
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
+  const char* env = getenv("GHF_MP_FLAGS");
+  const uint32_t flags = env ? (uint32_t)atoi(env) : kDefaultFlags;
   mp_umma_kernel<D><<<(unsigned)grid, C::kThreads, C::kSmem, stream>>>(
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo, wpack,
-      bias, acc);
+      bias, acc, unit_counter, flags);
   GHF_LAUNCH_CHECK();
   return 0;
 }
@@ -276,7 +328,7 @@ int mp_umma_pack(const ghf_graph* g, const float* W_msg, const float* W_self, vo
 }
 
 int mp_umma_launch(const ghf_graph* g, const float* h, const float* bias, float* acc, const void* pack_scratch,
-                   cudaStream_t stream) {
+                   int* unit_counter, cudaStream_t stream) {
   const int d = g->hidden_dim;
   GHF_REQUIRE(g->unit_edges % 128 == 0, "mp_umma: unit_edges=%d must be a multiple of 128", g->unit_edges);
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(acc) |
@@ -284,9 +336,9 @@ int mp_umma_launch(const ghf_graph* g, const float* h, const float* bias, float*
               "mp_umma: h / acc / bias / scratch must be 16-byte aligned");
   const uint8_t* pack = reinterpret_cast<const uint8_t*>(pack_scratch);
   switch (d) {
-    case 32: return launch<32>(g, h, pack, bias, acc, stream);
-    case 64: return launch<64>(g, h, pack, bias, acc, stream);
-    case 128: return launch<128>(g, h, pack, bias, acc, stream);
+    case 32: return launch<32>(g, h, pack, bias, acc, unit_counter, stream);
+    case 64: return launch<64>(g, h, pack, bias, acc, unit_counter, stream);
+    case 128: return launch<128>(g, h, pack, bias, acc, unit_counter, stream);
   }
   return fail("mp_umma: unsupported hidden_dim %d", d);
 }

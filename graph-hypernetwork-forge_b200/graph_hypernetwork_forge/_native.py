@@ -17,7 +17,8 @@ PREC_FP32 = 0
 PREC_TF32 = 1
 _PREC = {"fp32": PREC_FP32, "tf32": PREC_TF32}
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")
+_LIB_PATH = os.environ.get("GHF_LIB") or os.path.join(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")
 _lib = None
 
 

@@ -1,0 +1,60 @@
+"""Time the message-passing layer alone on the bench workload for several (sb_nodes, unit_edges, flags).
+    python tools/mp_sweep.py [--workload c3] "sb,unit,flags" ...      (GPU box only)
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "graph-hypernetwork-forge_b200")]
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from graph_hypernetwork_forge import _native  # noqa: E402
+
+args = sys.argv[1:]
+wl = "c3"
+if args and args[0] == "--workload":
+    wl, args = args[1], args[2:]
+w = bench.WORKLOADS[wl]
+dev = torch.device("cuda:0")
+model = bench.build_model(w, dev, "tf32")
+x, ei, rel, utf8, offsets = bench.make_device_inputs(w, dev)
+h = _native.linear(x, model.input_proj.weight, model.input_proj.bias, relu=True)
+# calibration: device copy bandwidth on this box (read + write bytes), and clocks
+import subprocess
+a = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+b = torch.empty_like(a)
+for _ in range(3):
+    b.copy_(a)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    b.copy_(a)
+e1.record()
+torch.cuda.synchronize()
+print(f"copy bandwidth {10 * 2 * a.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9:.0f} GB/s", flush=True)
+del a, b
+print(subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu,serial",
+                      "--format=csv,noheader"], capture_output=True, text=True).stdout.strip(), flush=True)
+packed = None
+for spec in args or ["0,0,7"]:
+    sb, unit, flags = (int(v) for v in spec.split(","))
+    os.environ["GHF_SB_NODES"], os.environ["GHF_UNIT_EDGES"], os.environ["GHF_MP_FLAGS"] = str(sb), str(unit), str(flags)
+    prepared = model.prepare_packed(ei, utf8, offsets, w["N"])
+    g = prepared.graph
+    text = model.text_encoder.encode_packed(prepared.packed)
+    wts = model.weight_generators[0](text)
+    ln = model.layer_norms[0]
+    for _ in range(2):
+        g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias, 1e-5, _native.PREC_TF32)
+    torch.cuda.synchronize()
+    _native.profile_enable(True)
+    _native.profile_read()
+    for _ in range(5):
+        g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias, 1e-5, _native.PREC_TF32)
+    prof, n = _native.profile_read()
+    _native.profile_enable(False)
+    print(f"sb={g.sb_nodes:6d} unit={g.unit_edges:5d} flags={flags} units={g.num_units:7d} "
+          f"contraction {prof['contraction_ms']/n:.3f} ms  epilogue {prof['epilogue_ms']/n:.3f}  prep {prof['prep_ms']/n:.3f}",
+          flush=True)
+    del prepared, g
