@@ -65,12 +65,16 @@ __global__ void unit_flag_kernel(const int32_t* __restrict__ gstart, int64_t kep
 
 __global__ void unit_fill_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ uidx,
                                  const uint64_t* __restrict__ keys, int64_t kept, int64_t sb, int64_t R,
-                                 int32_t* __restrict__ unit_start, int32_t* __restrict__ unit_rel) {
+                                 int32_t* __restrict__ unit_start, int32_t* __restrict__ unit_rel,
+                                 int32_t* __restrict__ unit_phase, int32_t* __restrict__ phase_units) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= kept || !flag[i]) return;
   const int32_t u = uidx[i];
+  const uint64_t g = keys[i] / sb;
   unit_start[u] = (int32_t)i;
-  unit_rel[u] = (int32_t)((keys[i] / sb) % R);
+  unit_rel[u] = (int32_t)(g % R);
+  unit_phase[u] = (int32_t)(g / R);
+  atomicAdd(&phase_units[g / R], 1);
 }
 
 __global__ void unit_count_kernel(const int32_t* __restrict__ unit_start, int64_t units, int64_t kept,
@@ -103,7 +107,7 @@ extern "C" void ghf_graph_free(ghf_graph* g) {
   if (!g) return;
   cudaStream_t s = (cudaStream_t)g->stream;  // the stream that last used the tables
   void* ptrs[] = {g->src_sorted, g->dst_sorted, g->perm, g->indeg, g->rowptr, g->unit_start, g->unit_count,
-                  g->unit_rel};
+                  g->unit_rel, g->unit_phase, g->phase_units};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, s);
   delete g;
@@ -117,8 +121,11 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const int
   const uint64_t invalid_key = (uint64_t)n_sb * R * sb;  // sorts after every valid key
   const int end_bit = bits_for(invalid_key);
 
+  g->num_phases = n_sb;
   GHF_CUDA(dmalloc(&g->indeg, nl, g));
   GHF_CUDA(dmalloc(&g->rowptr, nl + 1, g));
+  GHF_CUDA(dmalloc(&g->phase_units, n_sb, g));
+  GHF_CUDA(cudaMemsetAsync(g->phase_units, 0, (size_t)n_sb * sizeof(int32_t), stream));
   GHF_CUDA(cudaMemsetAsync(g->indeg, 0, (size_t)(nl > 0 ? nl : 1) * sizeof(int32_t), stream));
 
   TempBuf keys_a, keys_b, vals_a, vals_b, tmp;
@@ -175,6 +182,7 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const int
     GHF_CUDA(dmalloc(&g->unit_start, 1, g));
     GHF_CUDA(dmalloc(&g->unit_count, 1, g));
     GHF_CUDA(dmalloc(&g->unit_rel, 1, g));
+    GHF_CUDA(dmalloc(&g->unit_phase, 1, g));
     return 0;
   }
   TempBuf gstart, flag, uidx, total;
@@ -213,8 +221,9 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const int
   GHF_CUDA(dmalloc(&g->unit_start, g->num_units, g));
   GHF_CUDA(dmalloc(&g->unit_count, g->num_units, g));
   GHF_CUDA(dmalloc(&g->unit_rel, g->num_units, g));
+  GHF_CUDA(dmalloc(&g->unit_phase, g->num_units, g));
   unit_fill_kernel<<<kblocks, threads, 0, stream>>>(flag.as<int32_t>(), uidx.as<int32_t>(), kbuf.Current(), kept, sb,
-                                                    R, g->unit_start, g->unit_rel);
+                                                    R, g->unit_start, g->unit_rel, g->unit_phase, g->phase_units);
   GHF_LAUNCH_CHECK();
   unit_count_kernel<<<(unsigned)cdiv(g->num_units, threads), threads, 0, stream>>>(g->unit_start, g->num_units, kept,
                                                                                  g->unit_count);

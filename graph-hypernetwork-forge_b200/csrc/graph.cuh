@@ -20,6 +20,9 @@ struct ghf_graph {
   int32_t* unit_start = nullptr;   // [units] first sorted position of the unit
   int32_t* unit_count = nullptr;   // [units] edges in the unit (<= unit_edges)
   int32_t* unit_rel = nullptr;     // [units] the one relation all its edges share
+  int32_t* unit_phase = nullptr;   // [units] super-block ("phase") of the unit's destinations
+  int32_t* phase_units = nullptr;  // [phases] number of units per super-block
+  int64_t num_phases = 0;          // ceil(num_local / sb_nodes), at least 1
   int64_t bytes = 0;
   mutable void* stream = nullptr;  // stream the tables were allocated on / last used on (freed there)
 };

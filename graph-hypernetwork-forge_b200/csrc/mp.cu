@@ -8,6 +8,7 @@
 // linearity, which is why it rides along as the second half of K.  Two contraction engines:
 //   GHF_PREC_FP32  this file: CUDA-core FFMA tiles, exact fp32;
 //   GHF_PREC_TF32  mp_umma.cu: tcgen05 kind::tf32 with TMEM accumulators.
+#include <cstdlib>
 #include <vector>
 
 #include "ffma_gemm.cuh"
@@ -187,6 +188,11 @@ int launch_mp_fp32(const ghf_graph* g, const float* h, const float* W_msg, const
 
 using namespace ghf;
 
+static bool mp_fused_enabled() {
+  const char* env = getenv("GHF_MP_FUSED");
+  return !(env && env[0] == '0');
+}
+
 // ---- optional per-kernel timing (bench.py roofline): event triples per layer call
 namespace {
 struct ProfRec { cudaEvent_t e[4]; };
@@ -218,8 +224,10 @@ extern "C" int ghf_profile_read(double ms[3], int64_t* launches) {
 
 extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim, int precision) {
   if (!g) return -1;
-  int64_t bytes = 256 /* work counter */ + align_up(g->num_local * (int64_t)hidden_dim * 4, 256);
-  if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim);
+  const bool fused = precision == GHF_PREC_TF32 && mp_fused_enabled();
+  // unfused paths accumulate in scratch; the fused tf32 path accumulates in the output rows
+  int64_t bytes = 256 /* work counter */ + (fused ? 0 : align_up(g->num_local * (int64_t)hidden_dim * 4, 256));
+  if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim) + mp_umma_sync_bytes(g);
   return bytes + 256;
 }
 
@@ -234,6 +242,30 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
   const int64_t nl = g->num_local;
   g->stream = stream_;
   if (nl == 0) return 0;
+  if (precision == GHF_PREC_TF32 && mp_fused_enabled()) {
+    // workspace: [sync words][operand images]; one kernel does the whole layer in place
+    GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
+    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
+    void* sync = base;
+    void* pack = base + mp_umma_sync_bytes(g);
+    ProfRec rec{};
+    const bool prof = g_prof_on;
+    if (prof) {
+      for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
+      GHF_CUDA(cudaEventRecord(rec.e[0], stream));
+    }
+    if (g->num_units > 0)
+      if (int rc = mp_umma_pack(g, d_W_msg, d_W_self, pack, stream)) return rc;
+    if (prof) GHF_CUDA(cudaEventRecord(rec.e[1], stream));
+    if (int rc = mp_umma_launch_fused(g, d_h, d_bias, d_ln_w, d_ln_b, eps, d_out, d_upd, pack, sync, stream))
+      return rc;
+    if (prof) {
+      GHF_CUDA(cudaEventRecord(rec.e[2], stream));
+      GHF_CUDA(cudaEventRecord(rec.e[3], stream));
+      g_prof.push_back(rec);
+    }
+    return 0;
+  }
   // workspace: [work counter, 256 B][accumulator rows][operand images (tf32 path)]
   int* counter = reinterpret_cast<int*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
   float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) + 256);

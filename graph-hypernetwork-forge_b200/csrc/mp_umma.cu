@@ -16,6 +16,7 @@
 //   warp  8    MMA issuer (lane 0) + TMEM allocator
 //   warp  9    B loader   (lane 0, cp.async.bulk -> b_full)
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "mp.cuh"
@@ -70,14 +71,154 @@ __global__ void pack_weights_kernel(const float* __restrict__ W_msg, const float
   *reinterpret_cast<float*>(pack + r * ((int64_t)2 * D * D * 4) + pack_offset_bytes(D, n, k)) = to_tf32_rna(v);
 }
 
+// ---- in-place fusion of the layer epilogue -----------------------------------------------------------------
+// The output rows double as the accumulator.  `epi_ctas` CTAs (lowest block ids) do no contraction: they zero
+// the rows of super-block ("phase") p just before its units start reducing into them, and as soon as the last
+// unit of phase p has signalled they turn those rows into LayerNorm(relu(acc / max(indeg,1) + h)) in place -
+// while rows, h[dst] rows and in-degrees are still in L2.  No separate clear pass, no separate epilogue pass,
+// no accumulator round trip through HBM.
+//   zero_done[p]  : epilogue CTAs that have zeroed their share of phase p      (== epi_ctas -> units may start)
+//   units_done[p] : units of phase p whose reductions are complete            (== phase_units[p] -> epilogue)
+struct FuseArgs {
+  const int32_t* unit_phase;
+  const int32_t* phase_units;
+  int32_t* zero_done;
+  int32_t* units_done;
+  const int32_t* indeg;
+  const float* ln_w;
+  const float* ln_b;
+  float* upd;  // optional pre-residual update (parity taps)
+  float eps;
+  int64_t num_local;
+  int32_t sb_nodes, num_phases, epi_ctas;
+};
+
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until_at_least(const int32_t* p, int target) {
+  for (uint32_t spins = 0; ld_acquire(p) < target; ++spins) {
+    __nanosleep(64);
+    if (spins > (1u << 24)) __trap();
+  }
+}
+
+// V consecutive floats as one vector access (V = 1, 2, 4)
+template <int V> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+template <int V>
+__device__ __forceinline__ void vload_cg(float (&dst)[V], const float* p) {   // L2 (skips L1)
+  using T = typename VecT<V>::type;
+  const T v = __ldcg(reinterpret_cast<const T*>(p));
+  memcpy(dst, &v, sizeof(T));
+}
+template <int V>
+__device__ __forceinline__ void vload_nc(float (&dst)[V], const float* p) {   // read-only path
+  using T = typename VecT<V>::type;
+  const T v = __ldg(reinterpret_cast<const T*>(p));
+  memcpy(dst, &v, sizeof(T));
+}
+template <int V>
+__device__ __forceinline__ void vstore(float* p, const float (&src)[V]) {
+  using T = typename VecT<V>::type;
+  T v;
+  memcpy(&v, src, sizeof(T));
+  *reinterpret_cast<T*>(p) = v;
+}
+
 template <int D>
+__device__ void epilogue_cta(const FuseArgs& fa, float* __restrict__ out, const float* __restrict__ h,
+                             int64_t dst_lo) {
+  constexpr int V = D / 32;  // consecutive floats per lane: a warp covers one row with one vector access
+  constexpr int kRows = 8;   // rows in flight per warp (latency hiding: ~8 KB of loads per warp)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nslots = fa.epi_ctas * (blockDim.x >> 5);
+  const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+  float lw[V], lb[V];
+  vload_nc<V>(lw, fa.ln_w + lane * V);
+  vload_nc<V>(lb, fa.ln_b + lane * V);
+  const float zeros[V] = {};
+
+  auto zero_phase = [&](int p) {
+    const int64_t lo = (int64_t)p * fa.sb_nodes, hi = min(lo + fa.sb_nodes, fa.num_local);
+    for (int64_t r = lo + slot; r < hi; r += nslots) vstore<V>(out + r * D + lane * V, zeros);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&fa.zero_done[p], 1);
+    }
+  };
+
+  zero_phase(0);
+  if (fa.num_phases > 1) zero_phase(1);
+  for (int p = 0; p < fa.num_phases; ++p) {
+    if (threadIdx.x == 0) spin_until_at_least(&fa.units_done[p], fa.phase_units[p]);
+    __syncthreads();
+    __threadfence();
+    const int64_t lo = (int64_t)p * fa.sb_nodes, hi = min(lo + fa.sb_nodes, fa.num_local);
+    for (int64_t r0 = lo + slot; r0 < hi; r0 += (int64_t)kRows * nslots) {
+      float a[kRows][V], hv[kRows][V];
+      int deg[kRows];
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        const int64_t r = r0 + (int64_t)k * nslots;
+        if (r < hi) {
+          vload_cg<V>(a[k], out + r * D + lane * V);  // reductions live in L2, never in L1
+          vload_nc<V>(hv[k], h + (dst_lo + r) * D + lane * V);
+          deg[k] = __ldg(fa.indeg + r);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        const int64_t r = r0 + (int64_t)k * nslots;
+        if (r >= hi) break;
+        const float inv = 1.f / (float)max(deg[k], 1);
+        float x[V], u[V], sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          u[j] = a[k][j] * inv;
+          x[j] = fmaxf(u[j] + hv[k][j], 0.f);
+          sum += x[j];
+        }
+        if (fa.upd) vstore<V>(fa.upd + r * D + lane * V, u);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+        const float mean = sum / (float)D;
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) var += (x[j] - mean) * (x[j] - mean);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+        const float rstd = rsqrtf(var / (float)D + fa.eps);
+        float y[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) y[j] = (x[j] - mean) * rstd * lw[j] + lb[j];
+        vstore<V>(out + r * D + lane * V, y);
+      }
+    }
+    if (p + 2 < fa.num_phases) zero_phase(p + 2);
+  }
+}
+
+template <int D, bool FUSED>
 __global__ void __launch_bounds__(Cfg<D>::kThreads, 1)
 mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
                const int32_t* __restrict__ unit_rel, int64_t num_units,
                const int32_t* __restrict__ src_sorted, const int32_t* __restrict__ dst_sorted,
                const float* __restrict__ h, int64_t dst_lo, const uint8_t* __restrict__ wpack,
-               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter, uint32_t flags) {
+               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter, uint32_t flags,
+               const FuseArgs fa) {
   using C = Cfg<D>;
+  if constexpr (FUSED) {
+    if ((int)blockIdx.x < fa.epi_ctas) {  // epilogue CTAs: no tensor-core role, no shared-memory pipeline
+      epilogue_cta<D>(fa, acc, h, dst_lo);
+      return;
+    }
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sB = (raw + 1023u) & ~1023u;
@@ -183,6 +324,11 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
         tc_fence_before();
         mbar_arrive(acc_empty(a));
       }
+      if constexpr (FUSED) {  // this unit's reductions are complete: count it towards its phase
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 0) atomicAdd(&fa.units_done[fa.unit_phase[u]], 1);
+      }
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ A producers
@@ -261,12 +407,22 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
       int sq = 0;
       const uint64_t pol_w = (flags & kFlagWeightsEvictLast) ? policy_evict_last() : policy_evict_normal();
       int64_t static_next = blockIdx.x;
+      int ready_phase = -1;
       for (;;) {
         mbar_wait(q_empty0 + 8u * sq, sphase ^ 1u);
         int64_t u;
-        if (flags & kFlagStaticSchedule) { u = static_next; static_next += gridDim.x; }
+        if (!FUSED && (flags & kFlagStaticSchedule)) { u = static_next; static_next += gridDim.x; }
         else u = atomicAdd(unit_counter, 1);
         const bool done = u >= num_units;
+        if constexpr (FUSED) {
+          if (!done) {
+            const int p = fa.unit_phase[u];
+            if (p != ready_phase) {  // the rows this unit reduces into must have been cleared
+              spin_until_at_least(&fa.zero_done[p], fa.epi_ctas);
+              ready_phase = p;
+            }
+          }
+        }
         q_slot_ptr[sq] = done ? -1 : (int)u;
         mbar_arrive(q_full0 + 8u * sq);  // release: the slot write is visible to the waiters
         if (++sq == C::kQueue) { sq = 0; sphase ^= 1u; }
@@ -291,21 +447,49 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
   if (warp == 8) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
+uint32_t env_flags() {
+  const char* env = getenv("GHF_MP_FLAGS");
+  return env ? (uint32_t)atoi(env) : kDefaultFlags;
+}
+
 template <int D>
 int launch(const ghf_graph* g, const float* h, const uint8_t* wpack, const float* bias, float* acc,
            int* unit_counter, cudaStream_t stream) {
   using C = Cfg<D>;
   static bool configured = false;
   if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(mp_umma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_umma_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     configured = true;
   }
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
-  const char* env = getenv("GHF_MP_FLAGS");
-  const uint32_t flags = env ? (uint32_t)atoi(env) : kDefaultFlags;
-  mp_umma_kernel<D><<<(unsigned)grid, C::kThreads, C::kSmem, stream>>>(
+  mp_umma_kernel<D, false><<<(unsigned)grid, C::kThreads, C::kSmem, stream>>>(
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo, wpack,
-      bias, acc, unit_counter, flags);
+      bias, acc, unit_counter, env_flags(), FuseArgs{});
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int D>
+int launch_fused(const ghf_graph* g, const float* h, const uint8_t* wpack, const float* bias, float* out,
+                 int* unit_counter, FuseArgs fa, cudaStream_t stream) {
+  using C = Cfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    GHF_CUDA(cudaFuncSetAttribute(mp_umma_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    configured = true;
+  }
+  // every CTA must be resident at once (contraction CTAs wait on epilogue CTAs and vice versa):
+  // one CTA per SM by shared-memory size, grid <= SM count
+  const int sms = sm_count();
+  const char* env = getenv("GHF_EPI_CTAS");
+  int epi = env ? atoi(env) : 20;
+  epi = epi < 1 ? 1 : (epi > sms / 2 ? sms / 2 : epi);
+  const int64_t work = g->num_units > 0 ? g->num_units : 1;
+  const int64_t contraction = work < sms - epi ? work : sms - epi;
+  fa.epi_ctas = epi;
+  mp_umma_kernel<D, true><<<(unsigned)(epi + contraction), C::kThreads, C::kSmem, stream>>>(
+      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo, wpack,
+      bias, out, unit_counter, env_flags() & ~kFlagStaticSchedule, fa);
   GHF_LAUNCH_CHECK();
   return 0;
 }
@@ -339,6 +523,38 @@ int mp_umma_launch(const ghf_graph* g, const float* h, const float* bias, float*
     case 32: return launch<32>(g, h, pack, bias, acc, unit_counter, stream);
     case 64: return launch<64>(g, h, pack, bias, acc, unit_counter, stream);
     case 128: return launch<128>(g, h, pack, bias, acc, unit_counter, stream);
+  }
+  return fail("mp_umma: unsupported hidden_dim %d", d);
+}
+
+int64_t mp_umma_sync_bytes(const ghf_graph* g) { return align_up(256 + 2 * g->num_phases * 4, 256); }
+
+int mp_umma_launch_fused(const ghf_graph* g, const float* h, const float* bias, const float* ln_w, const float* ln_b,
+                         float eps, float* out, float* upd, const void* pack_scratch, void* sync_scratch,
+                         cudaStream_t stream) {
+  const int d = g->hidden_dim;
+  GHF_REQUIRE(g->unit_edges % 128 == 0, "mp_umma: unit_edges=%d must be a multiple of 128", g->unit_edges);
+  GHF_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
+               reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
+              "mp_umma: h / out / bias / scratch must be 16-byte aligned");
+  // sync scratch: [unit counter (256 B)][zero_done[phases]][units_done[phases]], all zero at launch
+  GHF_CUDA(cudaMemsetAsync(sync_scratch, 0, mp_umma_sync_bytes(g), stream));
+  int* counter = reinterpret_cast<int*>(sync_scratch);
+  FuseArgs fa{};
+  fa.unit_phase = g->unit_phase;
+  fa.phase_units = g->phase_units;
+  fa.zero_done = counter + 64;
+  fa.units_done = fa.zero_done + g->num_phases;
+  fa.indeg = g->indeg;
+  fa.ln_w = ln_w; fa.ln_b = ln_b; fa.eps = eps; fa.upd = upd;
+  fa.num_local = g->num_local;
+  fa.sb_nodes = g->sb_nodes;
+  fa.num_phases = (int32_t)g->num_phases;
+  const uint8_t* pack = reinterpret_cast<const uint8_t*>(pack_scratch);
+  switch (d) {
+    case 32: return launch_fused<32>(g, h, pack, bias, out, counter, fa, stream);
+    case 64: return launch_fused<64>(g, h, pack, bias, out, counter, fa, stream);
+    case 128: return launch_fused<128>(g, h, pack, bias, out, counter, fa, stream);
   }
   return fail("mp_umma: unsupported hidden_dim %d", d);
 }

@@ -227,11 +227,12 @@ class Graph:
                 "unit_rel": ur}
 
     def workspace(self, precision: int) -> torch.Tensor:
-        ws = self._workspace.get(precision)
+        key = (precision, os.environ.get("GHF_MP_FUSED"))   # the fused tf32 layer needs no accumulator scratch
+        ws = self._workspace.get(key)
         if ws is None:
             n = int(lib().ghf_mp_workspace_bytes(self._h, self.hidden_dim, precision))
             ws = torch.empty(n, dtype=torch.uint8, device=self.device)
-            self._workspace[precision] = ws
+            self._workspace[key] = ws
         return ws
 
     def mp_layer(self, h, W_msg, W_self, bias, ln_w, ln_b, eps: float, precision: int, out=None,
