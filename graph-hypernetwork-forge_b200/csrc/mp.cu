@@ -188,6 +188,11 @@ int launch_mp_fp32(const ghf_graph* g, const float* h, const float* W_msg, const
 
 using namespace ghf;
 
+static bool mp_ts_enabled(int d) {  // weights in tensor memory (hidden_dim 128) unless GHF_MP_TS=0
+  const char* env = getenv("GHF_MP_TS");
+  return mp_ts_supported(d) && !(env && env[0] == '0');
+}
+
 static bool mp_fused_enabled() {
   const char* env = getenv("GHF_MP_FUSED");
   return !(env && env[0] == '0');
@@ -254,10 +259,13 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
       for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
       GHF_CUDA(cudaEventRecord(rec.e[0], stream));
     }
+    const bool ts = mp_ts_enabled(d);
     if (g->num_units > 0)
-      if (int rc = mp_umma_pack(g, d_W_msg, d_W_self, pack, stream)) return rc;
+      if (int rc = ts ? mp_ts_pack(g, d_W_msg, d_W_self, pack, stream) : mp_umma_pack(g, d_W_msg, d_W_self, pack, stream))
+        return rc;
     if (prof) GHF_CUDA(cudaEventRecord(rec.e[1], stream));
-    if (int rc = mp_umma_launch_fused(g, d_h, d_bias, d_ln_w, d_ln_b, eps, d_out, d_upd, pack, sync, stream))
+    if (int rc = ts ? mp_ts_launch_fused(g, d_h, d_bias, d_ln_w, d_ln_b, eps, d_out, d_upd, pack, sync, stream)
+                    : mp_umma_launch_fused(g, d_h, d_bias, d_ln_w, d_ln_b, eps, d_out, d_upd, pack, sync, stream))
       return rc;
     if (prof) {
       GHF_CUDA(cudaEventRecord(rec.e[2], stream));
@@ -277,15 +285,20 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
     GHF_CUDA(cudaEventRecord(rec.e[0], stream));
   }
   GHF_CUDA(cudaMemsetAsync(counter, 0, 256 + nl * (size_t)d * 4, stream));
+  const bool ts = mp_ts_enabled(d);
   if (precision == GHF_PREC_TF32 && g->num_units > 0) {
     GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
-    if (int rc = mp_umma_pack(g, d_W_msg, d_W_self, reinterpret_cast<char*>(acc) + acc_bytes, stream)) return rc;
+    void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
+    if (int rc = ts ? mp_ts_pack(g, d_W_msg, d_W_self, pack, stream) : mp_umma_pack(g, d_W_msg, d_W_self, pack, stream))
+      return rc;
   }
   if (prof) GHF_CUDA(cudaEventRecord(rec.e[1], stream));
   if (g->num_units > 0) {
     if (precision == GHF_PREC_TF32) {
       void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
-      if (int rc = mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream)) return rc;
+      if (int rc = ts ? mp_ts_launch(g, d_h, d_bias, acc, pack, counter, stream)
+                      : mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream))
+        return rc;
     } else {
       int rc;
       if (d <= 32) rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);

@@ -26,4 +26,13 @@ int mp_umma_launch_fused(const ghf_graph* g, const float* h, const float* bias, 
                          float eps, float* out, float* upd, const void* pack_scratch, void* sync_scratch,
                          cudaStream_t stream);
 
+// hidden_dim 128 with the weights resident in tensor memory (mp_umma_ts.cu); same contracts as above
+bool mp_ts_supported(int hidden_dim);
+int mp_ts_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream);
+int mp_ts_launch(const ghf_graph* g, const float* h, const float* bias, float* acc, const void* pack_scratch,
+                 int* unit_counter, cudaStream_t stream);
+int mp_ts_launch_fused(const ghf_graph* g, const float* h, const float* bias, const float* ln_w, const float* ln_b,
+                       float eps, float* out, float* upd, const void* pack_scratch, void* sync_scratch,
+                       cudaStream_t stream);
+
 }  // namespace ghf

@@ -78,6 +78,9 @@ __device__ __forceinline__ void red_add_v4_hint(float* addr, float4 v, uint64_t 
                "f"(v.z), "f"(v.w), "l"(policy)
                : "memory");
 }
+__device__ __forceinline__ void red_add_f32_hint(float* addr, float v, uint64_t policy) {
+  asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(addr), "f"(v), "l"(policy) : "memory");
+}
 // arrive on `bar` once all cp.async issued so far by this thread have landed; counts as one of the
 // barrier's expected arrivals (.noinc)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
@@ -99,6 +102,21 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uin
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// one lane of the (converged) warp; the choice is made in uniform control flow so that everything computed
+// around it stays on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
