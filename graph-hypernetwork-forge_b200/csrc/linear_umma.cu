@@ -1,0 +1,239 @@
+// linear_umma.cu — Y = relu(X W^T + b) for the node-feature projection (HG:261) at K = N = 128 on tcgen05,
+// fp32-grade through a 3 x TF32 split:  x = xh + xl, w = wh + wl  (h = top 19 bits, l = the remainder),
+//     x.w ~ xh.wh + xl.wh + xh.wl            (the dropped xl.wl term is ~2^-22 relative)
+//
+// Layout mirrors mp_umma_ts.cu.  The transposed tile  Yt[128 n, 128 rows] = W[128 n, 128 k] * Xt  is computed
+// with A = W from TENSOR MEMORY (wh in columns [256,384), wl in [384,512), loaded once per CTA: nn.Linear's
+// weight [out, in] is already "lane = n, column = k") and B = X tiles staged in shared memory by the producers,
+// which split every value on the fly (hi tile + lo tile per 32-wide K chunk, 128 B swizzle, K-major).
+// Epilogue: TMEM -> registers -> transpose through shared memory -> + bias, ReLU -> coalesced 512 B row stores.
+//
+// Warp roles (544 threads, 1 CTA / SM, persistent over row tiles):
+//   0-7 epilogue (2 groups; warps 0-3 also load W into TMEM at start) | 8-15 producers (2 groups, alternating
+//   chunks) | 16 MMA issuer + TMEM allocator
+#include <cstdlib>
+
+#include "common.cuh"
+#include "ghf_b200.h"
+#include "umma.cuh"
+
+namespace ghf {
+namespace {
+
+using namespace ptx;
+
+constexpr int kD = 128;                     // K and N
+constexpr int kTile = 128;                  // rows per tile
+constexpr int kChunks = kD / 32;            // 4 K-chunks of 32
+constexpr int kSub = kTile * 128;           // 16 KiB: one chunk of one tile (hi or lo)
+constexpr int kStage = 2 * kSub;            // hi + lo
+constexpr int kStages = 6;
+constexpr int kStaging = 32 * kD * 4;       // per epilogue group
+constexpr int kSmem = 1024 + kStages * kStage + 2 * kStaging + 512;
+constexpr int kWarpProd = 8, kWarpMma = 16;
+constexpr int kThreads = 32 * (kWarpMma + 1);
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kWhCol = 256, kWlCol = 384;
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __restrict__ W,
+                      const float* __restrict__ bias, int relu, float* __restrict__ Y) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sA = (raw + 1023u) & ~1023u;
+  const uint32_t sStg = sA + kStages * kStage;
+  const uint32_t sBar = sStg + 2 * kStaging;
+  auto full = [&](int s) { return sBar + 8u * s; };
+  auto empty = [&](int s) { return sBar + 8u * (kStages + s); };
+  auto acc_full = [&](int a) { return sBar + 8u * (2 * kStages + a); };
+  auto acc_empty = [&](int a) { return sBar + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = sBar + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (M + kTile - 1) / kTile;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 128);   // the 128 threads of the producer group that owns the chunk
+      mbar_init(empty(s), 1);    // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 256);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kWarpMma) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // W -> TMEM once: thread n of warps 0-3 owns row n of W (lane n): 128 k values as hi and lo columns
+  if (warp < 4) {
+    const float* wrow = W + (int64_t)(warp * 32 + lane) * kD;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(wrow + c * 32 + 4 * j);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float h = to_tf32_rna(f[t]);
+          hi[4 * j + t] = __float_as_uint(h);
+          lo[4 * j + t] = __float_as_uint(to_tf32_rna(f[t] - h));
+        }
+      }
+      tmem_st_32x32(t_row + kWhCol + 32u * c, hi);
+      tmem_st_32x32(t_row + kWlCol + 32u * c, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp < kWarpProd) {
+    // ------------------------------------------------------------------ epilogue
+    const int grp = warp >> 2, q = warp & 3;
+    float* stg = reinterpret_cast<float*>(smem_raw + (sStg - raw) + grp * kStaging);
+    const float4* stg4 = reinterpret_cast<const float4*>(stg);
+    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int64_t row0 = tile * kTile;
+      mbar_wait(acc_full(a), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int bb = 0; bb < 2; ++bb) {
+        const int e0 = 64 * grp + 32 * bb;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kTile + e0), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) stg[e * kD + q * 32 + lane] = __uint_as_float(r[e]);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = 8 * q + i;
+          const int64_t row = row0 + e0 + e;
+          float4 v = stg4[e * (kD / 4) + lane];
+          if (row < M) {
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4*>(Y + row * kD + 4 * lane) = v;
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(a));
+    }
+  } else if (warp < kWarpMma) {
+    // ------------------------------------------------------------------ producers: split X into hi / lo tiles
+    // group g (4 warps) owns chunks with (global chunk counter) % 2 == g, so two chunks are in flight per SM
+    const int grp = (warp - kWarpProd) >> 2, pw = (warp - kWarpProd) & 3;
+    const int cj = lane & 7;
+    int64_t cc = grp;  // global chunk counter of this group's next chunk
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row0 = tile * kTile;
+      for (int c = grp; c < kChunks; c += 2, cc += 2) {
+        const int stage = (int)(cc % kStages);
+        const uint32_t phase = (uint32_t)((cc / kStages) & 1);
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // loads first: 8 x 16 B in flight per thread before the ring slot is needed
+          const int64_t row = row0 + pw * 32 + 4 * i + (lane >> 3);
+          v[i] = row < M ? __ldg(reinterpret_cast<const float4*>(X + row * kD + c * 32 + 4 * cj))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(empty(stage), phase ^ 1u);
+        const uint32_t hi_base = sA + stage * kStage, lo_base = hi_base + kSub;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = pw * 32 + 4 * i + (lane >> 3);
+          const uint32_t off = row * 128 + ((cj ^ (row & 7)) << 4);
+          const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+          const float4 l = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(h.x), "f"(h.y), "f"(h.z),
+                       "f"(h.w)
+                       : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z),
+                       "f"(l.w)
+                       : "memory");
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(full(stage));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
+    constexpr uint32_t idesc = umma_idesc_tf32(kD, kTile);
+    int64_t cc = 0;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(a * kTile);
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c, ++cc) {
+        const int stage = (int)(cc % kStages);
+        mbar_wait(full(stage), (uint32_t)((cc / kStages) & 1));
+        tc_fence_after();
+        const uint32_t hi_addr = sA + stage * kStage;
+        if (elect_one()) {
+          const uint64_t bh = umma_desc_k128(hi_addr), bl = umma_desc_k128(hi_addr + kSub);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t ah = tmem_base + kWhCol + (uint32_t)(32 * c + 8 * j);
+            const uint32_t al = tmem_base + kWlCol + (uint32_t)(32 * c + 8 * j);
+            umma_tf32_ts(d_tmem, ah, bl + 2 * j, idesc, (uint32_t)(c | j));  // small terms first
+            umma_tf32_ts(d_tmem, al, bh + 2 * j, idesc, 1u);
+            umma_tf32_ts(d_tmem, ah, bh + 2 * j, idesc, 1u);
+          }
+          umma_commit(empty(stage));
+          if (c + 1 == kChunks) umma_commit(acc_full(a));
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace
+
+bool linear_umma_eligible(int64_t M, int K, int N, int relu, const void* log_scale, const void* X, const void* W,
+                          const void* Y) {
+  const char* env = getenv("GHF_LINEAR_UMMA");
+  if (env && env[0] == '0') return false;
+  (void)relu;
+  return K == kD && N == kD && log_scale == nullptr && M >= 16384 &&
+         ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0);
+}
+
+int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int relu, float* Y,
+                       cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  const int64_t tiles = (M + kTile - 1) / kTile;
+  const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+  linear128_umma_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(X, M, W, b, relu, Y);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ghf

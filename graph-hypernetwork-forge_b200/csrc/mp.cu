@@ -193,9 +193,9 @@ static bool mp_ts_enabled(int d) {  // weights in tensor memory (hidden_dim 128)
   return mp_ts_supported(d) && !(env && env[0] == '0');
 }
 
-static bool mp_fused_enabled() {
+static bool mp_fused_enabled() {  // opt-in (GHF_MP_FUSED=1): measured slower than the three-kernel layer
   const char* env = getenv("GHF_MP_FUSED");
-  return !(env && env[0] == '0');
+  return env && env[0] == '1';
 }
 
 // ---- optional per-kernel timing (bench.py roofline): event triples per layer call

@@ -192,3 +192,20 @@ def test_message_passing_reference_signature():
                                  {"W_msg": torch.from_numpy(Wm).to(DEV), "W_self": torch.from_numpy(Ws).to(DEV),
                                   "bias": torch.from_numpy(b).to(DEV)})
     assert_close(got.cpu().numpy(), want, 1e-4, 1e-5, "_message_passing")
+
+
+@pytest.mark.parametrize("M,relu", [(16384, True), (50000, True), (33333, False)])
+def test_linear_tcgen05_3xtf32_is_fp32_grade(M, relu):
+    """ghf_linear at K = N = 128 and many rows runs on tcgen05 with a 3xTF32 split; it must stay within the
+    fp32 tolerance (rtol 1e-5 against a float64 reference, atol scaled to the output magnitude)."""
+    from graph_hypernetwork_forge import _native
+    rng = np.random.default_rng(M)
+    x = rng.standard_normal((M, 128)).astype(np.float32) * 3.0
+    w = (rng.standard_normal((128, 128)) / 11.0).astype(np.float32)
+    b = rng.standard_normal(128).astype(np.float32)
+    want = x.astype(np.float64) @ w.astype(np.float64).T + b
+    if relu:
+        want = np.maximum(want, 0)
+    got = _native.linear(torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV), torch.from_numpy(b).to(DEV),
+                         relu=relu).cpu().numpy()
+    assert_close(got, want, FP32_RTOL, 2e-6 * float(np.abs(want).max()), "linear 3xTF32")
