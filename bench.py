@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16", "tf32", "fp32"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and E (debugging only; not a bench number)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -191,7 +191,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
 
-    precision = args.precision if w["d"] in (32, 64, 128) else "fp32"
+    precision = args.precision
+    if precision == "auto":
+        precision = "f16" if w["d"] == 128 else "tf32"
+    if w["d"] not in (32, 64, 128):
+        precision = "fp32"
     model = build_model(w, device, precision)
     x, edge_index, _rel, utf8, offsets = make_device_inputs(w, device)
     N, E, L, d = w["N"], w["E"], w["L"], w["d"]
@@ -250,7 +254,9 @@ def main():
             traffic = json.load(f).get(f"{args.workload}:{precision}")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "mp_umma_kernel<128>" if precision == "tf32" else "mp_fp32_kernel",
+    kernel_name = {"f16": "mp_f16_kernel", "tf32": "mp_umma_ts_kernel" if d == 128 else f"mp_umma_kernel<{d}>",
+                   "fp32": "mp_fp32_kernel"}[precision]
+    roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_contr,
                 "ms_per_launch": t_contr,

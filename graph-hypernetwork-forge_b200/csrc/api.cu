@@ -132,10 +132,15 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
     ~Guard() { ghf_graph_free(g); }
   } guard{g};
 
-  const int prec = (desc->precision == GHF_PREC_TF32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
-                                                                                         : GHF_PREC_FP32;
+  const int prec = (desc->precision == GHF_PREC_F16 && d == 128) ? GHF_PREC_F16
+                   : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
+                                                                                           : GHF_PREC_FP32;
   const int64_t Un = U > 0 ? U : 1;
-  TempBuf wmsg, wself, wbias, hid_a, hid_b, ws;
+  TempBuf wmsg, wself, wbias, hid_a, hid_b, ws, h16a, h16b;
+  if (prec == GHF_PREC_F16) {  // fp16 shadow copies of the layer outputs (the first layer converts h0 inside)
+    GHF_CUDA(h16a.alloc(num_nodes * (size_t)d * 2, stream));
+    GHF_CUDA(h16b.alloc(num_nodes * (size_t)d * 2, stream));
+  }
   GHF_CUDA(wmsg.alloc(Un * (size_t)d * d * 4, stream));
   GHF_CUDA(wself.alloc(Un * (size_t)d * d * 4, stream));
   GHF_CUDA(wbias.alloc(Un * (size_t)d * 4, stream));
@@ -147,6 +152,8 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
 
   float* cur = h0.as<float>();
   float* nxt = h1.as<float>();
+  void* cur16 = nullptr;   // fp16 copy of `cur` (NULL: the layer makes one)
+  void* nxt16 = h16a.p;
   for (int l = 0; l < L; ++l) {
     // WG:137-141 for the U distinct relations
     for (int m = 0; m < 3 && U > 0; ++m) {
@@ -164,10 +171,13 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
         return rc;
     }
     // HG:286-296
-    if (int rc = ghf_mp_layer(g, cur, outs[0], outs[1], outs[2], layers[l].ln_w, layers[l].ln_b, desc->ln_eps, prec,
-                              nxt, nullptr, ws.p, stream))
+    void* out16 = (prec == GHF_PREC_F16 && l + 1 < L) ? nxt16 : nullptr;
+    if (int rc = ghf_mp_layer_f16(g, cur, cur16, outs[0], outs[1], outs[2], layers[l].ln_w, layers[l].ln_b,
+                                  desc->ln_eps, prec, nxt, out16, nullptr, ws.p, stream))
       return rc;
     float* t = cur; cur = nxt; nxt = t;
+    cur16 = out16;
+    nxt16 = (nxt16 == h16a.p) ? h16b.p : h16a.p;
   }
   GHF_CUDA(cudaMemcpyAsync(h_out, cur, num_nodes * (size_t)d * 4, cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaStreamSynchronize(stream));

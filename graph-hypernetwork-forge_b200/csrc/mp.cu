@@ -8,6 +8,8 @@
 // linearity, which is why it rides along as the second half of K.  Two contraction engines:
 //   GHF_PREC_FP32  this file: CUDA-core FFMA tiles, exact fp32;
 //   GHF_PREC_TF32  mp_umma.cu: tcgen05 kind::tf32 with TMEM accumulators.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <vector>
 
@@ -15,6 +17,7 @@
 #include "ghf_b200.h"
 #include "graph.cuh"
 #include "mp.cuh"
+#include "mp_fuse.cuh"
 
 namespace ghf {
 namespace {
@@ -163,6 +166,78 @@ mp_epilogue_kernel(const float* __restrict__ acc, const int32_t* __restrict__ in
   }
 }
 
+// The same epilogue for hidden_dim 32 / 64 / 128: a lane owns D/32 CONSECUTIVE columns (one vector access per row
+// and operand), four rows in flight per warp, and an optional fp16 copy of the output row for the next layer's
+// gathers (GHF_PREC_F16).
+template <int D>
+__global__ void __launch_bounds__(256)
+mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict__ indeg,
+                       const float* __restrict__ h, int64_t dst_lo, int64_t num_local,
+                       const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
+                       float* __restrict__ out, float* __restrict__ upd, __half* __restrict__ out16) {
+  using namespace fuse;
+  constexpr int V = D / 32;
+  constexpr int kRows = 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  float lw[V], lb[V];
+  vload_nc<V>(lw, ln_w + lane * V);
+  vload_nc<V>(lb, ln_b + lane * V);
+  for (int64_t r0 = w0; r0 < num_local; r0 += kRows * warps) {
+    float a[kRows][V], hv[kRows][V];
+    int deg[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int64_t r = r0 + k * warps;
+      if (r < num_local) {
+        vload_cg<V>(a[k], acc + r * D + lane * V);
+        vload_nc<V>(hv[k], h + (dst_lo + r) * D + lane * V);
+        deg[k] = __ldg(indeg + r);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int64_t r = r0 + k * warps;
+      if (r >= num_local) break;
+      const float inv = 1.f / (float)max(deg[k], 1);
+      float x[V], u[V], sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        u[j] = a[k][j] * inv;
+        x[j] = fmaxf(u[j] + hv[k][j], 0.f);
+        sum += x[j];
+      }
+      if (upd) vstore<V>(upd + r * D + lane * V, u);
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+      const float mean = sum / (float)D;
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) var += (x[j] - mean) * (x[j] - mean);
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+      const float rstd = rsqrtf(var / (float)D + eps);
+      float y[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) y[j] = (x[j] - mean) * rstd * lw[j] + lb[j];
+      vstore<V>(out + r * D + lane * V, y);
+      if (out16) {
+        __half* o = out16 + r * D + lane * V;
+        if constexpr (V == 4) {
+          const __half2 p0 = __floats2half2_rn(y[0], y[1]), p1 = __floats2half2_rn(y[2], y[3]);
+          *reinterpret_cast<uint2*>(o) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+        } else if constexpr (V == 2) {
+          *reinterpret_cast<__half2*>(o) = __floats2half2_rn(y[0], y[1]);
+        } else {
+          *o = __float2half_rn(y[0]);
+        }
+      }
+    }
+  }
+}
+
 template <int BN>
 int launch_mp_fp32(const ghf_graph* g, const float* h, const float* W_msg, const float* W_self,
                    const float* bias, float* acc, cudaStream_t stream) {
@@ -233,16 +308,53 @@ extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim
   // unfused paths accumulate in scratch; the fused tf32 path accumulates in the output rows
   int64_t bytes = 256 /* work counter */ + (fused ? 0 : align_up(g->num_local * (int64_t)hidden_dim * 4, 256));
   if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim) + mp_umma_sync_bytes(g);
+  if (precision == GHF_PREC_F16)  // weight images + the fp16 copy of h made when the caller passes none
+    bytes += mp_f16_pack_bytes(g->num_rel) + align_up(g->num_nodes * (int64_t)hidden_dim * 2, 256);
   return bytes + 256;
 }
 
-extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, const float* d_W_self,
-                            const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
-                            int precision, float* d_out, float* d_upd, void* d_workspace, void* stream_) {
+static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_h, const float* d_ln_w,
+                           const float* d_ln_b, float eps, float* d_out, float* d_upd, void* d_out16,
+                           cudaStream_t stream) {
+  const int d = g->hidden_dim;
+  const int64_t nl = g->num_local;
+  const int threads = 256;
+  const bool aligned = (reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(d_h) |
+                        reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_upd) |
+                        reinterpret_cast<uintptr_t>(d_ln_w) | reinterpret_cast<uintptr_t>(d_ln_b) |
+                        reinterpret_cast<uintptr_t>(d_out16)) % 16 == 0;
+  if (aligned && (d == 32 || d == 64 || d == 128)) {
+    const int64_t want = cdiv(nl, (threads / 32) * 4);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    __half* o16 = reinterpret_cast<__half*>(d_out16);
+    if (d == 32)
+      mp_epilogue_vec_kernel<32><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
+                                                               d_out, d_upd, o16);
+    else if (d == 64)
+      mp_epilogue_vec_kernel<64><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
+                                                               d_out, d_upd, o16);
+    else
+      mp_epilogue_vec_kernel<128><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b,
+                                                                eps, d_out, d_upd, o16);
+  } else {
+    GHF_REQUIRE(d_out16 == nullptr, "ghf_mp_layer: fp16 output needs hidden_dim 32/64/128 and 16-byte alignment");
+    mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(
+        acc, g->indeg, d_h, g->dst_lo, nl, d, d_ln_w, d_ln_b, eps, d_out, d_upd);
+  }
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_W_msg,
+                                const float* d_W_self, const float* d_bias, const float* d_ln_w,
+                                const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
+                                float* d_upd, void* d_workspace, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(g != nullptr, "ghf_mp_layer: graph is NULL");
   GHF_REQUIRE(d_workspace != nullptr, "ghf_mp_layer: workspace is NULL");
-  GHF_REQUIRE(precision == GHF_PREC_FP32 || precision == GHF_PREC_TF32, "ghf_mp_layer: precision=%d", precision);
+  GHF_REQUIRE(precision == GHF_PREC_FP32 || precision == GHF_PREC_TF32 || precision == GHF_PREC_F16,
+              "ghf_mp_layer: precision=%d", precision);
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
   g->stream = stream_;
@@ -250,6 +362,7 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
   if (precision == GHF_PREC_TF32 && mp_fused_enabled()) {
     // workspace: [sync words][operand images]; one kernel does the whole layer in place
     GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
+    GHF_REQUIRE(d_out16 == nullptr, "ghf_mp_layer: the fused tf32 layer has no fp16 output");
     char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
     void* sync = base;
     void* pack = base + mp_umma_sync_bytes(g);
@@ -274,10 +387,11 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
     }
     return 0;
   }
-  // workspace: [work counter, 256 B][accumulator rows][operand images (tf32 path)]
+  // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
   int* counter = reinterpret_cast<int*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
   float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) + 256);
   const int64_t acc_bytes = align_up(nl * (int64_t)d * 4, 256);
+  void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
   ProfRec rec{};
   const bool prof = g_prof_on;
   if (prof) {
@@ -286,35 +400,51 @@ extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d
   }
   GHF_CUDA(cudaMemsetAsync(counter, 0, 256 + nl * (size_t)d * 4, stream));
   const bool ts = mp_ts_enabled(d);
+  const void* h16 = d_h16;
   if (precision == GHF_PREC_TF32 && g->num_units > 0) {
     GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
-    void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
     if (int rc = ts ? mp_ts_pack(g, d_W_msg, d_W_self, pack, stream) : mp_umma_pack(g, d_W_msg, d_W_self, pack, stream))
       return rc;
+  } else if (precision == GHF_PREC_F16) {
+    GHF_REQUIRE(mp_f16_supported(d), "ghf_mp_layer: f16 path supports hidden_dim 128, got %d", d);
+    if (g->num_units > 0) {
+      if (int rc = mp_f16_pack(g, d_W_msg, d_W_self, pack, stream)) return rc;
+      if (h16 == nullptr) {  // no fp16 copy of h from the previous layer: make one
+        void* conv = reinterpret_cast<char*>(pack) + mp_f16_pack_bytes(g->num_rel);
+        if (int rc = mp_f16_convert(d_h, g->num_nodes * (int64_t)d, conv, stream)) return rc;
+        h16 = conv;
+      }
+    }
   }
   if (prof) GHF_CUDA(cudaEventRecord(rec.e[1], stream));
   if (g->num_units > 0) {
+    int rc;
     if (precision == GHF_PREC_TF32) {
-      void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
-      if (int rc = ts ? mp_ts_launch(g, d_h, d_bias, acc, pack, counter, stream)
-                      : mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream))
-        return rc;
+      rc = ts ? mp_ts_launch(g, d_h, d_bias, acc, pack, counter, stream)
+              : mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream);
+    } else if (precision == GHF_PREC_F16) {
+      rc = mp_f16_launch(g, h16, d_bias, acc, pack, counter, stream);
+    } else if (d <= 32) {
+      rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
+    } else if (d <= 64) {
+      rc = launch_mp_fp32<64>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
     } else {
-      int rc;
-      if (d <= 32) rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
-      else if (d <= 64) rc = launch_mp_fp32<64>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
-      else rc = launch_mp_fp32<128>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
-      if (rc) return rc;
+      rc = launch_mp_fp32<128>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
     }
+    if (rc) return rc;
   }
   if (prof) GHF_CUDA(cudaEventRecord(rec.e[2], stream));
-  const int threads = 256;
-  mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(
-      acc, g->indeg, d_h, g->dst_lo, nl, d, d_ln_w, d_ln_b, eps, d_out, d_upd);
-  GHF_LAUNCH_CHECK();
+  if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, stream)) return rc;
   if (prof) {
     GHF_CUDA(cudaEventRecord(rec.e[3], stream));
     g_prof.push_back(rec);
   }
   return 0;
+}
+
+extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, const float* d_W_self,
+                            const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
+                            int precision, float* d_out, float* d_upd, void* d_workspace, void* stream_) {
+  return ghf_mp_layer_f16(g, d_h, nullptr, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out, nullptr,
+                          d_upd, d_workspace, stream_);
 }

@@ -35,4 +35,16 @@ int mp_ts_launch_fused(const ghf_graph* g, const float* h, const float* bias, co
                        float eps, float* out, float* upd, const void* pack_scratch, void* sync_scratch,
                        cudaStream_t stream);
 
+
+// hidden_dim 128 with fp16 feature transport, kind::f16 MMA and double-buffered weights in TMEM (mp_f16.cu)
+bool mp_f16_supported(int hidden_dim);
+// scratch for the per-relation fp16 weight images [R][64 KiB] followed by their inverse power-of-two scales [R]
+int64_t mp_f16_pack_bytes(int num_rel);
+int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream);
+// h16[i] = fp16(h[i]) for `elems` values (a multiple of 8)
+int mp_f16_convert(const float* h, int64_t elems, void* h16, cudaStream_t stream);
+// acc[dst_local, :] += sum over edges of [h16_src | h16_dst] @ [W_msg; W_self][rel] + bias[rel]; h16 is [N, 128] fp16
+int mp_f16_launch(const ghf_graph* g, const void* h16, const float* bias, float* acc, const void* pack_scratch,
+                  int* unit_counter, cudaStream_t stream);
+
 }  // namespace ghf

@@ -1,0 +1,489 @@
+// mp_f16.cu — message-passing contraction for hidden_dim 128 with HALF-WIDTH TRANSPORT (GHF_PREC_F16).
+//
+// What bounds the layer on B200 (tools/l2_paths.cu, profiles/r01_l2_paths_microbench.txt):
+//   - the scatter of fp32 result rows into the L2-resident accumulator window costs 24 cycles per 512 B row per
+//     SM, whatever the warp count (the SM's store path), i.e. 1.35 ms for 16M edges - a floor no layout removes;
+//   - the random row gather runs at HBM speed (7+ TB/s) when >= 128 KB are in flight per SM, and it shares the
+//     SM <-> L2 path with the scatter: gathering 512 B rows next to the scatter takes 1.95 ms, 256 B rows 1.5 ms.
+// So the node features travel as fp16: h16 = fp16(h) (11-bit significand, the same as the TF32 operand the
+// tensor core would round an fp32 value to; power-of-two scales keep values inside the fp16 range), the
+// generated weights as fp16(W * 2^k_r) with a per-relation power of two, products accumulate in fp32 in TMEM
+// (tcgen05 kind::f16) and the epilogue undoes the scales exactly.  Half the gather bytes, half the shared
+// memory per tile (3.5 tiles in flight instead of 1.5), half the tensor-pipe time, and the weight image of a
+// relation shrinks to 128 TMEM columns, which leaves room to double-buffer it.
+//
+// Transposed tile, as in mp_umma_ts.cu:   Dt[128 out-cols, 128 edges] = Wt_r[128, 256] * [h16_src | h16_dst]^T
+//   A = Wt_r : TMEM columns [256,384) / [384,512)  (two units' weights; lane = output column, column = k pair)
+//   B = rows : gathered by cp.async into a 7 x 32 KiB ring (stage = the src halves or the dst halves of a tile)
+//   D = Dt   : TMEM columns [0,128) / [128,256)
+// The epilogue needs no shared-memory transpose: thread = output column, so one red.global.add.f32 per edge is
+// a coalesced 128 B line of acc[dst_e].
+//
+// Sixteen epilogue warps, not eight: a warp's 32 reds of a block go to 32 different rows, and that shape needs
+// 16 warps to saturate the store path (tools/l2_paths.cu: 2.13 ms with 8 warps, 1.42 ms with 16).
+//
+// Warp roles (832 threads, 1 CTA / SM, persistent):
+//   0-15  epilogue (group g = warp/4 owns edges [32g, 32g+32) of each tile, warp%4 = TMEM lane quarter)
+//   16-19 row-gather producers (warp p owns rows [32p, 32p+32) of each tile; ids prefetched one tile ahead)
+//   20    MMA issuer + TMEM allocator
+//   21    scheduler: draws units from the global counter and publishes TILE descriptors in shared memory
+//   22-25 weight loaders: global -> registers -> tcgen05.st, one unit ahead of the MMA
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "mp.cuh"
+#include "umma.cuh"
+
+namespace ghf {
+namespace {
+
+using namespace ptx;
+
+constexpr int kD = 128;
+constexpr int kTile = 128;                 // edges per tile (the N of the transposed product)
+constexpr int kRowBytes = kD * 2;          // one fp16 feature row
+constexpr int kSub = kTile * 128;          // 128 rows x 128 B (64 halfs of K): 16 KiB, one swizzle atom column
+constexpr int kStageBytes = 2 * kSub;      // the src halves (K 0..127) or the dst halves (K 128..255) of a tile
+constexpr int kStages = 7;                 // 224 KiB ring = 3.5 tiles of gathers in flight
+constexpr int kQueue = 16;                 // tile descriptors between the scheduler and the other roles
+constexpr int kEpiWarps = 16, kProdWarps = 4, kLoadWarps = 4;
+constexpr int kWarpProd = kEpiWarps, kWarpMma = kWarpProd + kProdWarps, kWarpSched = kWarpMma + 1,
+              kWarpLoad = kWarpSched + 1;
+constexpr int kThreads = 32 * (kWarpLoad + kLoadWarps);
+constexpr int kConsumers = kEpiWarps + kProdWarps + 1 + kLoadWarps;   // warps that read every descriptor
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kWCol = 256;            // first TMEM column of the weight buffers (2 x 128 columns)
+constexpr int kImageBytes = kD * 2 * kD * 2;   // one relation's Wt image: 128 x 256 fp16 = 64 KiB
+constexpr int kBarBytes = 1024;
+constexpr int kSmem = 1024 + kStages * kStageBytes + kQueue * 16 + kBarBytes;
+
+constexpr uint32_t kFlagSrcEvictFirst = 1u, kFlagDstEvictLast = 2u, kFlagRedEvictLast = 4u, kFlagWEvictLast = 8u;
+constexpr uint32_t kDefaultFlags = kFlagSrcEvictFirst | kFlagDstEvictLast | kFlagRedEvictLast;
+// timing experiments only (results are wrong): drop the reductions / the gathers
+constexpr uint32_t kDbgNoRed = 32u, kDbgNoGather = 64u;
+
+constexpr uint32_t kTileFirst = 1u, kTileLast = 2u, kTileWbuf = 4u;   // descriptor flags
+
+// Instruction descriptor, kind::f16: D fp32, A and B fp16, both K-major.
+//   [4,6) D fmt (1 = f32) | [7,10) A fmt (0 = f16) | [10,13) B fmt (0 = f16) | [17,23) N>>3 | [24,29) M>>4
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kD >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---- weight image ------------------------------------------------------------------------------------------
+// Element (n, k) of Wt_r (k < 128 -> W_msg[r][k][n], else W_self[r][k-128][n]) scaled by 2^k_r, as fp16, at
+// half index   piece c = k/64 | quarter q = n/32 | 16-byte group j = (k%64)/8 | lane l = n%32 | k%8
+// so that load j of piece c by loader warp q is one contiguous 512 B line set and the 8 loads of a lane are its
+// 64 consecutive k, i.e. the 32 TMEM columns [32c, 32c+32) of lane n (two halfs per column, even k low).
+__device__ __forceinline__ int wt_half_index(int n, int k) {
+  return ((((k >> 6) * 4 + (n >> 5)) * 8 + ((k & 63) >> 3)) * 32 + (n & 31)) * 8 + (k & 7);
+}
+
+// One CTA per relation: amax over [W_msg[r]; W_self[r]], k_r = 14 - floor(log2(amax)), scaled fp16 image.
+__global__ void __launch_bounds__(256)
+pack_f16_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_self, __half* __restrict__ pack,
+                float* __restrict__ inv_scale) {
+  __shared__ float s_max[8];
+  __shared__ float s_scale;
+  const int64_t r = blockIdx.x;
+  const float4* wm = reinterpret_cast<const float4*>(W_msg + r * kD * kD);
+  const float4* ws = reinterpret_cast<const float4*>(W_self + r * kD * kD);
+  float m = 0.f;
+  for (int i = threadIdx.x; i < kD * kD / 4; i += 256) {
+    const float4 a = wm[i], b = ws[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = 0.f;
+    for (int i = 0; i < 8; ++i) mm = fmaxf(mm, s_max[i]);
+    int e = 0;
+    float scale = 1.f;
+    if (mm > 0.f && isfinite(mm)) {
+      frexpf(mm, &e);                           // mm = f * 2^e, f in [0.5, 1)  ->  mm * 2^(15-e) in [2^14, 2^15)
+      e = 15 - e;
+      e = e > 100 ? 100 : (e < -100 ? -100 : e);
+      scale = ldexpf(1.f, e);
+    }
+    s_scale = scale;
+    inv_scale[r] = 1.f / scale;                 // exact: a power of two
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  __half* img = pack + r * (int64_t)(2 * kD * kD);
+  // thread = (8 consecutive k, one n): lanes walk n, so every read is a coalesced 128 B line of one W row and
+  // the eight halfs of a thread are one 16 B store, consecutive across the warp (512 B)
+  for (int i = threadIdx.x; i < (2 * kD / 8) * kD; i += 256) {
+    const int n = i % kD, k0 = (i / kD) * 8;
+    const float* src = k0 < kD ? W_msg + (r * kD + k0) * kD + n : W_self + (r * kD + (k0 - kD)) * kD + n;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 p = __floats2half2_rn(src[(2 * j) * kD] * scale, src[(2 * j + 1) * kD] * scale);
+      w[j] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+    *reinterpret_cast<uint4*>(img + wt_half_index(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// h16 = fp16(h): 8 values per thread (the layer-0 input; later layers get h16 from the layer epilogue)
+__global__ void __launch_bounds__(256)
+to_f16_kernel(const float* __restrict__ h, int64_t n8, __half* __restrict__ h16) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(h) + 2 * i);
+  const float4 b = __ldcs(reinterpret_cast<const float4*>(h) + 2 * i + 1);
+  const __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w);
+  const __half2 p2 = __floats2half2_rn(b.x, b.y), p3 = __floats2half2_rn(b.z, b.w);
+  uint4 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
+  o.z = *reinterpret_cast<const uint32_t*>(&p2); o.w = *reinterpret_cast<const uint32_t*>(&p3);
+  reinterpret_cast<uint4*>(h16)[i] = o;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
+              const int32_t* __restrict__ unit_rel, int64_t num_units, const int32_t* __restrict__ src_sorted,
+              const int32_t* __restrict__ dst_sorted, const __half* __restrict__ h16, int64_t dst_lo,
+              const __half* __restrict__ wpack, const float* __restrict__ w_inv_scale,
+              const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter,
+              uint32_t flags) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sA = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = sA + kStages * kStageBytes;          // kQueue x int4 tile descriptors
+  const uint32_t sBar = sQ + kQueue * 16;
+  auto full = [&](int s) { return sBar + 8u * s; };
+  auto empty = [&](int s) { return sBar + 8u * (kStages + s); };
+  const uint32_t bar2 = sBar + 8u * (2 * kStages);
+  auto acc_full = [&](int a) { return bar2 + 8u * a; };
+  auto acc_empty = [&](int a) { return bar2 + 16u + 8u * a; };
+  auto w_full = [&](int b) { return bar2 + 32u + 8u * b; };
+  auto w_empty = [&](int b) { return bar2 + 48u + 8u * b; };
+  const uint32_t q_full0 = bar2 + 64u;
+  const uint32_t q_empty0 = q_full0 + 8u * kQueue;
+  const uint32_t tmem_slot = q_empty0 + 8u * kQueue;
+  volatile int4* q_ptr = reinterpret_cast<volatile int4*>(smem_raw + (sQ - raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile-descriptor queue (consumer side).  acquire() blocks until descriptor `idx` is published and returns it
+  // {x = first sorted edge (-1: no more work), y = rows, z = relation, w = flags}; release() frees the slot once
+  // per warp.  Roles may hold several descriptors (the producers look one tile ahead).
+  auto q_acquire = [&](uint32_t idx) -> int4 {
+    mbar_wait(q_full0 + 8u * (idx % kQueue), (idx / kQueue) & 1u);
+    const volatile int4* p = q_ptr + (idx % kQueue);
+    int4 t;
+    t.x = p->x; t.y = p->y; t.z = p->z; t.w = p->w;
+    return t;
+  };
+  auto q_release = [&](uint32_t idx) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(q_empty0 + 8u * (idx % kQueue));
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 32 * kProdWarps);  // one cp.async-completion arrival per producer thread
+      mbar_init(empty(s), 1);               // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);            // tcgen05.commit
+      mbar_init(acc_empty(a), kEpiWarps);   // one arrival per epilogue warp
+      mbar_init(w_full(a), 32 * kLoadWarps);
+      mbar_init(w_empty(a), 1);             // tcgen05.commit
+    }
+    for (int q = 0; q < kQueue; ++q) {
+      mbar_init(q_full0 + 8u * q, 1);
+      mbar_init(q_empty0 + 8u * q, kConsumers);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kWarpMma) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < kWarpProd) {
+    // ------------------------------------------------------------------ epilogue: Dt -> red.f32 rows
+    const int grp = warp >> 2, q = warp & 3;
+    const int col = 32 * q + lane;                       // this thread's output column = its TMEM lane
+    float* acc_col = acc + col;
+    const int e0 = 32 * grp;
+    // Everything a tile's reductions need from global memory (the destination id of edge e0 + lane, the
+    // relation's bias entry and scale) is fetched one tile ahead, so that no load latency sits between
+    // "accumulator ready" and the first red.
+    struct TileRegs { int dst; float bias_n, inv; };
+    auto fetch = [&](const int4& t) -> TileRegs {
+      TileRegs x{-1, 0.f, 1.f};
+      if (t.x < 0) return x;
+      if (e0 + lane < t.y) x.dst = dst_sorted[t.x + e0 + lane];
+      x.bias_n = bias[(int64_t)t.z * kD + col];
+      x.inv = w_inv_scale[t.z];
+      return x;
+    };
+    int4 cur = q_acquire(0);
+    TileRegs cr = fetch(cur);
+    for (uint32_t it = 0; cur.x >= 0; ++it) {
+      const int4 nxt = q_acquire(it + 1);
+      const TileRegs nr = fetch(nxt);
+      const int a = it & 1;
+      mbar_wait(acc_full(a), (it >> 1) & 1);
+      tc_fence_after();
+      if (e0 < cur.y) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kTile + e0), r);
+        tmem_ld_wait();
+        if (!(flags & kDbgNoRed)) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int dsti = __shfl_sync(0xffffffffu, cr.dst, e);
+            if (dsti >= 0) red_add_f32(acc_col + (int64_t)dsti * kD, fmaf(__uint_as_float(r[e]), cr.inv, cr.bias_n));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(a));
+      q_release(it);
+      cur = nxt;
+      cr = nr;
+    }
+  } else if (warp < kWarpMma) {
+    // ------------------------------------------------------------------ row-gather producers
+    // Warp pw owns rows [32 pw, 32 pw + 32) of every tile: lane l keeps the source and destination id of row
+    // 32 pw + l.  One cp.async instruction moves two 256 B rows (16 lanes x 16 B each).
+    const int pw = warp - kWarpProd;
+    const int l16 = lane & 15, hi = lane >> 4;
+    const uint64_t pol_src = (flags & kFlagSrcEvictFirst) ? policy_evict_first() : policy_evict_normal();
+    const uint64_t pol_dst = (flags & kFlagDstEvictLast) ? policy_evict_last() : policy_evict_normal();
+    const uint8_t* hb = reinterpret_cast<const uint8_t*>(h16) + l16 * 16;
+    struct Ids { int64_t src, dst; };
+    auto ids_of = [&](const int4& t) -> Ids {
+      const int row = 32 * pw + lane;
+      if (t.x < 0 || row >= t.y) return Ids{-1, -1};
+      return Ids{(int64_t)src_sorted[t.x + row], dst_lo + dst_sorted[t.x + row]};
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    int4 cur = q_acquire(0);
+    Ids ids = ids_of(cur);
+    for (uint32_t it = 0; cur.x >= 0; ++it) {
+      const int4 nxt = q_acquire(it + 1);
+      const Ids ids_nxt = ids_of(nxt);                   // in flight while this tile's rows are issued
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {                      // s = 0: source rows, s = 1: destination rows
+        mbar_wait(empty(stage), phase ^ 1u);
+        const uint32_t base = sA + stage * kStageBytes + (l16 >> 3) * kSub;
+        const uint64_t pol = s ? pol_dst : pol_src;
+        const int64_t mine = s ? ids.dst : ids.src;
+        if (!(flags & kDbgNoGather)) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int rl = 2 * i + hi;                   // row within the warp's 32
+            const int64_t idx = __shfl_sync(0xffffffffu, mine, rl);
+            const int row = 32 * pw + rl;
+            const uint32_t to = base + row * 128 + (((l16 & 7) ^ (row & 7)) << 4);
+            if (idx >= 0) cp_async_16_hint(to, hb + idx * kRowBytes, pol);
+          }
+        }
+        cp_async_arrive_noinc(full(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      q_release(it);
+      cur = nxt;
+      ids = ids_nxt;
+    }
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
+    int stage = 0;
+    uint32_t phase = 0, wph = 0;                         // wph bit b: parity of the next w_full(b) wait
+    for (uint32_t it = 0;; ++it) {
+      const int4 t = q_acquire(it);
+      if (t.x < 0) break;
+      const uint32_t tf = (uint32_t)t.w;
+      q_release(it);
+      const int a = it & 1;
+      const int wb = (tf & kTileWbuf) ? 1 : 0;
+      mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1u);
+      if (tf & kTileFirst) {
+        mbar_wait(w_full(wb), (wph >> wb) & 1u);
+        wph ^= 1u << wb;
+      }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(a * kTile);
+      const uint32_t w_tmem = tmem_base + kWCol + (uint32_t)(wb * kD);
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        mbar_wait(full(stage), phase);
+        fence_proxy_async();                             // cp.async (generic proxy) writes -> tensor-core reads
+        tc_fence_after();
+        const uint32_t stage_addr = sA + stage * kStageBytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int cs = 0; cs < 2; ++cs) {
+            const uint64_t bdesc = umma_desc_k128(stage_addr + cs * kSub);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              umma_f16_ts(d_tmem, w_tmem + (uint32_t)(32 * (2 * s + cs) + 8 * j), bdesc + 2 * j, kIdesc,
+                          (uint32_t)(s | cs | j));
+          }
+          umma_commit(empty(stage));
+          if (s == 1) {
+            umma_commit(acc_full(a));
+            if (tf & kTileLast) umma_commit(w_empty(wb));  // every MMA that reads this unit's weights is done
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == kWarpSched) {
+    // ------------------------------------------------------------------ scheduler
+    if (lane == 0) {
+      uint32_t qi = 0, wb = 0;
+      auto publish = [&](int start, int rows, int rel, uint32_t tf) {
+        mbar_wait(q_empty0 + 8u * (qi % kQueue), ((qi / kQueue) & 1u) ^ 1u);
+        volatile int4* p = q_ptr + (qi % kQueue);
+        p->x = start; p->y = rows; p->z = rel; p->w = (int)tf;
+        mbar_arrive(q_full0 + 8u * (qi % kQueue));       // release: the descriptor is visible to the waiters
+        ++qi;
+      };
+      int64_t u = atomicAdd(unit_counter, 1);
+      while (u < num_units) {
+        const int start = unit_start[u], count = unit_count[u], rel = unit_rel[u];
+        const int64_t u_next = atomicAdd(unit_counter, 1);   // its latency hides behind the tiles published below
+        for (int t0 = 0; t0 < count; t0 += kTile) {
+          const uint32_t tf = (t0 == 0 ? kTileFirst : 0u) | (t0 + kTile >= count ? kTileLast : 0u) |
+                              (wb ? kTileWbuf : 0u);
+          publish(start + t0, min(kTile, count - t0), rel, tf);
+        }
+        wb ^= 1u;
+        u = u_next;
+      }
+      publish(-1, 0, 0, 0);
+      publish(-1, 0, 0, 0);                              // the producers look one descriptor ahead
+    }
+  } else {
+    // ------------------------------------------------------------------ weight loaders: Wt_r -> TMEM
+    // thread = output column n = 32 * quarter + lane = TMEM lane; 128 columns (256 k) in 4 pieces of 32
+    const int quarter = warp & 3;   // a warp reaches TMEM lanes [32 (warp % 4), +32) only
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + kWCol;
+    const uint64_t pol_w = (flags & kFlagWEvictLast) ? policy_evict_last() : policy_evict_normal();
+    (void)pol_w;
+    uint32_t eph = 0;                                    // bit b: parity of the next w_empty(b) wait
+    for (uint32_t it = 0;; ++it) {
+      const int4 t = q_acquire(it);
+      if (t.x < 0) break;
+      const uint32_t tf = (uint32_t)t.w;
+      q_release(it);
+      if (!(tf & kTileFirst)) continue;
+      const int wb = (tf & kTileWbuf) ? 1 : 0;
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(wpack) + (int64_t)t.z * kImageBytes +
+                           quarter * (8 * 32 * 16) + lane * 16;
+      uint32_t r[32];
+      auto fetch = [&](int piece) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = ldg_nc_v4(img + piece * (4 * 8 * 32 * 16) + j * (32 * 16));
+          r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+        }
+      };
+      fetch(0);                                          // in flight while the buffer is still being read
+      mbar_wait(w_empty(wb), ((eph >> wb) & 1u) ^ 1u);
+      eph ^= 1u << wb;
+      tc_fence_after();
+      const uint32_t dst = t_row + (uint32_t)(wb * kD);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_st_32x32(dst + 32u * c, r);
+        tmem_st_wait();
+        if (c < 3) fetch(c + 1);
+      }
+      tc_fence_before();
+      mbar_arrive(w_full(wb));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+uint32_t env_flags() {
+  const char* env = getenv("GHF_MP_FLAGS");
+  return env ? (uint32_t)atoi(env) : kDefaultFlags;
+}
+
+}  // namespace
+
+bool mp_f16_supported(int d) { return d == kD; }
+
+int64_t mp_f16_pack_bytes(int num_rel) {
+  return align_up((int64_t)num_rel * kImageBytes, 256) + align_up((int64_t)num_rel * 4, 256);
+}
+
+int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch,
+                cudaStream_t stream) {
+  GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
+  GHF_REQUIRE((reinterpret_cast<uintptr_t>(W_msg) | reinterpret_cast<uintptr_t>(W_self) |
+               reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
+              "mp_f16: W_msg / W_self / scratch must be 16-byte aligned");
+  __half* img = reinterpret_cast<__half*>(pack_scratch);
+  float* inv = reinterpret_cast<float*>(reinterpret_cast<char*>(pack_scratch) +
+                                        align_up((int64_t)g->num_rel * kImageBytes, 256));
+  pack_f16_kernel<<<(unsigned)g->num_rel, 256, 0, stream>>>(W_msg, W_self, img, inv);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+int mp_f16_convert(const float* h, int64_t elems, void* h16, cudaStream_t stream) {
+  GHF_REQUIRE(elems % 8 == 0, "mp_f16: element count must be a multiple of 8");
+  GHF_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h16)) % 16 == 0,
+              "mp_f16: h / h16 must be 16-byte aligned");
+  if (elems == 0) return 0;
+  to_f16_kernel<<<(unsigned)cdiv(elems / 8, 256), 256, 0, stream>>>(h, elems / 8, reinterpret_cast<__half*>(h16));
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+int mp_f16_launch(const ghf_graph* g, const void* h16, const float* bias, float* acc, const void* pack_scratch,
+                  int* unit_counter, cudaStream_t stream) {
+  GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
+  GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_f16: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
+  GHF_REQUIRE((reinterpret_cast<uintptr_t>(h16) | reinterpret_cast<uintptr_t>(acc) |
+               reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
+              "mp_f16: h16 / acc / scratch must be 16-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  const __half* img = reinterpret_cast<const __half*>(pack_scratch);
+  const float* inv = reinterpret_cast<const float*>(reinterpret_cast<const char*>(pack_scratch) +
+                                                    align_up((int64_t)g->num_rel * kImageBytes, 256));
+  const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
+  mp_f16_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(
+      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
+      reinterpret_cast<const __half*>(h16), g->dst_lo, img, inv, bias, acc, unit_counter, env_flags());
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ghf

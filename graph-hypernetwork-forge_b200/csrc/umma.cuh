@@ -78,6 +78,9 @@ __device__ __forceinline__ void red_add_v4_hint(float* addr, float4 v, uint64_t 
                "f"(v.z), "f"(v.w), "l"(policy)
                : "memory");
 }
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void red_add_f32_hint(float* addr, float v, uint64_t policy) {
   asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(addr), "f"(v), "l"(policy) : "memory");
 }

@@ -15,7 +15,9 @@ import torch
 
 PREC_FP32 = 0
 PREC_TF32 = 1
-_PREC = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+PREC_F16 = 2
+_PREC = {"fp32": PREC_FP32, "tf32": PREC_TF32, "f16": PREC_F16}
+ABI_VERSION = 2
 
 _LIB_PATH = os.environ.get("GHF_LIB") or os.path.join(
     os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")
@@ -57,6 +59,7 @@ def lib():
         "ghf_graph_export": (c_int, [P, P, P, P, P, P, P, P]),
         "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
+        "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P]),
         "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
                                               c_int64, P, P, P, P]),
         "ghf_launch_count": (c_int64, [c_int]),
@@ -67,8 +70,8 @@ def lib():
         fn = getattr(L, name)  # AttributeError here = header and library disagree
         fn.restype = res
         fn.argtypes = args
-    if L.ghf_abi_version() != 1:
-        raise ImportError(f"{_LIB_PATH}: ABI version {L.ghf_abi_version()} != 1")
+    if L.ghf_abi_version() != ABI_VERSION:
+        raise ImportError(f"{_LIB_PATH}: ABI version {L.ghf_abi_version()} != {ABI_VERSION}")
     _lib = L
     return L
 
@@ -76,7 +79,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_text_encode", "ghf_linear",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -236,8 +239,11 @@ class Graph:
         return ws
 
     def mp_layer(self, h, W_msg, W_self, bias, ln_w, ln_b, eps: float, precision: int, out=None,
-                 want_upd: bool = False):
-        """One message-passing layer on this graph's destination range -> (out, upd or None)."""
+                 want_upd: bool = False, h16=None, out16=None):
+        """One message-passing layer on this graph's destination range -> (out, upd or None).
+
+        `h16` (float16 [N, d], optional) is the fp16 copy of `h` the PREC_F16 contraction gathers from (made
+        inside when absent); `out16` (float16 [local nodes, d], optional) receives the fp16 copy of `out`."""
         dev = self.device
         h, W_msg, W_self, bias = _f32(h), _f32(W_msg), _f32(W_self), _f32(bias)
         ln_w, ln_b = _f32(ln_w), _f32(ln_b)
@@ -252,11 +258,14 @@ class Graph:
         elif out.shape != (self.num_local, d) or not out.is_contiguous() or out.dtype != torch.float32:
             raise RuntimeError("out must be a contiguous float32 [local nodes, d] tensor")
         upd = torch.empty_like(out) if want_upd else None
+        for name, t, rows in (("h16", h16, self.num_nodes), ("out16", out16, self.num_local)):
+            if t is not None and (t.dtype != torch.float16 or t.shape != (rows, d) or not t.is_contiguous()):
+                raise RuntimeError(f"{name} must be a contiguous float16 [{rows},{d}] tensor")
         ws = self.workspace(precision)
         with torch.cuda.device(dev):
-            _check(lib().ghf_mp_layer(self._h, _ptr(h), _ptr(W_msg), _ptr(W_self), _ptr(bias), _ptr(ln_w),
-                                      _ptr(ln_b), float(eps), precision, _ptr(out), _ptr(upd), _ptr(ws),
-                                      _stream(dev)), "ghf_mp_layer")
+            _check(lib().ghf_mp_layer_f16(self._h, _ptr(h), _ptr(h16), _ptr(W_msg), _ptr(W_self), _ptr(bias),
+                                          _ptr(ln_w), _ptr(ln_b), float(eps), precision, _ptr(out), _ptr(out16),
+                                          _ptr(upd), _ptr(ws), _stream(dev)), "ghf_mp_layer_f16")
         return out, upd
 
 

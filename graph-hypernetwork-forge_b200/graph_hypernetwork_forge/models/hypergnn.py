@@ -108,9 +108,11 @@ class HyperGNN(nn.Module):
     """Hypernetwork-conditioned relational GNN (forward pass), B200-native.
 
     ``HyperGNN(text_dim, node_feat_dim, hidden_dim, num_layers=2, dropout=0.0, char_emb_dim=32)``
-    as in the reference.  Extension (keyword-only): ``precision`` - ``"tf32"`` runs the per-edge
-    contraction on tcgen05 tensor cores (hidden_dim 32/64/128), ``"fp32"`` on CUDA cores,
-    ``None``/"auto" picks tf32 when the shape allows (env ``GHF_PRECISION`` overrides).
+    as in the reference.  Extension (keyword-only): ``precision`` - ``"f16"`` gathers an fp16 shadow copy
+    of the node features and runs the per-edge contraction on tcgen05 kind::f16 with fp32 accumulation
+    (hidden_dim 128; same 11-bit operand significand as TF32), ``"tf32"`` runs it on tcgen05 kind::tf32
+    (hidden_dim 32/64/128), ``"fp32"`` on CUDA cores; ``None``/"auto" picks f16, then tf32, then fp32 as
+    the shape allows (env ``GHF_PRECISION`` overrides).
     """
 
     def __init__(self, text_dim: int, node_feat_dim: int, hidden_dim: int, num_layers: int = 2,
@@ -134,7 +136,7 @@ class HyperGNN(nn.Module):
     def _precision_code(self) -> int:
         name = os.environ.get("GHF_PRECISION") or self.precision or "auto"
         if name == "auto":
-            name = "tf32" if self.hidden_dim in (32, 64, 128) else "fp32"
+            name = "f16" if self.hidden_dim == 128 else "tf32" if self.hidden_dim in (32, 64) else "fp32"
         return _native.precision_code(name)
 
     def prepare(self, edge_index: torch.Tensor, edge_texts: List[str], num_nodes: int,
@@ -198,11 +200,16 @@ class HyperGNN(nn.Module):
             if taps is not None:
                 taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
                 taps["in_degree"] = graph.export()["indeg"]
+            h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
             for l in range(self.num_layers):
                 w = self._generate(l, text_embs, packed.num_unique)
                 ln = self.layer_norms[l]
+                out16 = None
+                if prec == _native.PREC_F16 and l + 1 < self.num_layers:
+                    out16 = torch.empty((graph.num_local, self.hidden_dim), dtype=torch.float16, device=h.device)
                 h, upd = graph.mp_layer(h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
-                                        want_upd=taps is not None)
+                                        want_upd=taps is not None, h16=h16, out16=out16)
+                h16 = out16
                 if taps is not None:
                     taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
                     taps[f"upd.{l}"], taps[f"h.{l}"] = upd, h

@@ -24,11 +24,14 @@
 extern "C" {
 #endif
 
-#define GHF_ABI_VERSION 1
+#define GHF_ABI_VERSION 2
 
 /* precision of the relation-typed contraction in ghf_mp_layer */
 #define GHF_PREC_FP32 0 /* CUDA-core FFMA, fp32 end to end (rtol 1e-5 vs reference)          */
 #define GHF_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM (tolerance: DESIGN.md) */
+#define GHF_PREC_F16  2 /* fp16 feature/weight transport with exact power-of-two scaling, tcgen05 kind::f16,
+                           fp32 accumulate in TMEM: the same 11-bit operand significand as TF32 at half the
+                           bytes (hidden_dim 128; tolerance: DESIGN.md)                                  */
 
 int ghf_abi_version(void);
 const char* ghf_last_error(void);
@@ -92,6 +95,18 @@ int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim, int preci
 int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, const float* d_W_self,
                  const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
                  int precision, float* d_out, float* d_upd, void* d_workspace, void* stream);
+
+/* The same layer with the fp16 shadow copy of the node features made explicit (GHF_PREC_F16 chains it from
+ * layer to layer instead of re-converting):
+ *   d_h16     [num_nodes, d] fp16 copy of d_h, or NULL (then it is made inside, in the workspace).  When it is
+ *             given, d_h is only read at rows [dst_lo, dst_hi) (residual), so a multi-GPU caller needs to
+ *             all-gather only the fp16 copy between layers.
+ *   d_out16   [local nodes, d] fp16 copy of d_out for the next layer, or NULL (hidden_dim 32/64/128).
+ * With precision FP32 / TF32 this is ghf_mp_layer plus the optional d_out16. */
+int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_W_msg,
+                     const float* d_W_self, const float* d_bias, const float* d_ln_w, const float* d_ln_b,
+                     float eps, int precision, float* d_out, void* d_out16, float* d_upd, void* d_workspace,
+                     void* stream);
 
 /* ---- whole forward from HOST buffers (HG:236-298): the end-to-end entry point --------------
  * Parameters are passed as one flat array of DEVICE pointers in reference state_dict order

@@ -60,6 +60,18 @@ def test_tf32_path_matches_reference_golden(name):
     assert np.isfinite(out).all()
 
 
+@pytest.mark.parametrize("name", ["synth_d128", "synth_d128_scale1"])
+def test_f16_path_matches_reference_golden(name):
+    """fp16 transport + tcgen05 kind::f16 (fp32 accumulate): same operand significand as TF32, same tolerance."""
+    case = load_case(name)
+    model, out, taps = run_model(case, "f16")
+    ref = case["taps"]
+    assert_rel_to_max(taps["upd.0"], ref["upd.0"], TF32_UPD_REL, "upd.0")
+    atol = TF32_H_ATOL_SCALE1 if case["log_scale"] is not None else TF32_H_ATOL_INIT
+    assert_close(out, ref["out"], 0.0, atol, "out")
+    assert np.isfinite(out).all()
+
+
 def test_forward_call_is_drop_in(toy_kg):
     """model(node_features, edge_index, edge_texts) exactly as the reference is called."""
     case = load_case("toy_c1")
@@ -70,7 +82,8 @@ def test_forward_call_is_drop_in(toy_kg):
 
 
 @pytest.mark.parametrize("N,E,R,d,L,prec", [
-    (3000, 40000, 37, 128, 2, "tf32"), (3000, 40000, 37, 128, 2, "fp32"),
+    (3000, 40000, 37, 128, 2, "tf32"), (3000, 40000, 37, 128, 2, "fp32"), (3000, 40000, 37, 128, 3, "f16"),
+    (20000, 300000, 5, 128, 2, "f16"),
     (5000, 60000, 300, 64, 2, "tf32"), (2000, 30000, 11, 32, 3, "tf32"),
     (1500, 9000, 50, 256, 1, "fp32"), (700, 5000, 9, 48, 2, "fp32"),
 ])

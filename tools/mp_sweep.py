@@ -12,12 +12,17 @@ import bench  # noqa: E402
 from graph_hypernetwork_forge import _native  # noqa: E402
 
 args = sys.argv[1:]
-wl = "c3"
-if args and args[0] == "--workload":
-    wl, args = args[1], args[2:]
+wl, prec_name = "c3", "f16"
+while args and args[0] in ("--workload", "--precision"):
+    if args[0] == "--workload":
+        wl = args[1]
+    else:
+        prec_name = args[1]
+    args = args[2:]
+PREC = _native.precision_code(prec_name)
 w = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
-model = bench.build_model(w, dev, "tf32")
+model = bench.build_model(w, dev, prec_name)
 x, ei, rel, utf8, offsets = bench.make_device_inputs(w, dev)
 h = _native.linear(x, model.input_proj.weight, model.input_proj.bias, relu=True)
 # calibration: device copy bandwidth on this box (read + write bytes), and clocks
@@ -48,13 +53,14 @@ for spec in args or ["0,0,7"]:
     text = model.text_encoder.encode_packed(prepared.packed)
     wts = model.weight_generators[0](text)
     ln = model.layer_norms[0]
+    h16 = h.half() if PREC == _native.PREC_F16 else None   # as chained from the previous layer
     for _ in range(2):
-        g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias, 1e-5, _native.PREC_TF32)
+        g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias, 1e-5, PREC, h16=h16)
     torch.cuda.synchronize()
     _native.profile_enable(True)
     _native.profile_read()
     for _ in range(5):
-        g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias, 1e-5, _native.PREC_TF32)
+        g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias, 1e-5, PREC, h16=h16)
     prof, n = _native.profile_read()
     _native.profile_enable(False)
     print(f"sb={g.sb_nodes:6d} unit={g.unit_edges:5d} flags={flags} fused={os.environ['GHF_MP_FUSED']} "
