@@ -5,11 +5,11 @@
 #include "ghf_b200.h"
 
 namespace ghf {
-// tcgen05 3xTF32 path for K = N = 128 and many rows (linear_umma.cu)
+// tcgen05 3xTF32 path for K = 128, N a multiple of 128 and enough outputs to fill the machine (linear_umma.cu)
 bool linear_umma_eligible(int64_t M, int K, int N, int relu, const void* log_scale, const void* X, const void* W,
                           const void* Y);
-int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int relu, float* Y,
-                       cudaStream_t stream);
+int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int N, int relu,
+                       const float* log_scale, float* Y, cudaStream_t stream);
 namespace {
 
 template <int BN, bool VEC>
@@ -89,7 +89,7 @@ extern "C" int ghf_linear(const float* d_X, int64_t M, int K, const float* d_W, 
   GHF_REQUIRE(cdiv(N, 32) <= 65535, "ghf_linear: N=%d too large", N);
   if (M == 0) return 0;
   if (linear_umma_eligible(M, K, N, relu, d_log_scale, d_X, d_W, d_Y))
-    return linear_umma_launch(d_X, M, d_W, d_b, relu, d_Y, stream);
+    return linear_umma_launch(d_X, M, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
   if (N <= 32) return launch_linear<32>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
   if (N <= 64) return launch_linear<64>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
   return launch_linear<128>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);

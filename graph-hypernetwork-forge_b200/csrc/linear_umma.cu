@@ -1,5 +1,6 @@
-// linear_umma.cu — Y = relu(X W^T + b) for the node-feature projection (HG:261) at K = N = 128 on tcgen05,
-// fp32-grade through a 3 x TF32 split:  x = xh + xl, w = wh + wl  (h = top 19 bits, l = the remainder),
+// linear_umma.cu — Y = alpha * act(X W^T + b) at K = 128 and N a multiple of 128 on tcgen05: the node-feature
+// projection (HG:261, N = 128) and the last Linear of the weight generators (WG:138-140, N = d*d, alpha =
+// exp(log_scale)); blockIdx.y selects the 128-wide block of output features.  fp32-grade through a 3 x TF32 split:  x = xh + xl, w = wh + wl  (h = top 19 bits, l = the remainder),
 //     x.w ~ xh.wh + xl.wh + xh.wl            (the dropped xl.wl term is ~2^-22 relative)
 //
 // Layout mirrors mp_umma_ts.cu.  The transposed tile  Yt[128 n, 128 rows] = W[128 n, 128 k] * Xt  is computed
@@ -39,7 +40,13 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 
 __global__ void __launch_bounds__(kThreads, 1)
 linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __restrict__ W,
-                      const float* __restrict__ bias, int relu, float* __restrict__ Y) {
+                      const float* __restrict__ bias, int relu, const float* __restrict__ log_scale,
+                      float* __restrict__ Y, int64_t ldy) {
+  // this CTA's block of 128 output features: rows [128 y, 128 y + 128) of W, the same columns of Y
+  W += (int64_t)blockIdx.y * kD * kD;
+  Y += (int64_t)blockIdx.y * kD;
+  if (bias) bias += (int64_t)blockIdx.y * kD;
+  const float alpha = log_scale ? expf(*log_scale) : 1.f;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sA = (raw + 1023u) & ~1023u;
@@ -127,7 +134,8 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
           if (row < M) {
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            *reinterpret_cast<float4*>(Y + row * kD + 4 * lane) = v;
+            v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+            *reinterpret_cast<float4*>(Y + row * ldy + 4 * lane) = v;
           }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -217,21 +225,26 @@ bool linear_umma_eligible(int64_t M, int K, int N, int relu, const void* log_sca
                           const void* Y) {
   const char* env = getenv("GHF_LINEAR_UMMA");
   if (env && env[0] == '0') return false;
-  (void)relu;
-  return K == kD && N == kD && log_scale == nullptr && M >= 16384 &&
+  (void)relu; (void)log_scale;
+  // enough work to fill the machine: >= 2^21 outputs (node projection: many rows; generator: many columns)
+  return K == kD && N % kD == 0 && N / kD <= 65535 && M * (int64_t)N >= (1 << 21) && M >= 64 &&
          ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0);
 }
 
-int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int relu, float* Y,
-                       cudaStream_t stream) {
+int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int N, int relu,
+                       const float* log_scale, float* Y, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   const int64_t tiles = (M + kTile - 1) / kTile;
-  const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-  linear128_umma_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(X, M, W, b, relu, Y);
+  const int nblocks = N / kD;
+  // persistent over row tiles within a feature block: about one CTA per SM in total
+  int64_t gx = (sm_count() + nblocks - 1) / nblocks;
+  gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
+  linear128_umma_kernel<<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(X, M, W, b, relu,
+                                                                                          log_scale, Y, (int64_t)N);
   GHF_LAUNCH_CHECK();
   return 0;
 }

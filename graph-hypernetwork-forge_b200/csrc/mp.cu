@@ -308,8 +308,9 @@ extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim
   // unfused paths accumulate in scratch; the fused tf32 path accumulates in the output rows
   int64_t bytes = 256 /* work counter */ + (fused ? 0 : align_up(g->num_local * (int64_t)hidden_dim * 4, 256));
   if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim) + mp_umma_sync_bytes(g);
-  if (precision == GHF_PREC_F16)  // weight images + the fp16 copy of h made when the caller passes none
-    bytes += mp_f16_pack_bytes(g->num_rel) + align_up(g->num_nodes * (int64_t)hidden_dim * 2, 256);
+  if (precision == GHF_PREC_F16)  // sync words, weight images, the fp16 copy of h made when the caller passes none
+    bytes += mp_f16_sync_bytes(g) + mp_f16_pack_bytes(g->num_rel) +
+             align_up(g->num_nodes * (int64_t)hidden_dim * 2, 256);
   return bytes + 256;
 }
 
@@ -388,8 +389,11 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     return 0;
   }
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
+  // (the f16 kernel clears the accumulator itself and keeps per-phase sync words next to the counter)
+  const bool self_clearing = precision == GHF_PREC_F16 && g->num_units > 0;
   int* counter = reinterpret_cast<int*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
-  float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) + 256);
+  float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) +
+                                        (precision == GHF_PREC_F16 ? mp_f16_sync_bytes(g) : 256));
   const int64_t acc_bytes = align_up(nl * (int64_t)d * 4, 256);
   void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
   ProfRec rec{};
@@ -398,7 +402,9 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
     GHF_CUDA(cudaEventRecord(rec.e[0], stream));
   }
-  GHF_CUDA(cudaMemsetAsync(counter, 0, 256 + nl * (size_t)d * 4, stream));
+  if (!self_clearing)
+    GHF_CUDA(cudaMemsetAsync(counter, 0, (reinterpret_cast<char*>(acc) - reinterpret_cast<char*>(counter)) +
+                                             nl * (size_t)d * 4, stream));
   const bool ts = mp_ts_enabled(d);
   const void* h16 = d_h16;
   if (precision == GHF_PREC_TF32 && g->num_units > 0) {
@@ -440,6 +446,12 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     g_prof.push_back(rec);
   }
   return 0;
+}
+
+extern "C" int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, void* stream_) {
+  GHF_REQUIRE(elems >= 0 && (d_x != nullptr || elems == 0) && (d_y16 != nullptr || elems == 0),
+              "ghf_convert_f16: bad arguments");
+  return mp_f16_convert(d_x, elems, d_y16, (cudaStream_t)stream_);
 }
 
 extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, const float* d_W_self,

@@ -43,8 +43,10 @@ int64_t mp_f16_pack_bytes(int num_rel);
 int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream);
 // h16[i] = fp16(h[i]) for `elems` values (a multiple of 8)
 int mp_f16_convert(const float* h, int64_t elems, void* h16, cudaStream_t stream);
-// acc[dst_local, :] += sum over edges of [h16_src | h16_dst] @ [W_msg; W_self][rel] + bias[rel]; h16 is [N, 128] fp16
+// acc[dst_local, :] = sum over edges of [h16_src | h16_dst] @ [W_msg; W_self][rel] + bias[rel]; h16 is [N, 128] fp16.
+// The kernel clears acc itself (every local row, also those without in-edges).  sync_words: mp_f16_sync_bytes(g).
+int64_t mp_f16_sync_bytes(const ghf_graph* g);
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* bias, float* acc, const void* pack_scratch,
-                  int* unit_counter, cudaStream_t stream);
+                  int* sync_words, cudaStream_t stream);
 
 }  // namespace ghf

@@ -34,6 +34,7 @@
 
 #include "common.cuh"
 #include "mp.cuh"
+#include "mp_fuse.cuh"
 #include "umma.cuh"
 
 namespace ghf {
@@ -48,11 +49,11 @@ constexpr int kSub = kTile * 128;          // 128 rows x 128 B (64 halfs of K): 
 constexpr int kStageBytes = 2 * kSub;      // the src halves (K 0..127) or the dst halves (K 128..255) of a tile
 constexpr int kStages = 7;                 // 224 KiB ring = 3.5 tiles of gathers in flight
 constexpr int kQueue = 16;                 // tile descriptors between the scheduler and the other roles
-constexpr int kEpiWarps = 16, kProdWarps = 4, kLoadWarps = 4;
-constexpr int kWarpProd = kEpiWarps, kWarpMma = kWarpProd + kProdWarps, kWarpSched = kWarpMma + 1,
-              kWarpLoad = kWarpSched + 1;
-constexpr int kThreads = 32 * (kWarpLoad + kLoadWarps);
-constexpr int kConsumers = kEpiWarps + kProdWarps + 1 + kLoadWarps;   // warps that read every descriptor
+constexpr int kEpiWarps = 16, kLoadWarps = 4;
+// warp layout: [epilogue 16][weight loaders 4][MMA][scheduler][producers P]  (P = 4 or 8, template parameter)
+constexpr int kWarpLoad = kEpiWarps, kWarpMma = kWarpLoad + kLoadWarps, kWarpSched = kWarpMma + 1,
+              kWarpProd = kWarpSched + 1;
+constexpr int threads_for(int prod_warps) { return 32 * (kWarpProd + prod_warps); }
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kWCol = 256;            // first TMEM column of the weight buffers (2 x 128 columns)
 constexpr int kImageBytes = kD * 2 * kD * 2;   // one relation's Wt image: 128 x 256 fp16 = 64 KiB
@@ -155,13 +156,15 @@ to_f16_kernel(const float* __restrict__ h, int64_t n8, __half* __restrict__ h16)
   reinterpret_cast<uint4*>(h16)[i] = o;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kProdWarps>
+__global__ void __launch_bounds__(threads_for(kProdWarps), 1)
 mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
               const int32_t* __restrict__ unit_rel, int64_t num_units, const int32_t* __restrict__ src_sorted,
               const int32_t* __restrict__ dst_sorted, const __half* __restrict__ h16, int64_t dst_lo,
               const __half* __restrict__ wpack, const float* __restrict__ w_inv_scale,
               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter,
-              uint32_t flags) {
+              const int32_t* __restrict__ unit_phase, int* __restrict__ zero_done, int num_phases, int sb_nodes,
+              int64_t num_local, uint32_t flags) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sA = (raw + 1023u) & ~1023u;
@@ -181,6 +184,8 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int kConsumers = kEpiWarps + kProdWarps + 1 + kLoadWarps;   // warps that read every descriptor
+  constexpr int kRowsPerWarp = kTile / kProdWarps;                      // 32 or 16
 
   // tile-descriptor queue (consumer side).  acquire() blocks until descriptor `idx` is published and returns it
   // {x = first sorted edge (-1: no more work), y = rows, z = relation, w = flags}; release() frees the slot once
@@ -220,7 +225,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp < kWarpProd) {
+  if (warp < kEpiWarps) {
     // ------------------------------------------------------------------ epilogue: Dt -> red.f32 rows
     const int grp = warp >> 2, q = warp & 3;
     const int col = 32 * q + lane;                       // this thread's output column = its TMEM lane
@@ -265,10 +270,10 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       cur = nxt;
       cr = nr;
     }
-  } else if (warp < kWarpMma) {
+  } else if (warp >= kWarpProd) {
     // ------------------------------------------------------------------ row-gather producers
-    // Warp pw owns rows [32 pw, 32 pw + 32) of every tile: lane l keeps the source and destination id of row
-    // 32 pw + l.  One cp.async instruction moves two 256 B rows (16 lanes x 16 B each).
+    // Warp pw owns kRowsPerWarp consecutive rows of every tile; lane l keeps the source and destination id of
+    // its row l % kRowsPerWarp.  One cp.async instruction moves two 256 B rows (16 lanes x 16 B each).
     const int pw = warp - kWarpProd;
     const int l16 = lane & 15, hi = lane >> 4;
     const uint64_t pol_src = (flags & kFlagSrcEvictFirst) ? policy_evict_first() : policy_evict_normal();
@@ -276,7 +281,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
     const uint8_t* hb = reinterpret_cast<const uint8_t*>(h16) + l16 * 16;
     struct Ids { int64_t src, dst; };
     auto ids_of = [&](const int4& t) -> Ids {
-      const int row = 32 * pw + lane;
+      const int row = kRowsPerWarp * pw + lane % kRowsPerWarp;
       if (t.x < 0 || row >= t.y) return Ids{-1, -1};
       return Ids{(int64_t)src_sorted[t.x + row], dst_lo + dst_sorted[t.x + row]};
     };
@@ -295,10 +300,10 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
         const int64_t mine = s ? ids.dst : ids.src;
         if (!(flags & kDbgNoGather)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int rl = 2 * i + hi;                   // row within the warp's 32
+          for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+            const int rl = 2 * i + hi;                   // row within the warp's share
             const int64_t idx = __shfl_sync(0xffffffffu, mine, rl);
-            const int row = 32 * pw + rl;
+            const int row = kRowsPerWarp * pw + rl;
             const uint32_t to = base + row * 128 + (((l16 & 7) ^ (row & 7)) << 4);
             if (idx >= 0) cp_async_16_hint(to, hb + idx * kRowBytes, pol);
           }
@@ -355,38 +360,69 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       }
     }
   } else if (warp == kWarpSched) {
-    // ------------------------------------------------------------------ scheduler
-    if (lane == 0) {
-      uint32_t qi = 0, wb = 0;
-      auto publish = [&](int start, int rows, int rel, uint32_t tf) {
+    // ------------------------------------------------------------------ scheduler (+ accumulator clearing)
+    // The accumulator rows of super-block ("phase") p are zeroed INSIDE this kernel, one phase ahead of their
+    // first reduction: every CTA clears its 1/gridDim share of phase p + 1 when it first draws a unit of phase p,
+    // and no unit of phase p is published before all shares of p are in (zero_done[p] == gridDim.x).  The zero
+    // lines are created in L2 by full-line stores, so the reductions never fetch accumulator lines from HBM and
+    // there is no separate 1.28 GB clear pass.  (All CTAs are co-resident: 1 CTA / SM, grid <= SM count.)
+    uint32_t qi = 0, wb = 0;
+    int my_zeroed = -1, ready_phase = -1;
+    auto publish = [&](int start, int rows, int rel, uint32_t tf) {
+      if (lane == 0) {
         mbar_wait(q_empty0 + 8u * (qi % kQueue), ((qi / kQueue) & 1u) ^ 1u);
         volatile int4* p = q_ptr + (qi % kQueue);
         p->x = start; p->y = rows; p->z = rel; p->w = (int)tf;
         mbar_arrive(q_full0 + 8u * (qi % kQueue));       // release: the descriptor is visible to the waiters
-        ++qi;
-      };
-      int64_t u = atomicAdd(unit_counter, 1);
-      while (u < num_units) {
-        const int start = unit_start[u], count = unit_count[u], rel = unit_rel[u];
-        const int64_t u_next = atomicAdd(unit_counter, 1);   // its latency hides behind the tiles published below
-        for (int t0 = 0; t0 < count; t0 += kTile) {
-          const uint32_t tf = (t0 == 0 ? kTileFirst : 0u) | (t0 + kTile >= count ? kTileLast : 0u) |
-                              (wb ? kTileWbuf : 0u);
-          publish(start + t0, min(kTile, count - t0), rel, tf);
-        }
-        wb ^= 1u;
-        u = u_next;
       }
-      publish(-1, 0, 0, 0);
-      publish(-1, 0, 0, 0);                              // the producers look one descriptor ahead
+      ++qi;
+    };
+    auto draw = [&]() -> int64_t {
+      int v = 0;
+      if (lane == 0) v = atomicAdd(unit_counter, 1);
+      return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+    };
+    auto clear_share = [&](int p) {
+      const int64_t lo = (int64_t)p * sb_nodes;
+      const int64_t hi = min(lo + (int64_t)sb_nodes, num_local);
+      const int64_t share = (hi - lo + gridDim.x - 1) / gridDim.x;
+      const int64_t r0 = lo + (int64_t)blockIdx.x * share, r1 = min(hi, r0 + share);
+      float4* row = reinterpret_cast<float4*>(acc) + lane;
+      for (int64_t r = r0; r < r1; ++r) row[r * (kD / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(&zero_done[p], 1);
+      }
+    };
+    int64_t u = draw();
+    while (u < num_units) {
+      const int start = unit_start[u], count = unit_count[u], rel = unit_rel[u], ph = unit_phase[u];
+      const int64_t u_next = draw();                     // its latency hides behind the work below
+      const int ahead = min(ph + 1, num_phases - 1);
+      while (my_zeroed < ahead) clear_share(++my_zeroed);
+      if (ph != ready_phase) {
+        if (lane == 0) fuse::spin_until_at_least(&zero_done[ph], (int)gridDim.x);
+        __syncwarp();
+        ready_phase = ph;
+      }
+      for (int t0 = 0; t0 < count; t0 += kTile) {
+        const uint32_t tf = (t0 == 0 ? kTileFirst : 0u) | (t0 + kTile >= count ? kTileLast : 0u) |
+                            (wb ? kTileWbuf : 0u);
+        publish(start + t0, min(kTile, count - t0), rel, tf);
+      }
+      wb ^= 1u;
+      u = u_next;
     }
-  } else {
+    while (my_zeroed < num_phases - 1) clear_share(++my_zeroed);   // rows without in-edges are cleared too
+    publish(-1, 0, 0, 0);
+    publish(-1, 0, 0, 0);                                // producers and epilogue look one descriptor ahead
+  } else if (warp >= kWarpLoad && warp < kWarpMma) {
     // ------------------------------------------------------------------ weight loaders: Wt_r -> TMEM
     // thread = output column n = 32 * quarter + lane = TMEM lane; 128 columns (256 k) in 4 pieces of 32
     const int quarter = warp & 3;   // a warp reaches TMEM lanes [32 (warp % 4), +32) only
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + kWCol;
     const uint64_t pol_w = (flags & kFlagWEvictLast) ? policy_evict_last() : policy_evict_normal();
-    (void)pol_w;
     uint32_t eph = 0;                                    // bit b: parity of the next w_empty(b) wait
     for (uint32_t it = 0;; ++it) {
       const int4 t = q_acquire(it);
@@ -401,7 +437,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       auto fetch = [&](int piece) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint4 v = ldg_nc_v4(img + piece * (4 * 8 * 32 * 16) + j * (32 * 16));
+          const uint4 v = ldg_v4_hint(img + piece * (4 * 8 * 32 * 16) + j * (32 * 16), pol_w);
           r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
         }
       };
@@ -435,6 +471,8 @@ uint32_t env_flags() {
 
 bool mp_f16_supported(int d) { return d == kD; }
 
+int64_t mp_f16_sync_bytes(const ghf_graph* g) { return align_up(256 + g->num_phases * 4, 256); }
+
 int64_t mp_f16_pack_bytes(int num_rel) {
   return align_up((int64_t)num_rel * kImageBytes, 256) + align_up((int64_t)num_rel * 4, 256);
 }
@@ -464,7 +502,7 @@ int mp_f16_convert(const float* h, int64_t elems, void* h16, cudaStream_t stream
 }
 
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* bias, float* acc, const void* pack_scratch,
-                  int* unit_counter, cudaStream_t stream) {
+                  int* sync_words, cudaStream_t stream) {
   GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
   GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_f16: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(h16) | reinterpret_cast<uintptr_t>(acc) |
@@ -472,16 +510,30 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* bias, float*
               "mp_f16: h16 / acc / scratch must be 16-byte aligned");
   static bool configured = false;
   if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
+  const char* penv = getenv("GHF_F16_PROD");
+  const int prod = penv ? atoi(penv) : 8;
   const __half* img = reinterpret_cast<const __half*>(pack_scratch);
   const float* inv = reinterpret_cast<const float*>(reinterpret_cast<const char*>(pack_scratch) +
                                                     align_up((int64_t)g->num_rel * kImageBytes, 256));
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
-  mp_f16_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(
-      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
-      reinterpret_cast<const __half*>(h16), g->dst_lo, img, inv, bias, acc, unit_counter, env_flags());
+  // sync words (zero at launch): [0] unit counter, [64 + p] cleared shares of phase p
+  GHF_CUDA(cudaMemsetAsync(sync_words, 0, mp_f16_sync_bytes(g), stream));
+  int* unit_counter = sync_words;
+  int* zero_done = sync_words + 64;
+  if (prod == 8)
+    mp_f16_kernel<8><<<(unsigned)grid, threads_for(8), kSmem, stream>>>(
+        g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
+        reinterpret_cast<const __half*>(h16), g->dst_lo, img, inv, bias, acc, unit_counter, g->unit_phase, zero_done,
+        (int)g->num_phases, g->sb_nodes, g->num_local, env_flags());
+  else
+    mp_f16_kernel<4><<<(unsigned)grid, threads_for(4), kSmem, stream>>>(
+        g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
+        reinterpret_cast<const __half*>(h16), g->dst_lo, img, inv, bias, acc, unit_counter, g->unit_phase, zero_done,
+        (int)g->num_phases, g->sb_nodes, g->num_local, env_flags());
   GHF_LAUNCH_CHECK();
   return 0;
 }

@@ -202,6 +202,15 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return v;
 }
 
+// 16-byte load through L2 with an eviction-priority policy (data shared by every CTA: generated weights)
+__device__ __forceinline__ uint4 ldg_v4_hint(const void* p, uint64_t policy) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(policy));
+  return v;
+}
+
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 //   rows are 128 B apart, 8-row groups 1024 B apart (SBO), 16-byte chunk c of row r sits at chunk c ^ (r & 7).
 //   bits [0,14) addr>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1

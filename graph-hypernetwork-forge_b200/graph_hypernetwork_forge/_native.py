@@ -60,6 +60,7 @@ def lib():
         "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
         "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P]),
+        "ghf_convert_f16": (c_int, [P, c_int64, P, P]),
         "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
                                               c_int64, P, P, P, P]),
         "ghf_launch_count": (c_int64, [c_int]),
@@ -79,7 +80,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_text_encode", "ghf_linear",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -157,6 +158,18 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_
         _check(lib().ghf_linear(_ptr(x), M, K, _ptr(weight), _ptr(bias), N, int(relu), _ptr(log_scale), _ptr(y),
                                 _stream(dev)), "ghf_linear")
     return y
+
+
+def to_f16(x: torch.Tensor, out=None) -> torch.Tensor:
+    """fp16 copy of a float32 CUDA tensor (numel % 8 == 0): the shadow of h the PREC_F16 contraction gathers."""
+    x = _f32(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    elif out.dtype != torch.float16 or out.shape != x.shape or not out.is_contiguous():
+        raise RuntimeError("to_f16: out must be a contiguous float16 tensor of the same shape")
+    with torch.cuda.device(x.device):
+        _check(lib().ghf_convert_f16(_ptr(x), x.numel(), _ptr(out), _stream(x.device)), "ghf_convert_f16")
+    return out
 
 
 def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor):

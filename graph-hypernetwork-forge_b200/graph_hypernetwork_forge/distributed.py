@@ -55,6 +55,12 @@ class ShardedForward:
             self._bufs = [torch.zeros(shape, dtype=torch.float32, device=device) for _ in range(2)]
         return self._bufs
 
+    def _buffers16(self, device, d):
+        if getattr(self, "_bufs16", None) is None:
+            shape = (self.rows * self.world, d)
+            self._bufs16 = [torch.zeros(shape, dtype=torch.float16, device=device) for _ in range(2)]
+        return self._bufs16
+
     def forward_packed(self, node_features, edge_index, utf8, offsets) -> torch.Tensor:
         prepared = self.model.prepare_packed(edge_index, utf8, offsets, self.num_nodes, dst_range=(self.lo, self.hi))
         return self.forward_prepared(node_features, prepared)
@@ -72,6 +78,8 @@ class ShardedForward:
         N, d = self.num_nodes, m.hidden_dim
         prec = m._precision_code()
         cur, nxt = self._buffers(node_features.device, d)
+        if prec == _native.PREC_F16:
+            return self._forward_f16(node_features, graph, packed, cur, nxt)
         with torch.no_grad():
             # every rank projects all nodes (h is needed in full as the gather source)
             cur[:N] = _native.linear(node_features, m.input_proj.weight, m.input_proj.bias, relu=True)
@@ -86,4 +94,31 @@ class ShardedForward:
                 gather_rows(nxt, self.rows, self.rank, self.group)
                 cur, nxt = nxt, cur
         self._bufs = [cur, nxt]
+        return cur[:N]
+
+    def _forward_f16(self, node_features, graph, packed, cur, nxt) -> torch.Tensor:
+        """PREC_F16: a rank needs fp32 h only for its own rows (residual), and the fp16 shadow of h in full (gather
+        source).  So every rank projects only its own rows, and what travels between layers is the fp16 copy -
+        half the all-gather bytes; the fp32 rows are gathered once, after the last layer, for the return value."""
+        from . import _native
+        m = self.model
+        N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
+        cur16, nxt16 = self._buffers16(node_features.device, d)
+        with torch.no_grad():
+            if hi > lo:
+                cur[lo:hi] = _native.linear(node_features[lo:hi], m.input_proj.weight, m.input_proj.bias, relu=True)
+                _native.to_f16(cur[lo:hi], out=cur16[lo:hi])
+            gather_rows(cur16, self.rows, self.rank, self.group)
+            text_embs = m.text_encoder.encode_packed(packed)
+            for l in range(m.num_layers):
+                w = m._generate(l, text_embs, packed.num_unique)
+                ln = m.layer_norms[l]
+                last = l + 1 == m.num_layers
+                if hi > lo:
+                    graph.mp_layer(cur[:N], w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps,
+                                   _native.PREC_F16, out=nxt[lo:hi], h16=cur16[:N],
+                                   out16=None if last else nxt16[lo:hi])
+                gather_rows(nxt if last else nxt16, self.rows, self.rank, self.group)
+                cur, nxt, cur16, nxt16 = nxt, cur, nxt16, cur16
+        self._bufs, self._bufs16 = [cur, nxt], [cur16, nxt16]
         return cur[:N]

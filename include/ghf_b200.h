@@ -108,6 +108,10 @@ int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, co
                      float eps, int precision, float* d_out, void* d_out16, float* d_upd, void* d_workspace,
                      void* stream);
 
+/* d_y16[i] = fp16(d_x[i]) (round to nearest even) for `elems` values; elems % 8 == 0, 16-byte aligned pointers.
+ * The fp16 shadow copy of h that GHF_PREC_F16 gathers from (layer 0; later layers get it from d_out16). */
+int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, void* stream);
+
 /* ---- whole forward from HOST buffers (HG:236-298): the end-to-end entry point --------------
  * Parameters are passed as one flat array of DEVICE pointers in reference state_dict order
  * (see INTEGRATION.md for the exact list); inputs and output are HOST

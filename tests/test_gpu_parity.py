@@ -222,3 +222,19 @@ def test_linear_tcgen05_3xtf32_is_fp32_grade(M, relu):
     got = _native.linear(torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV), torch.from_numpy(b).to(DEV),
                          relu=relu).cpu().numpy()
     assert_close(got, want, FP32_RTOL, 2e-6 * float(np.abs(want).max()), "linear 3xTF32")
+
+
+@pytest.mark.parametrize("M,N", [(535, 16384), (200, 16384), (1000, 2048)])
+def test_linear_tcgen05_generator_shape(M, N):
+    """The weight generators' last Linear (WG:138-140): few rows, d*d output features, exp(log_scale) in the
+    epilogue - tcgen05 3xTF32 with blockIdx.y walking the 128-wide feature blocks; fp32 tolerance."""
+    from graph_hypernetwork_forge import _native
+    rng = np.random.default_rng(N + M)
+    x = np.maximum(rng.standard_normal((M, 128)), 0).astype(np.float32)
+    w = (rng.standard_normal((N, 128)) * 0.01).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.01).astype(np.float32)
+    ls = np.array([np.log(0.01)], dtype=np.float32)
+    want = (x.astype(np.float64) @ w.astype(np.float64).T + b) * np.exp(np.float64(ls[0]))
+    got = _native.linear(torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV), torch.from_numpy(b).to(DEV),
+                         relu=False, log_scale=torch.from_numpy(ls).to(DEV)).cpu().numpy()
+    assert_close(got, want, FP32_RTOL, 2e-6 * float(np.abs(want).max()), "generator linear 3xTF32")

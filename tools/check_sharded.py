@@ -1,0 +1,40 @@
+"""Multi-GPU parity: ShardedForward (dst-range partition + all-gather) against the single-GPU forward.
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_sharded.py
+Exits non-zero on mismatch.  GPU box only."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "graph-hypernetwork-forge_b200")]
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import bench  # noqa: E402
+from graph_hypernetwork_forge.distributed import ShardedForward  # noqa: E402
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+dev = torch.device(f"cuda:{local}")
+torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+rank, world = dist.get_rank(), dist.get_world_size()
+w = dict(bench.WORKLOADS["c3"], N=200_003, E=1_300_000, R=61, L=3)   # N not divisible by the world size
+ok = True
+for prec, tol in (("f16", 2e-3), ("tf32", 2e-3), ("fp32", 1e-4)):
+    model = bench.build_model(w, dev, prec)
+    with torch.no_grad():                      # O(1) generated weights so that the update matters
+        for gen in model.weight_generators:
+            for p in gen.log_scales.values():
+                p.fill_(-1.5)
+    x, ei, _rel, utf8, offsets = bench.make_device_inputs(w, dev)
+    single = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, w["N"]))
+    sharded = ShardedForward(model, w["N"], dist.group.WORLD).forward_packed(x, ei, utf8, offsets)
+    err = float((single - sharded).abs().max())
+    kept = torch.tensor([ShardedForward(model, w["N"], dist.group.WORLD).num_kept], device=dev)
+    if rank == 0:
+        print(f"{prec}: world {world}  max|single - sharded| = {err:.3e}  (tol {tol:g}; atomics reorder the sums)",
+              flush=True)
+    ok = ok and err <= tol and bool(torch.isfinite(sharded).all())
+flag = torch.tensor([0 if ok else 1], device=dev)
+dist.all_reduce(flag)
+dist.destroy_process_group()
+sys.exit(int(flag.item() != 0))

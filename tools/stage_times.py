@@ -14,7 +14,8 @@ from graph_hypernetwork_forge.models.hypergnn import PackedTexts  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
 w = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
-model = bench.build_model(w, dev, "tf32")
+model = bench.build_model(w, dev, "f16" if w["d"] == 128 else "tf32")
+PREC = _native.precision_code("f16" if w["d"] == 128 else "tf32")
 x, ei, rel, utf8, offsets = bench.make_device_inputs(w, dev)
 
 
@@ -37,7 +38,7 @@ for it in range(6):
         wts = timed("weight_gen", lambda: model.weight_generators[l](text), acc)
         ln = model.layer_norms[l]
         h = timed("mp_layer", lambda: g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias,
-                                                 1e-5, _native.PREC_TF32)[0], acc)
+                                                 1e-5, PREC)[0], acc)
     timed("graph_free", lambda: g.__del__(), acc)
     t0 = time.perf_counter()
     out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, w["N"]))
