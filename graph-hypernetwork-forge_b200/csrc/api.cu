@@ -97,7 +97,9 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
   }
 
   const int64_t text_bytes = E > 0 ? h_offsets[E] : 0;
-  TempBuf x, ei, utf8, offs, rel, first, h0, h1, temb;
+  const bool want_f16 = desc->precision == GHF_PREC_F16 && d == 128;
+  TempBuf x, ei, utf8, offs, rel, first, h0, h1, temb, h16_0;
+  if (want_f16) GHF_CUDA(h16_0.alloc(num_nodes * (size_t)d * 2, stream));   // fp16 shadow of h0 (h16_0.p stays NULL otherwise)
   GHF_CUDA(x.alloc(num_nodes * (size_t)F * 4, stream));
   GHF_CUDA(ei.alloc(2 * E * sizeof(int64_t), stream));
   GHF_CUDA(utf8.alloc(text_bytes, stream));
@@ -112,11 +114,12 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
   GHF_CUDA(cudaMemcpyAsync(offs.p, h_offsets, (E + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
 
   // HG:261  h = relu(input_proj(x))
-  if (int rc = ghf_linear(x.as<float>(), num_nodes, F, Win, bin, d, 1, nullptr, h0.as<float>(), stream)) return rc;
+  if (int rc = ghf_linear_f16out(x.as<float>(), num_nodes, F, Win, bin, d, 1, nullptr, h0.as<float>(), h16_0.p, stream))
+    return rc;
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
-  if (int rc = ghf_dedup_texts(utf8.as<uint8_t>(), offs.as<int64_t>(), E, rel.as<int32_t>(), first.as<int64_t>(),
-                               &U, stream))
+  if (int rc = ghf_dedup_texts(utf8.as<uint8_t>(), offs.as<int64_t>(), E, nullptr, 0, rel.as<int32_t>(),
+                               first.as<int64_t>(), &U, stream))
     return rc;
   GHF_CUDA(temb.alloc((U > 0 ? U : 1) * (size_t)T * 4, stream));
   if (int rc = ghf_text_encode(utf8.as<uint8_t>(), offs.as<int64_t>(), first.as<int64_t>(), U, emb, C, Wp, bp, T,
@@ -124,8 +127,8 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
     return rc;
 
   ghf_graph* g = nullptr;
-  if (int rc = ghf_graph_build(ei.as<int64_t>(), rel.as<int32_t>(), E, num_nodes, (int32_t)(U > 0 ? U : 1), d, 0,
-                               num_nodes, 0, 0, &g, stream))
+  if (int rc = ghf_graph_build(ei.as<int64_t>(), E, nullptr, 0, rel.as<int32_t>(), num_nodes,
+                               (int32_t)(U > 0 ? U : 1), d, 0, num_nodes, 0, 0, &g, stream))
     return rc;
   struct Guard {
     ghf_graph* g;
@@ -136,11 +139,9 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
                    : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
                                                                                            : GHF_PREC_FP32;
   const int64_t Un = U > 0 ? U : 1;
-  TempBuf wmsg, wself, wbias, hid_a, hid_b, ws, h16a, h16b;
-  if (prec == GHF_PREC_F16) {  // fp16 shadow copies of the layer outputs (the first layer converts h0 inside)
+  TempBuf wmsg, wself, wbias, hid_a, hid_b, ws, h16a;
+  if (prec == GHF_PREC_F16)  // second fp16 shadow buffer: layer outputs ping-pong between h16_0 and h16a
     GHF_CUDA(h16a.alloc(num_nodes * (size_t)d * 2, stream));
-    GHF_CUDA(h16b.alloc(num_nodes * (size_t)d * 2, stream));
-  }
   GHF_CUDA(wmsg.alloc(Un * (size_t)d * d * 4, stream));
   GHF_CUDA(wself.alloc(Un * (size_t)d * d * 4, stream));
   GHF_CUDA(wbias.alloc(Un * (size_t)d * 4, stream));
@@ -152,7 +153,7 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
 
   float* cur = h0.as<float>();
   float* nxt = h1.as<float>();
-  void* cur16 = nullptr;   // fp16 copy of `cur` (NULL: the layer makes one)
+  void* cur16 = prec == GHF_PREC_F16 ? h16_0.p : nullptr;   // fp16 copy of `cur`
   void* nxt16 = h16a.p;
   for (int l = 0; l < L; ++l) {
     // WG:137-141 for the U distinct relations
@@ -177,7 +178,7 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
       return rc;
     float* t = cur; cur = nxt; nxt = t;
     cur16 = out16;
-    nxt16 = (nxt16 == h16a.p) ? h16b.p : h16a.p;
+    nxt16 = (nxt16 == h16a.p) ? h16_0.p : h16a.p;
   }
   GHF_CUDA(cudaMemcpyAsync(h_out, cur, num_nodes * (size_t)d * 4, cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaStreamSynchronize(stream));

@@ -7,6 +7,8 @@
 // the h[dst] gathers stay on chip).  Integer results are bit-exact with oracle.edge_order().
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include "common.cuh"
@@ -19,32 +21,50 @@ namespace {
 struct ToI64 {
   __host__ __device__ int64_t operator()(int32_t v) const { return (int64_t)v; }
 };
-struct MaxOp {
-  __host__ __device__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+// edges of a (super-block, relation) group -> work units of that group
+struct UnitsOf {
+  int32_t unit_edges;
+  __host__ __device__ int32_t operator()(int32_t count) const { return (count + unit_edges - 1) / unit_edges; }
 };
 
-__global__ void keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
-                            const int32_t* __restrict__ rel, int64_t E, int64_t dst_lo, int64_t dst_hi,
-                            int64_t sb, int64_t R, uint64_t invalid_key, uint64_t* __restrict__ keys,
-                            uint32_t* __restrict__ vals, int32_t* __restrict__ indeg) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= E) return;
+// Sort key of edge e: ((super-block of dst) * R + relation) * sb + dst % sb, or `invalid_key` (sorts last) when the
+// destination lies outside [dst_lo, dst_hi).  Also counts in-degrees and the edges of every (super-block,
+// relation) group, from which the unit table follows without touching the sorted edges again.
+// Work item j is edge `edge_ids[j]` (a pre-selected subset, relation ids indexed by j) or edge j itself.
+template <class Key>
+__global__ void keys_kernel(const int64_t* __restrict__ dst, const int32_t* __restrict__ rel,
+                            const uint32_t* __restrict__ edge_ids, int64_t n, int64_t dst_lo, int64_t dst_hi,
+                            int64_t sb, int64_t R, uint64_t invalid_key, Key* __restrict__ keys,
+                            uint32_t* __restrict__ vals, int32_t* __restrict__ indeg,
+                            int32_t* __restrict__ group_count) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t e = edge_ids ? edge_ids[j] : j;
   const int64_t v = dst[e];
   uint64_t key = invalid_key;
   if (v >= dst_lo && v < dst_hi) {
     const int64_t dl = v - dst_lo;
-    key = (uint64_t)(((dl / sb) * R + rel[e]) * sb + dl % sb);
+    const int64_t grp = (dl / sb) * R + rel[j];
+    key = (uint64_t)(grp * sb + dl % sb);
     atomicAdd(&indeg[dl], 1);
+    atomicAdd(&group_count[grp], 1);
   }
-  keys[e] = key;
-  vals[e] = (uint32_t)e;
+  keys[j] = (Key)key;
+  vals[j] = (uint32_t)e;
 }
 
-// sorted position i -> (perm, src, local dst), plus "i if i starts a (super-block, relation) group"
-__global__ void gather_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+struct InDstRange {
+  const int64_t* dst;
+  int64_t lo, hi;
+  __host__ __device__ bool operator()(uint32_t e) const { return dst[e] >= lo && dst[e] < hi; }
+};
+
+// sorted position i -> (perm, src, local dst)
+template <class Key>
+__global__ void gather_kernel(const Key* __restrict__ keys, const uint32_t* __restrict__ vals,
                               const int64_t* __restrict__ src, int64_t kept, int64_t sb, int64_t R,
                               int64_t* __restrict__ perm, int32_t* __restrict__ src_sorted,
-                              int32_t* __restrict__ dst_sorted, int32_t* __restrict__ gstart_in) {
+                              int32_t* __restrict__ dst_sorted) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= kept) return;
   const uint64_t key = keys[i];
@@ -53,34 +73,31 @@ __global__ void gather_kernel(const uint64_t* __restrict__ keys, const uint32_t*
   perm[i] = e;
   src_sorted[i] = (int32_t)src[e];
   dst_sorted[i] = (int32_t)((g / R) * sb + key % sb);
-  const bool head = (i == 0) || (keys[i - 1] / sb != g);
-  gstart_in[i] = head ? (int32_t)i : 0;
 }
 
-__global__ void unit_flag_kernel(const int32_t* __restrict__ gstart, int64_t kept, int32_t unit_edges,
-                                 int32_t* __restrict__ flag) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < kept) flag[i] = ((int32_t)i - gstart[i]) % unit_edges == 0;
-}
-
-__global__ void unit_fill_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ uidx,
-                                 const uint64_t* __restrict__ keys, int64_t kept, int64_t sb, int64_t R,
-                                 int32_t* __restrict__ unit_start, int32_t* __restrict__ unit_rel,
-                                 int32_t* __restrict__ unit_phase, int32_t* __restrict__ phase_units) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= kept || !flag[i]) return;
-  const int32_t u = uidx[i];
-  const uint64_t g = keys[i] / sb;
-  unit_start[u] = (int32_t)i;
-  unit_rel[u] = (int32_t)(g % R);
-  unit_phase[u] = (int32_t)(g / R);
-  atomicAdd(&phase_units[g / R], 1);
-}
-
-__global__ void unit_count_kernel(const int32_t* __restrict__ unit_start, int64_t units, int64_t kept,
-                                  int32_t* __restrict__ unit_count) {
-  const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (u < units) unit_count[u] = (u + 1 < units ? unit_start[u + 1] : (int32_t)kept) - unit_start[u];
+// one thread per (super-block, relation) group: its units, in order
+__global__ void unit_fill_kernel(const int32_t* __restrict__ group_count, const int32_t* __restrict__ group_start,
+                                 const int32_t* __restrict__ unit_base, int64_t groups, int64_t R,
+                                 int32_t unit_edges, int32_t* __restrict__ unit_start,
+                                 int32_t* __restrict__ unit_count, int32_t* __restrict__ unit_rel,
+                                 int32_t* __restrict__ unit_phase, int32_t* __restrict__ phase_units,
+                                 int32_t* __restrict__ phase_tiles) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  const int32_t cnt = group_count[g];
+  if (cnt == 0) return;
+  const int32_t gs = group_start[g], ub = unit_base[g];
+  const int32_t n = (cnt + unit_edges - 1) / unit_edges;
+  int32_t tiles = 0;
+  for (int32_t j = 0; j < n; ++j) {
+    unit_start[ub + j] = gs + j * unit_edges;
+    unit_count[ub + j] = min(unit_edges, cnt - j * unit_edges);
+    tiles += (min(unit_edges, cnt - j * unit_edges) + 127) / 128;
+    unit_rel[ub + j] = (int32_t)(g % R);
+    unit_phase[ub + j] = (int32_t)(g / R);
+  }
+  atomicAdd(&phase_units[g / R], n);
+  atomicAdd(&phase_tiles[g / R], tiles);
 }
 
 int bits_for(uint64_t v) {
@@ -107,40 +124,50 @@ extern "C" void ghf_graph_free(ghf_graph* g) {
   if (!g) return;
   cudaStream_t s = (cudaStream_t)g->stream;  // the stream that last used the tables
   void* ptrs[] = {g->src_sorted, g->dst_sorted, g->perm, g->indeg, g->rowptr, g->unit_start, g->unit_count,
-                  g->unit_rel, g->unit_phase, g->phase_units};
+                  g->unit_rel, g->unit_phase, g->phase_units, g->phase_tiles};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, s);
   delete g;
 }
 
-static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const int32_t* d_rel_ids,
-                            cudaStream_t stream) {
-  const int64_t E = g->num_edges_in, sb = g->sb_nodes, R = g->num_rel, nl = g->num_local;
+template <class Key>
+static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uint32_t* d_edge_ids, int64_t n_items,
+                            const int32_t* d_rel_ids, cudaStream_t stream) {
+  // E: edges of edge_index (src = edge_index[0..E), dst = edge_index[E..2E)); n: work items (all edges, or the subset)
+  const int64_t E = g->num_edges_in, n = n_items, sb = g->sb_nodes, R = g->num_rel, nl = g->num_local;
   const int threads = 256;
   const int64_t n_sb = cdiv(nl > 0 ? nl : 1, sb);
+  const int64_t groups = n_sb * R;
   const uint64_t invalid_key = (uint64_t)n_sb * R * sb;  // sorts after every valid key
   const int end_bit = bits_for(invalid_key);
+  GHF_REQUIRE(groups < (int64_t)0x7FFFFFFF, "ghf_graph_build: %lld (super-block, relation) groups", (long long)groups);
 
   g->num_phases = n_sb;
   GHF_CUDA(dmalloc(&g->indeg, nl, g));
   GHF_CUDA(dmalloc(&g->rowptr, nl + 1, g));
   GHF_CUDA(dmalloc(&g->phase_units, n_sb, g));
   GHF_CUDA(cudaMemsetAsync(g->phase_units, 0, (size_t)n_sb * sizeof(int32_t), stream));
+  GHF_CUDA(dmalloc(&g->phase_tiles, n_sb, g));
+  GHF_CUDA(cudaMemsetAsync(g->phase_tiles, 0, (size_t)n_sb * sizeof(int32_t), stream));
   GHF_CUDA(cudaMemsetAsync(g->indeg, 0, (size_t)(nl > 0 ? nl : 1) * sizeof(int32_t), stream));
 
-  TempBuf keys_a, keys_b, vals_a, vals_b, tmp;
-  const int64_t En = E > 0 ? E : 1;
-  GHF_CUDA(keys_a.alloc(En * sizeof(uint64_t), stream));
-  GHF_CUDA(keys_b.alloc(En * sizeof(uint64_t), stream));
+  TempBuf keys_a, keys_b, vals_a, vals_b, tmp, gcount, gstart, ubase;
+  const int64_t En = n > 0 ? n : 1;
+  GHF_CUDA(keys_a.alloc(En * sizeof(Key), stream));
+  GHF_CUDA(keys_b.alloc(En * sizeof(Key), stream));
   GHF_CUDA(vals_a.alloc(En * sizeof(uint32_t), stream));
   GHF_CUDA(vals_b.alloc(En * sizeof(uint32_t), stream));
+  GHF_CUDA(gcount.alloc((groups + 1) * sizeof(int32_t), stream));   // one trailing zero: scans yield the totals
+  GHF_CUDA(gstart.alloc((groups + 1) * sizeof(int32_t), stream));
+  GHF_CUDA(ubase.alloc((groups + 1) * sizeof(int32_t), stream));
+  GHF_CUDA(cudaMemsetAsync(gcount.p, 0, (size_t)(groups + 1) * sizeof(int32_t), stream));
 
   const int64_t* src = d_edge_index;
   const int64_t* dst = d_edge_index + E;
-  if (E > 0) {
-    keys_kernel<<<(unsigned)cdiv(E, threads), threads, 0, stream>>>(
-        src, dst, d_rel_ids, E, g->dst_lo, g->dst_hi, sb, R, invalid_key, keys_a.as<uint64_t>(),
-        vals_a.as<uint32_t>(), g->indeg);
+  if (n > 0) {
+    keys_kernel<Key><<<(unsigned)cdiv(n, threads), threads, 0, stream>>>(
+        dst, d_rel_ids, d_edge_ids, n, g->dst_lo, g->dst_hi, sb, R, invalid_key, keys_a.as<Key>(),
+        vals_a.as<uint32_t>(), g->indeg, gcount.as<int32_t>());
     GHF_LAUNCH_CHECK();
   }
   // rowptr[0..local) = exclusive scan of in-degree (int64); rowptr[local] = kept is written below
@@ -153,89 +180,87 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const int
     GHF_CUDA(cub::DeviceScan::ExclusiveSum(t.p, bytes, it, g->rowptr, (int)nl, stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
-  cub::DoubleBuffer<uint64_t> kbuf(keys_a.as<uint64_t>(), keys_b.as<uint64_t>());
+  // group_start = exclusive scan of the group sizes (last entry: kept edges); unit_base likewise over the unit
+  // counts (last entry: number of units)
+  {
+    size_t b1 = 0, b2 = 0;
+    cub::TransformInputIterator<int32_t, UnitsOf, const int32_t*> units_it(gcount.as<int32_t>(),
+                                                                           UnitsOf{g->unit_edges});
+    GHF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b1, gcount.as<int32_t>(), gstart.as<int32_t>(), (int)(groups + 1),
+                                           stream));
+    GHF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, units_it, ubase.as<int32_t>(), (int)(groups + 1), stream));
+    TempBuf t;
+    GHF_CUDA(t.alloc(b1 > b2 ? b1 : b2, stream));
+    GHF_CUDA(cub::DeviceScan::ExclusiveSum(t.p, b1, gcount.as<int32_t>(), gstart.as<int32_t>(), (int)(groups + 1),
+                                           stream));
+    GHF_CUDA(cub::DeviceScan::ExclusiveSum(t.p, b2, units_it, ubase.as<int32_t>(), (int)(groups + 1), stream));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+  }
+  int32_t totals[2] = {0, 0};  // kept edges, units: the one host round trip of the build
+  GHF_CUDA(cudaMemcpyAsync(&totals[0], gstart.as<int32_t>() + groups, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  GHF_CUDA(cudaMemcpyAsync(&totals[1], ubase.as<int32_t>() + groups, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+
+  cub::DoubleBuffer<Key> kbuf(keys_a.as<Key>(), keys_b.as<Key>());
   cub::DoubleBuffer<uint32_t> vbuf(vals_a.as<uint32_t>(), vals_b.as<uint32_t>());
-  if (E > 0) {
+  if (n > 0) {
     size_t bytes = 0;
-    GHF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kbuf, vbuf, (int)E, 0, end_bit, stream));
+    GHF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kbuf, vbuf, (int)n, 0, end_bit, stream));
     GHF_CUDA(tmp.alloc(bytes, stream));
-    GHF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kbuf, vbuf, (int)E, 0, end_bit, stream));
+    GHF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kbuf, vbuf, (int)n, 0, end_bit, stream));
     g_launches.fetch_add((end_bit + 7) / 8 + 2, std::memory_order_relaxed);
   }
-  // kept = sum of in-degrees: last rowptr entry.  rowptr[nl] = rowptr[nl-1] + indeg[nl-1].
-  int64_t tail[2] = {0, 0};
-  int32_t last_deg = 0;
-  if (nl > 0) {
-    GHF_CUDA(cudaMemcpyAsync(&tail[0], g->rowptr + (nl - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    GHF_CUDA(cudaMemcpyAsync(&last_deg, g->indeg + (nl - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  }
   GHF_CUDA(cudaStreamSynchronize(stream));
-  const int64_t kept = tail[0] + last_deg;
+  const int64_t kept = totals[0];
   g->num_kept = kept;
+  g->num_units = totals[1];
   GHF_CUDA(cudaMemcpyAsync(g->rowptr + nl, &g->num_kept, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
 
   GHF_CUDA(dmalloc(&g->src_sorted, kept, g));
   GHF_CUDA(dmalloc(&g->dst_sorted, kept, g));
   GHF_CUDA(dmalloc(&g->perm, kept, g));
-  if (kept == 0) {
-    g->num_units = 0;
-    GHF_CUDA(dmalloc(&g->unit_start, 1, g));
-    GHF_CUDA(dmalloc(&g->unit_count, 1, g));
-    GHF_CUDA(dmalloc(&g->unit_rel, 1, g));
-    GHF_CUDA(dmalloc(&g->unit_phase, 1, g));
-    return 0;
-  }
-  TempBuf gstart, flag, uidx, total;
-  GHF_CUDA(gstart.alloc(kept * sizeof(int32_t), stream));
-  GHF_CUDA(flag.alloc(kept * sizeof(int32_t), stream));
-  GHF_CUDA(uidx.alloc((kept + 1) * sizeof(int32_t), stream));
-  const unsigned kblocks = (unsigned)cdiv(kept, threads);
-  gather_kernel<<<kblocks, threads, 0, stream>>>(kbuf.Current(), vbuf.Current(), src, kept, sb, R, g->perm,
-                                                 g->src_sorted, g->dst_sorted, gstart.as<int32_t>());
-  GHF_LAUNCH_CHECK();
-  {
-    size_t bytes = 0;
-    GHF_CUDA(cub::DeviceScan::InclusiveScan(nullptr, bytes, gstart.as<int32_t>(), gstart.as<int32_t>(), MaxOp(),
-                                            (int)kept, stream));
-    TempBuf t;
-    GHF_CUDA(t.alloc(bytes, stream));
-    GHF_CUDA(cub::DeviceScan::InclusiveScan(t.p, bytes, gstart.as<int32_t>(), gstart.as<int32_t>(), MaxOp(),
-                                            (int)kept, stream));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-  }
-  unit_flag_kernel<<<kblocks, threads, 0, stream>>>(gstart.as<int32_t>(), kept, g->unit_edges, flag.as<int32_t>());
-  GHF_LAUNCH_CHECK();
-  {
-    size_t bytes = 0;
-    GHF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.as<int32_t>(), uidx.as<int32_t>(), (int)kept, stream));
-    TempBuf t;
-    GHF_CUDA(t.alloc(bytes, stream));
-    GHF_CUDA(cub::DeviceScan::ExclusiveSum(t.p, bytes, flag.as<int32_t>(), uidx.as<int32_t>(), (int)kept, stream));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-  }
-  int32_t last_idx = 0, last_flag = 0;
-  GHF_CUDA(cudaMemcpyAsync(&last_idx, uidx.as<int32_t>() + (kept - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  GHF_CUDA(cudaMemcpyAsync(&last_flag, flag.as<int32_t>() + (kept - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  GHF_CUDA(cudaStreamSynchronize(stream));
-  g->num_units = (int64_t)last_idx + last_flag;
   GHF_CUDA(dmalloc(&g->unit_start, g->num_units, g));
   GHF_CUDA(dmalloc(&g->unit_count, g->num_units, g));
   GHF_CUDA(dmalloc(&g->unit_rel, g->num_units, g));
   GHF_CUDA(dmalloc(&g->unit_phase, g->num_units, g));
-  unit_fill_kernel<<<kblocks, threads, 0, stream>>>(flag.as<int32_t>(), uidx.as<int32_t>(), kbuf.Current(), kept, sb,
-                                                    R, g->unit_start, g->unit_rel, g->unit_phase, g->phase_units);
+  if (kept == 0) return 0;
+  gather_kernel<Key><<<(unsigned)cdiv(kept, threads), threads, 0, stream>>>(
+      kbuf.Current(), vbuf.Current(), src, kept, sb, R, g->perm, g->src_sorted, g->dst_sorted);
   GHF_LAUNCH_CHECK();
-  unit_count_kernel<<<(unsigned)cdiv(g->num_units, threads), threads, 0, stream>>>(g->unit_start, g->num_units, kept,
-                                                                                 g->unit_count);
+  unit_fill_kernel<<<(unsigned)cdiv(groups, threads), threads, 0, stream>>>(
+      gcount.as<int32_t>(), gstart.as<int32_t>(), ubase.as<int32_t>(), groups, R, g->unit_edges, g->unit_start,
+      g->unit_count, g->unit_rel, g->unit_phase, g->phase_units, g->phase_tiles);
   GHF_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ghf_graph_build(const int64_t* d_edge_index, const int32_t* d_rel_ids, int64_t E,
-                               int64_t num_nodes, int32_t num_rel, int32_t hidden_dim, int64_t dst_lo,
-                               int64_t dst_hi, int32_t sb_nodes, int32_t unit_edges, ghf_graph** out,
-                               void* stream_) {
+extern "C" int ghf_select_edges(const int64_t* d_edge_index, int64_t E, int64_t dst_lo, int64_t dst_hi,
+                                uint32_t* d_edge_ids, int64_t* h_count, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(E >= 0 && E < (int64_t)0x7FFFFFFF, "ghf_select_edges: E=%lld out of range", (long long)E);
+  GHF_REQUIRE(h_count != nullptr, "ghf_select_edges: h_count is NULL");
+  *h_count = 0;
+  if (E == 0) return 0;
+  TempBuf count, tmp;
+  GHF_CUDA(count.alloc(sizeof(int64_t), stream));
+  cub::CountingInputIterator<uint32_t> ids(0u);
+  InDstRange pred{d_edge_index + E, dst_lo, dst_hi};
+  size_t bytes = 0;
+  GHF_CUDA(cub::DeviceSelect::If(nullptr, bytes, ids, d_edge_ids, count.as<int64_t>(), (int)E, pred, stream));
+  GHF_CUDA(tmp.alloc(bytes, stream));
+  GHF_CUDA(cub::DeviceSelect::If(tmp.p, bytes, ids, d_edge_ids, count.as<int64_t>(), (int)E, pred, stream));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  GHF_CUDA(cudaMemcpyAsync(h_count, count.p, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  GHF_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+extern "C" int ghf_graph_build(const int64_t* d_edge_index, int64_t E, const uint32_t* d_edge_ids, int64_t n_subset,
+                               const int32_t* d_rel_ids, int64_t num_nodes, int32_t num_rel, int32_t hidden_dim,
+                               int64_t dst_lo, int64_t dst_hi, int32_t sb_nodes, int32_t unit_edges,
+                               ghf_graph** out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(d_edge_ids == nullptr || (n_subset >= 0 && n_subset <= E), "ghf_graph_build: bad subset size");
+  const int64_t n_items = d_edge_ids ? n_subset : E;
   GHF_REQUIRE(out != nullptr, "ghf_graph_build: out is NULL");
   GHF_REQUIRE(E >= 0 && E < (int64_t)0x7FFFFFFF, "ghf_graph_build: E=%lld out of range", (long long)E);
   GHF_REQUIRE(num_nodes >= 0 && num_nodes < (int64_t)0x7FFFFFFF, "ghf_graph_build: N=%lld out of range",
@@ -256,7 +281,12 @@ extern "C" int ghf_graph_build(const int64_t* d_edge_index, const int32_t* d_rel
   }
   g->sb_nodes = sb_nodes;
   g->unit_edges = unit_edges > 0 ? unit_edges : 1024;
-  const int rc = graph_build_impl(g, d_edge_index, d_rel_ids, stream);
+  // 32-bit sort keys whenever (super-blocks * relations * sb_nodes) fits: half the radix-sort traffic
+  const uint64_t key_range = (uint64_t)cdiv(g->num_local > 0 ? g->num_local : 1, g->sb_nodes) * g->num_rel *
+                             (uint64_t)g->sb_nodes;
+  const int rc = key_range < 0xFFFFFFFFull
+                     ? graph_build_impl<uint32_t>(g, d_edge_index, d_edge_ids, n_items, d_rel_ids, stream)
+                     : graph_build_impl<uint64_t>(g, d_edge_index, d_edge_ids, n_items, d_rel_ids, stream);
   if (rc != 0) {
     ghf_graph_free(g);
     return rc;

@@ -22,6 +22,7 @@ struct ghf_graph {
   int32_t* unit_rel = nullptr;     // [units] the one relation all its edges share
   int32_t* unit_phase = nullptr;   // [units] super-block ("phase") of the unit's destinations
   int32_t* phase_units = nullptr;  // [phases] number of units per super-block
+  int32_t* phase_tiles = nullptr;  // [phases] number of 128-edge tiles per super-block (sum over its units)
   int64_t num_phases = 0;          // ceil(num_local / sb_nodes), at least 1
   int64_t bytes = 0;
   mutable void* stream = nullptr;  // stream the tables were allocated on / last used on (freed there)

@@ -12,6 +12,8 @@
 // Warp roles (544 threads, 1 CTA / SM, persistent over row tiles):
 //   0-7 epilogue (2 groups; warps 0-3 also load W into TMEM at start) | 8-15 producers (2 groups, alternating
 //   chunks) | 16 MMA issuer + TMEM allocator
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -41,10 +43,11 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 __global__ void __launch_bounds__(kThreads, 1)
 linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __restrict__ W,
                       const float* __restrict__ bias, int relu, const float* __restrict__ log_scale,
-                      float* __restrict__ Y, int64_t ldy) {
+                      float* __restrict__ Y, int64_t ldy, __half* __restrict__ Y16) {
   // this CTA's block of 128 output features: rows [128 y, 128 y + 128) of W, the same columns of Y
   W += (int64_t)blockIdx.y * kD * kD;
   Y += (int64_t)blockIdx.y * kD;
+  if (Y16) Y16 += (int64_t)blockIdx.y * kD;   // optional fp16 copy of Y (same leading dimension)
   if (bias) bias += (int64_t)blockIdx.y * kD;
   const float alpha = log_scale ? expf(*log_scale) : 1.f;
   extern __shared__ uint8_t smem_raw[];
@@ -136,6 +139,11 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
             *reinterpret_cast<float4*>(Y + row * ldy + 4 * lane) = v;
+            if (Y16) {
+              const __half2 p0 = __floats2half2_rn(v.x, v.y), p1 = __floats2half2_rn(v.z, v.w);
+              *reinterpret_cast<uint2*>(Y16 + row * ldy + 4 * lane) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+            }
           }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -232,7 +240,7 @@ bool linear_umma_eligible(int64_t M, int K, int N, int relu, const void* log_sca
 }
 
 int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int N, int relu,
-                       const float* log_scale, float* Y, cudaStream_t stream) {
+                       const float* log_scale, float* Y, void* Y16, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -244,7 +252,8 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
   int64_t gx = (sm_count() + nblocks - 1) / nblocks;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
   linear128_umma_kernel<<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(X, M, W, b, relu,
-                                                                                          log_scale, Y, (int64_t)N);
+                                                                                          log_scale, Y, (int64_t)N,
+                                                                                          reinterpret_cast<__half*>(Y16));
   GHF_LAUNCH_CHECK();
   return 0;
 }

@@ -13,9 +13,40 @@ namespace {
 
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint64_t hash_bytes(const uint8_t* __restrict__ p, int64_t n) {
-  uint64_t h = 0xcbf29ce484222325ull;  // FNV-1a, then a 64-bit finaliser
-  for (int64_t i = 0; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+// Bytes [p, p + 4) of the packed strings as one little-endian word, from aligned 4-byte loads (the read-only
+// path caches them: neighbouring threads hash neighbouring strings).  The caller guarantees p + 4 <= total bytes;
+// `limit` = total rounded down to 4: words that would reach past it are assembled from byte loads.
+__device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ data, int64_t p, int64_t limit) {
+  const int64_t a = p & ~(int64_t)3;
+  if (a + 8 <= limit) {
+    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(data + a));
+    const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>(data + a + 4));
+    return __funnelshift_r(lo, hi, 8 * (int)(p & 3));
+  }
+  uint32_t w = 0;
+  for (int i = 0; i < 4; ++i) w |= (uint32_t)data[p + i] << (8 * i);
+  return w;
+}
+// word i of string [s0, s0 + n): bytes beyond the string are zeroed
+__device__ __forceinline__ uint32_t string_word(const uint8_t* __restrict__ data, int64_t s0, int64_t n, int64_t i,
+                                                int64_t limit, int64_t total) {
+  const int64_t p = s0 + 4 * i;
+  uint32_t w;
+  if (p + 4 <= total) {
+    w = load_word(data, p, limit);
+  } else {  // the last word of the buffer: byte loads only
+    w = 0;
+    for (int k = 0; k < 4; ++k)
+      if (p + k < total) w |= (uint32_t)data[p + k] << (8 * k);
+  }
+  const int64_t rem = n - 4 * i;
+  return rem >= 4 ? w : (w & ((1u << (8 * (int)rem)) - 1u));
+}
+
+__device__ __forceinline__ uint64_t hash_string(const uint8_t* __restrict__ data, int64_t s0, int64_t n,
+                                                int64_t limit, int64_t total) {
+  uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)n;  // word-wise FNV-style mix, then a 64-bit finaliser
+  for (int64_t i = 0; 4 * i < n; ++i) h = (h ^ string_word(data, s0, n, i, limit, total)) * 0x100000001b3ull;
   h ^= h >> 33; h *= 0xff51afd7ed558ccdull;
   h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull;
   h ^= h >> 33;
@@ -23,37 +54,44 @@ __device__ __forceinline__ uint64_t hash_bytes(const uint8_t* __restrict__ p, in
 }
 
 __device__ __forceinline__ bool same_string(const uint8_t* __restrict__ data,
-                                            const int64_t* __restrict__ off, int64_t a, int64_t b) {
+                                            const int64_t* __restrict__ off, int64_t a, int64_t b, int64_t limit,
+                                            int64_t total) {
   const int64_t a0 = off[a], b0 = off[b];
   const int64_t n = off[a + 1] - a0;
   if (off[b + 1] - b0 != n) return false;
-  for (int64_t i = 0; i < n; ++i)
-    if (data[a0 + i] != data[b0 + i]) return false;
+  for (int64_t i = 0; 4 * i < n; ++i)
+    if (string_word(data, a0, n, i, limit, total) != string_word(data, b0, n, i, limit, total)) return false;
   return true;
 }
 
 // Open-addressing table of representative edge ids.  Equal strings meet in one slot; the slot keeps
-// the smallest edge id that ever arrived (atomicMin), i.e. the first occurrence.
+// the smallest edge id that ever arrived (atomicMin), i.e. the first occurrence.  A thread that already sees
+// a smaller id in the slot skips the atomic: with few distinct strings almost every edge does.
+// Work item j is string `subset[j]` (ascending ids) or string j itself; the table holds work-item indices, so
+// "smallest index" is "first occurrence" either way.
 __global__ void dedup_insert_kernel(const uint8_t* __restrict__ data, const int64_t* __restrict__ off,
-                                    int64_t E, uint32_t* __restrict__ table, uint64_t mask,
-                                    uint32_t* __restrict__ slot_of) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= E) return;
+                                    int64_t E, const uint32_t* __restrict__ subset, int64_t n,
+                                    uint32_t* __restrict__ table, uint64_t mask, uint32_t* __restrict__ slot_of) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t e = subset ? subset[j] : j;
+  const int64_t total = off[E], limit = total & ~(int64_t)3;
   const int64_t s0 = off[e];
-  uint64_t slot = hash_bytes(data + s0, off[e + 1] - s0) & mask;
+  uint64_t slot = hash_string(data, s0, off[e + 1] - s0, limit, total) & mask;
   for (;;) {
-    uint32_t cur = table[slot];
+    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&table[slot]);
     if (cur == kEmpty) {
-      cur = atomicCAS(&table[slot], kEmpty, (uint32_t)e);
+      cur = atomicCAS(&table[slot], kEmpty, (uint32_t)j);
       if (cur == kEmpty) break;  // claimed
     }
-    if (same_string(data, off, e, cur)) {
-      atomicMin(&table[slot], (uint32_t)e);
+    if (cur == (uint32_t)j) break;
+    if (same_string(data, off, e, subset ? subset[cur] : cur, limit, total)) {
+      if (cur > (uint32_t)j) atomicMin(&table[slot], (uint32_t)j);   // entries only ever decrease
       break;
     }
     slot = (slot + 1) & mask;
   }
-  slot_of[e] = (uint32_t)slot;
+  slot_of[j] = (uint32_t)slot;
 }
 
 __global__ void dedup_flag_kernel(const uint32_t* __restrict__ table, const uint32_t* __restrict__ slot_of,
@@ -63,17 +101,17 @@ __global__ void dedup_flag_kernel(const uint32_t* __restrict__ table, const uint
 }
 
 __global__ void dedup_assign_kernel(const uint32_t* __restrict__ table, const uint32_t* __restrict__ slot_of,
-                                    const int32_t* __restrict__ rank, int64_t E,
-                                    int32_t* __restrict__ rel_ids, int64_t* __restrict__ first_edge,
+                                    const int32_t* __restrict__ rank, const uint32_t* __restrict__ subset,
+                                    int64_t n, int32_t* __restrict__ rel_ids, int64_t* __restrict__ first_edge,
                                     int64_t* __restrict__ num_unique) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const uint32_t rep = table[slot_of[e]];
-  rel_ids[e] = rank[rep];
-  if (rep == (uint32_t)e) {
-    if (first_edge) first_edge[rank[e]] = e;
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t rep = table[slot_of[j]];
+  rel_ids[j] = rank[rep];
+  if (rep == (uint32_t)j) {
+    if (first_edge) first_edge[rank[j]] = subset ? (int64_t)subset[j] : j;
   }
-  if (e == E - 1) *num_unique = rank[e] + (rep == (uint32_t)e ? 1 : 0);
+  if (j == n - 1) *num_unique = rank[j] + (rep == (uint32_t)j ? 1 : 0);
 }
 
 // One block per unique string: mean-pool character embeddings, project, tanh.
@@ -111,40 +149,43 @@ __global__ void text_encode_kernel(const uint8_t* __restrict__ data, const int64
 using namespace ghf;
 
 extern "C" int ghf_dedup_texts(const uint8_t* d_utf8, const int64_t* d_offsets, int64_t E,
-                               int32_t* d_rel_ids, int64_t* d_first_edge, int64_t* h_num_unique,
-                               void* stream_) {
+                               const uint32_t* d_subset, int64_t n_subset, int32_t* d_rel_ids,
+                               int64_t* d_first_edge, int64_t* h_num_unique, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(E >= 0 && E < (int64_t)0xFFFFFFFE, "ghf_dedup_texts: E=%lld out of range", (long long)E);
-  if (E == 0) {
+  GHF_REQUIRE(reinterpret_cast<uintptr_t>(d_utf8) % 4 == 0, "ghf_dedup_texts: d_utf8 must be 4-byte aligned");
+  GHF_REQUIRE(d_subset == nullptr || (n_subset >= 0 && n_subset <= E), "ghf_dedup_texts: bad subset size");
+  const int64_t n = d_subset ? n_subset : E;   // work items: the strings of the subset, or all of them
+  if (n == 0) {
     if (h_num_unique) *h_num_unique = 0;
     return 0;
   }
   uint64_t cap = 64;
-  while (cap < (uint64_t)E * 2) cap <<= 1;
+  while (cap < (uint64_t)n * 2) cap <<= 1;
   TempBuf table, slot_of, flag, rank, scan_tmp, count;
   GHF_CUDA(table.alloc(cap * sizeof(uint32_t), stream));
-  GHF_CUDA(slot_of.alloc(E * sizeof(uint32_t), stream));
-  GHF_CUDA(flag.alloc(E * sizeof(int32_t), stream));
-  GHF_CUDA(rank.alloc(E * sizeof(int32_t), stream));
+  GHF_CUDA(slot_of.alloc(n * sizeof(uint32_t), stream));
+  GHF_CUDA(flag.alloc(n * sizeof(int32_t), stream));
+  GHF_CUDA(rank.alloc(n * sizeof(int32_t), stream));
   GHF_CUDA(count.alloc(sizeof(int64_t), stream));
   GHF_CUDA(cudaMemsetAsync(table.p, 0xFF, cap * sizeof(uint32_t), stream));
   const int threads = 256;
-  const unsigned blocks = (unsigned)cdiv(E, threads);
-  dedup_insert_kernel<<<blocks, threads, 0, stream>>>(d_utf8, d_offsets, E, table.as<uint32_t>(),
+  const unsigned blocks = (unsigned)cdiv(n, threads);
+  dedup_insert_kernel<<<blocks, threads, 0, stream>>>(d_utf8, d_offsets, E, d_subset, n, table.as<uint32_t>(),
                                                       cap - 1, slot_of.as<uint32_t>());
   GHF_LAUNCH_CHECK();
-  dedup_flag_kernel<<<blocks, threads, 0, stream>>>(table.as<uint32_t>(), slot_of.as<uint32_t>(), E,
+  dedup_flag_kernel<<<blocks, threads, 0, stream>>>(table.as<uint32_t>(), slot_of.as<uint32_t>(), n,
                                                     flag.as<int32_t>());
   GHF_LAUNCH_CHECK();
   size_t tmp_bytes = 0;
   GHF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag.as<int32_t>(), rank.as<int32_t>(),
-                                         (int)E, stream));
+                                         (int)n, stream));
   GHF_CUDA(scan_tmp.alloc(tmp_bytes, stream));
   GHF_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, flag.as<int32_t>(), rank.as<int32_t>(),
-                                         (int)E, stream));
+                                         (int)n, stream));
   g_launches.fetch_add(2, std::memory_order_relaxed);
   dedup_assign_kernel<<<blocks, threads, 0, stream>>>(table.as<uint32_t>(), slot_of.as<uint32_t>(),
-                                                      rank.as<int32_t>(), E, d_rel_ids, d_first_edge,
+                                                      rank.as<int32_t>(), d_subset, n, d_rel_ids, d_first_edge,
                                                       count.as<int64_t>());
   GHF_LAUNCH_CHECK();
   if (h_num_unique) {

@@ -49,11 +49,13 @@ def lib():
         "ghf_abi_version": (c_int, []),
         "ghf_last_error": (c_char_p, []),
         "ghf_device_ok": (c_int, []),
-        "ghf_dedup_texts": (c_int, [P, P, c_int64, P, P, POINTER(c_int64), P]),
+        "ghf_dedup_texts": (c_int, [P, P, c_int64, P, c_int64, P, P, POINTER(c_int64), P]),
+        "ghf_select_edges": (c_int, [P, c_int64, c_int64, c_int64, P, POINTER(c_int64), P]),
         "ghf_text_encode": (c_int, [P, P, P, c_int64, P, c_int, P, P, c_int, P, P]),
         "ghf_linear": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P, P]),
-        "ghf_graph_build": (c_int, [P, P, c_int64, c_int64, c_int32, c_int32, c_int64, c_int64, c_int32,
-                                    c_int32, POINTER(c_void_p), P]),
+        "ghf_linear_f16out": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P, P, P]),
+        "ghf_graph_build": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int32, c_int32, c_int64, c_int64,
+                                    c_int32, c_int32, POINTER(c_void_p), P]),
         "ghf_graph_free": (None, [P]),
         "ghf_graph_info": (c_int, [P, POINTER(c_int64)]),
         "ghf_graph_export": (c_int, [P, P, P, P, P, P, P, P]),
@@ -78,7 +80,8 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_text_encode", "ghf_linear",
+    "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
+    "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
     "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
@@ -143,8 +146,8 @@ def profile_read():
 
 
 # ----------------------------------------------------------------------------- ops
-def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_scale=None) -> torch.Tensor:
-    """exp(log_scale) * act(x @ weight.T + bias); x [M,K] float32 CUDA."""
+def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_scale=None, want_f16: bool = False):
+    """exp(log_scale) * act(x @ weight.T + bias); x [M,K] float32 CUDA.  want_f16: -> (y, fp16 copy of y)."""
     x, weight = _f32(x), _f32(weight)
     dev = x.device
     M, K = x.shape
@@ -154,10 +157,11 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_
     bias = None if bias is None else _f32(bias)
     log_scale = None if log_scale is None else _f32(log_scale)
     y = torch.empty((M, N), dtype=torch.float32, device=dev)
+    y16 = torch.empty((M, N), dtype=torch.float16, device=dev) if want_f16 else None
     with torch.cuda.device(dev):
-        _check(lib().ghf_linear(_ptr(x), M, K, _ptr(weight), _ptr(bias), N, int(relu), _ptr(log_scale), _ptr(y),
-                                _stream(dev)), "ghf_linear")
-    return y
+        _check(lib().ghf_linear_f16out(_ptr(x), M, K, _ptr(weight), _ptr(bias), N, int(relu), _ptr(log_scale),
+                                       _ptr(y), _ptr(y16), _stream(dev)), "ghf_linear_f16out")
+    return (y, y16) if want_f16 else y
 
 
 def to_f16(x: torch.Tensor, out=None) -> torch.Tensor:
@@ -172,17 +176,36 @@ def to_f16(x: torch.Tensor, out=None) -> torch.Tensor:
     return out
 
 
-def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor):
-    """-> (rel_ids int32 [E], first_edge int64 [U]) for packed strings on the device."""
+def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor, subset=None):
+    """-> (rel_ids int32, first_edge int64 [U]) for packed strings on the device.  rel_ids has one entry per
+    string, or per entry of `subset` (ascending string ids, int32 storage read as uint32) when given."""
     dev = utf8.device
     E = offsets.numel() - 1
-    rel = torch.empty(E, dtype=torch.int32, device=dev)
-    first = torch.empty(max(E, 1), dtype=torch.int64, device=dev)
+    n = E if subset is None else subset.numel()
+    if subset is not None and subset.dtype != torch.int32:
+        raise RuntimeError("subset must be an int32 tensor")
+    rel = torch.empty(n, dtype=torch.int32, device=dev)
+    first = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    nu = c_int64(0)
+    with torch.cuda.device(dev):
+        _check(lib().ghf_dedup_texts(_ptr(utf8), _ptr(offsets), E, _ptr(subset), n if subset is not None else 0,
+                                     _ptr(rel), _ptr(first), ctypes.byref(nu), _stream(dev)), "ghf_dedup_texts")
+    return rel, first[: nu.value]
+
+
+def select_edges(edge_index: torch.Tensor, dst_lo: int, dst_hi: int) -> torch.Tensor:
+    """Ascending ids (int32 storage, uint32 values) of the edges whose destination lies in [dst_lo, dst_hi)."""
+    dev = edge_index.device
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
+    edge_index = edge_index.contiguous()
+    E = edge_index.shape[1]
+    ids = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
     n = c_int64(0)
     with torch.cuda.device(dev):
-        _check(lib().ghf_dedup_texts(_ptr(utf8), _ptr(offsets), E, _ptr(rel), _ptr(first), ctypes.byref(n),
-                                     _stream(dev)), "ghf_dedup_texts")
-    return rel, first[: n.value]
+        _check(lib().ghf_select_edges(_ptr(edge_index), E, int(dst_lo), int(dst_hi), _ptr(ids), ctypes.byref(n),
+                                      _stream(dev)), "ghf_select_edges")
+    return ids[: n.value]
 
 
 def text_encode(utf8, offsets, index, num, char_emb, proj_w, proj_b) -> torch.Tensor:
@@ -200,7 +223,9 @@ class Graph:
     """Owner of a ghf_graph handle (in-degree, dst-CSR, relation-grouped edge order)."""
 
     def __init__(self, edge_index: torch.Tensor, rel_ids: torch.Tensor, num_nodes: int, num_rel: int,
-                 hidden_dim: int, dst_lo: int = 0, dst_hi=None, sb_nodes: int = 0, unit_edges: int = 0):
+                 hidden_dim: int, dst_lo: int = 0, dst_hi=None, sb_nodes: int = 0, unit_edges: int = 0,
+                 edge_ids=None):
+        """`edge_ids` (from `select_edges`): build from those edges only; rel_ids is then indexed like edge_ids."""
         dev = edge_index.device
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
@@ -213,10 +238,14 @@ class Graph:
         self.dst_hi = int(num_nodes if dst_hi is None else dst_hi)
         self._h = c_void_p()
         E = edge_index.shape[1]
+        n_sub = 0 if edge_ids is None else edge_ids.numel()
+        if rel_ids.numel() != (E if edge_ids is None else n_sub):
+            raise RuntimeError("rel_ids must have one entry per edge (or per selected edge)")
         with torch.cuda.device(dev):
-            _check(lib().ghf_graph_build(_ptr(edge_index), _ptr(rel_ids.contiguous()), E, self.num_nodes,
-                                         self.num_rel, self.hidden_dim, self.dst_lo, self.dst_hi, int(sb_nodes),
-                                         int(unit_edges), ctypes.byref(self._h), _stream(dev)), "ghf_graph_build")
+            _check(lib().ghf_graph_build(_ptr(edge_index), E, _ptr(edge_ids), n_sub, _ptr(rel_ids.contiguous()),
+                                         self.num_nodes, self.num_rel, self.hidden_dim, self.dst_lo, self.dst_hi,
+                                         int(sb_nodes), int(unit_edges), ctypes.byref(self._h), _stream(dev)),
+                   "ghf_graph_build")
         info = (c_int64 * 6)()
         _check(lib().ghf_graph_info(self._h, info), "ghf_graph_info")
         (self.num_kept, self.num_units, self.sb_nodes, self.unit_edges, self.num_local, self.bytes) = map(int, info)

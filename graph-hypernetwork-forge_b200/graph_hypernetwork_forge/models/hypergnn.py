@@ -38,7 +38,10 @@ class PackedTexts:
     """Relation strings on the device: bytes, offsets, per-edge relation ids, distinct-string index."""
 
     def __init__(self, texts: Optional[List[str]], device: torch.device, utf8: Optional[torch.Tensor] = None,
-                 offsets: Optional[torch.Tensor] = None):
+                 offsets: Optional[torch.Tensor] = None, subset: Optional[torch.Tensor] = None):
+        """`subset` (packed path only): ids of the strings to consider (a rank's own edges); `rel_ids` is then
+        indexed like `subset`."""
+        self.subset = subset
         if texts is None:   # already packed on the device (UTF-8 bytes + int64 offsets[E+1])
             if utf8.dtype != torch.uint8 or offsets.dtype != torch.int64:
                 raise RuntimeError("packed texts must be uint8 bytes and int64 offsets")
@@ -49,7 +52,7 @@ class PackedTexts:
             self.num_edges = len(texts)
             self.utf8 = _to_device(data, device) if data.size else torch.zeros(1, dtype=torch.uint8, device=device)
             self.offsets = _to_device(offs, device)
-        ids, first = _native.dedup_texts(self.utf8, self.offsets)   # over the packed strings
+        ids, first = _native.dedup_texts(self.utf8, self.offsets, subset)   # over the packed strings
         self.first = first                                          # packed-string index of each distinct text
         self.num_unique = int(first.numel())
         if edge_map is None:
@@ -156,14 +159,18 @@ class HyperGNN(nn.Module):
             raise ValueError(
                 f"edge_index has {edge_index.size(1)} edges but edge_texts has {offsets.numel() - 1} entries")
         device = _native.require_cuda(edge_index, utf8, offsets, self.input_proj.weight)
-        return self._prepare(edge_index, PackedTexts(None, device, utf8, offsets), num_nodes, dst_range)
+        subset = None
+        if dst_range is not None and tuple(dst_range) != (0, num_nodes):
+            # a rank's share: select its edges once; dedup and graph build then touch only those
+            subset = _native.select_edges(edge_index, dst_range[0], dst_range[1])
+        return self._prepare(edge_index, PackedTexts(None, device, utf8, offsets, subset), num_nodes, dst_range)
 
     def _prepare(self, edge_index, packed, num_nodes, dst_range) -> PreparedGraph:
         lo, hi = (0, num_nodes) if dst_range is None else dst_range
         graph = _native.Graph(edge_index, packed.rel_ids, num_nodes, max(packed.num_unique, 1),
                               self.hidden_dim, dst_lo=lo, dst_hi=hi,
                               sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
-                              unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")))
+                              unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset)
         return PreparedGraph(packed, graph)
 
     def _message_passing(self, h: torch.Tensor, edge_index: torch.Tensor, rel_weights: dict) -> torch.Tensor:
@@ -195,12 +202,16 @@ class HyperGNN(nn.Module):
             raise RuntimeError("forward_prepared needs a full-range graph; see distributed.ShardedHyperGNN")
         prec = self._precision_code()
         with torch.no_grad():
-            h = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True)
+            h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
+            if prec == _native.PREC_F16 and node_features.size(0) * self.hidden_dim % 8 == 0:
+                h, h16 = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True,
+                                        want_f16=True)
+            else:
+                h = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True)
             text_embs = self.text_encoder.encode_packed(packed)
             if taps is not None:
                 taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
                 taps["in_degree"] = graph.export()["indeg"]
-            h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
             for l in range(self.num_layers):
                 w = self._generate(l, text_embs, packed.num_unique)
                 ln = self.layer_norms[l]

@@ -40,12 +40,18 @@ int ghf_device_ok(void);
 
 /* ---- a4: relation dedup (HG:264-268) -------------------------------------------------------
  * Strings are packed as UTF-8 bytes + offsets[E+1] (string e = bytes [off[e], off[e+1])).
- * d_rel_ids[e] = rank of string e among the distinct strings in FIRST-OCCURRENCE order;
- * d_first_edge[u] = smallest e with d_rel_ids[e] == u (capacity E).  The number of distinct
- * strings is written to *h_num_unique after an internal stream synchronise. */
-int ghf_dedup_texts(const uint8_t* d_utf8, const int64_t* d_offsets, int64_t E,
-                    int32_t* d_rel_ids, int64_t* d_first_edge, int64_t* h_num_unique,
+ * Work items: all E strings (d_subset NULL), or the strings d_subset[0..n_subset) (ascending ids; a rank's own
+ * edges from ghf_select_edges).  d_rel_ids[j] = rank of work item j's string among the distinct strings of the
+ * work items in FIRST-OCCURRENCE order; d_first_edge[u] = smallest string id with rank u (capacity: number of
+ * work items).  The number of distinct strings is written to *h_num_unique after an internal stream synchronise. */
+int ghf_dedup_texts(const uint8_t* d_utf8, const int64_t* d_offsets, int64_t E, const uint32_t* d_subset,
+                    int64_t n_subset, int32_t* d_rel_ids, int64_t* d_first_edge, int64_t* h_num_unique,
                     void* stream);
+
+/* Multi-GPU helper: the edges whose destination lies in [dst_lo, dst_hi), as ascending edge ids in d_edge_ids
+ * (capacity E); their number in *h_count (synchronises).  Dedup and graph build then touch only those edges. */
+int ghf_select_edges(const int64_t* d_edge_index, int64_t E, int64_t dst_lo, int64_t dst_hi,
+                     uint32_t* d_edge_ids, int64_t* h_count, void* stream);
 
 /* ---- a5+a6: TextEncoder (HG:66-81) ----------------------------------------------------------
  * out[u,:] = tanh( mean_i Emb[tok_i] @ Wp^T + bp ), tok = code points clamped to 127 recovered
@@ -63,16 +69,23 @@ int ghf_text_encode(const uint8_t* d_utf8, const int64_t* d_offsets, const int64
 int ghf_linear(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
                int relu, const float* d_log_scale, float* d_Y, void* stream);
 
+/* ghf_linear plus an fp16 copy of Y in d_Y16 ([M,N], may be NULL): the node-feature projection (HG:261) emits
+ * the fp16 shadow of h that GHF_PREC_F16 gathers from in the same pass (fused on the tcgen05 path; otherwise a
+ * conversion pass follows, which needs M*N % 8 == 0 and 16-byte aligned pointers). */
+int ghf_linear_f16out(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
+                      int relu, const float* d_log_scale, float* d_Y, void* d_Y16, void* stream);
+
 /* ---- graph preprocessing (replaces the per-call gathers HG:281-283, scatter index HG:207-219)
  * Builds, for destinations dst in [dst_lo, dst_hi):
  *   in-degree, dst-CSR rowptr, and the edge order (super-block of dst, relation, dst), stable,
  *   cut into work units of <= unit_edges edges that share one relation.
  * d_edge_index is the reference's [2,E] int64 tensor.  Edges with dst outside the range are
- * dropped (1-D destination partition for multi-GPU).  sb_nodes <= 0 / unit_edges <= 0 pick
- * defaults.  Synchronises `stream` once (to size the unit table). */
+ * dropped (1-D destination partition for multi-GPU).  Work items: all E edges with d_rel_ids[E] (d_edge_ids
+ * NULL), or the pre-selected edges d_edge_ids[0..n_subset) with d_rel_ids[n_subset] indexed like d_edge_ids.
+ * sb_nodes <= 0 / unit_edges <= 0 pick defaults.  Synchronises `stream` once (to size the tables). */
 typedef struct ghf_graph ghf_graph;
-int ghf_graph_build(const int64_t* d_edge_index, const int32_t* d_rel_ids, int64_t E,
-                    int64_t num_nodes, int32_t num_rel, int32_t hidden_dim,
+int ghf_graph_build(const int64_t* d_edge_index, int64_t E, const uint32_t* d_edge_ids, int64_t n_subset,
+                    const int32_t* d_rel_ids, int64_t num_nodes, int32_t num_rel, int32_t hidden_dim,
                     int64_t dst_lo, int64_t dst_hi, int32_t sb_nodes, int32_t unit_edges,
                     ghf_graph** out, void* stream);
 void ghf_graph_free(ghf_graph* g);

@@ -135,6 +135,15 @@ def test_graph_tables_bit_exact():
         deg = O.in_degree(dst, N)[lo:hi]
         assert np.array_equal(t["indeg"], deg)
         assert np.array_equal(t["rowptr"], np.concatenate([[0], np.cumsum(deg)]))
+        # the same tables from the pre-selected edge subset (what a rank of the multi-GPU path builds)
+        ids = _native.select_edges(ei, lo, hi)
+        keep = np.nonzero((dst >= lo) & (dst < hi))[0]
+        assert np.array_equal(ids.cpu().numpy().astype(np.int64), keep)
+        g2 = _native.Graph(ei, relt[ids.long()].contiguous(), N, R, 64, dst_lo=lo, dst_hi=hi, sb_nodes=sb,
+                           unit_edges=ue, edge_ids=ids)
+        t2 = {k: v.cpu().numpy() for k, v in g2.export().items()}
+        for k in t:
+            assert np.array_equal(t[k], t2[k]), k
 
 
 def test_dedup_and_text_encoder_edge_cases():
@@ -159,6 +168,15 @@ def test_dedup_and_text_encoder_edge_cases():
     p2 = PackedTexts(big, torch.device(DEV))
     u2, i2 = O.dedup_texts(big)
     assert np.array_equal(p2.rel_ids.cpu().numpy().astype(np.int64), i2) and p2.num_unique == len(u2)
+    # dedup restricted to a subset of the strings (a rank's own edges): ids rank the subset's distinct strings
+    from graph_hypernetwork_forge import _text
+    data, offs = _text.pack_utf8(big)
+    sub = np.sort(rng.choice(len(big), 7000, replace=False)).astype(np.int32)
+    rel, first = _native.dedup_texts(torch.from_numpy(data.copy()).to(DEV), torch.from_numpy(offs).to(DEV),
+                                     torch.from_numpy(sub).to(DEV))
+    u3, i3 = O.dedup_texts([big[i] for i in sub])
+    assert np.array_equal(rel.cpu().numpy().astype(np.int64), i3) and first.numel() == len(u3)
+    assert [big[i] for i in first.cpu().numpy()] == u3
 
 
 def test_empty_graph_and_isolated_nodes():
