@@ -48,6 +48,15 @@ inline int64_t align_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 
 int sm_count();  // SMs of the current device (cached; api.cu)
 
+// GHF_PREC_F16 range guard: one device word per device, set by every kernel that writes an fp16 shadow of h when a
+// magnitude exceeds the fp16 range (api.cu).  nullptr when it cannot be allocated.
+int* f16_overflow_flag();
+#ifdef __CUDACC__
+__device__ __forceinline__ void flag_f16_overflow(float max_abs, int* flag) {
+  if (max_abs > 65504.f) atomicOr(flag, 1);
+}
+#endif
+
 // stream-ordered scratch that is returned to the pool at scope exit
 struct TempBuf {
   void* p = nullptr;

@@ -43,7 +43,7 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 __global__ void __launch_bounds__(kThreads, 1)
 linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __restrict__ W,
                       const float* __restrict__ bias, int relu, const float* __restrict__ log_scale,
-                      float* __restrict__ Y, int64_t ldy, __half* __restrict__ Y16) {
+                      float* __restrict__ Y, int64_t ldy, __half* __restrict__ Y16, int* __restrict__ overflow) {
   // this CTA's block of 128 output features: rows [128 y, 128 y + 128) of W, the same columns of Y
   W += (int64_t)blockIdx.y * kD * kD;
   Y += (int64_t)blockIdx.y * kD;
@@ -140,6 +140,7 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
             v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
             *reinterpret_cast<float4*>(Y + row * ldy + 4 * lane) = v;
             if (Y16) {
+              flag_f16_overflow(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))), overflow);
               const __half2 p0 = __floats2half2_rn(v.x, v.y), p1 = __floats2half2_rn(v.z, v.w);
               *reinterpret_cast<uint2*>(Y16 + row * ldy + 4 * lane) =
                   make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
@@ -246,6 +247,8 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
     GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
+  int* flag = Y16 ? f16_overflow_flag() : nullptr;
+  GHF_REQUIRE(Y16 == nullptr || flag != nullptr, "linear_umma: cannot allocate the overflow flag");
   const int64_t tiles = (M + kTile - 1) / kTile;
   const int nblocks = N / kD;
   // persistent over row tiles within a feature block: about one CTA per SM in total
@@ -253,7 +256,7 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
   linear128_umma_kernel<<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(X, M, W, b, relu,
                                                                                           log_scale, Y, (int64_t)N,
-                                                                                          reinterpret_cast<__half*>(Y16));
+                                                                                          reinterpret_cast<__half*>(Y16), flag);
   GHF_LAUNCH_CHECK();
   return 0;
 }

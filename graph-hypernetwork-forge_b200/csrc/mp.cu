@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256)
 mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict__ indeg,
                        const float* __restrict__ h, int64_t dst_lo, int64_t num_local,
                        const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
-                       float* __restrict__ out, float* __restrict__ upd, __half* __restrict__ out16) {
+                       float* __restrict__ out, float* __restrict__ upd, __half* __restrict__ out16,
+                       int* __restrict__ overflow) {
   using namespace fuse;
   constexpr int V = D / 32;
   constexpr int kRows = 4;
@@ -223,6 +224,10 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
       for (int j = 0; j < V; ++j) y[j] = (x[j] - mean) * rstd * lw[j] + lb[j];
       vstore<V>(out + r * D + lane * V, y);
       if (out16) {
+        float m = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) m = fmaxf(m, fabsf(y[j]));
+        flag_f16_overflow(m, overflow);
         __half* o = out16 + r * D + lane * V;
         if constexpr (V == 4) {
           const __half2 p0 = __floats2half2_rn(y[0], y[1]), p1 = __floats2half2_rn(y[2], y[3]);
@@ -329,15 +334,17 @@ static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_
     const int64_t cap = (int64_t)sm_count() * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     __half* o16 = reinterpret_cast<__half*>(d_out16);
+    int* flag = o16 ? f16_overflow_flag() : nullptr;
+    GHF_REQUIRE(o16 == nullptr || flag != nullptr, "ghf_mp_layer: cannot allocate the overflow flag");
     if (d == 32)
       mp_epilogue_vec_kernel<32><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16);
+                                                               d_out, d_upd, o16, flag);
     else if (d == 64)
       mp_epilogue_vec_kernel<64><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16);
+                                                               d_out, d_upd, o16, flag);
     else
       mp_epilogue_vec_kernel<128><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b,
-                                                                eps, d_out, d_upd, o16);
+                                                                eps, d_out, d_upd, o16, flag);
   } else {
     GHF_REQUIRE(d_out16 == nullptr, "ghf_mp_layer: fp16 output needs hidden_dim 32/64/128 and 16-byte alignment");
     mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(

@@ -143,11 +143,13 @@ pack_f16_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_sel
 
 // h16 = fp16(h): 8 values per thread (the layer-0 input; later layers get h16 from the layer epilogue)
 __global__ void __launch_bounds__(256)
-to_f16_kernel(const float* __restrict__ h, int64_t n8, __half* __restrict__ h16) {
+to_f16_kernel(const float* __restrict__ h, int64_t n8, __half* __restrict__ h16, int* __restrict__ overflow) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const float4 a = __ldcs(reinterpret_cast<const float4*>(h) + 2 * i);
   const float4 b = __ldcs(reinterpret_cast<const float4*>(h) + 2 * i + 1);
+  flag_f16_overflow(fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                          fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))), overflow);
   const __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w);
   const __half2 p2 = __floats2half2_rn(b.x, b.y), p3 = __floats2half2_rn(b.z, b.w);
   uint4 o;
@@ -496,7 +498,10 @@ int mp_f16_convert(const float* h, int64_t elems, void* h16, cudaStream_t stream
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h16)) % 16 == 0,
               "mp_f16: h / h16 must be 16-byte aligned");
   if (elems == 0) return 0;
-  to_f16_kernel<<<(unsigned)cdiv(elems / 8, 256), 256, 0, stream>>>(h, elems / 8, reinterpret_cast<__half*>(h16));
+  int* flag = f16_overflow_flag();
+  GHF_REQUIRE(flag != nullptr, "mp_f16: cannot allocate the overflow flag");
+  to_f16_kernel<<<(unsigned)cdiv(elems / 8, 256), 256, 0, stream>>>(h, elems / 8, reinterpret_cast<__half*>(h16),
+                                                                   flag);
   GHF_LAUNCH_CHECK();
   return 0;
 }

@@ -63,6 +63,7 @@ def lib():
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
         "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P]),
         "ghf_convert_f16": (c_int, [P, c_int64, P, P]),
+        "ghf_f16_overflow": (c_int, [c_int, POINTER(c_int), P]),
         "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
                                               c_int64, P, P, P, P]),
         "ghf_launch_count": (c_int64, [c_int]),
@@ -83,7 +84,7 @@ EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
     "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_convert_f16", "ghf_f16_overflow", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -174,6 +175,16 @@ def to_f16(x: torch.Tensor, out=None) -> torch.Tensor:
     with torch.cuda.device(x.device):
         _check(lib().ghf_convert_f16(_ptr(x), x.numel(), _ptr(out), _stream(x.device)), "ghf_convert_f16")
     return out
+
+
+def f16_overflow(device, reset: bool = True, read: bool = True) -> bool:
+    """PREC_F16 range guard: True when a kernel wrote a value beyond the fp16 range into an fp16 shadow of h since
+    the last reset (synchronises when `read`; with read=False it only clears the flag, stream-ordered)."""
+    v = c_int(0)
+    with torch.cuda.device(device):
+        _check(lib().ghf_f16_overflow(int(reset), ctypes.byref(v) if read else None, _stream(device)),
+               "ghf_f16_overflow")
+    return bool(v.value)
 
 
 def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor, subset=None):

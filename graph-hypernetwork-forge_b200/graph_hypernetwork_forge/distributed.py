@@ -79,7 +79,16 @@ class ShardedForward:
         prec = m._precision_code()
         cur, nxt = self._buffers(node_features.device, d)
         if prec == _native.PREC_F16:
-            return self._forward_f16(node_features, graph, packed, cur, nxt)
+            dev = node_features.device
+            _native.f16_overflow(dev, reset=True, read=False)
+            out = self._forward_f16(node_features, graph, packed, cur, nxt)
+            # range guard: if any rank wrote a value beyond the fp16 range, every rank redoes the tf32 path
+            flag = torch.tensor([int(_native.f16_overflow(dev))], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            if int(flag.item()) == 0:
+                return out
+            prec = _native.PREC_TF32
+            cur, nxt = self._bufs
         with torch.no_grad():
             # every rank projects all nodes (h is needed in full as the gather source)
             cur[:N] = _native.linear(node_features, m.input_proj.weight, m.input_proj.bias, relu=True)

@@ -125,6 +125,12 @@ int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, co
  * The fp16 shadow copy of h that GHF_PREC_F16 gathers from (layer 0; later layers get it from d_out16). */
 int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, void* stream);
 
+/* GHF_PREC_F16 range guard.  Every kernel that writes an fp16 shadow of h (ghf_convert_f16, ghf_linear_f16out,
+ * ghf_mp_layer_f16 with d_out16) raises a device flag when a magnitude exceeds the fp16 range (65504).  This call
+ * returns the flag in *h_flag (0 / 1), optionally clears it, and synchronises `stream`.  A caller that sees 1
+ * discards the result and reruns with GHF_PREC_TF32 (the Python mirror and ghf_hypergnn_forward_host do). */
+int ghf_f16_overflow(int reset, int* h_flag, void* stream);
+
 /* ---- whole forward from HOST buffers (HG:236-298): the end-to-end entry point --------------
  * Parameters are passed as one flat array of DEVICE pointers in reference state_dict order
  * (see INTEGRATION.md for the exact list); inputs and output are HOST
