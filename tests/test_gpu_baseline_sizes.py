@@ -1,0 +1,144 @@
+"""GPU parity at the sizes BASELINE.json names (`-m gpu`, B200).
+
+The literal oracle cannot run at these sizes in seconds, so each case is checked through
+  * a SAMPLED-DESTINATION oracle: for a few hundred destination nodes the pre-residual update of layer 0 is
+    recomputed in float64 on the host from the raw edge list (every in-edge of the sampled nodes), the layer-0
+    input h0 and the generated weights - exactly the sum HG:201-228 defines;
+  * size-independent properties: in-degrees sum to E, the result does not depend on the order of the edge list
+    (the reference sums per destination, HG:207-219), repeated runs agree up to the order of atomic additions.
+c2 (FB15k-237 shape) is small enough for the full float64 oracle as well.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hypergnn_oracle as O
+from _util import TF32_H_ATOL_SCALE1, TF32_UPD_REL, assert_close, assert_rel_to_max, model_params_numpy
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NAME_LEN = 14
+
+
+def synthetic_on_device(N, E, R, F, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    ei = torch.randint(0, N, (2, E), generator=g, device=DEV, dtype=torch.int64)
+    rel = torch.randint(0, R, (E,), generator=g, device=DEV, dtype=torch.int64)
+    x = torch.randn(N, F, generator=g, device=DEV, dtype=torch.float32)
+    names = np.frombuffer("".join(f"relation_{r:05d}" for r in range(R)).encode(), dtype=np.uint8).reshape(R, NAME_LEN)
+    utf8 = torch.from_numpy(names.copy()).to(DEV)[rel].reshape(-1).contiguous()
+    offsets = torch.arange(E + 1, device=DEV, dtype=torch.int64) * NAME_LEN
+    return x, ei, rel, utf8, offsets
+
+
+def build(T, F, d, L, precision, log_scale=-1.0, seed=0):
+    from graph_hypernetwork_forge import HyperGNN
+    torch.manual_seed(seed)
+    m = HyperGNN(T, F, d, L, precision=precision).eval()
+    with torch.no_grad():                      # O(1) generated weights: the update must matter (SURVEY hard part 4)
+        for gen in m.weight_generators:
+            for p in gen.log_scales.values():
+                p.fill_(log_scale)
+    return m.to(DEV)
+
+
+def sampled_update_check(taps, ei, n_samples, rel_tol, seed=1):
+    """upd.0 of sampled destinations against a float64 recomputation from the raw edges."""
+    N = taps["h0"].shape[0]
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    sample = torch.unique(torch.randint(0, N, (n_samples,), generator=g, device=DEV))
+    mask = torch.isin(ei[1], sample)
+    idx = mask.nonzero().squeeze(1)
+    src, dst = ei[0][idx], ei[1][idx]
+    rid = taps["edge_rel_ids"][idx].long()
+    h0 = taps["h0"].double()
+    Wm, Ws, b = taps["W_msg.0"].double(), taps["W_self.0"].double(), taps["bias.0"].double()
+    d = h0.shape[1]
+    want = torch.zeros(sample.numel(), d, dtype=torch.float64, device=DEV)
+    pos = torch.searchsorted(sample, dst)
+    msg = torch.empty(idx.numel(), d, dtype=torch.float64, device=DEV)
+    for lo in range(0, idx.numel(), 2048):         # per-edge weights in chunks (each is d*d doubles)
+        sl = slice(lo, lo + 2048)
+        msg[sl] = torch.bmm(h0[src[sl]].unsqueeze(1), Wm[rid[sl]]).squeeze(1) + b[rid[sl]] \
+            + torch.bmm(h0[dst[sl]].unsqueeze(1), Ws[rid[sl]]).squeeze(1)
+    want.index_add_(0, pos, msg)
+    cnt = torch.zeros(sample.numel(), dtype=torch.float64, device=DEV).index_add_(
+        0, pos, torch.ones(idx.numel(), dtype=torch.float64, device=DEV)).clamp_(min=1)
+    want /= cnt.unsqueeze(1)
+    got = taps["upd.0"][sample].double()
+    assert_rel_to_max(got.cpu().numpy(), want.cpu().numpy(), rel_tol, f"upd.0 at {sample.numel()} sampled destinations")
+    indeg = taps["in_degree"][sample].double()
+    assert torch.equal(indeg.clamp(min=1), cnt), "in-degree of the sampled destinations"
+
+
+@pytest.mark.parametrize("precision", ["f16", "fp32"])
+def test_c2_fb15k237_shape_full_oracle(precision):
+    """BASELINE config 2 at full size: 14,541 nodes, 272,115 edges, 237 relations, hidden 128, 2 layers."""
+    N, E, R, d, L, T, F = 14_541, 272_115, 237, 128, 2, 64, 128
+    src, dst, rel, names, feats = O.synthetic_kg(N, E, R, F, seed=2)
+    texts = [names[r] for r in rel]
+    model = build(T, F, d, L, precision)
+    params = model_params_numpy(model)
+    ref_taps = {}
+    ref = O.hypergnn_forward(params, feats, np.stack([src, dst]), texts, d, L, dtype=np.float64, taps=ref_taps)
+    taps = {}
+    ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+    out = model.forward_prepared(torch.from_numpy(feats).to(DEV), model.prepare(ei, texts, N), taps=taps)
+    assert np.array_equal(taps["edge_rel_ids"].cpu().numpy().astype(np.int64), ref_taps["edge_rel_ids"])
+    assert np.array_equal(taps["in_degree"].cpu().numpy().astype(np.int64), ref_taps["in_degree"])
+    upd0 = taps["upd.0"].cpu().numpy()
+    if precision == "fp32":
+        assert_close(upd0, ref_taps["upd.0"], 1e-4, 2e-5 * float(np.abs(ref_taps["upd.0"]).max()), "upd.0")
+        assert_close(out.cpu().numpy(), ref, 1e-4, 5e-5, "out")
+    else:
+        assert_rel_to_max(upd0, ref_taps["upd.0"], TF32_UPD_REL, "upd.0")
+        assert_close(out.cpu().numpy(), ref, 0.0, TF32_H_ATOL_SCALE1, "out")
+
+
+def test_c3_wikikg2_shape_full_size_properties():
+    """BASELINE config 3 at full size (2.5M nodes, 16M edges, 535 relations, hidden 128, 3 layers), f16 path."""
+    N, E, R, d, L, T, F = 2_500_000, 16_000_000, 535, 128, 3, 64, 128
+    x, ei, rel, utf8, offsets = synthetic_on_device(N, E, R, F)
+    model = build(T, F, d, L, "f16")
+    taps = {}
+    out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N), taps=taps)
+    assert out.shape == (N, d) and bool(torch.isfinite(out).all())
+    assert int(taps["in_degree"].sum()) == E
+    assert int(taps["edge_rel_ids"].max()) == R - 1
+    # first-occurrence order: relation id u first appears after ids 0..u-1 did
+    first_pos = torch.full((R,), E, device=DEV, dtype=torch.int64).scatter_reduce_(
+        0, taps["edge_rel_ids"].long(), torch.arange(E, device=DEV), reduce="amin")
+    assert bool((first_pos[1:] > first_pos[:-1]).all())
+    sampled_update_check(taps, ei, 256, TF32_UPD_REL)
+    del taps
+    # repeated run: only the order of the atomic additions differs
+    out2 = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N))
+    assert float((out - out2).abs().max()) < 1e-4
+    # the edge list in another order (strings permuted alike) gives the same embeddings
+    perm = torch.randperm(E, device=DEV)
+    ei_p = ei[:, perm].contiguous()
+    utf8_p = utf8.view(E, NAME_LEN)[perm].reshape(-1).contiguous()
+    out3 = model.forward_prepared(x, model.prepare_packed(ei_p, utf8_p, offsets, N))
+    assert float((out - out3).abs().max()) < 1e-4
+
+
+def test_c5_large_shape_scaled_tf32_hidden64():
+    """BASELINE config 5's shape (hidden 64, 1k relations, in-degree 10) at 1/100 scale on one GPU, tf32 path."""
+    N, E, R, d, L, T, F = 500_000, 5_000_000, 1000, 64, 2, 64, 64
+    x, ei, rel, utf8, offsets = synthetic_on_device(N, E, R, F, seed=3)
+    model = build(T, F, d, L, "tf32")
+    taps = {}
+    out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N), taps=taps)
+    assert bool(torch.isfinite(out).all()) and int(taps["in_degree"].sum()) == E
+    sampled_update_check(taps, ei, 256, TF32_UPD_REL)
+
+
+def test_c4_zero_shot_shape_scaled_fp32_hidden256():
+    """BASELINE config 4's shape (hidden 256, 1 relation text per 100 edges) at 1/10 scale, fp32 path."""
+    N, E, R, d, L, T, F = 10_000, 200_000, 2_000, 256, 2, 64, 256
+    x, ei, rel, utf8, offsets = synthetic_on_device(N, E, R, F, seed=4)
+    model = build(T, F, d, L, "fp32")
+    taps = {}
+    out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N), taps=taps)
+    assert bool(torch.isfinite(out).all()) and int(taps["in_degree"].sum()) == E
+    sampled_update_check(taps, ei, 128, 1e-4)
