@@ -61,6 +61,24 @@ class PackedTexts:
             self.rel_ids = ids[_to_device(edge_map, device).long()].contiguous()
 
 
+class RelationIds(PackedTexts):
+    """The ids-in form of the relation input: per-edge relation ids plus the distinct relation texts, for callers
+    that already hold a relation vocabulary (no per-edge strings, no dedup pass).  `rel_ids[e]` indexes
+    `unique_texts`; ids need not be in first-occurrence order - they only name rows of the generated weights."""
+
+    def __init__(self, rel_ids: torch.Tensor, unique_texts: List[str], device: torch.device):
+        if rel_ids.dim() != 1 or rel_ids.dtype not in (torch.int32, torch.int64):
+            raise RuntimeError("rel_ids must be a 1-D int32/int64 tensor")
+        data, offs = _text.pack_utf8(unique_texts)
+        self.subset = None
+        self.num_edges = rel_ids.numel()
+        self.utf8 = _to_device(data, device) if data.size else torch.zeros(4, dtype=torch.uint8, device=device)
+        self.offsets = _to_device(offs, device)
+        self.num_unique = len(unique_texts)
+        self.first = torch.arange(self.num_unique, dtype=torch.int64, device=device)   # text u is packed string u
+        self.rel_ids = rel_ids.to(device=device, dtype=torch.int32).contiguous()
+
+
 class TextEncoder(nn.Module):
     """Character-bag relation encoder: ``tanh(mean(Emb[min(ord(c),127)]) @ W^T + b)``."""
 
@@ -164,6 +182,18 @@ class HyperGNN(nn.Module):
             # a rank's share: select its edges once; dedup and graph build then touch only those
             subset = _native.select_edges(edge_index, dst_range[0], dst_range[1])
         return self._prepare(edge_index, PackedTexts(None, device, utf8, offsets, subset), num_nodes, dst_range)
+
+    def prepare_ids(self, edge_index: torch.Tensor, rel_ids: torch.Tensor, unique_texts: List[str], num_nodes: int,
+                    dst_range=None) -> PreparedGraph:
+        """`prepare` for callers that hold a relation vocabulary: `rel_ids[e]` indexes `unique_texts` (the ids-in
+        API of SURVEY 8f; the way in for edge lists of 1e8+ edges, where per-edge strings are impractical)."""
+        if edge_index.size(1) != rel_ids.numel():
+            raise ValueError(
+                f"edge_index has {edge_index.size(1)} edges but rel_ids has {rel_ids.numel()} entries")
+        device = _native.require_cuda(edge_index, self.input_proj.weight)
+        if rel_ids.numel() and (int(rel_ids.min()) < 0 or int(rel_ids.max()) >= len(unique_texts)):
+            raise ValueError("rel_ids must index unique_texts")
+        return self._prepare(edge_index, RelationIds(rel_ids, unique_texts, device), num_nodes, dst_range)
 
     def _prepare(self, edge_index, packed, num_nodes, dst_range) -> PreparedGraph:
         lo, hi = (0, num_nodes) if dst_range is None else dst_range

@@ -279,3 +279,19 @@ def test_f16_range_guard_falls_back_to_tf32():
     x_ok = torch.from_numpy((feats / 3e5).astype(np.float32)).to(DEV)
     model(x_ok, ei, texts)
     assert not _native.f16_overflow(torch.device(DEV))
+
+
+def test_ids_in_api_matches_string_api():
+    """prepare_ids(edge_index, rel_ids, unique_texts): same embeddings as the List[str] call, whatever the id order."""
+    from graph_hypernetwork_forge import HyperGNN
+    N, E, R, d, L = 3000, 50000, 41, 128, 2
+    src, dst, rel, names, feats = O.synthetic_kg(N, E, R, 32, seed=21)
+    torch.manual_seed(9)
+    model = HyperGNN(32, 32, d, L, precision="fp32").eval().to(DEV)
+    ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+    x = torch.from_numpy(feats).to(DEV)
+    want = model(x, ei, [names[r] for r in rel])
+    got = model.forward_prepared(x, model.prepare_ids(ei, torch.from_numpy(rel).to(DEV), list(names), N))
+    assert_close(got.cpu().numpy(), want.cpu().numpy(), 1e-4, 2e-5, "ids-in forward")
+    with pytest.raises(ValueError):
+        model.prepare_ids(ei, torch.from_numpy(rel[:-1]).to(DEV), list(names), N)
