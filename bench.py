@@ -85,12 +85,20 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(mhz)}
 
 
-def make_device_inputs(w, device, seed=0):
-    """Synthetic KG of the named shape, created on the device (uniform src/dst/rel)."""
+def make_device_inputs(w, device, seed=0, skew=False):
+    """Synthetic KG of the named shape, created on the device.  Headline: uniform src/dst/rel (the worst
+    case for relation grouping).  skew=True: destinations and relations follow Zipf(1) (rank = n^u, u uniform; node
+    ranks scattered over the id range by a fixed permutation) - closer to real knowledge graphs, secondary."""
     g = torch.Generator(device=device).manual_seed(seed)
     N, E, R, F = w["N"], w["E"], w["R"], w["F"]
     edge_index = torch.randint(0, N, (2, E), generator=g, device=device, dtype=torch.int64)
     rel = torch.randint(0, R, (E,), generator=g, device=device, dtype=torch.int64)
+    if skew:
+        node_of_rank = torch.randperm(N, generator=g, device=device)
+        u = torch.rand(E, generator=g, device=device, dtype=torch.float64)
+        edge_index[1] = node_of_rank[(torch.pow(float(N), u).long() - 1).clamp_(0, N - 1)]
+        u = torch.rand(E, generator=g, device=device, dtype=torch.float64)
+        rel = (torch.pow(float(R), u).long() - 1).clamp_(0, R - 1)
     x = torch.randn(N, F, generator=g, device=device, dtype=torch.float32)
     names = np.frombuffer("".join(f"relation_{r:05d}" for r in range(R)).encode(), dtype=np.uint8).reshape(R, NAME_LEN)
     utf8 = torch.from_numpy(names.copy()).to(device)[rel].reshape(-1).contiguous()
@@ -187,6 +195,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "tf32", "fp32"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and E (debugging only; not a bench number)")
+    ap.add_argument("--skew", action="store_true", help="Zipf destinations/relations (secondary workload)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -214,7 +223,7 @@ def main():
     if w["d"] not in (32, 64, 128):
         precision = "fp32"
     model = build_model(w, device, precision)
-    x, edge_index, _rel, utf8, offsets = make_device_inputs(w, device)
+    x, edge_index, _rel, utf8, offsets = make_device_inputs(w, device, skew=args.skew)
     N, E, L, d = w["N"], w["E"], w["L"], w["d"]
 
     if world == 1:
@@ -320,7 +329,8 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": precision,
                 "data": "synthetic",
-                "config": {"workload": f"{w['name']} N={N} E={E} R={w['R']} d={d} L={L} T={w['T']} F={w['F']}",
+                "config": {"workload": f"{w['name']} N={N} E={E} R={w['R']} d={d} L={L} T={w['T']} F={w['F']}"
+                                       + (" zipf-dst-rel" if args.skew else " uniform"),
                            "step": "dedup + text encoder + input projection + graph build + L layers",
                            "l2": "inputs larger than L2 (h 1.28 GB, edges 0.26 GB); no explicit flush",
                            "parallelism": "single GPU" if world == 1 else f"dst-range x{world} + all-gather(h) per layer"},

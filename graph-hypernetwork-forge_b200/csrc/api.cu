@@ -29,36 +29,9 @@ int sm_count() {
   return cached;
 }
 
-int* f16_overflow_flag() {
-  static int* flags[64] = {nullptr};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!flags[dev]) {
-    if (cudaMalloc(&flags[dev], sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(flags[dev], 0, sizeof(int));
-  }
-  return flags[dev];
-}
-
 }  // namespace ghf
 
 using namespace ghf;
-
-extern "C" int ghf_f16_overflow(int reset, int* h_flag, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  int* flag = f16_overflow_flag();
-  GHF_REQUIRE(flag != nullptr, "ghf_f16_overflow: no device flag");
-  if (h_flag == nullptr) {  // clear only: stream-ordered, no synchronisation
-    if (reset) GHF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
-    return 0;
-  }
-  int v = 0;
-  GHF_CUDA(cudaMemcpyAsync(&v, flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  if (reset) GHF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
-  GHF_CUDA(cudaStreamSynchronize(stream));
-  *h_flag = v;
-  return 0;
-}
 
 extern "C" int ghf_abi_version(void) { return GHF_ABI_VERSION; }
 extern "C" const char* ghf_last_error(void) { return err_buf(); }
@@ -125,7 +98,8 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
 
   const int64_t text_bytes = E > 0 ? h_offsets[E] : 0;
   const bool want_f16 = desc->precision == GHF_PREC_F16 && d == 128;
-  TempBuf x, ei, utf8, offs, rel, first, h0, h1, temb, h16_0;
+  TempBuf x, ei, utf8, offs, rel, first, h0, h1, temb, h16_0, scales;
+  GHF_CUDA(scales.alloc(4 * sizeof(float), stream));   // scale words of the two fp16 shadows (float[2] each)
   if (want_f16) GHF_CUDA(h16_0.alloc(num_nodes * (size_t)d * 2, stream));   // fp16 shadow of h0 (h16_0.p stays NULL otherwise)
   GHF_CUDA(x.alloc(num_nodes * (size_t)F * 4, stream));
   GHF_CUDA(ei.alloc(2 * E * sizeof(int64_t), stream));
@@ -140,6 +114,10 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
   GHF_CUDA(cudaMemcpyAsync(utf8.p, h_utf8, text_bytes, cudaMemcpyHostToDevice, stream));
   GHF_CUDA(cudaMemcpyAsync(offs.p, h_offsets, (E + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
 
+  // HG:261  h = relu(input_proj(x))
+  if (int rc = ghf_linear_f16out(x.as<float>(), num_nodes, F, Win, bin, d, 1, nullptr, h0.as<float>(), h16_0.p,
+                                 want_f16 ? scales.as<float>() : nullptr, stream))
+    return rc;
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
   if (int rc = ghf_dedup_texts(utf8.as<uint8_t>(), offs.as<int64_t>(), E, nullptr, 0, rel.as<int32_t>(),
@@ -171,62 +149,42 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
   GHF_CUDA(wbias.alloc(Un * (size_t)d * 4, stream));
   GHF_CUDA(hid_a.alloc(Un * (size_t)(H > 0 ? H : 1) * 4, stream));
   GHF_CUDA(hid_b.alloc(Un * (size_t)(H > 0 ? H : 1) * 4, stream));
-  {  // the f16 path may have to be redone on the tf32 path (range guard): size the workspace for both
-    int64_t ws_bytes = ghf_mp_workspace_bytes(g, d, prec);
-    if (prec == GHF_PREC_F16) {
-      const int64_t alt = ghf_mp_workspace_bytes(g, d, GHF_PREC_TF32);
-      ws_bytes = alt > ws_bytes ? alt : ws_bytes;
-    }
-    GHF_CUDA(ws.alloc(ws_bytes, stream));
-  }
+  GHF_CUDA(ws.alloc(ghf_mp_workspace_bytes(g, d, prec), stream));
   float* outs[3] = {wmsg.as<float>(), wself.as<float>(), wbias.as<float>()};
   const int n_out[3] = {d * d, d * d, d};
 
-  // projection + layers at a given precision; `cur` ends up pointing at the final embeddings
-  float* cur = nullptr;
-  auto run = [&](int prec) -> int {
-    // HG:261  h = relu(input_proj(x))  (+ the fp16 shadow of h on the f16 path)
-    if (int rc = ghf_linear_f16out(x.as<float>(), num_nodes, F, Win, bin, d, 1, nullptr, h0.as<float>(),
-                                   prec == GHF_PREC_F16 ? h16_0.p : nullptr, stream))
-      return rc;
-    cur = h0.as<float>();
-    float* nxt = h1.as<float>();
-    void* cur16 = prec == GHF_PREC_F16 ? h16_0.p : nullptr;   // fp16 copy of `cur`
-    void* nxt16 = h16a.p;
-    for (int l = 0; l < L; ++l) {
-      // WG:137-141 for the U distinct relations
-      for (int m = 0; m < 3 && U > 0; ++m) {
-        const float* in = temb.as<float>();
-        int in_dim = T;
-        for (int i = 0; i < depth; ++i) {
-          float* o = (i & 1) ? hid_b.as<float>() : hid_a.as<float>();
-          if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][i], layers[l].b[m][i], H, 1, nullptr, o, stream))
-            return rc;
-          in = o;
-          in_dim = H;
-        }
-        if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][depth], layers[l].b[m][depth], n_out[m], 0,
-                                layers[l].log_scale[m], outs[m], stream))
+  float* cur = h0.as<float>();
+  float* nxt = h1.as<float>();
+  void* cur16 = prec == GHF_PREC_F16 ? h16_0.p : nullptr;   // fp16 shadow of `cur` and its scale words
+  void* nxt16 = h16a.p;
+  float* cur_sc = scales.as<float>();
+  float* nxt_sc = scales.as<float>() + 2;
+  for (int l = 0; l < L; ++l) {
+    // WG:137-141 for the U distinct relations
+    for (int m = 0; m < 3 && U > 0; ++m) {
+      const float* in = temb.as<float>();
+      int in_dim = T;
+      for (int i = 0; i < depth; ++i) {
+        float* o = (i & 1) ? hid_b.as<float>() : hid_a.as<float>();
+        if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][i], layers[l].b[m][i], H, 1, nullptr, o, stream))
           return rc;
+        in = o;
+        in_dim = H;
       }
-      // HG:286-296
-      void* out16 = (prec == GHF_PREC_F16 && l + 1 < L) ? nxt16 : nullptr;
-      if (int rc = ghf_mp_layer_f16(g, cur, cur16, outs[0], outs[1], outs[2], layers[l].ln_w, layers[l].ln_b,
-                                    desc->ln_eps, prec, nxt, out16, nullptr, ws.p, stream))
+      if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][depth], layers[l].b[m][depth], n_out[m], 0,
+                              layers[l].log_scale[m], outs[m], stream))
         return rc;
-      float* t = cur; cur = nxt; nxt = t;
-      cur16 = out16;
-      nxt16 = (nxt16 == h16a.p) ? h16_0.p : h16a.p;
     }
-    return 0;
-  };
-  if (prec == GHF_PREC_F16) GHF_CUDA(cudaMemsetAsync(f16_overflow_flag(), 0, sizeof(int), stream));
-  if (int rc = run(prec)) return rc;
-  if (prec == GHF_PREC_F16) {  // range guard: a value beyond the fp16 range -> redo on the tf32 path
-    int overflow = 0;
-    if (int rc = ghf_f16_overflow(1, &overflow, stream)) return rc;
-    if (overflow)
-      if (int rc = run(GHF_PREC_TF32)) return rc;
+    // HG:286-296
+    void* out16 = (prec == GHF_PREC_F16 && l + 1 < L) ? nxt16 : nullptr;
+    if (int rc = ghf_mp_layer_f16(g, cur, cur16, cur16 ? cur_sc : nullptr, outs[0], outs[1], outs[2], layers[l].ln_w,
+                                  layers[l].ln_b, desc->ln_eps, prec, nxt, out16, out16 ? nxt_sc : nullptr, nullptr,
+                                  ws.p, stream))
+      return rc;
+    float* t = cur; cur = nxt; nxt = t;
+    t = cur_sc; cur_sc = nxt_sc; nxt_sc = t;
+    cur16 = out16;
+    nxt16 = (nxt16 == h16a.p) ? h16_0.p : h16a.p;
   }
   GHF_CUDA(cudaMemcpyAsync(h_out, cur, num_nodes * (size_t)d * 4, cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaStreamSynchronize(stream));

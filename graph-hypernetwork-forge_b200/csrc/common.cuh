@@ -48,12 +48,22 @@ inline int64_t align_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 
 int sm_count();  // SMs of the current device (cached; api.cu)
 
-// GHF_PREC_F16 range guard: one device word per device, set by every kernel that writes an fp16 shadow of h when a
-// magnitude exceeds the fp16 range (api.cu).  nullptr when it cannot be allocated.
-int* f16_overflow_flag();
+// ---- fp16 shadow of h (GHF_PREC_F16) ------------------------------------------------------------------------
+// A shadow is (h16, scale) with scale = float[2] in device memory: h = h16 * scale[0] (scale[0] is an exact power of
+// two), scale[1] = max |h| (written by the producer of h, read by the kernel that picks the scale).  Everything is
+// decided on the device: no host round trip, no dependence on the data range.
 #ifdef __CUDACC__
-__device__ __forceinline__ void flag_f16_overflow(float max_abs, int* flag) {
-  if (max_abs > 65504.f) atomicOr(flag, 1);
+// power of two s with amax * s in [2^13, 2^14): inside the fp16 range with headroom; 1 for amax = 0 / inf / nan
+__device__ __forceinline__ float f16_scale_for(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
+  e = 14 - e;
+  return ldexpf(1.f, e > 120 ? 120 : (e < -120 ? -120 : e));
+}
+// max over non-negative floats (their IEEE bit patterns order like integers)
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+  atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
 }
 #endif
 

@@ -9,8 +9,9 @@ namespace ghf {
 bool linear_umma_eligible(int64_t M, int K, int N, int relu, const void* log_scale, const void* X, const void* W,
                           const void* Y);
 int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int N, int relu,
-                       const float* log_scale, float* Y, void* Y16, cudaStream_t stream);
-int mp_f16_convert(const float* h, int64_t elems, void* h16, cudaStream_t stream);  // mp_f16.cu
+                       const float* log_scale, float* Y, void* Y16, float* y16_scale, cudaStream_t stream);
+int mp_f16_absmax(const float* x, int64_t elems, float* scale, cudaStream_t stream);                      // mp_f16.cu
+int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool rescue, cudaStream_t stream);
 namespace {
 
 template <int BN, bool VEC>
@@ -85,22 +86,29 @@ using namespace ghf;
 
 extern "C" int ghf_linear(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
                           int relu, const float* d_log_scale, float* d_Y, void* stream_) {
-  return ghf_linear_f16out(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, nullptr, stream_);
+  return ghf_linear_f16out(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, nullptr, nullptr, stream_);
 }
 
 extern "C" int ghf_linear_f16out(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
-                                 int relu, const float* d_log_scale, float* d_Y, void* d_Y16, void* stream_) {
+                                 int relu, const float* d_log_scale, float* d_Y, void* d_Y16, float* d_Y16_scale,
+                                 void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(M >= 0 && K > 0 && N > 0, "ghf_linear: bad dims M=%lld K=%d N=%d", (long long)M, K, N);
   GHF_REQUIRE(cdiv(N, 32) <= 65535, "ghf_linear: N=%d too large", N);
   GHF_REQUIRE(reinterpret_cast<uintptr_t>(d_Y16) % 16 == 0, "ghf_linear_f16out: d_Y16 must be 16-byte aligned");
+  GHF_REQUIRE(d_Y16 == nullptr || d_Y16_scale != nullptr, "ghf_linear_f16out: d_Y16 needs d_Y16_scale (float[2])");
   if (M == 0) return 0;
-  if (linear_umma_eligible(M, K, N, relu, d_log_scale, d_X, d_W, d_Y))
-    return linear_umma_launch(d_X, M, d_W, d_b, N, relu, d_log_scale, d_Y, d_Y16, stream);
+  if (linear_umma_eligible(M, K, N, relu, d_log_scale, d_X, d_W, d_Y)) {
+    // fused: the kernel writes fp16(Y) and max|Y|; a rescue pass rewrites the shadow only if the range needs a scale
+    if (d_Y16) GHF_CUDA(cudaMemsetAsync(d_Y16_scale + 1, 0, sizeof(float), stream));
+    if (int rc = linear_umma_launch(d_X, M, d_W, d_b, N, relu, d_log_scale, d_Y, d_Y16, d_Y16_scale, stream)) return rc;
+    return d_Y16 ? mp_f16_convert(d_Y, M * (int64_t)N, d_Y16, d_Y16_scale, /*rescue=*/true, stream) : 0;
+  }
   int rc;
   if (N <= 32) rc = launch_linear<32>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
   else if (N <= 64) rc = launch_linear<64>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
   else rc = launch_linear<128>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
-  if (rc == 0 && d_Y16) rc = mp_f16_convert(d_Y, M * (int64_t)N, d_Y16, stream);   // fused only on the tcgen05 path
+  if (rc == 0 && d_Y16) rc = mp_f16_absmax(d_Y, M * (int64_t)N, d_Y16_scale, stream);   // fused only on the tcgen05 path
+  if (rc == 0 && d_Y16) rc = mp_f16_convert(d_Y, M * (int64_t)N, d_Y16, d_Y16_scale, /*rescue=*/false, stream);
   return rc;
 }

@@ -43,7 +43,8 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 __global__ void __launch_bounds__(kThreads, 1)
 linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __restrict__ W,
                       const float* __restrict__ bias, int relu, const float* __restrict__ log_scale,
-                      float* __restrict__ Y, int64_t ldy, __half* __restrict__ Y16, int* __restrict__ overflow) {
+                      float* __restrict__ Y, int64_t ldy, __half* __restrict__ Y16,
+                      float* __restrict__ y16_scale) {
   // this CTA's block of 128 output features: rows [128 y, 128 y + 128) of W, the same columns of Y
   W += (int64_t)blockIdx.y * kD * kD;
   Y += (int64_t)blockIdx.y * kD;
@@ -114,6 +115,7 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
     float* stg = reinterpret_cast<float*>(smem_raw + (sStg - raw) + grp * kStaging);
     const float4* stg4 = reinterpret_cast<const float4*>(stg);
     const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float amax = 0.f;   // max |Y| seen by this thread (the fp16 shadow's range check)
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
@@ -140,7 +142,7 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
             v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
             *reinterpret_cast<float4*>(Y + row * ldy + 4 * lane) = v;
             if (Y16) {
-              flag_f16_overflow(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))), overflow);
+              amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
               const __half2 p0 = __floats2half2_rn(v.x, v.y), p1 = __floats2half2_rn(v.z, v.w);
               *reinterpret_cast<uint2*>(Y16 + row * ldy + 4 * lane) =
                   make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
@@ -151,6 +153,11 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
       }
       tc_fence_before();
       mbar_arrive(acc_empty(a));
+    }
+    if (Y16) {   // speculative unscaled shadow: publish the range, the rescue pass decides whether to rescale
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, sft));
+      if (lane == 0) atomic_max_nonneg(y16_scale + 1, amax);
     }
   } else if (warp < kWarpMma) {
     // ------------------------------------------------------------------ producers: split X into hi / lo tiles
@@ -241,14 +248,12 @@ bool linear_umma_eligible(int64_t M, int K, int N, int relu, const void* log_sca
 }
 
 int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int N, int relu,
-                       const float* log_scale, float* Y, void* Y16, cudaStream_t stream) {
+                       const float* log_scale, float* Y, void* Y16, float* y16_scale, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
-  int* flag = Y16 ? f16_overflow_flag() : nullptr;
-  GHF_REQUIRE(Y16 == nullptr || flag != nullptr, "linear_umma: cannot allocate the overflow flag");
   const int64_t tiles = (M + kTile - 1) / kTile;
   const int nblocks = N / kD;
   // persistent over row tiles within a feature block: about one CTA per SM in total
@@ -256,7 +261,7 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
   linear128_umma_kernel<<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(X, M, W, b, relu,
                                                                                           log_scale, Y, (int64_t)N,
-                                                                                          reinterpret_cast<__half*>(Y16), flag);
+                                                                                          reinterpret_cast<__half*>(Y16), y16_scale);
   GHF_LAUNCH_CHECK();
   return 0;
 }

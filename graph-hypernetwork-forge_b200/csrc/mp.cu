@@ -175,7 +175,7 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
                        const float* __restrict__ h, int64_t dst_lo, int64_t num_local,
                        const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
                        float* __restrict__ out, float* __restrict__ upd, __half* __restrict__ out16,
-                       int* __restrict__ overflow) {
+                       float* __restrict__ out16_scale) {
   using namespace fuse;
   constexpr int V = D / 32;
   constexpr int kRows = 4;
@@ -185,6 +185,21 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
   float lw[V], lb[V];
   vload_nc<V>(lw, ln_w + lane * V);
   vload_nc<V>(lb, ln_b + lane * V);
+  // fp16 shadow of the output: |LayerNorm(x)_c| <= sqrt(D-1) |w_c| + |b_c|, so a power-of-two scale that fits the
+  // largest such bound fits every row - chosen here, identically by every warp (and every rank), from w and b alone
+  float s16 = 1.f;
+  if (out16) {
+    float bound = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) bound = fmaxf(bound, sqrtf((float)(D - 1)) * fabsf(lw[j]) + fabsf(lb[j]));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, s));
+    s16 = f16_scale_for(bound);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      out16_scale[0] = 1.f / s16;
+      out16_scale[1] = bound;
+    }
+  }
   for (int64_t r0 = w0; r0 < num_local; r0 += kRows * warps) {
     float a[kRows][V], hv[kRows][V];
     int deg[kRows];
@@ -224,19 +239,15 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
       for (int j = 0; j < V; ++j) y[j] = (x[j] - mean) * rstd * lw[j] + lb[j];
       vstore<V>(out + r * D + lane * V, y);
       if (out16) {
-        float m = 0.f;
-#pragma unroll
-        for (int j = 0; j < V; ++j) m = fmaxf(m, fabsf(y[j]));
-        flag_f16_overflow(m, overflow);
         __half* o = out16 + r * D + lane * V;
         if constexpr (V == 4) {
-          const __half2 p0 = __floats2half2_rn(y[0], y[1]), p1 = __floats2half2_rn(y[2], y[3]);
+          const __half2 p0 = __floats2half2_rn(y[0] * s16, y[1] * s16), p1 = __floats2half2_rn(y[2] * s16, y[3] * s16);
           *reinterpret_cast<uint2*>(o) =
               make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
         } else if constexpr (V == 2) {
-          *reinterpret_cast<__half2*>(o) = __floats2half2_rn(y[0], y[1]);
+          *reinterpret_cast<__half2*>(o) = __floats2half2_rn(y[0] * s16, y[1] * s16);
         } else {
-          *o = __float2half_rn(y[0]);
+          *o = __float2half_rn(y[0] * s16);
         }
       }
     }
@@ -314,14 +325,14 @@ extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim
   int64_t bytes = 256 /* work counter */ + (fused ? 0 : align_up(g->num_local * (int64_t)hidden_dim * 4, 256));
   if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim) + mp_umma_sync_bytes(g);
   if (precision == GHF_PREC_F16)  // sync words, weight images, the fp16 copy of h made when the caller passes none
-    bytes += mp_f16_sync_bytes(g) + mp_f16_pack_bytes(g->num_rel) +
+    bytes += mp_f16_sync_bytes(g) + mp_f16_pack_bytes(g->num_rel) + 256 /* scale words */ +
              align_up(g->num_nodes * (int64_t)hidden_dim * 2, 256);
   return bytes + 256;
 }
 
 static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_h, const float* d_ln_w,
                            const float* d_ln_b, float eps, float* d_out, float* d_upd, void* d_out16,
-                           cudaStream_t stream) {
+                           float* d_out16_scale, cudaStream_t stream) {
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
   const int threads = 256;
@@ -334,17 +345,15 @@ static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_
     const int64_t cap = (int64_t)sm_count() * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     __half* o16 = reinterpret_cast<__half*>(d_out16);
-    int* flag = o16 ? f16_overflow_flag() : nullptr;
-    GHF_REQUIRE(o16 == nullptr || flag != nullptr, "ghf_mp_layer: cannot allocate the overflow flag");
     if (d == 32)
       mp_epilogue_vec_kernel<32><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16, flag);
+                                                               d_out, d_upd, o16, d_out16_scale);
     else if (d == 64)
       mp_epilogue_vec_kernel<64><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16, flag);
+                                                               d_out, d_upd, o16, d_out16_scale);
     else
       mp_epilogue_vec_kernel<128><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b,
-                                                                eps, d_out, d_upd, o16, flag);
+                                                                eps, d_out, d_upd, o16, d_out16_scale);
   } else {
     GHF_REQUIRE(d_out16 == nullptr, "ghf_mp_layer: fp16 output needs hidden_dim 32/64/128 and 16-byte alignment");
     mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(
@@ -354,15 +363,18 @@ static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_
   return 0;
 }
 
-extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_W_msg,
-                                const float* d_W_self, const float* d_bias, const float* d_ln_w,
-                                const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
-                                float* d_upd, void* d_workspace, void* stream_) {
+extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                                const float* d_W_msg, const float* d_W_self, const float* d_bias,
+                                const float* d_ln_w, const float* d_ln_b, float eps, int precision, float* d_out,
+                                void* d_out16, float* d_out16_scale, float* d_upd, void* d_workspace,
+                                void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(g != nullptr, "ghf_mp_layer: graph is NULL");
   GHF_REQUIRE(d_workspace != nullptr, "ghf_mp_layer: workspace is NULL");
   GHF_REQUIRE(precision == GHF_PREC_FP32 || precision == GHF_PREC_TF32 || precision == GHF_PREC_F16,
               "ghf_mp_layer: precision=%d", precision);
+  GHF_REQUIRE(d_h16 == nullptr || d_h16_scale != nullptr, "ghf_mp_layer: d_h16 needs d_h16_scale (float[2])");
+  GHF_REQUIRE(d_out16 == nullptr || d_out16_scale != nullptr, "ghf_mp_layer: d_out16 needs d_out16_scale (float[2])");
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
   g->stream = stream_;
@@ -414,6 +426,7 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
                                              nl * (size_t)d * 4, stream));
   const bool ts = mp_ts_enabled(d);
   const void* h16 = d_h16;
+  const float* h16_scale = d_h16_scale;
   if (precision == GHF_PREC_TF32 && g->num_units > 0) {
     GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
     if (int rc = ts ? mp_ts_pack(g, d_W_msg, d_W_self, pack, stream) : mp_umma_pack(g, d_W_msg, d_W_self, pack, stream))
@@ -422,10 +435,13 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     GHF_REQUIRE(mp_f16_supported(d), "ghf_mp_layer: f16 path supports hidden_dim 128, got %d", d);
     if (g->num_units > 0) {
       if (int rc = mp_f16_pack(g, d_W_msg, d_W_self, pack, stream)) return rc;
-      if (h16 == nullptr) {  // no fp16 copy of h from the previous layer: make one
-        void* conv = reinterpret_cast<char*>(pack) + mp_f16_pack_bytes(g->num_rel);
-        if (int rc = mp_f16_convert(d_h, g->num_nodes * (int64_t)d, conv, stream)) return rc;
+      if (h16 == nullptr) {  // no fp16 shadow of h from the previous layer: make one (scale words, then the rows)
+        float* sc = reinterpret_cast<float*>(reinterpret_cast<char*>(pack) + mp_f16_pack_bytes(g->num_rel));
+        void* conv = reinterpret_cast<char*>(sc) + 256;
+        if (int rc = mp_f16_absmax(d_h, g->num_nodes * (int64_t)d, sc, stream)) return rc;
+        if (int rc = mp_f16_convert(d_h, g->num_nodes * (int64_t)d, conv, sc, /*rescue=*/false, stream)) return rc;
         h16 = conv;
+        h16_scale = sc;
       }
     }
   }
@@ -436,7 +452,7 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
       rc = ts ? mp_ts_launch(g, d_h, d_bias, acc, pack, counter, stream)
               : mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream);
     } else if (precision == GHF_PREC_F16) {
-      rc = mp_f16_launch(g, h16, d_bias, acc, pack, counter, stream);
+      rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream);
     } else if (d <= 32) {
       rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
     } else if (d <= 64) {
@@ -447,7 +463,8 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     if (rc) return rc;
   }
   if (prof) GHF_CUDA(cudaEventRecord(rec.e[2], stream));
-  if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, stream)) return rc;
+  if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream))
+    return rc;
   if (prof) {
     GHF_CUDA(cudaEventRecord(rec.e[3], stream));
     g_prof.push_back(rec);
@@ -455,15 +472,23 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
   return 0;
 }
 
-extern "C" int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, void* stream_) {
-  GHF_REQUIRE(elems >= 0 && (d_x != nullptr || elems == 0) && (d_y16 != nullptr || elems == 0),
+extern "C" int ghf_absmax(const float* d_x, int64_t elems, float* d_scale, void* stream_) {
+  GHF_REQUIRE(elems >= 0 && (d_x != nullptr || elems == 0) && d_scale != nullptr, "ghf_absmax: bad arguments");
+  return mp_f16_absmax(d_x, elems, d_scale, (cudaStream_t)stream_);
+}
+
+extern "C" int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, float* d_scale, int have_amax,
+                               void* stream_) {
+  GHF_REQUIRE(elems >= 0 && (d_x != nullptr || elems == 0) && (d_y16 != nullptr || elems == 0) && d_scale != nullptr,
               "ghf_convert_f16: bad arguments");
-  return mp_f16_convert(d_x, elems, d_y16, (cudaStream_t)stream_);
+  if (!have_amax)
+    if (int rc = mp_f16_absmax(d_x, elems, d_scale, (cudaStream_t)stream_)) return rc;
+  return mp_f16_convert(d_x, elems, d_y16, d_scale, /*rescue=*/false, (cudaStream_t)stream_);
 }
 
 extern "C" int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, const float* d_W_self,
                             const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
                             int precision, float* d_out, float* d_upd, void* d_workspace, void* stream_) {
-  return ghf_mp_layer_f16(g, d_h, nullptr, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out, nullptr,
-                          d_upd, d_workspace, stream_);
+  return ghf_mp_layer_f16(g, d_h, nullptr, nullptr, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out,
+                          nullptr, nullptr, d_upd, d_workspace, stream_);
 }

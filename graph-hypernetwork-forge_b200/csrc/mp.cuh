@@ -41,12 +41,15 @@ bool mp_f16_supported(int hidden_dim);
 // scratch for the per-relation fp16 weight images [R][64 KiB] followed by their inverse power-of-two scales [R]
 int64_t mp_f16_pack_bytes(int num_rel);
 int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream);
-// h16[i] = fp16(h[i]) for `elems` values (a multiple of 8)
-int mp_f16_convert(const float* h, int64_t elems, void* h16, cudaStream_t stream);
+// fp16 shadow of h: (h16, scale[2]) with h = h16 * scale[0], scale[1] = max|h| (see common.cuh).
+// absmax: scale[1] = max|x|.  convert: scale chosen from scale[1], scale[0] written, h16 = fp16(h * s); with
+// `rescue` the shadow already holds fp16(h) and is rewritten only if the range demands a scale.
+int mp_f16_absmax(const float* x, int64_t elems, float* scale, cudaStream_t stream);
+int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool rescue, cudaStream_t stream);
 // acc[dst_local, :] = sum over edges of [h16_src | h16_dst] @ [W_msg; W_self][rel] + bias[rel]; h16 is [N, 128] fp16.
 // The kernel clears acc itself (every local row, also those without in-edges).  sync_words: mp_f16_sync_bytes(g).
 int64_t mp_f16_sync_bytes(const ghf_graph* g);
-int mp_f16_launch(const ghf_graph* g, const void* h16, const float* bias, float* acc, const void* pack_scratch,
-                  int* sync_words, cudaStream_t stream);
+int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
+                  const void* pack_scratch, int* sync_words, cudaStream_t stream);
 
 }  // namespace ghf

@@ -141,21 +141,41 @@ pack_f16_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_sel
   }
 }
 
-// h16 = fp16(h): 8 values per thread (the layer-0 input; later layers get h16 from the layer epilogue)
+// scale[1] = max |x| over `n8` groups of 8 floats (scale[1] must be zero at launch)
 __global__ void __launch_bounds__(256)
-to_f16_kernel(const float* __restrict__ h, int64_t n8, __half* __restrict__ h16, int* __restrict__ overflow) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  const float4 a = __ldcs(reinterpret_cast<const float4*>(h) + 2 * i);
-  const float4 b = __ldcs(reinterpret_cast<const float4*>(h) + 2 * i + 1);
-  flag_f16_overflow(fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
-                          fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))), overflow);
-  const __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w);
-  const __half2 p2 = __floats2half2_rn(b.x, b.y), p3 = __floats2half2_rn(b.z, b.w);
-  uint4 o;
-  o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
-  o.z = *reinterpret_cast<const uint32_t*>(&p2); o.w = *reinterpret_cast<const uint32_t*>(&p3);
-  reinterpret_cast<uint4*>(h16)[i] = o;
+absmax_kernel(const float* __restrict__ x, int64_t n8, float* __restrict__ scale) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+    m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                       fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(scale + 1, m);
+}
+
+// h16 = fp16(h * s), s = f16_scale_for(scale[1]); scale[0] = 1 / s.  RESCUE = true: the shadow was already written
+// unscaled by the producer of h (speculatively, fused); only if the range demands it is it rewritten with a scale.
+template <bool RESCUE>
+__global__ void __launch_bounds__(256)
+to_f16_kernel(const float* __restrict__ h, int64_t n8, __half* __restrict__ h16, float* __restrict__ scale) {
+  const float amax = scale[1];
+  float s = f16_scale_for(amax);
+  if (RESCUE && ((amax >= 0.0625f && amax < 32768.f) || !(amax > 0.f))) s = 1.f;   // the unscaled shadow is fine
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale[0] = 1.f / s;
+  if (RESCUE && s == 1.f) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(h) + 2 * i);
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(h) + 2 * i + 1);
+    const __half2 p0 = __floats2half2_rn(a.x * s, a.y * s), p1 = __floats2half2_rn(a.z * s, a.w * s);
+    const __half2 p2 = __floats2half2_rn(b.x * s, b.y * s), p3 = __floats2half2_rn(b.z * s, b.w * s);
+    uint4 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
+    o.z = *reinterpret_cast<const uint32_t*>(&p2); o.w = *reinterpret_cast<const uint32_t*>(&p3);
+    reinterpret_cast<uint4*>(h16)[i] = o;
+  }
 }
 
 template <int kProdWarps>
@@ -163,7 +183,8 @@ __global__ void __launch_bounds__(threads_for(kProdWarps), 1)
 mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
               const int32_t* __restrict__ unit_rel, int64_t num_units, const int32_t* __restrict__ src_sorted,
               const int32_t* __restrict__ dst_sorted, const __half* __restrict__ h16, int64_t dst_lo,
-              const __half* __restrict__ wpack, const float* __restrict__ w_inv_scale,
+              const float* __restrict__ h_scale, const __half* __restrict__ wpack,
+              const float* __restrict__ w_inv_scale,
               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter,
               const int32_t* __restrict__ unit_phase, int* __restrict__ zero_done, int num_phases, int sb_nodes,
               int64_t num_local, uint32_t flags) {
@@ -232,6 +253,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
     const int grp = warp >> 2, q = warp & 3;
     const int col = 32 * q + lane;                       // this thread's output column = its TMEM lane
     float* acc_col = acc + col;
+    const float h_inv = h_scale[0];                      // h = h16 * h_inv (exact power of two)
     const int e0 = 32 * grp;
     // Everything a tile's reductions need from global memory (the destination id of edge e0 + lane, the
     // relation's bias entry and scale) is fetched one tile ahead, so that no load latency sits between
@@ -242,7 +264,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       if (t.x < 0) return x;
       if (e0 + lane < t.y) x.dst = dst_sorted[t.x + e0 + lane];
       x.bias_n = bias[(int64_t)t.z * kD + col];
-      x.inv = w_inv_scale[t.z];
+      x.inv = w_inv_scale[t.z] * h_inv;
       return x;
     };
     int4 cur = q_acquire(0);
@@ -258,11 +280,22 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kTile + e0), r);
         tmem_ld_wait();
         if (!(flags & kDbgNoRed)) {
+          // Segmented sum along the sorted order: edges of one (destination, relation) pair are adjacent, so their
+          // contributions are added in a register and leave as ONE red (multigraphs, hub destinations); with all
+          // destinations distinct this is one red per edge as before.
+          float run = 0.f;
+          int run_dst = -1;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int dsti = __shfl_sync(0xffffffffu, cr.dst, e);
-            if (dsti >= 0) red_add_f32(acc_col + (int64_t)dsti * kD, fmaf(__uint_as_float(r[e]), cr.inv, cr.bias_n));
+            if (dsti != run_dst) {
+              if (run_dst >= 0) red_add_f32(acc_col + (int64_t)run_dst * kD, run);
+              run = 0.f;
+              run_dst = dsti;
+            }
+            run += fmaf(__uint_as_float(r[e]), cr.inv, cr.bias_n);
           }
+          if (run_dst >= 0) red_add_f32(acc_col + (int64_t)run_dst * kD, run);
         }
       }
       tc_fence_before();
@@ -390,7 +423,15 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       const int64_t share = (hi - lo + gridDim.x - 1) / gridDim.x;
       const int64_t r0 = lo + (int64_t)blockIdx.x * share, r1 = min(hi, r0 + share);
       float4* row = reinterpret_cast<float4*>(acc) + lane;
-      for (int64_t r = r0; r < r1; ++r) row[r * (kD / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (flags & kFlagRedEvictLast) {                   // keep the zero lines in L2 until their reductions arrive
+        const uint64_t pol = policy_evict_last();
+        for (int64_t r = r0; r < r1; ++r)
+          asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%1,%1,%1}, %2;" ::"l"(row + r * (kD / 4)), "f"(0.f),
+                       "l"(pol)
+                       : "memory");
+      } else {
+        for (int64_t r = r0; r < r1; ++r) row[r * (kD / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       __syncwarp();
       if (lane == 0) {
         __threadfence();
@@ -493,21 +534,38 @@ int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, voi
   return 0;
 }
 
-int mp_f16_convert(const float* h, int64_t elems, void* h16, cudaStream_t stream) {
+static unsigned stride_grid(int64_t n8) {
+  const int64_t want = cdiv(n8, 256), cap = (int64_t)sm_count() * 16;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+int mp_f16_absmax(const float* x, int64_t elems, float* scale, cudaStream_t stream) {
   GHF_REQUIRE(elems % 8 == 0, "mp_f16: element count must be a multiple of 8");
-  GHF_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h16)) % 16 == 0,
-              "mp_f16: h / h16 must be 16-byte aligned");
+  GHF_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0, "mp_f16: x must be 16-byte aligned");
+  GHF_CUDA(cudaMemsetAsync(scale + 1, 0, sizeof(float), stream));
   if (elems == 0) return 0;
-  int* flag = f16_overflow_flag();
-  GHF_REQUIRE(flag != nullptr, "mp_f16: cannot allocate the overflow flag");
-  to_f16_kernel<<<(unsigned)cdiv(elems / 8, 256), 256, 0, stream>>>(h, elems / 8, reinterpret_cast<__half*>(h16),
-                                                                   flag);
+  absmax_kernel<<<stride_grid(elems / 8), 256, 0, stream>>>(x, elems / 8, scale);
   GHF_LAUNCH_CHECK();
   return 0;
 }
 
-int mp_f16_launch(const ghf_graph* g, const void* h16, const float* bias, float* acc, const void* pack_scratch,
-                  int* sync_words, cudaStream_t stream) {
+int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool rescue, cudaStream_t stream) {
+  GHF_REQUIRE(elems % 8 == 0, "mp_f16: element count must be a multiple of 8");
+  GHF_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h16)) % 16 == 0,
+              "mp_f16: h / h16 must be 16-byte aligned");
+  GHF_REQUIRE(scale != nullptr, "mp_f16: the fp16 shadow needs its scale words");
+  __half* out = reinterpret_cast<__half*>(h16);
+  if (rescue)
+    to_f16_kernel<true><<<stride_grid(elems / 8), 256, 0, stream>>>(h, elems / 8, out, scale);
+  else
+    to_f16_kernel<false><<<stride_grid(elems / 8), 256, 0, stream>>>(h, elems / 8, out, scale);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
+                  const void* pack_scratch, int* sync_words, cudaStream_t stream) {
+  GHF_REQUIRE(h16_scale != nullptr, "mp_f16: the fp16 shadow needs its scale words");
   GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
   GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_f16: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(h16) | reinterpret_cast<uintptr_t>(acc) |
@@ -532,12 +590,12 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* bias, float*
   if (prod == 8)
     mp_f16_kernel<8><<<(unsigned)grid, threads_for(8), kSmem, stream>>>(
         g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
-        reinterpret_cast<const __half*>(h16), g->dst_lo, img, inv, bias, acc, unit_counter, g->unit_phase, zero_done,
+        reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, zero_done,
         (int)g->num_phases, g->sb_nodes, g->num_local, env_flags());
   else
     mp_f16_kernel<4><<<(unsigned)grid, threads_for(4), kSmem, stream>>>(
         g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
-        reinterpret_cast<const __half*>(h16), g->dst_lo, img, inv, bias, acc, unit_counter, g->unit_phase, zero_done,
+        reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, zero_done,
         (int)g->num_phases, g->sb_nodes, g->num_local, env_flags());
   GHF_LAUNCH_CHECK();
   return 0;

@@ -17,7 +17,7 @@ PREC_FP32 = 0
 PREC_TF32 = 1
 PREC_F16 = 2
 _PREC = {"fp32": PREC_FP32, "tf32": PREC_TF32, "f16": PREC_F16}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _LIB_PATH = os.environ.get("GHF_LIB") or os.path.join(
     os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")
@@ -53,7 +53,7 @@ def lib():
         "ghf_select_edges": (c_int, [P, c_int64, c_int64, c_int64, P, POINTER(c_int64), P]),
         "ghf_text_encode": (c_int, [P, P, P, c_int64, P, c_int, P, P, c_int, P, P]),
         "ghf_linear": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P, P]),
-        "ghf_linear_f16out": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P, P, P]),
+        "ghf_linear_f16out": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P, P, P, P]),
         "ghf_graph_build": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int32, c_int32, c_int64, c_int64,
                                     c_int32, c_int32, POINTER(c_void_p), P]),
         "ghf_graph_free": (None, [P]),
@@ -61,9 +61,9 @@ def lib():
         "ghf_graph_export": (c_int, [P, P, P, P, P, P, P, P]),
         "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
-        "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P]),
-        "ghf_convert_f16": (c_int, [P, c_int64, P, P]),
-        "ghf_f16_overflow": (c_int, [c_int, POINTER(c_int), P]),
+        "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
+        "ghf_absmax": (c_int, [P, c_int64, P, P]),
+        "ghf_convert_f16": (c_int, [P, c_int64, P, P, c_int, P]),
         "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
                                               c_int64, P, P, P, P]),
         "ghf_launch_count": (c_int64, [c_int]),
@@ -84,7 +84,7 @@ EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
     "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_convert_f16", "ghf_f16_overflow", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -147,8 +147,22 @@ def profile_read():
 
 
 # ----------------------------------------------------------------------------- ops
+class Shadow:
+    """fp16 shadow of a float32 feature matrix: `data` (float16) and `scale` (float32[2] on the device) with
+    features = data * scale[0]; scale[0] is an exact power of two chosen on the device, scale[1] = max |features|."""
+
+    def __init__(self, data: torch.Tensor, scale: torch.Tensor = None):
+        if data.dtype != torch.float16 or not data.is_contiguous():
+            raise RuntimeError("Shadow data must be a contiguous float16 tensor")
+        self.data = data
+        self.scale = torch.zeros(2, dtype=torch.float32, device=data.device) if scale is None else scale
+
+    def rows(self, lo: int, hi: int) -> "Shadow":
+        return Shadow(self.data[lo:hi], self.scale)
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_scale=None, want_f16: bool = False):
-    """exp(log_scale) * act(x @ weight.T + bias); x [M,K] float32 CUDA.  want_f16: -> (y, fp16 copy of y)."""
+    """exp(log_scale) * act(x @ weight.T + bias); x [M,K] float32 CUDA.  want_f16: -> (y, Shadow of y)."""
     x, weight = _f32(x), _f32(weight)
     dev = x.device
     M, K = x.shape
@@ -158,33 +172,31 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_
     bias = None if bias is None else _f32(bias)
     log_scale = None if log_scale is None else _f32(log_scale)
     y = torch.empty((M, N), dtype=torch.float32, device=dev)
-    y16 = torch.empty((M, N), dtype=torch.float16, device=dev) if want_f16 else None
+    y16 = Shadow(torch.empty((M, N), dtype=torch.float16, device=dev)) if want_f16 else None
     with torch.cuda.device(dev):
         _check(lib().ghf_linear_f16out(_ptr(x), M, K, _ptr(weight), _ptr(bias), N, int(relu), _ptr(log_scale),
-                                       _ptr(y), _ptr(y16), _stream(dev)), "ghf_linear_f16out")
+                                       _ptr(y), _ptr(y16.data) if y16 else None, _ptr(y16.scale) if y16 else None,
+                                       _stream(dev)), "ghf_linear_f16out")
     return (y, y16) if want_f16 else y
 
 
-def to_f16(x: torch.Tensor, out=None) -> torch.Tensor:
-    """fp16 copy of a float32 CUDA tensor (numel % 8 == 0): the shadow of h the PREC_F16 contraction gathers."""
+def absmax(x: torch.Tensor, shadow: Shadow) -> None:
+    """shadow.scale[1] = max |x| (float32 CUDA, numel % 8 == 0)."""
     x = _f32(x)
-    if out is None:
-        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
-    elif out.dtype != torch.float16 or out.shape != x.shape or not out.is_contiguous():
-        raise RuntimeError("to_f16: out must be a contiguous float16 tensor of the same shape")
     with torch.cuda.device(x.device):
-        _check(lib().ghf_convert_f16(_ptr(x), x.numel(), _ptr(out), _stream(x.device)), "ghf_convert_f16")
-    return out
+        _check(lib().ghf_absmax(_ptr(x), x.numel(), _ptr(shadow.scale), _stream(x.device)), "ghf_absmax")
 
 
-def f16_overflow(device, reset: bool = True, read: bool = True) -> bool:
-    """PREC_F16 range guard: True when a kernel wrote a value beyond the fp16 range into an fp16 shadow of h since
-    the last reset (synchronises when `read`; with read=False it only clears the flag, stream-ordered)."""
-    v = c_int(0)
-    with torch.cuda.device(device):
-        _check(lib().ghf_f16_overflow(int(reset), ctypes.byref(v) if read else None, _stream(device)),
-               "ghf_f16_overflow")
-    return bool(v.value)
+def to_f16(x: torch.Tensor, shadow: Shadow, have_amax: bool = False) -> Shadow:
+    """shadow.data = fp16(x * 2^k) with the scale picked on the device from max |x| (from shadow.scale[1] when
+    `have_amax`, e.g. after an all-reduce over ranks; computed here otherwise)."""
+    x = _f32(x)
+    if shadow.data.shape != x.shape:
+        raise RuntimeError("to_f16: shadow and x must have the same shape")
+    with torch.cuda.device(x.device):
+        _check(lib().ghf_convert_f16(_ptr(x), x.numel(), _ptr(shadow.data), _ptr(shadow.scale), int(have_amax),
+                                     _stream(x.device)), "ghf_convert_f16")
+    return shadow
 
 
 def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor, subset=None):
@@ -295,8 +307,8 @@ class Graph:
                  want_upd: bool = False, h16=None, out16=None):
         """One message-passing layer on this graph's destination range -> (out, upd or None).
 
-        `h16` (float16 [N, d], optional) is the fp16 copy of `h` the PREC_F16 contraction gathers from (made
-        inside when absent); `out16` (float16 [local nodes, d], optional) receives the fp16 copy of `out`."""
+        `h16` (Shadow of [N, d], optional) is the fp16 shadow of `h` the PREC_F16 contraction gathers from (made
+        inside when absent); `out16` (Shadow of [local nodes, d], optional) receives the shadow of `out`."""
         dev = self.device
         h, W_msg, W_self, bias = _f32(h), _f32(W_msg), _f32(W_self), _f32(bias)
         ln_w, ln_b = _f32(ln_w), _f32(ln_b)
@@ -312,12 +324,14 @@ class Graph:
             raise RuntimeError("out must be a contiguous float32 [local nodes, d] tensor")
         upd = torch.empty_like(out) if want_upd else None
         for name, t, rows in (("h16", h16, self.num_nodes), ("out16", out16, self.num_local)):
-            if t is not None and (t.dtype != torch.float16 or t.shape != (rows, d) or not t.is_contiguous()):
-                raise RuntimeError(f"{name} must be a contiguous float16 [{rows},{d}] tensor")
+            if t is not None and (not isinstance(t, Shadow) or t.data.shape != (rows, d)):
+                raise RuntimeError(f"{name} must be a Shadow of a [{rows},{d}] matrix")
         ws = self.workspace(precision)
         with torch.cuda.device(dev):
-            _check(lib().ghf_mp_layer_f16(self._h, _ptr(h), _ptr(h16), _ptr(W_msg), _ptr(W_self), _ptr(bias),
-                                          _ptr(ln_w), _ptr(ln_b), float(eps), precision, _ptr(out), _ptr(out16),
+            _check(lib().ghf_mp_layer_f16(self._h, _ptr(h), _ptr(h16.data) if h16 else None,
+                                          _ptr(h16.scale) if h16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
+                                          _ptr(ln_w), _ptr(ln_b), float(eps), precision, _ptr(out),
+                                          _ptr(out16.data) if out16 else None, _ptr(out16.scale) if out16 else None,
                                           _ptr(upd), _ptr(ws), _stream(dev)), "ghf_mp_layer_f16")
         return out, upd
 

@@ -57,8 +57,9 @@ class ShardedForward:
 
     def _buffers16(self, device, d):
         if getattr(self, "_bufs16", None) is None:
+            from . import _native
             shape = (self.rows * self.world, d)
-            self._bufs16 = [torch.zeros(shape, dtype=torch.float16, device=device) for _ in range(2)]
+            self._bufs16 = [_native.Shadow(torch.zeros(shape, dtype=torch.float16, device=device)) for _ in range(2)]
         return self._bufs16
 
     def forward_packed(self, node_features, edge_index, utf8, offsets) -> torch.Tensor:
@@ -79,16 +80,7 @@ class ShardedForward:
         prec = m._precision_code()
         cur, nxt = self._buffers(node_features.device, d)
         if prec == _native.PREC_F16:
-            dev = node_features.device
-            _native.f16_overflow(dev, reset=True, read=False)
-            out = self._forward_f16(node_features, graph, packed, cur, nxt)
-            # range guard: if any rank wrote a value beyond the fp16 range, every rank redoes the tf32 path
-            flag = torch.tensor([int(_native.f16_overflow(dev))], device=dev, dtype=torch.int32)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-            if int(flag.item()) == 0:
-                return out
-            prec = _native.PREC_TF32
-            cur, nxt = self._bufs
+            return self._forward_f16(node_features, graph, packed, cur, nxt)
         with torch.no_grad():
             # every rank projects all nodes (h is needed in full as the gather source)
             cur[:N] = _native.linear(node_features, m.input_proj.weight, m.input_proj.bias, relu=True)
@@ -114,10 +106,17 @@ class ShardedForward:
         N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
         cur16, nxt16 = self._buffers16(node_features.device, d)
         with torch.no_grad():
+            cur16.scale.zero_()
             if hi > lo:
                 cur[lo:hi] = _native.linear(node_features[lo:hi], m.input_proj.weight, m.input_proj.bias, relu=True)
-                _native.to_f16(cur[lo:hi], out=cur16[lo:hi])
-            gather_rows(cur16, self.rows, self.rank, self.group)
+                _native.absmax(cur[lo:hi], cur16)
+            # one scale for the whole shadow: the ranks agree on max |h0| first (a 4-byte all-reduce, stream-ordered)
+            dist.all_reduce(cur16.scale[1:2], op=dist.ReduceOp.MAX, group=self.group)
+            if hi > lo:
+                _native.to_f16(cur[lo:hi], cur16.rows(lo, hi), have_amax=True)
+            else:
+                _native.to_f16(cur[:0], cur16.rows(0, 0), have_amax=True)   # still writes the scale
+            gather_rows(cur16.data, self.rows, self.rank, self.group)
             text_embs = m.text_encoder.encode_packed(packed)
             for l in range(m.num_layers):
                 w = m._generate(l, text_embs, packed.num_unique)
@@ -125,9 +124,9 @@ class ShardedForward:
                 last = l + 1 == m.num_layers
                 if hi > lo:
                     graph.mp_layer(cur[:N], w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps,
-                                   _native.PREC_F16, out=nxt[lo:hi], h16=cur16[:N],
-                                   out16=None if last else nxt16[lo:hi])
-                gather_rows(nxt if last else nxt16, self.rows, self.rank, self.group)
+                                   _native.PREC_F16, out=nxt[lo:hi], h16=cur16.rows(0, N),
+                                   out16=None if last else nxt16.rows(lo, hi))
+                gather_rows(nxt if last else nxt16.data, self.rows, self.rank, self.group)
                 cur, nxt, cur16, nxt16 = nxt, cur, nxt16, cur16
         self._bufs, self._bufs16 = [cur, nxt], [cur16, nxt16]
         return cur[:N]

@@ -232,40 +232,29 @@ class HyperGNN(nn.Module):
             raise RuntimeError("forward_prepared needs a full-range graph; see distributed.ShardedHyperGNN")
         prec = self._precision_code()
         with torch.no_grad():
+            h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
+            if prec == _native.PREC_F16 and node_features.size(0) * self.hidden_dim % 8 == 0:
+                h, h16 = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True,
+                                        want_f16=True)
+            else:
+                h = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True)
             text_embs = self.text_encoder.encode_packed(packed)
             if taps is not None:
-                taps["edge_rel_ids"], taps["text_embs"] = packed.rel_ids, text_embs
+                taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
                 taps["in_degree"] = graph.export()["indeg"]
-            if prec == _native.PREC_F16:
-                _native.f16_overflow(node_features.device, reset=True, read=False)
-            h = self._layers(node_features, graph, packed, text_embs, prec, taps)
-            if prec == _native.PREC_F16 and _native.f16_overflow(node_features.device):
-                # range guard: some |h| exceeded the fp16 range (65504) - redo on the tf32 path
-                h = self._layers(node_features, graph, packed, text_embs, _native.PREC_TF32, taps)
-        return h
-
-    def _layers(self, node_features, graph, packed, text_embs, prec: int, taps: Optional[dict]) -> torch.Tensor:
-        """Input projection and the message-passing layers at one precision (HG:261, HG:272-296)."""
-        h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
-        if prec == _native.PREC_F16 and node_features.size(0) * self.hidden_dim % 8 == 0:
-            h, h16 = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True,
-                                    want_f16=True)
-        else:
-            h = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True)
-        if taps is not None:
-            taps["h0"] = h
-        for l in range(self.num_layers):
-            w = self._generate(l, text_embs, packed.num_unique)
-            ln = self.layer_norms[l]
-            out16 = None
-            if prec == _native.PREC_F16 and l + 1 < self.num_layers:
-                out16 = torch.empty((graph.num_local, self.hidden_dim), dtype=torch.float16, device=h.device)
-            h, upd = graph.mp_layer(h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
-                                    want_upd=taps is not None, h16=h16, out16=out16)
-            h16 = out16
-            if taps is not None:
-                taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
-                taps[f"upd.{l}"], taps[f"h.{l}"] = upd, h
+            for l in range(self.num_layers):
+                w = self._generate(l, text_embs, packed.num_unique)
+                ln = self.layer_norms[l]
+                out16 = None
+                if prec == _native.PREC_F16 and l + 1 < self.num_layers:
+                    out16 = _native.Shadow(torch.empty((graph.num_local, self.hidden_dim), dtype=torch.float16,
+                                                       device=h.device))
+                h, upd = graph.mp_layer(h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
+                                        want_upd=taps is not None, h16=h16, out16=out16)
+                h16 = out16
+                if taps is not None:
+                    taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
+                    taps[f"upd.{l}"], taps[f"h.{l}"] = upd, h
         return h
 
     def _generate(self, layer: int, text_embs: torch.Tensor, num_unique: int) -> dict:

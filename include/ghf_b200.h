@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GHF_ABI_VERSION 2
+#define GHF_ABI_VERSION 3
 
 /* precision of the relation-typed contraction in ghf_mp_layer */
 #define GHF_PREC_FP32 0 /* CUDA-core FFMA, fp32 end to end (rtol 1e-5 vs reference)          */
@@ -69,11 +69,17 @@ int ghf_text_encode(const uint8_t* d_utf8, const int64_t* d_offsets, const int64
 int ghf_linear(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
                int relu, const float* d_log_scale, float* d_Y, void* stream);
 
-/* ghf_linear plus an fp16 copy of Y in d_Y16 ([M,N], may be NULL): the node-feature projection (HG:261) emits
- * the fp16 shadow of h that GHF_PREC_F16 gathers from in the same pass (fused on the tcgen05 path; otherwise a
- * conversion pass follows, which needs M*N % 8 == 0 and 16-byte aligned pointers). */
+/* fp16 SHADOW of a feature matrix (GHF_PREC_F16): a pair (d_y16, d_scale) with d_scale = float[2] in device
+ * memory: y = y16 * d_scale[0] (an exact power of two, chosen on the device so that the largest magnitude lands in
+ * [2^13, 2^14) - no host round trip, no dependence on the data range), d_scale[1] = max |y|.
+ *
+ * ghf_linear plus an fp16 shadow of Y in (d_Y16 [M,N], d_Y16_scale), both NULL for none: the node-feature
+ * projection (HG:261) emits the shadow of h that GHF_PREC_F16 gathers from in the same pass (fused on the tcgen05
+ * path: written unscaled with its range, rewritten by a rescue pass only if the range demands a scale; otherwise
+ * a range pass and a conversion pass follow, which need M*N % 8 == 0 and 16-byte aligned pointers). */
 int ghf_linear_f16out(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
-                      int relu, const float* d_log_scale, float* d_Y, void* d_Y16, void* stream);
+                      int relu, const float* d_log_scale, float* d_Y, void* d_Y16, float* d_Y16_scale,
+                      void* stream);
 
 /* ---- graph preprocessing (replaces the per-call gathers HG:281-283, scatter index HG:207-219)
  * Builds, for destinations dst in [dst_lo, dst_hi):
@@ -109,27 +115,25 @@ int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, con
                  const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
                  int precision, float* d_out, float* d_upd, void* d_workspace, void* stream);
 
-/* The same layer with the fp16 shadow copy of the node features made explicit (GHF_PREC_F16 chains it from
- * layer to layer instead of re-converting):
- *   d_h16     [num_nodes, d] fp16 copy of d_h, or NULL (then it is made inside, in the workspace).  When it is
- *             given, d_h is only read at rows [dst_lo, dst_hi) (residual), so a multi-GPU caller needs to
- *             all-gather only the fp16 copy between layers.
- *   d_out16   [local nodes, d] fp16 copy of d_out for the next layer, or NULL (hidden_dim 32/64/128).
- * With precision FP32 / TF32 this is ghf_mp_layer plus the optional d_out16. */
-int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_W_msg,
-                     const float* d_W_self, const float* d_bias, const float* d_ln_w, const float* d_ln_b,
-                     float eps, int precision, float* d_out, void* d_out16, float* d_upd, void* d_workspace,
-                     void* stream);
+/* The same layer with the fp16 shadow of the node features made explicit (GHF_PREC_F16 chains it from layer to
+ * layer instead of re-converting):
+ *   (d_h16, d_h16_scale)       shadow of d_h ([num_nodes, d] fp16 + float[2]), or NULL/NULL (then it is made inside,
+ *                              in the workspace).  When given, d_h is only read at rows [dst_lo, dst_hi)
+ *                              (residual), so a multi-GPU caller all-gathers only the fp16 rows between layers.
+ *   (d_out16, d_out16_scale)   shadow of d_out ([local nodes, d] fp16 + float[2]) for the next layer, or NULL/NULL
+ *                              (hidden_dim 32/64/128).  Its scale follows from ln_w / ln_b alone
+ *                              (|LayerNorm(x)_c| <= sqrt(d-1)|w_c| + |b_c|), so every rank picks the same one.
+ * With precision FP32 / TF32 this is ghf_mp_layer plus the optional output shadow. */
+int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                     const float* d_W_msg, const float* d_W_self, const float* d_bias, const float* d_ln_w,
+                     const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
+                     float* d_out16_scale, float* d_upd, void* d_workspace, void* stream);
 
-/* d_y16[i] = fp16(d_x[i]) (round to nearest even) for `elems` values; elems % 8 == 0, 16-byte aligned pointers.
- * The fp16 shadow copy of h that GHF_PREC_F16 gathers from (layer 0; later layers get it from d_out16). */
-int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, void* stream);
-
-/* GHF_PREC_F16 range guard.  Every kernel that writes an fp16 shadow of h (ghf_convert_f16, ghf_linear_f16out,
- * ghf_mp_layer_f16 with d_out16) raises a device flag when a magnitude exceeds the fp16 range (65504).  This call
- * returns the flag in *h_flag (0 / 1), optionally clears it, and synchronises `stream`.  A caller that sees 1
- * discards the result and reruns with GHF_PREC_TF32 (the Python mirror and ghf_hypergnn_forward_host do). */
-int ghf_f16_overflow(int reset, int* h_flag, void* stream);
+/* Building a shadow by hand (layer 0 of a multi-GPU run, where max|h| must be agreed between ranks first):
+ * ghf_absmax writes d_scale[1] = max |x|; ghf_convert_f16 picks the scale from d_scale[1] (computing it first when
+ * have_amax == 0), writes d_scale[0] and d_y16 = fp16(x * 2^k).  elems % 8 == 0, 16-byte aligned pointers. */
+int ghf_absmax(const float* d_x, int64_t elems, float* d_scale, void* stream);
+int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, float* d_scale, int have_amax, void* stream);
 
 /* ---- whole forward from HOST buffers (HG:236-298): the end-to-end entry point --------------
  * Parameters are passed as one flat array of DEVICE pointers in reference state_dict order

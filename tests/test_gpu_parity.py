@@ -258,27 +258,33 @@ def test_linear_tcgen05_generator_shape(M, N):
     assert_close(got, want, FP32_RTOL, 2e-6 * float(np.abs(want).max()), "generator linear 3xTF32")
 
 
-def test_f16_range_guard_falls_back_to_tf32():
-    """Features beyond the fp16 range (|h| > 65504) must not poison the f16 path: the overflow flag is raised by
-    the kernels that write the fp16 shadow and the forward is redone on the tf32 path."""
-    from graph_hypernetwork_forge import HyperGNN, _native
+def test_f16_large_and_tiny_features_are_rescaled():
+    """Features far outside the fp16 range (|h0| ~ 1e6, and ~ 1e-7) must not poison the f16 path: the fp16 shadow of
+    h carries an exact power-of-two scale chosen on the device (no host round trip)."""
+    from graph_hypernetwork_forge import HyperGNN
     N, E, R, d, L = 2000, 20000, 7, 128, 2
     src, dst, rel, names, feats = O.synthetic_kg(N, E, R, 24, seed=11)
-    feats = (feats * 3e5).astype(np.float32)          # relu(x W^T + b) reaches ~1e6
     texts = [names[r] for r in rel]
-    torch.manual_seed(4)
-    model = HyperGNN(32, 24, d, L, precision="f16").eval()
-    params = model_params_numpy(model)
-    ref = O.hypergnn_forward(params, feats, np.stack([src, dst]), texts, d, L, dtype=np.float64)
-    model = model.to(DEV)
     ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
-    out = model(torch.from_numpy(feats).to(DEV), ei, texts).cpu().numpy()
-    assert np.isfinite(out).all()
-    assert_close(out, ref, 0.0, TF32_H_ATOL_INIT * 10, "out after the tf32 fallback")
-    # the flag was consumed; an in-range forward does not raise it
-    x_ok = torch.from_numpy((feats / 3e5).astype(np.float32)).to(DEV)
-    model(x_ok, ei, texts)
-    assert not _native.f16_overflow(torch.device(DEV))
+    for factor in (3e5, 1e-7, 1.0):
+        x = (feats * factor).astype(np.float32)
+        torch.manual_seed(4)
+        model = HyperGNN(32, 24, d, L, precision="f16").eval()
+        with torch.no_grad():
+            model.input_proj.bias.zero_()               # h0 scales with the features
+            for gen in model.weight_generators:
+                for p in gen.log_scales.values():
+                    p.fill_(-1.0)
+        params = model_params_numpy(model)
+        ref_taps = {}
+        ref = O.hypergnn_forward(params, x, np.stack([src, dst]), texts, d, L, dtype=np.float64, taps=ref_taps)
+        taps = {}
+        model = model.to(DEV)
+        out = model.forward_prepared(torch.from_numpy(x).to(DEV), model.prepare(ei, texts, N), taps=taps)
+        out = out.cpu().numpy()
+        assert np.isfinite(out).all()
+        assert_rel_to_max(taps["upd.0"].cpu().numpy(), ref_taps["upd.0"], TF32_UPD_REL, f"upd.0 at x * {factor:g}")
+        assert_close(out, ref, 0.0, TF32_H_ATOL_SCALE1, f"out at x * {factor:g}")
 
 
 def test_ids_in_api_matches_string_api():

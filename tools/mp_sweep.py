@@ -53,7 +53,9 @@ for spec in args or ["0,0,7"]:
     text = model.text_encoder.encode_packed(prepared.packed)
     wts = model.weight_generators[0](text)
     ln = model.layer_norms[0]
-    h16 = h.half() if PREC == _native.PREC_F16 else None   # as chained from the previous layer
+    h16 = None
+    if PREC == _native.PREC_F16:                             # as chained from the previous layer
+        h16 = _native.to_f16(h, _native.Shadow(torch.empty(h.shape, dtype=torch.float16, device=dev)))
     for _ in range(2):
         g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias, 1e-5, PREC, h16=h16)
     torch.cuda.synchronize()
