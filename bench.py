@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "tf32", "fp32"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and E (debugging only; not a bench number)")
     ap.add_argument("--skew", action="store_true", help="Zipf destinations/relations (secondary workload)")
+    ap.add_argument("--python-path", action="store_true",
+                    help="enqueue the stages from Python (prepare_packed + forward_prepared) instead of one native call")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -228,8 +230,9 @@ def main():
 
     if world == 1:
         def step():
-            prepared = model.prepare_packed(edge_index, utf8, offsets, N)
-            return model.forward_prepared(x, prepared)
+            if args.python_path:    # the same stages enqueued one by one from Python (~60 native calls per forward)
+                return model.forward_prepared(x, model.prepare_packed(edge_index, utf8, offsets, N))
+            return model.forward_packed(x, edge_index, utf8, offsets)   # one native call per forward
         n_local = N
     else:
         from graph_hypernetwork_forge.distributed import ShardedForward

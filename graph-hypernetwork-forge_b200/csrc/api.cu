@@ -1,6 +1,7 @@
 // api.cu — library-wide state and ghf_hypergnn_forward_host, the end-to-end entry point that takes
 // HOST buffers (the shape of the reference's HyperGNN.forward, HG:236-298, at a C boundary).
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -63,14 +64,47 @@ struct LayerParams {
   const float *ln_w, *ln_b;
 };
 
+// Grow-only device arenas for the scratch of the whole-forward entry points (per device, two generations: sizes
+// known at entry, and sizes known after dedup + graph build).  The stream-ordered pool is fine for the small
+// scratch inside the stages, but re-allocating gigabytes from it on every call costs milliseconds of host time
+// with the GPU idle.  One forward at a time per device (the entry points hold a lock).
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  cudaError_t reserve(size_t bytes) {
+    used = 0;
+    if (bytes <= cap) return cudaSuccess;
+    if (base) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) return e;
+      cudaFree(base);
+      base = nullptr;
+      cap = 0;
+    }
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&base), want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T>
+  T* take(size_t n) {
+    const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    T* p = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return p;
+  }
+  static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+};
+Arena g_arena[64][2];
+std::mutex g_forward_lock;
+
 }  // namespace
 
-extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float* const* d_params,
-                                         int64_t n_params, const float* h_node_features, int64_t num_nodes,
-                                         const int64_t* h_edge_index, int64_t E, const uint8_t* h_utf8,
-                                         const int64_t* h_offsets, float* h_out, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  GHF_REQUIRE(desc && d_params, "ghf_hypergnn_forward_host: NULL model");
+// The whole forward on DEVICE buffers (HG:236-298); d_out receives the final embeddings [num_nodes, d].
+static int forward_device_impl(const ghf_model_desc* desc, const float* const* d_params, int64_t n_params,
+                               const float* d_x, int64_t num_nodes, const int64_t* d_ei, int64_t E,
+                               const uint8_t* d_utf8, const int64_t* d_offs, float* d_out, cudaStream_t stream) {
+  GHF_REQUIRE(desc && d_params, "ghf_hypergnn_forward: NULL model");
   const int T = desc->text_dim, F = desc->node_feat_dim, d = desc->hidden_dim, L = desc->num_layers;
   const int C = desc->char_emb_dim, H = desc->gen_hidden, depth = desc->gen_depth;
   GHF_REQUIRE(L >= 1, "num_layers must be at least 1");
@@ -96,41 +130,35 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
     }
   }
 
-  const int64_t text_bytes = E > 0 ? h_offsets[E] : 0;
   const bool want_f16 = desc->precision == GHF_PREC_F16 && d == 128;
-  TempBuf x, ei, utf8, offs, rel, first, h0, h1, temb, h16_0, scales;
-  GHF_CUDA(scales.alloc(4 * sizeof(float), stream));   // scale words of the two fp16 shadows (float[2] each)
-  if (want_f16) GHF_CUDA(h16_0.alloc(num_nodes * (size_t)d * 2, stream));   // fp16 shadow of h0 (h16_0.p stays NULL otherwise)
-  GHF_CUDA(x.alloc(num_nodes * (size_t)F * 4, stream));
-  GHF_CUDA(ei.alloc(2 * E * sizeof(int64_t), stream));
-  GHF_CUDA(utf8.alloc(text_bytes, stream));
-  GHF_CUDA(offs.alloc((E + 1) * sizeof(int64_t), stream));
-  GHF_CUDA(rel.alloc(E * sizeof(int32_t), stream));
-  GHF_CUDA(first.alloc(E * sizeof(int64_t), stream));
-  GHF_CUDA(h0.alloc(num_nodes * (size_t)d * 4, stream));
-  GHF_CUDA(h1.alloc(num_nodes * (size_t)d * 4, stream));
-  GHF_CUDA(cudaMemcpyAsync(x.p, h_node_features, num_nodes * (size_t)F * 4, cudaMemcpyHostToDevice, stream));
-  GHF_CUDA(cudaMemcpyAsync(ei.p, h_edge_index, 2 * E * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
-  GHF_CUDA(cudaMemcpyAsync(utf8.p, h_utf8, text_bytes, cudaMemcpyHostToDevice, stream));
-  GHF_CUDA(cudaMemcpyAsync(offs.p, h_offsets, (E + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  std::lock_guard<std::mutex> lock(g_forward_lock);
+  int dev = 0;
+  GHF_CUDA(cudaGetDevice(&dev));
+  GHF_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  Arena& A = g_arena[dev][0];
+  Arena& B = g_arena[dev][1];
+  const size_t hbytes = (size_t)num_nodes * d * 4;
+  GHF_CUDA(A.reserve(Arena::padded(16) + Arena::padded(E * sizeof(int32_t)) + Arena::padded(E * sizeof(int64_t)) +
+                     2 * Arena::padded(hbytes) + (want_f16 ? 2 * Arena::padded(hbytes / 2) : 0) + 4096));
+  float* scales = A.take<float>(4);                     // scale words of the two fp16 shadows (float[2] each)
+  int32_t* rel = A.take<int32_t>(E > 0 ? E : 1);
+  int64_t* first = A.take<int64_t>(E > 0 ? E : 1);
+  float* h0 = A.take<float>((size_t)num_nodes * d);
+  float* h1 = A.take<float>((size_t)num_nodes * d);
+  void* h16_0 = want_f16 ? A.take<uint16_t>((size_t)num_nodes * d) : nullptr;   // fp16 shadow buffers (ping-pong)
+  void* h16_1 = want_f16 ? A.take<uint16_t>((size_t)num_nodes * d) : nullptr;
 
-  // HG:261  h = relu(input_proj(x))
-  if (int rc = ghf_linear_f16out(x.as<float>(), num_nodes, F, Win, bin, d, 1, nullptr, h0.as<float>(), h16_0.p,
-                                 want_f16 ? scales.as<float>() : nullptr, stream))
+  // HG:261  h = relu(input_proj(x))  (+ the fp16 shadow of h on the f16 path)
+  if (int rc = ghf_linear_f16out(d_x, num_nodes, F, Win, bin, d, 1, nullptr, h0, h16_0, want_f16 ? scales : nullptr,
+                                 stream))
     return rc;
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
-  if (int rc = ghf_dedup_texts(utf8.as<uint8_t>(), offs.as<int64_t>(), E, nullptr, 0, rel.as<int32_t>(),
-                               first.as<int64_t>(), &U, stream))
-    return rc;
-  GHF_CUDA(temb.alloc((U > 0 ? U : 1) * (size_t)T * 4, stream));
-  if (int rc = ghf_text_encode(utf8.as<uint8_t>(), offs.as<int64_t>(), first.as<int64_t>(), U, emb, C, Wp, bp, T,
-                               temb.as<float>(), stream))
-    return rc;
+  if (int rc = ghf_dedup_texts(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream)) return rc;
 
   ghf_graph* g = nullptr;
-  if (int rc = ghf_graph_build(ei.as<int64_t>(), E, nullptr, 0, rel.as<int32_t>(), num_nodes,
-                               (int32_t)(U > 0 ? U : 1), d, 0, num_nodes, 0, 0, &g, stream))
+  if (int rc = ghf_graph_build(d_ei, E, nullptr, 0, rel, num_nodes, (int32_t)(U > 0 ? U : 1), d, 0, num_nodes, 0, 0,
+                               &g, stream))
     return rc;
   struct Guard {
     ghf_graph* g;
@@ -140,32 +168,32 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
   const int prec = (desc->precision == GHF_PREC_F16 && d == 128) ? GHF_PREC_F16
                    : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
                                                                                            : GHF_PREC_FP32;
-  const int64_t Un = U > 0 ? U : 1;
-  TempBuf wmsg, wself, wbias, hid_a, hid_b, ws, h16a;
-  if (prec == GHF_PREC_F16)  // second fp16 shadow buffer: layer outputs ping-pong between h16_0 and h16a
-    GHF_CUDA(h16a.alloc(num_nodes * (size_t)d * 2, stream));
-  GHF_CUDA(wmsg.alloc(Un * (size_t)d * d * 4, stream));
-  GHF_CUDA(wself.alloc(Un * (size_t)d * d * 4, stream));
-  GHF_CUDA(wbias.alloc(Un * (size_t)d * 4, stream));
-  GHF_CUDA(hid_a.alloc(Un * (size_t)(H > 0 ? H : 1) * 4, stream));
-  GHF_CUDA(hid_b.alloc(Un * (size_t)(H > 0 ? H : 1) * 4, stream));
-  GHF_CUDA(ws.alloc(ghf_mp_workspace_bytes(g, d, prec), stream));
-  float* outs[3] = {wmsg.as<float>(), wself.as<float>(), wbias.as<float>()};
+  // second arena: everything whose size depends on the number of distinct relations or on the graph tables
+  const size_t Un = (size_t)(U > 0 ? U : 1), Hn = (size_t)(H > 0 ? H : 1);
+  const size_t ws_bytes = (size_t)ghf_mp_workspace_bytes(g, d, prec);
+  GHF_CUDA(B.reserve(Arena::padded(Un * T * 4) + 2 * Arena::padded(Un * d * d * 4) + Arena::padded(Un * d * 4) +
+                     2 * Arena::padded(Un * Hn * 4) + Arena::padded(ws_bytes) + 4096));
+  float* temb = B.take<float>(Un * T);
+  float* outs[3] = {B.take<float>(Un * d * d), B.take<float>(Un * d * d), B.take<float>(Un * d)};
+  float* hid_a = B.take<float>(Un * Hn);
+  float* hid_b = B.take<float>(Un * Hn);
+  void* ws = B.take<char>(ws_bytes);
   const int n_out[3] = {d * d, d * d, d};
+  if (int rc = ghf_text_encode(d_utf8, d_offs, first, U, emb, C, Wp, bp, T, temb, stream)) return rc;
 
-  float* cur = h0.as<float>();
-  float* nxt = h1.as<float>();
-  void* cur16 = prec == GHF_PREC_F16 ? h16_0.p : nullptr;   // fp16 shadow of `cur` and its scale words
-  void* nxt16 = h16a.p;
-  float* cur_sc = scales.as<float>();
-  float* nxt_sc = scales.as<float>() + 2;
+  float* cur = h0;
+  float* nxt = h1;
+  void* cur16 = prec == GHF_PREC_F16 ? h16_0 : nullptr;   // fp16 shadow of `cur` and its scale words
+  void* nxt16 = h16_1;
+  float* cur_sc = scales;
+  float* nxt_sc = scales + 2;
   for (int l = 0; l < L; ++l) {
     // WG:137-141 for the U distinct relations
     for (int m = 0; m < 3 && U > 0; ++m) {
-      const float* in = temb.as<float>();
+      const float* in = temb;
       int in_dim = T;
       for (int i = 0; i < depth; ++i) {
-        float* o = (i & 1) ? hid_b.as<float>() : hid_a.as<float>();
+        float* o = (i & 1) ? hid_b : hid_a;
         if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][i], layers[l].b[m][i], H, 1, nullptr, o, stream))
           return rc;
         in = o;
@@ -177,16 +205,50 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
     }
     // HG:286-296
     void* out16 = (prec == GHF_PREC_F16 && l + 1 < L) ? nxt16 : nullptr;
+    float* dst = l + 1 < L ? nxt : d_out;                // the last layer writes the caller's buffer
     if (int rc = ghf_mp_layer_f16(g, cur, cur16, cur16 ? cur_sc : nullptr, outs[0], outs[1], outs[2], layers[l].ln_w,
-                                  layers[l].ln_b, desc->ln_eps, prec, nxt, out16, out16 ? nxt_sc : nullptr, nullptr,
-                                  ws.p, stream))
+                                  layers[l].ln_b, desc->ln_eps, prec, dst, out16, out16 ? nxt_sc : nullptr, nullptr,
+                                  ws, stream))
       return rc;
     float* t = cur; cur = nxt; nxt = t;
     t = cur_sc; cur_sc = nxt_sc; nxt_sc = t;
     cur16 = out16;
-    nxt16 = (nxt16 == h16a.p) ? h16_0.p : h16a.p;
+    nxt16 = (nxt16 == h16_1) ? h16_0 : h16_1;
   }
-  GHF_CUDA(cudaMemcpyAsync(h_out, cur, num_nodes * (size_t)d * 4, cudaMemcpyDeviceToHost, stream));
+  return 0;
+}
+
+extern "C" int ghf_hypergnn_forward_device(const ghf_model_desc* desc, const float* const* d_params,
+                                           int64_t n_params, const float* d_node_features, int64_t num_nodes,
+                                           const int64_t* d_edge_index, int64_t E, const uint8_t* d_utf8,
+                                           const int64_t* d_offsets, float* d_out, void* stream_) {
+  return forward_device_impl(desc, d_params, n_params, d_node_features, num_nodes, d_edge_index, E, d_utf8,
+                             d_offsets, d_out, (cudaStream_t)stream_);
+}
+
+extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float* const* d_params,
+                                         int64_t n_params, const float* h_node_features, int64_t num_nodes,
+                                         const int64_t* h_edge_index, int64_t E, const uint8_t* h_utf8,
+                                         const int64_t* h_offsets, float* h_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(desc && d_params, "ghf_hypergnn_forward_host: NULL model");
+  GHF_REQUIRE(desc->node_feat_dim > 0 && desc->hidden_dim > 0, "bad model dimensions");
+  const int F = desc->node_feat_dim, d = desc->hidden_dim;
+  const int64_t text_bytes = E > 0 ? h_offsets[E] : 0;
+  TempBuf x, ei, utf8, offs, out;
+  GHF_CUDA(x.alloc(num_nodes * (size_t)F * 4, stream));
+  GHF_CUDA(ei.alloc(2 * E * sizeof(int64_t), stream));
+  GHF_CUDA(utf8.alloc(text_bytes, stream));
+  GHF_CUDA(offs.alloc((E + 1) * sizeof(int64_t), stream));
+  GHF_CUDA(out.alloc(num_nodes * (size_t)d * 4, stream));
+  GHF_CUDA(cudaMemcpyAsync(x.p, h_node_features, num_nodes * (size_t)F * 4, cudaMemcpyHostToDevice, stream));
+  GHF_CUDA(cudaMemcpyAsync(ei.p, h_edge_index, 2 * E * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  GHF_CUDA(cudaMemcpyAsync(utf8.p, h_utf8, text_bytes, cudaMemcpyHostToDevice, stream));
+  GHF_CUDA(cudaMemcpyAsync(offs.p, h_offsets, (E + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  if (int rc = forward_device_impl(desc, d_params, n_params, x.as<float>(), num_nodes, ei.as<int64_t>(), E,
+                                   utf8.as<uint8_t>(), offs.as<int64_t>(), out.as<float>(), stream))
+    return rc;
+  GHF_CUDA(cudaMemcpyAsync(h_out, out.p, num_nodes * (size_t)d * 4, cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaStreamSynchronize(stream));
   return 0;
 }

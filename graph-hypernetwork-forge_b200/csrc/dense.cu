@@ -104,9 +104,13 @@ extern "C" int ghf_linear_f16out(const float* d_X, int64_t M, int K, const float
     if (int rc = linear_umma_launch(d_X, M, d_W, d_b, N, relu, d_log_scale, d_Y, d_Y16, d_Y16_scale, stream)) return rc;
     return d_Y16 ? mp_f16_convert(d_Y, M * (int64_t)N, d_Y16, d_Y16_scale, /*rescue=*/true, stream) : 0;
   }
+  // column-tile width: as wide as N allows, narrowed while the grid would leave most SMs idle (the generator's
+  // hidden Linears have a few hundred rows)
+  int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  while (bn > 32 && cdiv(M, kFfmaBM) * cdiv(N, bn) < sm_count()) bn >>= 1;
   int rc;
-  if (N <= 32) rc = launch_linear<32>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
-  else if (N <= 64) rc = launch_linear<64>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
+  if (bn == 32) rc = launch_linear<32>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
+  else if (bn == 64) rc = launch_linear<64>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
   else rc = launch_linear<128>(d_X, M, K, d_W, d_b, N, relu, d_log_scale, d_Y, stream);
   if (rc == 0 && d_Y16) rc = mp_f16_absmax(d_Y, M * (int64_t)N, d_Y16_scale, stream);   // fused only on the tcgen05 path
   if (rc == 0 && d_Y16) rc = mp_f16_convert(d_Y, M * (int64_t)N, d_Y16, d_Y16_scale, /*rescue=*/false, stream);

@@ -200,13 +200,14 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
       out16_scale[1] = bound;
     }
   }
+  // rows are walked from the END: the accumulator rows the contraction touched last are still in L2
   for (int64_t r0 = w0; r0 < num_local; r0 += kRows * warps) {
     float a[kRows][V], hv[kRows][V];
     int deg[kRows];
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
-      const int64_t r = r0 + k * warps;
-      if (r < num_local) {
+      const int64_t r = num_local - 1 - (r0 + k * warps);
+      if (r >= 0) {
         vload_cg<V>(a[k], acc + r * D + lane * V);
         vload_nc<V>(hv[k], h + (dst_lo + r) * D + lane * V);
         deg[k] = __ldg(indeg + r);
@@ -214,8 +215,8 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
     }
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
-      const int64_t r = r0 + k * warps;
-      if (r >= num_local) break;
+      const int64_t r = num_local - 1 - (r0 + k * warps);
+      if (r < 0) break;
       const float inv = 1.f / (float)max(deg[k], 1);
       float x[V], u[V], sum = 0.f;
 #pragma unroll

@@ -22,12 +22,14 @@
 // Sixteen epilogue warps, not eight: a warp's 32 reds of a block go to 32 different rows, and that shape needs
 // 16 warps to saturate the store path (tools/l2_paths.cu: 2.13 ms with 8 warps, 1.42 ms with 16).
 //
-// Warp roles (832 threads, 1 CTA / SM, persistent):
+// Warp roles (832 threads with 4 producer warps, 1 CTA / SM, persistent):
 //   0-15  epilogue (group g = warp/4 owns edges [32g, 32g+32) of each tile, warp%4 = TMEM lane quarter)
-//   16-19 row-gather producers (warp p owns rows [32p, 32p+32) of each tile; ids prefetched one tile ahead)
+//   16-19 weight loaders: global -> registers -> tcgen05.st, one unit ahead of the MMA
 //   20    MMA issuer + TMEM allocator
-//   21    scheduler: draws units from the global counter and publishes TILE descriptors in shared memory
-//   22-25 weight loaders: global -> registers -> tcgen05.st, one unit ahead of the MMA
+//   21    scheduler: draws units from the global counter, publishes TILE descriptors in shared memory and clears
+//         this CTA's share of the next super-block's accumulator rows
+//   22-   row-gather producers (4 by default, 8 with GHF_F16_PROD=8): warp p owns 128/P rows of each tile; ids are
+//         prefetched one tile ahead
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -55,15 +57,26 @@ constexpr int kWarpLoad = kEpiWarps, kWarpMma = kWarpLoad + kLoadWarps, kWarpSch
               kWarpProd = kWarpSched + 1;
 constexpr int threads_for(int prod_warps) { return 32 * (kWarpProd + prod_warps); }
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kWCol = 256;            // first TMEM column of the weight buffers (2 x 128 columns)
+// TMEM: two accumulators [0,256) + two weight buffers [256,512): the next unit's weights load while the current
+// unit computes.
+// What the per-role cycle accounting (GHF_F16_TRACE=1) shows at c3: per 128-edge tile the 512 reds occupy the SM's
+// store path for ~3800 cycles (7.4 cycles per 128 B red), the tensor pipe is busy ~1100 cycles, MMA and producers
+// wait ~2900 cycles for the epilogue; descriptor + barrier + TMEM load cost the epilogue warps ~800 cycles per tile.
+// Tried against that bubble, A/B in one run: two sets of 8 epilogue warps on alternate tiles with three accumulators
+// and one weight buffer (2.25 ms vs 2.23 ms) - no gain, the queued reds already cover the bubble.  The kernel runs
+// at the store-path rate; only fewer or narrower reds would make it faster.
+constexpr int kAccBufs = 2, kWBufs = 2;
+constexpr uint32_t kWCol = kAccBufs * kTile;   // first TMEM column of the weight buffers
+static_assert(kAccBufs * kTile + kWBufs * kD <= 512, "TMEM columns");
 constexpr int kImageBytes = kD * 2 * kD * 2;   // one relation's Wt image: 128 x 256 fp16 = 64 KiB
 constexpr int kBarBytes = 1024;
 constexpr int kSmem = 1024 + kStages * kStageBytes + kQueue * 16 + kBarBytes;
 
-constexpr uint32_t kFlagSrcEvictFirst = 1u, kFlagDstEvictLast = 2u, kFlagRedEvictLast = 4u, kFlagWEvictLast = 8u;
+constexpr uint32_t kFlagSrcEvictFirst = 1u, kFlagDstEvictLast = 2u, kFlagRedEvictLast = 4u, kFlagWEvictLast = 8u,
+                   kFlagWEvictFirst = 16u;
 constexpr uint32_t kDefaultFlags = kFlagSrcEvictFirst | kFlagDstEvictLast | kFlagRedEvictLast;
 // timing experiments only (results are wrong): drop the reductions / the gathers
-constexpr uint32_t kDbgNoRed = 32u, kDbgNoGather = 64u;
+constexpr uint32_t kDbgNoRed = 32u, kDbgNoGather = 64u, kDbgNoClear = 128u;
 
 constexpr uint32_t kTileFirst = 1u, kTileLast = 2u, kTileWbuf = 4u;   // descriptor flags
 
@@ -178,7 +191,7 @@ to_f16_kernel(const float* __restrict__ h, int64_t n8, __half* __restrict__ h16,
   }
 }
 
-template <int kProdWarps>
+template <int kProdWarps, bool kTrace>
 __global__ void __launch_bounds__(threads_for(kProdWarps), 1)
 mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
               const int32_t* __restrict__ unit_rel, int64_t num_units, const int32_t* __restrict__ src_sorted,
@@ -187,7 +200,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
               const float* __restrict__ w_inv_scale,
               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter,
               const int32_t* __restrict__ unit_phase, int* __restrict__ zero_done, int num_phases, int sb_nodes,
-              int64_t num_local, uint32_t flags) {
+              int64_t num_local, uint32_t flags, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sA = (raw + 1023u) & ~1023u;
@@ -196,17 +209,27 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
   auto full = [&](int s) { return sBar + 8u * s; };
   auto empty = [&](int s) { return sBar + 8u * (kStages + s); };
   const uint32_t bar2 = sBar + 8u * (2 * kStages);
-  auto acc_full = [&](int a) { return bar2 + 8u * a; };
-  auto acc_empty = [&](int a) { return bar2 + 16u + 8u * a; };
-  auto w_full = [&](int b) { return bar2 + 32u + 8u * b; };
-  auto w_empty = [&](int b) { return bar2 + 48u + 8u * b; };
-  const uint32_t q_full0 = bar2 + 64u;
+  auto acc_full = [&](int a) { return bar2 + 8u * a; };             // up to 4 accumulators
+  auto acc_empty = [&](int a) { return bar2 + 32u + 8u * a; };
+  auto w_full = [&](int b) { return bar2 + 64u + 8u * b; };          // up to 2 weight buffers
+  auto w_empty = [&](int b) { return bar2 + 80u + 8u * b; };
+  const uint32_t q_full0 = bar2 + 96u;
   const uint32_t q_empty0 = q_full0 + 8u * kQueue;
   const uint32_t tmem_slot = q_empty0 + 8u * kQueue;
   volatile int4* q_ptr = reinterpret_cast<volatile int4*>(smem_raw + (sQ - raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // cycle accounting of CTA 0 (kTrace instantiation only, GHF_F16_TRACE=1): trace[role * 8 + slot] += cycles
+  const bool tracing = kTrace && blockIdx.x == 0 && lane == 0;
+  long long tr[kTrace ? 6 : 1] = {};
+  auto tick = [&]() -> long long {
+    if constexpr (kTrace) return tracing ? clock64() : 0;
+    return 0;
+  };
+  auto tadd = [&](int k, long long v) {
+    if constexpr (kTrace) tr[k] += v;
+  };
   constexpr int kConsumers = kEpiWarps + kProdWarps + 1 + kLoadWarps;   // warps that read every descriptor
   constexpr int kRowsPerWarp = kTile / kProdWarps;                      // 32 or 16
 
@@ -230,11 +253,13 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       mbar_init(full(s), 32 * kProdWarps);  // one cp.async-completion arrival per producer thread
       mbar_init(empty(s), 1);               // tcgen05.commit
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(acc_full(a), 1);            // tcgen05.commit
-      mbar_init(acc_empty(a), kEpiWarps);   // one arrival per epilogue warp
-      mbar_init(w_full(a), 32 * kLoadWarps);
-      mbar_init(w_empty(a), 1);             // tcgen05.commit
+    for (int a = 0; a < kAccBufs; ++a) {
+      mbar_init(acc_full(a), 1);                // tcgen05.commit
+      mbar_init(acc_empty(a), kEpiWarps);       // one arrival per epilogue warp
+    }
+    for (int b = 0; b < kWBufs; ++b) {
+      mbar_init(w_full(b), 32 * kLoadWarps);
+      mbar_init(w_empty(b), 1);                 // tcgen05.commit
     }
     for (int q = 0; q < kQueue; ++q) {
       mbar_init(q_full0 + 8u * q, 1);
@@ -250,39 +275,47 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
 
   if (warp < kEpiWarps) {
     // ------------------------------------------------------------------ epilogue: Dt -> red.f32 rows
+    // All 16 warps work on every tile: group g = warp / 4 owns edges [32g, 32g + 32), warp % 4 = TMEM lane quarter.
     const int grp = warp >> 2, q = warp & 3;
     const int col = 32 * q + lane;                       // this thread's output column = its TMEM lane
     float* acc_col = acc + col;
     const float h_inv = h_scale[0];                      // h = h16 * h_inv (exact power of two)
     const int e0 = 32 * grp;
-    // Everything a tile's reductions need from global memory (the destination id of edge e0 + lane, the
-    // relation's bias entry and scale) is fetched one tile ahead, so that no load latency sits between
-    // "accumulator ready" and the first red.
-    struct TileRegs { int dst; float bias_n, inv; };
+    // Everything a tile's reductions need from global memory (the destination id of edge e0 + lane, the relation's
+    // bias entry and scale) is fetched one tile ahead, so that no load latency sits between "accumulator ready" and
+    // the first red.  (Loaded values are kept raw - arithmetic on them here would wait for the load right away.)
+    struct TileRegs { int dst; float bias_n, w_inv; };
     auto fetch = [&](const int4& t) -> TileRegs {
       TileRegs x{-1, 0.f, 1.f};
       if (t.x < 0) return x;
       if (e0 + lane < t.y) x.dst = dst_sorted[t.x + e0 + lane];
       x.bias_n = bias[(int64_t)t.z * kD + col];
-      x.inv = w_inv_scale[t.z] * h_inv;
+      x.w_inv = w_inv_scale[t.z];
       return x;
     };
     int4 cur = q_acquire(0);
     TileRegs cr = fetch(cur);
     for (uint32_t it = 0; cur.x >= 0; ++it) {
+      long long t0 = tick();
       const int4 nxt = q_acquire(it + 1);
       const TileRegs nr = fetch(nxt);
-      const int a = it & 1;
-      mbar_wait(acc_full(a), (it >> 1) & 1);
+      const int a = (int)(it % kAccBufs);
+      long long t1 = tick();
+      mbar_wait(acc_full(a), (it / kAccBufs) & 1u);
       tc_fence_after();
+      long long t2 = tick();
+      tadd(0, t1 - t0); tadd(1, t2 - t1); tadd(5, 1);
       if (e0 < cur.y) {
+        const float inv = cr.w_inv * h_inv;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kTile + e0), r);
         tmem_ld_wait();
+        t1 = tick();
+        tadd(2, t1 - t2);
         if (!(flags & kDbgNoRed)) {
           // Segmented sum along the sorted order: edges of one (destination, relation) pair are adjacent, so their
           // contributions are added in a register and leave as ONE red (multigraphs, hub destinations); with all
-          // destinations distinct this is one red per edge as before.
+          // destinations distinct this is one red per edge.
           float run = 0.f;
           int run_dst = -1;
 #pragma unroll
@@ -293,18 +326,24 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
               run = 0.f;
               run_dst = dsti;
             }
-            run += fmaf(__uint_as_float(r[e]), cr.inv, cr.bias_n);
+            run += fmaf(__uint_as_float(r[e]), inv, cr.bias_n);
           }
           if (run_dst >= 0) red_add_f32(acc_col + (int64_t)run_dst * kD, run);
         }
+        t2 = tick();
+        tadd(3, t2 - t1);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(a));
       q_release(it);
+      tadd(4, tick() - t2);
       cur = nxt;
       cr = nr;
     }
+    if constexpr (kTrace)
+      if (tracing && warp == 0)                          // acquire+fetch | acc_full wait | tmem ld | reds | release | tiles
+        for (int k = 0; k < 6; ++k) trace[k] = tr[k];
   } else if (warp >= kWarpProd) {
     // ------------------------------------------------------------------ row-gather producers
     // Warp pw owns kRowsPerWarp consecutive rows of every tile; lane l keeps the source and destination id of
@@ -314,11 +353,11 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
     const uint64_t pol_src = (flags & kFlagSrcEvictFirst) ? policy_evict_first() : policy_evict_normal();
     const uint64_t pol_dst = (flags & kFlagDstEvictLast) ? policy_evict_last() : policy_evict_normal();
     const uint8_t* hb = reinterpret_cast<const uint8_t*>(h16) + l16 * 16;
-    struct Ids { int64_t src, dst; };
+    struct Ids { int src, dst; };                        // raw loads: converted where they are used
     auto ids_of = [&](const int4& t) -> Ids {
       const int row = kRowsPerWarp * pw + lane % kRowsPerWarp;
       if (t.x < 0 || row >= t.y) return Ids{-1, -1};
-      return Ids{(int64_t)src_sorted[t.x + row], dst_lo + dst_sorted[t.x + row]};
+      return Ids{src_sorted[t.x + row], dst_sorted[t.x + row]};
     };
     int stage = 0;
     uint32_t phase = 0;
@@ -329,18 +368,21 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       const Ids ids_nxt = ids_of(nxt);                   // in flight while this tile's rows are issued
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {                      // s = 0: source rows, s = 1: destination rows
+        const long long t0 = tick();
         mbar_wait(empty(stage), phase ^ 1u);
+        tadd(0, tick() - t0);
         const uint32_t base = sA + stage * kStageBytes + (l16 >> 3) * kSub;
         const uint64_t pol = s ? pol_dst : pol_src;
-        const int64_t mine = s ? ids.dst : ids.src;
+        const int mine = s ? ids.dst : ids.src;
+        const uint8_t* table = s ? hb + dst_lo * kRowBytes : hb;   // destination ids are local to the rank's range
         if (!(flags & kDbgNoGather)) {
 #pragma unroll
           for (int i = 0; i < kRowsPerWarp / 2; ++i) {
             const int rl = 2 * i + hi;                   // row within the warp's share
-            const int64_t idx = __shfl_sync(0xffffffffu, mine, rl);
+            const int idx = __shfl_sync(0xffffffffu, mine, rl);
             const int row = kRowsPerWarp * pw + rl;
             const uint32_t to = base + row * 128 + (((l16 & 7) ^ (row & 7)) << 4);
-            if (idx >= 0) cp_async_16_hint(to, hb + idx * kRowBytes, pol);
+            if (idx >= 0) cp_async_16_hint(to, table + (int64_t)idx * kRowBytes, pol);
           }
         }
         cp_async_arrive_noinc(full(stage));
@@ -349,29 +391,41 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       q_release(it);
       cur = nxt;
       ids = ids_nxt;
+      tadd(5, 1);
     }
+    if constexpr (kTrace)
+      if (tracing && warp == kWarpProd) {
+        trace[16] = tr[0];                               // empty(stage) wait
+        trace[21] = tr[5];
+      }
   } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
     int stage = 0;
     uint32_t phase = 0, wph = 0;                         // wph bit b: parity of the next w_full(b) wait
+    const long long t_begin = tick();
     for (uint32_t it = 0;; ++it) {
       const int4 t = q_acquire(it);
       if (t.x < 0) break;
       const uint32_t tf = (uint32_t)t.w;
       q_release(it);
-      const int a = it & 1;
+      const int a = (int)(it % kAccBufs);
       const int wb = (tf & kTileWbuf) ? 1 : 0;
-      mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1u);
+      long long t0 = tick();
+      mbar_wait(acc_empty(a), ((it / kAccBufs) & 1u) ^ 1u);
+      long long t1 = tick();
       if (tf & kTileFirst) {
         mbar_wait(w_full(wb), (wph >> wb) & 1u);
         wph ^= 1u << wb;
       }
+      tadd(0, t1 - t0); tadd(1, tick() - t1); tadd(5, 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(a * kTile);
       const uint32_t w_tmem = tmem_base + kWCol + (uint32_t)(wb * kD);
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
+        t0 = tick();
         mbar_wait(full(stage), phase);
+        tadd(2, tick() - t0);
         fence_proxy_async();                             // cp.async (generic proxy) writes -> tensor-core reads
         tc_fence_after();
         const uint32_t stage_addr = sA + stage * kStageBytes;
@@ -394,6 +448,11 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
+    if constexpr (kTrace)
+      if (tracing) {
+        for (int k = 0; k < 6; ++k) trace[8 + k] = tr[k];  // acc_empty | w_full | full(stage) waits | - | - | tiles
+        trace[14] = tick() - t_begin;                      // cycles from the first to the last tile of this CTA
+      }
   } else if (warp == kWarpSched) {
     // ------------------------------------------------------------------ scheduler (+ accumulator clearing)
     // The accumulator rows of super-block ("phase") p are zeroed INSIDE this kernel, one phase ahead of their
@@ -423,7 +482,8 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       const int64_t share = (hi - lo + gridDim.x - 1) / gridDim.x;
       const int64_t r0 = lo + (int64_t)blockIdx.x * share, r1 = min(hi, r0 + share);
       float4* row = reinterpret_cast<float4*>(acc) + lane;
-      if (flags & kFlagRedEvictLast) {                   // keep the zero lines in L2 until their reductions arrive
+      if (flags & kDbgNoClear) {
+      } else if (flags & kFlagRedEvictLast) {                   // keep the zero lines in L2 until their reductions arrive
         const uint64_t pol = policy_evict_last();
         for (int64_t r = r0; r < r1; ++r)
           asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%1,%1,%1}, %2;" ::"l"(row + r * (kD / 4)), "f"(0.f),
@@ -454,7 +514,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
                             (wb ? kTileWbuf : 0u);
         publish(start + t0, min(kTile, count - t0), rel, tf);
       }
-      wb ^= 1u;
+      wb = (wb + 1u) % kWBufs;
       u = u_next;
     }
     while (my_zeroed < num_phases - 1) clear_share(++my_zeroed);   // rows without in-edges are cleared too
@@ -465,7 +525,8 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
     // thread = output column n = 32 * quarter + lane = TMEM lane; 128 columns (256 k) in 4 pieces of 32
     const int quarter = warp & 3;   // a warp reaches TMEM lanes [32 (warp % 4), +32) only
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + kWCol;
-    const uint64_t pol_w = (flags & kFlagWEvictLast) ? policy_evict_last() : policy_evict_normal();
+    const uint64_t pol_w = (flags & kFlagWEvictLast) ? policy_evict_last()
+                           : (flags & kFlagWEvictFirst) ? policy_evict_first() : policy_evict_normal();
     uint32_t eph = 0;                                    // bit b: parity of the next w_empty(b) wait
     for (uint32_t it = 0;; ++it) {
       const int4 t = q_acquire(it);
@@ -573,31 +634,50 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
               "mp_f16: h16 / acc / scratch must be 16-byte aligned");
   static bool configured = false;
   if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   const char* penv = getenv("GHF_F16_PROD");
-  const int prod = penv ? atoi(penv) : 8;
+  const int prod = penv ? atoi(penv) : 4;
   const __half* img = reinterpret_cast<const __half*>(pack_scratch);
   const float* inv = reinterpret_cast<const float*>(reinterpret_cast<const char*>(pack_scratch) +
                                                     align_up((int64_t)g->num_rel * kImageBytes, 256));
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
+  long long* trace = nullptr;   // GHF_F16_TRACE=1: cycle accounting of CTA 0 printed after the launch (synchronises)
+  TempBuf trace_buf;
+  if (getenv("GHF_F16_TRACE")) {
+    GHF_CUDA(trace_buf.alloc(32 * sizeof(long long), stream));
+    GHF_CUDA(cudaMemsetAsync(trace_buf.p, 0, 32 * sizeof(long long), stream));
+    trace = trace_buf.as<long long>();
+  }
   // sync words (zero at launch): [0] unit counter, [64 + p] cleared shares of phase p
   GHF_CUDA(cudaMemsetAsync(sync_words, 0, mp_f16_sync_bytes(g), stream));
   int* unit_counter = sync_words;
   int* zero_done = sync_words + 64;
-  if (prod == 8)
-    mp_f16_kernel<8><<<(unsigned)grid, threads_for(8), kSmem, stream>>>(
-        g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
-        reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, zero_done,
-        (int)g->num_phases, g->sb_nodes, g->num_local, env_flags());
-  else
-    mp_f16_kernel<4><<<(unsigned)grid, threads_for(4), kSmem, stream>>>(
-        g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
-        reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, zero_done,
-        (int)g->num_phases, g->sb_nodes, g->num_local, env_flags());
+#define GHF_F16_LAUNCH(P, T)                                                                                      \
+  mp_f16_kernel<P, T><<<(unsigned)grid, threads_for(P), kSmem, stream>>>(                                        \
+      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,                    \
+      reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, \
+      zero_done, (int)g->num_phases, g->sb_nodes, g->num_local, env_flags(), trace)
+  if (trace) GHF_F16_LAUNCH(4, true);
+  else if (prod == 8) GHF_F16_LAUNCH(8, false);
+  else GHF_F16_LAUNCH(4, false);
+#undef GHF_F16_LAUNCH
   GHF_LAUNCH_CHECK();
+  if (trace) {
+    long long t[32];
+    GHF_CUDA(cudaMemcpyAsync(t, trace, sizeof(t), cudaMemcpyDeviceToHost, stream));
+    GHF_CUDA(cudaStreamSynchronize(stream));
+    auto per = [&](int i, int n) { return t[n] ? (double)t[i] / (double)t[n] : 0.0; };
+    fprintf(stderr,
+            "mp_f16 trace (CTA 0, cycles per tile): epilogue[acquire %.0f | acc_full %.0f | tmem %.0f | reds %.0f | "
+            "release %.0f] x %lld   mma[acc_empty %.0f | w_full %.0f | full %.0f] x %lld   producer[empty %.0f] x %lld"
+            "   total %lld cycles\n",
+            per(0, 5), per(1, 5), per(2, 5), per(3, 5), per(4, 5), t[5], per(8, 13), per(9, 13), per(10, 13), t[13],
+            per(16, 21), t[21], t[14]);
+  }
   return 0;
 }
 

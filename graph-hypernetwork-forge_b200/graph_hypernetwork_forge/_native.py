@@ -66,6 +66,8 @@ def lib():
         "ghf_convert_f16": (c_int, [P, c_int64, P, P, c_int, P]),
         "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
                                               c_int64, P, P, P, P]),
+        "ghf_hypergnn_forward_device": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
+                                                c_int64, P, P, P, P]),
         "ghf_launch_count": (c_int64, [c_int]),
         "ghf_profile_enable": (c_int, [c_int]),
         "ghf_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
@@ -84,7 +86,7 @@ EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
     "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -346,4 +348,22 @@ def forward_host(desc: ModelDesc, params, node_features, edge_index, utf8, offse
             ctypes.byref(desc), arr, len(params), c_void_p(node_features.data_ptr()), N,
             c_void_p(edge_index.data_ptr()), E, c_void_p(utf8.data_ptr()), c_void_p(offsets.data_ptr()),
             c_void_p(out.data_ptr()), _stream(device)), "ghf_hypergnn_forward_host")
+    return out
+
+
+def forward_device(desc: ModelDesc, params, node_features, edge_index, utf8, offsets, out=None):
+    """ghf_hypergnn_forward_device: the whole forward on CUDA tensors in ONE native call -> out [N, hidden]."""
+    dev = node_features.device
+    node_features = _f32(node_features)
+    edge_index = edge_index.contiguous()
+    if edge_index.dtype != torch.int64 or utf8.dtype != torch.uint8 or offsets.dtype != torch.int64:
+        raise RuntimeError("edge_index/offsets must be int64 and utf8 uint8")
+    N, E = node_features.shape[0], edge_index.shape[1]
+    if out is None:
+        out = torch.empty((N, desc.hidden_dim), dtype=torch.float32, device=dev)
+    arr = (c_void_p * len(params))(*[p.data_ptr() for p in params])
+    with torch.cuda.device(dev):
+        _check(lib().ghf_hypergnn_forward_device(
+            ctypes.byref(desc), arr, len(params), _ptr(node_features), N, _ptr(edge_index), E, _ptr(utf8.contiguous()),
+            _ptr(offsets.contiguous()), _ptr(out), _stream(dev)), "ghf_hypergnn_forward_device")
     return out

@@ -31,9 +31,10 @@ def plan_partition(num_nodes: int, world_size: int) -> Tuple[int, List[Tuple[int
     return rows, ranges
 
 
-def gather_rows(buf: torch.Tensor, rows: int, rank: int, group) -> None:
-    """In-place all-gather: rank r has filled buf[r*rows:(r+1)*rows]; afterwards every rank has all of buf."""
-    dist.all_gather_into_tensor(buf, buf[rank * rows:(rank + 1) * rows], group=group)
+def gather_rows(buf: torch.Tensor, rows: int, rank: int, group, async_op: bool = False):
+    """In-place all-gather: rank r has filled buf[r*rows:(r+1)*rows]; afterwards every rank has all of buf.
+    async_op: returns the work handle; kernels enqueued before `.wait()` overlap the transfer."""
+    return dist.all_gather_into_tensor(buf, buf[rank * rows:(rank + 1) * rows], group=group, async_op=async_op)
 
 
 class ShardedForward:
@@ -116,17 +117,23 @@ class ShardedForward:
                 _native.to_f16(cur[lo:hi], cur16.rows(lo, hi), have_amax=True)
             else:
                 _native.to_f16(cur[:0], cur16.rows(0, 0), have_amax=True)   # still writes the scale
-            gather_rows(cur16.data, self.rows, self.rank, self.group)
+            # every all-gather is asynchronous: the generator kernels of the next layer (they do not depend on h) are
+            # enqueued before the wait and run while the rows travel over NVLink
+            pending = gather_rows(cur16.data, self.rows, self.rank, self.group, async_op=True)
             text_embs = m.text_encoder.encode_packed(packed)
+            w = m._generate(0, text_embs, packed.num_unique)
             for l in range(m.num_layers):
-                w = m._generate(l, text_embs, packed.num_unique)
                 ln = m.layer_norms[l]
                 last = l + 1 == m.num_layers
+                pending.wait()
                 if hi > lo:
                     graph.mp_layer(cur[:N], w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps,
                                    _native.PREC_F16, out=nxt[lo:hi], h16=cur16.rows(0, N),
                                    out16=None if last else nxt16.rows(lo, hi))
-                gather_rows(nxt if last else nxt16.data, self.rows, self.rank, self.group)
+                pending = gather_rows(nxt if last else nxt16.data, self.rows, self.rank, self.group, async_op=True)
+                if not last:
+                    w = m._generate(l + 1, text_embs, packed.num_unique)
                 cur, nxt, cur16, nxt16 = nxt, cur, nxt16, cur16
+            pending.wait()
         self._bufs, self._bufs16 = [cur, nxt], [cur16, nxt16]
         return cur[:N]

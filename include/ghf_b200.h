@@ -148,6 +148,12 @@ int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float* const* d_
                               int64_t n_params, const float* h_node_features, int64_t num_nodes,
                               const int64_t* h_edge_index, int64_t E, const uint8_t* h_utf8,
                               const int64_t* h_offsets, float* h_out, void* stream);
+/* The same forward on DEVICE buffers (no copies; stream-ordered except for the two size read-backs of dedup and
+ * graph build): one call per forward instead of ~60 from the host language. */
+int ghf_hypergnn_forward_device(const ghf_model_desc* desc, const float* const* d_params,
+                                int64_t n_params, const float* d_node_features, int64_t num_nodes,
+                                const int64_t* d_edge_index, int64_t E, const uint8_t* d_utf8,
+                                const int64_t* d_offsets, float* d_out, void* stream);
 
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t ghf_launch_count(int reset);

@@ -301,3 +301,21 @@ def test_ids_in_api_matches_string_api():
     assert_close(got.cpu().numpy(), want.cpu().numpy(), 1e-4, 2e-5, "ids-in forward")
     with pytest.raises(ValueError):
         model.prepare_ids(ei, torch.from_numpy(rel[:-1]).to(DEV), list(names), N)
+
+
+def test_forward_packed_single_native_call_matches_staged_path():
+    """forward_packed (ghf_hypergnn_forward_device: one native call) == prepare_packed + forward_prepared."""
+    from graph_hypernetwork_forge import HyperGNN, _text
+    N, E, R, L = 4000, 60000, 29, 3
+    for d, prec in ((128, "f16"), (64, "tf32"), (48, "fp32")):
+        src, dst, rel, names, feats = O.synthetic_kg(N, E, R, 40, seed=d)
+        texts = [names[r] for r in rel]
+        torch.manual_seed(d)
+        model = HyperGNN(32, 40, d, L, precision=prec).eval().to(DEV)
+        ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+        x = torch.from_numpy(feats).to(DEV)
+        data, offs = _text.pack_utf8(texts)
+        utf8, offsets = torch.from_numpy(data.copy()).to(DEV), torch.from_numpy(offs).to(DEV)
+        want = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N))
+        got = model.forward_packed(x, ei, utf8, offsets)
+        assert_close(got.cpu().numpy(), want.cpu().numpy(), 1e-4, 5e-5, f"forward_packed d={d} {prec}")
