@@ -103,7 +103,8 @@ std::mutex g_forward_lock;
 // The whole forward on DEVICE buffers (HG:236-298); d_out receives the final embeddings [num_nodes, d].
 static int forward_device_impl(const ghf_model_desc* desc, const float* const* d_params, int64_t n_params,
                                const float* d_x, int64_t num_nodes, const int64_t* d_ei, int64_t E,
-                               const uint8_t* d_utf8, const int64_t* d_offs, float* d_out, cudaStream_t stream) {
+                               const uint8_t* d_utf8, const int64_t* d_offs, float* d_out, cudaEvent_t x_ready,
+                               cudaStream_t stream) {
   GHF_REQUIRE(desc && d_params, "ghf_hypergnn_forward: NULL model");
   const int T = desc->text_dim, F = desc->node_feat_dim, d = desc->hidden_dim, L = desc->num_layers;
   const int C = desc->char_emb_dim, H = desc->gen_hidden, depth = desc->gen_depth;
@@ -148,10 +149,6 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   void* h16_0 = want_f16 ? A.take<uint16_t>((size_t)num_nodes * d) : nullptr;   // fp16 shadow buffers (ping-pong)
   void* h16_1 = want_f16 ? A.take<uint16_t>((size_t)num_nodes * d) : nullptr;
 
-  // HG:261  h = relu(input_proj(x))  (+ the fp16 shadow of h on the f16 path)
-  if (int rc = ghf_linear_f16out(d_x, num_nodes, F, Win, bin, d, 1, nullptr, h0, h16_0, want_f16 ? scales : nullptr,
-                                 stream))
-    return rc;
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
   if (int rc = ghf_dedup_texts(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream)) return rc;
@@ -180,6 +177,13 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   void* ws = B.take<char>(ws_bytes);
   const int n_out[3] = {d * d, d * d, d};
   if (int rc = ghf_text_encode(d_utf8, d_offs, first, U, emb, C, Wp, bp, T, temb, stream)) return rc;
+  // the node features are needed only now: a caller that copies them on another stream overlaps that copy with
+  // dedup and graph build
+  if (x_ready) GHF_CUDA(cudaStreamWaitEvent(stream, x_ready, 0));
+  // HG:261  h = relu(input_proj(x))  (+ the fp16 shadow of h on the f16 path)
+  if (int rc = ghf_linear_f16out(d_x, num_nodes, F, Win, bin, d, 1, nullptr, h0, h16_0, want_f16 ? scales : nullptr,
+                                 stream))
+    return rc;
 
   float* cur = h0;
   float* nxt = h1;
@@ -223,7 +227,7 @@ extern "C" int ghf_hypergnn_forward_device(const ghf_model_desc* desc, const flo
                                            const int64_t* d_edge_index, int64_t E, const uint8_t* d_utf8,
                                            const int64_t* d_offsets, float* d_out, void* stream_) {
   return forward_device_impl(desc, d_params, n_params, d_node_features, num_nodes, d_edge_index, E, d_utf8,
-                             d_offsets, d_out, (cudaStream_t)stream_);
+                             d_offsets, d_out, nullptr, (cudaStream_t)stream_);
 }
 
 extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float* const* d_params,
@@ -241,12 +245,28 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
   GHF_CUDA(utf8.alloc(text_bytes, stream));
   GHF_CUDA(offs.alloc((E + 1) * sizeof(int64_t), stream));
   GHF_CUDA(out.alloc(num_nodes * (size_t)d * 4, stream));
-  GHF_CUDA(cudaMemcpyAsync(x.p, h_node_features, num_nodes * (size_t)F * 4, cudaMemcpyHostToDevice, stream));
+  // edges and strings first (dedup and graph build need only them); the node features follow on a second stream
+  // and are waited for right before the input projection
+  static cudaStream_t copy_stream[64] = {nullptr};
+  static cudaEvent_t x_ready[64] = {nullptr}, buffers_ready[64] = {nullptr};
+  int dev = 0;
+  GHF_CUDA(cudaGetDevice(&dev));
+  GHF_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  if (!copy_stream[dev]) {
+    GHF_CUDA(cudaStreamCreateWithFlags(&copy_stream[dev], cudaStreamNonBlocking));
+    GHF_CUDA(cudaEventCreateWithFlags(&x_ready[dev], cudaEventDisableTiming));
+    GHF_CUDA(cudaEventCreateWithFlags(&buffers_ready[dev], cudaEventDisableTiming));
+  }
   GHF_CUDA(cudaMemcpyAsync(ei.p, h_edge_index, 2 * E * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
   GHF_CUDA(cudaMemcpyAsync(utf8.p, h_utf8, text_bytes, cudaMemcpyHostToDevice, stream));
   GHF_CUDA(cudaMemcpyAsync(offs.p, h_offsets, (E + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  // the feature copy starts when those three are through (the link is shared), in `stream` order after x.p exists
+  GHF_CUDA(cudaEventRecord(buffers_ready[dev], stream));
+  GHF_CUDA(cudaStreamWaitEvent(copy_stream[dev], buffers_ready[dev], 0));
+  GHF_CUDA(cudaMemcpyAsync(x.p, h_node_features, num_nodes * (size_t)F * 4, cudaMemcpyHostToDevice, copy_stream[dev]));
+  GHF_CUDA(cudaEventRecord(x_ready[dev], copy_stream[dev]));
   if (int rc = forward_device_impl(desc, d_params, n_params, x.as<float>(), num_nodes, ei.as<int64_t>(), E,
-                                   utf8.as<uint8_t>(), offs.as<int64_t>(), out.as<float>(), stream))
+                                   utf8.as<uint8_t>(), offs.as<int64_t>(), out.as<float>(), x_ready[dev], stream))
     return rc;
   GHF_CUDA(cudaMemcpyAsync(h_out, out.p, num_nodes * (size_t)d * 4, cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaStreamSynchronize(stream));
