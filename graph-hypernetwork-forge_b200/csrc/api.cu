@@ -1,5 +1,6 @@
 // api.cu — library-wide state and ghf_hypergnn_forward_host, the end-to-end entry point that takes
 // HOST buffers (the shape of the reference's HyperGNN.forward, HG:236-298, at a C boundary).
+#include <array>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -95,8 +96,26 @@ struct Arena {
   }
   static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 };
-Arena g_arena[64][2];
+Arena g_arena[64][3];
 std::mutex g_forward_lock;
+
+// side stream + events of the whole-forward entry points: the weight generators of all layers depend only on the
+// text embeddings, so they run beside graph build and input projection instead of between the layers
+constexpr int kMaxSideLayers = 16;
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t text_ready = nullptr, weights_ready[kMaxSideLayers] = {};
+  cudaError_t init() {
+    if (stream) return cudaSuccess;
+    cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&text_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (auto& ev : weights_ready)
+      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    return cudaSuccess;
+  }
+};
+SideStream g_side[64];
 
 }  // namespace
 
@@ -152,6 +171,51 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
   if (int rc = ghf_dedup_texts(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream)) return rc;
+  const int prec = (desc->precision == GHF_PREC_F16 && d == 128) ? GHF_PREC_F16
+                   : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
+                                                                                           : GHF_PREC_FP32;
+  // second arena: everything whose size depends on the number of distinct relations
+  const size_t Un = (size_t)(U > 0 ? U : 1), Hn = (size_t)(H > 0 ? H : 1);
+  const size_t w_layer = 2 * Arena::padded(Un * d * d * 4) + Arena::padded(Un * d * 4);
+  GHF_CUDA(B.reserve(Arena::padded(Un * T * 4) + (size_t)L * w_layer + 2 * Arena::padded(Un * Hn * 4) + 4096));
+  float* temb = B.take<float>(Un * T);
+  float* hid_a = B.take<float>(Un * Hn);
+  float* hid_b = B.take<float>(Un * Hn);
+  std::vector<std::array<float*, 3>> outs(L);
+  for (int l = 0; l < L; ++l) outs[l] = {B.take<float>(Un * d * d), B.take<float>(Un * d * d), B.take<float>(Un * d)};
+  const int n_out[3] = {d * d, d * d, d};
+  if (int rc = ghf_text_encode(d_utf8, d_offs, first, U, emb, C, Wp, bp, T, temb, stream)) return rc;
+
+  // WG:137-141 for the U distinct relations, every layer: on the side stream, beside graph build and projection
+  SideStream& side = g_side[dev];
+  const bool use_side = L <= kMaxSideLayers && side.init() == cudaSuccess;
+  cudaStream_t gen_stream = use_side ? side.stream : stream;
+  if (use_side) {
+    GHF_CUDA(cudaEventRecord(side.text_ready, stream));
+    GHF_CUDA(cudaStreamWaitEvent(side.stream, side.text_ready, 0));
+  }
+  auto generate = [&](int l) -> int {
+    for (int m = 0; m < 3 && U > 0; ++m) {
+      const float* in = temb;
+      int in_dim = T;
+      for (int i = 0; i < depth; ++i) {
+        float* o = (i & 1) ? hid_b : hid_a;
+        if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][i], layers[l].b[m][i], H, 1, nullptr, o, gen_stream))
+          return rc;
+        in = o;
+        in_dim = H;
+      }
+      if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][depth], layers[l].b[m][depth], n_out[m], 0,
+                              layers[l].log_scale[m], outs[l][m], gen_stream))
+        return rc;
+    }
+    return 0;
+  };
+  if (use_side)
+    for (int l = 0; l < L; ++l) {
+      if (int rc = generate(l)) return rc;
+      GHF_CUDA(cudaEventRecord(side.weights_ready[l], side.stream));
+    }
 
   ghf_graph* g = nullptr;
   if (int rc = ghf_graph_build(d_ei, E, nullptr, 0, rel, num_nodes, (int32_t)(U > 0 ? U : 1), d, 0, num_nodes, 0, 0,
@@ -161,22 +225,11 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
     ghf_graph* g;
     ~Guard() { ghf_graph_free(g); }
   } guard{g};
-
-  const int prec = (desc->precision == GHF_PREC_F16 && d == 128) ? GHF_PREC_F16
-                   : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
-                                                                                           : GHF_PREC_FP32;
-  // second arena: everything whose size depends on the number of distinct relations or on the graph tables
-  const size_t Un = (size_t)(U > 0 ? U : 1), Hn = (size_t)(H > 0 ? H : 1);
+  Arena& Cws = g_arena[dev][2];                          // third arena: the layer workspace (sized by the graph tables)
   const size_t ws_bytes = (size_t)ghf_mp_workspace_bytes(g, d, prec);
-  GHF_CUDA(B.reserve(Arena::padded(Un * T * 4) + 2 * Arena::padded(Un * d * d * 4) + Arena::padded(Un * d * 4) +
-                     2 * Arena::padded(Un * Hn * 4) + Arena::padded(ws_bytes) + 4096));
-  float* temb = B.take<float>(Un * T);
-  float* outs[3] = {B.take<float>(Un * d * d), B.take<float>(Un * d * d), B.take<float>(Un * d)};
-  float* hid_a = B.take<float>(Un * Hn);
-  float* hid_b = B.take<float>(Un * Hn);
-  void* ws = B.take<char>(ws_bytes);
-  const int n_out[3] = {d * d, d * d, d};
-  if (int rc = ghf_text_encode(d_utf8, d_offs, first, U, emb, C, Wp, bp, T, temb, stream)) return rc;
+  GHF_CUDA(Cws.reserve(ws_bytes + 4096));
+  void* ws = Cws.take<char>(ws_bytes);
+
   // the node features are needed only now: a caller that copies them on another stream overlaps that copy with
   // dedup and graph build
   if (x_ready) GHF_CUDA(cudaStreamWaitEvent(stream, x_ready, 0));
@@ -192,27 +245,17 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   float* cur_sc = scales;
   float* nxt_sc = scales + 2;
   for (int l = 0; l < L; ++l) {
-    // WG:137-141 for the U distinct relations
-    for (int m = 0; m < 3 && U > 0; ++m) {
-      const float* in = temb;
-      int in_dim = T;
-      for (int i = 0; i < depth; ++i) {
-        float* o = (i & 1) ? hid_b : hid_a;
-        if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][i], layers[l].b[m][i], H, 1, nullptr, o, stream))
-          return rc;
-        in = o;
-        in_dim = H;
-      }
-      if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][depth], layers[l].b[m][depth], n_out[m], 0,
-                              layers[l].log_scale[m], outs[m], stream))
-        return rc;
+    if (use_side) {
+      GHF_CUDA(cudaStreamWaitEvent(stream, side.weights_ready[l], 0));
+    } else if (int rc = generate(l)) {
+      return rc;
     }
     // HG:286-296
     void* out16 = (prec == GHF_PREC_F16 && l + 1 < L) ? nxt16 : nullptr;
     float* dst = l + 1 < L ? nxt : d_out;                // the last layer writes the caller's buffer
-    if (int rc = ghf_mp_layer_f16(g, cur, cur16, cur16 ? cur_sc : nullptr, outs[0], outs[1], outs[2], layers[l].ln_w,
-                                  layers[l].ln_b, desc->ln_eps, prec, dst, out16, out16 ? nxt_sc : nullptr, nullptr,
-                                  ws, stream))
+    if (int rc = ghf_mp_layer_f16(g, cur, cur16, cur16 ? cur_sc : nullptr, outs[l][0], outs[l][1], outs[l][2],
+                                  layers[l].ln_w, layers[l].ln_b, desc->ln_eps, prec, dst, out16,
+                                  out16 ? nxt_sc : nullptr, nullptr, ws, stream))
       return rc;
     float* t = cur; cur = nxt; nxt = t;
     t = cur_sc; cur_sc = nxt_sc; nxt_sc = t;
