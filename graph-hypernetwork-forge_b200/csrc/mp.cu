@@ -285,11 +285,6 @@ static bool mp_ts_enabled(int d) {  // weights in tensor memory (hidden_dim 128)
   return mp_ts_supported(d) && !(env && env[0] == '0');
 }
 
-static bool mp_fused_enabled() {  // opt-in (GHF_MP_FUSED=1): measured slower than the three-kernel layer
-  const char* env = getenv("GHF_MP_FUSED");
-  return env && env[0] == '1';
-}
-
 // ---- optional per-kernel timing (bench.py roofline): event triples per layer call
 namespace {
 struct ProfRec { cudaEvent_t e[4]; };
@@ -321,10 +316,8 @@ extern "C" int ghf_profile_read(double ms[3], int64_t* launches) {
 
 extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim, int precision) {
   if (!g) return -1;
-  const bool fused = precision == GHF_PREC_TF32 && mp_fused_enabled();
-  // unfused paths accumulate in scratch; the fused tf32 path accumulates in the output rows
-  int64_t bytes = 256 /* work counter */ + (fused ? 0 : align_up(g->num_local * (int64_t)hidden_dim * 4, 256));
-  if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim) + mp_umma_sync_bytes(g);
+  int64_t bytes = 256 /* work counter */ + align_up(g->num_local * (int64_t)hidden_dim * 4, 256);
+  if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim);
   if (precision == GHF_PREC_F16)  // sync words, weight images, the fp16 copy of h made when the caller passes none
     bytes += mp_f16_sync_bytes(g) + mp_f16_pack_bytes(g->num_rel) + 256 /* scale words */ +
              align_up(g->num_nodes * (int64_t)hidden_dim * 2, 256);
@@ -380,34 +373,6 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
   const int64_t nl = g->num_local;
   g->stream = stream_;
   if (nl == 0) return 0;
-  if (precision == GHF_PREC_TF32 && mp_fused_enabled()) {
-    // workspace: [sync words][operand images]; one kernel does the whole layer in place
-    GHF_REQUIRE(mp_umma_supported(d), "ghf_mp_layer: tf32 path supports hidden_dim in {32,64,128}, got %d", d);
-    GHF_REQUIRE(d_out16 == nullptr, "ghf_mp_layer: the fused tf32 layer has no fp16 output");
-    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
-    void* sync = base;
-    void* pack = base + mp_umma_sync_bytes(g);
-    ProfRec rec{};
-    const bool prof = g_prof_on;
-    if (prof) {
-      for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
-      GHF_CUDA(cudaEventRecord(rec.e[0], stream));
-    }
-    const bool ts = mp_ts_enabled(d);
-    if (g->num_units > 0)
-      if (int rc = ts ? mp_ts_pack(g, d_W_msg, d_W_self, pack, stream) : mp_umma_pack(g, d_W_msg, d_W_self, pack, stream))
-        return rc;
-    if (prof) GHF_CUDA(cudaEventRecord(rec.e[1], stream));
-    if (int rc = ts ? mp_ts_launch_fused(g, d_h, d_bias, d_ln_w, d_ln_b, eps, d_out, d_upd, pack, sync, stream)
-                    : mp_umma_launch_fused(g, d_h, d_bias, d_ln_w, d_ln_b, eps, d_out, d_upd, pack, sync, stream))
-      return rc;
-    if (prof) {
-      GHF_CUDA(cudaEventRecord(rec.e[2], stream));
-      GHF_CUDA(cudaEventRecord(rec.e[3], stream));
-      g_prof.push_back(rec);
-    }
-    return 0;
-  }
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
   // (the f16 kernel clears the accumulator itself and keeps per-phase sync words next to the counter)
   const bool self_clearing = precision == GHF_PREC_F16 && g->num_units > 0;

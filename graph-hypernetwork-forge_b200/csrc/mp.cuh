@@ -19,21 +19,11 @@ int mp_umma_pack(const ghf_graph* g, const float* W_msg, const float* W_self, vo
 int mp_umma_launch(const ghf_graph* g, const float* h, const float* bias, float* acc, const void* pack_scratch,
                    int* unit_counter, cudaStream_t stream);
 
-// Fused layer: contraction + mean + self-loop + residual + ReLU + LayerNorm in ONE persistent kernel; `out`
-// [local, d] is the accumulator and the result (see mp_umma.cu).  sync_scratch: mp_umma_sync_bytes(g) bytes.
-int64_t mp_umma_sync_bytes(const ghf_graph* g);
-int mp_umma_launch_fused(const ghf_graph* g, const float* h, const float* bias, const float* ln_w, const float* ln_b,
-                         float eps, float* out, float* upd, const void* pack_scratch, void* sync_scratch,
-                         cudaStream_t stream);
-
 // hidden_dim 128 with the weights resident in tensor memory (mp_umma_ts.cu); same contracts as above
 bool mp_ts_supported(int hidden_dim);
 int mp_ts_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream);
 int mp_ts_launch(const ghf_graph* g, const float* h, const float* bias, float* acc, const void* pack_scratch,
                  int* unit_counter, cudaStream_t stream);
-int mp_ts_launch_fused(const ghf_graph* g, const float* h, const float* bias, const float* ln_w, const float* ln_b,
-                       float eps, float* out, float* upd, const void* pack_scratch, void* sync_scratch,
-                       cudaStream_t stream);
 
 
 // hidden_dim 128 with fp16 feature transport, kind::f16 MMA and double-buffered weights in TMEM (mp_f16.cu)

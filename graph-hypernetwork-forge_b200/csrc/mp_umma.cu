@@ -20,14 +20,12 @@
 
 #include "common.cuh"
 #include "mp.cuh"
-#include "mp_fuse.cuh"
 #include "umma.cuh"
 
 namespace ghf {
 namespace {
 
 using namespace ptx;
-using namespace fuse;
 
 // L2 residency flags (GHF_MP_FLAGS): the destination super-block (h[dst] rows + accumulator rows) should
 // stay in L2 while the source rows stream through once.
@@ -73,21 +71,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ W_msg, const float
   *reinterpret_cast<float*>(pack + r * ((int64_t)2 * D * D * 4) + pack_offset_bytes(D, n, k)) = to_tf32_rna(v);
 }
 
-template <int D, bool FUSED>
+template <int D>
 __global__ void __launch_bounds__(Cfg<D>::kThreads, 1)
 mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
                const int32_t* __restrict__ unit_rel, int64_t num_units,
                const int32_t* __restrict__ src_sorted, const int32_t* __restrict__ dst_sorted,
                const float* __restrict__ h, int64_t dst_lo, const uint8_t* __restrict__ wpack,
-               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter, uint32_t flags,
-               const FuseArgs fa) {
+               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter, uint32_t flags) {
   using C = Cfg<D>;
-  if constexpr (FUSED) {
-    if ((int)blockIdx.x < fa.epi_ctas) {  // epilogue CTAs: no tensor-core role, no shared-memory pipeline
-      epilogue_cta<D>(fa, acc, h, dst_lo);
-      return;
-    }
-  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sB = (raw + 1023u) & ~1023u;
@@ -193,11 +184,6 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
         tc_fence_before();
         mbar_arrive(acc_empty(a));
       }
-      if constexpr (FUSED) {  // this unit's reductions are complete: count it towards its phase
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 0) atomicAdd(&fa.units_done[fa.unit_phase[u]], 1);
-      }
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ A producers
@@ -276,22 +262,12 @@ mp_umma_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict
       int sq = 0;
       const uint64_t pol_w = (flags & kFlagWeightsEvictLast) ? policy_evict_last() : policy_evict_normal();
       int64_t static_next = blockIdx.x;
-      int ready_phase = -1;
-      for (;;) {
+          for (;;) {
         mbar_wait(q_empty0 + 8u * sq, sphase ^ 1u);
         int64_t u;
-        if (!FUSED && (flags & kFlagStaticSchedule)) { u = static_next; static_next += gridDim.x; }
+        if (flags & kFlagStaticSchedule) { u = static_next; static_next += gridDim.x; }
         else u = atomicAdd(unit_counter, 1);
         const bool done = u >= num_units;
-        if constexpr (FUSED) {
-          if (!done) {
-            const int p = fa.unit_phase[u];
-            if (p != ready_phase) {  // the rows this unit reduces into must have been cleared
-              spin_until_at_least(&fa.zero_done[p], fa.epi_ctas);
-              ready_phase = p;
-            }
-          }
-        }
         q_slot_ptr[sq] = done ? -1 : (int)u;
         mbar_arrive(q_full0 + 8u * sq);  // release: the slot write is visible to the waiters
         if (++sq == C::kQueue) { sq = 0; sphase ^= 1u; }
@@ -327,38 +303,13 @@ int launch(const ghf_graph* g, const float* h, const uint8_t* wpack, const float
   using C = Cfg<D>;
   static bool configured = false;
   if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(mp_umma_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_umma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     configured = true;
   }
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
-  mp_umma_kernel<D, false><<<(unsigned)grid, C::kThreads, C::kSmem, stream>>>(
+  mp_umma_kernel<D><<<(unsigned)grid, C::kThreads, C::kSmem, stream>>>(
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo, wpack,
-      bias, acc, unit_counter, env_flags(), FuseArgs{});
-  GHF_LAUNCH_CHECK();
-  return 0;
-}
-
-template <int D>
-int launch_fused(const ghf_graph* g, const float* h, const uint8_t* wpack, const float* bias, float* out,
-                 int* unit_counter, FuseArgs fa, cudaStream_t stream) {
-  using C = Cfg<D>;
-  static bool configured = false;
-  if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(mp_umma_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    configured = true;
-  }
-  // every CTA must be resident at once (contraction CTAs wait on epilogue CTAs and vice versa):
-  // one CTA per SM by shared-memory size, grid <= SM count
-  const int sms = sm_count();
-  const char* env = getenv("GHF_EPI_CTAS");
-  int epi = env ? atoi(env) : 20;
-  epi = epi < 1 ? 1 : (epi > sms / 2 ? sms / 2 : epi);
-  const int64_t work = g->num_units > 0 ? g->num_units : 1;
-  const int64_t contraction = work < sms - epi ? work : sms - epi;
-  fa.epi_ctas = epi;
-  mp_umma_kernel<D, true><<<(unsigned)(epi + contraction), C::kThreads, C::kSmem, stream>>>(
-      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo, wpack,
-      bias, out, unit_counter, env_flags() & ~kFlagStaticSchedule, fa);
+      bias, acc, unit_counter, env_flags());
   GHF_LAUNCH_CHECK();
   return 0;
 }
@@ -392,38 +343,6 @@ int mp_umma_launch(const ghf_graph* g, const float* h, const float* bias, float*
     case 32: return launch<32>(g, h, pack, bias, acc, unit_counter, stream);
     case 64: return launch<64>(g, h, pack, bias, acc, unit_counter, stream);
     case 128: return launch<128>(g, h, pack, bias, acc, unit_counter, stream);
-  }
-  return fail("mp_umma: unsupported hidden_dim %d", d);
-}
-
-int64_t mp_umma_sync_bytes(const ghf_graph* g) { return align_up(256 + 2 * g->num_phases * 4, 256); }
-
-int mp_umma_launch_fused(const ghf_graph* g, const float* h, const float* bias, const float* ln_w, const float* ln_b,
-                         float eps, float* out, float* upd, const void* pack_scratch, void* sync_scratch,
-                         cudaStream_t stream) {
-  const int d = g->hidden_dim;
-  GHF_REQUIRE(g->unit_edges % 128 == 0, "mp_umma: unit_edges=%d must be a multiple of 128", g->unit_edges);
-  GHF_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
-               reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
-              "mp_umma: h / out / bias / scratch must be 16-byte aligned");
-  // sync scratch: [unit counter (256 B)][zero_done[phases]][units_done[phases]], all zero at launch
-  GHF_CUDA(cudaMemsetAsync(sync_scratch, 0, mp_umma_sync_bytes(g), stream));
-  int* counter = reinterpret_cast<int*>(sync_scratch);
-  FuseArgs fa{};
-  fa.unit_phase = g->unit_phase;
-  fa.phase_units = g->phase_units;
-  fa.zero_done = counter + 64;
-  fa.units_done = fa.zero_done + g->num_phases;
-  fa.indeg = g->indeg;
-  fa.ln_w = ln_w; fa.ln_b = ln_b; fa.eps = eps; fa.upd = upd;
-  fa.num_local = g->num_local;
-  fa.sb_nodes = g->sb_nodes;
-  fa.num_phases = (int32_t)g->num_phases;
-  const uint8_t* pack = reinterpret_cast<const uint8_t*>(pack_scratch);
-  switch (d) {
-    case 32: return launch_fused<32>(g, h, pack, bias, out, counter, fa, stream);
-    case 64: return launch_fused<64>(g, h, pack, bias, out, counter, fa, stream);
-    case 128: return launch_fused<128>(g, h, pack, bias, out, counter, fa, stream);
   }
   return fail("mp_umma: unsupported hidden_dim %d", d);
 }

@@ -17,19 +17,16 @@
 // Warp roles (576 threads, 1 CTA / SM):
 //   0-7 epilogue (2 groups) | 8-11 row-gather producers | 12 MMA issuer + TMEM allocator | 13 unit scheduler |
 //   14-17 weight loaders
-// With FUSED, the lowest `epi_ctas` CTAs run the in-place layer epilogue instead (mp_fuse.cuh).
 #include <cstdlib>
 
 #include "common.cuh"
 #include "mp.cuh"
-#include "mp_fuse.cuh"
 #include "umma.cuh"
 
 namespace ghf {
 namespace {
 
 using namespace ptx;
-using namespace fuse;
 
 constexpr int kD = 128;
 constexpr int kTile = 128;                 // edges per MMA tile (the N of the transposed product)
@@ -80,19 +77,12 @@ __global__ void pack_wt_kernel(const float* __restrict__ W_msg, const float* __r
   pack[r * (2 * kD * kD) + wt_offset(n, k)] = to_tf32_rna(v);
 }
 
-template <bool FUSED>
 __global__ void __launch_bounds__(kThreads, 1)
 mp_umma_ts_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
                   const int32_t* __restrict__ unit_rel, int64_t num_units, const int32_t* __restrict__ src_sorted,
                   const int32_t* __restrict__ dst_sorted, const float* __restrict__ h, int64_t dst_lo,
                   const float* __restrict__ wpack, const float* __restrict__ bias, float* __restrict__ acc,
-                  int* __restrict__ unit_counter, uint32_t flags, const FuseArgs fa) {
-  if constexpr (FUSED) {
-    if ((int)blockIdx.x < fa.epi_ctas) {
-      epilogue_cta<kD>(fa, acc, h, dst_lo);
-      return;
-    }
-  }
+                  int* __restrict__ unit_counter, uint32_t flags) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sA = (raw + 1023u) & ~1023u;
@@ -194,11 +184,6 @@ mp_umma_ts_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restr
         tc_fence_before();
         mbar_arrive(acc_empty(a));
       }
-      if constexpr (FUSED) {
-        __threadfence();
-        asm volatile("bar.sync 3, %0;" ::"n"(128 * kEpiGroups) : "memory");
-        if (threadIdx.x == 0) atomicAdd(&fa.units_done[fa.unit_phase[u]], 1);
-      }
     }
   } else if (warp < kWarpMma) {
     // ------------------------------------------------------------------ row-gather producers
@@ -293,20 +278,11 @@ mp_umma_ts_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restr
     // ------------------------------------------------------------------ unit scheduler
     if (lane == 0) {
       uint32_t sphase = 0;
-      int sq = 0, ready_phase = -1;
+      int sq = 0;
       for (;;) {
         mbar_wait(q_empty0 + 8u * sq, sphase ^ 1u);
         const int64_t u = atomicAdd(unit_counter, 1);
         const bool done = u >= num_units;
-        if constexpr (FUSED) {
-          if (!done) {
-            const int p = fa.unit_phase[u];
-            if (p != ready_phase) {
-              spin_until_at_least(&fa.zero_done[p], fa.epi_ctas);
-              ready_phase = p;
-            }
-          }
-        }
         q_slot_ptr[sq] = done ? -1 : (int)u;
         mbar_arrive(q_full0 + 8u * sq);
         if (++sq == kQueue) { sq = 0; sphase ^= 1u; }
@@ -366,11 +342,10 @@ uint32_t env_flags() {
   return env ? (uint32_t)atoi(env) : kDefaultFlags;
 }
 
-template <bool FUSED>
 int configure() {
   static bool done = false;
   if (!done) {
-    GHF_CUDA(cudaFuncSetAttribute(mp_umma_ts_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_umma_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     done = true;
   }
   return 0;
@@ -392,42 +367,11 @@ int mp_ts_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void
 int mp_ts_launch(const ghf_graph* g, const float* h, const float* bias, float* acc, const void* pack_scratch,
                  int* unit_counter, cudaStream_t stream) {
   GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_ts: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
-  if (int rc = configure<false>()) return rc;
+  if (int rc = configure()) return rc;
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
-  mp_umma_ts_kernel<false><<<(unsigned)grid, kThreads, kSmem, stream>>>(
+  mp_umma_ts_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo,
-      reinterpret_cast<const float*>(pack_scratch), bias, acc, unit_counter, env_flags(), FuseArgs{});
-  GHF_LAUNCH_CHECK();
-  return 0;
-}
-
-int mp_ts_launch_fused(const ghf_graph* g, const float* h, const float* bias, const float* ln_w, const float* ln_b,
-                       float eps, float* out, float* upd, const void* pack_scratch, void* sync_scratch,
-                       cudaStream_t stream) {
-  GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_ts: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
-  if (int rc = configure<true>()) return rc;
-  GHF_CUDA(cudaMemsetAsync(sync_scratch, 0, mp_umma_sync_bytes(g), stream));
-  int* counter = reinterpret_cast<int*>(sync_scratch);
-  FuseArgs fa{};
-  fa.unit_phase = g->unit_phase;
-  fa.phase_units = g->phase_units;
-  fa.zero_done = counter + 64;
-  fa.units_done = fa.zero_done + g->num_phases;
-  fa.indeg = g->indeg;
-  fa.ln_w = ln_w; fa.ln_b = ln_b; fa.eps = eps; fa.upd = upd;
-  fa.num_local = g->num_local;
-  fa.sb_nodes = g->sb_nodes;
-  fa.num_phases = (int32_t)g->num_phases;
-  const int sms = sm_count();
-  const char* env = getenv("GHF_EPI_CTAS");
-  int epi = env ? atoi(env) : 24;
-  epi = epi < 1 ? 1 : (epi > sms / 2 ? sms / 2 : epi);
-  const int64_t work = g->num_units > 0 ? g->num_units : 1;
-  const int64_t contraction = work < sms - epi ? work : sms - epi;
-  fa.epi_ctas = epi;
-  mp_umma_ts_kernel<true><<<(unsigned)(epi + contraction), kThreads, kSmem, stream>>>(
-      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h, g->dst_lo,
-      reinterpret_cast<const float*>(pack_scratch), bias, out, counter, env_flags(), fa);
+      reinterpret_cast<const float*>(pack_scratch), bias, acc, unit_counter, env_flags());
   GHF_LAUNCH_CHECK();
   return 0;
 }

@@ -297,7 +297,7 @@ class Graph:
                 "unit_rel": ur}
 
     def workspace(self, precision: int) -> torch.Tensor:
-        key = (precision, os.environ.get("GHF_MP_FUSED"))   # the fused tf32 layer needs no accumulator scratch
+        key = precision
         ws = self._workspace.get(key)
         if ws is None:
             n = int(lib().ghf_mp_workspace_bytes(self._h, self.hidden_dim, precision))

@@ -45,8 +45,6 @@ packed = None
 for spec in args or ["0,0,7"]:
     vals = [int(v) for v in spec.split(",")]
     sb, unit, flags = vals[:3]
-    os.environ["GHF_MP_FUSED"] = str(vals[3]) if len(vals) > 3 else "1"
-    os.environ["GHF_EPI_CTAS"] = str(vals[4]) if len(vals) > 4 else "20"
     os.environ["GHF_SB_NODES"], os.environ["GHF_UNIT_EDGES"], os.environ["GHF_MP_FLAGS"] = str(sb), str(unit), str(flags)
     prepared = model.prepare_packed(ei, utf8, offsets, w["N"])
     g = prepared.graph
@@ -65,8 +63,7 @@ for spec in args or ["0,0,7"]:
         g.mp_layer(h, wts["W_msg"], wts["W_self"], wts["bias"], ln.weight, ln.bias, 1e-5, PREC, h16=h16)
     prof, n = _native.profile_read()
     _native.profile_enable(False)
-    print(f"sb={g.sb_nodes:6d} unit={g.unit_edges:5d} flags={flags} fused={os.environ['GHF_MP_FUSED']} "
-          f"epi={os.environ['GHF_EPI_CTAS']} units={g.num_units:7d} "
+    print(f"sb={g.sb_nodes:6d} unit={g.unit_edges:5d} flags={flags} units={g.num_units:7d} "
           f"contraction {prof['contraction_ms']/n:.3f} ms  epilogue {prof['epilogue_ms']/n:.3f}  prep {prof['prep_ms']/n:.3f}",
           flush=True)
     del prepared, g
