@@ -42,8 +42,10 @@ extern "C" int64_t ghf_launch_count(int reset) {
 }
 
 extern "C" int ghf_device_ok(void) {
+  static bool checked[64] = {false};   // per device, once: the calls below are not allowed during stream capture
   int dev = 0, major = 0;
   GHF_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && checked[dev]) return 0;
   GHF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   GHF_REQUIRE(major == 10, "ghf_b200 needs a compute-capability 10.x device (sm_100a); current device is %d.x",
               major);
@@ -52,6 +54,7 @@ extern "C" int ghf_device_ok(void) {
   GHF_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
   uint64_t keep = ~0ull;
   GHF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  if (dev >= 0 && dev < 64) checked[dev] = true;
   return 0;
 }
 

@@ -257,6 +257,26 @@ class HyperGNN(nn.Module):
                     taps[f"upd.{l}"], taps[f"h.{l}"] = upd, h
         return h
 
+    def capture_prepared(self, node_features: torch.Tensor, prepared: PreparedGraph):
+        """CUDA-graph the layers of `forward_prepared` for one prepared graph: -> (replay, static_input, static_output).
+
+        Small graphs are launch-bound (BASELINE config 2: ~50 kernels of a few microseconds each); after the graph
+        tables are built nothing in the forward needs the host (the fp16 scales are chosen on the device), so the
+        whole sequence is captured once and replayed with one launch.  Copy new features into `static_input`
+        (same shape), call `replay()`, read `static_output`.  Parameters are read at replay time, in place."""
+        dev = _native.require_cuda(node_features, self.input_proj.weight)
+        static_in = node_features.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm up outside capture: lazy kernel configuration
+            for _ in range(2):
+                self.forward_prepared(static_in, prepared)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self.forward_prepared(static_in, prepared)
+        return graph.replay, static_in, static_out
+
     def _generate(self, layer: int, text_embs: torch.Tensor, num_unique: int) -> dict:
         d = self.hidden_dim
         if num_unique == 0:  # no edges: one all-zero relation keeps shapes valid
