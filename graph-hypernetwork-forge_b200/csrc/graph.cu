@@ -275,9 +275,21 @@ extern "C" int ghf_graph_build(const int64_t* d_edge_index, int64_t E, const uin
   g->num_edges_in = E; g->num_nodes = num_nodes; g->dst_lo = dst_lo; g->dst_hi = dst_hi;
   g->num_local = dst_hi - dst_lo; g->num_rel = num_rel > 0 ? num_rel : 1; g->hidden_dim = hidden_dim;
   if (sb_nodes <= 0) {
-    // destinations of one super-block: h[dst] rows + accumulator rows (2 * d * 4 B per node) ~ 48 MiB of L2
+    // Super-block size.  Small enough: the accumulator rows and the h[dst] rows of one super-block
+    // (2 * d * 4 B per node) fit in ~48 MiB of L2, so reductions and destination gathers stay on chip.  But every
+    // super-block re-reads the generated weights of the relations it touches: with many relations and few edges
+    // per relation (BASELINE config 4: 20k relations, 10.5 GB of weights per layer) that re-read costs more HBM
+    // traffic than letting the reductions go to HBM (a read-modify-write of 4d bytes per edge) in ONE block.
+    const int64_t nl = dst_hi - dst_lo > 0 ? dst_hi - dst_lo : 1;
     int64_t s = ((int64_t)48 << 20) / (8 * (int64_t)hidden_dim);
-    sb_nodes = (int32_t)(s < 1024 ? 1024 : s);
+    s = s < 1024 ? 1024 : s;
+    const int64_t n_sb = cdiv(nl, s);
+    const double w_bytes = (double)num_rel * 2.0 * hidden_dim * hidden_dim * 4.0;
+    const bool weights_stay_in_l2 = w_bytes < 48.0 * (1 << 20);
+    const double tiled = weights_stay_in_l2 ? w_bytes : (double)n_sb * w_bytes;
+    const double single = w_bytes + 2.0 * (double)E * hidden_dim * 4.0;
+    if (n_sb > 1 && single < tiled) s = nl;
+    sb_nodes = (int32_t)(s > 0x7FFFFFF0 ? 0x7FFFFFF0 : s);
   }
   g->sb_nodes = sb_nodes;
   g->unit_edges = unit_edges > 0 ? unit_edges : 1024;
