@@ -163,8 +163,10 @@ class Shadow:
         return Shadow(self.data[lo:hi], self.scale)
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_scale=None, want_f16: bool = False):
-    """exp(log_scale) * act(x @ weight.T + bias); x [M,K] float32 CUDA.  want_f16: -> (y, Shadow of y)."""
+def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_scale=None, want_f16: bool = False,
+           out=None, out_shadow=None):
+    """exp(log_scale) * act(x @ weight.T + bias); x [M,K] float32 CUDA.  want_f16: -> (y, Shadow of y).
+    `out` / `out_shadow`: write into these (contiguous float32 [M,N] / Shadow of [M,N]) instead of allocating."""
     x, weight = _f32(x), _f32(weight)
     dev = x.device
     M, K = x.shape
@@ -173,8 +175,14 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_
         raise RuntimeError(f"linear: x is [{M},{K}] but weight is {tuple(weight.shape)}")
     bias = None if bias is None else _f32(bias)
     log_scale = None if log_scale is None else _f32(log_scale)
-    y = torch.empty((M, N), dtype=torch.float32, device=dev)
-    y16 = Shadow(torch.empty((M, N), dtype=torch.float16, device=dev)) if want_f16 else None
+    y = torch.empty((M, N), dtype=torch.float32, device=dev) if out is None else out
+    if y.shape != (M, N) or y.dtype != torch.float32 or not y.is_contiguous():
+        raise RuntimeError(f"linear: out must be a contiguous float32 [{M},{N}] tensor")
+    y16 = None
+    if want_f16:
+        y16 = out_shadow if out_shadow is not None else Shadow(torch.empty((M, N), dtype=torch.float16, device=dev))
+        if y16.data.shape != (M, N):
+            raise RuntimeError(f"linear: out_shadow must shadow a [{M},{N}] matrix")
     with torch.cuda.device(dev):
         _check(lib().ghf_linear_f16out(_ptr(x), M, K, _ptr(weight), _ptr(bias), N, int(relu), _ptr(log_scale),
                                        _ptr(y), _ptr(y16.data) if y16 else None, _ptr(y16.scale) if y16 else None,
