@@ -214,11 +214,12 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
     }
     return 0;
   };
-  if (use_side)
-    for (int l = 0; l < L; ++l) {
-      if (int rc = generate(l)) return rc;
-      GHF_CUDA(cudaEventRecord(side.weights_ready[l], side.stream));
-    }
+  // only layer 0's generator is enqueued before graph build: the host spends ~10 us per launch, and the main
+  // stream should not wait for 27 of them; the other layers follow while graph build's tail and the projection run
+  if (use_side) {
+    if (int rc = generate(0)) return rc;
+    GHF_CUDA(cudaEventRecord(side.weights_ready[0], side.stream));
+  }
 
   ghf_graph* g = nullptr;
   if (int rc = ghf_graph_build(d_ei, E, nullptr, 0, rel, num_nodes, (int32_t)(U > 0 ? U : 1), d, 0, num_nodes, 0, 0,
@@ -240,6 +241,11 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   if (int rc = ghf_linear_f16out(d_x, num_nodes, F, Win, bin, d, 1, nullptr, h0, h16_0, want_f16 ? scales : nullptr,
                                  stream))
     return rc;
+  if (use_side)
+    for (int l = 1; l < L; ++l) {
+      if (int rc = generate(l)) return rc;
+      GHF_CUDA(cudaEventRecord(side.weights_ready[l], side.stream));
+    }
 
   float* cur = h0;
   float* nxt = h1;
