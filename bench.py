@@ -34,6 +34,8 @@ WORKLOADS = {
     # T = 64 (so generator hidden = 128) and F = d for c2-c4
     "c2": dict(name="fb15k237-shaped", N=14_541, E=272_115, R=237, d=128, L=2, T=64, F=128),
     "c3": dict(name="wikikg2-shaped", N=2_500_000, E=16_000_000, R=535, d=128, L=3, T=64, F=128),
+    # one eighth of BASELINE config 5 (50M nodes, 500M edges over 8 GPUs): the hidden-64 kernels at a rank's edge count
+    "c5s": dict(name="large-shape-1/8", N=6_250_000, E=62_500_000, R=1000, d=64, L=2, T=64, F=64),
     "c4": dict(name="zero-shot-20k-rel", N=100_000, E=2_000_000, R=20_000, d=256, L=2, T=64, F=256),
 }
 NAME_LEN = 14  # len("relation_00000")

@@ -31,11 +31,14 @@ struct UnitsOf {
 // destination lies outside [dst_lo, dst_hi).  Also counts in-degrees and the edges of every (super-block,
 // relation) group, from which the unit table follows without touching the sorted edges again.
 // Work item j is edge `edge_ids[j]` (a pre-selected subset, relation ids indexed by j) or edge j itself.
+// The sort payload is the SOURCE id (src != NULL): the sorted payload then IS src_sorted, no random gather after
+// the sort.  With src == NULL the payload is the edge id and nothing is counted (ghf_graph_export recomputes the
+// permutation that way, for parity checks only).
 template <class Key>
-__global__ void keys_kernel(const int64_t* __restrict__ dst, const int32_t* __restrict__ rel,
-                            const uint32_t* __restrict__ edge_ids, int64_t n, int64_t dst_lo, int64_t dst_hi,
-                            int64_t sb, int64_t R, uint64_t invalid_key, Key* __restrict__ keys,
-                            uint32_t* __restrict__ vals, int32_t* __restrict__ indeg,
+__global__ void keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                            const int32_t* __restrict__ rel, const uint32_t* __restrict__ edge_ids, int64_t n,
+                            int64_t dst_lo, int64_t dst_hi, int64_t sb, int64_t R, uint64_t invalid_key,
+                            Key* __restrict__ keys, uint32_t* __restrict__ vals, int32_t* __restrict__ indeg,
                             int32_t* __restrict__ group_count) {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -46,11 +49,13 @@ __global__ void keys_kernel(const int64_t* __restrict__ dst, const int32_t* __re
     const int64_t dl = v - dst_lo;
     const int64_t grp = (dl / sb) * R + rel[j];
     key = (uint64_t)(grp * sb + dl % sb);
-    atomicAdd(&indeg[dl], 1);
-    atomicAdd(&group_count[grp], 1);
+    if (src) {
+      atomicAdd(&indeg[dl], 1);
+      atomicAdd(&group_count[grp], 1);
+    }
   }
   keys[j] = (Key)key;
-  vals[j] = (uint32_t)e;
+  vals[j] = src ? (uint32_t)src[e] : (uint32_t)e;
 }
 
 struct InDstRange {
@@ -59,20 +64,20 @@ struct InDstRange {
   __host__ __device__ bool operator()(uint32_t e) const { return dst[e] >= lo && dst[e] < hi; }
 };
 
-// sorted position i -> (perm, src, local dst)
+// sorted position i -> local destination id, straight from the key
 template <class Key>
-__global__ void gather_kernel(const Key* __restrict__ keys, const uint32_t* __restrict__ vals,
-                              const int64_t* __restrict__ src, int64_t kept, int64_t sb, int64_t R,
-                              int64_t* __restrict__ perm, int32_t* __restrict__ src_sorted,
-                              int32_t* __restrict__ dst_sorted) {
+__global__ void dst_from_keys_kernel(const Key* __restrict__ keys, int64_t kept, int64_t sb, int64_t R,
+                                     int32_t* __restrict__ dst_sorted) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= kept) return;
   const uint64_t key = keys[i];
-  const uint32_t e = vals[i];
   const uint64_t g = key / sb;
-  perm[i] = e;
-  src_sorted[i] = (int32_t)src[e];
   dst_sorted[i] = (int32_t)((g / R) * sb + key % sb);
+}
+
+__global__ void widen_kernel(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
 }
 
 // one thread per (super-block, relation) group: its units, in order
@@ -123,7 +128,7 @@ using namespace ghf;
 extern "C" void ghf_graph_free(ghf_graph* g) {
   if (!g) return;
   cudaStream_t s = (cudaStream_t)g->stream;  // the stream that last used the tables
-  void* ptrs[] = {g->src_sorted, g->dst_sorted, g->perm, g->indeg, g->rowptr, g->unit_start, g->unit_count,
+  void* ptrs[] = {g->src_sorted, g->dst_sorted, g->indeg, g->rowptr, g->unit_start, g->unit_count,
                   g->unit_rel, g->unit_phase, g->phase_units, g->phase_tiles};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, s);
@@ -155,8 +160,8 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uin
   const int64_t En = n > 0 ? n : 1;
   GHF_CUDA(keys_a.alloc(En * sizeof(Key), stream));
   GHF_CUDA(keys_b.alloc(En * sizeof(Key), stream));
-  GHF_CUDA(vals_a.alloc(En * sizeof(uint32_t), stream));
-  GHF_CUDA(vals_b.alloc(En * sizeof(uint32_t), stream));
+  GHF_CUDA(vals_a.alloc(En * sizeof(uint32_t), stream));   // the payload (source ids): whichever of the two buffers
+  GHF_CUDA(vals_b.alloc(En * sizeof(uint32_t), stream));   // the sort ends in becomes the graph's src_sorted
   GHF_CUDA(gcount.alloc((groups + 1) * sizeof(int32_t), stream));   // one trailing zero: scans yield the totals
   GHF_CUDA(gstart.alloc((groups + 1) * sizeof(int32_t), stream));
   GHF_CUDA(ubase.alloc((groups + 1) * sizeof(int32_t), stream));
@@ -166,7 +171,7 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uin
   const int64_t* dst = d_edge_index + E;
   if (n > 0) {
     keys_kernel<Key><<<(unsigned)cdiv(n, threads), threads, 0, stream>>>(
-        dst, d_rel_ids, d_edge_ids, n, g->dst_lo, g->dst_hi, sb, R, invalid_key, keys_a.as<Key>(),
+        src, dst, d_rel_ids, d_edge_ids, n, g->dst_lo, g->dst_hi, sb, R, invalid_key, keys_a.as<Key>(),
         vals_a.as<uint32_t>(), g->indeg, gcount.as<int32_t>());
     GHF_LAUNCH_CHECK();
   }
@@ -215,16 +220,20 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uin
   g->num_units = totals[1];
   GHF_CUDA(cudaMemcpyAsync(g->rowptr + nl, &g->num_kept, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
 
-  GHF_CUDA(dmalloc(&g->src_sorted, kept, g));
+  {  // adopt the sorted payload as src_sorted (its first `kept` entries; the rest belongs to dropped edges)
+    TempBuf& cur = vbuf.Current() == vals_a.as<uint32_t>() ? vals_a : vals_b;
+    g->src_sorted = reinterpret_cast<int32_t*>(cur.p);
+    g->bytes += (size_t)En * sizeof(uint32_t);
+    cur.p = nullptr;   // ownership moved to the graph (freed in ghf_graph_free)
+  }
   GHF_CUDA(dmalloc(&g->dst_sorted, kept, g));
-  GHF_CUDA(dmalloc(&g->perm, kept, g));
   GHF_CUDA(dmalloc(&g->unit_start, g->num_units, g));
   GHF_CUDA(dmalloc(&g->unit_count, g->num_units, g));
   GHF_CUDA(dmalloc(&g->unit_rel, g->num_units, g));
   GHF_CUDA(dmalloc(&g->unit_phase, g->num_units, g));
   if (kept == 0) return 0;
-  gather_kernel<Key><<<(unsigned)cdiv(kept, threads), threads, 0, stream>>>(
-      kbuf.Current(), vbuf.Current(), src, kept, sb, R, g->perm, g->src_sorted, g->dst_sorted);
+  dst_from_keys_kernel<Key><<<(unsigned)cdiv(kept, threads), threads, 0, stream>>>(kbuf.Current(), kept, sb, R,
+                                                                                     g->dst_sorted);
   GHF_LAUNCH_CHECK();
   unit_fill_kernel<<<(unsigned)cdiv(groups, threads), threads, 0, stream>>>(
       gcount.as<int32_t>(), gstart.as<int32_t>(), ubase.as<int32_t>(), groups, R, g->unit_edges, g->unit_start,
@@ -314,15 +323,57 @@ extern "C" int ghf_graph_info(const ghf_graph* g, int64_t info[6]) {
   return 0;
 }
 
-extern "C" int ghf_graph_export(const ghf_graph* g, int64_t* d_perm, int32_t* d_indeg, int64_t* d_rowptr,
-                                int32_t* d_unit_start, int32_t* d_unit_count, int32_t* d_unit_rel,
-                                void* stream_) {
+// The permutation (original edge id at each sorted position) is not needed by any kernel; parity checks ask for it
+// through ghf_graph_export, which re-sorts (key, edge id) from the build inputs.
+template <class Key>
+static int recompute_perm(const ghf_graph* g, const int64_t* d_edge_index, const uint32_t* d_edge_ids, int64_t n,
+                          const int32_t* d_rel_ids, int64_t* d_perm, cudaStream_t stream) {
+  const int64_t E = g->num_edges_in, sb = g->sb_nodes, R = g->num_rel, nl = g->num_local;
+  const int64_t n_sb = cdiv(nl > 0 ? nl : 1, sb);
+  const uint64_t invalid_key = (uint64_t)n_sb * R * sb;
+  const int end_bit = bits_for(invalid_key);
+  if (n == 0 || g->num_kept == 0) return 0;
+  TempBuf keys_a, keys_b, vals_a, vals_b, tmp;
+  GHF_CUDA(keys_a.alloc(n * sizeof(Key), stream));
+  GHF_CUDA(keys_b.alloc(n * sizeof(Key), stream));
+  GHF_CUDA(vals_a.alloc(n * sizeof(uint32_t), stream));
+  GHF_CUDA(vals_b.alloc(n * sizeof(uint32_t), stream));
+  const int threads = 256;
+  keys_kernel<Key><<<(unsigned)cdiv(n, threads), threads, 0, stream>>>(
+      nullptr, d_edge_index + E, d_rel_ids, d_edge_ids, n, g->dst_lo, g->dst_hi, sb, R, invalid_key, keys_a.as<Key>(),
+      vals_a.as<uint32_t>(), nullptr, nullptr);
+  GHF_LAUNCH_CHECK();
+  cub::DoubleBuffer<Key> kbuf(keys_a.as<Key>(), keys_b.as<Key>());
+  cub::DoubleBuffer<uint32_t> vbuf(vals_a.as<uint32_t>(), vals_b.as<uint32_t>());
+  size_t bytes = 0;
+  GHF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kbuf, vbuf, (int)n, 0, end_bit, stream));
+  GHF_CUDA(tmp.alloc(bytes, stream));
+  GHF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kbuf, vbuf, (int)n, 0, end_bit, stream));
+  widen_kernel<<<(unsigned)cdiv(g->num_kept, threads), threads, 0, stream>>>(vbuf.Current(), g->num_kept, d_perm);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ghf_graph_export(const ghf_graph* g, const int64_t* d_edge_index, const uint32_t* d_edge_ids,
+                                int64_t n_subset, const int32_t* d_rel_ids, int64_t* d_perm, int32_t* d_indeg,
+                                int64_t* d_rowptr, int32_t* d_unit_start, int32_t* d_unit_count,
+                                int32_t* d_unit_rel, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(g != nullptr, "ghf_graph_export: graph is NULL");
+  if (d_perm) {
+    GHF_REQUIRE(d_edge_index != nullptr && d_rel_ids != nullptr,
+                "ghf_graph_export: the permutation is recomputed from the build inputs (edge_index, rel_ids)");
+    const int64_t n_items = d_edge_ids ? n_subset : g->num_edges_in;
+    const uint64_t key_range = (uint64_t)cdiv(g->num_local > 0 ? g->num_local : 1, g->sb_nodes) * g->num_rel *
+                               (uint64_t)g->sb_nodes;
+    if (int rc = key_range < 0xFFFFFFFFull
+                     ? recompute_perm<uint32_t>(g, d_edge_index, d_edge_ids, n_items, d_rel_ids, d_perm, stream)
+                     : recompute_perm<uint64_t>(g, d_edge_index, d_edge_ids, n_items, d_rel_ids, d_perm, stream))
+      return rc;
+  }
   auto cp = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
     return (dst && bytes) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream) : cudaSuccess;
   };
-  GHF_CUDA(cp(d_perm, g->perm, g->num_kept * sizeof(int64_t)));
   GHF_CUDA(cp(d_indeg, g->indeg, g->num_local * sizeof(int32_t)));
   GHF_CUDA(cp(d_rowptr, g->rowptr, (g->num_local + 1) * sizeof(int64_t)));
   GHF_CUDA(cp(d_unit_start, g->unit_start, g->num_units * sizeof(int32_t)));

@@ -14,7 +14,6 @@ struct ghf_graph {
   // all arrays below are device memory owned by the graph
   int32_t* src_sorted = nullptr;   // [kept]  global source id at each sorted position
   int32_t* dst_sorted = nullptr;   // [kept]  LOCAL destination id (dst - dst_lo)
-  int64_t* perm = nullptr;         // [kept]  original edge id at each sorted position
   int32_t* indeg = nullptr;        // [local] in-degree (multi-edges counted)
   int64_t* rowptr = nullptr;       // [local+1] exclusive scan of indeg (dst-CSR row pointer)
   int32_t* unit_start = nullptr;   // [units] first sorted position of the unit

@@ -58,7 +58,7 @@ def lib():
                                     c_int32, c_int32, POINTER(c_void_p), P]),
         "ghf_graph_free": (None, [P]),
         "ghf_graph_info": (c_int, [P, POINTER(c_int64)]),
-        "ghf_graph_export": (c_int, [P, P, P, P, P, P, P, P]),
+        "ghf_graph_export": (c_int, [P, P, P, c_int64, P, P, P, P, P, P, P, P]),
         "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
         "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
@@ -279,6 +279,7 @@ class Graph:
                                          self.num_nodes, self.num_rel, self.hidden_dim, self.dst_lo, self.dst_hi,
                                          int(sb_nodes), int(unit_edges), ctypes.byref(self._h), _stream(dev)),
                    "ghf_graph_build")
+        self._inputs = (edge_index, edge_ids, rel_ids.contiguous())   # export() recomputes the permutation from them
         info = (c_int64 * 6)()
         _check(lib().ghf_graph_info(self._h, info), "ghf_graph_info")
         (self.num_kept, self.num_units, self.sb_nodes, self.unit_edges, self.num_local, self.bytes) = map(int, info)
@@ -299,8 +300,10 @@ class Graph:
         uc = torch.empty_like(us)
         ur = torch.empty_like(us)
         with torch.cuda.device(dev):
-            _check(lib().ghf_graph_export(self._h, _ptr(perm), _ptr(indeg), _ptr(rowptr), _ptr(us), _ptr(uc),
-                                          _ptr(ur), _stream(dev)), "ghf_graph_export")
+            ei, ids, rel = self._inputs
+            _check(lib().ghf_graph_export(self._h, _ptr(ei), _ptr(ids), 0 if ids is None else ids.numel(), _ptr(rel),
+                                          _ptr(perm), _ptr(indeg), _ptr(rowptr), _ptr(us), _ptr(uc), _ptr(ur),
+                                          _stream(dev)), "ghf_graph_export")
         return {"perm": perm, "indeg": indeg, "rowptr": rowptr, "unit_start": us, "unit_count": uc,
                 "unit_rel": ur}
 

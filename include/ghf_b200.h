@@ -97,12 +97,13 @@ int ghf_graph_build(const int64_t* d_edge_index, int64_t E, const uint32_t* d_ed
 void ghf_graph_free(ghf_graph* g);
 /* sizes: [0]=kept edges, [1]=units, [2]=sb_nodes, [3]=unit_edges, [4]=local nodes, [5]=bytes held */
 int ghf_graph_info(const ghf_graph* g, int64_t info[6]);
-/* device views for parity checks: any pointer may be NULL.  perm[kept] int64 (original edge id
- * at each sorted position), indeg[local nodes] int32, rowptr[local nodes+1] int64,
- * unit_start/unit_count/unit_rel [units] int32. */
-int ghf_graph_export(const ghf_graph* g, int64_t* d_perm, int32_t* d_indeg, int64_t* d_rowptr,
-                     int32_t* d_unit_start, int32_t* d_unit_count, int32_t* d_unit_rel,
-                     void* stream);
+/* device views for parity checks: any output pointer may be NULL.  perm[kept] int64 (original edge id at each
+ * sorted position; no kernel needs it, so it is recomputed here by re-sorting - pass the SAME d_edge_index,
+ * d_edge_ids / n_subset and d_rel_ids the graph was built from; they may be NULL when d_perm is NULL),
+ * indeg[local nodes] int32, rowptr[local nodes+1] int64, unit_start/unit_count/unit_rel [units] int32. */
+int ghf_graph_export(const ghf_graph* g, const int64_t* d_edge_index, const uint32_t* d_edge_ids, int64_t n_subset,
+                     const int32_t* d_rel_ids, int64_t* d_perm, int32_t* d_indeg, int64_t* d_rowptr,
+                     int32_t* d_unit_start, int32_t* d_unit_count, int32_t* d_unit_rel, void* stream);
 
 /* ---- a10-a13: one message-passing layer (HG:160-230, HG:289-296) ---------------------------
  *   upd_v = (1/c_v) sum_{e:(u->v)} ( h_u W_msg[r_e] + bias[r_e] + h_v W_self[r_e] ),  c_v = max(indeg,1)
