@@ -39,13 +39,18 @@ __global__ void keys_kernel(const int64_t* __restrict__ src, const int64_t* __re
                             const int32_t* __restrict__ rel, const uint32_t* __restrict__ edge_ids, int64_t n,
                             int64_t dst_lo, int64_t dst_hi, int64_t sb, int64_t R, uint64_t invalid_key,
                             Key* __restrict__ keys, uint32_t* __restrict__ vals, int32_t* __restrict__ indeg,
-                            int32_t* __restrict__ group_count) {
+                            int32_t* __restrict__ group_count, int64_t num_nodes, int32_t* __restrict__ bad_ids) {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int64_t e = edge_ids ? edge_ids[j] : j;
   const int64_t v = dst[e];
+  if (src) {  // node ids outside [0, N) would make the gathers read out of bounds: reported by ghf_graph_build
+    const int64_t u = src[e];
+    if (u < 0 || u >= num_nodes || v < 0 || v >= num_nodes) atomicOr(bad_ids, 1);
+    if (rel[j] < 0 || rel[j] >= R) atomicOr(bad_ids, 2);
+  }
   uint64_t key = invalid_key;
-  if (v >= dst_lo && v < dst_hi) {
+  if (v >= dst_lo && v < dst_hi && rel[j] >= 0 && rel[j] < R) {
     const int64_t dl = v - dst_lo;
     const int64_t grp = (dl / sb) * R + rel[j];
     key = (uint64_t)(grp * sb + dl % sb);
@@ -55,7 +60,7 @@ __global__ void keys_kernel(const int64_t* __restrict__ src, const int64_t* __re
     }
   }
   keys[j] = (Key)key;
-  vals[j] = src ? (uint32_t)src[e] : (uint32_t)e;
+  vals[j] = src ? (uint32_t)src[e] : (uint32_t)e;   // (an out-of-range source id never reaches a kernel: the build fails)
 }
 
 struct InDstRange {
@@ -166,13 +171,16 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uin
   GHF_CUDA(gstart.alloc((groups + 1) * sizeof(int32_t), stream));
   GHF_CUDA(ubase.alloc((groups + 1) * sizeof(int32_t), stream));
   GHF_CUDA(cudaMemsetAsync(gcount.p, 0, (size_t)(groups + 1) * sizeof(int32_t), stream));
+  TempBuf bad;
+  GHF_CUDA(bad.alloc(sizeof(int32_t), stream));
+  GHF_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int32_t), stream));
 
   const int64_t* src = d_edge_index;
   const int64_t* dst = d_edge_index + E;
   if (n > 0) {
     keys_kernel<Key><<<(unsigned)cdiv(n, threads), threads, 0, stream>>>(
         src, dst, d_rel_ids, d_edge_ids, n, g->dst_lo, g->dst_hi, sb, R, invalid_key, keys_a.as<Key>(),
-        vals_a.as<uint32_t>(), g->indeg, gcount.as<int32_t>());
+        vals_a.as<uint32_t>(), g->indeg, gcount.as<int32_t>(), g->num_nodes, bad.as<int32_t>());
     GHF_LAUNCH_CHECK();
   }
   // rowptr[0..local) = exclusive scan of in-degree (int64); rowptr[local] = kept is written below
@@ -201,7 +209,8 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uin
     GHF_CUDA(cub::DeviceScan::ExclusiveSum(t.p, b2, units_it, ubase.as<int32_t>(), (int)(groups + 1), stream));
     g_launches.fetch_add(2, std::memory_order_relaxed);
   }
-  int32_t totals[2] = {0, 0};  // kept edges, units: the one host round trip of the build
+  int32_t totals[2] = {0, 0}, bad_ids = 0;  // kept edges, units, id check: the one host round trip of the build
+  GHF_CUDA(cudaMemcpyAsync(&bad_ids, bad.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaMemcpyAsync(&totals[0], gstart.as<int32_t>() + groups, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaMemcpyAsync(&totals[1], ubase.as<int32_t>() + groups, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
 
@@ -215,6 +224,9 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uin
     g_launches.fetch_add((end_bit + 7) / 8 + 2, std::memory_order_relaxed);
   }
   GHF_CUDA(cudaStreamSynchronize(stream));
+  GHF_REQUIRE((bad_ids & 1) == 0, "ghf_graph_build: edge_index holds node ids outside [0, %lld)",
+              (long long)g->num_nodes);
+  GHF_REQUIRE((bad_ids & 2) == 0, "ghf_graph_build: relation ids outside [0, %d)", g->num_rel);
   const int64_t kept = totals[0];
   g->num_kept = kept;
   g->num_units = totals[1];
@@ -341,7 +353,7 @@ static int recompute_perm(const ghf_graph* g, const int64_t* d_edge_index, const
   const int threads = 256;
   keys_kernel<Key><<<(unsigned)cdiv(n, threads), threads, 0, stream>>>(
       nullptr, d_edge_index + E, d_rel_ids, d_edge_ids, n, g->dst_lo, g->dst_hi, sb, R, invalid_key, keys_a.as<Key>(),
-      vals_a.as<uint32_t>(), nullptr, nullptr);
+      vals_a.as<uint32_t>(), nullptr, nullptr, g->num_nodes, nullptr);
   GHF_LAUNCH_CHECK();
   cub::DoubleBuffer<Key> kbuf(keys_a.as<Key>(), keys_b.as<Key>());
   cub::DoubleBuffer<uint32_t> vbuf(vals_a.as<uint32_t>(), vals_b.as<uint32_t>());

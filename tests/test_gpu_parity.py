@@ -352,3 +352,19 @@ def test_cuda_graph_replay_of_prepared_forward():
         return 1e3 * (time.perf_counter() - t0) / n
     print(f"c2 forward_prepared: eager {bench(lambda: model.forward_prepared(x, prepared)):.3f} ms, "
           f"CUDA graph replay {bench(replay):.3f} ms")
+
+
+def test_out_of_range_node_ids_are_reported():
+    """Node ids outside [0, N) would read out of bounds in the gathers: the graph build reports them (the reference
+    raises an IndexError from torch's scatter/gather)."""
+    from graph_hypernetwork_forge import _native
+    N, E = 100, 1000
+    rng = np.random.default_rng(0)
+    ei = torch.from_numpy(rng.integers(0, N, (2, E))).to(DEV)
+    rel = torch.zeros(E, dtype=torch.int32, device=DEV)
+    _native.Graph(ei, rel, N, 1, 32)                     # fine
+    for row, val in ((0, N), (0, -1), (1, N + 5), (1, -3)):
+        bad = ei.clone()
+        bad[row, 17] = val
+        with pytest.raises(RuntimeError, match="outside"):
+            _native.Graph(bad, rel, N, 1, 32)
