@@ -65,7 +65,8 @@ int ghf_text_encode(const uint8_t* d_utf8, const int64_t* d_offsets, const int64
 
 /* ---- a3 / a8: Linear (+ReLU) (+exp(log_scale)) (HG:261, WG:97-107, WG:138-140) -------------
  * Y[M,N] = alpha * act( X[M,K] @ W[N,K]^T + b[N] ), act = ReLU when relu != 0,
- * alpha = exp(*d_log_scale) when d_log_scale != NULL else 1.  fp32 FFMA. */
+ * alpha = exp(*d_log_scale) when d_log_scale != NULL else 1.  fp32-grade: tcgen05 with a 3xTF32 split when K = 128,
+ * N % 128 == 0 and M*N >= 2^21 (node projection, the generators' last Linear), fp32 FFMA tiles otherwise. */
 int ghf_linear(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
                int relu, const float* d_log_scale, float* d_Y, void* stream);
 
@@ -88,7 +89,8 @@ int ghf_linear_f16out(const float* d_X, int64_t M, int K, const float* d_W, cons
  * d_edge_index is the reference's [2,E] int64 tensor.  Edges with dst outside the range are
  * dropped (1-D destination partition for multi-GPU).  Work items: all E edges with d_rel_ids[E] (d_edge_ids
  * NULL), or the pre-selected edges d_edge_ids[0..n_subset) with d_rel_ids[n_subset] indexed like d_edge_ids.
- * sb_nodes <= 0 / unit_edges <= 0 pick defaults.  Synchronises `stream` once (to size the tables). */
+ * sb_nodes <= 0 / unit_edges <= 0 pick defaults.  Synchronises `stream` once (to size the tables); fails when a
+ * node id lies outside [0, num_nodes) or a relation id outside [0, num_rel). */
 typedef struct ghf_graph ghf_graph;
 int ghf_graph_build(const int64_t* d_edge_index, int64_t E, const uint32_t* d_edge_ids, int64_t n_subset,
                     const int32_t* d_rel_ids, int64_t num_nodes, int32_t num_rel, int32_t hidden_dim,
