@@ -357,39 +357,33 @@ static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_
   return 0;
 }
 
-extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
-                                const float* d_W_msg, const float* d_W_self, const float* d_bias,
-                                const float* d_ln_w, const float* d_ln_b, float eps, int precision, float* d_out,
-                                void* d_out16, float* d_out16_scale, float* d_upd, void* d_workspace,
-                                void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  GHF_REQUIRE(g != nullptr, "ghf_mp_layer: graph is NULL");
-  GHF_REQUIRE(d_workspace != nullptr, "ghf_mp_layer: workspace is NULL");
-  GHF_REQUIRE(precision == GHF_PREC_FP32 || precision == GHF_PREC_TF32 || precision == GHF_PREC_F16,
-              "ghf_mp_layer: precision=%d", precision);
-  GHF_REQUIRE(d_h16 == nullptr || d_h16_scale != nullptr, "ghf_mp_layer: d_h16 needs d_h16_scale (float[2])");
-  GHF_REQUIRE(d_out16 == nullptr || d_out16_scale != nullptr, "ghf_mp_layer: d_out16 needs d_out16_scale (float[2])");
+// The contraction of one layer: acc[v] = sum over in-edges of [h_u | h_v] @ [W_msg[r] ; W_self[r]] + bias[r].
+// `acc_ext` (optional) receives the sums; otherwise they stay in the workspace for the epilogue.  -> *acc_used.
+static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                           const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
+                           float* acc_ext, void* d_workspace, cudaStream_t stream, float** acc_used, ProfRec* rec) {
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
-  g->stream = stream_;
-  if (nl == 0) return 0;
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
   // (the f16 kernel clears the accumulator itself and keeps per-phase sync words next to the counter)
   const bool self_clearing = precision == GHF_PREC_F16 && g->num_units > 0;
   int* counter = reinterpret_cast<int*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
-  float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) +
-                                        (precision == GHF_PREC_F16 ? mp_f16_sync_bytes(g) : 256));
+  float* acc_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) +
+                                           (precision == GHF_PREC_F16 ? mp_f16_sync_bytes(g) : 256));
   const int64_t acc_bytes = align_up(nl * (int64_t)d * 4, 256);
-  void* pack = reinterpret_cast<char*>(acc) + acc_bytes;
-  ProfRec rec{};
-  const bool prof = g_prof_on;
-  if (prof) {
-    for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
-    GHF_CUDA(cudaEventRecord(rec.e[0], stream));
+  void* pack = reinterpret_cast<char*>(acc_ws) + acc_bytes;
+  float* acc = acc_ext ? acc_ext : acc_ws;
+  *acc_used = acc;
+  if (rec) GHF_CUDA(cudaEventRecord(rec->e[0], stream));
+  if (!self_clearing) {
+    const size_t head = reinterpret_cast<char*>(acc_ws) - reinterpret_cast<char*>(counter);
+    if (acc_ext) {
+      GHF_CUDA(cudaMemsetAsync(counter, 0, head, stream));
+      GHF_CUDA(cudaMemsetAsync(acc_ext, 0, nl * (size_t)d * 4, stream));
+    } else {
+      GHF_CUDA(cudaMemsetAsync(counter, 0, head + nl * (size_t)d * 4, stream));
+    }
   }
-  if (!self_clearing)
-    GHF_CUDA(cudaMemsetAsync(counter, 0, (reinterpret_cast<char*>(acc) - reinterpret_cast<char*>(counter)) +
-                                             nl * (size_t)d * 4, stream));
   const bool ts = mp_ts_enabled(d);
   const void* h16 = d_h16;
   const float* h16_scale = d_h16_scale;
@@ -411,7 +405,7 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
       }
     }
   }
-  if (prof) GHF_CUDA(cudaEventRecord(rec.e[1], stream));
+  if (rec) GHF_CUDA(cudaEventRecord(rec->e[1], stream));
   if (g->num_units > 0) {
     int rc;
     if (precision == GHF_PREC_TF32) {
@@ -428,7 +422,38 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     }
     if (rc) return rc;
   }
-  if (prof) GHF_CUDA(cudaEventRecord(rec.e[2], stream));
+  if (rec) GHF_CUDA(cudaEventRecord(rec->e[2], stream));
+  return 0;
+}
+
+static int check_layer_args(const ghf_graph* g, const void* d_workspace, int precision, const void* d_h16,
+                            const float* d_h16_scale) {
+  GHF_REQUIRE(g != nullptr, "ghf_mp_layer: graph is NULL");
+  GHF_REQUIRE(d_workspace != nullptr, "ghf_mp_layer: workspace is NULL");
+  GHF_REQUIRE(precision == GHF_PREC_FP32 || precision == GHF_PREC_TF32 || precision == GHF_PREC_F16,
+              "ghf_mp_layer: precision=%d", precision);
+  GHF_REQUIRE(d_h16 == nullptr || d_h16_scale != nullptr, "ghf_mp_layer: d_h16 needs d_h16_scale (float[2])");
+  return 0;
+}
+
+extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                                const float* d_W_msg, const float* d_W_self, const float* d_bias,
+                                const float* d_ln_w, const float* d_ln_b, float eps, int precision, float* d_out,
+                                void* d_out16, float* d_out16_scale, float* d_upd, void* d_workspace,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = check_layer_args(g, d_workspace, precision, d_h16, d_h16_scale)) return rc;
+  GHF_REQUIRE(d_out16 == nullptr || d_out16_scale != nullptr, "ghf_mp_layer: d_out16 needs d_out16_scale (float[2])");
+  g->stream = stream_;
+  if (g->num_local == 0) return 0;
+  ProfRec rec{};
+  const bool prof = g_prof_on;
+  if (prof)
+    for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
+  float* acc = nullptr;
+  if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
+                               d_workspace, stream, &acc, prof ? &rec : nullptr))
+    return rc;
   if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream))
     return rc;
   if (prof) {
@@ -436,6 +461,20 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     g_prof.push_back(rec);
   }
   return 0;
+}
+
+extern "C" int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void* d_x16, const float* d_x16_scale,
+                               const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
+                               float* d_acc, void* d_workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = check_layer_args(g, d_workspace, precision, d_x16, d_x16_scale)) return rc;
+  GHF_REQUIRE(d_acc != nullptr && reinterpret_cast<uintptr_t>(d_acc) % 256 == 0,
+              "ghf_mp_contract: d_acc must be a 256-byte aligned [local nodes, hidden] buffer");
+  g->stream = stream_;
+  if (g->num_local == 0) return 0;
+  float* acc = nullptr;
+  return run_contraction(g, d_x, d_x16, d_x16_scale, d_W_msg, d_W_self, d_bias, precision, d_acc, d_workspace,
+                         stream, &acc, nullptr);
 }
 
 extern "C" int ghf_absmax(const float* d_x, int64_t elems, float* d_scale, void* stream_) {

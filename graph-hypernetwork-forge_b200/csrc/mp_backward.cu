@@ -1,0 +1,234 @@
+// mp_backward.cu — gradient kernels of one message-passing layer (the reference is trainable,
+// tests/test_hypergnn.py:183-226 and demo.py:79-101 call loss.backward() through HyperGNN.forward).
+//
+// Forward (mp.cu):   acc_v = sum_{e:(u->v), r} ( h_u W_msg[r] + h_v W_self[r] + bias[r] )
+//                    upd_v = acc_v / max(indeg_v, 1);  x_v = relu(upd_v + h_v);  out_v = LayerNorm(x_v)
+// Backward, given g_out:
+//   (1) ghf_mp_epilogue_backward:  g_pre_v = dL/d(upd_v + h_v)  (LayerNorm and ReLU undone), g_acc_v = g_pre_v / cnt_v,
+//                                  g_ln_w, g_ln_b (column sums over the rows)
+//   (2) dL/dh = g_pre + sum_{e:(u->v)} g_acc_v W_msg[r]^T (at u) + sum_{e:(.->v)} g_acc_v W_self[r]^T (at v):
+//       the SAME contraction as the forward, run by the host side through ghf_mp_contract on the reversed graph
+//       (transposed W_msg) and on the graph itself (transposed W_self) - no new kernel;
+//   (3) ghf_mp_weight_grad:  g_W_msg[r] = sum_{e in r} h_u^T g_acc_v,  g_W_self[r] = sum_{e in r} h_v^T g_acc_v,
+//                            g_bias[r] = sum_{e in r} g_acc_v      - a contraction over the EDGES of each unit.
+#include "common.cuh"
+#include "ghf_b200.h"
+#include "graph.cuh"
+
+namespace ghf {
+namespace {
+
+constexpr int kBwdMaxV = 8;  // hidden_dim <= 256 keeps a row in registers (one warp per row)
+
+__global__ void __launch_bounds__(256)
+mp_epilogue_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ upd,
+                       const int32_t* __restrict__ indeg, const float* __restrict__ h, int64_t dst_lo,
+                       int64_t num_local, int d, const float* __restrict__ ln_w, float eps,
+                       float* __restrict__ g_pre, float* __restrict__ g_acc, float* __restrict__ g_lnw,
+                       float* __restrict__ g_lnb) {
+  extern __shared__ float red[];  // [2][d] block partials of the LayerNorm parameter gradients
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) red[c] = 0.f;
+  __syncthreads();
+  float pw[kBwdMaxV], pb[kBwdMaxV], lw[kBwdMaxV];
+#pragma unroll
+  for (int i = 0; i < kBwdMaxV; ++i) {
+    pw[i] = pb[i] = 0.f;
+    const int c = lane + 32 * i;
+    lw[i] = c < d ? ln_w[c] : 0.f;
+  }
+  const float inv_d = 1.f / (float)d;
+  for (int64_t v = w0; v < num_local; v += warps) {
+    const float inv_cnt = 1.f / (float)max(indeg[v], 1);
+    const float* up = upd + v * d;
+    const float* hv = h + (dst_lo + v) * d;
+    const float* go = g_out + v * d;
+    float x[kBwdMaxV], gy[kBwdMaxV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBwdMaxV; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = gy[i] = 0.f;
+      if (c < d) {
+        x[i] = fmaxf(up[c] + hv[c], 0.f);
+        gy[i] = go[c];
+        sum += x[i];
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    const float mean = sum * inv_d;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBwdMaxV; ++i)
+      if (lane + 32 * i < d) var += (x[i] - mean) * (x[i] - mean);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+    const float rstd = rsqrtf(var * inv_d + eps);
+    float s1 = 0.f, s2 = 0.f;
+    float xh[kBwdMaxV];
+#pragma unroll
+    for (int i = 0; i < kBwdMaxV; ++i) {
+      xh[i] = (x[i] - mean) * rstd;
+      if (lane + 32 * i < d) {
+        const float gh = gy[i] * lw[i];
+        s1 += gh;
+        s2 += gh * xh[i];
+        pw[i] += gy[i] * xh[i];
+        pb[i] += gy[i];
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, s);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, s);
+    }
+    s1 *= inv_d;
+    s2 *= inv_d;
+#pragma unroll
+    for (int i = 0; i < kBwdMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d) {
+        const float gx = rstd * (gy[i] * lw[i] - s1 - xh[i] * s2);
+        const float gp = x[i] > 0.f ? gx : 0.f;  // relu'(0) = 0, as torch
+        g_pre[v * d + c] = gp;
+        g_acc[v * d + c] = gp * inv_cnt;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kBwdMaxV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < d) {
+      atomicAdd(&red[c], pw[i]);
+      atomicAdd(&red[d + c], pb[i]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    atomicAdd(&g_lnw[c], red[c]);
+    atomicAdd(&g_lnb[c], red[d + c]);
+  }
+}
+
+// ---- weight gradients, CUDA cores (any hidden_dim): one CTA per (unit, 64-row tile of [W_msg ; W_self], 64-column
+// tile); the unit's edges are the contraction dimension, staged 32 at a time.
+constexpr int kWgTM = 64, kWgTN = 64, kWgTE = 32;
+
+__global__ void __launch_bounds__(256)
+mp_wgrad_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
+                const int32_t* __restrict__ unit_rel, const int32_t* __restrict__ src_sorted,
+                const int32_t* __restrict__ dst_sorted, const float* __restrict__ h, const float* __restrict__ g_acc,
+                int64_t dst_lo, int d, float* __restrict__ gW_msg, float* __restrict__ gW_self,
+                float* __restrict__ gbias) {
+  __shared__ __align__(16) float sA[kWgTE][kWgTM];
+  __shared__ __align__(16) float sG[kWgTE][kWgTN];
+  __shared__ int64_t s_src[kWgTE], s_dst[kWgTE];
+  const int64_t u = blockIdx.x;
+  const int m0 = blockIdx.y * kWgTM, n0 = blockIdx.z * kWgTN;
+  const int start = unit_start[u], count = unit_count[u];
+  const int64_t r = unit_rel[u];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  float bsum[4] = {};
+  for (int e0 = 0; e0 < count; e0 += kWgTE) {
+    const int rows = min(kWgTE, count - e0);
+    __syncthreads();
+    if (threadIdx.x < kWgTE) {
+      const bool ok = (int)threadIdx.x < rows;
+      s_src[threadIdx.x] = ok ? src_sorted[start + e0 + threadIdx.x] : -1;
+      s_dst[threadIdx.x] = ok ? dst_sorted[start + e0 + threadIdx.x] : -1;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kWgTE * kWgTM; idx += 256) {
+      const int e = idx / kWgTM, m = m0 + idx % kWgTM;
+      float a = 0.f;
+      if (s_src[e] >= 0 && m < 2 * d)
+        a = m < d ? h[s_src[e] * d + m] : h[(dst_lo + s_dst[e]) * d + (m - d)];
+      sA[e][idx % kWgTM] = a;
+      const int n = n0 + idx % kWgTN;
+      sG[e][idx % kWgTN] = (s_src[e] >= 0 && n < d) ? g_acc[s_dst[e] * d + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int e = 0; e < kWgTE; ++e) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[e][ty * 4]);
+      const float4 g = *reinterpret_cast<const float4*>(&sG[e][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
+      if (blockIdx.y == 0 && ty == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bsum[j] += gv[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= 2 * d) continue;
+    float* row = m < d ? gW_msg + (r * d + m) * d : gW_self + (r * d + (m - d)) * d;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < d) atomicAdd(row + n, acc[i][j]);
+    }
+  }
+  if (blockIdx.y == 0 && ty == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < d) atomicAdd(gbias + r * d + n, bsum[j]);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace ghf
+
+using namespace ghf;
+
+extern "C" int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out, const float* d_upd,
+                                        const float* d_h, const float* d_ln_w, float eps, float* d_g_pre,
+                                        float* d_g_acc, float* d_g_ln_w, float* d_g_ln_b, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(g != nullptr, "ghf_mp_epilogue_backward: graph is NULL");
+  const int d = g->hidden_dim;
+  GHF_REQUIRE(d <= 32 * kBwdMaxV, "ghf_mp_epilogue_backward: hidden_dim %d > %d", d, 32 * kBwdMaxV);
+  GHF_REQUIRE(d_g_out && d_upd && d_h && d_ln_w && d_g_pre && d_g_acc && d_g_ln_w && d_g_ln_b,
+              "ghf_mp_epilogue_backward: NULL argument");
+  GHF_CUDA(cudaMemsetAsync(d_g_ln_w, 0, d * sizeof(float), stream));
+  GHF_CUDA(cudaMemsetAsync(d_g_ln_b, 0, d * sizeof(float), stream));
+  if (g->num_local == 0) return 0;
+  const int64_t want = cdiv(g->num_local, 8 * 4);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  mp_epilogue_bwd_kernel<<<(unsigned)(want < cap ? want : cap), 256, 2 * d * sizeof(float), stream>>>(
+      d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local, d, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ghf_mp_weight_grad(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                                  const float* d_g_acc, int precision, float* d_gW_msg, float* d_gW_self,
+                                  float* d_gbias, void* d_workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(g != nullptr, "ghf_mp_weight_grad: graph is NULL");
+  GHF_REQUIRE(d_h && d_g_acc && d_gW_msg && d_gW_self && d_gbias, "ghf_mp_weight_grad: NULL argument");
+  const int d = g->hidden_dim;
+  const size_t wbytes = (size_t)g->num_rel * d * d * sizeof(float);
+  GHF_CUDA(cudaMemsetAsync(d_gW_msg, 0, wbytes, stream));
+  GHF_CUDA(cudaMemsetAsync(d_gW_self, 0, wbytes, stream));
+  GHF_CUDA(cudaMemsetAsync(d_gbias, 0, (size_t)g->num_rel * d * sizeof(float), stream));
+  if (g->num_units == 0) return 0;
+  (void)d_h16; (void)d_h16_scale; (void)precision; (void)d_workspace;
+  const dim3 grid((unsigned)g->num_units, (unsigned)cdiv(2 * d, kWgTM), (unsigned)cdiv(d, kWgTN));
+  GHF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "ghf_mp_weight_grad: hidden_dim %d too large", d);
+  mp_wgrad_kernel<<<grid, 256, 0, stream>>>(g->unit_start, g->unit_count, g->unit_rel, g->src_sorted, g->dst_sorted,
+                                            d_h, d_g_acc, g->dst_lo, d, d_gW_msg, d_gW_self, d_gbias);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}

@@ -143,6 +143,62 @@ __global__ void text_encode_kernel(const uint8_t* __restrict__ data, const int64
   }
 }
 
+// Backward of text_encode_kernel: one CTA per string.  out = tanh(pooled Wp^T + bp), pooled = mean of the code
+// points' embedding rows; the three parameter gradients are accumulated with atomics (U strings, a few thousand
+// addresses - this stage is microseconds next to the layers).
+__global__ void text_encode_bwd_kernel(const uint8_t* __restrict__ data, const int64_t* __restrict__ off,
+                                       const int64_t* __restrict__ index, const float* __restrict__ emb, int C,
+                                       const float* __restrict__ Wp, int T, const float* __restrict__ out,
+                                       const float* __restrict__ g_out, float* __restrict__ g_emb,
+                                       float* __restrict__ g_Wp, float* __restrict__ g_bp) {
+  extern __shared__ float sh[];  // pooled[C] | gmean[C] | gpre[T]
+  float* pooled = sh;
+  float* gmean = sh + C;
+  float* gpre = sh + 2 * C;
+  __shared__ int s_len;
+  const int64_t u = blockIdx.x;
+  const int64_t str = index ? index[u] : u;
+  const int64_t s0 = off[str], s1 = off[str + 1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sum = 0.f;
+    int len = 0;
+    for (int64_t i = s0; i < s1; ++i) {
+      const uint32_t b = data[i];
+      if ((b & 0xC0u) == 0x80u) continue;
+      sum += emb[(b < 128u ? b : 127u) * C + c];
+      ++len;
+    }
+    if (len == 0) { sum = emb[c]; len = 1; }
+    pooled[c] = sum / (float)len;
+    if (c == 0) s_len = len;
+  }
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float y = out[u * T + t];
+    const float gp = g_out[u * T + t] * (1.f - y * y);
+    gpre[t] = gp;
+    atomicAdd(g_bp + t, gp);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < T * C; idx += blockDim.x)
+    atomicAdd(g_Wp + idx, gpre[idx / C] * pooled[idx % C]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float gm = 0.f;
+    for (int t = 0; t < T; ++t) gm = fmaf(gpre[t], Wp[(int64_t)t * C + c], gm);
+    gmean[c] = gm / (float)s_len;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int seen = 0;
+    for (int64_t i = s0; i < s1; ++i) {
+      const uint32_t b = data[i];
+      if ((b & 0xC0u) == 0x80u) continue;
+      atomicAdd(g_emb + (b < 128u ? b : 127u) * C + c, gmean[c]);
+      ++seen;
+    }
+    if (seen == 0) atomicAdd(g_emb + c, gmean[c]);  // "" -> [0]
+  }
+}
+
 }  // namespace
 }  // namespace ghf
 
@@ -203,6 +259,23 @@ extern "C" int ghf_text_encode(const uint8_t* d_utf8, const int64_t* d_offsets, 
   if (U == 0) return 0;
   text_encode_kernel<<<(unsigned)U, 128, C * sizeof(float), stream>>>(d_utf8, d_offsets, d_string_index, d_emb, C,
                                                                      d_Wp, d_bp, T, d_out);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ghf_text_encode_backward(const uint8_t* d_utf8, const int64_t* d_offsets, const int64_t* d_string_index,
+                                        int64_t U, const float* d_emb, int C, const float* d_Wp, int T,
+                                        const float* d_out, const float* d_g_out, float* d_g_emb, float* d_g_Wp,
+                                        float* d_g_bp, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(C > 0 && T > 0 && U >= 0, "ghf_text_encode_backward: bad dims U=%lld C=%d T=%d", (long long)U, C, T);
+  GHF_REQUIRE(d_g_emb && d_g_Wp && d_g_bp, "ghf_text_encode_backward: NULL gradient buffer");
+  GHF_CUDA(cudaMemsetAsync(d_g_emb, 0, (size_t)128 * C * sizeof(float), stream));
+  GHF_CUDA(cudaMemsetAsync(d_g_Wp, 0, (size_t)T * C * sizeof(float), stream));
+  GHF_CUDA(cudaMemsetAsync(d_g_bp, 0, (size_t)T * sizeof(float), stream));
+  if (U == 0) return 0;
+  text_encode_bwd_kernel<<<(unsigned)U, 128, (2 * C + T) * sizeof(float), stream>>>(
+      d_utf8, d_offsets, d_string_index, d_emb, C, d_Wp, T, d_out, d_g_out, d_g_emb, d_g_Wp, d_g_bp);
   GHF_LAUNCH_CHECK();
   return 0;
 }

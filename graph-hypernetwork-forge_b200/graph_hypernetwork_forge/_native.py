@@ -17,7 +17,7 @@ PREC_FP32 = 0
 PREC_TF32 = 1
 PREC_F16 = 2
 _PREC = {"fp32": PREC_FP32, "tf32": PREC_TF32, "f16": PREC_F16}
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _LIB_PATH = os.environ.get("GHF_LIB") or os.path.join(
     os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")
@@ -62,6 +62,10 @@ def lib():
         "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
         "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
+        "ghf_mp_contract": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P]),
+        "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P]),
+        "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, c_int, P, P, P, P, P]),
+        "ghf_text_encode_backward": (c_int, [P, P, P, c_int64, P, c_int, P, c_int, P, P, P, P, P, P]),
         "ghf_absmax": (c_int, [P, c_int64, P, P]),
         "ghf_convert_f16": (c_int, [P, c_int64, P, P, c_int, P]),
         "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
@@ -86,7 +90,8 @@ EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
     "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
+    "ghf_text_encode_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -252,6 +257,20 @@ def text_encode(utf8, offsets, index, num, char_emb, proj_w, proj_b) -> torch.Te
     return out
 
 
+def text_encode_backward(utf8, offsets, index, num, char_emb, proj_w, out, g_out):
+    """Parameter gradients of `text_encode` -> (g_char_emb [128,C], g_proj_w [T,C], g_proj_b [T])."""
+    dev = utf8.device
+    char_emb, proj_w, out, g_out = _f32(char_emb), _f32(proj_w), _f32(out), _f32(g_out)
+    C, T = char_emb.shape[1], proj_w.shape[0]
+    g_emb, g_w = torch.empty_like(char_emb), torch.empty_like(proj_w)
+    g_b = torch.empty(T, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().ghf_text_encode_backward(_ptr(utf8), _ptr(offsets), _ptr(index), num, _ptr(char_emb), C,
+                                              _ptr(proj_w), T, _ptr(out), _ptr(g_out), _ptr(g_emb), _ptr(g_w),
+                                              _ptr(g_b), _stream(dev)), "ghf_text_encode_backward")
+    return g_emb, g_w, g_b
+
+
 class Graph:
     """Owner of a ghf_graph handle (in-degree, dst-CSR, relation-grouped edge order)."""
 
@@ -348,6 +367,65 @@ class Graph:
                                           _ptr(upd), _ptr(ws), _stream(dev)), "ghf_mp_layer_f16")
         return out, upd
 
+    # ---- gradients -------------------------------------------------------------------
+    def reversed(self) -> "Graph":
+        """The graph of the reversed edge list (same relations), built on first use: the contraction over it
+        carries gradients from destinations back to sources."""
+        rev = getattr(self, "_reversed", None)
+        if rev is None:
+            ei, ids, rel = self._inputs
+            if ids is not None or self.dst_lo != 0 or self.dst_hi != self.num_nodes:
+                raise RuntimeError("gradients need a full-range graph (one GPU)")
+            rev = Graph(ei.flip(0).contiguous(), rel, self.num_nodes, self.num_rel, self.hidden_dim)
+            self._reversed = rev
+        return rev
+
+    def contract(self, x, W_msg, W_self, bias, precision: int, x16=None) -> torch.Tensor:
+        """Raw per-destination sums of x_u W_msg[r] + x_v W_self[r] + bias[r] -> [local nodes, d]."""
+        dev, d = self.device, self.hidden_dim
+        x, W_msg, W_self, bias = _f32(x), _f32(W_msg), _f32(W_self), _f32(bias)
+        if x.shape != (self.num_nodes, d):
+            raise RuntimeError(f"x must be [{self.num_nodes},{d}], got {tuple(x.shape)}")
+        if W_msg.shape != (self.num_rel, d, d) or W_self.shape != (self.num_rel, d, d) or \
+                bias.shape != (self.num_rel, d):
+            raise RuntimeError("relation weights must be [R,d,d], [R,d,d], [R,d]")
+        acc = torch.empty((self.num_local, d), dtype=torch.float32, device=dev)
+        ws = self.workspace(precision)
+        with torch.cuda.device(dev):
+            _check(lib().ghf_mp_contract(self._h, _ptr(x), _ptr(x16.data) if x16 else None,
+                                         _ptr(x16.scale) if x16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
+                                         precision, _ptr(acc), _ptr(ws), _stream(dev)), "ghf_mp_contract")
+        return acc
+
+    def epilogue_backward(self, g_out, upd, h, ln_w, eps: float):
+        """-> (g_pre, g_acc, g_ln_w, g_ln_b); see ghf_mp_epilogue_backward."""
+        dev, d = self.device, self.hidden_dim
+        g_out, upd, h, ln_w = _f32(g_out), _f32(upd), _f32(h), _f32(ln_w)
+        if g_out.shape != (self.num_local, d) or upd.shape != g_out.shape or h.shape != (self.num_nodes, d):
+            raise RuntimeError("epilogue_backward: shape mismatch")
+        g_pre, g_acc = torch.empty_like(g_out), torch.empty_like(g_out)
+        g_w, g_b = torch.empty_like(ln_w), torch.empty_like(ln_w)
+        with torch.cuda.device(dev):
+            _check(lib().ghf_mp_epilogue_backward(self._h, _ptr(g_out), _ptr(upd), _ptr(h), _ptr(ln_w), float(eps),
+                                                  _ptr(g_pre), _ptr(g_acc), _ptr(g_w), _ptr(g_b), _stream(dev)),
+                   "ghf_mp_epilogue_backward")
+        return g_pre, g_acc, g_w, g_b
+
+    def weight_grad(self, h, g_acc, precision: int, h16=None):
+        """-> (g_W_msg [R,d,d], g_W_self [R,d,d], g_bias [R,d]); see ghf_mp_weight_grad."""
+        dev, d = self.device, self.hidden_dim
+        h, g_acc = _f32(h), _f32(g_acc)
+        if h.shape != (self.num_nodes, d) or g_acc.shape != (self.num_local, d):
+            raise RuntimeError("weight_grad: shape mismatch")
+        gm = torch.empty((self.num_rel, d, d), dtype=torch.float32, device=dev)
+        gs = torch.empty_like(gm)
+        gb = torch.empty((self.num_rel, d), dtype=torch.float32, device=dev)
+        ws = self.workspace(precision)
+        with torch.cuda.device(dev):
+            _check(lib().ghf_mp_weight_grad(self._h, _ptr(h), _ptr(h16.data) if h16 else None,
+                                            _ptr(h16.scale) if h16 else None, _ptr(g_acc), precision, _ptr(gm),
+                                            _ptr(gs), _ptr(gb), _ptr(ws), _stream(dev)), "ghf_mp_weight_grad")
+        return gm, gs, gb
 
 def forward_host(desc: ModelDesc, params, node_features, edge_index, utf8, offsets, out, device):
     """ghf_hypergnn_forward_host: HOST numpy/pinned buffers in, host buffer out (copies inside)."""

@@ -11,7 +11,8 @@ work happens.  `HyperGNN.forward` is
 
 with every stage a hand-written sm_100a kernel behind the C ABI in
 `include/ghf_b200.h`.  Tensors must live on a CUDA device; there is no CPU or
-eager-PyTorch fallback, and the path is forward-only (no autograd).
+eager-PyTorch fallback.  With gradients enabled the same kernels run under
+`autograd.py` and `loss.backward()` reaches every parameter.
 """
 from __future__ import annotations
 
@@ -22,7 +23,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import _native, _text
+from .. import _native, _text, autograd
 from .weight_generator import WeightGenerator
 
 
@@ -95,11 +96,16 @@ class TextEncoder(nn.Module):
         codes = [min(ord(ch), self.ASCII_VOCAB - 1) for ch in text] or [0]
         return torch.tensor(codes, dtype=torch.long, device=device)
 
+    def _encode(self, utf8, offsets, index, num) -> torch.Tensor:
+        params = (self.char_emb.weight, self.proj[0].weight, self.proj[0].bias)
+        if autograd.wants_grad(*params):
+            return autograd.TextEncodeFn.apply(*params, utf8, offsets, index, num)
+        return _native.text_encode(utf8, offsets, index, num, *params)
+
     def encode_packed(self, packed: PackedTexts, distinct_only: bool = True) -> torch.Tensor:
         index = packed.first if distinct_only else None
         num = packed.num_unique if distinct_only else packed.offsets.numel() - 1
-        return _native.text_encode(packed.utf8, packed.offsets, index, num, self.char_emb.weight,
-                                   self.proj[0].weight, self.proj[0].bias)
+        return self._encode(packed.utf8, packed.offsets, index, num)
 
     def forward(self, texts: List[str], device: torch.device) -> torch.Tensor:
         """``[len(texts), text_dim]`` - one row per string, in list order (no dedup)."""
@@ -110,8 +116,7 @@ class TextEncoder(nn.Module):
         device = own
         data, offsets = _text.pack_utf8(texts)
         utf8 = _to_device(data, device) if data.size else torch.zeros(1, dtype=torch.uint8, device=device)
-        return _native.text_encode(utf8, _to_device(offsets, device), None, len(texts), self.char_emb.weight,
-                                   self.proj[0].weight, self.proj[0].bias)
+        return self._encode(utf8, _to_device(offsets, device), None, len(texts))
 
     def encode_one(self, text: str, device: torch.device) -> torch.Tensor:
         return self.forward([text], device)[0]
@@ -231,6 +236,8 @@ class HyperGNN(nn.Module):
         if graph.dst_lo != 0 or graph.dst_hi != graph.num_nodes:
             raise RuntimeError("forward_prepared needs a full-range graph; see distributed.ShardedHyperGNN")
         prec = self._precision_code()
+        if autograd.wants_grad(node_features, *self.parameters()):
+            return self._forward_autograd(node_features, prepared, prec, taps)
         with torch.no_grad():
             h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
             if prec == _native.PREC_F16 and node_features.size(0) * self.hidden_dim % 8 == 0:
@@ -255,6 +262,24 @@ class HyperGNN(nn.Module):
                 if taps is not None:
                     taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
                     taps[f"upd.{l}"], taps[f"h.{l}"] = upd, h
+        return h
+
+    def _forward_autograd(self, node_features, prepared: PreparedGraph, prec: int, taps) -> torch.Tensor:
+        """The same forward with the autograd graph recorded (`autograd.py`): every stage is the forward kernel
+        wrapped in a Function whose backward is the gradient kernel, so `loss.backward()` and an optimiser step
+        work as they do on the reference (tests/test_hypergnn.py:183-226, demo.py:79-101)."""
+        graph, packed = prepared.graph, prepared.packed
+        h = autograd.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True)
+        text_embs = self.text_encoder.encode_packed(packed)
+        if taps is not None:
+            taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
+        for l in range(self.num_layers):
+            w = self._generate(l, text_embs, packed.num_unique)
+            ln = self.layer_norms[l]
+            h = autograd.mp_layer(graph, h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec)
+            if taps is not None:
+                taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
+                taps[f"h.{l}"] = h
         return h
 
     def capture_prepared(self, node_features: torch.Tensor, prepared: PreparedGraph):

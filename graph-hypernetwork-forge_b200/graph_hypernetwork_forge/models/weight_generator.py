@@ -4,8 +4,8 @@ Drop-in for the reference class of the same name
 (`graph_hypernetwork_forge/models/weight_generator.py:33-143`): same constructor,
 attributes, parameter names (`generators.{W_msg,W_self,bias}.<i>.{weight,bias}`,
 `log_scales.{W_msg,W_self,bias}`), initialisation stream and return convention.
-The forward pass runs on the B200 through `ghf_linear` (fp32 tiles with the
-ReLU and the `exp(log_scale)` factor fused into the store); there is no CPU path.
+The forward pass runs on the B200 through `ghf_linear` (ReLU and the `exp(log_scale)`
+factor fused into the store); there is no CPU path.  Gradients: `autograd.LinearFn`.
 """
 from __future__ import annotations
 
@@ -15,7 +15,7 @@ from typing import Dict
 import torch
 import torch.nn as nn
 
-from .. import _native
+from .. import _native, autograd
 
 _KINDS = ("W_msg", "W_self", "bias")
 
@@ -59,15 +59,18 @@ class WeightGenerator(nn.Module):
 
     # ------------------------------------------------------------------
     def _run_mlp(self, kind: str, x: torch.Tensor) -> torch.Tensor:
-        """flat = MLP_kind(x) * exp(log_scale_kind), every Linear one fused kernel."""
+        """flat = MLP_kind(x) * exp(log_scale_kind), every Linear (+ReLU, + the scale) one fused kernel; with
+        gradients enabled the same kernels run under `autograd.LinearFn`."""
         mods = list(self.generators[kind])
         linears = [i for i, m in enumerate(mods) if isinstance(m, nn.Linear)]
-        if self.training and self._dropout > 0.0 and len(linears) > 1:
-            raise NotImplementedError("dropout in training mode is outside the forward-only B200 path")
+        ls = self.log_scales[kind]
+        grad = autograd.wants_grad(x, ls, *self.generators[kind].parameters())
+        run = autograd.linear if grad else _native.linear
         for pos, i in enumerate(linears):
             last = pos == len(linears) - 1
-            x = _native.linear(x, mods[i].weight, mods[i].bias, relu=not last,
-                               log_scale=self.log_scales[kind] if last else None)
+            x = run(x, mods[i].weight, mods[i].bias, relu=not last, log_scale=ls if last else None)
+            if not last and self.training and self._dropout > 0.0:
+                x = nn.functional.dropout(x, self._dropout)       # the Dropout module after each hidden ReLU
         return x
 
     def forward(self, text_emb: torch.Tensor) -> Dict[str, torch.Tensor]:

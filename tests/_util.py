@@ -68,3 +68,34 @@ def assert_rel_to_max(got, want, rel, what):
     scale = max(float(np.abs(want).max()), 1e-30)
     err = float(np.abs(got - want).max())
     assert err <= rel * scale, f"{what}: max|err|={err:.3e} > {rel:g} * max|ref|={scale:.3e}"
+
+
+# ---- gradient fixtures (tests/golden/make_grad_golden.py) ----
+GRAD_CASES = ["grad_toy", "grad_edge_cases_d24", "grad_synth_d64", "grad_synth_d128"]
+
+
+def load_grad_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    case = {"name": name, "ctor": ast.literal_eval(str(z["ctor"])), "seed": int(z["seed"]),
+            "log_scale": float(z["log_scale"]), "params": None, "param_checksum": z["param_checksum"],
+            "node_features": z["node_features"], "edge_index": z["edge_index"],
+            "edge_texts": [str(t) for t in z["edge_texts"]], "loss_weight": z["loss_weight"],
+            "loss": float(z["loss"]), "out": z["out"],
+            "grads": {k[5:]: z[k] for k in z.files if k.startswith("grad/")},
+            "grad_samples": {k[11:]: (z["gradsample_idx/" + k[11:]], z[k], float(z["gradnorm/" + k[11:]]))
+                             for k in z.files if k.startswith("gradsample/")}}
+    return case
+
+
+def check_grads(case, grads, rel, what=""):
+    """`grads`: name -> array-like (full gradient tensors) against the reference's, each relative to the largest
+    reference entry of that tensor (tensors stored as a sample: the sampled entries and the L2 norm)."""
+    names = set(case["grads"]) | set(case["grad_samples"])
+    missing = names - set(grads)
+    assert not missing, f"{what}: no gradient for {sorted(missing)}"
+    for k, want in case["grads"].items():
+        assert_rel_to_max(np.asarray(grads[k]).reshape(want.shape), want, rel, f"{what} grad {k}")
+    for k, (idx, want, norm) in case["grad_samples"].items():
+        got = np.asarray(grads[k], dtype=np.float64).reshape(-1)
+        assert_rel_to_max(got[idx], want, rel, f"{what} grad {k} (sample)")
+        assert abs(float(np.linalg.norm(got)) - norm) <= 2 * rel * norm, f"{what} grad {k}: norm"

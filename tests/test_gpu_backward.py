@@ -1,0 +1,179 @@
+"""Gradients of the B200 path (`-m gpu`): `loss.backward()` through `HyperGNN.forward` against
+  * the gradients of the UNMODIFIED reference (tests/golden/grad_*.npz, made by tests/golden/make_grad_golden.py), and
+  * the float64 autograd of the differentiable oracle (oracle/hypergnn_torch.py, itself pinned to those fixtures)
+    on graphs too large for a fixture,
+plus the reference's own five training tests (tests/test_hypergnn.py:183-226, tests/test_weight_generator.py:86-106).
+
+Tolerances, each relative to the largest entry of the reference gradient tensor: fp32 path 2e-4 (float32 atomics
+and a different summation order than ATen); tensor-core paths (tf32, f16: 11-bit operands in two chained
+contractions per layer) 2e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import GRAD_CASES, build_model, check_grads, load_grad_case, assert_rel_to_max
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+FP32_GRAD_REL, TC_GRAD_REL = 2e-4, 2e-2
+
+
+def run_case(gc, precision):
+    model = build_model(gc, DEV, precision).train()
+    x = torch.tensor(gc["node_features"], device=DEV, requires_grad=True)
+    out = model(x, torch.tensor(gc["edge_index"], device=DEV), gc["edge_texts"])
+    loss = (out * torch.tensor(gc["loss_weight"], device=DEV)).sum()
+    loss.backward()
+    grads = {k: p.grad.cpu().numpy() for k, p in model.named_parameters()}
+    grads["node_features"] = x.grad.cpu().numpy()
+    return out.detach().cpu().numpy(), float(loss.detach()), grads
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_fp32_gradients_match_reference(name):
+    gc = load_grad_case(name)
+    out, loss, grads = run_case(gc, "fp32")
+    assert np.abs(out - gc["out"]).max() <= 5e-5
+    check_grads(gc, grads, FP32_GRAD_REL, f"{name} fp32")
+
+
+@pytest.mark.parametrize("name,precision", [("grad_toy", "tf32"), ("grad_synth_d64", "tf32"),
+                                            ("grad_synth_d128", "tf32"), ("grad_synth_d128", "f16")])
+def test_tensor_core_gradients_match_reference(name, precision):
+    gc = load_grad_case(name)
+    out, loss, grads = run_case(gc, precision)
+    check_grads(gc, grads, TC_GRAD_REL, f"{name} {precision}")
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_GRAD_REL), ("f16", TC_GRAD_REL)])
+def test_medium_graph_against_float64_oracle(precision, tol):
+    """20k nodes, 200k edges, 37 relations, hidden 128, 2 layers: many units per relation and several edges per
+    destination, against float64 autograd of the torch oracle on the same device."""
+    from graph_hypernetwork_forge import HyperGNN
+    from oracle import hypergnn_torch as OT
+    N, E, R, d, L, T, F = 20_000, 200_000, 37, 128, 2, 64, 48
+    g = torch.Generator(device=DEV).manual_seed(5)
+    ei = torch.randint(0, N, (2, E), generator=g, device=DEV)
+    rel = torch.randint(0, R, (E,), generator=g, device=DEV)
+    x = torch.randn(N, F, generator=g, device=DEV)
+    loss_w = torch.randn(N, d, generator=g, device=DEV)
+    names = [f"relation_{r:05d}" for r in range(R)]
+    torch.manual_seed(5)
+    model = HyperGNN(T, F, d, L, precision=precision)
+    with torch.no_grad():
+        for gen in model.weight_generators:
+            for p in gen.log_scales.values():
+                p.fill_(-1.5)
+    model = model.to(DEV).train()
+    prepared = model.prepare_ids(ei, rel, names, N)
+    xg = x.clone().requires_grad_(True)
+    out = model.forward_prepared(xg, prepared)
+    (out * loss_w).sum().backward()
+
+    params = {k: v.detach().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    x64 = x.double().requires_grad_(True)
+    ref = OT.hypergnn_forward(params, x64, ei, rel, names, d, L)
+    (ref * loss_w.double()).sum().backward()
+    assert_rel_to_max(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), 5e-3 if precision == "f16" else 1e-4, "out")
+    assert_rel_to_max(xg.grad.cpu().numpy(), x64.grad.cpu().numpy(), tol, "grad node_features")
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert_rel_to_max(p.grad.cpu().numpy(), params[k].grad.cpu().numpy(), tol, f"grad {k}")
+
+
+# ---- the reference's training tests, on CUDA tensors (tests/test_hypergnn.py:183-226) ----
+@pytest.fixture
+def toy_kg():
+    from graph_hypernetwork_forge import ToyKnowledgeGraph
+    kg = ToyKnowledgeGraph(feat_dim=16)
+    kg.node_features, kg.edge_index = kg.node_features.to(DEV), kg.edge_index.to(DEV)
+    return kg
+
+
+@pytest.fixture
+def small_model():
+    from graph_hypernetwork_forge import HyperGNN
+    return HyperGNN(text_dim=32, node_feat_dim=16, hidden_dim=16, num_layers=2, dropout=0.0).to(DEV)
+
+
+class TestTraining:
+    def test_backward_no_error(self, small_model, toy_kg):
+        out = small_model(toy_kg.node_features, toy_kg.edge_index, toy_kg.edge_texts)
+        out.sum().backward()
+
+    def test_parameters_update(self, small_model, toy_kg):
+        opt = torch.optim.SGD(small_model.parameters(), lr=0.1)
+        before = {n: p.clone().detach() for n, p in small_model.named_parameters()}
+        opt.zero_grad()
+        out = small_model(toy_kg.node_features, toy_kg.edge_index, toy_kg.edge_texts)
+        out.sum().backward()
+        opt.step()
+        changed = sum(not torch.allclose(before[n], p.detach()) for n, p in small_model.named_parameters())
+        assert changed > 0, "No parameters changed after an optimiser step"
+
+    def test_loss_decreases(self, toy_kg):
+        from graph_hypernetwork_forge import HyperGNN
+        model = HyperGNN(text_dim=32, node_feat_dim=16, hidden_dim=16, num_layers=2).to(DEV)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+        losses = []
+        src, dst = toy_kg.edge_index
+        for _ in range(15):
+            opt.zero_grad()
+            embs = model(toy_kg.node_features, toy_kg.edge_index, toy_kg.edge_texts)
+            pos = model.score_triple(embs[src], embs[dst])
+            perm = torch.randperm(dst.size(0), device=DEV)
+            neg = model.score_triple(embs[src], embs[dst[perm]])
+            loss = torch.clamp(1.0 - pos + neg, min=0.0).mean()
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        assert losses[-1] <= losses[0] * 2, "Loss does not appear to decrease at all"
+
+    def test_every_parameter_gets_a_gradient(self, small_model, toy_kg):
+        out = small_model(toy_kg.node_features, toy_kg.edge_index, toy_kg.edge_texts)
+        (out * torch.randn_like(out)).sum().backward()
+        for n, p in small_model.named_parameters():
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+            assert float(p.grad.abs().max()) > 0, f"{n}: gradient is identically zero"
+
+    def test_no_grad_forward_is_unchanged(self, small_model, toy_kg):
+        out = small_model(toy_kg.node_features, toy_kg.edge_index, toy_kg.edge_texts)
+        with torch.no_grad():
+            out2 = small_model(toy_kg.node_features, toy_kg.edge_index, toy_kg.edge_texts)
+        assert out.requires_grad and not out2.requires_grad
+        assert torch.allclose(out, out2, atol=1e-5)
+
+
+class TestWeightGeneratorGradients:
+    """tests/test_weight_generator.py:86-106."""
+
+    @pytest.fixture
+    def weight_gen(self):
+        from graph_hypernetwork_forge import WeightGenerator
+        return WeightGenerator(text_dim=32, d_in=16, d_out=16, hidden_dim=64).to(DEV)
+
+    def test_gradients_flow(self, weight_gen):
+        emb = torch.randn(32, device=DEV, requires_grad=True)
+        out = weight_gen(emb)
+        (out["W_msg"].sum() + out["W_self"].sum() + out["bias"].sum()).backward()
+        assert emb.grad is not None and emb.grad.shape == emb.shape
+
+    def test_scales_appear_in_optimizer(self, weight_gen):
+        opt = torch.optim.Adam(weight_gen.parameters(), lr=1e-3)
+        out = weight_gen(torch.randn(32, device=DEV))
+        sum(v.sum() for v in out.values()).backward()
+        opt.step()
+
+    def test_generator_gradients_match_torch(self, weight_gen):
+        """LinearFn against torch's own autograd on the same Sequential stacks."""
+        x = torch.randn(7, 32, device=DEV)
+        out = weight_gen(x)
+        wts = [torch.randn_like(v) for v in out.values()]
+        sum((v * w).sum() for v, w in zip(out.values(), wts)).backward()
+        got = {n: p.grad.clone() for n, p in weight_gen.named_parameters()}
+        weight_gen.zero_grad()
+        ref = [weight_gen.generators[k](x).view(out[k].shape) * weight_gen.log_scales[k].exp() for k in out]
+        sum((v * w).sum() for v, w in zip(ref, wts)).backward()
+        for n, p in weight_gen.named_parameters():
+            assert_rel_to_max(got[n].cpu().numpy(), p.grad.cpu().numpy(), 1e-4, f"grad {n}")
