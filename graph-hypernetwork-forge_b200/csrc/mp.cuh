@@ -42,4 +42,10 @@ int64_t mp_f16_sync_bytes(const ghf_graph* g);
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
                   const void* pack_scratch, int* sync_words, cudaStream_t stream);
 
+// gradients of the generated relation tensors on tcgen05 (mp_wgrad_f16.cu, hidden_dim 128): g_W_msg[r] / g_W_self[r] /
+// g_bias[r] += sums over the edges of r (buffers zero at entry); h16 / g16 are fp16 shadows with their scale words.
+int mp_wgrad_f16_launch(const ghf_graph* g, const void* h16, const float* h_scale, const void* g16,
+                        const float* g_scale, float* gW_msg, float* gW_self, float* gbias, int* unit_counter,
+                        cudaStream_t stream);
+
 }  // namespace ghf

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "ghf_b200.h"
 #include "graph.cuh"
+#include "mp.cuh"
 
 namespace ghf {
 namespace {
@@ -224,7 +225,30 @@ extern "C" int ghf_mp_weight_grad(const ghf_graph* g, const float* d_h, const vo
   GHF_CUDA(cudaMemsetAsync(d_gW_self, 0, wbytes, stream));
   GHF_CUDA(cudaMemsetAsync(d_gbias, 0, (size_t)g->num_rel * d * sizeof(float), stream));
   if (g->num_units == 0) return 0;
-  (void)d_h16; (void)d_h16_scale; (void)precision; (void)d_workspace;
+  if (precision == GHF_PREC_F16 && mp_f16_supported(d)) {
+    // tensor-core path (mp_wgrad_f16.cu).  Workspace regions as in ghf_mp_layer: [sync words][accumulator rows]
+    // [weight images][scale words][fp16 h]; the accumulator region holds the fp16 shadow of g_acc here.
+    GHF_REQUIRE(d_workspace != nullptr, "ghf_mp_weight_grad: workspace is NULL");
+    GHF_REQUIRE(d_h16 == nullptr || d_h16_scale != nullptr, "ghf_mp_weight_grad: d_h16 needs d_h16_scale");
+    int* counter = reinterpret_cast<int*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
+    char* acc_ws = reinterpret_cast<char*>(counter) + mp_f16_sync_bytes(g);
+    char* pack = acc_ws + align_up(g->num_local * (int64_t)d * 4, 256);
+    float* sc = reinterpret_cast<float*>(pack + mp_f16_pack_bytes(g->num_rel));
+    const void* h16 = d_h16;
+    const float* h_scale = d_h16_scale;
+    if (h16 == nullptr) {
+      void* conv = reinterpret_cast<char*>(sc) + 256;
+      if (int rc = mp_f16_absmax(d_h, g->num_nodes * (int64_t)d, sc, stream)) return rc;
+      if (int rc = mp_f16_convert(d_h, g->num_nodes * (int64_t)d, conv, sc, /*rescue=*/false, stream)) return rc;
+      h16 = conv;
+      h_scale = sc;
+    }
+    float* g_scale = sc + 16;
+    if (int rc = mp_f16_absmax(d_g_acc, g->num_local * (int64_t)d, g_scale, stream)) return rc;
+    if (int rc = mp_f16_convert(d_g_acc, g->num_local * (int64_t)d, acc_ws, g_scale, /*rescue=*/false, stream))
+      return rc;
+    return mp_wgrad_f16_launch(g, h16, h_scale, acc_ws, g_scale, d_gW_msg, d_gW_self, d_gbias, counter, stream);
+  }
   const dim3 grid((unsigned)g->num_units, (unsigned)cdiv(2 * d, kWgTM), (unsigned)cdiv(d, kWgTN));
   GHF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "ghf_mp_weight_grad: hidden_dim %d too large", d);
   mp_wgrad_kernel<<<grid, 256, 0, stream>>>(g->unit_start, g->unit_count, g->unit_rel, g->src_sorted, g->dst_sorted,
