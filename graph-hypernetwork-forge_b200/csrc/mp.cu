@@ -361,7 +361,8 @@ static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_
 // `acc_ext` (optional) receives the sums; otherwise they stay in the workspace for the epilogue.  -> *acc_used.
 static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
                            const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
-                           float* acc_ext, void* d_workspace, cudaStream_t stream, float** acc_used, ProfRec* rec) {
+                           float* acc_ext, bool accumulate, void* d_workspace, cudaStream_t stream, float** acc_used,
+                           ProfRec* rec) {
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
@@ -379,7 +380,7 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
     const size_t head = reinterpret_cast<char*>(acc_ws) - reinterpret_cast<char*>(counter);
     if (acc_ext) {
       GHF_CUDA(cudaMemsetAsync(counter, 0, head, stream));
-      GHF_CUDA(cudaMemsetAsync(acc_ext, 0, nl * (size_t)d * 4, stream));
+      if (!accumulate) GHF_CUDA(cudaMemsetAsync(acc_ext, 0, nl * (size_t)d * 4, stream));
     } else {
       GHF_CUDA(cudaMemsetAsync(counter, 0, head + nl * (size_t)d * 4, stream));
     }
@@ -412,7 +413,7 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
       rc = ts ? mp_ts_launch(g, d_h, d_bias, acc, pack, counter, stream)
               : mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream);
     } else if (precision == GHF_PREC_F16) {
-      rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream);
+      rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream, accumulate);
     } else if (d <= 32) {
       rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
     } else if (d <= 64) {
@@ -452,7 +453,7 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
   float* acc = nullptr;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
-                               d_workspace, stream, &acc, prof ? &rec : nullptr))
+                               false, d_workspace, stream, &acc, prof ? &rec : nullptr))
     return rc;
   if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream))
     return rc;
@@ -465,7 +466,7 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
 
 extern "C" int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void* d_x16, const float* d_x16_scale,
                                const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
-                               float* d_acc, void* d_workspace, void* stream_) {
+                               float* d_acc, int accumulate, void* d_workspace, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_layer_args(g, d_workspace, precision, d_x16, d_x16_scale)) return rc;
   GHF_REQUIRE(d_acc != nullptr && reinterpret_cast<uintptr_t>(d_acc) % 256 == 0,
@@ -473,8 +474,8 @@ extern "C" int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void*
   g->stream = stream_;
   if (g->num_local == 0) return 0;
   float* acc = nullptr;
-  return run_contraction(g, d_x, d_x16, d_x16_scale, d_W_msg, d_W_self, d_bias, precision, d_acc, d_workspace,
-                         stream, &acc, nullptr);
+  return run_contraction(g, d_x, d_x16, d_x16_scale, d_W_msg, d_W_self, d_bias, precision, d_acc, accumulate != 0,
+                         d_workspace, stream, &acc, nullptr);
 }
 
 extern "C" int ghf_absmax(const float* d_x, int64_t elems, float* d_scale, void* stream_) {

@@ -37,10 +37,11 @@ int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, voi
 int mp_f16_absmax(const float* x, int64_t elems, float* scale, cudaStream_t stream);
 int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool rescue, cudaStream_t stream);
 // acc[dst_local, :] = sum over edges of [h16_src | h16_dst] @ [W_msg; W_self][rel] + bias[rel]; h16 is [N, 128] fp16.
-// The kernel clears acc itself (every local row, also those without in-edges).  sync_words: mp_f16_sync_bytes(g).
+// The kernel clears acc itself (every local row, also those without in-edges) unless `keep_acc` (then it adds to
+// what the rows hold).  sync_words: mp_f16_sync_bytes(g).
 int64_t mp_f16_sync_bytes(const ghf_graph* g);
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
-                  const void* pack_scratch, int* sync_words, cudaStream_t stream);
+                  const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc = false);
 
 // gradients of the generated relation tensors on tcgen05 (mp_wgrad_f16.cu, hidden_dim 128): g_W_msg[r] / g_W_self[r] /
 // g_bias[r] += sums over the edges of r (buffers zero at entry); h16 / g16 are fp16 shadows with their scale words.

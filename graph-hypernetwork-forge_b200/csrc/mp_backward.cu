@@ -15,6 +15,7 @@
 #include "ghf_b200.h"
 #include "graph.cuh"
 #include "mp.cuh"
+#include "mp_fuse.cuh"
 
 namespace ghf {
 namespace {
@@ -114,6 +115,109 @@ mp_epilogue_bwd_kernel(const float* __restrict__ g_out, const float* __restrict_
   }
 }
 
+// The same for hidden_dim 32 / 64 / 128: a lane owns D/32 CONSECUTIVE columns (one vector access per row and
+// operand), four rows in flight per warp; optionally max |g_acc| for the fp16 shadow the next kernels gather from.
+template <int D>
+__global__ void __launch_bounds__(256)
+mp_epilogue_bwd_vec_kernel(const float* __restrict__ g_out, const float* __restrict__ upd,
+                           const int32_t* __restrict__ indeg, const float* __restrict__ h, int64_t dst_lo,
+                           int64_t num_local, const float* __restrict__ ln_w, float eps, float* __restrict__ g_pre,
+                           float* __restrict__ g_acc, float* __restrict__ g_lnw, float* __restrict__ g_lnb,
+                           float* __restrict__ g_acc_scale) {
+  using namespace fuse;
+  constexpr int V = D / 32;
+  constexpr int kRows = 4;
+  __shared__ float red[2 * D];
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) red[c] = 0.f;
+  __syncthreads();
+  float lw[V], pw[V], pb[V];
+  vload_nc<V>(lw, ln_w + lane * V);
+#pragma unroll
+  for (int j = 0; j < V; ++j) pw[j] = pb[j] = 0.f;
+  float amax = 0.f;
+  const float inv_d = 1.f / (float)D;
+  for (int64_t r0 = w0; r0 < num_local; r0 += kRows * warps) {
+    float up[kRows][V], hv[kRows][V], gy[kRows][V];
+    int deg[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int64_t r = r0 + k * warps;
+      if (r < num_local) {
+        vload_nc<V>(up[k], upd + r * D + lane * V);
+        vload_nc<V>(hv[k], h + (dst_lo + r) * D + lane * V);
+        vload_nc<V>(gy[k], g_out + r * D + lane * V);
+        deg[k] = __ldg(indeg + r);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int64_t r = r0 + k * warps;
+      if (r >= num_local) break;
+      const float inv_cnt = 1.f / (float)max(deg[k], 1);
+      float x[V], sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        x[j] = fmaxf(up[k][j] + hv[k][j], 0.f);
+        sum += x[j];
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+      const float mean = sum * inv_d;
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) var += (x[j] - mean) * (x[j] - mean);
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+      const float rstd = rsqrtf(var * inv_d + eps);
+      float xh[V], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        xh[j] = (x[j] - mean) * rstd;
+        const float gh = gy[k][j] * lw[j];
+        s1 += gh;
+        s2 += gh * xh[j];
+        pw[j] += gy[k][j] * xh[j];
+        pb[j] += gy[k][j];
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, s);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, s);
+      }
+      s1 *= inv_d;
+      s2 *= inv_d;
+      float gp[V], ga[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float gx = rstd * (gy[k][j] * lw[j] - s1 - xh[j] * s2);
+        gp[j] = x[j] > 0.f ? gx : 0.f;
+        ga[j] = gp[j] * inv_cnt;
+        amax = fmaxf(amax, fabsf(ga[j]));
+      }
+      vstore<V>(g_pre + r * D + lane * V, gp);
+      vstore<V>(g_acc + r * D + lane * V, ga);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    atomicAdd(&red[lane * V + j], pw[j]);
+    atomicAdd(&red[D + lane * V + j], pb[j]);
+  }
+  if (g_acc_scale) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
+    if (lane == 0) atomic_max_nonneg(g_acc_scale + 1, amax);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(&g_lnw[c], red[c]);
+    atomicAdd(&g_lnb[c], red[D + c]);
+  }
+}
+
 // ---- weight gradients, CUDA cores (any hidden_dim): one CTA per (unit, 64-row tile of [W_msg ; W_self], 64-column
 // tile); the unit's edges are the contraction dimension, staged 32 at a time.
 constexpr int kWgTM = 64, kWgTN = 64, kWgTE = 32;
@@ -195,7 +299,8 @@ using namespace ghf;
 
 extern "C" int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out, const float* d_upd,
                                         const float* d_h, const float* d_ln_w, float eps, float* d_g_pre,
-                                        float* d_g_acc, float* d_g_ln_w, float* d_g_ln_b, void* stream_) {
+                                        float* d_g_acc, float* d_g_ln_w, float* d_g_ln_b, float* d_g_acc_scale,
+                                        void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(g != nullptr, "ghf_mp_epilogue_backward: graph is NULL");
   const int d = g->hidden_dim;
@@ -204,18 +309,35 @@ extern "C" int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out
               "ghf_mp_epilogue_backward: NULL argument");
   GHF_CUDA(cudaMemsetAsync(d_g_ln_w, 0, d * sizeof(float), stream));
   GHF_CUDA(cudaMemsetAsync(d_g_ln_b, 0, d * sizeof(float), stream));
+  if (d_g_acc_scale) GHF_CUDA(cudaMemsetAsync(d_g_acc_scale, 0, 2 * sizeof(float), stream));
   if (g->num_local == 0) return 0;
   const int64_t want = cdiv(g->num_local, 8 * 4);
   const int64_t cap = (int64_t)sm_count() * 8;
-  mp_epilogue_bwd_kernel<<<(unsigned)(want < cap ? want : cap), 256, 2 * d * sizeof(float), stream>>>(
-      d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local, d, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b);
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  const bool aligned = (reinterpret_cast<uintptr_t>(d_g_out) | reinterpret_cast<uintptr_t>(d_upd) |
+                        reinterpret_cast<uintptr_t>(d_h) | reinterpret_cast<uintptr_t>(d_ln_w) |
+                        reinterpret_cast<uintptr_t>(d_g_pre) | reinterpret_cast<uintptr_t>(d_g_acc)) % 16 == 0;
+#define GHF_BWD_VEC(D)                                                                                              \
+  mp_epilogue_bwd_vec_kernel<D><<<grid, 256, 0, stream>>>(d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local,   \
+                                                          d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b,        \
+                                                          d_g_acc_scale)
+  if (aligned && d == 128) GHF_BWD_VEC(128);
+  else if (aligned && d == 64) GHF_BWD_VEC(64);
+  else if (aligned && d == 32) GHF_BWD_VEC(32);
+  else {
+    GHF_REQUIRE(d_g_acc_scale == nullptr, "ghf_mp_epilogue_backward: max|g_acc| needs hidden_dim 32/64/128");
+    mp_epilogue_bwd_kernel<<<grid, 256, 2 * d * sizeof(float), stream>>>(
+        d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local, d, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b);
+  }
+#undef GHF_BWD_VEC
   GHF_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int ghf_mp_weight_grad(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
-                                  const float* d_g_acc, int precision, float* d_gW_msg, float* d_gW_self,
-                                  float* d_gbias, void* d_workspace, void* stream_) {
+                                  const float* d_g_acc, const void* d_g16, const float* d_g16_scale, int precision,
+                                  float* d_gW_msg, float* d_gW_self, float* d_gbias, void* d_workspace,
+                                  void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(g != nullptr, "ghf_mp_weight_grad: graph is NULL");
   GHF_REQUIRE(d_h && d_g_acc && d_gW_msg && d_gW_self && d_gbias, "ghf_mp_weight_grad: NULL argument");
@@ -243,11 +365,17 @@ extern "C" int ghf_mp_weight_grad(const ghf_graph* g, const float* d_h, const vo
       h16 = conv;
       h_scale = sc;
     }
-    float* g_scale = sc + 16;
-    if (int rc = mp_f16_absmax(d_g_acc, g->num_local * (int64_t)d, g_scale, stream)) return rc;
-    if (int rc = mp_f16_convert(d_g_acc, g->num_local * (int64_t)d, acc_ws, g_scale, /*rescue=*/false, stream))
-      return rc;
-    return mp_wgrad_f16_launch(g, h16, h_scale, acc_ws, g_scale, d_gW_msg, d_gW_self, d_gbias, counter, stream);
+    const void* g16 = d_g16;
+    const float* g_scale = d_g16_scale;
+    GHF_REQUIRE(g16 == nullptr || g_scale != nullptr, "ghf_mp_weight_grad: d_g16 needs d_g16_scale");
+    if (g16 == nullptr) {
+      float* gs = sc + 16;
+      if (int rc = mp_f16_absmax(d_g_acc, g->num_local * (int64_t)d, gs, stream)) return rc;
+      if (int rc = mp_f16_convert(d_g_acc, g->num_local * (int64_t)d, acc_ws, gs, /*rescue=*/false, stream)) return rc;
+      g16 = acc_ws;
+      g_scale = gs;
+    }
+    return mp_wgrad_f16_launch(g, h16, h_scale, g16, g_scale, d_gW_msg, d_gW_self, d_gbias, counter, stream);
   }
   const dim3 grid((unsigned)g->num_units, (unsigned)cdiv(2 * d, kWgTM), (unsigned)cdiv(d, kWgTN));
   GHF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "ghf_mp_weight_grad: hidden_dim %d too large", d);

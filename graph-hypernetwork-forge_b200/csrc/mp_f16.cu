@@ -76,7 +76,9 @@ constexpr uint32_t kFlagSrcEvictFirst = 1u, kFlagDstEvictLast = 2u, kFlagRedEvic
                    kFlagWEvictFirst = 16u;
 constexpr uint32_t kDefaultFlags = kFlagSrcEvictFirst | kFlagDstEvictLast | kFlagRedEvictLast;
 // timing experiments only (results are wrong): drop the reductions / the gathers
-constexpr uint32_t kDbgNoRed = 32u, kDbgNoGather = 64u, kDbgNoClear = 128u;
+constexpr uint32_t kDbgNoRed = 32u, kDbgNoGather = 64u;
+// accumulate into the rows as they are (ghf_mp_contract with accumulate != 0): no clearing, same synchronisation
+constexpr uint32_t kFlagNoClear = 128u;
 
 constexpr uint32_t kTileFirst = 1u, kTileLast = 2u, kTileWbuf = 4u;   // descriptor flags
 
@@ -482,7 +484,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       const int64_t share = (hi - lo + gridDim.x - 1) / gridDim.x;
       const int64_t r0 = lo + (int64_t)blockIdx.x * share, r1 = min(hi, r0 + share);
       float4* row = reinterpret_cast<float4*>(acc) + lane;
-      if (flags & kDbgNoClear) {
+      if (flags & kFlagNoClear) {
       } else if (flags & kFlagRedEvictLast) {                   // keep the zero lines in L2 until their reductions arrive
         const uint64_t pol = policy_evict_last();
         for (int64_t r = r0; r < r1; ++r)
@@ -625,7 +627,7 @@ int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool 
 }
 
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
-                  const void* pack_scratch, int* sync_words, cudaStream_t stream) {
+                  const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc) {
   GHF_REQUIRE(h16_scale != nullptr, "mp_f16: the fp16 shadow needs its scale words");
   GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
   GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_f16: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
@@ -660,7 +662,7 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
   mp_f16_kernel<P, T><<<(unsigned)grid, threads_for(P), kSmem, stream>>>(                                        \
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,                    \
       reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, \
-      zero_done, (int)g->num_phases, g->sb_nodes, g->num_local, env_flags(), trace)
+      zero_done, (int)g->num_phases, g->sb_nodes, g->num_local, env_flags() | (keep_acc ? kFlagNoClear : 0u), trace)
   if (trace) GHF_F16_LAUNCH(4, true);
   else if (prod == 8) GHF_F16_LAUNCH(8, false);
   else GHF_F16_LAUNCH(4, false);

@@ -62,9 +62,9 @@ def lib():
         "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
         "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
-        "ghf_mp_contract": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P]),
-        "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P]),
-        "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, c_int, P, P, P, P, P]),
+        "ghf_mp_contract": (c_int, [P, P, P, P, P, P, P, c_int, P, c_int, P, P]),
+        "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P, P]),
+        "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, P]),
         "ghf_text_encode_backward": (c_int, [P, P, P, c_int64, P, c_int, P, c_int, P, P, P, P, P, P]),
         "ghf_absmax": (c_int, [P, c_int64, P, P]),
         "ghf_convert_f16": (c_int, [P, c_int64, P, P, c_int, P]),
@@ -380,8 +380,9 @@ class Graph:
             self._reversed = rev
         return rev
 
-    def contract(self, x, W_msg, W_self, bias, precision: int, x16=None) -> torch.Tensor:
-        """Raw per-destination sums of x_u W_msg[r] + x_v W_self[r] + bias[r] -> [local nodes, d]."""
+    def contract(self, x, W_msg, W_self, bias, precision: int, x16=None, out=None, accumulate: bool = False):
+        """Raw per-destination sums of x_u W_msg[r] + x_v W_self[r] + bias[r] -> [local nodes, d]; with
+        `accumulate` they are added to `out`."""
         dev, d = self.device, self.hidden_dim
         x, W_msg, W_self, bias = _f32(x), _f32(W_msg), _f32(W_self), _f32(bias)
         if x.shape != (self.num_nodes, d):
@@ -389,29 +390,39 @@ class Graph:
         if W_msg.shape != (self.num_rel, d, d) or W_self.shape != (self.num_rel, d, d) or \
                 bias.shape != (self.num_rel, d):
             raise RuntimeError("relation weights must be [R,d,d], [R,d,d], [R,d]")
-        acc = torch.empty((self.num_local, d), dtype=torch.float32, device=dev)
+        if out is None:
+            if accumulate:
+                raise RuntimeError("contract: accumulate needs `out`")
+            out = torch.empty((self.num_local, d), dtype=torch.float32, device=dev)
+        elif out.shape != (self.num_local, d) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise RuntimeError("contract: out must be a contiguous float32 [local nodes, d] tensor")
         ws = self.workspace(precision)
         with torch.cuda.device(dev):
             _check(lib().ghf_mp_contract(self._h, _ptr(x), _ptr(x16.data) if x16 else None,
                                          _ptr(x16.scale) if x16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
-                                         precision, _ptr(acc), _ptr(ws), _stream(dev)), "ghf_mp_contract")
-        return acc
+                                         precision, _ptr(out), int(accumulate), _ptr(ws), _stream(dev)),
+                   "ghf_mp_contract")
+        return out
 
-    def epilogue_backward(self, g_out, upd, h, ln_w, eps: float):
-        """-> (g_pre, g_acc, g_ln_w, g_ln_b); see ghf_mp_epilogue_backward."""
+    def epilogue_backward(self, g_out, upd, h, ln_w, eps: float, want_shadow: bool = False):
+        """-> (g_pre, g_acc, g_ln_w, g_ln_b, Shadow of g_acc or None); see ghf_mp_epilogue_backward."""
         dev, d = self.device, self.hidden_dim
         g_out, upd, h, ln_w = _f32(g_out), _f32(upd), _f32(h), _f32(ln_w)
         if g_out.shape != (self.num_local, d) or upd.shape != g_out.shape or h.shape != (self.num_nodes, d):
             raise RuntimeError("epilogue_backward: shape mismatch")
         g_pre, g_acc = torch.empty_like(g_out), torch.empty_like(g_out)
         g_w, g_b = torch.empty_like(ln_w), torch.empty_like(ln_w)
+        g16 = Shadow(torch.empty(g_acc.shape, dtype=torch.float16, device=dev)) if want_shadow else None
         with torch.cuda.device(dev):
             _check(lib().ghf_mp_epilogue_backward(self._h, _ptr(g_out), _ptr(upd), _ptr(h), _ptr(ln_w), float(eps),
-                                                  _ptr(g_pre), _ptr(g_acc), _ptr(g_w), _ptr(g_b), _stream(dev)),
+                                                  _ptr(g_pre), _ptr(g_acc), _ptr(g_w), _ptr(g_b),
+                                                  _ptr(g16.scale) if g16 else None, _stream(dev)),
                    "ghf_mp_epilogue_backward")
-        return g_pre, g_acc, g_w, g_b
+        if g16 is not None:
+            to_f16(g_acc, g16, have_amax=True)
+        return g_pre, g_acc, g_w, g_b, g16
 
-    def weight_grad(self, h, g_acc, precision: int, h16=None):
+    def weight_grad(self, h, g_acc, precision: int, h16=None, g16=None):
         """-> (g_W_msg [R,d,d], g_W_self [R,d,d], g_bias [R,d]); see ghf_mp_weight_grad."""
         dev, d = self.device, self.hidden_dim
         h, g_acc = _f32(h), _f32(g_acc)
@@ -423,8 +434,10 @@ class Graph:
         ws = self.workspace(precision)
         with torch.cuda.device(dev):
             _check(lib().ghf_mp_weight_grad(self._h, _ptr(h), _ptr(h16.data) if h16 else None,
-                                            _ptr(h16.scale) if h16 else None, _ptr(g_acc), precision, _ptr(gm),
-                                            _ptr(gs), _ptr(gb), _ptr(ws), _stream(dev)), "ghf_mp_weight_grad")
+                                            _ptr(h16.scale) if h16 else None, _ptr(g_acc),
+                                            _ptr(g16.data) if g16 else None, _ptr(g16.scale) if g16 else None,
+                                            precision, _ptr(gm), _ptr(gs), _ptr(gb), _ptr(ws), _stream(dev)),
+                   "ghf_mp_weight_grad")
         return gm, gs, gb
 
 def forward_host(desc: ModelDesc, params, node_features, edge_index, utf8, offsets, out, device):

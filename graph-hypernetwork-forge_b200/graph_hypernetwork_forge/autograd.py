@@ -17,11 +17,16 @@ def wants_grad(*tensors) -> bool:
 
 
 class LinearFn(torch.autograd.Function):
-    """y = exp(log_scale) * act(x W^T + b) (ghf_linear).  Backward: three GEMMs through torch.matmul."""
+    """y = exp(log_scale) * act(x W^T + b) (ghf_linear).  Backward: three GEMMs through torch.matmul.
+    `shadow` (a list, optional) receives the fp16 Shadow of y made by the same kernel (the input projection)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, log_scale, relu: bool):
-        y = _native.linear(x, weight, bias, relu=relu, log_scale=log_scale)
+    def forward(ctx, x, weight, bias, log_scale, relu: bool, shadow):
+        if shadow is not None:
+            y, y16 = _native.linear(x, weight, bias, relu=relu, log_scale=log_scale, want_f16=True)
+            shadow.append(y16)
+        else:
+            y = _native.linear(x, weight, bias, relu=relu, log_scale=log_scale)
         ctx.relu = relu
         ctx.save_for_backward(x, weight, log_scale, y)
         ctx.has_bias = bias is not None
@@ -41,11 +46,11 @@ class LinearFn(torch.autograd.Function):
         g_x = g_pre @ weight if ctx.needs_input_grad[0] else None
         g_w = g_pre.t() @ x if ctx.needs_input_grad[1] else None
         g_b = g_pre.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return g_x, g_w, g_b, g_ls, None
+        return g_x, g_w, g_b, g_ls, None, None
 
 
-def linear(x, weight, bias, relu=False, log_scale=None):
-    return LinearFn.apply(x, weight, bias, log_scale, relu)
+def linear(x, weight, bias, relu=False, log_scale=None, shadow=None):
+    return LinearFn.apply(x, weight, bias, log_scale, relu, shadow)
 
 
 class TextEncodeFn(torch.autograd.Function):
@@ -83,19 +88,25 @@ class MPLayerFn(torch.autograd.Function):
     def backward(ctx, g_out):
         h, W_msg, W_self, ln_w, upd = ctx.saved_tensors
         graph, prec = ctx.graph, ctx.precision
-        g_pre, g_acc, g_ln_w, g_ln_b = graph.epilogue_backward(g_out.contiguous(), upd, h, ln_w, ctx.eps)
+        f16 = prec == _native.PREC_F16
+        # g_acc travels as ONE fp16 shadow to the two contractions and to the weight gradients (its max comes out
+        # of the epilogue kernel itself)
+        g_pre, g_acc, g_ln_w, g_ln_b, g16 = graph.epilogue_backward(g_out.contiguous(), upd, h, ln_w, ctx.eps,
+                                                                    want_shadow=f16 and graph.hidden_dim == 128)
         g_h = None
         if ctx.needs_input_grad[0]:
             zero_w = torch.zeros_like(W_msg)
             zero_b = torch.zeros(W_msg.shape[:2], dtype=W_msg.dtype, device=W_msg.device)
+            g_h = g_pre                                    # the residual's share; the other two are added in place
             # messages: g_acc_v W_msg[r]^T lands on the SOURCE u - the same contraction over the reversed edges
-            g_h = graph.reversed().contract(g_acc, W_msg.transpose(1, 2).contiguous(), zero_w, zero_b, prec)
+            graph.reversed().contract(g_acc, W_msg.transpose(1, 2).contiguous(), zero_w, zero_b, prec, x16=g16,
+                                      out=g_h, accumulate=True)
             # self-loop: g_acc_v W_self[r]^T summed over v's in-edges stays at v
-            g_h += graph.contract(g_acc, zero_w, W_self.transpose(1, 2).contiguous(), zero_b, prec)
-            g_h += g_pre                                                             # residual
+            graph.contract(g_acc, zero_w, W_self.transpose(1, 2).contiguous(), zero_b, prec, x16=g16, out=g_h,
+                           accumulate=True)
         g_wm = g_ws = g_b = None
         if any(ctx.needs_input_grad[1:4]):
-            g_wm, g_ws, g_b = graph.weight_grad(h, g_acc, prec, h16=ctx.h16)
+            g_wm, g_ws, g_b = graph.weight_grad(h, g_acc, prec, h16=ctx.h16, g16=g16)
         return g_h, g_wm, g_ws, g_b, g_ln_w, g_ln_b, None, None, None, None, None
 
 

@@ -269,14 +269,23 @@ class HyperGNN(nn.Module):
         wrapped in a Function whose backward is the gradient kernel, so `loss.backward()` and an optimiser step
         work as they do on the reference (tests/test_hypergnn.py:183-226, demo.py:79-101)."""
         graph, packed = prepared.graph, prepared.packed
-        h = autograd.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True)
+        N, d = graph.num_nodes, self.hidden_dim
+        chain = prec == _native.PREC_F16 and N * d % 8 == 0      # fp16 shadows chained as in the no-grad path
+        made = [] if chain else None
+        h = autograd.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True, shadow=made)
+        h16 = made[0] if chain else None
         text_embs = self.text_encoder.encode_packed(packed)
         if taps is not None:
             taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
         for l in range(self.num_layers):
             w = self._generate(l, text_embs, packed.num_unique)
             ln = self.layer_norms[l]
-            h = autograd.mp_layer(graph, h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec)
+            out16 = None
+            if chain and l + 1 < self.num_layers:
+                out16 = _native.Shadow(torch.empty((graph.num_local, d), dtype=torch.float16, device=h.device))
+            h = autograd.mp_layer(graph, h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
+                                  h16=h16, out16=out16)
+            h16 = out16
             if taps is not None:
                 taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
                 taps[f"h.{l}"] = h

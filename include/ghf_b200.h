@@ -144,23 +144,27 @@ int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, float* d_scale
  *   x_u W_msg[r] + x_v W_self[r] + bias[r]   (no mean, no epilogue; [local nodes, d], 256-byte aligned).
  * It is the forward kernel, and it is also the gradient w.r.t. h: with x = g_acc and the relation matrices
  * transposed, on the graph built from the REVERSED edge list (W_self = 0) it yields the message term, on the
- * graph itself (W_msg = 0) the self-loop term.  (d_x16, d_x16_scale) as in ghf_mp_layer_f16. */
+ * graph itself (W_msg = 0) the self-loop term.  (d_x16, d_x16_scale) as in ghf_mp_layer_f16.  accumulate != 0: the
+ * sums are ADDED to what d_acc holds (the three shares of dL/dh land in one buffer without extra passes). */
 int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void* d_x16, const float* d_x16_scale,
                     const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
-                    float* d_acc, void* d_workspace, void* stream);
+                    float* d_acc, int accumulate, void* d_workspace, void* stream);
 /* Undo LayerNorm, ReLU and the mean (HG:212-213, 289-296) for rows [dst_lo, dst_hi): from d_g_out = dL/d out,
  * the saved pre-residual update d_upd (ghf_mp_layer's tap) and d_h:
  *   d_g_pre = dL/d(upd + h)  (also the residual's share of dL/dh),  d_g_acc = d_g_pre / max(indeg, 1),
- *   d_g_ln_w[d], d_g_ln_b[d] = LayerNorm parameter gradients (overwritten).  hidden_dim <= 256. */
+ *   d_g_ln_w[d], d_g_ln_b[d] = LayerNorm parameter gradients (overwritten).  hidden_dim <= 256.
+ *   d_g_acc_scale (float[2], optional, hidden_dim 32/64/128): [1] = max |g_acc|, ready for ghf_convert_f16 with
+ *   have_amax = 1 - the fp16 shadow of g_acc the gradient contractions gather from. */
 int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out, const float* d_upd, const float* d_h,
                              const float* d_ln_w, float eps, float* d_g_pre, float* d_g_acc, float* d_g_ln_w,
-                             float* d_g_ln_b, void* stream);
+                             float* d_g_ln_b, float* d_g_acc_scale, void* stream);
 /* Gradients of the generated relation tensors (overwritten): g_W_msg[r] = sum_{e in r} h_u^T g_acc_v,
  * g_W_self[r] = sum_{e in r} h_v^T g_acc_v, g_bias[r] = sum_{e in r} g_acc_v  ([R,d,d], [R,d,d], [R,d]).
- * (d_h16, d_h16_scale): optional fp16 shadow of h for the tensor-core path (precision GHF_PREC_F16, hidden 128). */
+ * (d_h16, d_h16_scale), (d_g16, d_g16_scale): optional fp16 shadows of h and g_acc for the tensor-core path
+ * (precision GHF_PREC_F16, hidden 128; made inside, in the workspace, when NULL). */
 int ghf_mp_weight_grad(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
-                       const float* d_g_acc, int precision, float* d_gW_msg, float* d_gW_self, float* d_gbias,
-                       void* d_workspace, void* stream);
+                       const float* d_g_acc, const void* d_g16, const float* d_g16_scale, int precision,
+                       float* d_gW_msg, float* d_gW_self, float* d_gbias, void* d_workspace, void* stream);
 /* Backward of ghf_text_encode: parameter gradients g_emb [128,C], g_Wp [T,C], g_bp [T] (overwritten) from
  * d_out (the forward result) and d_g_out. */
 int ghf_text_encode_backward(const uint8_t* d_utf8, const int64_t* d_offsets, const int64_t* d_string_index,
