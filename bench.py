@@ -242,7 +242,8 @@ def main():
     if world == 1:
         def step():
             if args.python_path:    # the same stages enqueued one by one from Python (~60 native calls per forward)
-                return model.forward_prepared(x, model.prepare_packed(edge_index, utf8, offsets, N))
+                with torch.no_grad():
+                    return model.forward_prepared(x, model.prepare_packed(edge_index, utf8, offsets, N))
             return model.forward_packed(x, edge_index, utf8, offsets)   # one native call per forward
         n_local = N
     else:

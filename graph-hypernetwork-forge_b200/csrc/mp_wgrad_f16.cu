@@ -21,6 +21,8 @@
 // TMEM: 2 buffers x (msg 128 + self 128 columns): the epilogue of unit i overlaps the products of unit i + 1.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mp.cuh"
 #include "umma.cuh"
@@ -44,6 +46,13 @@ constexpr int kRowsPerWarp = kT / kProdWarps;   // 8
 constexpr uint32_t kTmemCols = 512;
 constexpr int kXposeBytes = kEpiWarps * 32 * 33 * 4;
 constexpr int kSmem = 1024 + kStages * kStageBytes + kXposeBytes + kQueue * 16 + 512;
+// Optional L2 eviction-priority hints (GHF_WGRAD_FLAGS): source rows evict_first / destination rows evict_last / g_W
+// reductions evict_last.  At c3 no combination moves the kernel outside run-to-run noise (tools/wgrad_sweep.py), so the
+// default is none.  The kernel is HBM-bound (ncu, profiles/r01_ncu_backward_summary.txt): 5.4 GB of row gathers that
+// miss L2 plus 2 x 3.5 GB for the read-modify-write of g_W lines - a relation's 128 KiB come back every ~50 units,
+// after ~240 MB of row traffic has passed through L2.
+constexpr uint32_t kFlagSrcEvictFirst = 1u, kFlagDstEvictLast = 2u, kFlagRedEvictLast = 4u;
+constexpr uint32_t kDefaultFlags = 0u;
 
 // kind::f16, D fp32, A and B fp16, BOTH MN-major ([15], [16]), N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(kD >> 3) << 17) | ((uint32_t)(kD >> 4) << 24);
@@ -74,7 +83,7 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
                     const int32_t* __restrict__ dst_sorted, const __half* __restrict__ h16, int64_t dst_lo,
                     const float* __restrict__ h_scale, const __half* __restrict__ g16,
                     const float* __restrict__ g_scale, float* __restrict__ gW_msg, float* __restrict__ gW_self,
-                    int* __restrict__ unit_counter) {
+                    int* __restrict__ unit_counter, uint32_t flags) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sA = (raw + 1023u) & ~1023u;
@@ -132,6 +141,7 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
     const int q = warp;                                    // TMEM lanes [32q, 32q + 32) = matrix rows
     float* xp = reinterpret_cast<float*>(smem_raw + (sX - raw)) + warp * (32 * 33);
     const float scale = h_scale[0] * g_scale[0];
+    const uint64_t pol_red = (flags & kFlagRedEvictLast) ? policy_evict_last() : policy_evict_normal();
     for (uint32_t it = 0;; ++it) {
       const int4 t = q_acquire(it);
       if (t.x < 0) break;
@@ -152,7 +162,7 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
           __syncwarp();
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr)                 // one matrix row per instruction: a 128 B line
-            red_add_f32(out + (int64_t)rr * kD + cb * 32, xp[rr * 33 + lane]);
+            red_add_f32_hint(out + (int64_t)rr * kD + cb * 32, xp[rr * 33 + lane], pol_red);
           __syncwarp();
         }
       }
@@ -166,6 +176,8 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
     const int l16 = lane & 15, hi = lane >> 4;
     const uint8_t* hb = reinterpret_cast<const uint8_t*>(h16) + l16 * 16;
     const uint8_t* gb = reinterpret_cast<const uint8_t*>(g16) + l16 * 16;
+    const uint64_t pol_src = (flags & kFlagSrcEvictFirst) ? policy_evict_first() : policy_evict_normal();
+    const uint64_t pol_dst = (flags & kFlagDstEvictLast) ? policy_evict_last() : policy_evict_normal();
     struct Ids { int src, dst; };
     auto ids_of = [&](const int4& t, int s) -> Ids {
       const int row = s * kT + kRowsPerWarp * pw + (lane & (kRowsPerWarp - 1));
@@ -195,13 +207,14 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
       for (int set = 0; set < 3; ++set) {
         const int mine = set == 0 ? ids.src : ids.dst;
         const uint8_t* table = set == 0 ? hb : (set == 1 ? hb + dst_lo * (kD * 2) : gb);
+        const uint64_t pol = set == 0 ? pol_src : pol_dst;
 #pragma unroll
         for (int i = 0; i < kRowsPerWarp / 2; ++i) {
           const int rl = 2 * i + hi;
           const int idx = __shfl_sync(0xffffffffu, mine, rl);
           const int row = kRowsPerWarp * pw + rl;
           const uint32_t to = base + set * kSet + row * 128 + (((l16 & 7) ^ (row & 7)) << 4);
-          if (idx >= 0) cp_async_16(to, table + (int64_t)idx * (kD * 2));
+          if (idx >= 0) cp_async_16_hint(to, table + (int64_t)idx * (kD * 2), pol);
           else if (row < rows16) cp_async_16_zfill(to, table, 0u);
         }
       }
@@ -328,11 +341,13 @@ int mp_wgrad_f16_launch(const ghf_graph* g, const void* h16, const float* h_scal
     configured = true;
   }
   GHF_CUDA(cudaMemsetAsync(unit_counter, 0, sizeof(int), stream));
+  const char* fenv = getenv("GHF_WGRAD_FLAGS");
+  const uint32_t flags = fenv ? (uint32_t)atoi(fenv) : kDefaultFlags;
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
   mp_wgrad_f16_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
       reinterpret_cast<const __half*>(h16), g->dst_lo, h_scale, reinterpret_cast<const __half*>(g16), g_scale, gW_msg,
-      gW_self, unit_counter);
+      gW_self, unit_counter, flags);
   GHF_LAUNCH_CHECK();
   mp_bgrad_f16_kernel<<<(unsigned)g->num_units, 64, 0, stream>>>(g->unit_start, g->unit_count, g->unit_rel,
                                                                 g->dst_sorted, reinterpret_cast<const __half2*>(g16),

@@ -14,7 +14,7 @@ import torch
 
 from _util import GRAD_CASES, build_model, check_grads, load_grad_case, assert_rel_to_max
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.grad]
 DEV = torch.device("cuda:0")
 FP32_GRAD_REL, TC_GRAD_REL = 2e-4, 2e-2
 
@@ -138,6 +138,7 @@ class TestTraining:
             assert float(p.grad.abs().max()) > 0, f"{n}: gradient is identically zero"
 
     def test_no_grad_forward_is_unchanged(self, small_model, toy_kg):
+        assert torch.is_grad_enabled()
         out = small_model(toy_kg.node_features, toy_kg.edge_index, toy_kg.edge_texts)
         with torch.no_grad():
             out2 = small_model(toy_kg.node_features, toy_kg.edge_index, toy_kg.edge_texts)

@@ -9,6 +9,8 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "graph-hypernetwork-forge_b200")]
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+torch.set_grad_enabled(False)   # inference tool: no autograd graph
+
 from graph_hypernetwork_forge import HyperGNN, ToyKnowledgeGraph  # noqa: E402
 from oracle import hypergnn_oracle as O  # noqa: E402
 

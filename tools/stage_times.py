@@ -7,6 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "graph-hypernetwork-forge_b200")]
 import torch  # noqa: E402
 
+torch.set_grad_enabled(False)   # inference tool: no autograd graph
+
 import bench  # noqa: E402
 from graph_hypernetwork_forge import _native  # noqa: E402
 from graph_hypernetwork_forge.models.hypergnn import PackedTexts  # noqa: E402
