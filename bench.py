@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    torch.set_grad_enabled(False)   # inference benchmark: no autograd graph is recorded
     w = dict(WORKLOADS[args.workload])
     if args.scale != 1.0:
         w["N"], w["E"] = max(64, int(w["N"] * args.scale)), max(64, int(w["E"] * args.scale))

@@ -66,6 +66,8 @@ def lib():
         "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P, P]),
         "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, P]),
         "ghf_text_encode_backward": (c_int, [P, P, P, c_int64, P, c_int, P, c_int, P, P, P, P, P, P]),
+        "ghf_score_pairs": (c_int, [P, c_int64, c_int, P, P, c_int64, P, P]),
+        "ghf_score_pairs_backward": (c_int, [P, c_int64, c_int, P, P, c_int64, P, P, P]),
         "ghf_absmax": (c_int, [P, c_int64, P, P]),
         "ghf_convert_f16": (c_int, [P, c_int64, P, P, c_int, P]),
         "ghf_hypergnn_forward_host": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
@@ -91,7 +93,7 @@ EXPORTED_SYMBOLS = (
     "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
     "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
-    "ghf_text_encode_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_text_encode_backward", "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -271,6 +273,36 @@ def text_encode_backward(utf8, offsets, index, num, char_emb, proj_w, out, g_out
     return g_emb, g_w, g_b
 
 
+def _pair_ids(emb, heads, tails):
+    if heads.dtype != torch.int64 or tails.dtype != torch.int64 or heads.shape != tails.shape or heads.dim() != 1:
+        raise RuntimeError("heads and tails must be 1-D int64 tensors of the same length")
+    return heads.contiguous(), tails.contiguous()
+
+
+def score_pairs(emb: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor) -> torch.Tensor:
+    """out[b] = <emb[heads[b]], emb[tails[b]]> without materialising the gathered rows."""
+    emb = _f32(emb)
+    heads, tails = _pair_ids(emb, heads, tails)
+    dev = emb.device
+    out = torch.empty(heads.numel(), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().ghf_score_pairs(_ptr(emb), emb.shape[0], emb.shape[1], _ptr(heads), _ptr(tails), heads.numel(),
+                                     _ptr(out), _stream(dev)), "ghf_score_pairs")
+    return out
+
+
+def score_pairs_backward(emb, heads, tails, g_out) -> torch.Tensor:
+    emb, g_out = _f32(emb), _f32(g_out)
+    heads, tails = _pair_ids(emb, heads, tails)
+    dev = emb.device
+    g_emb = torch.empty_like(emb)
+    with torch.cuda.device(dev):
+        _check(lib().ghf_score_pairs_backward(_ptr(emb), emb.shape[0], emb.shape[1], _ptr(heads), _ptr(tails),
+                                              heads.numel(), _ptr(g_out), _ptr(g_emb), _stream(dev)),
+               "ghf_score_pairs_backward")
+    return g_emb
+
+
 class Graph:
     """Owner of a ghf_graph handle (in-degree, dst-CSR, relation-grouped edge order)."""
 
@@ -325,6 +357,13 @@ class Graph:
                                           _stream(dev)), "ghf_graph_export")
         return {"perm": perm, "indeg": indeg, "rowptr": rowptr, "unit_start": us, "unit_count": uc,
                 "unit_rel": ur}
+
+    def in_degree(self) -> torch.Tensor:
+        """int32 [local nodes] (multi-edges counted), cached."""
+        deg = getattr(self, "_indeg", None)
+        if deg is None:
+            deg = self._indeg = self.export()["indeg"]
+        return deg
 
     def workspace(self, precision: int) -> torch.Tensor:
         key = precision

@@ -72,6 +72,27 @@ class TextEncodeFn(torch.autograd.Function):
         return g_emb, g_w, g_b, None, None, None, None
 
 
+def _contraction_backward(graph, prec, h, W_msg, W_self, g_acc, g16, h16, needs, g_h):
+    """Gradients of acc_v = sum_{(u->v), r} (h_u W_msg[r] + h_v W_self[r] + bias[r]) given g_acc = dL/d acc.
+    `g_h` (or None): buffer that already holds the other shares of dL/dh; the two contraction terms are added to it.
+    -> (g_h, g_W_msg, g_W_self, g_bias)"""
+    if needs[0]:
+        zero_w = torch.zeros_like(W_msg)
+        zero_b = torch.zeros(W_msg.shape[:2], dtype=W_msg.dtype, device=W_msg.device)
+        # messages: g_acc_v W_msg[r]^T lands on the SOURCE u - the same contraction over the reversed edges
+        g_h = graph.reversed().contract(g_acc, W_msg.transpose(1, 2).contiguous(), zero_w, zero_b, prec, x16=g16,
+                                        out=g_h, accumulate=g_h is not None)
+        # self-loop: g_acc_v W_self[r]^T summed over v's in-edges stays at v
+        graph.contract(g_acc, zero_w, W_self.transpose(1, 2).contiguous(), zero_b, prec, x16=g16, out=g_h,
+                       accumulate=True)
+    else:
+        g_h = None
+    g_wm = g_ws = g_b = None
+    if any(needs[1:4]):
+        g_wm, g_ws, g_b = graph.weight_grad(h, g_acc, prec, h16=h16, g16=g16)
+    return g_h, g_wm, g_ws, g_b
+
+
 class MPLayerFn(torch.autograd.Function):
     """One message-passing layer (ghf_mp_layer_f16) with its gradients w.r.t. h, the generated relation tensors
     and the LayerNorm parameters."""
@@ -90,25 +111,53 @@ class MPLayerFn(torch.autograd.Function):
         graph, prec = ctx.graph, ctx.precision
         f16 = prec == _native.PREC_F16
         # g_acc travels as ONE fp16 shadow to the two contractions and to the weight gradients (its max comes out
-        # of the epilogue kernel itself)
+        # of the epilogue kernel itself); g_pre, the residual's share of dL/dh, is the buffer the others add to
         g_pre, g_acc, g_ln_w, g_ln_b, g16 = graph.epilogue_backward(g_out.contiguous(), upd, h, ln_w, ctx.eps,
                                                                     want_shadow=f16 and graph.hidden_dim == 128)
-        g_h = None
-        if ctx.needs_input_grad[0]:
-            zero_w = torch.zeros_like(W_msg)
-            zero_b = torch.zeros(W_msg.shape[:2], dtype=W_msg.dtype, device=W_msg.device)
-            g_h = g_pre                                    # the residual's share; the other two are added in place
-            # messages: g_acc_v W_msg[r]^T lands on the SOURCE u - the same contraction over the reversed edges
-            graph.reversed().contract(g_acc, W_msg.transpose(1, 2).contiguous(), zero_w, zero_b, prec, x16=g16,
-                                      out=g_h, accumulate=True)
-            # self-loop: g_acc_v W_self[r]^T summed over v's in-edges stays at v
-            graph.contract(g_acc, zero_w, W_self.transpose(1, 2).contiguous(), zero_b, prec, x16=g16, out=g_h,
-                           accumulate=True)
-        g_wm = g_ws = g_b = None
-        if any(ctx.needs_input_grad[1:4]):
-            g_wm, g_ws, g_b = graph.weight_grad(h, g_acc, prec, h16=ctx.h16, g16=g16)
+        g_h, g_wm, g_ws, g_b = _contraction_backward(graph, prec, h, W_msg, W_self, g_acc, g16, ctx.h16,
+                                                     ctx.needs_input_grad, g_pre)
         return g_h, g_wm, g_ws, g_b, g_ln_w, g_ln_b, None, None, None, None, None
 
 
 def mp_layer(graph, h, W_msg, W_self, bias, ln_w, ln_b, eps, precision, h16=None, out16=None):
     return MPLayerFn.apply(h, W_msg, W_self, bias, ln_w, ln_b, graph, eps, precision, h16, out16)
+
+
+class MPUpdateFn(torch.autograd.Function):
+    """Only the pre-residual update of a layer, upd_v = acc_v / max(indeg_v, 1) (HG:160-230, what the reference's
+    `_message_passing` returns).  Used when something sits between the update and the LayerNorm that the fused
+    epilogue does not do - dropout in training mode (HG:293-294) - so that the rest of the layer runs as torch ops."""
+
+    @staticmethod
+    def forward(ctx, h, W_msg, W_self, bias, graph, precision: int, h16):
+        acc = graph.contract(h, W_msg, W_self, bias, precision, x16=h16)
+        inv = 1.0 / graph.in_degree().clamp(min=1).to(acc.dtype)
+        ctx.graph, ctx.precision, ctx.h16 = graph, precision, h16
+        ctx.save_for_backward(h, W_msg, W_self, inv)
+        return acc.mul_(inv.unsqueeze(1))
+
+    @staticmethod
+    def backward(ctx, g_upd):
+        h, W_msg, W_self, inv = ctx.saved_tensors
+        g_acc = g_upd * inv.unsqueeze(1)
+        g_h, g_wm, g_ws, g_b = _contraction_backward(ctx.graph, ctx.precision, h, W_msg, W_self, g_acc, None, ctx.h16,
+                                                     ctx.needs_input_grad, None)
+        return g_h, g_wm, g_ws, g_b, None, None, None
+
+
+def mp_update(graph, h, W_msg, W_self, bias, precision, h16=None):
+    return MPUpdateFn.apply(h, W_msg, W_self, bias, graph, precision, h16)
+
+
+class ScorePairsFn(torch.autograd.Function):
+    """out[b] = <emb[heads[b]], emb[tails[b]]> (ghf_score_pairs / ghf_score_pairs_backward)."""
+
+    @staticmethod
+    def forward(ctx, emb, heads, tails):
+        ctx.save_for_backward(emb, heads, tails)
+        return _native.score_pairs(emb, heads, tails)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        emb, heads, tails = ctx.saved_tensors
+        return _native.score_pairs_backward(emb, heads, tails, g_out.contiguous()), None, None

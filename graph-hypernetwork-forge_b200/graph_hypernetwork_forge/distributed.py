@@ -75,6 +75,8 @@ class ShardedForward:
         """-> [num_nodes, hidden] on every rank (the last layer's slices are gathered as well)."""
         from . import _native
         m = self.model
+        if m.training and m.dropout > 0.0:
+            raise NotImplementedError("the multi-GPU path is inference-only (no dropout, no gradients)")
         graph, packed = prepared.graph, prepared.packed
         self.num_kept = graph.num_kept
         N, d = self.num_nodes, m.hidden_dim

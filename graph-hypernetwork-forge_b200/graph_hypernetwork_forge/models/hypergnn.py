@@ -227,8 +227,6 @@ class HyperGNN(nn.Module):
 
     def forward_prepared(self, node_features: torch.Tensor, prepared: PreparedGraph,
                          taps: Optional[dict] = None) -> torch.Tensor:
-        if self.training and self.dropout > 0.0:
-            raise NotImplementedError("dropout in training mode is outside the forward-only B200 path")
         _native.require_cuda(node_features, self.input_proj.weight)
         graph, packed = prepared.graph, prepared.packed
         if node_features.size(0) != graph.num_nodes:
@@ -236,8 +234,9 @@ class HyperGNN(nn.Module):
         if graph.dst_lo != 0 or graph.dst_hi != graph.num_nodes:
             raise RuntimeError("forward_prepared needs a full-range graph; see distributed.ShardedHyperGNN")
         prec = self._precision_code()
-        if autograd.wants_grad(node_features, *self.parameters()):
-            return self._forward_autograd(node_features, prepared, prec, taps)
+        dropping = self.training and self.dropout > 0.0
+        if dropping or autograd.wants_grad(node_features, *self.parameters()):
+            return self._forward_autograd(node_features, prepared, prec, taps, dropping)
         with torch.no_grad():
             h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
             if prec == _native.PREC_F16 and node_features.size(0) * self.hidden_dim % 8 == 0:
@@ -264,13 +263,18 @@ class HyperGNN(nn.Module):
                     taps[f"upd.{l}"], taps[f"h.{l}"] = upd, h
         return h
 
-    def _forward_autograd(self, node_features, prepared: PreparedGraph, prec: int, taps) -> torch.Tensor:
+    def _forward_autograd(self, node_features, prepared: PreparedGraph, prec: int, taps, dropping=False) -> torch.Tensor:
         """The same forward with the autograd graph recorded (`autograd.py`): every stage is the forward kernel
         wrapped in a Function whose backward is the gradient kernel, so `loss.backward()` and an optimiser step
-        work as they do on the reference (tests/test_hypergnn.py:183-226, demo.py:79-101)."""
+        work as they do on the reference (tests/test_hypergnn.py:183-226, demo.py:79-101).
+
+        `dropping` (training mode with dropout > 0, HG:293-294): the dropout sits between the ReLU and the
+        LayerNorm, inside what the fused epilogue computes, so the layer is split - the contraction and the mean
+        stay native (`autograd.MPUpdateFn`), residual + ReLU + `F.dropout` + LayerNorm run as torch ops on the
+        device.  `F.dropout` draws from torch's CUDA generator in the reference's call order."""
         graph, packed = prepared.graph, prepared.packed
         N, d = graph.num_nodes, self.hidden_dim
-        chain = prec == _native.PREC_F16 and N * d % 8 == 0      # fp16 shadows chained as in the no-grad path
+        chain = prec == _native.PREC_F16 and N * d % 8 == 0 and not dropping   # fp16 shadows chained layer to layer
         made = [] if chain else None
         h = autograd.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True, shadow=made)
         h16 = made[0] if chain else None
@@ -283,8 +287,13 @@ class HyperGNN(nn.Module):
             out16 = None
             if chain and l + 1 < self.num_layers:
                 out16 = _native.Shadow(torch.empty((graph.num_local, d), dtype=torch.float16, device=h.device))
-            h = autograd.mp_layer(graph, h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
-                                  h16=h16, out16=out16)
+            if dropping:
+                upd = autograd.mp_update(graph, h, w["W_msg"], w["W_self"], w["bias"], prec, h16=h16)
+                x = nn.functional.dropout(torch.relu(upd + h), p=self.dropout)
+                h = nn.functional.layer_norm(x, (d,), ln.weight, ln.bias, ln.eps)
+            else:
+                h = autograd.mp_layer(graph, h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps,
+                                      prec, h16=h16, out16=out16)
             h16 = out16
             if taps is not None:
                 taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
@@ -328,9 +337,11 @@ class HyperGNN(nn.Module):
         if edge_index.size(1) != offsets.numel() - 1:
             raise ValueError(
                 f"edge_index has {edge_index.size(1)} edges but edge_texts has {offsets.numel() - 1} entries")
-        if self.training and self.dropout > 0.0:
-            raise NotImplementedError("dropout in training mode is outside the forward-only B200 path")
         _native.require_cuda(node_features, edge_index, utf8, offsets, self.input_proj.weight)
+        if (self.training and self.dropout > 0.0) or autograd.wants_grad(node_features, *self.parameters()):
+            # the one-call native forward records no autograd graph and has no dropout: go stage by stage
+            return self.forward_prepared(node_features,
+                                         self.prepare_packed(edge_index, utf8, offsets, node_features.size(0)))
         gen = self.weight_generators[0].generators["W_msg"]
         linears = [m for m in gen if isinstance(m, nn.Linear)]
         desc = _native.ModelDesc(self.text_dim, self.node_feat_dim, self.hidden_dim, self.num_layers,
@@ -349,6 +360,14 @@ class HyperGNN(nn.Module):
     def score_triple(self, head_emb: torch.Tensor, tail_emb: torch.Tensor) -> torch.Tensor:
         """Dot-product link score (hypergnn.py:304-318); plain tensor arithmetic, not a kernel target."""
         return (head_emb * tail_emb).sum(dim=-1)
+
+    def score_edges(self, embs: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor) -> torch.Tensor:
+        """``score_triple(embs[heads], embs[tails])`` in one kernel: the two ``[B, hidden]`` gathers the training
+        loop of the reference materialises (demo.py:90-94) are read in place.  Differentiable w.r.t. ``embs``."""
+        _native.require_cuda(embs, heads, tails)
+        if autograd.wants_grad(embs):
+            return autograd.ScorePairsFn.apply(embs, heads, tails)
+        return _native.score_pairs(embs, heads, tails)
 
     def num_parameters(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)

@@ -171,6 +171,14 @@ int ghf_text_encode_backward(const uint8_t* d_utf8, const int64_t* d_offsets, co
                              int64_t U, const float* d_emb, int C, const float* d_Wp, int T, const float* d_out,
                              const float* d_g_out, float* d_g_emb, float* d_g_Wp, float* d_g_bp, void* stream);
 
+/* ---- batched link scores fused with the row gather (HG:304-318 applied to `embs[heads]`, `embs[tails]`, as
+ * demo.py:90-94 does): out[b] = <emb[heads[b]], emb[tails[b]]>, emb [N,d] fp32, ids int64 in [0,N) (checked;
+ * synchronises for the check).  The backward overwrites d_g_emb [N,d] with the scattered gradient. */
+int ghf_score_pairs(const float* d_emb, int64_t N, int d, const int64_t* d_heads, const int64_t* d_tails, int64_t B,
+                    float* d_out, void* stream);
+int ghf_score_pairs_backward(const float* d_emb, int64_t N, int d, const int64_t* d_heads, const int64_t* d_tails,
+                             int64_t B, const float* d_g_out, float* d_g_emb, void* stream);
+
 /* ---- whole forward from HOST buffers (HG:236-298): the end-to-end entry point --------------
  * Parameters are passed as one flat array of DEVICE pointers in reference state_dict order
  * (see INTEGRATION.md for the exact list); inputs and output are HOST

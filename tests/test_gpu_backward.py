@@ -178,3 +178,62 @@ class TestWeightGeneratorGradients:
         sum((v * w).sum() for v, w in zip(ref, wts)).backward()
         for n, p in weight_gen.named_parameters():
             assert_rel_to_max(got[n].cpu().numpy(), p.grad.cpu().numpy(), 1e-4, f"grad {n}")
+
+
+def test_dropout_in_training_mode_matches_torch_stream():
+    """Training mode with dropout > 0 (HG:293-294, WG:103-104): the drop-in draws its masks with F.dropout in the
+    reference's call order, so with the same CUDA seed it reproduces the oracle's forward and gradients."""
+    from graph_hypernetwork_forge import HyperGNN
+    from oracle import hypergnn_torch as OT
+    N, E, R, d, L, T, F, p = 500, 4000, 9, 32, 2, 16, 12, 0.25
+    g = torch.Generator(device=DEV).manual_seed(9)
+    ei = torch.randint(0, N, (2, E), generator=g, device=DEV)
+    rel = torch.randint(0, R, (E,), generator=g, device=DEV)
+    x = torch.randn(N, F, generator=g, device=DEV)
+    loss_w = torch.randn(N, d, generator=g, device=DEV)
+    names = [f"r{r}" for r in range(R)]
+    torch.manual_seed(9)
+    model = HyperGNN(T, F, d, L, dropout=p, precision="fp32")
+    with torch.no_grad():
+        for gen in model.weight_generators:
+            for q in gen.log_scales.values():
+                q.fill_(-1.0)
+    model = model.to(DEV).train()
+    prepared = model.prepare_ids(ei, rel, names, N)
+    torch.manual_seed(1234)
+    out = model.forward_prepared(x, prepared)
+    (out * loss_w).sum().backward()
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    torch.manual_seed(1234)
+    ref = OT.hypergnn_forward(params, x, ei, rel, names, d, L, dropout=p)
+    (ref * loss_w).sum().backward()
+    assert_rel_to_max(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), 1e-4, "out with dropout")
+    for k, q in model.named_parameters():
+        assert_rel_to_max(q.grad.cpu().numpy(), params[k].grad.cpu().numpy(), 5e-4, f"grad {k} with dropout")
+    model.eval()                                     # eval mode: no dropout, the fused path
+    with torch.no_grad():
+        a, b = model.forward_prepared(x, prepared), model.forward_prepared(x, prepared)
+    assert torch.equal(a, b) or float((a - b).abs().max()) < 1e-5
+
+
+def test_score_edges_matches_score_triple_and_its_gradient():
+    """`score_edges(embs, heads, tails)` = `score_triple(embs[heads], embs[tails])` (HG:304-318), forward and
+    gradient, with repeated ids; out-of-range ids raise."""
+    from graph_hypernetwork_forge import HyperGNN
+    model = HyperGNN(16, 8, 32, 1).to(DEV)
+    for d in (32, 50, 128):
+        g = torch.Generator(device=DEV).manual_seed(d)
+        embs = torch.randn(300, d, generator=g, device=DEV, requires_grad=True)
+        heads = torch.randint(0, 300, (2000,), generator=g, device=DEV)
+        tails = torch.randint(0, 300, (2000,), generator=g, device=DEV)
+        w = torch.randn(2000, generator=g, device=DEV)
+        got = model.score_edges(embs, heads, tails)
+        (got * w).sum().backward()
+        g_got = embs.grad.clone()
+        embs.grad = None
+        want = model.score_triple(embs[heads], embs[tails])
+        (want * w).sum().backward()
+        assert_rel_to_max(got.detach().cpu().numpy(), want.detach().cpu().numpy(), 1e-5, f"scores d={d}")
+        assert_rel_to_max(g_got.cpu().numpy(), embs.grad.cpu().numpy(), 1e-5, f"score gradient d={d}")
+    with pytest.raises(RuntimeError):
+        model.score_edges(embs.detach(), torch.tensor([0, 300], device=DEV), torch.tensor([1, 2], device=DEV))
