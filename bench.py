@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--skew", action="store_true", help="Zipf destinations/relations (secondary workload)")
     ap.add_argument("--python-path", action="store_true",
                     help="enqueue the stages from Python (prepare_packed + forward_prepared) instead of one native call")
+    ap.add_argument("--train", action="store_true",
+                    help="also time a training step (forward + backward on a prepared graph) -> key 'train_step'")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -344,6 +346,35 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(hout.numel() * 4),
                "api": "ghf_hypergnn_forward_host (C ABI, pinned host buffers)"}
 
+    # ---- optional: one training step (forward with the autograd graph + backward through the gradient kernels)
+    train = None
+    if world == 1 and args.train:
+        with torch.enable_grad():
+            model.train()
+            prepared = model.prepare_packed(edge_index, utf8, offsets, N)
+            loss_w = torch.randn(N, d, device=device)
+
+            def train_step():
+                model.zero_grad(set_to_none=True)
+                (model.forward_prepared(x, prepared) * loss_w).sum().backward()
+            for _ in range(2):
+                train_step()
+            k = max(1, min(args.steps, 5))
+            tv0, tv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(device)
+            tv0.record()
+            for _ in range(k):
+                train_step()
+            tv1.record()
+            torch.cuda.synchronize(device)
+            t_ms = tv0.elapsed_time(tv1) / k
+            model.eval()
+            model.zero_grad(set_to_none=True)
+            del prepared, loss_w
+        train = {"ms_per_step": t_ms, "value": E * L / (t_ms / 1e3), "unit": "edges/s/layer, forward + backward",
+                 "peak_memory_gib": torch.cuda.max_memory_allocated(device) / 2**30,
+                 "what": "prepared graph reused; loss = (out * W).sum(); gradients of every parameter"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = min(E, max(100_000, E // 10))      # a tenth of the edges, all nodes: ~20 s on 16 cores at c3
@@ -366,6 +397,8 @@ def main():
                            "parallelism": "single GPU" if world == 1 else f"dst-range x{world} + all-gather(h) per layer"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks.summary()}
+        if train is not None:
+            line["train_step"] = train
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

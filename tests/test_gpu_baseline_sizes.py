@@ -142,3 +142,50 @@ def test_c4_zero_shot_shape_scaled_fp32_hidden256():
     out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N), taps=taps)
     assert bool(torch.isfinite(out).all()) and int(taps["in_degree"].sum()) == E
     sampled_update_check(taps, ei, 128, 1e-4)
+
+
+@pytest.mark.grad
+def test_c3_wikikg2_shape_full_size_gradients_sampled():
+    """BASELINE config 3 at full size, one layer of the training step: the gradient kernels against float64
+    recomputations from the raw edge list on samples -
+      * dL/dW_msg[r], dL/dW_self[r], dL/dbias[r] of three relations (every edge of those relations),
+      * dL/dh at 256 sampled nodes (every out-edge and in-edge of those nodes),
+    given g_acc = dL/d acc.  Size-independent property: sum_r dL/dbias[r] = sum_v indeg_v * g_acc_v."""
+    from graph_hypernetwork_forge import _native
+    N, E, R, d = 2_500_000, 16_000_000, 535, 128
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    ei = torch.randint(0, N, (2, E), generator=gen, device=DEV, dtype=torch.int64)
+    rel = torch.randint(0, R, (E,), generator=gen, device=DEV, dtype=torch.int32)
+    h = torch.randn(N, d, generator=gen, device=DEV)
+    g_acc = torch.randn(N, d, generator=gen, device=DEV) * 1e-3
+    W_msg = torch.randn(R, d, d, generator=gen, device=DEV) * 0.05
+    W_self = torch.randn(R, d, d, generator=gen, device=DEV) * 0.05
+    graph = _native.Graph(ei, rel, N, R, d)
+    src, dst = ei[0], ei[1]
+
+    gm, gs, gb = graph.weight_grad(h, g_acc, _native.PREC_F16)
+    for r in (0, 77, R - 1):
+        idx = (rel == r).nonzero().squeeze(1)
+        hs, hd, ga = h[src[idx]].double(), h[dst[idx]].double(), g_acc[dst[idx]].double()
+        assert_rel_to_max(gm[r].cpu().numpy(), (hs.T @ ga).cpu().numpy(), 3e-3, f"dL/dW_msg[{r}] ({idx.numel()} edges)")
+        assert_rel_to_max(gs[r].cpu().numpy(), (hd.T @ ga).cpu().numpy(), 3e-3, f"dL/dW_self[{r}]")
+        assert_rel_to_max(gb[r].cpu().numpy(), ga.sum(0).cpu().numpy(), 3e-3, f"dL/dbias[{r}]")
+    indeg = graph.in_degree().double()
+    want_total = (indeg.unsqueeze(1) * g_acc.double()).sum(0)
+    assert_rel_to_max(gb.double().sum(0).cpu().numpy(), want_total.cpu().numpy(), 3e-3, "sum_r dL/dbias[r]")
+
+    # dL/dh through the two contractions (reversed graph for the messages, the graph itself for the self-loop)
+    zero_w, zero_b = torch.zeros_like(W_msg), torch.zeros(R, d, device=DEV)
+    g_h = graph.reversed().contract(g_acc, W_msg.transpose(1, 2).contiguous(), zero_w, zero_b, _native.PREC_F16)
+    graph.contract(g_acc, zero_w, W_self.transpose(1, 2).contiguous(), zero_b, _native.PREC_F16, out=g_h,
+                   accumulate=True)
+    sample = torch.unique(torch.randint(0, N, (256,), generator=gen, device=DEV))
+    want = torch.zeros(sample.numel(), d, dtype=torch.float64, device=DEV)
+    out_e = torch.isin(src, sample).nonzero().squeeze(1)          # messages sent by the sampled nodes
+    in_e = torch.isin(dst, sample).nonzero().squeeze(1)           # self-loop terms of the sampled nodes
+    for edges, at, W in ((out_e, src, W_msg), (in_e, dst, W_self)):
+        for lo in range(0, edges.numel(), 2048):
+            e = edges[lo:lo + 2048]
+            contrib = torch.bmm(g_acc[dst[e]].double().unsqueeze(1), W[rel[e].long()].double().transpose(1, 2)).squeeze(1)
+            want.index_add_(0, torch.searchsorted(sample, at[e]), contrib)
+    assert_rel_to_max(g_h[sample].cpu().numpy(), want.cpu().numpy(), 3e-3, "dL/dh at sampled nodes")
