@@ -64,14 +64,17 @@ class ShardedForward:
         return self._bufs16
 
     def forward_packed(self, node_features, edge_index, utf8, offsets) -> torch.Tensor:
+        # the projection of this rank's rows and the all-gather of their fp16 shadow do not depend on the graph:
+        # they are enqueued first, and the rows travel over NVLink while edge selection, dedup and graph build run
+        started = self._start_h0(node_features)
         prepared = self.model.prepare_packed(edge_index, utf8, offsets, self.num_nodes, dst_range=(self.lo, self.hi))
-        return self.forward_prepared(node_features, prepared)
+        return self.forward_prepared(node_features, prepared, _started=started)
 
     def forward(self, node_features, edge_index, edge_texts) -> torch.Tensor:
         prepared = self.model.prepare(edge_index, edge_texts, self.num_nodes, dst_range=(self.lo, self.hi))
         return self.forward_prepared(node_features, prepared)
 
-    def forward_prepared(self, node_features, prepared) -> torch.Tensor:
+    def forward_prepared(self, node_features, prepared, _started=None) -> torch.Tensor:
         """-> [num_nodes, hidden] on every rank (the last layer's slices are gathered as well)."""
         from . import _native
         m = self.model
@@ -83,7 +86,7 @@ class ShardedForward:
         prec = m._precision_code()
         cur, nxt = self._buffers(node_features.device, d)
         if prec == _native.PREC_F16:
-            return self._forward_f16(node_features, graph, packed, cur, nxt)
+            return self._forward_f16(graph, packed, _started or self._start_h0(node_features))
         with torch.no_grad():
             # every rank projects all nodes (h is needed in full as the gather source)
             cur[:N] = _native.linear(node_features, m.input_proj.weight, m.input_proj.bias, relu=True)
@@ -100,43 +103,47 @@ class ShardedForward:
         self._bufs = [cur, nxt]
         return cur[:N]
 
-    def _forward_f16(self, node_features, graph, packed, cur, nxt) -> torch.Tensor:
+    def _start_h0(self, node_features):
+        """PREC_F16, layer-0 input: project this rank's rows, agree on one scale, convert, start the all-gather of
+        the fp16 rows.  -> (cur, nxt, cur16, nxt16, pending work) or None when the path is not the f16 one."""
+        from . import _native
+        m = self.model
+        N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
+        if m._precision_code() != _native.PREC_F16:
+            return None
+        cur, nxt = self._buffers(node_features.device, d)
+        cur16, nxt16 = self._buffers16(node_features.device, d)
+        with torch.no_grad():
+            cur16.scale.zero_()
+            if hi > lo:
+                cur[lo:hi] = _native.linear(node_features[lo:hi], m.input_proj.weight, m.input_proj.bias, relu=True)
+                _native.absmax(cur[lo:hi], cur16)
+            # one scale for the whole shadow: the ranks agree on max |h0| first (4 bytes, stream-ordered)
+            dist.all_reduce(cur16.scale[1:2], op=dist.ReduceOp.MAX, group=self.group)
+            if hi > lo:
+                _native.to_f16(cur[lo:hi], cur16.rows(lo, hi), have_amax=True)
+            else:
+                _native.to_f16(cur[:0], cur16.rows(0, 0), have_amax=True)   # still writes the scale
+            # every all-gather is asynchronous: kernels enqueued before the wait (graph preparation here, the
+            # generator of the next layer later) run while the rows travel over NVLink
+            pending = gather_rows(cur16.data, self.rows, self.rank, self.group, async_op=True)
+        return cur, nxt, cur16, nxt16, pending
+
+    def _forward_f16(self, graph, packed, started) -> torch.Tensor:
         """PREC_F16: a rank needs fp32 h only for its own rows (residual), and the fp16 shadow of h in full (gather
         source).  So every rank projects only its own rows, and what travels between layers is the fp16 copy -
         half the all-gather bytes; the fp32 rows are gathered once, after the last layer, for the return value."""
         from . import _native
         m = self.model
-        N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
-        cur16, nxt16 = self._buffers16(node_features.device, d)
+        N, lo, hi = self.num_nodes, self.lo, self.hi
+        cur, nxt, cur16, nxt16, pending = started
         with torch.no_grad():
-            if self.world >= 4 and N * d % 8 == 0:
-                # from 4 ranks on, projecting all nodes redundantly (0.5 ms at c3) is cheaper than all-gathering the
-                # fp16 shadow of h0 (7/8 of 0.64 GB per rank); every rank then also picks the same scale by itself
-                _native.linear(node_features, m.input_proj.weight, m.input_proj.bias, relu=True, want_f16=True,
-                               out=cur[:N], out_shadow=cur16.rows(0, N))
-                pending = None
-            else:
-                cur16.scale.zero_()
-                if hi > lo:
-                    cur[lo:hi] = _native.linear(node_features[lo:hi], m.input_proj.weight, m.input_proj.bias,
-                                                relu=True)
-                    _native.absmax(cur[lo:hi], cur16)
-                # one scale for the whole shadow: the ranks agree on max |h0| first (4 bytes, stream-ordered)
-                dist.all_reduce(cur16.scale[1:2], op=dist.ReduceOp.MAX, group=self.group)
-                if hi > lo:
-                    _native.to_f16(cur[lo:hi], cur16.rows(lo, hi), have_amax=True)
-                else:
-                    _native.to_f16(cur[:0], cur16.rows(0, 0), have_amax=True)   # still writes the scale
-                # every all-gather is asynchronous: the generator kernels of the next layer (they do not depend on
-                # h) are enqueued before the wait and run while the rows travel over NVLink
-                pending = gather_rows(cur16.data, self.rows, self.rank, self.group, async_op=True)
             text_embs = m.text_encoder.encode_packed(packed)
             w = m._generate(0, text_embs, packed.num_unique)
             for l in range(m.num_layers):
                 ln = m.layer_norms[l]
                 last = l + 1 == m.num_layers
-                if pending is not None:
-                    pending.wait()
+                pending.wait()
                 if hi > lo:
                     graph.mp_layer(cur[:N], w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps,
                                    _native.PREC_F16, out=nxt[lo:hi], h16=cur16.rows(0, N),
