@@ -8,6 +8,7 @@ with these the drop-in does too: when gradients are enabled and something requir
 from __future__ import annotations
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _native
 
@@ -64,6 +65,7 @@ class TextEncodeFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_out):
         char_emb, proj_w, out = ctx.saved_tensors
         utf8, offsets, index, num = ctx.packed
@@ -106,6 +108,7 @@ class MPLayerFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_out):
         h, W_msg, W_self, ln_w, upd = ctx.saved_tensors
         graph, prec = ctx.graph, ctx.precision
@@ -137,6 +140,7 @@ class MPUpdateFn(torch.autograd.Function):
         return acc.mul_(inv.unsqueeze(1))
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_upd):
         h, W_msg, W_self, inv = ctx.saved_tensors
         g_acc = g_upd * inv.unsqueeze(1)
@@ -158,6 +162,7 @@ class ScorePairsFn(torch.autograd.Function):
         return _native.score_pairs(emb, heads, tails)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_out):
         emb, heads, tails = ctx.saved_tensors
         return _native.score_pairs_backward(emb, heads, tails, g_out.contiguous()), None, None

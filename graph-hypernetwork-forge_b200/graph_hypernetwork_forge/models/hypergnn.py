@@ -222,6 +222,8 @@ class HyperGNN(nn.Module):
         if E == 0:
             W_msg = W_self = torch.zeros(1, d, d, device=device)
             bias = torch.zeros(1, d, device=device)
+        if autograd.wants_grad(h, W_msg, W_self, bias):     # the reference's entry is differentiable; so is this one
+            return autograd.mp_update(g, h, W_msg, W_self, bias, _native.PREC_FP32)
         _, upd = g.mp_layer(h, W_msg, W_self, bias, ones, zeros, 1e-5, _native.PREC_FP32, want_upd=True)
         return upd
 

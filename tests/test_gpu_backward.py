@@ -237,3 +237,32 @@ def test_score_edges_matches_score_triple_and_its_gradient():
         assert_rel_to_max(g_got.cpu().numpy(), embs.grad.cpu().numpy(), 1e-5, f"score gradient d={d}")
     with pytest.raises(RuntimeError):
         model.score_edges(embs.detach(), torch.tensor([0, 300], device=DEV), torch.tensor([1, 2], device=DEV))
+
+
+def test_reference_shaped_message_passing_is_differentiable():
+    """`_message_passing(h, edge_index, per-edge weights)` (HG:160-230) against the literal torch formula, forward
+    and gradients w.r.t. h and the per-edge tensors."""
+    from graph_hypernetwork_forge import HyperGNN
+    N, E, d = 40, 300, 24
+    g = torch.Generator(device=DEV).manual_seed(3)
+    model = HyperGNN(16, 8, d, 1).to(DEV)
+    ei = torch.randint(0, N, (2, E), generator=g, device=DEV)
+    leaves = [torch.randn(N, d, generator=g, device=DEV), torch.randn(E, d, d, generator=g, device=DEV) * 0.1,
+              torch.randn(E, d, d, generator=g, device=DEV) * 0.1, torch.randn(E, d, generator=g, device=DEV)]
+    w = torch.randn(N, d, generator=g, device=DEV)
+    grads = []
+    for native in (True, False):
+        h, Wm, Ws, b = [t.clone().requires_grad_(True) for t in leaves]
+        if native:
+            out = model._message_passing(h, ei, {"W_msg": Wm, "W_self": Ws, "bias": b})
+        else:                                                      # HG:201-228, literally
+            src, dst = ei
+            msg = torch.bmm(h[src].unsqueeze(1), Wm).squeeze(1) + b
+            cnt = torch.zeros(N, 1, device=DEV).index_add_(0, dst, torch.ones(E, 1, device=DEV)).clamp(min=1)
+            agg = torch.zeros(N, d, device=DEV).index_add(0, dst, msg) / cnt
+            S = torch.zeros(N, d, d, device=DEV).index_add(0, dst, Ws) / cnt.unsqueeze(-1)
+            out = agg + torch.bmm(h.unsqueeze(1), S).squeeze(1)
+        (out * w).sum().backward()
+        grads.append([out.detach()] + [t.grad for t in (h, Wm, Ws, b)])
+    for name, a, b_ in zip(("out", "g_h", "g_W_msg", "g_W_self", "g_bias"), *grads):
+        assert_rel_to_max(a.cpu().numpy(), b_.cpu().numpy(), 2e-4, name)
