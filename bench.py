@@ -64,6 +64,12 @@ class ClockSampler:
                                           "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi needs a few hundred milliseconds to initialise NVML and attach to the GPU, and CUDA calls
+            # of this process can stall meanwhile: wait for its first sample so that none of that falls into the
+            # timed region (a 5-step warm-up is far shorter than the start-up)
+            t_end = time.time() + 5.0
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
         return self
@@ -282,13 +288,17 @@ def main():
         barrier()
         t_wall0 = time.time()
         ev0.record()
+        marks = []
         for _ in range(args.steps):
             out = timed_step()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         ev1.record()
         barrier()
         t_wall1 = time.time()
     clocks.window(t_wall0, t_wall1)
     ms = ev0.elapsed_time(ev1) / args.steps
+    each = [a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks)]     # per-step device time (diagnostic)
     launches = _native.launch_count()
     prof, n_layers_timed = _native.profile_read()
     _native.profile_enable(False)
@@ -396,6 +406,7 @@ def main():
                                  "workload smaller than L2: 256 MB scratch written between steps",
                            "parallelism": "single GPU" if world == 1 else f"dst-range x{world} + all-gather(h) per layer"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "ms_each_step": [round(v, 3) for v in each],
                 "clocks": clocks.summary()}
         if train is not None:
             line["train_step"] = train

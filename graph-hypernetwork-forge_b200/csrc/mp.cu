@@ -361,8 +361,8 @@ static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_
 // `acc_ext` (optional) receives the sums; otherwise they stay in the workspace for the epilogue.  -> *acc_used.
 static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
                            const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
-                           float* acc_ext, bool accumulate, void* d_workspace, cudaStream_t stream, float** acc_used,
-                           ProfRec* rec) {
+                           float* acc_ext, bool accumulate, bool transposed, void* d_workspace, cudaStream_t stream,
+                           float** acc_used, ProfRec* rec) {
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
@@ -385,6 +385,12 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
       GHF_CUDA(cudaMemsetAsync(counter, 0, head + nl * (size_t)d * 4, stream));
     }
   }
+  // gradient contractions (ghf_mp_contract): transposed relation matrices and an absent (NULL) half are understood
+  // by the f16 engine only; the host side materialises them for the other engines
+  const bool plain = !transposed && d_W_msg != nullptr && d_W_self != nullptr && d_bias != nullptr;
+  GHF_REQUIRE(plain || (precision == GHF_PREC_F16 && mp_f16_supported(d) && (d_W_msg != nullptr || d_W_self != nullptr)),
+              "ghf_mp_contract: transposed / NULL weight tensors need precision f16 and hidden_dim 128");
+  const int skip_half = d_W_msg == nullptr ? 1 : (d_W_self == nullptr ? 2 : 0);
   const bool ts = mp_ts_enabled(d);
   const void* h16 = d_h16;
   const float* h16_scale = d_h16_scale;
@@ -395,7 +401,7 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
   } else if (precision == GHF_PREC_F16) {
     GHF_REQUIRE(mp_f16_supported(d), "ghf_mp_layer: f16 path supports hidden_dim 128, got %d", d);
     if (g->num_units > 0) {
-      if (int rc = mp_f16_pack(g, d_W_msg, d_W_self, pack, stream)) return rc;
+      if (int rc = mp_f16_pack(g, d_W_msg, d_W_self, pack, stream, transposed)) return rc;
       if (h16 == nullptr) {  // no fp16 shadow of h from the previous layer: make one (scale words, then the rows)
         float* sc = reinterpret_cast<float*>(reinterpret_cast<char*>(pack) + mp_f16_pack_bytes(g->num_rel));
         void* conv = reinterpret_cast<char*>(sc) + 256;
@@ -413,7 +419,7 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
       rc = ts ? mp_ts_launch(g, d_h, d_bias, acc, pack, counter, stream)
               : mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream);
     } else if (precision == GHF_PREC_F16) {
-      rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream, accumulate);
+      rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream, accumulate, skip_half);
     } else if (d <= 32) {
       rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
     } else if (d <= 64) {
@@ -453,7 +459,7 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
   float* acc = nullptr;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
-                               false, d_workspace, stream, &acc, prof ? &rec : nullptr))
+                               false, false, d_workspace, stream, &acc, prof ? &rec : nullptr))
     return rc;
   if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream))
     return rc;
@@ -466,7 +472,7 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
 
 extern "C" int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void* d_x16, const float* d_x16_scale,
                                const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
-                               float* d_acc, int accumulate, void* d_workspace, void* stream_) {
+                               float* d_acc, int accumulate, int transposed, void* d_workspace, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_layer_args(g, d_workspace, precision, d_x16, d_x16_scale)) return rc;
   GHF_REQUIRE(d_acc != nullptr && reinterpret_cast<uintptr_t>(d_acc) % 256 == 0,
@@ -475,7 +481,7 @@ extern "C" int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void*
   if (g->num_local == 0) return 0;
   float* acc = nullptr;
   return run_contraction(g, d_x, d_x16, d_x16_scale, d_W_msg, d_W_self, d_bias, precision, d_acc, accumulate != 0,
-                         d_workspace, stream, &acc, nullptr);
+                         transposed != 0, d_workspace, stream, &acc, nullptr);
 }
 
 extern "C" int ghf_absmax(const float* d_x, int64_t elems, float* d_scale, void* stream_) {

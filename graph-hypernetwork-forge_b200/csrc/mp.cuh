@@ -30,7 +30,9 @@ int mp_ts_launch(const ghf_graph* g, const float* h, const float* bias, float* a
 bool mp_f16_supported(int hidden_dim);
 // scratch for the per-relation fp16 weight images [R][64 KiB] followed by their inverse power-of-two scales [R]
 int64_t mp_f16_pack_bytes(int num_rel);
-int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream);
+// W_msg or W_self may be NULL (zeros); `transposed`: the images are built from W[r]^T
+int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream,
+                bool transposed = false);
 // fp16 shadow of h: (h16, scale[2]) with h = h16 * scale[0], scale[1] = max|h| (see common.cuh).
 // absmax: scale[1] = max|x|.  convert: scale chosen from scale[1], scale[0] written, h16 = fp16(h * s); with
 // `rescue` the shadow already holds fp16(h) and is rewritten only if the range demands a scale.
@@ -41,7 +43,8 @@ int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool 
 // what the rows hold).  sync_words: mp_f16_sync_bytes(g).
 int64_t mp_f16_sync_bytes(const ghf_graph* g);
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
-                  const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc = false);
+                  const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc = false,
+                  int skip_half = 0);   // skip_half: 1 = no source term (W_msg NULL), 2 = no destination term
 
 // gradients of the generated relation tensors on tcgen05 (mp_wgrad_f16.cu, hidden_dim 128): g_W_msg[r] / g_W_self[r] /
 // g_bias[r] += sums over the edges of r (buffers zero at entry); h16 / g16 are fp16 shadows with their scale words.

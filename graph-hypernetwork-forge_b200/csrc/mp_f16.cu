@@ -79,6 +79,9 @@ constexpr uint32_t kDefaultFlags = kFlagSrcEvictFirst | kFlagDstEvictLast | kFla
 constexpr uint32_t kDbgNoRed = 32u, kDbgNoGather = 64u;
 // accumulate into the rows as they are (ghf_mp_contract with accumulate != 0): no clearing, same synchronisation
 constexpr uint32_t kFlagNoClear = 128u;
+// one half of K absent (gradient contractions, ghf_mp_contract with a NULL weight tensor): its rows are neither
+// gathered nor multiplied.  Bit 256 << s drops stage s (0 = source rows, 1 = destination rows).
+constexpr uint32_t kFlagSkipSrc = 256u, kFlagSkipDst = 512u;
 
 constexpr uint32_t kTileFirst = 1u, kTileLast = 2u, kTileWbuf = 4u;   // descriptor flags
 
@@ -106,19 +109,22 @@ __device__ __forceinline__ int wt_half_index(int n, int k) {
 }
 
 // One CTA per relation: amax over [W_msg[r]; W_self[r]], k_r = 14 - floor(log2(amax)), scaled fp16 image.
+// A NULL tensor stands for zeros; `transposed`: the image is built from W[r]^T (element (k, n) read at [n][k]).
 __global__ void __launch_bounds__(256)
 pack_f16_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_self, __half* __restrict__ pack,
-                float* __restrict__ inv_scale) {
+                float* __restrict__ inv_scale, int transposed) {
   __shared__ float s_max[8];
   __shared__ float s_scale;
   const int64_t r = blockIdx.x;
-  const float4* wm = reinterpret_cast<const float4*>(W_msg + r * kD * kD);
-  const float4* ws = reinterpret_cast<const float4*>(W_self + r * kD * kD);
   float m = 0.f;
-  for (int i = threadIdx.x; i < kD * kD / 4; i += 256) {
-    const float4 a = wm[i], b = ws[i];
-    m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
-    m = fmaxf(m, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+  for (int which = 0; which < 2; ++which) {
+    const float* W = which ? W_self : W_msg;
+    if (W == nullptr) continue;
+    const float4* w4 = reinterpret_cast<const float4*>(W + r * kD * kD);
+    for (int i = threadIdx.x; i < kD * kD / 4; i += 256) {
+      const float4 a = w4[i];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
@@ -142,15 +148,21 @@ pack_f16_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_sel
   const float scale = s_scale;
   __half* img = pack + r * (int64_t)(2 * kD * kD);
   // thread = (8 consecutive k, one n): lanes walk n, so every read is a coalesced 128 B line of one W row and
-  // the eight halfs of a thread are one 16 B store, consecutive across the warp (512 B)
+  // the eight halfs of a thread are one 16 B store, consecutive across the warp (512 B).  (Transposed: a thread
+  // reads its 8 values from one row - 32 B pieces, the 64 KiB of a relation come through L2 either way.)
   for (int i = threadIdx.x; i < (2 * kD / 8) * kD; i += 256) {
     const int n = i % kD, k0 = (i / kD) * 8;
-    const float* src = k0 < kD ? W_msg + (r * kD + k0) * kD + n : W_self + (r * kD + (k0 - kD)) * kD + n;
-    uint32_t w[4];
+    const float* W = k0 < kD ? W_msg : W_self;
+    const int kk = k0 < kD ? k0 : k0 - kD;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (W != nullptr) {
+      const float* src = transposed ? W + (r * kD + n) * kD + kk : W + (r * kD + kk) * kD + n;
+      const int step = transposed ? 1 : kD;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __half2 p = __floats2half2_rn(src[(2 * j) * kD] * scale, src[(2 * j + 1) * kD] * scale);
-      w[j] = *reinterpret_cast<const uint32_t*>(&p);
+      for (int j = 0; j < 4; ++j) {
+        const __half2 p = __floats2half2_rn(src[(2 * j) * step] * scale, src[(2 * j + 1) * step] * scale);
+        w[j] = *reinterpret_cast<const uint32_t*>(&p);
+      }
     }
     *reinterpret_cast<uint4*>(img + wt_half_index(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -291,7 +303,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       TileRegs x{-1, 0.f, 1.f};
       if (t.x < 0) return x;
       if (e0 + lane < t.y) x.dst = dst_sorted[t.x + e0 + lane];
-      x.bias_n = bias[(int64_t)t.z * kD + col];
+      x.bias_n = bias ? bias[(int64_t)t.z * kD + col] : 0.f;
       x.w_inv = w_inv_scale[t.z];
       return x;
     };
@@ -370,6 +382,7 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       const Ids ids_nxt = ids_of(nxt);                   // in flight while this tile's rows are issued
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {                      // s = 0: source rows, s = 1: destination rows
+        if (flags & (kFlagSkipSrc << s)) continue;       // this half of K is absent
         const long long t0 = tick();
         mbar_wait(empty(stage), phase ^ 1u);
         tadd(0, tick() - t0);
@@ -423,32 +436,37 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(a * kTile);
       const uint32_t w_tmem = tmem_base + kWCol + (uint32_t)(wb * kD);
+      const bool leader = elect_one();                   // the one lane that issues (and commits) this tile's MMAs
+      bool first = true;
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
+        if (flags & (kFlagSkipSrc << s)) continue;       // this half of K is absent (gradient contractions)
         t0 = tick();
         mbar_wait(full(stage), phase);
         tadd(2, tick() - t0);
         fence_proxy_async();                             // cp.async (generic proxy) writes -> tensor-core reads
         tc_fence_after();
         const uint32_t stage_addr = sA + stage * kStageBytes;
-        if (elect_one()) {
+        if (leader) {
 #pragma unroll
           for (int cs = 0; cs < 2; ++cs) {
             const uint64_t bdesc = umma_desc_k128(stage_addr + cs * kSub);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               umma_f16_ts(d_tmem, w_tmem + (uint32_t)(32 * (2 * s + cs) + 8 * j), bdesc + 2 * j, kIdesc,
-                          (uint32_t)(s | cs | j));
+                          first ? (uint32_t)(cs | j) : 1u);
           }
           umma_commit(empty(stage));
-          if (s == 1) {
-            umma_commit(acc_full(a));
-            if (tf & kTileLast) umma_commit(w_empty(wb));  // every MMA that reads this unit's weights is done
-          }
         }
+        first = false;
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
+      if (leader) {
+        umma_commit(acc_full(a));
+        if (tf & kTileLast) umma_commit(w_empty(wb));    // every MMA that reads this unit's weights is done
+      }
+      __syncwarp();
     }
     if constexpr (kTrace)
       if (tracing) {
@@ -584,7 +602,7 @@ int64_t mp_f16_pack_bytes(int num_rel) {
 }
 
 int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch,
-                cudaStream_t stream) {
+                cudaStream_t stream, bool transposed) {
   GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(W_msg) | reinterpret_cast<uintptr_t>(W_self) |
                reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
@@ -592,7 +610,7 @@ int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, voi
   __half* img = reinterpret_cast<__half*>(pack_scratch);
   float* inv = reinterpret_cast<float*>(reinterpret_cast<char*>(pack_scratch) +
                                         align_up((int64_t)g->num_rel * kImageBytes, 256));
-  pack_f16_kernel<<<(unsigned)g->num_rel, 256, 0, stream>>>(W_msg, W_self, img, inv);
+  pack_f16_kernel<<<(unsigned)g->num_rel, 256, 0, stream>>>(W_msg, W_self, img, inv, transposed ? 1 : 0);
   GHF_LAUNCH_CHECK();
   return 0;
 }
@@ -627,7 +645,7 @@ int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool 
 }
 
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
-                  const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc) {
+                  const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc, int skip_half) {
   GHF_REQUIRE(h16_scale != nullptr, "mp_f16: the fp16 shadow needs its scale words");
   GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
   GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_f16: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
@@ -662,7 +680,7 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
   mp_f16_kernel<P, T><<<(unsigned)grid, threads_for(P), kSmem, stream>>>(                                        \
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,                    \
       reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, \
-      zero_done, (int)g->num_phases, g->sb_nodes, g->num_local, env_flags() | (keep_acc ? kFlagNoClear : 0u), trace)
+      zero_done, (int)g->num_phases, g->sb_nodes, g->num_local, env_flags() | (keep_acc ? kFlagNoClear : 0u) | (skip_half == 1 ? kFlagSkipSrc : skip_half == 2 ? kFlagSkipDst : 0u), trace)
   if (trace) GHF_F16_LAUNCH(4, true);
   else if (prod == 8) GHF_F16_LAUNCH(8, false);
   else GHF_F16_LAUNCH(4, false);

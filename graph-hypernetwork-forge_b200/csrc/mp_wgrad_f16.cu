@@ -18,6 +18,8 @@
 //         instruction (a unit's two matrices are 128 KiB of reductions into g_W[r])
 //   4     MMA issuer + TMEM allocator     5  scheduler (unit descriptors through a shared-memory queue)
 //   6-13  row-gather producers (cp.async, zero-fill for the tail rows)
+//   14    bias-gradient warp: column sums of the gathered gradient rows of every stage, read from shared memory
+//         next to the tensor core (g_bias[r] = sum over the unit's edges of g_acc[dst]), one atomic per column and unit
 // TMEM: 2 buffers x (msg 128 + self 128 columns): the epilogue of unit i overlaps the products of unit i + 1.
 #include <cuda_fp16.h>
 
@@ -40,8 +42,9 @@ constexpr int kStageBytes = 3 * kSet;        // h16[src] | h16[dst] | g16[dst]
 constexpr int kStages = 4;
 constexpr int kQueue = 8;
 constexpr int kEpiWarps = 4, kProdWarps = 8;
-constexpr int kWarpMma = kEpiWarps, kWarpSched = kWarpMma + 1, kWarpProd = kWarpSched + 1;
-constexpr int kThreads = 32 * (kWarpProd + kProdWarps);
+constexpr int kWarpMma = kEpiWarps, kWarpSched = kWarpMma + 1, kWarpProd = kWarpSched + 1,
+              kWarpBias = kWarpProd + kProdWarps;
+constexpr int kThreads = 32 * (kWarpBias + 1);
 constexpr int kRowsPerWarp = kT / kProdWarps;   // 8
 constexpr uint32_t kTmemCols = 512;
 constexpr int kXposeBytes = kEpiWarps * 32 * 33 * 4;
@@ -83,7 +86,7 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
                     const int32_t* __restrict__ dst_sorted, const __half* __restrict__ h16, int64_t dst_lo,
                     const float* __restrict__ h_scale, const __half* __restrict__ g16,
                     const float* __restrict__ g_scale, float* __restrict__ gW_msg, float* __restrict__ gW_self,
-                    int* __restrict__ unit_counter, uint32_t flags) {
+                    float* __restrict__ gbias, int* __restrict__ unit_counter, uint32_t flags) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sA = (raw + 1023u) & ~1023u;
@@ -101,7 +104,7 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kConsumers = kEpiWarps + 1 + kProdWarps;
+  constexpr int kConsumers = kEpiWarps + 1 + kProdWarps + 1;
 
   auto q_acquire = [&](uint32_t idx) -> int4 {             // {first sorted edge (-1: done), edges, relation, -}
     mbar_wait(q_full0 + 8u * (idx % kQueue), (idx / kQueue) & 1u);
@@ -118,7 +121,7 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full(s), 32 * kProdWarps);
-      mbar_init(empty(s), 1);
+      mbar_init(empty(s), 2);               // tcgen05.commit + the bias-gradient warp
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full(a), 1);
@@ -170,7 +173,7 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(a));
     }
-  } else if (warp >= kWarpProd) {
+  } else if (warp >= kWarpProd && warp < kWarpBias) {
     // ------------------------------------------------------------------ row-gather producers
     const int pw = warp - kWarpProd;
     const int l16 = lane & 15, hi = lane >> 4;
@@ -258,6 +261,42 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
+  } else if (warp == kWarpBias) {
+    // ------------------------------------------------------------------ bias gradient: column sums of the g rows
+    // lane l owns columns [4l, 4l + 4): chunk l / 16, 16-byte group (l % 16) / 2, half of the group l % 2
+    const uint32_t lane_off = (uint32_t)(2 * kSet + (lane >> 4) * kChunk + 8 * (lane & 1));
+    const int grp = (lane & 15) >> 1;
+    const float gs = g_scale[0];
+    int stage = 0;
+    uint32_t phase = 0;
+    for (uint32_t it = 0;; ++it) {
+      const int4 t = q_acquire(it);
+      if (t.x < 0) break;
+      q_release(it);
+      float sum[4] = {0.f, 0.f, 0.f, 0.f};
+      const int nstages = (t.y + kT - 1) / kT;
+#pragma unroll 1
+      for (int s = 0; s < nstages; ++s) {
+        const int rows = min(kT, t.y - s * kT);
+        mbar_wait(full(stage), phase);
+        const uint32_t base = sA + stage * kStageBytes + lane_off;
+#pragma unroll 4
+        for (int e = 0; e < rows; ++e) {
+          uint32_t lo, hi;
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi)
+                       : "r"(base + e * 128 + ((grp ^ (e & 7)) << 4)));
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+          sum[0] += a.x; sum[1] += a.y; sum[2] += b.x; sum[3] += b.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      float* out = gbias + (int64_t)t.z * kD + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(out + j, sum[j] * gs);
+    }
   } else if (warp == kWarpSched) {
     // ------------------------------------------------------------------ scheduler
     uint32_t qi = 0;
@@ -290,40 +329,6 @@ mp_wgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __res
   if (warp == kWarpMma) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-// g_bias[r] = sum over the edges of relation r of g_acc[dst]: one CTA per unit, thread = 2 columns (fp16 pairs)
-__global__ void __launch_bounds__(64)
-mp_bgrad_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
-                    const int32_t* __restrict__ unit_rel, const int32_t* __restrict__ dst_sorted,
-                    const __half2* __restrict__ g16, const float* __restrict__ g_scale, float* __restrict__ gbias) {
-  const int64_t u = blockIdx.x;
-  const int start = unit_start[u], count = unit_count[u];
-  float sx = 0.f, sy = 0.f;
-  int e = 0;
-  for (; e + 4 <= count; e += 4) {
-    int d[4];
-    __half2 v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d[i] = dst_sorted[start + e + i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = g16[(int64_t)d[i] * (kD / 2) + threadIdx.x];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(v[i]);
-      sx += f.x;
-      sy += f.y;
-    }
-  }
-  for (; e < count; ++e) {
-    const float2 f = __half22float2(g16[(int64_t)dst_sorted[start + e] * (kD / 2) + threadIdx.x]);
-    sx += f.x;
-    sy += f.y;
-  }
-  const float s = g_scale[0];
-  float* out = gbias + (int64_t)unit_rel[u] * kD + 2 * threadIdx.x;
-  atomicAdd(out, sx * s);
-  atomicAdd(out + 1, sy * s);
-}
-
 }  // namespace
 
 // g_W_msg / g_W_self / g_bias must be zero at entry.  h16: [N,128] fp16 shadow of h (+ scale), g16: [local,128] fp16
@@ -347,11 +352,7 @@ int mp_wgrad_f16_launch(const ghf_graph* g, const void* h16, const float* h_scal
   mp_wgrad_f16_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
       reinterpret_cast<const __half*>(h16), g->dst_lo, h_scale, reinterpret_cast<const __half*>(g16), g_scale, gW_msg,
-      gW_self, unit_counter, flags);
-  GHF_LAUNCH_CHECK();
-  mp_bgrad_f16_kernel<<<(unsigned)g->num_units, 64, 0, stream>>>(g->unit_start, g->unit_count, g->unit_rel,
-                                                                g->dst_sorted, reinterpret_cast<const __half2*>(g16),
-                                                                g_scale, gbias);
+      gW_self, gbias, unit_counter, flags);
   GHF_LAUNCH_CHECK();
   return 0;
 }

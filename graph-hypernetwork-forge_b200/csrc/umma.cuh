@@ -37,10 +37,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.  A failed try_wait returns after a
+// few microseconds, so 2^23 spins are tens of seconds - orders of magnitude above any legitimate wait.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-    if (spins > (1u << 26)) __trap();
+    if (spins > (1u << 23)) __trap();
   }
 }
 

@@ -62,7 +62,7 @@ def lib():
         "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
         "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
-        "ghf_mp_contract": (c_int, [P, P, P, P, P, P, P, c_int, P, c_int, P, P]),
+        "ghf_mp_contract": (c_int, [P, P, P, P, P, P, P, c_int, P, c_int, c_int, P, P]),
         "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P, P]),
         "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, P]),
         "ghf_text_encode_backward": (c_int, [P, P, P, c_int64, P, c_int, P, c_int, P, P, P, P, P, P]),
@@ -419,16 +419,19 @@ class Graph:
             self._reversed = rev
         return rev
 
-    def contract(self, x, W_msg, W_self, bias, precision: int, x16=None, out=None, accumulate: bool = False):
+    def contract(self, x, W_msg, W_self, bias, precision: int, x16=None, out=None, accumulate: bool = False,
+                 transposed: bool = False):
         """Raw per-destination sums of x_u W_msg[r] + x_v W_self[r] + bias[r] -> [local nodes, d]; with
-        `accumulate` they are added to `out`."""
+        `accumulate` they are added to `out`.  PREC_F16 at hidden 128 only: `transposed` uses W[r]^T, and W_msg,
+        W_self or bias may be None (zeros; the rows of an absent half are not even gathered)."""
         dev, d = self.device, self.hidden_dim
-        x, W_msg, W_self, bias = _f32(x), _f32(W_msg), _f32(W_self), _f32(bias)
+        x = _f32(x)
         if x.shape != (self.num_nodes, d):
             raise RuntimeError(f"x must be [{self.num_nodes},{d}], got {tuple(x.shape)}")
-        if W_msg.shape != (self.num_rel, d, d) or W_self.shape != (self.num_rel, d, d) or \
-                bias.shape != (self.num_rel, d):
-            raise RuntimeError("relation weights must be [R,d,d], [R,d,d], [R,d]")
+        W_msg, W_self, bias = (None if t is None else _f32(t) for t in (W_msg, W_self, bias))
+        for t, shape in ((W_msg, (self.num_rel, d, d)), (W_self, (self.num_rel, d, d)), (bias, (self.num_rel, d))):
+            if t is not None and t.shape != shape:
+                raise RuntimeError("relation weights must be [R,d,d], [R,d,d], [R,d]")
         if out is None:
             if accumulate:
                 raise RuntimeError("contract: accumulate needs `out`")
@@ -439,8 +442,8 @@ class Graph:
         with torch.cuda.device(dev):
             _check(lib().ghf_mp_contract(self._h, _ptr(x), _ptr(x16.data) if x16 else None,
                                          _ptr(x16.scale) if x16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
-                                         precision, _ptr(out), int(accumulate), _ptr(ws), _stream(dev)),
-                   "ghf_mp_contract")
+                                         precision, _ptr(out), int(accumulate), int(transposed), _ptr(ws),
+                                         _stream(dev)), "ghf_mp_contract")
         return out
 
     def epilogue_backward(self, g_out, upd, h, ln_w, eps: float, want_shadow: bool = False):

@@ -18,11 +18,13 @@ def wants_grad(*tensors) -> bool:
 
 
 class LinearFn(torch.autograd.Function):
-    """y = exp(log_scale) * act(x W^T + b) (ghf_linear).  Backward: three GEMMs through torch.matmul.
+    """y = exp(log_scale) * act(x W^T + b) (ghf_linear).  Backward: three GEMMs through torch.matmul (library
+    GEMMs) - in TF32 when `tf32` is set, i.e. when the model runs a tensor-core precision mode anyway, else fp32.
     `shadow` (a list, optional) receives the fp16 Shadow of y made by the same kernel (the input projection)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, log_scale, relu: bool, shadow):
+    def forward(ctx, x, weight, bias, log_scale, relu: bool, shadow, tf32: bool):
+        ctx.tf32 = bool(tf32)
         if shadow is not None:
             y, y16 = _native.linear(x, weight, bias, relu=relu, log_scale=log_scale, want_f16=True)
             shadow.append(y16)
@@ -37,21 +39,28 @@ class LinearFn(torch.autograd.Function):
     def backward(ctx, g_y):
         x, weight, log_scale, y = ctx.saved_tensors
         g_pre = g_y
-        if ctx.relu:
-            g_pre = g_pre * (y > 0)          # exp(log_scale) > 0: y and the pre-activation share their sign
-        g_ls = None
+        if ctx.relu:      # exp(log_scale) > 0: y and the pre-activation share their sign; one fused pass
+            g_pre = torch.ops.aten.threshold_backward(g_y.contiguous(), y, 0.0)
+        g_ls = alpha = None
         if log_scale is not None:
             if ctx.needs_input_grad[3]:
                 g_ls = (g_y * y).sum().reshape(log_scale.shape)
-            g_pre = g_pre * log_scale.exp()
-        g_x = g_pre @ weight if ctx.needs_input_grad[0] else None
-        g_w = g_pre.t() @ x if ctx.needs_input_grad[1] else None
+            alpha = log_scale.exp()                     # a scalar: applied to the (small) products, not to g_pre
+        allow = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = ctx.tf32
+        try:
+            g_x = g_pre @ weight if ctx.needs_input_grad[0] else None
+            g_w = g_pre.t() @ x if ctx.needs_input_grad[1] else None
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = allow
         g_b = g_pre.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return g_x, g_w, g_b, g_ls, None, None
+        if alpha is not None:
+            g_x, g_w, g_b = (None if t is None else t * alpha for t in (g_x, g_w, g_b))
+        return g_x, g_w, g_b, g_ls, None, None, None
 
 
-def linear(x, weight, bias, relu=False, log_scale=None, shadow=None):
-    return LinearFn.apply(x, weight, bias, log_scale, relu, shadow)
+def linear(x, weight, bias, relu=False, log_scale=None, shadow=None, tf32=False):
+    return LinearFn.apply(x, weight, bias, log_scale, relu, shadow, tf32)
 
 
 class TextEncodeFn(torch.autograd.Function):
@@ -79,14 +88,21 @@ def _contraction_backward(graph, prec, h, W_msg, W_self, g_acc, g16, h16, needs,
     `g_h` (or None): buffer that already holds the other shares of dL/dh; the two contraction terms are added to it.
     -> (g_h, g_W_msg, g_W_self, g_bias)"""
     if needs[0]:
-        zero_w = torch.zeros_like(W_msg)
-        zero_b = torch.zeros(W_msg.shape[:2], dtype=W_msg.dtype, device=W_msg.device)
-        # messages: g_acc_v W_msg[r]^T lands on the SOURCE u - the same contraction over the reversed edges
-        g_h = graph.reversed().contract(g_acc, W_msg.transpose(1, 2).contiguous(), zero_w, zero_b, prec, x16=g16,
-                                        out=g_h, accumulate=g_h is not None)
-        # self-loop: g_acc_v W_self[r]^T summed over v's in-edges stays at v
-        graph.contract(g_acc, zero_w, W_self.transpose(1, 2).contiguous(), zero_b, prec, x16=g16, out=g_h,
-                       accumulate=True)
+        rev = graph.reversed()
+        if prec == _native.PREC_F16 and graph.hidden_dim == 128:
+            # the f16 engine transposes while packing and skips the absent half of K (no zero tensors, no copies)
+            g_h = rev.contract(g_acc, W_msg, None, None, prec, x16=g16, out=g_h, accumulate=g_h is not None,
+                               transposed=True)
+            graph.contract(g_acc, None, W_self, None, prec, x16=g16, out=g_h, accumulate=True, transposed=True)
+        else:
+            zero_w = torch.zeros_like(W_msg)
+            zero_b = torch.zeros(W_msg.shape[:2], dtype=W_msg.dtype, device=W_msg.device)
+            # messages: g_acc_v W_msg[r]^T lands on the SOURCE u - the same contraction over the reversed edges
+            g_h = rev.contract(g_acc, W_msg.transpose(1, 2).contiguous(), zero_w, zero_b, prec, x16=g16, out=g_h,
+                               accumulate=g_h is not None)
+            # self-loop: g_acc_v W_self[r]^T summed over v's in-edges stays at v
+            graph.contract(g_acc, zero_w, W_self.transpose(1, 2).contiguous(), zero_b, prec, x16=g16, out=g_h,
+                           accumulate=True)
     else:
         g_h = None
     g_wm = g_ws = g_b = None

@@ -278,7 +278,11 @@ class HyperGNN(nn.Module):
         N, d = graph.num_nodes, self.hidden_dim
         chain = prec == _native.PREC_F16 and N * d % 8 == 0 and not dropping   # fp16 shadows chained layer to layer
         made = [] if chain else None
-        h = autograd.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True, shadow=made)
+        fast = prec != _native.PREC_FP32             # tensor-core precision mode: the backward GEMMs may use TF32
+        for gen in self.weight_generators:
+            gen.grad_tf32 = fast
+        h = autograd.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True, shadow=made,
+                            tf32=fast)
         h16 = made[0] if chain else None
         text_embs = self.text_encoder.encode_packed(packed)
         if taps is not None:

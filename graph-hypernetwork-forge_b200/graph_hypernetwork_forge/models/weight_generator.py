@@ -36,6 +36,7 @@ class WeightGenerator(nn.Module):
         self.text_dim, self.d_in, self.d_out = text_dim, d_in, d_out
         self.init_scale = init_scale
         self._dropout = float(dropout)
+        self.grad_tf32 = False     # backward GEMMs of the MLPs in TF32 (HyperGNN sets it in tensor-core precision modes)
         self._shapes = {"W_msg": (d_in, d_out), "W_self": (d_in, d_out), "bias": (d_out,)}
 
         # Parameter creation order matters: with the same torch seed the drop-in must draw the
@@ -65,10 +66,13 @@ class WeightGenerator(nn.Module):
         linears = [i for i, m in enumerate(mods) if isinstance(m, nn.Linear)]
         ls = self.log_scales[kind]
         grad = autograd.wants_grad(x, ls, *self.generators[kind].parameters())
-        run = autograd.linear if grad else _native.linear
         for pos, i in enumerate(linears):
             last = pos == len(linears) - 1
-            x = run(x, mods[i].weight, mods[i].bias, relu=not last, log_scale=ls if last else None)
+            if grad:
+                x = autograd.linear(x, mods[i].weight, mods[i].bias, relu=not last, log_scale=ls if last else None,
+                                    tf32=self.grad_tf32)
+            else:
+                x = _native.linear(x, mods[i].weight, mods[i].bias, relu=not last, log_scale=ls if last else None)
             if not last and self.training and self._dropout > 0.0:
                 x = nn.functional.dropout(x, self._dropout)       # the Dropout module after each hidden ReLU
         return x

@@ -145,10 +145,13 @@ int ghf_convert_f16(const float* d_x, int64_t elems, void* d_y16, float* d_scale
  * It is the forward kernel, and it is also the gradient w.r.t. h: with x = g_acc and the relation matrices
  * transposed, on the graph built from the REVERSED edge list (W_self = 0) it yields the message term, on the
  * graph itself (W_msg = 0) the self-loop term.  (d_x16, d_x16_scale) as in ghf_mp_layer_f16.  accumulate != 0: the
- * sums are ADDED to what d_acc holds (the three shares of dL/dh land in one buffer without extra passes). */
+ * sums are ADDED to what d_acc holds (the three shares of dL/dh land in one buffer without extra passes).
+ * With precision GHF_PREC_F16 (hidden 128): transposed != 0 reads the relation matrices as W[r]^T while packing (no
+ * transposed copy), and d_W_msg, d_W_self or d_bias may be NULL (zeros) - the rows of an absent half are neither
+ * gathered nor multiplied. */
 int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void* d_x16, const float* d_x16_scale,
                     const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
-                    float* d_acc, int accumulate, void* d_workspace, void* stream);
+                    float* d_acc, int accumulate, int transposed, void* d_workspace, void* stream);
 /* Undo LayerNorm, ReLU and the mean (HG:212-213, 289-296) for rows [dst_lo, dst_hi): from d_g_out = dL/d out,
  * the saved pre-residual update d_upd (ghf_mp_layer's tap) and d_h:
  *   d_g_pre = dL/d(upd + h)  (also the residual's share of dL/dh),  d_g_acc = d_g_pre / max(indeg, 1),

@@ -179,6 +179,10 @@ def test_c3_wikikg2_shape_full_size_gradients_sampled():
     g_h = graph.reversed().contract(g_acc, W_msg.transpose(1, 2).contiguous(), zero_w, zero_b, _native.PREC_F16)
     graph.contract(g_acc, zero_w, W_self.transpose(1, 2).contiguous(), zero_b, _native.PREC_F16, out=g_h,
                    accumulate=True)
+    # the same through the engine's own transposition and half-skipping (what autograd.py uses at hidden 128)
+    g_h2 = graph.reversed().contract(g_acc, W_msg, None, None, _native.PREC_F16, transposed=True)
+    graph.contract(g_acc, None, W_self, None, _native.PREC_F16, out=g_h2, accumulate=True, transposed=True)
+    assert float((g_h - g_h2).abs().max()) <= 1e-5 * float(g_h.abs().max()), "transposed/NULL-half contraction"
     sample = torch.unique(torch.randint(0, N, (256,), generator=gen, device=DEV))
     want = torch.zeros(sample.numel(), d, dtype=torch.float64, device=DEV)
     out_e = torch.isin(src, sample).nonzero().squeeze(1)          # messages sent by the sampled nodes
