@@ -266,3 +266,44 @@ def test_reference_shaped_message_passing_is_differentiable():
         grads.append([out.detach()] + [t.grad for t in (h, Wm, Ws, b)])
     for name, a, b_ in zip(("out", "g_h", "g_W_msg", "g_W_self", "g_bias"), *grads):
         assert_rel_to_max(a.cpu().numpy(), b_.cpu().numpy(), 2e-4, name)
+
+
+def test_backward_without_edges_and_with_frozen_parameters():
+    """No edges at all: the layers reduce to LN(relu(h)) and only the projection / LayerNorm parameters receive a
+    gradient; and with every parameter frozen the gradient w.r.t. the node features still flows."""
+    from graph_hypernetwork_forge import HyperGNN
+    torch.manual_seed(4)
+    model = HyperGNN(16, 8, 32, 2, precision="fp32").to(DEV)
+    x = torch.randn(6, 8, device=DEV, requires_grad=True)
+    out = model(x, torch.zeros(2, 0, dtype=torch.long, device=DEV), [])
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    ref_h = torch.relu(x.detach() @ model.input_proj.weight.T + model.input_proj.bias)
+    for ln in model.layer_norms:
+        ref_h = torch.nn.functional.layer_norm(torch.relu(ref_h), (32,), ln.weight, ln.bias, ln.eps)
+    assert_rel_to_max(out.detach().cpu().numpy(), ref_h.detach().cpu().numpy(), 1e-5, "no-edge forward")
+    assert model.input_proj.weight.grad is not None and float(model.input_proj.weight.grad.abs().max()) > 0
+    assert x.grad is not None and bool(torch.isfinite(x.grad).all())
+
+    kg_ei = torch.tensor([[0, 1, 2, 3, 4], [1, 2, 3, 4, 5]], device=DEV)
+    model.requires_grad_(False)
+    model.zero_grad(set_to_none=True)
+    x2 = torch.randn(6, 8, device=DEV, requires_grad=True)
+    out2 = model(x2, kg_ei, ["a", "b", "a", "c", "b"])
+    (out2 * w).sum().backward()
+    assert x2.grad is not None and float(x2.grad.abs().max()) > 0
+    assert all(p.grad is None for p in model.parameters())
+
+
+def test_example_training_script_runs():
+    """examples/train_link_prediction.py: the reference's demo flow (train with a margin loss, zero-shot relation)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples",
+                        "train_link_prediction.py")
+    spec = importlib.util.spec_from_file_location("train_link_prediction", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    losses, zero_shot = mod.main(steps=15, verbose=False)
+    assert all(l == l for l in losses) and losses[-1] <= losses[0] * 2
+    assert zero_shot.shape == (8, 32) and bool(torch.isfinite(zero_shot).all())
