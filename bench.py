@@ -241,8 +241,8 @@ def main():
 
     precision = args.precision
     if precision == "auto":
-        precision = "f16" if w["d"] == 128 else "tf32"
-    if w["d"] not in (32, 64, 128):
+        precision = "f16" if w["d"] in (128, 256) else "tf32"
+    if w["d"] not in (32, 64, 128, 256):
         precision = "fp32"
     model = build_model(w, device, precision)
     x, edge_index, _rel, utf8, offsets = make_device_inputs(w, device, skew=args.skew)
@@ -320,7 +320,7 @@ def main():
             traffic = json.load(f).get(f"{args.workload}:{precision}")
     except Exception:
         pass
-    kernel_name = {"f16": "mp_f16_kernel", "tf32": "mp_umma_ts_kernel" if d == 128 else f"mp_umma_kernel<{d}>",
+    kernel_name = {"f16": "mp_f16_kernel" if d == 128 else "mp_f16_ss_kernel", "tf32": "mp_umma_ts_kernel" if d == 128 else f"mp_umma_kernel<{d}>",
                    "fp32": "mp_fp32_kernel"}[precision]
     roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

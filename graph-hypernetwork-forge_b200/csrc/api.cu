@@ -174,7 +174,7 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
   if (int rc = ghf_dedup_texts(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream)) return rc;
-  const int prec = (desc->precision == GHF_PREC_F16 && d == 128) ? GHF_PREC_F16
+  const int prec = (desc->precision == GHF_PREC_F16 && (d == 128 || d == 256)) ? GHF_PREC_F16
                    : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
                                                                                            : GHF_PREC_FP32;
   // second arena: everything whose size depends on the number of distinct relations
@@ -249,7 +249,7 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
 
   float* cur = h0;
   float* nxt = h1;
-  void* cur16 = prec == GHF_PREC_F16 ? h16_0 : nullptr;   // fp16 shadow of `cur` and its scale words
+  void* cur16 = want_f16 ? h16_0 : nullptr;   // fp16 shadow of `cur` and its scale words (chained at hidden 128)
   void* nxt16 = h16_1;
   float* cur_sc = scales;
   float* nxt_sc = scales + 2;
@@ -260,7 +260,7 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
       return rc;
     }
     // HG:286-296
-    void* out16 = (prec == GHF_PREC_F16 && l + 1 < L) ? nxt16 : nullptr;
+    void* out16 = (want_f16 && l + 1 < L) ? nxt16 : nullptr;
     float* dst = l + 1 < L ? nxt : d_out;                // the last layer writes the caller's buffer
     if (int rc = ghf_mp_layer_f16(g, cur, cur16, cur16 ? cur_sc : nullptr, outs[l][0], outs[l][1], outs[l][2],
                                   layers[l].ln_w, layers[l].ln_b, desc->ln_eps, prec, dst, out16,

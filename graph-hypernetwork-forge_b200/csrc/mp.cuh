@@ -46,6 +46,14 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
                   const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc = false,
                   int skip_half = 0);   // skip_half: 1 = no source term (W_msg NULL), 2 = no destination term
 
+// hidden_dim 256 with streamed fp16 weights (mp_f16_ss.cu): operand images [R][256 KiB] + inverse scales [R];
+// acc must be zero at entry, `unit_counter` one zeroed int
+bool mp_f16ss_supported(int hidden_dim);
+int64_t mp_f16ss_pack_bytes(int num_rel);
+int mp_f16ss_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream);
+int mp_f16ss_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
+                    const void* pack_scratch, int* unit_counter, cudaStream_t stream);
+
 // gradients of the generated relation tensors on tcgen05 (mp_wgrad_f16.cu, hidden_dim 128): g_W_msg[r] / g_W_self[r] /
 // g_bias[r] += sums over the edges of r (buffers zero at entry); h16 / g16 are fp16 shadows with their scale words.
 int mp_wgrad_f16_launch(const ghf_graph* g, const void* h16, const float* h_scale, const void* g16,

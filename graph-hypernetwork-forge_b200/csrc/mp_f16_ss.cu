@@ -1,0 +1,368 @@
+// mp_f16_ss.cu — message-passing contraction for hidden_dim 256 on tcgen05 kind::f16 with STREAMED weights
+// (GHF_PREC_F16; BASELINE config 4: 20k relation texts, ~100 edges per relation, 10.5 GB of generated fp32 weights
+// per layer).
+//
+// At hidden 256 one relation's operand [W_msg[r]; W_self[r]] is 512 x 256 values: 256 KiB even as fp16 - more than
+// shared memory, twice tensor memory.  And with ~100 edges per relation every tile needs a different one.  So the
+// weights are not resident anywhere: for every 128-edge tile
+//     D[128 edges, 256] = A[128, 512] * B_r[512, 256]      (fp16 operands, fp32 accumulation in TMEM)
+// runs over 8 K-chunks of 64, and a pipeline stage carries BOTH operands of one chunk:
+//     A chunk: 128 gathered half-rows of h16 (cp.async, 128 B each, 128B-swizzled)                     16 KiB
+//     B chunk: 256 x 64 halfs of relation r's pre-swizzled image (cp.async.bulk, contiguous 32 KiB)    32 KiB
+// 4 stages = 192 KiB.  The kernel is bound by the weight stream (256 KiB per tile): at c4 5.2 GB per layer instead of
+// the 10.5 GB of fp32 weights the CUDA-core kernel reads - and on tensor cores instead of 524 GFLOP of FFMA.
+// Scales as in mp_f16.cu: h16 = fp16(h * 2^k), image = fp16(W_r * 2^k_r), the epilogue multiplies by 2^-(k + k_r).
+//
+// Warp roles (320 threads, 1 CTA / SM, persistent; the layout of mp_umma.cu):
+//   0-3  epilogue (TMEM -> 32x32 transposes through shared memory -> red.global.add.v4.f32 rows of acc[dst])
+//   4-7  A producers (row gather)      8  MMA issuer + TMEM allocator
+//   9    unit scheduler (one unit AHEAD of the loads) + B loader (bulk copies)
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "mp.cuh"
+#include "umma.cuh"
+
+namespace ghf {
+namespace {
+
+using namespace ptx;
+
+constexpr int kD = 256;
+constexpr int kTileM = 128;
+constexpr int kChunks = 2 * kD / 64;              // 8 K-chunks of 64 halfs (one 128 B swizzle row)
+constexpr int kHalfChunks = kChunks / 2;          // chunks taken from h16[src]; the rest from h16[dst]
+constexpr int kABytes = kTileM * 128;             // 16 KiB
+constexpr int kBBytes = kD * 128;                 // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kStages = 4;
+constexpr int kStaging = 4 * 32 * 128;            // 4 epilogue warps x (32 rows x 32 fp32)
+constexpr int kQueue = 4;
+constexpr int kThreads = 320;
+constexpr uint32_t kTmemCols = 2 * kD;            // two accumulators
+constexpr int kSmem = 1024 + kStages * kStageBytes + kStaging + 512;
+constexpr int64_t kImageBytes = (int64_t)kChunks * kBBytes;   // 256 KiB per relation
+
+// kind::f16: D fp32, A and B fp16, both K-major, M = 128, N = 256
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kD >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// element (n, k) of relation r's operand image (k < D -> W_msg[r][k][n], else W_self[r][k-D][n]): chunk k/64, row n,
+// 16-byte group (k%64)/8 swizzled by n%8 - what the K-major SWIZZLE_128B descriptor expects for N rows of 128 B
+__device__ __forceinline__ int64_t image_offset_bytes(int n, int k) {
+  const int c = k >> 6, kk = k & 63;
+  return (int64_t)c * kBBytes + (int64_t)n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1));
+}
+
+// One CTA per relation: max |W| -> power-of-two scale -> scaled fp16 image (see pack_f16_kernel in mp_f16.cu).
+__global__ void __launch_bounds__(256)
+pack_f16_ss_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_self, uint8_t* __restrict__ pack,
+                   float* __restrict__ inv_scale) {
+  __shared__ float s_max[8];
+  __shared__ float s_scale;
+  const int64_t r = blockIdx.x;
+  float m = 0.f;
+  for (int which = 0; which < 2; ++which) {
+    const float4* w4 = reinterpret_cast<const float4*>((which ? W_self : W_msg) + r * kD * kD);
+    for (int i = threadIdx.x; i < kD * kD / 4; i += 256) {
+      const float4 a = w4[i];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = 0.f;
+    for (int i = 0; i < 8; ++i) mm = fmaxf(mm, s_max[i]);
+    int e = 0;
+    float scale = 1.f;
+    if (mm > 0.f && isfinite(mm)) {
+      frexpf(mm, &e);
+      e = 15 - e;                                  // mm * 2^(15-e) in [2^14, 2^15)
+      e = e > 100 ? 100 : (e < -100 ? -100 : e);
+      scale = ldexpf(1.f, e);
+    }
+    s_scale = scale;
+    inv_scale[r] = 1.f / scale;
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  uint8_t* img = pack + r * kImageBytes;
+  // thread = (8 consecutive k, one n): lanes walk n (coalesced 128 B reads of one W row), one 16 B store each
+  for (int i = threadIdx.x; i < (2 * kD / 8) * kD; i += 256) {
+    const int n = i % kD, k0 = (i / kD) * 8;
+    const float* src = k0 < kD ? W_msg + (r * kD + k0) * kD + n : W_self + (r * kD + (k0 - kD)) * kD + n;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 p = __floats2half2_rn(src[(2 * j) * kD] * scale, src[(2 * j + 1) * kD] * scale);
+      w[j] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+    *reinterpret_cast<uint4*>(img + image_offset_bytes(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mp_f16_ss_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
+                 const int32_t* __restrict__ unit_rel, int64_t num_units, const int32_t* __restrict__ src_sorted,
+                 const int32_t* __restrict__ dst_sorted, const __half* __restrict__ h16, int64_t dst_lo,
+                 const float* __restrict__ h_scale, const uint8_t* __restrict__ wpack,
+                 const float* __restrict__ w_inv_scale, const float* __restrict__ bias, float* __restrict__ acc,
+                 int* __restrict__ unit_counter) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sS = (raw + 1023u) & ~1023u;              // stages: [A chunk 16 KiB | B chunk 32 KiB]
+  const uint32_t sStg = sS + kStages * kStageBytes;
+  const uint32_t sBar = sStg + kStaging;
+  auto full = [&](int s) { return sBar + 8u * s; };
+  auto empty = [&](int s) { return sBar + 8u * (kStages + s); };
+  auto acc_full = [&](int a) { return sBar + 8u * (2 * kStages + a); };
+  auto acc_empty = [&](int a) { return sBar + 8u * (2 * kStages + 2 + a); };
+  const uint32_t q_full0 = sBar + 8u * (2 * kStages + 4);
+  const uint32_t q_empty0 = q_full0 + 8u * kQueue;
+  const uint32_t q_slots = q_empty0 + 8u * kQueue;
+  const uint32_t tmem_slot = q_slots + 4u * kQueue;
+  volatile int32_t* q_slot_ptr = reinterpret_cast<volatile int32_t*>(smem_raw + (q_slots - raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // unit queue: the scheduler publishes unit ids; 4 epilogue warps + 4 producer warps + the MMA thread consume each
+  int q_idx = 0;
+  uint32_t q_phase = 0;
+  auto next_unit = [&](bool whole_warp) -> int {
+    mbar_wait(q_full0 + 8u * q_idx, q_phase);
+    const int u = q_slot_ptr[q_idx];
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) mbar_arrive(q_empty0 + 8u * q_idx);
+    if (++q_idx == kQueue) { q_idx = 0; q_phase ^= 1u; }
+    return u;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 128 + 1);  // every producer thread (cp.async completion) + the loader's expect_tx arrival
+      mbar_init(empty(s), 1);       // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 128);
+    }
+    for (int q = 0; q < kQueue; ++q) {
+      mbar_init(q_full0 + 8u * q, 1);
+      mbar_init(q_empty0 + 8u * q, 9);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ epilogue
+    float4* stg = reinterpret_cast<float4*>(smem_raw + (sStg - raw) + warp * 4096);
+    const int cj = lane & 7;
+    const float h_inv = h_scale[0];
+    uint32_t it = 0;
+    for (int u = next_unit(true); u >= 0; u = next_unit(true)) {
+      const int start = unit_start[u], count = unit_count[u];
+      const int64_t rel = unit_rel[u];
+      const float inv = w_inv_scale[rel] * h_inv;
+      for (int t0 = 0; t0 < count; t0 += kTileM, ++it) {
+        const int a = it & 1;
+        const int rows = min(kTileM, count - t0);
+        const int my_row = warp * 32 + lane;
+        const int my_dst = my_row < rows ? dst_sorted[start + t0 + my_row] : -1;
+        mbar_wait(acc_full(a), (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < kD / 32; ++cc) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + rel * kD + cc * 32 + 4 * cj);
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kD + cc * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            stg[lane * 8 + (j ^ (lane & 7))] =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            const int dsti = __shfl_sync(0xffffffffu, my_dst, rr);
+            float4 v = stg[rr * 8 + (cj ^ (rr & 7))];
+            if (dsti >= 0) {
+              v.x = fmaf(v.x, inv, b4.x); v.y = fmaf(v.y, inv, b4.y);
+              v.z = fmaf(v.z, inv, b4.z); v.w = fmaf(v.w, inv, b4.w);
+              red_add_v4(acc + (int64_t)dsti * kD + cc * 32 + 4 * cj, v);
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty(a));
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ A producers (half-rows of h16)
+    const int pw = warp - 4;
+    const int cj = lane & 7;
+    const uint8_t* hb = reinterpret_cast<const uint8_t*>(h16) + cj * 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = next_unit(true); u >= 0; u = next_unit(true)) {
+      const int start = unit_start[u], count = unit_count[u];
+      for (int t0 = 0; t0 < count; t0 += kTileM) {
+        const int rows = min(kTileM, count - t0);
+        const int my_row = pw * 32 + lane;
+        const bool ok = my_row < rows;
+        const int64_t my_src = ok ? (int64_t)src_sorted[start + t0 + my_row] : -1;
+        const int64_t my_dst = ok ? dst_lo + dst_sorted[start + t0 + my_row] : -1;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          const bool from_src = c < kHalfChunks;
+          const int64_t mine = from_src ? my_src : my_dst;
+          const int col_bytes = (from_src ? c : c - kHalfChunks) * 128;
+          const uint32_t dst_base = sS + stage * kStageBytes;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            const int64_t idx = __shfl_sync(0xffffffffu, mine, rr);
+            const int row = pw * 32 + rr;
+            const uint32_t to = dst_base + row * 128 + ((cj ^ (row & 7)) << 4);
+            if (idx >= 0) cp_async_16(to, hb + idx * (kD * 2) + col_bytes);
+          }
+          cp_async_arrive_noinc(full(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int u = next_unit(false); u >= 0; u = next_unit(false)) {
+        const int count = unit_count[u];
+        for (int t0 = 0; t0 < count; t0 += kTileM, ++it) {
+          const int a = it & 1;
+          mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * kD);
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c) {
+            mbar_wait(full(stage), phase);
+            fence_proxy_async();
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_k128(sS + stage * kStageBytes);
+            const uint64_t bdesc = umma_desc_k128(sS + stage * kStageBytes + kABytes);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_f16_ss(d_tmem, adesc + 2 * j, bdesc + 2 * j, kIdesc, (c | j) != 0);
+            umma_commit(empty(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(acc_full(a));
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ unit scheduler + B loader
+    if (lane == 0) {
+      uint32_t sphase = 0, phase = 0;
+      int sq = 0, stage = 0;
+      auto publish = [&](int64_t u) {
+        mbar_wait(q_empty0 + 8u * sq, sphase ^ 1u);
+        q_slot_ptr[sq] = u >= num_units ? -1 : (int)u;
+        mbar_arrive(q_full0 + 8u * sq);
+        if (++sq == kQueue) { sq = 0; sphase ^= 1u; }
+      };
+      int64_t u = atomicAdd(unit_counter, 1);
+      publish(u);
+      while (u < num_units) {
+        const int64_t u_next = atomicAdd(unit_counter, 1);   // the other roles learn the next unit while this one loads
+        publish(u_next);
+        const int count = unit_count[u];
+        const uint8_t* img = wpack + (int64_t)unit_rel[u] * kImageBytes;
+        for (int t0 = 0; t0 < count; t0 += kTileM) {
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c) {
+            mbar_wait(empty(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full(stage), kBBytes);
+            const uint32_t to = sS + stage * kStageBytes + kABytes;
+            bulk_g2s(to, img + (int64_t)c * kBBytes, kBBytes / 2, full(stage));
+            bulk_g2s(to + kBBytes / 2, img + (int64_t)c * kBBytes + kBBytes / 2, kBBytes / 2, full(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        u = u_next;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace
+
+bool mp_f16ss_supported(int d) { return d == kD; }
+
+int64_t mp_f16ss_pack_bytes(int num_rel) {
+  return align_up((int64_t)num_rel * kImageBytes, 256) + align_up((int64_t)num_rel * 4, 256);
+}
+
+int mp_f16ss_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch,
+                  cudaStream_t stream) {
+  GHF_REQUIRE(g->hidden_dim == kD, "mp_f16_ss: hidden_dim must be %d", kD);
+  GHF_REQUIRE((reinterpret_cast<uintptr_t>(W_msg) | reinterpret_cast<uintptr_t>(W_self) |
+               reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
+              "mp_f16_ss: W_msg / W_self / scratch must be 16-byte aligned");
+  uint8_t* img = reinterpret_cast<uint8_t*>(pack_scratch);
+  float* inv = reinterpret_cast<float*>(img + align_up((int64_t)g->num_rel * kImageBytes, 256));
+  pack_f16_ss_kernel<<<(unsigned)g->num_rel, 256, 0, stream>>>(W_msg, W_self, img, inv);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+// acc (zero at entry) += the tiles' products; `unit_counter`: one zeroed int
+int mp_f16ss_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
+                    const void* pack_scratch, int* unit_counter, cudaStream_t stream) {
+  GHF_REQUIRE(g->hidden_dim == kD, "mp_f16_ss: hidden_dim must be %d", kD);
+  GHF_REQUIRE(h16_scale != nullptr, "mp_f16_ss: the fp16 shadow needs its scale words");
+  GHF_REQUIRE(g->unit_edges % kTileM == 0, "mp_f16_ss: unit_edges=%d must be a multiple of %d", g->unit_edges, kTileM);
+  GHF_REQUIRE((reinterpret_cast<uintptr_t>(h16) | reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(bias) |
+               reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
+              "mp_f16_ss: h16 / acc / bias / scratch must be 16-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(pack_scratch);
+  const float* inv = reinterpret_cast<const float*>(img + align_up((int64_t)g->num_rel * kImageBytes, 256));
+  const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
+  mp_f16_ss_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(
+      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
+      reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ghf

@@ -85,7 +85,7 @@ class ShardedForward:
         N, d = self.num_nodes, m.hidden_dim
         prec = m._precision_code()
         cur, nxt = self._buffers(node_features.device, d)
-        if prec == _native.PREC_F16:
+        if prec == _native.PREC_F16 and d == 128:
             return self._forward_f16(graph, packed, _started or self._start_h0(node_features))
         with torch.no_grad():
             # every rank projects all nodes (h is needed in full as the gather source)
@@ -109,7 +109,7 @@ class ShardedForward:
         from . import _native
         m = self.model
         N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
-        if m._precision_code() != _native.PREC_F16:
+        if m._precision_code() != _native.PREC_F16 or d != 128:      # fp16 shadows are chained at hidden 128 only
             return None
         cur, nxt = self._buffers(node_features.device, d)
         cur16, nxt16 = self._buffers16(node_features.device, d)

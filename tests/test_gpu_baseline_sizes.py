@@ -133,15 +133,21 @@ def test_c5_large_shape_scaled_tf32_hidden64():
     sampled_update_check(taps, ei, 256, TF32_UPD_REL)
 
 
-def test_c4_zero_shot_shape_scaled_fp32_hidden256():
-    """BASELINE config 4's shape (hidden 256, 1 relation text per 100 edges) at 1/10 scale, fp32 path."""
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("f16", TF32_UPD_REL)])
+def test_c4_zero_shot_shape_scaled_hidden256(precision, tol):
+    """BASELINE config 4's shape (hidden 256, 1 relation text per 100 edges) at 1/10 scale: the fp32 path and the
+    f16 path with streamed weights (mp_f16_ss_kernel), which must also agree with each other on the final h."""
     N, E, R, d, L, T, F = 10_000, 200_000, 2_000, 256, 2, 64, 256
     x, ei, rel, utf8, offsets = synthetic_on_device(N, E, R, F, seed=4)
-    model = build(T, F, d, L, "fp32")
+    model = build(T, F, d, L, precision)
     taps = {}
     out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N), taps=taps)
     assert bool(torch.isfinite(out).all()) and int(taps["in_degree"].sum()) == E
-    sampled_update_check(taps, ei, 128, 1e-4)
+    sampled_update_check(taps, ei, 128, tol)
+    if precision == "f16":
+        ref = build(T, F, d, L, "fp32")
+        want = ref.forward_prepared(x, ref.prepare_packed(ei, utf8, offsets, N))
+        assert float((out - want).abs().max()) <= TF32_H_ATOL_SCALE1
 
 
 @pytest.mark.grad
