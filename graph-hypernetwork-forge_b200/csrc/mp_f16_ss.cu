@@ -66,52 +66,61 @@ __device__ __forceinline__ int64_t image_offset_bytes(int n, int k) {
 }
 
 // One CTA per relation: max |W| -> power-of-two scale -> scaled fp16 image (see pack_f16_kernel in mp_f16.cu).
-__global__ void __launch_bounds__(256)
+// A relation is 512 KiB of fp32 and is read twice (range, then conversion).  1024 threads and ONE CTA per SM (the
+// launch asks for shared memory it does not use): 148 relations = 76 MB are in flight, so the second read hits L2 and
+// HBM sees the weights once.
+constexpr int kPackThreads = 1024;
+constexpr int kPackSmem = 160 * 1024;
+__global__ void __launch_bounds__(kPackThreads, 1)
 pack_f16_ss_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_self, uint8_t* __restrict__ pack,
-                   float* __restrict__ inv_scale) {
-  __shared__ float s_max[8];
+                   float* __restrict__ inv_scale, int num_rel) {
+  __shared__ float s_max[kPackThreads / 32];
   __shared__ float s_scale;
-  const int64_t r = blockIdx.x;
-  float m = 0.f;
-  for (int which = 0; which < 2; ++which) {
-    const float4* w4 = reinterpret_cast<const float4*>((which ? W_self : W_msg) + r * kD * kD);
-    for (int i = threadIdx.x; i < kD * kD / 4; i += 256) {
-      const float4 a = w4[i];
-      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+  for (int64_t r = blockIdx.x; r < num_rel; r += gridDim.x) {
+    float m = 0.f;
+    for (int which = 0; which < 2; ++which) {
+      const float4* w4 = reinterpret_cast<const float4*>((which ? W_self : W_msg) + r * kD * kD);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < kD * kD / 4; i += kPackThreads) {
+        const float4 a = __ldcg(w4 + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+      }
     }
-  }
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float mm = 0.f;
-    for (int i = 0; i < 8; ++i) mm = fmaxf(mm, s_max[i]);
-    int e = 0;
-    float scale = 1.f;
-    if (mm > 0.f && isfinite(mm)) {
-      frexpf(mm, &e);
-      e = 15 - e;                                  // mm * 2^(15-e) in [2^14, 2^15)
-      e = e > 100 ? 100 : (e < -100 ? -100 : e);
-      scale = ldexpf(1.f, e);
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    __syncthreads();                             // s_max / s_scale of the previous relation are no longer read
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float mm = 0.f;
+      for (int i = 0; i < kPackThreads / 32; ++i) mm = fmaxf(mm, s_max[i]);
+      int e = 0;
+      float scale = 1.f;
+      if (mm > 0.f && isfinite(mm)) {
+        frexpf(mm, &e);
+        e = 15 - e;                                // mm * 2^(15-e) in [2^14, 2^15)
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+        scale = ldexpf(1.f, e);
+      }
+      s_scale = scale;
+      inv_scale[r] = 1.f / scale;
     }
-    s_scale = scale;
-    inv_scale[r] = 1.f / scale;
-  }
-  __syncthreads();
-  const float scale = s_scale;
-  uint8_t* img = pack + r * kImageBytes;
-  // thread = (8 consecutive k, one n): lanes walk n (coalesced 128 B reads of one W row), one 16 B store each
-  for (int i = threadIdx.x; i < (2 * kD / 8) * kD; i += 256) {
-    const int n = i % kD, k0 = (i / kD) * 8;
-    const float* src = k0 < kD ? W_msg + (r * kD + k0) * kD + n : W_self + (r * kD + (k0 - kD)) * kD + n;
-    uint32_t w[4];
+    __syncthreads();
+    const float scale = s_scale;
+    uint8_t* img = pack + r * kImageBytes;
+    // thread = (8 consecutive k, one n): lanes walk n (coalesced 128 B reads of one W row), one 16 B store each
+#pragma unroll 2
+    for (int i = threadIdx.x; i < (2 * kD / 8) * kD; i += kPackThreads) {
+      const int n = i % kD, k0 = (i / kD) * 8;
+      const float* src = k0 < kD ? W_msg + (r * kD + k0) * kD + n : W_self + (r * kD + (k0 - kD)) * kD + n;
+      uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __half2 p = __floats2half2_rn(src[(2 * j) * kD] * scale, src[(2 * j + 1) * kD] * scale);
-      w[j] = *reinterpret_cast<const uint32_t*>(&p);
+      for (int j = 0; j < 4; ++j) {
+        const __half2 p = __floats2half2_rn(__ldcg(src + (2 * j) * kD) * scale, __ldcg(src + (2 * j + 1) * kD) * scale);
+        w[j] = *reinterpret_cast<const uint32_t*>(&p);
+      }
+      *reinterpret_cast<uint4*>(img + image_offset_bytes(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    *reinterpret_cast<uint4*>(img + image_offset_bytes(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -336,7 +345,13 @@ int mp_f16ss_pack(const ghf_graph* g, const float* W_msg, const float* W_self, v
               "mp_f16_ss: W_msg / W_self / scratch must be 16-byte aligned");
   uint8_t* img = reinterpret_cast<uint8_t*>(pack_scratch);
   float* inv = reinterpret_cast<float*>(img + align_up((int64_t)g->num_rel * kImageBytes, 256));
-  pack_f16_ss_kernel<<<(unsigned)g->num_rel, 256, 0, stream>>>(W_msg, W_self, img, inv);
+  static bool configured = false;
+  if (!configured) {
+    GHF_CUDA(cudaFuncSetAttribute(pack_f16_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackSmem));
+    configured = true;
+  }
+  const int grid = g->num_rel < sm_count() ? g->num_rel : sm_count();
+  pack_f16_ss_kernel<<<(unsigned)grid, kPackThreads, kPackSmem, stream>>>(W_msg, W_self, img, inv, g->num_rel);
   GHF_LAUNCH_CHECK();
   return 0;
 }
