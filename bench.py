@@ -241,7 +241,7 @@ def main():
 
     precision = args.precision
     if precision == "auto":
-        precision = "f16" if w["d"] in (128, 256) else "tf32"
+        precision = "f16" if w["d"] in (64, 128, 256) else "tf32"
     if w["d"] not in (32, 64, 128, 256):
         precision = "fp32"
     model = build_model(w, device, precision)

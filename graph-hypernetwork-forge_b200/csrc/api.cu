@@ -153,7 +153,7 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
     }
   }
 
-  const bool want_f16 = desc->precision == GHF_PREC_F16 && d == 128;
+  const bool want_f16 = desc->precision == GHF_PREC_F16 && (d == 128 || d == 64);   // shadows chained layer to layer
   std::lock_guard<std::mutex> lock(g_forward_lock);
   int dev = 0;
   GHF_CUDA(cudaGetDevice(&dev));
@@ -174,7 +174,7 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
   if (int rc = ghf_dedup_texts(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream)) return rc;
-  const int prec = (desc->precision == GHF_PREC_F16 && (d == 128 || d == 256)) ? GHF_PREC_F16
+  const int prec = (desc->precision == GHF_PREC_F16 && (d == 64 || d == 128 || d == 256)) ? GHF_PREC_F16
                    : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
                                                                                            : GHF_PREC_FP32;
   // second arena: everything whose size depends on the number of distinct relations

@@ -320,7 +320,7 @@ extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim
   if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim);
   if (precision == GHF_PREC_F16)  // sync words, weight images, the fp16 copy of h made when the caller passes none
     bytes += mp_f16_sync_bytes(g) +
-             (mp_f16ss_supported(hidden_dim) ? mp_f16ss_pack_bytes(g->num_rel) : mp_f16_pack_bytes(g->num_rel)) +
+             (mp_f16ss_supported(hidden_dim) ? mp_f16ss_pack_bytes(g->num_rel, hidden_dim) : mp_f16_pack_bytes(g->num_rel)) +
              256 /* scale words */ + align_up(g->num_nodes * (int64_t)hidden_dim * 2, 256);
   return bytes + 256;
 }
@@ -401,14 +401,14 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
     if (int rc = ts ? mp_ts_pack(g, d_W_msg, d_W_self, pack, stream) : mp_umma_pack(g, d_W_msg, d_W_self, pack, stream))
       return rc;
   } else if (precision == GHF_PREC_F16) {
-    GHF_REQUIRE(mp_f16_supported(d) || f16_ss, "ghf_mp_layer: f16 path supports hidden_dim 128 and 256, got %d", d);
+    GHF_REQUIRE(mp_f16_supported(d) || f16_ss, "ghf_mp_layer: f16 path supports hidden_dim 64, 128 and 256, got %d", d);
     if (g->num_units > 0) {
       if (int rc = f16_ss ? mp_f16ss_pack(g, d_W_msg, d_W_self, pack, stream)
                           : mp_f16_pack(g, d_W_msg, d_W_self, pack, stream, transposed))
         return rc;
       if (h16 == nullptr) {  // no fp16 shadow of h from the previous layer: make one (scale words, then the rows)
         float* sc = reinterpret_cast<float*>(reinterpret_cast<char*>(pack) +
-                                             (f16_ss ? mp_f16ss_pack_bytes(g->num_rel) : mp_f16_pack_bytes(g->num_rel)));
+                                             (f16_ss ? mp_f16ss_pack_bytes(g->num_rel, d) : mp_f16_pack_bytes(g->num_rel)));
         void* conv = reinterpret_cast<char*>(sc) + 256;
         if (int rc = mp_f16_absmax(d_h, g->num_nodes * (int64_t)d, sc, stream)) return rc;
         if (int rc = mp_f16_convert(d_h, g->num_nodes * (int64_t)d, conv, sc, /*rescue=*/false, stream)) return rc;

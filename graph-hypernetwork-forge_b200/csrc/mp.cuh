@@ -46,10 +46,10 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
                   const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc = false,
                   int skip_half = 0);   // skip_half: 1 = no source term (W_msg NULL), 2 = no destination term
 
-// hidden_dim 256 with streamed fp16 weights (mp_f16_ss.cu): operand images [R][256 KiB] + inverse scales [R];
-// acc must be zero at entry, `unit_counter` one zeroed int
+// hidden_dim 256 / 64 with streamed fp16 weights (mp_f16_ss.cu): operand images [R][256 KiB / 16 KiB] + inverse
+// scales [R]; acc must be zero at entry, `unit_counter` one zeroed int
 bool mp_f16ss_supported(int hidden_dim);
-int64_t mp_f16ss_pack_bytes(int num_rel);
+int64_t mp_f16ss_pack_bytes(int num_rel, int hidden_dim);
 int mp_f16ss_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream);
 int mp_f16ss_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
                     const void* pack_scratch, int* unit_counter, cudaStream_t stream);

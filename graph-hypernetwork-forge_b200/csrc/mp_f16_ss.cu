@@ -1,6 +1,7 @@
-// mp_f16_ss.cu — message-passing contraction for hidden_dim 256 on tcgen05 kind::f16 with STREAMED weights
+// mp_f16_ss.cu — message-passing contraction on tcgen05 kind::f16 with STREAMED weights, hidden_dim 256 and 64
 // (GHF_PREC_F16; BASELINE config 4: 20k relation texts, ~100 edges per relation, 10.5 GB of generated fp32 weights
-// per layer).
+// per layer - and config 5, hidden 64, where the point is the halved row-gather traffic).  Written for hidden 256
+// (numbers below); hidden 64 is the same kernel with 2 K-chunks, 8 KiB weight chunks and 8 stages.
 //
 // At hidden 256 one relation's operand [W_msg[r]; W_self[r]] is 512 x 256 values: 256 KiB even as fp16 - more than
 // shared memory, twice tensor memory.  And with ~100 edges per relation every tile needs a different one.  So the
@@ -30,23 +31,25 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kD = 256;
 constexpr int kTileM = 128;
-constexpr int kChunks = 2 * kD / 64;              // 8 K-chunks of 64 halfs (one 128 B swizzle row)
-constexpr int kHalfChunks = kChunks / 2;          // chunks taken from h16[src]; the rest from h16[dst]
-constexpr int kABytes = kTileM * 128;             // 16 KiB
-constexpr int kBBytes = kD * 128;                 // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kStages = 4;
+constexpr int kABytes = kTileM * 128;             // A chunk: 128 half-rows of 128 B = 16 KiB
 constexpr int kStaging = 4 * 32 * 128;            // 4 epilogue warps x (32 rows x 32 fp32)
 constexpr int kQueue = 4;
 constexpr int kThreads = 320;
-constexpr uint32_t kTmemCols = 2 * kD;            // two accumulators
-constexpr int kSmem = 1024 + kStages * kStageBytes + kStaging + 512;
-constexpr int64_t kImageBytes = (int64_t)kChunks * kBBytes;   // 256 KiB per relation
 
-// kind::f16: D fp32, A and B fp16, both K-major, M = 128, N = 256
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kD >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+template <int D>
+struct Cfg {
+  static constexpr int kChunks = 2 * D / 64;              // K-chunks of 64 halfs (one 128 B swizzle row): 8 / 2
+  static constexpr int kHalfChunks = kChunks / 2;         // chunks taken from h16[src]; the rest from h16[dst]
+  static constexpr int kBBytes = D * 128;                 // B chunk: D rows of 128 B = 32 KiB / 8 KiB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = D == 256 ? 4 : 8;
+  static constexpr uint32_t kTmemCols = 2 * D;            // two accumulators
+  static constexpr int kSmem = 1024 + kStages * kStageBytes + kStaging + 512;
+  static constexpr int64_t kImageBytes = (int64_t)kChunks * kBBytes;   // 256 KiB / 16 KiB per relation
+  // kind::f16: D fp32, A and B fp16, both K-major, M = 128, N = D
+  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+};
 
 __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -60,9 +63,10 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 
 // element (n, k) of relation r's operand image (k < D -> W_msg[r][k][n], else W_self[r][k-D][n]): chunk k/64, row n,
 // 16-byte group (k%64)/8 swizzled by n%8 - what the K-major SWIZZLE_128B descriptor expects for N rows of 128 B
+template <int D>
 __device__ __forceinline__ int64_t image_offset_bytes(int n, int k) {
   const int c = k >> 6, kk = k & 63;
-  return (int64_t)c * kBBytes + (int64_t)n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1));
+  return (int64_t)c * Cfg<D>::kBBytes + (int64_t)n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1));
 }
 
 // One CTA per relation: max |W| -> power-of-two scale -> scaled fp16 image (see pack_f16_kernel in mp_f16.cu).
@@ -71,6 +75,7 @@ __device__ __forceinline__ int64_t image_offset_bytes(int n, int k) {
 // HBM sees the weights once.
 constexpr int kPackThreads = 1024;
 constexpr int kPackSmem = 160 * 1024;
+template <int kD>
 __global__ void __launch_bounds__(kPackThreads, 1)
 pack_f16_ss_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_self, uint8_t* __restrict__ pack,
                    float* __restrict__ inv_scale, int num_rel) {
@@ -107,7 +112,7 @@ pack_f16_ss_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_
     }
     __syncthreads();
     const float scale = s_scale;
-    uint8_t* img = pack + r * kImageBytes;
+    uint8_t* img = pack + r * Cfg<kD>::kImageBytes;
     // thread = (8 consecutive k, one n): lanes walk n (coalesced 128 B reads of one W row), one 16 B store each
 #pragma unroll 2
     for (int i = threadIdx.x; i < (2 * kD / 8) * kD; i += kPackThreads) {
@@ -119,11 +124,12 @@ pack_f16_ss_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_
         const __half2 p = __floats2half2_rn(__ldcg(src + (2 * j) * kD) * scale, __ldcg(src + (2 * j + 1) * kD) * scale);
         w[j] = *reinterpret_cast<const uint32_t*>(&p);
       }
-      *reinterpret_cast<uint4*>(img + image_offset_bytes(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(img + image_offset_bytes<kD>(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }
 
+template <int kD>
 __global__ void __launch_bounds__(kThreads, 1)
 mp_f16_ss_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
                  const int32_t* __restrict__ unit_rel, int64_t num_units, const int32_t* __restrict__ src_sorted,
@@ -131,9 +137,14 @@ mp_f16_ss_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restri
                  const float* __restrict__ h_scale, const uint8_t* __restrict__ wpack,
                  const float* __restrict__ w_inv_scale, const float* __restrict__ bias, float* __restrict__ acc,
                  int* __restrict__ unit_counter) {
+  using C = Cfg<kD>;
+  constexpr int kChunks = C::kChunks, kHalfChunks = C::kHalfChunks, kBBytes = C::kBBytes,
+                kStageBytes = C::kStageBytes, kStages = C::kStages;
+  constexpr uint32_t kTmemCols = C::kTmemCols, kIdesc = C::kIdesc;
+  constexpr int64_t kImageBytes = C::kImageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t sS = (raw + 1023u) & ~1023u;              // stages: [A chunk 16 KiB | B chunk 32 KiB]
+  const uint32_t sS = (raw + 1023u) & ~1023u;              // stages: [A chunk 16 KiB | B chunk]
   const uint32_t sStg = sS + kStages * kStageBytes;
   const uint32_t sBar = sStg + kStaging;
   auto full = [&](int s) { return sBar + 8u * s; };
@@ -314,8 +325,10 @@ mp_f16_ss_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restri
             mbar_wait(empty(stage), phase ^ 1u);
             mbar_arrive_expect_tx(full(stage), kBBytes);
             const uint32_t to = sS + stage * kStageBytes + kABytes;
-            bulk_g2s(to, img + (int64_t)c * kBBytes, kBBytes / 2, full(stage));
-            bulk_g2s(to + kBBytes / 2, img + (int64_t)c * kBBytes + kBBytes / 2, kBBytes / 2, full(stage));
+            constexpr int kPiece = kBBytes > 16384 ? 16384 : kBBytes;
+#pragma unroll
+            for (int off = 0; off < kBBytes; off += kPiece)
+              bulk_g2s(to + off, img + (int64_t)c * kBBytes + off, kPiece, full(stage));
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -331,27 +344,52 @@ mp_f16_ss_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restri
 
 }  // namespace
 
-bool mp_f16ss_supported(int d) { return d == kD; }
+bool mp_f16ss_supported(int d) { return d == 256 || d == 64; }
 
-int64_t mp_f16ss_pack_bytes(int num_rel) {
-  return align_up((int64_t)num_rel * kImageBytes, 256) + align_up((int64_t)num_rel * 4, 256);
+static int64_t image_bytes(int d) { return d == 256 ? Cfg<256>::kImageBytes : Cfg<64>::kImageBytes; }
+
+int64_t mp_f16ss_pack_bytes(int num_rel, int d) {
+  return align_up((int64_t)num_rel * image_bytes(d), 256) + align_up((int64_t)num_rel * 4, 256);
+}
+
+template <int D>
+static int pack_impl(const ghf_graph* g, const float* W_msg, const float* W_self, uint8_t* img, float* inv,
+                     cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    GHF_CUDA(cudaFuncSetAttribute(pack_f16_ss_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackSmem));
+    configured = true;
+  }
+  const int grid = g->num_rel < sm_count() ? g->num_rel : sm_count();
+  pack_f16_ss_kernel<D><<<(unsigned)grid, kPackThreads, kPackSmem, stream>>>(W_msg, W_self, img, inv, g->num_rel);
+  GHF_LAUNCH_CHECK();
+  return 0;
 }
 
 int mp_f16ss_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch,
                   cudaStream_t stream) {
-  GHF_REQUIRE(g->hidden_dim == kD, "mp_f16_ss: hidden_dim must be %d", kD);
+  const int d = g->hidden_dim;
+  GHF_REQUIRE(mp_f16ss_supported(d), "mp_f16_ss: hidden_dim must be 64 or 256, got %d", d);
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(W_msg) | reinterpret_cast<uintptr_t>(W_self) |
                reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
               "mp_f16_ss: W_msg / W_self / scratch must be 16-byte aligned");
   uint8_t* img = reinterpret_cast<uint8_t*>(pack_scratch);
-  float* inv = reinterpret_cast<float*>(img + align_up((int64_t)g->num_rel * kImageBytes, 256));
+  float* inv = reinterpret_cast<float*>(img + align_up((int64_t)g->num_rel * image_bytes(d), 256));
+  return d == 256 ? pack_impl<256>(g, W_msg, W_self, img, inv, stream) : pack_impl<64>(g, W_msg, W_self, img, inv, stream);
+}
+
+template <int D>
+static int launch_impl(const ghf_graph* g, const __half* h16, const float* h16_scale, const float* bias, float* acc,
+                       const uint8_t* img, const float* inv, int* unit_counter, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(pack_f16_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_ss_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::kSmem));
     configured = true;
   }
-  const int grid = g->num_rel < sm_count() ? g->num_rel : sm_count();
-  pack_f16_ss_kernel<<<(unsigned)grid, kPackThreads, kPackSmem, stream>>>(W_msg, W_self, img, inv, g->num_rel);
+  const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
+  mp_f16_ss_kernel<D><<<(unsigned)grid, kThreads, Cfg<D>::kSmem, stream>>>(
+      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted, h16, g->dst_lo, h16_scale,
+      img, inv, bias, acc, unit_counter);
   GHF_LAUNCH_CHECK();
   return 0;
 }
@@ -359,25 +397,18 @@ int mp_f16ss_pack(const ghf_graph* g, const float* W_msg, const float* W_self, v
 // acc (zero at entry) += the tiles' products; `unit_counter`: one zeroed int
 int mp_f16ss_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
                     const void* pack_scratch, int* unit_counter, cudaStream_t stream) {
-  GHF_REQUIRE(g->hidden_dim == kD, "mp_f16_ss: hidden_dim must be %d", kD);
+  const int d = g->hidden_dim;
+  GHF_REQUIRE(mp_f16ss_supported(d), "mp_f16_ss: hidden_dim must be 64 or 256, got %d", d);
   GHF_REQUIRE(h16_scale != nullptr, "mp_f16_ss: the fp16 shadow needs its scale words");
   GHF_REQUIRE(g->unit_edges % kTileM == 0, "mp_f16_ss: unit_edges=%d must be a multiple of %d", g->unit_edges, kTileM);
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(h16) | reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(bias) |
                reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
               "mp_f16_ss: h16 / acc / bias / scratch must be 16-byte aligned");
-  static bool configured = false;
-  if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(mp_f16_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
-  }
   const uint8_t* img = reinterpret_cast<const uint8_t*>(pack_scratch);
-  const float* inv = reinterpret_cast<const float*>(img + align_up((int64_t)g->num_rel * kImageBytes, 256));
-  const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
-  mp_f16_ss_kernel<<<(unsigned)grid, kThreads, kSmem, stream>>>(
-      g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,
-      reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter);
-  GHF_LAUNCH_CHECK();
-  return 0;
+  const float* inv = reinterpret_cast<const float*>(img + align_up((int64_t)g->num_rel * image_bytes(d), 256));
+  const __half* h = reinterpret_cast<const __half*>(h16);
+  return d == 256 ? launch_impl<256>(g, h, h16_scale, bias, acc, img, inv, unit_counter, stream)
+                  : launch_impl<64>(g, h, h16_scale, bias, acc, img, inv, unit_counter, stream);
 }
 
 }  // namespace ghf

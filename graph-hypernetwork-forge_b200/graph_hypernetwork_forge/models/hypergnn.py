@@ -136,7 +136,7 @@ class HyperGNN(nn.Module):
     ``HyperGNN(text_dim, node_feat_dim, hidden_dim, num_layers=2, dropout=0.0, char_emb_dim=32)``
     as in the reference.  Extension (keyword-only): ``precision`` - ``"f16"`` gathers an fp16 shadow copy
     of the node features and runs the per-edge contraction on tcgen05 kind::f16 with fp32 accumulation
-    (hidden_dim 128, and 256 with streamed weights; same 11-bit operand significand as TF32), ``"tf32"`` runs it on tcgen05 kind::tf32
+    (hidden_dim 128, and 64 / 256 with streamed weights; same 11-bit operand significand as TF32), ``"tf32"`` runs it on tcgen05 kind::tf32
     (hidden_dim 32/64/128), ``"fp32"`` on CUDA cores; ``None``/"auto" picks f16, then tf32, then fp32 as
     the shape allows (env ``GHF_PRECISION`` overrides).
     """
@@ -162,7 +162,7 @@ class HyperGNN(nn.Module):
     def _precision_code(self) -> int:
         name = os.environ.get("GHF_PRECISION") or self.precision or "auto"
         if name == "auto":
-            name = "f16" if self.hidden_dim in (128, 256) else "tf32" if self.hidden_dim in (32, 64) else "fp32"
+            name = "f16" if self.hidden_dim in (64, 128, 256) else "tf32" if self.hidden_dim == 32 else "fp32"
         return _native.precision_code(name)
 
     def prepare(self, edge_index: torch.Tensor, edge_texts: List[str], num_nodes: int,
@@ -241,7 +241,7 @@ class HyperGNN(nn.Module):
             return self._forward_autograd(node_features, prepared, prec, taps, dropping)
         with torch.no_grad():
             h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
-            chain = prec == _native.PREC_F16 and self.hidden_dim == 128      # shadows chained layer to layer
+            chain = prec == _native.PREC_F16 and self.hidden_dim in (64, 128)   # shadows chained layer to layer
             if chain:
                 h, h16 = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True,
                                         want_f16=True)
@@ -277,7 +277,7 @@ class HyperGNN(nn.Module):
         device.  `F.dropout` draws from torch's CUDA generator in the reference's call order."""
         graph, packed = prepared.graph, prepared.packed
         N, d = graph.num_nodes, self.hidden_dim
-        chain = prec == _native.PREC_F16 and d == 128 and not dropping   # fp16 shadows chained layer to layer
+        chain = prec == _native.PREC_F16 and d in (64, 128) and not dropping   # fp16 shadows chained layer to layer
         made = [] if chain else None
         fast = prec != _native.PREC_FP32             # tensor-core precision mode: the backward GEMMs may use TF32
         for gen in self.weight_generators:

@@ -31,7 +31,7 @@ extern "C" {
 #define GHF_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM (tolerance: DESIGN.md) */
 #define GHF_PREC_F16  2 /* fp16 feature/weight transport with exact power-of-two scaling, tcgen05 kind::f16,
                            fp32 accumulate in TMEM: the same 11-bit operand significand as TF32 at half the
-                           bytes (hidden_dim 128, and 256 with streamed weights; tolerance: DESIGN.md)  */
+                           bytes (hidden_dim 128; 64 and 256 with streamed weights; tolerance: DESIGN.md) */
 
 int ghf_abi_version(void);
 const char* ghf_last_error(void);

@@ -122,11 +122,13 @@ def test_c3_wikikg2_shape_full_size_properties():
     assert float((out - out3).abs().max()) < 1e-4
 
 
-def test_c5_large_shape_scaled_tf32_hidden64():
-    """BASELINE config 5's shape (hidden 64, 1k relations, in-degree 10) at 1/100 scale on one GPU, tf32 path."""
+@pytest.mark.parametrize("precision", ["tf32", "f16"])
+def test_c5_large_shape_scaled_hidden64(precision):
+    """BASELINE config 5's shape (hidden 64, 1k relations, in-degree 10) at 1/100 scale on one GPU: the tf32 engine
+    and the f16 engine with streamed weights."""
     N, E, R, d, L, T, F = 500_000, 5_000_000, 1000, 64, 2, 64, 64
     x, ei, rel, utf8, offsets = synthetic_on_device(N, E, R, F, seed=3)
-    model = build(T, F, d, L, "tf32")
+    model = build(T, F, d, L, precision)
     taps = {}
     out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N), taps=taps)
     assert bool(torch.isfinite(out).all()) and int(taps["in_degree"].sum()) == E

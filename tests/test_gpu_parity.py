@@ -84,7 +84,8 @@ def test_forward_call_is_drop_in(toy_kg):
 @pytest.mark.parametrize("N,E,R,d,L,prec", [
     (3000, 40000, 37, 128, 2, "tf32"), (3000, 40000, 37, 128, 2, "fp32"), (3000, 40000, 37, 128, 3, "f16"),
     (20000, 300000, 5, 128, 2, "f16"),
-    (5000, 60000, 300, 64, 2, "tf32"), (2000, 30000, 11, 32, 3, "tf32"),
+    (5000, 60000, 300, 64, 2, "tf32"), (5000, 60000, 300, 64, 3, "f16"), (2000, 30000, 11, 32, 3, "tf32"),
+    (1500, 20000, 41, 256, 2, "f16"),
     (1500, 9000, 50, 256, 1, "fp32"), (700, 5000, 9, 48, 2, "fp32"),
 ])
 def test_against_oracle_on_seeded_graphs(N, E, R, d, L, prec):
@@ -307,7 +308,7 @@ def test_forward_packed_single_native_call_matches_staged_path():
     """forward_packed (ghf_hypergnn_forward_device: one native call) == prepare_packed + forward_prepared."""
     from graph_hypernetwork_forge import HyperGNN, _text
     N, E, R, L = 4000, 60000, 29, 3
-    for d, prec in ((128, "f16"), (64, "tf32"), (48, "fp32")):
+    for d, prec in ((128, "f16"), (64, "tf32"), (64, "f16"), (256, "f16"), (48, "fp32")):
         src, dst, rel, names, feats = O.synthetic_kg(N, E, R, 40, seed=d)
         texts = [names[r] for r in rel]
         torch.manual_seed(d)

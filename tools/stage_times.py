@@ -16,8 +16,8 @@ from graph_hypernetwork_forge.models.hypergnn import PackedTexts  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
 w = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
-model = bench.build_model(w, dev, "f16" if w["d"] == 128 else "tf32")
-PREC = _native.precision_code("f16" if w["d"] == 128 else "tf32")
+model = bench.build_model(w, dev, "f16" if w["d"] in (64, 128, 256) else "tf32" if w["d"] == 32 else "fp32")
+PREC = _native.precision_code("f16" if w["d"] in (64, 128, 256) else "tf32" if w["d"] == 32 else "fp32")
 x, ei, rel, utf8, offsets = bench.make_device_inputs(w, dev)
 
 

@@ -15,7 +15,7 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 wl = args[0] if args else "c3"
 w = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
-prec = os.environ.get("GHF_PRECISION") or ("f16" if w["d"] == 128 else "tf32")
+prec = os.environ.get("GHF_PRECISION") or ("f16" if w["d"] in (64, 128, 256) else "tf32" if w["d"] == 32 else "fp32")
 model = bench.build_model(w, dev, prec).train()
 x, ei, rel, utf8, offsets = bench.make_device_inputs(w, dev)
 prepared = model.prepare_packed(ei, utf8, offsets, w["N"])
