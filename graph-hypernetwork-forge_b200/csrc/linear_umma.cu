@@ -40,14 +40,27 @@ constexpr uint32_t kWhCol = 256, kWlCol = 384;
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// kImage: instead of fp32 rows, the epilogue writes the result straight into the per-relation fp16 OPERAND IMAGES of
+// the hidden-64/256 contraction (mp_f16_ss.cu): row m = relation, output feature j = k * d + n = entry (k, n) of the
+// generated matrix, scaled by the relation's power of two `row_scale[m]` - the fp32 weights never exist (SURVEY 8f
+// rank 1).  Image of relation m: K-chunks of 64 (k + which * d counts through [W_msg; W_self]), inside a chunk
+// 64-wide n blocks of [64 k][128 B], 16-byte groups swizzled by k % 8 - an MN-major SWIZZLE_128B operand.
+struct ImageOut {
+  uint8_t* img;             // [M][image_bytes]
+  const float* row_scale;   // [M]
+  int64_t image_bytes;
+  int d, which;             // hidden_dim; 0 = W_msg half, 1 = W_self half
+};
+
+template <bool kImage>
 __global__ void __launch_bounds__(kThreads, 1)
 linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __restrict__ W,
                       const float* __restrict__ bias, int relu, const float* __restrict__ log_scale,
                       float* __restrict__ Y, int64_t ldy, __half* __restrict__ Y16,
-                      float* __restrict__ y16_scale) {
+                      float* __restrict__ y16_scale, ImageOut io) {
   // this CTA's block of 128 output features: rows [128 y, 128 y + 128) of W, the same columns of Y
   W += (int64_t)blockIdx.y * kD * kD;
-  Y += (int64_t)blockIdx.y * kD;
+  if (!kImage) Y += (int64_t)blockIdx.y * kD;
   if (Y16) Y16 += (int64_t)blockIdx.y * kD;   // optional fp16 copy of Y (same leading dimension)
   if (bias) bias += (int64_t)blockIdx.y * kD;
   const float alpha = log_scale ? expf(*log_scale) : 1.f;
@@ -116,6 +129,13 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
     const float4* stg4 = reinterpret_cast<const float4*>(stg);
     const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     float amax = 0.f;   // max |Y| seen by this thread (the fp16 shadow's range check)
+    int64_t img_off = 0;   // kImage: where this lane's 4 consecutive n of entry (k, n..n+3) sit inside a relation's image
+    if constexpr (kImage) {
+      const int j0 = (int)blockIdx.y * kD + 4 * lane;          // flat output feature = k * d + n
+      const int kk = j0 / io.d + io.which * io.d, n = j0 % io.d;
+      img_off = (int64_t)(kk >> 6) * (io.d * 128) + (int64_t)(n >> 6) * (64 * 128) + (kk & 63) * 128 +
+                (((((n & 63) >> 3) ^ (kk & 7))) << 4) + (n & 7) * 2;
+    }
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
@@ -140,6 +160,13 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+            if constexpr (kImage) {
+              const float sc = io.row_scale[row];
+              const __half2 p0 = __floats2half2_rn(v.x * sc, v.y * sc), p1 = __floats2half2_rn(v.z * sc, v.w * sc);
+              *reinterpret_cast<uint2*>(io.img + row * io.image_bytes + img_off) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+              continue;
+            }
             *reinterpret_cast<float4*>(Y + row * ldy + 4 * lane) = v;
             if (Y16) {
               amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
@@ -251,7 +278,7 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
                        const float* log_scale, float* Y, void* Y16, float* y16_scale, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   const int64_t tiles = (M + kTile - 1) / kTile;
@@ -259,9 +286,31 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
   // persistent over row tiles within a feature block: about one CTA per SM in total
   int64_t gx = (sm_count() + nblocks - 1) / nblocks;
   gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
-  linear128_umma_kernel<<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(X, M, W, b, relu,
-                                                                                          log_scale, Y, (int64_t)N,
-                                                                                          reinterpret_cast<__half*>(Y16), y16_scale);
+  linear128_umma_kernel<false><<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(
+      X, M, W, b, relu, log_scale, Y, (int64_t)N, reinterpret_cast<__half*>(Y16), y16_scale, ImageOut{});
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+// The last Linear of a weight generator written as fp16 operand images: image[m] entry (k + which * d, n) =
+// fp16( exp(log_scale) * (X[m] . W[k * d + n] + b[k * d + n]) * row_scale[m] ).   K = 128, N = d * d.
+int linear_umma_to_images(const float* X, int64_t M, const float* W, const float* b, int d, int which,
+                          const float* log_scale, const float* row_scale, void* images, int64_t image_bytes,
+                          cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  const int N = d * d;
+  GHF_REQUIRE(N % kD == 0 && d % 4 == 0 && N / kD <= 65535, "linear_umma_to_images: hidden_dim %d", d);
+  const int64_t tiles = (M + kTile - 1) / kTile;
+  const int nblocks = N / kD;
+  int64_t gx = (sm_count() + nblocks - 1) / nblocks;
+  gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
+  ImageOut io{reinterpret_cast<uint8_t*>(images), row_scale, image_bytes, d, which};
+  linear128_umma_kernel<true><<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(
+      X, M, W, b, 0, log_scale, nullptr, (int64_t)N, nullptr, nullptr, io);
   GHF_LAUNCH_CHECK();
   return 0;
 }

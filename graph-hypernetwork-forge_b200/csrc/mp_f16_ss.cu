@@ -9,7 +9,7 @@
 //     D[128 edges, 256] = A[128, 512] * B_r[512, 256]      (fp16 operands, fp32 accumulation in TMEM)
 // runs over 8 K-chunks of 64, and a pipeline stage carries BOTH operands of one chunk:
 //     A chunk: 128 gathered half-rows of h16 (cp.async, 128 B each, 128B-swizzled)                     16 KiB
-//     B chunk: 256 x 64 halfs of relation r's pre-swizzled image (cp.async.bulk, contiguous 32 KiB)    32 KiB
+//     B chunk: 64 k x 256 n halfs of relation r's pre-swizzled image (cp.async.bulk, contiguous 32 KiB) 32 KiB
 // 4 stages = 192 KiB.  The kernel is bound by the weight stream (256 KiB per tile): at c4 5.2 GB per layer instead of
 // the 10.5 GB of fp32 weights the CUDA-core kernel reads - and on tensor cores instead of 524 GFLOP of FFMA.
 // Scales as in mp_f16.cu: h16 = fp16(h * 2^k), image = fp16(W_r * 2^k_r), the epilogue multiplies by 2^-(k + k_r).
@@ -47,26 +47,20 @@ struct Cfg {
   static constexpr uint32_t kTmemCols = 2 * D;            // two accumulators
   static constexpr int kSmem = 1024 + kStages * kStageBytes + kStaging + 512;
   static constexpr int64_t kImageBytes = (int64_t)kChunks * kBBytes;   // 256 KiB / 16 KiB per relation
-  // kind::f16: D fp32, A and B fp16, both K-major, M = 128, N = D
-  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  // kind::f16: D fp32, A fp16 K-major (gathered rows), B fp16 MN-major ([16]: n is the contiguous index of a
+  // generated matrix, W[k][n]), M = 128, N = D
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 };
 
-__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
-// element (n, k) of relation r's operand image (k < D -> W_msg[r][k][n], else W_self[r][k-D][n]): chunk k/64, row n,
-// 16-byte group (k%64)/8 swizzled by n%8 - what the K-major SWIZZLE_128B descriptor expects for N rows of 128 B
+// entry (k, n) of relation r's operand image (k < D -> W_msg[r][k][n], else W_self[r][k-D][n]): K-chunk k/64, inside it
+// 64-wide n blocks of [64 k][128 B], 16-byte group (n%64)/8 swizzled by k%8 - the MN-major SWIZZLE_128B operand
+// (LBO = 8 KiB between n blocks, SBO = 1 KiB per 8 k).  n is the contiguous index, as in W itself, which is what lets
+// the generator's last Linear write images directly (linear_umma.cu, ImageOut - the same formula).
 template <int D>
 __device__ __forceinline__ int64_t image_offset_bytes(int n, int k) {
-  const int c = k >> 6, kk = k & 63;
-  return (int64_t)c * Cfg<D>::kBBytes + (int64_t)n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1));
+  return (int64_t)(k >> 6) * Cfg<D>::kBBytes + (int64_t)(n >> 6) * (64 * 128) + (k & 63) * 128 +
+         (((((n & 63) >> 3) ^ (k & 7))) << 4) + (n & 7) * 2;
 }
 
 // One CTA per relation: max |W| -> power-of-two scale -> scaled fp16 image (see pack_f16_kernel in mp_f16.cu).
@@ -113,18 +107,17 @@ pack_f16_ss_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_
     __syncthreads();
     const float scale = s_scale;
     uint8_t* img = pack + r * Cfg<kD>::kImageBytes;
-    // thread = (8 consecutive k, one n): lanes walk n (coalesced 128 B reads of one W row), one 16 B store each
+    // thread = (one k, 8 consecutive n): 32 B read from one W row, one 16 B store
 #pragma unroll 2
-    for (int i = threadIdx.x; i < (2 * kD / 8) * kD; i += kPackThreads) {
-      const int n = i % kD, k0 = (i / kD) * 8;
-      const float* src = k0 < kD ? W_msg + (r * kD + k0) * kD + n : W_self + (r * kD + (k0 - kD)) * kD + n;
-      uint32_t w[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __half2 p = __floats2half2_rn(__ldcg(src + (2 * j) * kD) * scale, __ldcg(src + (2 * j + 1) * kD) * scale);
-        w[j] = *reinterpret_cast<const uint32_t*>(&p);
-      }
-      *reinterpret_cast<uint4*>(img + image_offset_bytes<kD>(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int i = threadIdx.x; i < 2 * kD * (kD / 8); i += kPackThreads) {
+      const int k = i / (kD / 8), n0 = (i % (kD / 8)) * 8;
+      const float* src = k < kD ? W_msg + (r * kD + k) * kD + n0 : W_self + (r * kD + (k - kD)) * kD + n0;
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(src)), b = __ldcg(reinterpret_cast<const float4*>(src) + 1);
+      const __half2 p0 = __floats2half2_rn(a.x * scale, a.y * scale), p1 = __floats2half2_rn(a.z * scale, a.w * scale);
+      const __half2 p2 = __floats2half2_rn(b.x * scale, b.y * scale), p3 = __floats2half2_rn(b.z * scale, b.w * scale);
+      *reinterpret_cast<uint4*>(img + image_offset_bytes<kD>(n0, k)) =
+          make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                     *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
     }
   }
 }
@@ -291,9 +284,10 @@ mp_f16_ss_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restri
             fence_proxy_async();
             tc_fence_after();
             const uint64_t adesc = umma_desc_k128(sS + stage * kStageBytes);
-            const uint64_t bdesc = umma_desc_k128(sS + stage * kStageBytes + kABytes);
+            const uint32_t b_addr = sS + stage * kStageBytes + kABytes;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) umma_f16_ss(d_tmem, adesc + 2 * j, bdesc + 2 * j, kIdesc, (c | j) != 0);
+            for (int j = 0; j < 4; ++j)          // K step of 16: +32 B in the K-major A rows, +2 KiB (16 k rows) in B
+              umma_f16_ss(d_tmem, adesc + 2 * j, umma_desc_mn128(b_addr + j * 2048, 64 * 128), kIdesc, (c | j) != 0);
             umma_commit(empty(stage));
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }

@@ -60,21 +60,6 @@ constexpr uint32_t kDefaultFlags = 0u;
 // kind::f16, D fp32, A and B fp16, BOTH MN-major ([15], [16]), N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(kD >> 3) << 17) | ((uint32_t)(kD >> 4) << 24);
 
-// MN-major operand, 128-byte swizzle: 64 elements contiguous along M/N, 8 K-rows per 1024 B atom (SBO), next 64
-// elements of M/N `lbo` bytes further.
-__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // 16 bytes global -> shared, or 16 zero bytes when `bytes` == 0
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");

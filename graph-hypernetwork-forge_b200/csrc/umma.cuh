@@ -230,6 +230,23 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
+// MN-major operand (the M resp. N index is the contiguous one), 128-byte swizzle: 64 elements (fp16) contiguous along
+// M/N per 128 B row, 8 K-rows per 1024 B atom (SBO), the next 64 elements of M/N `lbo` bytes further
+// (cute/atom/mma_traits_sm100.hpp, "make_umma_desc<Major::MN>").  Advancing K by 16 = two atoms = +2048 B.
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 operands, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major:
 //   [4,6) D fmt (1 = f32) | [7,10) A fmt (2 = tf32) | [10,13) B fmt (2 = tf32) | [15] A major | [16] B major
 //   | [17,23) N>>3 | [24,29) M>>4
