@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "ghf_b200.h"
 #include "graph.cuh"
+#include "mp.cuh"
 
 namespace ghf {
 
@@ -179,13 +180,32 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
                                                                                            : GHF_PREC_FP32;
   // second arena: everything whose size depends on the number of distinct relations
   const size_t Un = (size_t)(U > 0 ? U : 1), Hn = (size_t)(H > 0 ? H : 1);
-  const size_t w_layer = 2 * Arena::padded(Un * d * d * 4) + Arena::padded(Un * d * 4);
-  GHF_CUDA(B.reserve(Arena::padded(Un * T * 4) + (size_t)L * w_layer + 2 * Arena::padded(Un * Hn * 4) + 4096));
+  // Hidden 64 / 256 on the f16 engine: the generator's last Linear writes the fp16 operand images of the contraction
+  // itself (linear_umma_to_images) - no fp32 W_msg / W_self, no packing pass.  Needs the tcgen05
+  // Linear (its input width is 128) and enough relations to fill it.
+  const bool fuse = prec == GHF_PREC_F16 && mp_f16ss_supported(d) && H == 128 && depth >= 1 && U >= 64 &&
+                    (int64_t)U * d * d >= (1 << 21) && !getenv("GHF_NO_FUSED_GENERATOR");
+  const size_t img_bytes = fuse ? (size_t)mp_f16ss_pack_bytes((int)Un, d) : 0;
+  const size_t w_layer = fuse ? Arena::padded(img_bytes) + Arena::padded(Un * 4) + Arena::padded(Un * d * 4)
+                              : 2 * Arena::padded(Un * d * d * 4) + Arena::padded(Un * d * 4);
+  GHF_CUDA(B.reserve(Arena::padded(Un * T * 4) + (size_t)L * w_layer + 4 * Arena::padded(Un * Hn * 4) + 8192));
   float* temb = B.take<float>(Un * T);
   float* hid_a = B.take<float>(Un * Hn);
   float* hid_b = B.take<float>(Un * Hn);
+  float* zfin[2] = {B.take<float>(Un * Hn), B.take<float>(Un * Hn)};   // inputs of the two last Linears (fused path)
+  float* words = B.take<float>(16);
   std::vector<std::array<float*, 3>> outs(L);
-  for (int l = 0; l < L; ++l) outs[l] = {B.take<float>(Un * d * d), B.take<float>(Un * d * d), B.take<float>(Un * d)};
+  std::vector<void*> images(L, nullptr);
+  std::vector<float*> img_scale(L, nullptr);
+  for (int l = 0; l < L; ++l) {
+    if (fuse) {
+      images[l] = B.take<char>(img_bytes);
+      img_scale[l] = B.take<float>(Un);
+      outs[l] = {nullptr, nullptr, B.take<float>(Un * d)};
+    } else {
+      outs[l] = {B.take<float>(Un * d * d), B.take<float>(Un * d * d), B.take<float>(Un * d)};
+    }
+  }
   const int n_out[3] = {d * d, d * d, d};
   if (int rc = ghf_text_encode(d_utf8, d_offs, first, U, emb, C, Wp, bp, T, temb, stream)) return rc;
 
@@ -202,15 +222,27 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
       const float* in = temb;
       int in_dim = T;
       for (int i = 0; i < depth; ++i) {
-        float* o = (i & 1) ? hid_b : hid_a;
+        float* o = (fuse && m < 2 && i == depth - 1) ? zfin[m] : ((i & 1) ? hid_b : hid_a);
         if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][i], layers[l].b[m][i], H, 1, nullptr, o, gen_stream))
           return rc;
         in = o;
         in_dim = H;
       }
+      if (fuse && m < 2) continue;                         // the two big Linears follow, once both inputs exist
       if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][depth], layers[l].b[m][depth], n_out[m], 0,
                               layers[l].log_scale[m], outs[l][m], gen_stream))
         return rc;
+    }
+    if (fuse && U > 0) {
+      if (int rc = mp_f16ss_image_scales(zfin[0], zfin[1], H, U, layers[l].w[0][depth], layers[l].b[0][depth],
+                                         layers[l].w[1][depth], layers[l].b[1][depth], d, layers[l].log_scale[0],
+                                         layers[l].log_scale[1], words, img_scale[l], images[l], gen_stream))
+        return rc;
+      for (int m = 0; m < 2; ++m)
+        if (int rc = linear_umma_to_images(zfin[m], U, layers[l].w[m][depth], layers[l].b[m][depth], d, m,
+                                           layers[l].log_scale[m], img_scale[l], images[l],
+                                           mp_f16ss_image_bytes(d), gen_stream))
+          return rc;
     }
     return 0;
   };
@@ -262,10 +294,15 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
     // HG:286-296
     void* out16 = (want_f16 && l + 1 < L) ? nxt16 : nullptr;
     float* dst = l + 1 < L ? nxt : d_out;                // the last layer writes the caller's buffer
-    if (int rc = ghf_mp_layer_f16(g, cur, cur16, cur16 ? cur_sc : nullptr, outs[l][0], outs[l][1], outs[l][2],
-                                  layers[l].ln_w, layers[l].ln_b, desc->ln_eps, prec, dst, out16,
-                                  out16 ? nxt_sc : nullptr, nullptr, ws, stream))
+    if (fuse && U > 0) {
+      if (int rc = mp_layer_prepacked(g, cur, cur16, cur16 ? cur_sc : nullptr, images[l], outs[l][2], layers[l].ln_w,
+                                      layers[l].ln_b, desc->ln_eps, dst, out16, out16 ? nxt_sc : nullptr, ws, stream))
+        return rc;
+    } else if (int rc = ghf_mp_layer_f16(g, cur, cur16, cur16 ? cur_sc : nullptr, outs[l][0], outs[l][1], outs[l][2],
+                                         layers[l].ln_w, layers[l].ln_b, desc->ln_eps, prec, dst, out16,
+                                         out16 ? nxt_sc : nullptr, nullptr, ws, stream)) {
       return rc;
+    }
     float* t = cur; cur = nxt; nxt = t;
     t = cur_sc; cur_sc = nxt_sc; nxt_sc = t;
     cur16 = out16;

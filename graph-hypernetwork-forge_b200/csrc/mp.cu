@@ -363,7 +363,7 @@ static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_
 static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
                            const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
                            float* acc_ext, bool accumulate, bool transposed, void* d_workspace, cudaStream_t stream,
-                           float** acc_used, ProfRec* rec) {
+                           float** acc_used, ProfRec* rec, const void* prepacked = nullptr) {
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
@@ -389,7 +389,8 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
   }
   // gradient contractions (ghf_mp_contract): transposed relation matrices and an absent (NULL) half are understood
   // by the f16 engine only; the host side materialises them for the other engines
-  const bool plain = !transposed && d_W_msg != nullptr && d_W_self != nullptr && d_bias != nullptr;
+  if (prepacked) pack = const_cast<void*>(prepacked);   // operand images built by the generator (hidden 64 / 256)
+  const bool plain = prepacked || (!transposed && d_W_msg != nullptr && d_W_self != nullptr && d_bias != nullptr);
   GHF_REQUIRE(plain || (precision == GHF_PREC_F16 && mp_f16_supported(d) && (d_W_msg != nullptr || d_W_self != nullptr)),
               "ghf_mp_contract: transposed / NULL weight tensors need precision f16 and hidden_dim 128");
   const int skip_half = d_W_msg == nullptr ? 1 : (d_W_self == nullptr ? 2 : 0);
@@ -403,11 +404,12 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
   } else if (precision == GHF_PREC_F16) {
     GHF_REQUIRE(mp_f16_supported(d) || f16_ss, "ghf_mp_layer: f16 path supports hidden_dim 64, 128 and 256, got %d", d);
     if (g->num_units > 0) {
-      if (int rc = f16_ss ? mp_f16ss_pack(g, d_W_msg, d_W_self, pack, stream)
-                          : mp_f16_pack(g, d_W_msg, d_W_self, pack, stream, transposed))
-        return rc;
+      if (!prepacked)
+        if (int rc = f16_ss ? mp_f16ss_pack(g, d_W_msg, d_W_self, pack, stream)
+                            : mp_f16_pack(g, d_W_msg, d_W_self, pack, stream, transposed))
+          return rc;
       if (h16 == nullptr) {  // no fp16 shadow of h from the previous layer: make one (scale words, then the rows)
-        float* sc = reinterpret_cast<float*>(reinterpret_cast<char*>(pack) +
+        float* sc = reinterpret_cast<float*>(reinterpret_cast<char*>(acc_ws) + acc_bytes +
                                              (f16_ss ? mp_f16ss_pack_bytes(g->num_rel, d) : mp_f16_pack_bytes(g->num_rel)));
         void* conv = reinterpret_cast<char*>(sc) + 256;
         if (int rc = mp_f16_absmax(d_h, g->num_nodes * (int64_t)d, sc, stream)) return rc;
@@ -476,6 +478,32 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
   }
   return 0;
 }
+
+namespace ghf {
+int mp_layer_prepacked(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                       const void* images, const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
+                       float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace, cudaStream_t stream) {
+  if (int rc = check_layer_args(g, d_workspace, GHF_PREC_F16, d_h16, d_h16_scale)) return rc;
+  GHF_REQUIRE(images != nullptr && mp_f16ss_supported(g->hidden_dim), "mp_layer_prepacked: hidden_dim 64 / 256 only");
+  g->stream = stream;
+  if (g->num_local == 0) return 0;
+  ProfRec rec{};
+  const bool prof = g_prof_on;
+  if (prof)
+    for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
+  float* acc = nullptr;
+  if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, nullptr, nullptr, d_bias, GHF_PREC_F16, nullptr, false,
+                               false, d_workspace, stream, &acc, prof ? &rec : nullptr, images))
+    return rc;
+  if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, nullptr, d_out16, d_out16_scale, stream))
+    return rc;
+  if (prof) {
+    GHF_CUDA(cudaEventRecord(rec.e[3], stream));
+    g_prof.push_back(rec);
+  }
+  return 0;
+}
+}  // namespace ghf
 
 extern "C" int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void* d_x16, const float* d_x16_scale,
                                const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,

@@ -54,6 +54,20 @@ int mp_f16ss_pack(const ghf_graph* g, const float* W_msg, const float* W_self, v
 int mp_f16ss_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
                     const void* pack_scratch, int* unit_counter, cudaStream_t stream);
 
+// images written by the generator itself (linear_umma.cu: linear_umma_to_images): per-relation scales from an
+// analytic bound, and the layer on pre-built images
+int64_t mp_f16ss_image_bytes(int hidden_dim);
+int mp_f16ss_image_scales(const float* Zm, const float* Zs, int H, int64_t R, const float* W3m, const float* b3m,
+                          const float* W3s, const float* b3s, int d, const float* ls_m, const float* ls_s,
+                          float* words, float* scale, void* images, cudaStream_t stream);
+int linear_umma_to_images(const float* X, int64_t M, const float* W, const float* b, int d, int which,
+                          const float* log_scale, const float* row_scale, void* images, int64_t image_bytes,
+                          cudaStream_t stream);
+// ghf_mp_layer_f16 for hidden 64 / 256 with the operand images already built (`images`: mp_f16ss_pack_bytes layout)
+int mp_layer_prepacked(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                       const void* images, const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
+                       float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace, cudaStream_t stream);
+
 // gradients of the generated relation tensors on tcgen05 (mp_wgrad_f16.cu, hidden_dim 128): g_W_msg[r] / g_W_self[r] /
 // g_bias[r] += sums over the edges of r (buffers zero at entry); h16 / g16 are fp16 shadows with their scale words.
 int mp_wgrad_f16_launch(const ghf_graph* g, const void* h16, const float* h_scale, const void* g16,

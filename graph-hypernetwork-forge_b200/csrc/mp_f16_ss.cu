@@ -336,6 +336,45 @@ mp_f16_ss_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restri
   if (warp == 8) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// Per-relation power-of-two scale of the operand images WITHOUT a pass over the generated values: an entry of
+// W[r] is alpha * (z_r . w_j + b_j), so |entry| <= alpha * (|z_r|_1 * max|w| + max|b|) - z_r the (post-ReLU) input of
+// the generator's last Linear, w / b its parameters.  The bound is loose by about |z|_1 / |z|_2 ~ 2^4, which only
+// costs exponent headroom (fp16 keeps its 11-bit significand for anything within 2^25 of the scaled maximum).
+// One scale per relation, shared by the W_msg and W_self halves (they meet in one accumulator).
+__global__ void __launch_bounds__(256)
+image_scale_kernel(const float* __restrict__ Zm, const float* __restrict__ Zs, int H, int64_t R,
+                   const float* __restrict__ words, const float* __restrict__ ls_m, const float* __restrict__ ls_s,
+                   float* __restrict__ scale, float* __restrict__ inv_scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= R) return;
+  float l1m = 0.f, l1s = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    l1m += fabsf(Zm[r * H + c]);
+    l1s += fabsf(Zs[r * H + c]);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    l1m += __shfl_xor_sync(0xffffffffu, l1m, s);
+    l1s += __shfl_xor_sync(0xffffffffu, l1s, s);
+  }
+  if (lane == 0) {
+    // words: [2i + 1] = max |.| of W3_msg, b3_msg, W3_self, b3_self (the scale-word pairs of mp_f16_absmax)
+    const float bm = expf(*ls_m) * (l1m * words[1] + words[3]);
+    const float bs = expf(*ls_s) * (l1s * words[5] + words[7]);
+    const float bound = fmaxf(bm, bs);
+    float sc = 1.f;
+    if (bound > 0.f && isfinite(bound)) {
+      int e;
+      frexpf(bound, &e);                          // bound < 2^e  ->  bound * 2^(15 - e) < 2^15
+      e = 15 - e;
+      sc = ldexpf(1.f, e > 100 ? 100 : (e < -100 ? -100 : e));
+    }
+    scale[r] = sc;
+    inv_scale[r] = 1.f / sc;
+  }
+}
+
 }  // namespace
 
 bool mp_f16ss_supported(int d) { return d == 256 || d == 64; }
@@ -404,5 +443,25 @@ int mp_f16ss_launch(const ghf_graph* g, const void* h16, const float* h16_scale,
   return d == 256 ? launch_impl<256>(g, h, h16_scale, bias, acc, img, inv, unit_counter, stream)
                   : launch_impl<64>(g, h, h16_scale, bias, acc, img, inv, unit_counter, stream);
 }
+
+// scales for generator-written images (see image_scale_kernel): fills scale[R] and the inverse scales behind the
+// images (the layout mp_f16ss_launch reads).  `words`: 8 floats of scratch.
+int mp_f16ss_image_scales(const float* Zm, const float* Zs, int H, int64_t R, const float* W3m, const float* b3m,
+                          const float* W3s, const float* b3s, int d, const float* ls_m, const float* ls_s,
+                          float* words, float* scale, void* images, cudaStream_t stream) {
+  GHF_REQUIRE(mp_f16ss_supported(d), "mp_f16_ss: hidden_dim must be 64 or 256, got %d", d);
+  const int64_t n_w = (int64_t)d * d * H, n_b = (int64_t)d * d;
+  if (int rc = mp_f16_absmax(W3m, n_w, words + 0, stream)) return rc;
+  if (int rc = mp_f16_absmax(b3m, n_b, words + 2, stream)) return rc;
+  if (int rc = mp_f16_absmax(W3s, n_w, words + 4, stream)) return rc;
+  if (int rc = mp_f16_absmax(b3s, n_b, words + 6, stream)) return rc;
+  float* inv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(images) + align_up(R * image_bytes(d), 256));
+  if (R == 0) return 0;
+  image_scale_kernel<<<(unsigned)cdiv(R * 32, 256), 256, 0, stream>>>(Zm, Zs, H, R, words, ls_m, ls_s, scale, inv);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
+int64_t mp_f16ss_image_bytes(int d) { return image_bytes(d); }
 
 }  // namespace ghf
