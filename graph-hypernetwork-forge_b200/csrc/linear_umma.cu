@@ -14,6 +14,7 @@
 //   chunks) | 16 MMA issuer + TMEM allocator
 #include <cuda_fp16.h>
 
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -210,6 +211,12 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
         for (int i = 0; i < 8; ++i) {
           const int row = pw * 32 + 4 * i + (lane >> 3);
           const uint32_t off = row * 128 + ((cj ^ (row & 7)) << 4);
+          if constexpr (kImage) {   // one TF32 product: X rounded to nearest, no remainder tile
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(to_tf32_rna(v[i].x)),
+                         "f"(to_tf32_rna(v[i].y)), "f"(to_tf32_rna(v[i].z)), "f"(to_tf32_rna(v[i].w))
+                         : "memory");
+            continue;
+          }
           const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
           const float4 l = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
           asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(h.x), "f"(h.y), "f"(h.z),
@@ -245,9 +252,15 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
           for (int j = 0; j < 4; ++j) {
             const uint32_t ah = tmem_base + kWhCol + (uint32_t)(32 * c + 8 * j);
             const uint32_t al = tmem_base + kWlCol + (uint32_t)(32 * c + 8 * j);
-            umma_tf32_ts(d_tmem, ah, bl + 2 * j, idesc, (uint32_t)(c | j));  // small terms first
-            umma_tf32_ts(d_tmem, al, bh + 2 * j, idesc, 1u);
-            umma_tf32_ts(d_tmem, ah, bh + 2 * j, idesc, 1u);
+            if constexpr (kImage) {
+              // the result is rounded to fp16 (11-bit significand) anyway: one TF32 product (operands rounded to
+              // nearest) instead of the 3-term split - a third of the tensor work
+              umma_tf32_ts(d_tmem, ah, bh + 2 * j, idesc, (uint32_t)(c | j));
+            } else {
+              umma_tf32_ts(d_tmem, ah, bl + 2 * j, idesc, (uint32_t)(c | j));  // small terms first
+              umma_tf32_ts(d_tmem, al, bh + 2 * j, idesc, 1u);
+              umma_tf32_ts(d_tmem, ah, bh + 2 * j, idesc, 1u);
+            }
           }
           umma_commit(empty(stage));
           if (c + 1 == kChunks) umma_commit(acc_full(a));
@@ -274,6 +287,22 @@ bool linear_umma_eligible(int64_t M, int K, int N, int relu, const void* log_sca
          ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0);
 }
 
+// CTAs per feature block: the grid is gx x nblocks persistent CTAs, each walking ceil(tiles / gx) row tiles after
+// loading its block of W into tensor memory (about one tile's worth of time).  Pick gx for the fewest tile-times on
+// the critical path - with many feature blocks (weight generators) that is not always 1: 512 blocks on 148 SMs are
+// 4 waves of 157 tiles with gx = 1, but 7 waves of 79 with gx = 2.
+static int64_t pick_gx(int64_t tiles, int nblocks) {
+  const int sms = sm_count();
+  int64_t best = 1, best_cost = INT64_MAX;
+  const int64_t hi = tiles < sms ? tiles : sms;
+  for (int64_t gx = 1; gx <= hi; ++gx) {
+    const int64_t waves = (gx * nblocks + sms - 1) / sms;
+    const int64_t cost = waves * ((tiles + gx - 1) / gx + 1);
+    if (cost < best_cost) { best_cost = cost; best = gx; }
+  }
+  return best;
+}
+
 int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int N, int relu,
                        const float* log_scale, float* Y, void* Y16, float* y16_scale, cudaStream_t stream) {
   static bool configured = false;
@@ -283,9 +312,7 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
   }
   const int64_t tiles = (M + kTile - 1) / kTile;
   const int nblocks = N / kD;
-  // persistent over row tiles within a feature block: about one CTA per SM in total
-  int64_t gx = (sm_count() + nblocks - 1) / nblocks;
-  gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
+  const int64_t gx = pick_gx(tiles, nblocks);
   linear128_umma_kernel<false><<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(
       X, M, W, b, relu, log_scale, Y, (int64_t)N, reinterpret_cast<__half*>(Y16), y16_scale, ImageOut{});
   GHF_LAUNCH_CHECK();
@@ -306,8 +333,7 @@ int linear_umma_to_images(const float* X, int64_t M, const float* W, const float
   GHF_REQUIRE(N % kD == 0 && d % 4 == 0 && N / kD <= 65535, "linear_umma_to_images: hidden_dim %d", d);
   const int64_t tiles = (M + kTile - 1) / kTile;
   const int nblocks = N / kD;
-  int64_t gx = (sm_count() + nblocks - 1) / nblocks;
-  gx = gx < 1 ? 1 : (gx > tiles ? tiles : gx);
+  const int64_t gx = pick_gx(tiles, nblocks);
   ImageOut io{reinterpret_cast<uint8_t*>(images), row_scale, image_bytes, d, which};
   linear128_umma_kernel<true><<<dim3((unsigned)gx, (unsigned)nblocks), kThreads, kSmem, stream>>>(
       X, M, W, b, 0, log_scale, nullptr, (int64_t)N, nullptr, nullptr, io);

@@ -325,8 +325,8 @@ def test_forward_packed_single_native_call_matches_staged_path():
 def test_generator_written_operand_images_match_the_packed_path():
     """Hidden 64 / 256 on the f16 engine, enough relations and generator width 128: the one-call forward lets the
     generator's last Linear write the fp16 operand images itself (no fp32 W_msg / W_self, scales from an analytic
-    bound); the staged path generates fp32 weights and packs them (scales from their maximum).  Both scales are
-    powers of two, so the two must agree to summation order - and both with the float64 oracle."""
+    bound, one TF32 product since the result is rounded to 11 bits anyway); the staged path generates fp32 weights
+    (3xTF32) and packs them.  The two agree within the tensor-core tolerance, and both with the float64 oracle."""
     from graph_hypernetwork_forge import HyperGNN, _text
     N, E, L = 3000, 60000, 2
     for d, R in ((256, 150), (64, 700)):
@@ -346,7 +346,8 @@ def test_generator_written_operand_images_match_the_packed_path():
         utf8, offsets = torch.from_numpy(data.copy()).to(DEV), torch.from_numpy(offs).to(DEV)
         staged = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N))
         fused = model.forward_packed(x, ei, utf8, offsets)
-        assert_close(fused.cpu().numpy(), staged.cpu().numpy(), 1e-4, 5e-5, f"generator-written images d={d}")
+        assert_close(fused.cpu().numpy(), staged.cpu().numpy(), 0.0, TF32_H_ATOL_SCALE1 / 4,
+                     f"generator-written images d={d}")
         ref = O.hypergnn_forward(params, feats, np.stack([src, dst]), texts, d, L, dtype=np.float64)
         assert_close(fused.cpu().numpy(), ref, 0.0, TF32_H_ATOL_SCALE1, f"generator-written images vs oracle d={d}")
 
