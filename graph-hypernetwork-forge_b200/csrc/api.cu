@@ -361,3 +361,41 @@ extern "C" int ghf_hypergnn_forward_host(const ghf_model_desc* desc, const float
   GHF_CUDA(cudaStreamSynchronize(stream));
   return 0;
 }
+
+// ---- generator -> operand-image fusion as C-ABI pieces (the whole-forward entry points use the same functions)
+extern "C" int64_t ghf_weight_images_bytes(int64_t R, int32_t hidden_dim) {
+  if (!mp_f16ss_supported(hidden_dim) || R < 0) return -1;
+  return mp_f16ss_pack_bytes((int)(R > 0 ? R : 1), hidden_dim) + 256;
+}
+
+extern "C" int ghf_weight_images_f16(const float* d_Zm, const float* d_Zs, int64_t R, const float* d_W3m,
+                                     const float* d_b3m, const float* d_lsm, const float* d_W3s, const float* d_b3s,
+                                     const float* d_lss, int32_t hidden_dim, void* d_images, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(mp_f16ss_supported(hidden_dim), "ghf_weight_images_f16: hidden_dim 64 or 256, got %d", hidden_dim);
+  GHF_REQUIRE(R >= 0 && d_Zm && d_Zs && d_W3m && d_b3m && d_lsm && d_W3s && d_b3s && d_lss && d_images,
+              "ghf_weight_images_f16: NULL argument");
+  GHF_REQUIRE(reinterpret_cast<uintptr_t>(d_images) % 1024 == 0, "ghf_weight_images_f16: d_images must be 1 KiB aligned");
+  if (R == 0) return 0;
+  TempBuf scratch;                                   // [8 floats of range words][R scales]
+  GHF_CUDA(scratch.alloc(256 + (size_t)R * sizeof(float), stream));
+  float* words = scratch.as<float>();
+  float* scale = words + 64;
+  if (int rc = mp_f16ss_image_scales(d_Zm, d_Zs, 128, R, d_W3m, d_b3m, d_W3s, d_b3s, hidden_dim, d_lsm, d_lss, words,
+                                     scale, d_images, stream))
+    return rc;
+  if (int rc = linear_umma_to_images(d_Zm, R, d_W3m, d_b3m, hidden_dim, 0, d_lsm, scale, d_images,
+                                     mp_f16ss_image_bytes(hidden_dim), stream))
+    return rc;
+  return linear_umma_to_images(d_Zs, R, d_W3s, d_b3s, hidden_dim, 1, d_lss, scale, d_images,
+                               mp_f16ss_image_bytes(hidden_dim), stream);
+}
+
+extern "C" int ghf_mp_layer_images(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                                   const void* d_images, const float* d_bias, const float* d_ln_w, const float* d_ln_b,
+                                   float eps, float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace,
+                                   void* stream_) {
+  GHF_REQUIRE(d_out16 == nullptr || d_out16_scale != nullptr, "ghf_mp_layer_images: d_out16 needs d_out16_scale");
+  return mp_layer_prepacked(g, d_h, d_h16, d_h16_scale, d_images, d_bias, d_ln_w, d_ln_b, eps, d_out, d_out16,
+                            d_out16_scale, d_workspace, (cudaStream_t)stream_);
+}

@@ -66,6 +66,9 @@ def lib():
         "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P, P]),
         "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, P]),
         "ghf_text_encode_backward": (c_int, [P, P, P, c_int64, P, c_int, P, c_int, P, P, P, P, P, P]),
+        "ghf_weight_images_bytes": (c_int64, [c_int64, c_int32]),
+        "ghf_weight_images_f16": (c_int, [P, P, c_int64, P, P, P, P, P, P, c_int32, P, P]),
+        "ghf_mp_layer_images": (c_int, [P, P, P, P, P, P, P, P, c_float, P, P, P, P, P]),
         "ghf_score_pairs": (c_int, [P, c_int64, c_int, P, P, c_int64, P, P]),
         "ghf_score_pairs_backward": (c_int, [P, c_int64, c_int, P, P, c_int64, P, P, P]),
         "ghf_absmax": (c_int, [P, c_int64, P, P]),
@@ -93,7 +96,8 @@ EXPORTED_SYMBOLS = (
     "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
     "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
-    "ghf_text_encode_backward", "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_text_encode_backward", "ghf_weight_images_bytes", "ghf_weight_images_f16", "ghf_mp_layer_images",
+    "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -303,6 +307,26 @@ def score_pairs_backward(emb, heads, tails, g_out) -> torch.Tensor:
     return g_emb
 
 
+def weight_images(Zm, Zs, W3m, b3m, ls_m, W3s, b3s, ls_s, hidden_dim: int) -> torch.Tensor:
+    """ghf_weight_images_f16: the last Linear of the W_msg / W_self generators written as the fp16 operand images of
+    the hidden-64/256 contraction (inputs [R,128]; -> uint8 tensor for `Graph.mp_layer_images`)."""
+    Zm, Zs, W3m, b3m, W3s, b3s, ls_m, ls_s = map(_f32, (Zm, Zs, W3m, b3m, W3s, b3s, ls_m, ls_s))
+    dev, R = Zm.device, Zm.shape[0]
+    if Zm.shape != (R, 128) or Zs.shape != (R, 128) or W3m.shape != (hidden_dim ** 2, 128) or W3s.shape != W3m.shape:
+        raise RuntimeError("weight_images: inputs must be [R,128], parameters [d*d,128]")
+    n = int(lib().ghf_weight_images_bytes(R, hidden_dim))
+    if n < 0:
+        raise RuntimeError(f"weight_images: hidden_dim {hidden_dim} has no streamed-weights engine")
+    buf = torch.empty(n + 1024, dtype=torch.uint8, device=dev)
+    off = (-buf.data_ptr()) % 1024
+    images = buf[off:off + n]
+    with torch.cuda.device(dev):
+        _check(lib().ghf_weight_images_f16(_ptr(Zm), _ptr(Zs), R, _ptr(W3m), _ptr(b3m), _ptr(ls_m), _ptr(W3s),
+                                           _ptr(b3s), _ptr(ls_s), hidden_dim, _ptr(images), _stream(dev)),
+               "ghf_weight_images_f16")
+    return images
+
+
 class Graph:
     """Owner of a ghf_graph handle (in-degree, dst-CSR, relation-grouped edge order)."""
 
@@ -405,6 +429,22 @@ class Graph:
                                           _ptr(out16.data) if out16 else None, _ptr(out16.scale) if out16 else None,
                                           _ptr(upd), _ptr(ws), _stream(dev)), "ghf_mp_layer_f16")
         return out, upd
+
+    def mp_layer_images(self, h, images, bias, ln_w, ln_b, eps: float, h16=None, out16=None) -> torch.Tensor:
+        """`mp_layer` (PREC_F16, hidden 64 / 256) on operand images made by `weight_images`."""
+        dev, d = self.device, self.hidden_dim
+        h, bias, ln_w, ln_b = _f32(h), _f32(bias), _f32(ln_w), _f32(ln_b)
+        if h.shape != (self.num_nodes, d) or bias.shape != (self.num_rel, d):
+            raise RuntimeError("mp_layer_images: h must be [N,d], bias [R,d]")
+        out = torch.empty((self.num_local, d), dtype=torch.float32, device=dev)
+        ws = self.workspace(PREC_F16)
+        with torch.cuda.device(dev):
+            _check(lib().ghf_mp_layer_images(self._h, _ptr(h), _ptr(h16.data) if h16 else None,
+                                             _ptr(h16.scale) if h16 else None, _ptr(images), _ptr(bias), _ptr(ln_w),
+                                             _ptr(ln_b), float(eps), _ptr(out), _ptr(out16.data) if out16 else None,
+                                             _ptr(out16.scale) if out16 else None, _ptr(ws), _stream(dev)),
+                   "ghf_mp_layer_images")
+        return out
 
     # ---- gradients (SURVEY 8f rank 3) -------------------------------------------------------------------
     def reversed(self) -> "Graph":

@@ -174,6 +174,21 @@ int ghf_text_encode_backward(const uint8_t* d_utf8, const int64_t* d_offsets, co
                              int64_t U, const float* d_emb, int C, const float* d_Wp, int T, const float* d_out,
                              const float* d_g_out, float* d_g_emb, float* d_g_Wp, float* d_g_bp, void* stream);
 
+/* ---- generator -> operand-image fusion (hidden_dim 64 / 256, precision GHF_PREC_F16) -----------
+ * The last Linear of the W_msg and W_self generators (WG:138-140) written directly as the fp16 operand images of the
+ * contraction: no fp32 [R,d,d] tensors, no packing pass.  d_Zm / d_Zs [R,128]: the inputs of those two Linears (the
+ * outputs of the generators' last hidden layer); d_W3* [d*d,128], d_b3* [d*d], d_ls* [1]: their parameters and
+ * log-scales.  d_images: ghf_weight_images_bytes(R, d) bytes.  The per-relation power-of-two scales come from an
+ * analytic bound (no pass over the generated values); the products use TF32 operands (the result is fp16).
+ * ghf_mp_layer_images is ghf_mp_layer_f16 on such images (d_bias [R,d] fp32 from the third generator). */
+int64_t ghf_weight_images_bytes(int64_t R, int32_t hidden_dim);
+int ghf_weight_images_f16(const float* d_Zm, const float* d_Zs, int64_t R, const float* d_W3m, const float* d_b3m,
+                          const float* d_lsm, const float* d_W3s, const float* d_b3s, const float* d_lss,
+                          int32_t hidden_dim, void* d_images, void* stream);
+int ghf_mp_layer_images(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                        const void* d_images, const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
+                        float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace, void* stream);
+
 /* ---- batched link scores fused with the row gather (HG:304-318 applied to `embs[heads]`, `embs[tails]`, as
  * demo.py:90-94 does): out[b] = <emb[heads[b]], emb[tails[b]]>, emb [N,d] fp32, ids int64 in [0,N) (checked;
  * synchronises for the check).  The backward overwrites d_g_emb [N,d] with the scattered gradient. */

@@ -352,6 +352,40 @@ def test_generator_written_operand_images_match_the_packed_path():
         assert_close(fused.cpu().numpy(), ref, 0.0, TF32_H_ATOL_SCALE1, f"generator-written images vs oracle d={d}")
 
 
+def test_weight_images_c_abi_pieces():
+    """ghf_weight_images_f16 + ghf_mp_layer_images called piecewise (what a host-language integrator would do) against
+    the layer on fp32 generated weights."""
+    from graph_hypernetwork_forge import HyperGNN, _native
+    N, E, R, d = 2000, 30000, 120, 256
+    src, dst, rel, names, feats = O.synthetic_kg(N, E, R, 24, seed=77)
+    torch.manual_seed(3)
+    model = HyperGNN(64, 24, d, 1, precision="f16").eval()
+    with torch.no_grad():
+        for p in model.weight_generators[0].log_scales.values():
+            p.fill_(-1.0)
+    model = model.to(DEV)
+    ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+    prepared = model.prepare_ids(ei, torch.from_numpy(rel).to(DEV), list(names), N)
+    h = torch.relu(torch.from_numpy(feats).to(DEV) @ model.input_proj.weight.T + model.input_proj.bias).contiguous()
+    temb = model.text_encoder.encode_packed(prepared.packed)
+    gen, ln = model.weight_generators[0], model.layer_norms[0]
+    w = gen(temb)
+    want, _ = prepared.graph.mp_layer(h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps,
+                                      _native.PREC_F16)
+    Z = {}
+    for kind in ("W_msg", "W_self"):
+        lin = [m for m in gen.generators[kind] if isinstance(m, torch.nn.Linear)]
+        z = temb
+        for m in lin[:-1]:
+            z = _native.linear(z, m.weight, m.bias, relu=True)
+        Z[kind] = (z, lin[-1])
+    images = _native.weight_images(Z["W_msg"][0], Z["W_self"][0], Z["W_msg"][1].weight, Z["W_msg"][1].bias,
+                                   gen.log_scales["W_msg"], Z["W_self"][1].weight, Z["W_self"][1].bias,
+                                   gen.log_scales["W_self"], d)
+    got = prepared.graph.mp_layer_images(h, images, w["bias"], ln.weight, ln.bias, ln.eps)
+    assert_close(got.cpu().numpy(), want.cpu().numpy(), 0.0, TF32_H_ATOL_SCALE1 / 4, "layer on generator-written images")
+
+
 def test_cuda_graph_replay_of_prepared_forward():
     """The layers of a prepared graph captured in a CUDA graph (launch-bound small graphs): same output, new features
     take effect on replay."""
