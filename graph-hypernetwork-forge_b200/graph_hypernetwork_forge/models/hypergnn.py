@@ -251,13 +251,23 @@ class HyperGNN(nn.Module):
             if taps is not None:
                 taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
                 taps["in_degree"] = graph.export()["indeg"]
+            fuse = taps is None and self._can_fuse_generator(prec, packed.num_unique, text_embs)
             for l in range(self.num_layers):
-                w = self._generate(l, text_embs, packed.num_unique)
                 ln = self.layer_norms[l]
                 out16 = None
                 if chain and l + 1 < self.num_layers:
                     out16 = _native.Shadow(torch.empty((graph.num_local, self.hidden_dim), dtype=torch.float16,
                                                        device=h.device))
+                if fuse:    # hidden 64 / 256: the generator writes the contraction's fp16 operand images itself
+                    gen = self.weight_generators[l]
+                    (zm, lm), (zs, lsf) = gen.hidden("W_msg", text_embs), gen.hidden("W_self", text_embs)
+                    images = _native.weight_images(zm, zs, lm.weight, lm.bias, gen.log_scales["W_msg"], lsf.weight,
+                                                   lsf.bias, gen.log_scales["W_self"], self.hidden_dim)
+                    bias = gen._run_mlp("bias", text_embs).view(packed.num_unique, self.hidden_dim)
+                    h = graph.mp_layer_images(h, images, bias, ln.weight, ln.bias, ln.eps, h16=h16, out16=out16)
+                    h16 = out16
+                    continue
+                w = self._generate(l, text_embs, packed.num_unique)
                 h, upd = graph.mp_layer(h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
                                         want_upd=taps is not None, h16=h16, out16=out16)
                 h16 = out16
@@ -265,6 +275,17 @@ class HyperGNN(nn.Module):
                     taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]
                     taps[f"upd.{l}"], taps[f"h.{l}"] = upd, h
         return h
+
+    def _can_fuse_generator(self, prec: int, num_unique: int, text_embs: torch.Tensor) -> bool:
+        """Generator -> operand-image fusion (`ghf_weight_images_f16`): f16 engine at hidden 64 / 256, generator MLPs
+        with hidden layers of width 128, no dropout in flight, enough relations to fill the tcgen05 Linear."""
+        d = self.hidden_dim
+        if prec != _native.PREC_F16 or d not in (64, 256) or os.environ.get("GHF_NO_FUSED_GENERATOR"):
+            return False
+        if self.training and self.dropout > 0.0:
+            return False
+        lin = [m for m in self.weight_generators[0].generators["W_msg"] if isinstance(m, nn.Linear)]
+        return len(lin) >= 2 and lin[-1].in_features == 128 and num_unique >= 64 and num_unique * d * d >= (1 << 21)
 
     def _forward_autograd(self, node_features, prepared: PreparedGraph, prec: int, taps, dropping=False) -> torch.Tensor:
         """The same forward with the autograd graph recorded (`autograd.py`): every stage is the forward kernel

@@ -77,6 +77,14 @@ class WeightGenerator(nn.Module):
                 x = nn.functional.dropout(x, self._dropout)       # the Dropout module after each hidden ReLU
         return x
 
+    def hidden(self, kind: str, x: torch.Tensor):
+        """(input of the last Linear of MLP `kind`, that Linear) - inference only; what the generator -> operand-image
+        fusion consumes instead of the generated fp32 tensor (`_native.weight_images`)."""
+        linears = [m for m in self.generators[kind] if isinstance(m, nn.Linear)]
+        for lin in linears[:-1]:
+            x = _native.linear(x, lin.weight, lin.bias, relu=True)
+        return x, linears[-1]
+
     def forward(self, text_emb: torch.Tensor) -> Dict[str, torch.Tensor]:
         """``[text_dim]`` or ``[B, text_dim]`` -> {"W_msg", "W_self", "bias"} (unbatched in, unbatched out)."""
         _native.require_cuda(text_emb, self.log_scales["W_msg"])

@@ -1,5 +1,7 @@
 """GPU parity: the CUDA path (through the C ABI) against the golden vectors of the reference and
 against the oracle on the same seeded inputs.  Run with `-m gpu` on a B200."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -344,10 +346,16 @@ def test_generator_written_operand_images_match_the_packed_path():
         x = torch.from_numpy(feats).to(DEV)
         data, offs = _text.pack_utf8(texts)
         utf8, offsets = torch.from_numpy(data.copy()).to(DEV), torch.from_numpy(offs).to(DEV)
-        staged = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N))
-        fused = model.forward_packed(x, ei, utf8, offsets)
+        os.environ["GHF_NO_FUSED_GENERATOR"] = "1"          # fp32 weights + packing pass
+        try:
+            staged = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N))
+        finally:
+            del os.environ["GHF_NO_FUSED_GENERATOR"]
+        fused = model.forward_packed(x, ei, utf8, offsets)                                   # native one-call forward
+        fused_py = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N))     # the same pieces from Python
         assert_close(fused.cpu().numpy(), staged.cpu().numpy(), 0.0, TF32_H_ATOL_SCALE1 / 4,
                      f"generator-written images d={d}")
+        assert_close(fused_py.cpu().numpy(), fused.cpu().numpy(), 1e-4, 5e-5, f"fused staged path d={d}")
         ref = O.hypergnn_forward(params, feats, np.stack([src, dst]), texts, d, L, dtype=np.float64)
         assert_close(fused.cpu().numpy(), ref, 0.0, TF32_H_ATOL_SCALE1, f"generator-written images vs oracle d={d}")
 
