@@ -193,42 +193,53 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
     const int grp = (warp - kWarpProd) >> 2, pw = (warp - kWarpProd) & 3;
     const int cj = lane & 7;
     int64_t cc = grp;  // global chunk counter of this group's next chunk
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t row0 = tile * kTile;
-      for (int c = grp; c < kChunks; c += 2, cc += 2) {
-        const int stage = (int)(cc % kStages);
-        const uint32_t phase = (uint32_t)((cc / kStages) & 1);
-        float4 v[8];
+    // this group's chunks in order: (tile, c) with c = grp, grp + 2.  The loads of the NEXT chunk are issued before
+    // the current one is converted and stored, so the L2 / HBM latency of one chunk hides behind the other's work
+    // (a generator Linear re-reads a small, L2-resident X for each of its hundreds of feature blocks: latency, not
+    // bandwidth, is what its producers wait for).
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * 2;
+    auto load = [&](int64_t idx, float4 (&v)[8]) {
+      const int64_t row0 = (blockIdx.x + (idx >> 1) * gridDim.x) * kTile;
+      const int c = grp + 2 * (int)(idx & 1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {  // loads first: 8 x 16 B in flight per thread before the ring slot is needed
-          const int64_t row = row0 + pw * 32 + 4 * i + (lane >> 3);
-          v[i] = row < M ? __ldg(reinterpret_cast<const float4*>(X + row * kD + c * 32 + 4 * cj))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        mbar_wait(empty(stage), phase ^ 1u);
-        const uint32_t hi_base = sA + stage * kStage, lo_base = hi_base + kSub;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = pw * 32 + 4 * i + (lane >> 3);
-          const uint32_t off = row * 128 + ((cj ^ (row & 7)) << 4);
-          if constexpr (kImage) {   // one TF32 product: X rounded to nearest, no remainder tile
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(to_tf32_rna(v[i].x)),
-                         "f"(to_tf32_rna(v[i].y)), "f"(to_tf32_rna(v[i].z)), "f"(to_tf32_rna(v[i].w))
-                         : "memory");
-            continue;
-          }
-          const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
-          const float4 l = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(h.x), "f"(h.y), "f"(h.z),
-                       "f"(h.w)
-                       : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z),
-                       "f"(l.w)
-                       : "memory");
-        }
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        mbar_arrive(full(stage));
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = row0 + pw * 32 + 4 * i + (lane >> 3);
+        v[i] = row < M ? __ldg(reinterpret_cast<const float4*>(X + row * kD + c * 32 + 4 * cj))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    float4 v[8], nv[8];
+    if (total > 0) load(0, v);
+    for (int64_t idx = 0; idx < total; ++idx, cc += 2) {
+      if (idx + 1 < total) load(idx + 1, nv);
+      const int stage = (int)(cc % kStages);
+      const uint32_t phase = (uint32_t)((cc / kStages) & 1);
+      mbar_wait(empty(stage), phase ^ 1u);
+      const uint32_t hi_base = sA + stage * kStage, lo_base = hi_base + kSub;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = pw * 32 + 4 * i + (lane >> 3);
+        const uint32_t off = row * 128 + ((cj ^ (row & 7)) << 4);
+        if constexpr (kImage) {   // one TF32 product: X rounded to nearest, no remainder tile
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(to_tf32_rna(v[i].x)),
+                       "f"(to_tf32_rna(v[i].y)), "f"(to_tf32_rna(v[i].z)), "f"(to_tf32_rna(v[i].w))
+                       : "memory");
+          continue;
+        }
+        const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+        const float4 l = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_base + off), "f"(h.x), "f"(h.y), "f"(h.z),
+                     "f"(h.w)
+                     : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_base + off), "f"(l.x), "f"(l.y), "f"(l.z),
+                     "f"(l.w)
+                     : "memory");
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      mbar_arrive(full(stage));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = nv[i];
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
