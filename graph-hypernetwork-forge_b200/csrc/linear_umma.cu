@@ -151,6 +151,14 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) stg[e * kD + q * 32 + lane] = __uint_as_float(r[e]);
+        float sc8[8];                                  // kImage: this thread's 8 relation scales, in flight over the barrier
+        if constexpr (kImage) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t row = row0 + e0 + 8 * q + i;
+            sc8[i] = row < M ? __ldg(io.row_scale + row) : 0.f;
+          }
+        }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -162,7 +170,7 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
             if constexpr (kImage) {
-              const float sc = io.row_scale[row];
+              const float sc = sc8[i];
               const __half2 p0 = __floats2half2_rn(v.x * sc, v.y * sc), p1 = __floats2half2_rn(v.z * sc, v.w * sc);
               *reinterpret_cast<uint2*>(io.img + row * io.image_bytes + img_off) =
                   make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
@@ -209,10 +217,7 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    float4 v[8], nv[8];
-    if (total > 0) load(0, v);
-    for (int64_t idx = 0; idx < total; ++idx, cc += 2) {
-      if (idx + 1 < total) load(idx + 1, nv);
+    auto store = [&](const float4 (&v)[8]) {   // convert + store one chunk into the ring slot of chunk counter cc
       const int stage = (int)(cc % kStages);
       const uint32_t phase = (uint32_t)((cc / kStages) & 1);
       mbar_wait(empty(stage), phase ^ 1u);
@@ -238,8 +243,16 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
       }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive(full(stage));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = nv[i];
+      cc += 2;
+    };
+    // two register sets, alternating: a chunk's loads are in flight while the previous chunk is converted and stored
+    float4 va[8], vb[8];
+    if (total > 0) load(0, va);
+    for (int64_t idx = 0; idx < total; idx += 2) {
+      if (idx + 1 < total) load(idx + 1, vb);
+      store(va);
+      if (idx + 2 < total) load(idx + 2, va);
+      if (idx + 1 < total) store(vb);
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
