@@ -107,3 +107,39 @@ def test_identity_collapse_composes_to_first_occurrence_ids():
     want_unique, want = O.dedup_texts(texts)
     assert np.array_equal(ids_packed[edge_map], want)
     assert len(set(ids_packed.tolist())) == len(want_unique)
+
+
+def test_analytic_bound_of_generated_weights_holds_and_is_not_too_loose():
+    """The generator -> operand-image fusion scales a relation's fp16 image by a power of two chosen from
+    |W[r]| <= exp(log_scale) * (|z_r|_1 * max|W3| + max|b3|) without looking at the generated values
+    (image_scale_kernel, mp_f16_ss.cu).  Checked here on the numpy oracle's generator: the bound holds for every
+    relation and is loose by far less than the 2^14 of exponent headroom fp16 leaves below its 11-bit significand."""
+    import numpy as np
+    from oracle import hypergnn_oracle as O
+    rng = np.random.default_rng(0)
+    T, H, d, R = 64, 128, 64, 300
+    text = np.tanh(rng.standard_normal((R, T))).astype(np.float32)
+    prefix = "g."
+    params = {}
+    for kind, n_out in (("W_msg", d * d), ("W_self", d * d), ("bias", d)):
+        dims = [T, H, H, n_out]
+        for li, idx in enumerate((0, 2, 4)):
+            fan_in = dims[li]
+            lim = 1.0 / np.sqrt(fan_in)
+            params[f"{prefix}generators.{kind}.{idx}.weight"] = rng.uniform(-lim, lim, (dims[li + 1], fan_in)).astype(np.float32)
+            params[f"{prefix}generators.{kind}.{idx}.bias"] = rng.uniform(-lim, lim, dims[li + 1]).astype(np.float32)
+        params[f"{prefix}log_scales.{kind}"] = np.array([rng.uniform(-3, 0.5)], dtype=np.float32)
+    w = O.weight_generator(text, params, prefix, d, d, dtype=np.float64)
+    worst_loose = 0.0
+    for kind in ("W_msg", "W_self"):
+        z = text.astype(np.float64)
+        for idx in (0, 2):                                   # the hidden layers: Linear + ReLU
+            z = np.maximum(z @ params[f"{prefix}generators.{kind}.{idx}.weight"].T.astype(np.float64)
+                           + params[f"{prefix}generators.{kind}.{idx}.bias"], 0)
+        W3, b3 = params[f"{prefix}generators.{kind}.4.weight"], params[f"{prefix}generators.{kind}.4.bias"]
+        alpha = float(np.exp(params[f"{prefix}log_scales.{kind}"][0]))
+        bound = alpha * (np.abs(z).sum(axis=1) * np.abs(W3).max() + np.abs(b3).max())       # [R]
+        actual = np.abs(w[kind]).reshape(R, -1).max(axis=1)
+        assert np.all(actual <= bound * (1 + 1e-6)), kind
+        worst_loose = max(worst_loose, float((bound / actual).max()))
+    assert worst_loose < 2 ** 8, f"bound loose by {worst_loose:.1f}x"
