@@ -143,3 +143,26 @@ def test_analytic_bound_of_generated_weights_holds_and_is_not_too_loose():
         assert np.all(actual <= bound * (1 + 1e-6)), kind
         worst_loose = max(worst_loose, float((bound / actual).max()))
     assert worst_loose < 2 ** 8, f"bound loose by {worst_loose:.1f}x"
+
+
+@pytest.mark.grad
+def test_fusion_eligibility_and_autograd_routing_are_host_logic():
+    """`_can_fuse_generator` (when the generator may write operand images) and `autograd.wants_grad` need no GPU."""
+    import torch
+    from graph_hypernetwork_forge import HyperGNN, _native, autograd
+    m256 = HyperGNN(64, 16, 256, 2)          # generator width max(64, 2 * 64) = 128
+    m64_narrow = HyperGNN(16, 16, 64, 2)     # generator width 64: the tcgen05 Linear needs 128
+    m128 = HyperGNN(64, 16, 128, 2)
+    t = torch.zeros(1)
+    assert m256._can_fuse_generator(_native.PREC_F16, 200, t)
+    assert not m256._can_fuse_generator(_native.PREC_F16, 20, t)            # too few relations to fill the kernel
+    assert not m256._can_fuse_generator(_native.PREC_FP32, 200, t)
+    assert not m64_narrow._can_fuse_generator(_native.PREC_F16, 5000, t)
+    assert not m128._can_fuse_generator(_native.PREC_F16, 5000, t)          # hidden 128 keeps weights in TMEM instead
+    assert HyperGNN(64, 16, 64, 1)._can_fuse_generator(_native.PREC_F16, 600, t)
+    x = torch.zeros(2, requires_grad=True)
+    assert autograd.wants_grad(x) and not autograd.wants_grad(x.detach(), None)
+    with torch.no_grad():
+        assert not autograd.wants_grad(x)
+    assert m128._precision_code() == _native.PREC_F16 and HyperGNN(8, 8, 32, 1)._precision_code() == _native.PREC_TF32
+    assert HyperGNN(8, 8, 24, 1)._precision_code() == _native.PREC_FP32
