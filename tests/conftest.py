@@ -31,3 +31,26 @@ def _no_grad_unless_marked(request):
 def toy_kg():
     from graph_hypernetwork_forge import ToyKnowledgeGraph
     return ToyKnowledgeGraph(feat_dim=16)
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Measured error of every parity comparison next to its bound (see _util.RECORDS)."""
+    import json
+    from _util import RECORDS
+    if not RECORDS:
+        return
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_errors.json"), "w") as f:
+            json.dump(RECORDS, f, indent=0)
+    worst = {}
+    for r in RECORDS:                                   # per (test function, quantity): the largest share of the bound
+        key = (r["test"].split("::")[-1].split("[")[0], r["what"].split(" ")[0], r["kind"])
+        if key not in worst or r["used"] > worst[key]["used"]:
+            worst[key] = r
+    tr = terminalreporter
+    tr.write_line("")
+    tr.write_line(f"parity: {len(RECORDS)} comparisons; largest measured error per (test, quantity, tolerance):")
+    for (test, what, kind), r in sorted(worst.items()):
+        tr.write_line(f"  {test:58s} {what:14s} err {r['max_err']:.3e}  ref {r['max_ref']:.3e}  "
+                      f"bound {r['bound']:.3e} ({100 * r['used']:.0f}% used)  [{kind}]")
