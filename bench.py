@@ -8,10 +8,15 @@ input projection + graph build + L x (weight generation + message passing + Laye
   value  : E * L / step time with inputs resident in HBM (device-timed, CUDA events)
   e2e    : the same through the C ABI entry ghf_hypergnn_forward_host with HOST buffers
            (H2D of features / edges / strings and D2H of the embeddings inside the timed region)
-  roofline: the message-passing contraction kernel, algorithmic bytes / its event-timed duration
-  cpu_baseline: the numpy oracle (a port of the reference algorithm) on a bounded sample, host cores
-`--impl reference` times that CPU port alone (the reference is pure Python/torch and cannot travel to
-the GPU box).  Prints ONE JSON line on rank 0.
+  roofline: the dominant kernel (the fused layer kernel at hidden 128), SURVEY 8(d) algorithmic bytes / its
+           event-timed duration; also the bytes at the operand width the kernel really reads, the whole layer
+           and the whole step against the same roofline
+  precision_alt: the same step on the tf32 and fp32 engines (the fp32-tolerance context of an f16 headline)
+  cpu_baseline: the reference's CPU path on a bounded sample of the same workload, host cores
+`--impl reference` times the UNMODIFIED reference (installed under baseline/_ref by baseline/install_reference.sh,
+git-ignored, travels with the snapshot) on the host cores, on a sample of the workload with N and E scaled
+together; without that install it falls back to the numpy port of the reference algorithm (oracle/).  Both
+arms print the same `config`.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -132,77 +137,149 @@ def build_model(w, device, precision):
 
 
 def algorithmic_bytes(w, E, N_local, N):
+    """SURVEY 8(d): fp32 features, int32 ids.  contraction = row gathers + ids + h[dst] once + weights once;
+    layer = contraction + write h' + rowptr/in-degree."""
     d, R = w["d"], w["R"]
-    contraction = E * (4 * d + 8) + N_local * 4 * d + R * (2 * d * d + d) * 4   # gathers + ids + h[dst] once + weights
-    layer = contraction + N_local * 4 * d + 4 * (N_local + 1)                   # + write h', read rowptr/in-degree
+    contraction = E * (4 * d + 8) + N_local * 4 * d + R * (2 * d * d + d) * 4
+    layer = contraction + N_local * 4 * d + 4 * (N_local + 1)
     return contraction, layer
 
 
-def cpu_port_forward(w, sample_edges, seed=0, threads=None):
-    """The oracle (numpy port of the reference algorithm) on the first `sample_edges` edges of the workload."""
-    from oracle import hypergnn_oracle as O
-    src, dst, rel, names, feats = O.synthetic_kg(w["N"], sample_edges, w["R"], w["F"], seed=seed)
-    texts = [names[r] for r in rel]
-    torch.manual_seed(0)
-    from graph_hypernetwork_forge import HyperGNN
-    params = {k: v.numpy() for k, v in HyperGNN(w["T"], w["F"], w["d"], w["L"]).state_dict().items()}
-    ei = np.stack([src, dst])
+def bytes_as_read(w, E, N_local, precision, fused):
+    """The same accounting at the operand width the engine really moves (second figure next to SURVEY's fp32 one):
+    f16 engines gather fp16 rows and stream fp16 weight images; the fused layer kernel also reads the fp32 residual
+    row and writes the fp32 row + its fp16 shadow; the unfused contraction writes and re-reads an fp32 accumulator."""
+    d, R = w["d"], w["R"]
+    row = 2 * d if precision == "f16" else 4 * d
+    wbytes = R * (2 * d * d) * (2 if precision == "f16" else 4) + R * d * 4
+    gathers = E * (2 * row + 8)                              # source row + destination row + two ids per edge
+    contraction = gathers + wbytes + (0 if fused else N_local * 4 * d)
+    layer = gathers + wbytes + N_local * (4 * d + 4 * d + 4) + (N_local * 2 * d if precision == "f16" else 0) \
+        + (0 if fused else 2 * N_local * 4 * d)
+    return contraction, layer
 
-    def run():
+
+def make_config(w, world, skew):
+    """`config` of the JSON line: identical in the b200 arm and the reference arm (the driver compares them)."""
+    N, E, d, L = w["N"], w["E"], w["d"], w["L"]
+    return {"workload": f"{w['name']} N={N} E={E} R={w['R']} d={d} L={L} T={w['T']} F={w['F']}"
+                        + (" zipf-dst-rel" if skew else " uniform"),
+            "step": "dedup + text encoder + input projection + graph build + L layers",
+            "l2": (f"inputs larger than L2 (h {N * d * 4 / 1e9:.2f} GB, edges {E * 16 / 1e9:.2f} GB); "
+                   "no explicit flush") if N * d * 4 > 256e6 else
+                  "workload smaller than L2: 256 MB scratch written between steps",
+            "parallelism": "single GPU" if world == 1 else f"dst-range x{world} + all-gather(h) per layer"}
+
+
+def sampled_workload(w, edges, seed=0):
+    """A bounded sample of the workload for the CPU legs: N and E scaled TOGETHER (same in-degree, same relation
+    vocabulary, same generator), so per-node work (projection, LayerNorm) and per-edge work keep their proportion.
+    One sampler for `cpu_baseline` and `--impl reference`."""
+    from oracle import hypergnn_oracle as O
+    k = int(min(w["E"], max(1, edges)))
+    n = int(max(64, min(w["N"], round(w["N"] * k / w["E"]))))
+    src, dst, rel, names, feats = O.synthetic_kg(n, k, w["R"], w["F"], seed=seed)
+    return n, k, src, dst, [names[r] for r in rel], feats
+
+
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+REF_EDGE_RATE = 3.0e4     # edge-layers/s of the literal reference on ~8 cores (BASELINE.md): sizes the sample only
+REF_MAX_EDGES = 60_000    # the literal reference needs ~268 KB per edge at d = 128 (per-edge weight gathers)
+
+
+def time_literal_reference(w, edges, steps, warmup):
+    """The UNMODIFIED reference (baseline/_ref) on the host cores: model(x, edge_index, List[str]), eval, no_grad."""
+    import importlib
+    for name in [m for m in sys.modules if m.split(".")[0] == "graph_hypernetwork_forge"]:
+        del sys.modules[name]                      # the drop-in shares the import path: make sure the reference loads
+    sys.path[:] = [REF_DIR] + [q for q in sys.path if "graph-hypernetwork-forge_b200" not in q]
+    ref = importlib.import_module("graph_hypernetwork_forge")
+    assert os.path.realpath(ref.__file__).startswith(os.path.realpath(REF_DIR)), ref.__file__
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, k, src, dst, texts, feats = sampled_workload(w, edges)
+    torch.manual_seed(0)
+    model = ref.HyperGNN(w["T"], w["F"], w["d"], w["L"]).eval()
+    x, ei = torch.from_numpy(feats), torch.from_numpy(np.stack([src, dst]))
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            model(x, ei, texts)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return n, k, times
+
+
+def time_port(w, edges, steps, warmup):
+    """The numpy port of the reference algorithm (oracle/) on the same kind of sample."""
+    from oracle import hypergnn_oracle as O
+    n, k, src, dst, texts, feats = sampled_workload(w, edges)
+    torch.manual_seed(0)
+    sys.path.insert(0, os.path.join(ROOT, "graph-hypernetwork-forge_b200"))
+    from graph_hypernetwork_forge import HyperGNN
+    params = {kk: v.numpy() for kk, v in HyperGNN(w["T"], w["F"], w["d"], w["L"]).state_dict().items()}
+    ei = np.stack([src, dst])
+    times = []
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
         O.hypergnn_forward(params, feats, ei, texts, w["d"], w["L"])
-        return time.perf_counter() - t0
-    return run
-
-
-def cpu_sample_for_budget(w, seconds):
-    """Edges of the workload the CPU port gets through in about `seconds` per forward (all N nodes are always
-    present: input projection, residual and LayerNorm are per node).  Two probes fit time = a + b * edges."""
-    e1, e2 = min(w["E"], 100_000), min(w["E"], 400_000)
-    t1 = cpu_port_forward(w, e1)()
-    if e2 == e1:
-        return e1, t1
-    t2 = cpu_port_forward(w, e2)()
-    per_edge = max((t2 - t1) / (e2 - e1), 1e-9)
-    fixed = max(t1 - per_edge * e1, 0.0)
-    sample = int((seconds - fixed) / per_edge) if seconds > fixed else e1
-    sample = max(e1, min(w["E"], sample))
-    # the cost grows faster than linearly once the working set leaves the caches: one calibration pass, then shrink
-    t = cpu_port_forward(w, sample)()
-    if t > 1.25 * seconds and sample > e1:
-        sample = max(e1, int(sample * seconds / t))
-    return sample, t
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return n, k, times
 
 
 def run_reference(args, w):
-    """--impl reference: the CPU port of the reference algorithm, all host threads, bounded sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, a bounded sample of
+    the workload per step (sampled_workload).  Rank 0 alone runs; the other ranks exit 0."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    # size the per-step sample so that (warmup + steps) steps finish in about two and a half minutes
-    budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
-    sample, _ = cpu_sample_for_budget(w, budget)
-    run = cpu_port_forward(w, sample)
-    for _ in range(args.warmup):
-        run()
-    times = [run() for _ in range(args.steps)]
-    ms = 1e3 * sum(times) / len(times)
-    value = sample * w["L"] / (ms / 1e3)
-    line = {"impl": "reference", "metric": "hypergnn_fwd_edges_per_sec_per_layer", "value": value,
+    L = w["L"]
+    budget = min(15.0, 120.0 / max(1, args.steps + args.warmup))      # seconds of CPU work per step
+    literal = os.path.isdir(os.path.join(REF_DIR, "graph_hypernetwork_forge")) and not args.port
+    port = None
+    if not args.no_port_extra or not literal:
+        # the memory-feasible port, one pass on a larger sample (it does not materialise per-edge weights)
+        pn, pk, pt = time_port(w, args.sample_edges or int(min(w["E"], 4.0e5 * budget / 5.0)), 1 if literal else args.steps,
+                               0 if literal else args.warmup)
+        pms = 1e3 * sum(pt) / len(pt)
+        port = {"value": pk * L / (pms / 1e3), "unit": "edges/s/layer", "cores": cores, "kind": "port",
+                "ms_per_step": pms,
+                "sample": f"{pk} edges, {pn} nodes (N and E scaled together), {L} layers: numpy port of the reference "
+                          "algorithm (oracle/hypergnn_oracle.py)"}
+    if literal:
+        k = args.sample_edges or int(max(5_000, min(REF_MAX_EDGES, budget * REF_EDGE_RATE / L)))
+        n, k, times = time_literal_reference(w, k, args.steps, args.warmup)
+        ms = 1e3 * sum(times) / len(times)
+        base = {"value": k * L / (ms / 1e3), "unit": "edges/s/layer", "cores": cores, "kind": "reference",
+                "sample": f"{k} edges, {n} nodes (N and E of the workload scaled together, same R, same generator), "
+                          f"{L} layers per step: the unmodified reference from baseline/_ref, "
+                          f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads",
+                "port": port}
+    else:
+        ms, base = port["ms_per_step"], dict(port)
+    line = {"impl": "reference", "metric": "hypergnn_fwd_edges_per_sec_per_layer", "value": base["value"],
             "unit": "edges/s/layer", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"{w['name']} N={w['N']} E={w['E']} R={w['R']} d={w['d']} L={w['L']} T={w['T']} "
-                                   f"F={w['F']}",
-                       "sample": f"first {sample} edges, all {w['N']} nodes, per step"},
-            "cpu_baseline": {"value": value, "unit": "edges/s/layer", "cores": cores, "kind": "port",
-                             "sample": f"{sample} edges x {w['L']} layers per step, numpy oracle (port of the "
-                                       "reference algorithm; the reference itself is Python/torch and is not on "
-                                       "the GPU box)"},
-            "e2e": {"value": value, "unit": "edges/s/layer", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "data": "synthetic", "config": make_config(w, args.gpus, args.skew), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "edges/s/layer", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """The reference arm in a child process (the reference and the drop-in share an import path), one step."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "1",
+           "--warmup", "1", "--scale", str(args.scale)] + (["--skew"] if args.skew else [])
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (out.stderr or out.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def main():
@@ -221,6 +298,10 @@ def main():
                     help="also time a training step (forward + backward on a prepared graph) -> key 'train_step'")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the tf32 / fp32 engines (precision_alt)")
+    ap.add_argument("--port", action="store_true", help="--impl reference: time the numpy port even if baseline/_ref exists")
+    ap.add_argument("--no-port-extra", action="store_true", help="--impl reference: skip the extra pass of the numpy port")
+    ap.add_argument("--sample-edges", type=int, default=0, help="--impl reference: edges of the per-step sample")
     args = ap.parse_args()
     torch.set_grad_enabled(False)   # inference benchmark: no autograd graph is recorded
     w = dict(WORKLOADS[args.workload])
@@ -317,24 +398,40 @@ def main():
     hbm_peak, peak_src = peaks()
     local_edges = E if world == 1 else sharded.num_kept
     b_contr, b_layer = algorithmic_bytes(w, local_edges, n_local, N)
+    fused = precision == "f16" and d == 128 and os.environ.get("GHF_MP_FUSED", "0") == "1"
+    r_contr, r_layer = bytes_as_read(w, local_edges, n_local, precision, fused)
     t_contr = prof["contraction_ms"] / max(n_layers_timed, 1)
     t_layer = (prof["contraction_ms"] + prof["epilogue_ms"] + prof["prep_ms"]) / max(n_layers_timed, 1)
-    achieved = b_contr / (t_contr * 1e-3) / 1e9 if t_contr > 0 else 0.0
+    # the dominant kernel: the fused layer kernel does the whole layer, so it is charged the layer's bytes
+    b_kernel, r_kernel = (b_layer, r_layer) if fused else (b_contr, r_contr)
+    gbs = lambda nbytes, t_ms: nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0   # noqa: E731
+    achieved = gbs(b_kernel, t_contr)
     traffic = None
-    try:  # per-launch DRAM bytes of the contraction kernel from the committed ncu capture, when present
+    try:  # per-launch DRAM bytes of that kernel from the committed ncu capture, when present (1 GPU, full graph)
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{args.workload}:{precision}")
+            traffic = json.load(f).get(f"{args.workload}:{precision}" + (":fused" if fused else "")) if world == 1 else None
     except Exception:
         pass
-    kernel_name = {"f16": "mp_f16_kernel" if d == 128 else "mp_f16_ss_kernel", "tf32": "mp_umma_ts_kernel" if d == 128 else f"mp_umma_kernel<{d}>",
-                   "fp32": "mp_fp32_kernel"}[precision]
+    kernel_name = {"f16": ("mp_f16_fused_kernel" if fused else "mp_f16_kernel") if d == 128 else "mp_f16_ss_kernel",
+                   "tf32": "mp_umma_ts_kernel" if d == 128 else f"mp_umma_kernel<{d}>", "fp32": "mp_fp32_kernel"}[precision]
     roofline = {"bound": "hbm", "kernel": kernel_name,
+                "what": "whole layer (contraction + mean + residual + ReLU + LayerNorm) in one kernel" if fused
+                        else "contraction kernel",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_contr,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_kernel,
                 "ms_per_launch": t_contr,
-                "layer": {"algorithmic_bytes": b_layer, "ms": t_layer,
-                          "achieved": b_layer / (t_layer * 1e-3) / 1e9 if t_layer > 0 else 0.0,
-                          "frac": (b_layer / (t_layer * 1e-3) / 1e9) / hbm_peak if t_layer > 0 else 0.0}}
+                "as_read": {"bytes_per_launch": r_kernel, "achieved": gbs(r_kernel, t_contr),
+                            "frac": gbs(r_kernel, t_contr) / hbm_peak,
+                            "what": "same accounting at the operand width the kernel moves (fp16 rows and weight "
+                                    "images on the f16 engine; fp32 residual in, fp32 + fp16 rows out)"},
+                "layer": {"algorithmic_bytes": b_layer, "ms": t_layer, "achieved": gbs(b_layer, t_layer),
+                          "frac": gbs(b_layer, t_layer) / hbm_peak,
+                          "what": "weight-image packing + layer kernel(s), per layer"},
+                "step": {"algorithmic_bytes": b_layer * L, "ms": ms, "achieved": gbs(b_layer * L, ms),
+                         "frac": gbs(b_layer * L, ms) / hbm_peak,
+                         "what": "the whole forward (dedup, text encoder, projection, graph build, generators, L "
+                                 "layers) charged only the L layers' algorithmic bytes: value / (E / (B_layer / "
+                                 "peak)); the north-star target is 0.60 of this"}}
 
     # ---- end to end through the C ABI with host buffers (rank 0 of a 1-GPU run)
     e2e = None
@@ -391,27 +488,54 @@ def main():
                  "peak_memory_gib": torch.cuda.max_memory_allocated(device) / 2**30,
                  "what": "prepared graph reused; loss = (out * W).sum(); gradients of every parameter"}
 
+    # ---- the same step on the other engines (fp32-tolerance context of an f16 / tf32 headline)
+    alt = None
+    if world == 1 and not args.no_alt and precision != "fp32":
+        alt = {}
+        try:
+            del out
+        except NameError:
+            pass
+        for other in [q for q in ("tf32", "fp32") if q != precision and (q != "tf32" or d in (32, 64, 128))]:
+            m2 = build_model(w, device, other)
+            torch.cuda.synchronize(device)
+            for _ in range(2):
+                o2 = m2.forward_packed(x, edge_index, utf8, offsets)
+            _native.profile_enable(True)
+            _native.profile_read()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k = 3
+            a0.record()
+            for _ in range(k):
+                o2 = m2.forward_packed(x, edge_index, utf8, offsets)
+            a1.record()
+            torch.cuda.synchronize(device)
+            prof2, n2 = _native.profile_read()
+            _native.profile_enable(False)
+            ms2 = a0.elapsed_time(a1) / k
+            tc2 = prof2["contraction_ms"] / max(n2, 1)
+            tl2 = (prof2["contraction_ms"] + prof2["epilogue_ms"] + prof2["prep_ms"]) / max(n2, 1)
+            alt[other] = {"ms_per_step": ms2, "value": E * L / (ms2 / 1e3), "unit": "edges/s/layer",
+                          "contraction_ms": tc2, "contraction_frac": gbs(b_contr, tc2) / hbm_peak,
+                          "layer_ms": tl2, "layer_frac": gbs(b_layer, tl2) / hbm_peak,
+                          "step_frac": gbs(b_layer * L, ms2) / hbm_peak,
+                          "tolerance": {"tf32": "upd 2e-3 of max, h 8e-4 abs (tests/_util.py)",
+                                        "fp32": "rtol 1e-4 / atol 2e-5 on upd, h (fp32 end to end)"}[other]}
+            del m2, o2
+        alt["note"] = ("engines: f16 = fp16 operand transport + tcgen05 kind::f16, tf32 = tcgen05 kind::tf32 on fp32 rows, "
+                       "fp32 = CUDA-core FFMA; all accumulate in fp32")
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = min(E, max(100_000, E // 10))      # a tenth of the edges, all nodes: ~20 s on 16 cores at c3
-        t = cpu_port_forward(w, sample)()
-        cpu = {"value": sample * L / t, "unit": "edges/s/layer", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"first {sample} edges of the workload, all {N} nodes, {L} layers, one pass of {t:.1f} s "
-                         "(numpy oracle = port of the reference algorithm; the per-node work is not scaled down)"}
+        cpu = cpu_baseline_subprocess(args)
 
     if rank == 0:
         line = {"metric": "hypergnn_fwd_edges_per_sec_per_layer", "value": value, "unit": "edges/s/layer",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": precision,
                 "data": "synthetic",
-                "config": {"workload": f"{w['name']} N={N} E={E} R={w['R']} d={d} L={L} T={w['T']} F={w['F']}"
-                                       + (" zipf-dst-rel" if args.skew else " uniform"),
-                           "step": "dedup + text encoder + input projection + graph build + L layers",
-                           "l2": (f"inputs larger than L2 (h {N * d * 4 / 1e9:.2f} GB, edges {E * 16 / 1e9:.2f} GB); "
-                                  "no explicit flush") if N * d * 4 > 256e6 else
-                                 "workload smaller than L2: 256 MB scratch written between steps",
-                           "parallelism": "single GPU" if world == 1 else f"dst-range x{world} + all-gather(h) per layer"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "config": make_config(w, world, args.skew),
+                "roofline": roofline, "precision_alt": alt, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "ms_each_step": [round(v, 3) for v in each],
                 "clocks": clocks.summary()}
         if train is not None:

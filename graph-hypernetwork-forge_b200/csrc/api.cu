@@ -42,6 +42,13 @@ extern "C" int64_t ghf_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
+extern "C" int ghf_copy_async(void* d_dst, const void* d_src, int64_t bytes, void* stream_) {
+  GHF_REQUIRE(bytes >= 0 && (bytes == 0 || (d_dst != nullptr && d_src != nullptr)), "ghf_copy_async: bad arguments");
+  if (bytes == 0) return 0;
+  GHF_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream_));
+  return 0;
+}
+
 extern "C" int ghf_device_ok(void) {
   static bool checked[64] = {false};   // per device, once: the calls below are not allowed during stream capture
   int dev = 0, major = 0;
@@ -107,12 +114,19 @@ std::mutex g_forward_lock;
 // text embeddings, so they run beside graph build and input projection instead of between the layers
 constexpr int kMaxSideLayers = 16;
 struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t text_ready = nullptr, weights_ready[kMaxSideLayers] = {};
+  cudaStream_t stream = nullptr;        // weight generators (+ operand-image packing) of every layer
+  cudaStream_t proj_stream = nullptr;   // input projection: independent of dedup and graph build
+  cudaEvent_t text_ready = nullptr, weights_ready[kMaxSideLayers] = {}, entry = nullptr, proj_done = nullptr,
+              forward_done = nullptr;
+  bool forward_recorded = false;
   cudaError_t init() {
     if (stream) return cudaSuccess;
     cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&proj_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&entry, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&proj_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&forward_done, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&text_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
     for (auto& ev : weights_ready)
       if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -122,6 +136,35 @@ struct SideStream {
 SideStream g_side[64];
 
 }  // namespace
+
+// GHF_FWD_TRACE=1: CUDA events on the main stream between the stages of the whole-forward entry, printed per call
+// (synchronises; diagnostics only).
+struct StageTrace {
+  bool on = getenv("GHF_FWD_TRACE") != nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    marks.push_back({name, e});
+  }
+  ~StageTrace() {
+    if (!on || marks.empty()) return;
+    cudaEventSynchronize(marks.back().second);
+    fprintf(stderr, "forward stages (ms):");
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      fprintf(stderr, " %s %.3f |", marks[i].first, ms);
+    }
+    float total = 0;
+    cudaEventElapsedTime(&total, marks.front().second, marks.back().second);
+    fprintf(stderr, " total %.3f\n", total);
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
+};
 
 // The whole forward on DEVICE buffers (HG:236-298); d_out receives the final embeddings [num_nodes, d].
 static int forward_device_impl(const ghf_model_desc* desc, const float* const* d_params, int64_t n_params,
@@ -172,9 +215,45 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   void* h16_0 = want_f16 ? A.take<uint16_t>((size_t)num_nodes * d) : nullptr;   // fp16 shadow buffers (ping-pong)
   void* h16_1 = want_f16 ? A.take<uint16_t>((size_t)num_nodes * d) : nullptr;
 
+  // The arenas are shared by consecutive forwards on this device: whatever stream the previous one ran on, this one
+  // starts after it (an event, not a host wait).
+  SideStream& side = g_side[dev];
+  const bool use_side = L <= kMaxSideLayers && side.init() == cudaSuccess;
+  if (use_side && side.forward_recorded) GHF_CUDA(cudaStreamWaitEvent(stream, side.forward_done, 0));
+  // Side work must be joined before an error return lets the caller free or reuse buffers.
+  struct JoinOnError {
+    SideStream* s;
+    bool armed;
+    ~JoinOnError() {
+      if (armed && s->stream) {
+        cudaStreamSynchronize(s->stream);
+        cudaStreamSynchronize(s->proj_stream);
+      }
+    }
+  } join{&side, use_side};
+
+  // HG:261  h = relu(input_proj(x))  (+ the fp16 shadow of h on the f16 path): depends on nothing but x, so it runs on
+  // its own stream beside dedup, text encoder and graph build (HBM-bound vs. sort passes: they overlap well)
+  cudaStream_t proj_stream = use_side ? side.proj_stream : stream;
+  auto project = [&]() -> int {
+    if (x_ready) GHF_CUDA(cudaStreamWaitEvent(proj_stream, x_ready, 0));
+    return ghf_linear_f16out(d_x, num_nodes, F, Win, bin, d, 1, nullptr, h0, h16_0, want_f16 ? scales : nullptr,
+                             proj_stream);
+  };
+  if (use_side) {
+    GHF_CUDA(cudaEventRecord(side.entry, stream));
+    GHF_CUDA(cudaStreamWaitEvent(proj_stream, side.entry, 0));
+    if (int rc = project()) return rc;
+    GHF_CUDA(cudaEventRecord(side.proj_done, proj_stream));
+  }
+
+  StageTrace trace;
+  trace.stream = stream;
+  trace.mark("start");
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
   if (int rc = ghf_dedup_texts(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream)) return rc;
+  trace.mark("dedup");
   const int prec = (desc->precision == GHF_PREC_F16 && (d == 64 || d == 128 || d == 256)) ? GHF_PREC_F16
                    : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
                                                                                            : GHF_PREC_FP32;
@@ -185,10 +264,14 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   // Linear (its input width is 128) and enough relations to fill it.
   const bool fuse = prec == GHF_PREC_F16 && mp_f16ss_supported(d) && H == 128 && depth >= 1 && U >= 64 &&
                     (int64_t)U * d * d >= (1 << 21) && !getenv("GHF_NO_FUSED_GENERATOR");
-  const size_t img_bytes = fuse ? (size_t)mp_f16ss_pack_bytes((int)Un, d) : 0;
+  // Hidden 128 on the f16 engine: fp32 weights are generated (70 MB at c3), and their fp16 operand images are packed
+  // on the generator's stream too, so the layers on the main stream start with their operands ready.
+  const bool prepack = !fuse && prec == GHF_PREC_F16 && mp_f16_supported(d) && U > 0;
+  const size_t img_bytes = fuse ? (size_t)mp_f16ss_pack_bytes((int)Un, d) : prepack ? (size_t)mp_f16_pack_bytes((int)Un) : 0;
   const size_t w_layer = fuse ? Arena::padded(img_bytes) + Arena::padded(Un * 4) + Arena::padded(Un * d * 4)
                               : 2 * Arena::padded(Un * d * d * 4) + Arena::padded(Un * d * 4);
-  GHF_CUDA(B.reserve(Arena::padded(Un * T * 4) + (size_t)L * w_layer + 4 * Arena::padded(Un * Hn * 4) + 8192));
+  GHF_CUDA(B.reserve(Arena::padded(Un * T * 4) + (size_t)L * (w_layer + (prepack ? Arena::padded(img_bytes) : 0)) +
+                     4 * Arena::padded(Un * Hn * 4) + 8192));
   float* temb = B.take<float>(Un * T);
   float* hid_a = B.take<float>(Un * Hn);
   float* hid_b = B.take<float>(Un * Hn);
@@ -204,14 +287,13 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
       outs[l] = {nullptr, nullptr, B.take<float>(Un * d)};
     } else {
       outs[l] = {B.take<float>(Un * d * d), B.take<float>(Un * d * d), B.take<float>(Un * d)};
+      if (prepack) images[l] = B.take<char>(img_bytes);
     }
   }
   const int n_out[3] = {d * d, d * d, d};
   if (int rc = ghf_text_encode(d_utf8, d_offs, first, U, emb, C, Wp, bp, T, temb, stream)) return rc;
 
   // WG:137-141 for the U distinct relations, every layer: on the side stream, beside graph build and projection
-  SideStream& side = g_side[dev];
-  const bool use_side = L <= kMaxSideLayers && side.init() == cudaSuccess;
   cudaStream_t gen_stream = use_side ? side.stream : stream;
   if (use_side) {
     GHF_CUDA(cudaEventRecord(side.text_ready, stream));
@@ -233,6 +315,8 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
                               layers[l].log_scale[m], outs[l][m], gen_stream))
         return rc;
     }
+    if (prepack)
+      if (int rc = mp_f16_pack_rel((int)U, outs[l][0], outs[l][1], images[l], gen_stream, false)) return rc;
     if (fuse && U > 0) {
       if (int rc = mp_f16ss_image_scales(zfin[0], zfin[1], H, U, layers[l].w[0][depth], layers[l].b[0][depth],
                                          layers[l].w[1][depth], layers[l].b[1][depth], d, layers[l].log_scale[0],
@@ -261,18 +345,18 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
     ghf_graph* g;
     ~Guard() { ghf_graph_free(g); }
   } guard{g};
+  trace.mark("text+graph");
   Arena& Cws = g_arena[dev][2];                          // third arena: the layer workspace (sized by the graph tables)
   const size_t ws_bytes = (size_t)ghf_mp_workspace_bytes(g, d, prec);
   GHF_CUDA(Cws.reserve(ws_bytes + 4096));
   void* ws = Cws.take<char>(ws_bytes);
 
-  // the node features are needed only now: a caller that copies them on another stream overlaps that copy with
-  // dedup and graph build
-  if (x_ready) GHF_CUDA(cudaStreamWaitEvent(stream, x_ready, 0));
-  // HG:261  h = relu(input_proj(x))  (+ the fp16 shadow of h on the f16 path)
-  if (int rc = ghf_linear_f16out(d_x, num_nodes, F, Win, bin, d, 1, nullptr, h0, h16_0, want_f16 ? scales : nullptr,
-                                 stream))
+  if (use_side) {
+    GHF_CUDA(cudaStreamWaitEvent(stream, side.proj_done, 0));
+  } else if (int rc = project()) {
     return rc;
+  }
+  trace.mark("proj-join");
   if (use_side)
     for (int l = 1; l < L; ++l) {
       if (int rc = generate(l)) return rc;
@@ -294,7 +378,7 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
     // HG:286-296
     void* out16 = (want_f16 && l + 1 < L) ? nxt16 : nullptr;
     float* dst = l + 1 < L ? nxt : d_out;                // the last layer writes the caller's buffer
-    if (fuse && U > 0) {
+    if ((fuse || prepack) && U > 0) {
       if (int rc = mp_layer_prepacked(g, cur, cur16, cur16 ? cur_sc : nullptr, images[l], outs[l][2], layers[l].ln_w,
                                       layers[l].ln_b, desc->ln_eps, dst, out16, out16 ? nxt_sc : nullptr, ws, stream))
         return rc;
@@ -303,11 +387,17 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
                                          out16 ? nxt_sc : nullptr, nullptr, ws, stream)) {
       return rc;
     }
+    trace.mark("layer");
     float* t = cur; cur = nxt; nxt = t;
     t = cur_sc; cur_sc = nxt_sc; nxt_sc = t;
     cur16 = out16;
     nxt16 = (nxt16 == h16_1) ? h16_0 : h16_1;
   }
+  if (use_side) {
+    GHF_CUDA(cudaEventRecord(side.forward_done, stream));
+    side.forward_recorded = true;
+  }
+  join.armed = false;                                    // everything was joined into `stream` by events
   return 0;
 }
 

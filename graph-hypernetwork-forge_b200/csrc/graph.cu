@@ -11,6 +11,8 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ghf_b200.h"
 #include "graph.cuh"
@@ -295,6 +297,9 @@ extern "C" int ghf_graph_build(const int64_t* d_edge_index, int64_t E, const uin
   g->stream = stream_;
   g->num_edges_in = E; g->num_nodes = num_nodes; g->dst_lo = dst_lo; g->dst_hi = dst_hi;
   g->num_local = dst_hi - dst_lo; g->num_rel = num_rel > 0 ? num_rel : 1; g->hidden_dim = hidden_dim;
+  if (sb_nodes <= 0) {
+    if (const char* env = getenv("GHF_SB_NODES")) sb_nodes = atoi(env);   // tuning knob for the whole-forward entries
+  }
   if (sb_nodes <= 0) {
     // Super-block size.  Small enough: the accumulator rows and the h[dst] rows of one super-block
     // (2 * d * 4 B per node) fit in ~48 MiB of L2, so reductions and destination gathers stay on chip.  But every

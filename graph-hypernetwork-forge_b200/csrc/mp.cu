@@ -314,9 +314,16 @@ extern "C" int ghf_profile_read(double ms[3], int64_t* launches) {
   return 0;
 }
 
+// accumulator region of the workspace: [local rows, d] floats, or the fused kernel's ring when that is larger
+static int64_t acc_region_bytes(const ghf_graph* g, int d, int precision) {
+  int64_t rows = g->num_local;
+  if (precision == GHF_PREC_F16 && mp_f16_supported(d) && mp_f16_fused_ring_rows(g) > rows) rows = mp_f16_fused_ring_rows(g);
+  return align_up(rows * (int64_t)d * 4, 256);
+}
+
 extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim, int precision) {
   if (!g) return -1;
-  int64_t bytes = 256 /* work counter */ + align_up(g->num_local * (int64_t)hidden_dim * 4, 256);
+  int64_t bytes = 256 /* work counter */ + acc_region_bytes(g, hidden_dim, precision);
   if (precision == GHF_PREC_TF32) bytes += mp_umma_pack_bytes(g->num_rel, hidden_dim);
   if (precision == GHF_PREC_F16)  // sync words, weight images, the fp16 copy of h made when the caller passes none
     bytes += mp_f16_sync_bytes(g) +
@@ -358,22 +365,37 @@ static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_
   return 0;
 }
 
+// what the fused layer kernel (mp_f16_fused.cu) needs beyond the contraction's own arguments
+struct FusedEpilogue {
+  const float *h, *ln_w, *ln_b;
+  float eps;
+  float *out, *upd;
+  void* out16;
+  float* out16_scale;
+};
+
 // The contraction of one layer: acc[v] = sum over in-edges of [h_u | h_v] @ [W_msg[r] ; W_self[r]] + bias[r].
 // `acc_ext` (optional) receives the sums; otherwise they stay in the workspace for the epilogue.  -> *acc_used.
 static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
                            const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
                            float* acc_ext, bool accumulate, bool transposed, void* d_workspace, cudaStream_t stream,
-                           float** acc_used, ProfRec* rec, const void* prepacked = nullptr) {
+                           float** acc_used, ProfRec* rec, const void* prepacked = nullptr,
+                           const FusedEpilogue* fe = nullptr, bool* fused_done = nullptr) {
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
   // (the f16 kernel clears the accumulator itself and keeps per-phase sync words next to the counter)
   const bool f16_ss = precision == GHF_PREC_F16 && mp_f16ss_supported(d);   // hidden 256: streamed weights
+  const bool fused = fe != nullptr && precision == GHF_PREC_F16 && !f16_ss && mp_f16_supported(d) &&
+                     mp_f16_fused_enabled(g) && fe->ln_w != nullptr && fe->ln_b != nullptr &&
+                     (reinterpret_cast<uintptr_t>(fe->ln_w) | reinterpret_cast<uintptr_t>(fe->ln_b) |
+                      reinterpret_cast<uintptr_t>(fe->h) | reinterpret_cast<uintptr_t>(fe->out) |
+                      reinterpret_cast<uintptr_t>(fe->upd) | reinterpret_cast<uintptr_t>(fe->out16)) % 16 == 0;
   const bool self_clearing = precision == GHF_PREC_F16 && !f16_ss && g->num_units > 0;
   int* counter = reinterpret_cast<int*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
   float* acc_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) +
                                            (precision == GHF_PREC_F16 ? mp_f16_sync_bytes(g) : 256));
-  const int64_t acc_bytes = align_up(nl * (int64_t)d * 4, 256);
+  const int64_t acc_bytes = acc_region_bytes(g, d, precision);
   void* pack = reinterpret_cast<char*>(acc_ws) + acc_bytes;
   float* acc = acc_ext ? acc_ext : acc_ws;
   *acc_used = acc;
@@ -393,7 +415,7 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
   const bool plain = prepacked || (!transposed && d_W_msg != nullptr && d_W_self != nullptr && d_bias != nullptr);
   GHF_REQUIRE(plain || (precision == GHF_PREC_F16 && mp_f16_supported(d) && (d_W_msg != nullptr || d_W_self != nullptr)),
               "ghf_mp_contract: transposed / NULL weight tensors need precision f16 and hidden_dim 128");
-  const int skip_half = d_W_msg == nullptr ? 1 : (d_W_self == nullptr ? 2 : 0);
+  const int skip_half = prepacked ? 0 : (d_W_msg == nullptr ? 1 : (d_W_self == nullptr ? 2 : 0));
   const bool ts = mp_ts_enabled(d);
   const void* h16 = d_h16;
   const float* h16_scale = d_h16_scale;
@@ -427,6 +449,10 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
               : mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream);
     } else if (f16_ss) {
       rc = mp_f16ss_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream);
+    } else if (fused) {    // contraction + row epilogue in one kernel; the accumulator region is its ring
+      rc = mp_f16_fused_launch(g, h16, h16_scale, d_bias, pack, acc_ws, counter, fe->h, fe->ln_w, fe->ln_b, fe->eps,
+                               fe->out, fe->upd, fe->out16, fe->out16_scale, stream);
+      if (fused_done) *fused_done = true;
     } else if (precision == GHF_PREC_F16) {
       rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream, accumulate, skip_half);
     } else if (d <= 32) {
@@ -467,11 +493,15 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
   if (prof)
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
   float* acc = nullptr;
+  const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale};
+  bool fused_done = false;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
-                               false, false, d_workspace, stream, &acc, prof ? &rec : nullptr))
+                               false, false, d_workspace, stream, &acc, prof ? &rec : nullptr, nullptr, &fe,
+                               &fused_done))
     return rc;
-  if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream))
-    return rc;
+  if (!fused_done)
+    if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream))
+      return rc;
   if (prof) {
     GHF_CUDA(cudaEventRecord(rec.e[3], stream));
     g_prof.push_back(rec);
@@ -484,7 +514,8 @@ int mp_layer_prepacked(const ghf_graph* g, const float* d_h, const void* d_h16, 
                        const void* images, const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
                        float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace, cudaStream_t stream) {
   if (int rc = check_layer_args(g, d_workspace, GHF_PREC_F16, d_h16, d_h16_scale)) return rc;
-  GHF_REQUIRE(images != nullptr && mp_f16ss_supported(g->hidden_dim), "mp_layer_prepacked: hidden_dim 64 / 256 only");
+  GHF_REQUIRE(images != nullptr && (mp_f16ss_supported(g->hidden_dim) || mp_f16_supported(g->hidden_dim)),
+              "mp_layer_prepacked: hidden_dim 64 / 128 / 256 only");
   g->stream = stream;
   if (g->num_local == 0) return 0;
   ProfRec rec{};
@@ -492,11 +523,14 @@ int mp_layer_prepacked(const ghf_graph* g, const float* d_h, const void* d_h16, 
   if (prof)
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
   float* acc = nullptr;
+  const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, nullptr, d_out16, d_out16_scale};
+  bool fused_done = false;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, nullptr, nullptr, d_bias, GHF_PREC_F16, nullptr, false,
-                               false, d_workspace, stream, &acc, prof ? &rec : nullptr, images))
+                               false, d_workspace, stream, &acc, prof ? &rec : nullptr, images, &fe, &fused_done))
     return rc;
-  if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, nullptr, d_out16, d_out16_scale, stream))
-    return rc;
+  if (!fused_done)
+    if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, nullptr, d_out16, d_out16_scale, stream))
+      return rc;
   if (prof) {
     GHF_CUDA(cudaEventRecord(rec.e[3], stream));
     g_prof.push_back(rec);

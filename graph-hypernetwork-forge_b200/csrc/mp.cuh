@@ -33,6 +33,9 @@ int64_t mp_f16_pack_bytes(int num_rel);
 // W_msg or W_self may be NULL (zeros); `transposed`: the images are built from W[r]^T
 int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream,
                 bool transposed = false);
+// the same without a graph (the whole-forward entry packs on the generator's stream, before the graph exists)
+int mp_f16_pack_rel(int num_rel, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream,
+                    bool transposed = false);
 // fp16 shadow of h: (h16, scale[2]) with h = h16 * scale[0], scale[1] = max|h| (see common.cuh).
 // absmax: scale[1] = max|x|.  convert: scale chosen from scale[1], scale[0] written, h16 = fp16(h * s); with
 // `rescue` the shadow already holds fp16(h) and is rewritten only if the range demands a scale.
@@ -45,6 +48,17 @@ int64_t mp_f16_sync_bytes(const ghf_graph* g);
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
                   const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc = false,
                   int skip_half = 0);   // skip_half: 1 = no source term (W_msg NULL), 2 = no destination term
+
+// The whole layer in one kernel (mp_f16_fused.cu, hidden_dim 128): the contraction reduces into a ring of L2-resident
+// accumulator windows and the row epilogue (mean, residual, ReLU, LayerNorm, fp16 shadow) runs per super-block inside
+// the same kernel.  `ring`: mp_f16_fused_ring_rows(g) x 128 floats; sync_words: mp_f16_sync_bytes(g); `upd`, `out16`
+// optional.  GHF_MP_FUSED=0 falls back to mp_f16_launch + the separate epilogue kernel.
+bool mp_f16_fused_enabled(const ghf_graph* g);
+int64_t mp_f16_fused_ring_rows(const ghf_graph* g);
+int mp_f16_fused_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias,
+                        const void* pack_scratch, float* ring, int* sync_words, const float* h, const float* ln_w,
+                        const float* ln_b, float eps, float* out, float* upd, void* out16, float* out16_scale,
+                        cudaStream_t stream);
 
 // hidden_dim 256 / 64 with streamed fp16 weights (mp_f16_ss.cu): operand images [R][256 KiB / 16 KiB] + inverse
 // scales [R]; acc must be zero at entry, `unit_counter` one zeroed int

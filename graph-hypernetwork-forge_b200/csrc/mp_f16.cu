@@ -595,7 +595,8 @@ uint32_t env_flags() {
 
 bool mp_f16_supported(int d) { return d == kD; }
 
-int64_t mp_f16_sync_bytes(const ghf_graph* g) { return align_up(256 + g->num_phases * 4, 256); }
+// [0, 256): counters | then two int32 per super-block (mp_f16_kernel uses one, mp_f16_fused_kernel both)
+int64_t mp_f16_sync_bytes(const ghf_graph* g) { return align_up(256 + g->num_phases * 8, 256); }
 
 int64_t mp_f16_pack_bytes(int num_rel) {
   return align_up((int64_t)num_rel * kImageBytes, 256) + align_up((int64_t)num_rel * 4, 256);
@@ -604,13 +605,18 @@ int64_t mp_f16_pack_bytes(int num_rel) {
 int mp_f16_pack(const ghf_graph* g, const float* W_msg, const float* W_self, void* pack_scratch,
                 cudaStream_t stream, bool transposed) {
   GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
+  return mp_f16_pack_rel(g->num_rel, W_msg, W_self, pack_scratch, stream, transposed);
+}
+
+int mp_f16_pack_rel(int num_rel, const float* W_msg, const float* W_self, void* pack_scratch, cudaStream_t stream,
+                    bool transposed) {
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(W_msg) | reinterpret_cast<uintptr_t>(W_self) |
                reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
               "mp_f16: W_msg / W_self / scratch must be 16-byte aligned");
   __half* img = reinterpret_cast<__half*>(pack_scratch);
   float* inv = reinterpret_cast<float*>(reinterpret_cast<char*>(pack_scratch) +
-                                        align_up((int64_t)g->num_rel * kImageBytes, 256));
-  pack_f16_kernel<<<(unsigned)g->num_rel, 256, 0, stream>>>(W_msg, W_self, img, inv, transposed ? 1 : 0);
+                                        align_up((int64_t)num_rel * kImageBytes, 256));
+  pack_f16_kernel<<<(unsigned)num_rel, 256, 0, stream>>>(W_msg, W_self, img, inv, transposed ? 1 : 0);
   GHF_LAUNCH_CHECK();
   return 0;
 }

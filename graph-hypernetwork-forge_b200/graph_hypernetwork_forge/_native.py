@@ -77,6 +77,7 @@ def lib():
                                               c_int64, P, P, P, P]),
         "ghf_hypergnn_forward_device": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
                                                 c_int64, P, P, P, P]),
+        "ghf_copy_async": (c_int, [P, P, c_int64, P]),
         "ghf_launch_count": (c_int64, [c_int]),
         "ghf_profile_enable": (c_int, [c_int]),
         "ghf_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
@@ -97,7 +98,7 @@ EXPORTED_SYMBOLS = (
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
     "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
     "ghf_text_encode_backward", "ghf_weight_images_bytes", "ghf_weight_images_f16", "ghf_mp_layer_images",
-    "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_copy_async", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -199,6 +200,17 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_
                                        _ptr(y), _ptr(y16.data) if y16 else None, _ptr(y16.scale) if y16 else None,
                                        _stream(dev)), "ghf_linear_f16out")
     return (y, y16) if want_f16 else y
+
+
+def copy_async(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """Stream-ordered raw copy src -> dst (same byte size, contiguous); dst may be a peer-mapped view of another
+    GPU's buffer (torch symmetric memory): the copy engines move the rows over NVLink, no SM is used."""
+    if not (dst.is_contiguous() and src.is_contiguous()) or dst.numel() * dst.element_size() != src.numel() * src.element_size():
+        raise RuntimeError("copy_async: contiguous tensors of equal byte size")
+    dev = src.device
+    with torch.cuda.device(dev):
+        _check(lib().ghf_copy_async(_ptr(dst), _ptr(src), src.numel() * src.element_size(), _stream(dev)),
+               "ghf_copy_async")
 
 
 def absmax(x: torch.Tensor, shadow: Shadow) -> None:
@@ -399,16 +411,25 @@ class Graph:
         return ws
 
     def mp_layer(self, h, W_msg, W_self, bias, ln_w, ln_b, eps: float, precision: int, out=None,
-                 want_upd: bool = False, h16=None, out16=None):
+                 want_upd: bool = False, h16=None, out16=None, h_row0=None):
         """One message-passing layer on this graph's destination range -> (out, upd or None).
 
         `h16` (Shadow of [N, d], optional) is the fp16 shadow of `h` the PREC_F16 contraction gathers from (made
-        inside when absent); `out16` (Shadow of [local nodes, d], optional) receives the shadow of `out`."""
+        inside when absent); `out16` (Shadow of [local nodes, d], optional) receives the shadow of `out`.
+        `h_row0` (PREC_F16 with `h16` only): `h` holds just the rows [h_row0, h_row0 + len(h)) of the fp32 features
+        - enough, because with a shadow the fp32 rows are read only at this graph's own destinations (residual)."""
         dev = self.device
         h, W_msg, W_self, bias = _f32(h), _f32(W_msg), _f32(W_self), _f32(bias)
         ln_w, ln_b = _f32(ln_w), _f32(ln_b)
         d = self.hidden_dim
-        if h.shape != (self.num_nodes, d):
+        h_ptr = _ptr(h)
+        if h_row0 is not None:
+            if precision != PREC_F16 or h16 is None:
+                raise RuntimeError("h_row0 needs precision f16 and the fp16 shadow h16")
+            if h.dim() != 2 or h.shape[1] != d or h_row0 > self.dst_lo or h_row0 + h.shape[0] < self.dst_hi:
+                raise RuntimeError(f"h rows [{h_row0},{h_row0 + h.shape[0]}) must cover [{self.dst_lo},{self.dst_hi})")
+            h_ptr = c_void_p(h.data_ptr() - int(h_row0) * d * 4)     # row dst_lo of this pointer is h[dst_lo - h_row0]
+        elif h.shape != (self.num_nodes, d):
             raise RuntimeError(f"h must be [{self.num_nodes},{d}], got {tuple(h.shape)}")
         if W_msg.shape != (self.num_rel, d, d) or W_self.shape != (self.num_rel, d, d) or \
                 bias.shape != (self.num_rel, d):
@@ -423,7 +444,7 @@ class Graph:
                 raise RuntimeError(f"{name} must be a Shadow of a [{rows},{d}] matrix")
         ws = self.workspace(precision)
         with torch.cuda.device(dev):
-            _check(lib().ghf_mp_layer_f16(self._h, _ptr(h), _ptr(h16.data) if h16 else None,
+            _check(lib().ghf_mp_layer_f16(self._h, h_ptr, _ptr(h16.data) if h16 else None,
                                           _ptr(h16.scale) if h16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
                                           _ptr(ln_w), _ptr(ln_b), float(eps), precision, _ptr(out),
                                           _ptr(out16.data) if out16 else None, _ptr(out16.scale) if out16 else None,

@@ -334,7 +334,9 @@ class HyperGNN(nn.Module):
         Small graphs are launch-bound (BASELINE config 2: ~50 kernels of a few microseconds each); after the graph
         tables are built nothing in the forward needs the host (the fp16 scales are chosen on the device), so the
         whole sequence is captured once and replayed with one launch.  Copy new features into `static_input`
-        (same shape), call `replay()`, read `static_output`.  Parameters are read at replay time, in place."""
+        (same shape), call `replay()`, read `static_output`.  Parameters are read at replay time, in place (do not
+        reallocate them, e.g. by `model.to(...)`, between capture and replay).  `replay` keeps `prepared` alive: the
+        captured kernels hold raw pointers into its graph tables and workspace."""
         dev = _native.require_cuda(node_features, self.input_proj.weight)
         static_in = node_features.clone()
         side = torch.cuda.Stream(device=dev)
@@ -346,7 +348,10 @@ class HyperGNN(nn.Module):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             static_out = self.forward_prepared(static_in, prepared)
-        return graph.replay, static_in, static_out
+
+        def replay(_keep=(prepared, graph, static_in, static_out)):
+            _keep[1].replay()
+        return replay, static_in, static_out
 
     def _generate(self, layer: int, text_embs: torch.Tensor, num_unique: int) -> dict:
         d = self.hidden_dim

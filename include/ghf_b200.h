@@ -122,7 +122,8 @@ int ghf_mp_layer(const ghf_graph* g, const float* d_h, const float* d_W_msg, con
  * layer instead of re-converting):
  *   (d_h16, d_h16_scale)       shadow of d_h ([num_nodes, d] fp16 + float[2]), or NULL/NULL (then it is made inside,
  *                              in the workspace).  When given, d_h is only read at rows [dst_lo, dst_hi)
- *                              (residual), so a multi-GPU caller all-gathers only the fp16 rows between layers.
+ *                              (residual), so a multi-GPU caller exchanges only the fp16 rows between layers and may
+ *                              keep just its own fp32 rows: d_h = (pointer to row dst_lo) - dst_lo * d floats.
  *   (d_out16, d_out16_scale)   shadow of d_out ([local nodes, d] fp16 + float[2]) for the next layer, or NULL/NULL
  *                              (hidden_dim 32/64/128).  Its scale follows from ln_w / ln_b alone
  *                              (|LayerNorm(x)_c| <= sqrt(d-1)|w_c| + |b_c|), so every rank picks the same one.
@@ -216,6 +217,12 @@ int ghf_hypergnn_forward_device(const ghf_model_desc* desc, const float* const* 
                                 int64_t n_params, const float* d_node_features, int64_t num_nodes,
                                 const int64_t* d_edge_index, int64_t E, const uint8_t* d_utf8,
                                 const int64_t* d_offsets, float* d_out, void* stream);
+
+/* ---- multi-GPU plumbing --------------------------------------------------------------------------
+ * Stream-ordered copy between device buffers that may live on different GPUs of one box (peer-mapped / symmetric
+ * memory): a rank pushes the fp16 rows it has just computed into every peer's copy of h16 over NVLink with the copy
+ * engines - no SM is taken from the contraction kernel that is still running on the next chunk of rows. */
+int ghf_copy_async(void* d_dst, const void* d_src, int64_t bytes, void* stream);
 
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t ghf_launch_count(int reset);

@@ -359,6 +359,43 @@ def test_forward_packed_single_native_call_matches_staged_path():
         assert_close(got.cpu().numpy(), want.cpu().numpy(), 1e-4, 5e-5, f"forward_packed d={d} {prec}")
 
 
+def test_fused_layer_kernel_matches_oracle_over_several_ring_turns(monkeypatch):
+    """GHF_MP_FUSED=1 (off by default: slower than contraction + separate epilogue on B200): contraction,
+    mean, residual, ReLU, LayerNorm and fp16 shadow in one kernel over a ring of accumulator windows.  Small
+    super-blocks make the ring turn several times (20 phases over 2 and 3 slots); both entries against the oracle."""
+    from graph_hypernetwork_forge import HyperGNN, _text
+    N, E, R, d, L = 20000, 300000, 37, 128, 3
+    src, dst, rel, names, feats = O.synthetic_kg(N, E, R, 40, seed=99)
+    texts = [names[r] for r in rel]
+    torch.manual_seed(7)
+    model = HyperGNN(32, 40, d, L, precision="f16").eval()
+    with torch.no_grad():
+        for gen in model.weight_generators:
+            for p in gen.log_scales.values():
+                p.fill_(-1.0)
+    ref_taps = {}
+    ref = O.hypergnn_forward(model_params_numpy(model), feats, np.stack([src, dst]), texts, d, L, dtype=np.float64,
+                             taps=ref_taps)
+    model = model.to(DEV)
+    ei, x = torch.from_numpy(np.stack([src, dst])).to(DEV), torch.from_numpy(feats).to(DEV)
+    data, offs = _text.pack_utf8(texts)
+    utf8, offsets = torch.from_numpy(data.copy()).to(DEV), torch.from_numpy(offs).to(DEV)
+    monkeypatch.setenv("GHF_MP_FUSED", "1")
+    monkeypatch.setenv("GHF_SB_NODES", "1024")
+    for slots in ("2", "3"):
+        monkeypatch.setenv("GHF_FUSED_SLOTS", slots)
+        taps = {}
+        out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, N), taps=taps).cpu().numpy()
+        for l in range(L):
+            assert_rel_to_max(taps[f"upd.{l}"].cpu().numpy(), ref_taps[f"upd.{l}"], TC_UPD_REL["f16"],
+                              f"upd.{l} f16 fused slots={slots}")
+            assert_close(taps[f"h.{l}"].cpu().numpy(), ref_taps[f"h.{l}"], 0.0, TC_H_ATOL_SCALE1["f16"],
+                         f"h.{l} f16 fused slots={slots}")
+        assert_close(out, ref, 0.0, TC_H_ATOL_SCALE1["f16"], f"out f16 fused slots={slots}")
+        packed = model.forward_packed(x, ei, utf8, offsets).cpu().numpy()
+        assert_close(packed, ref, 0.0, TC_H_ATOL_SCALE1["f16"], f"out f16 fused forward_packed slots={slots}")
+
+
 def test_generator_written_operand_images_match_the_packed_path():
     """Hidden 64 / 256 on the f16 engine, enough relations and generator width 128: the one-call forward lets the
     generator's last Linear write the fp16 operand images itself (no fp32 W_msg / W_self, scales from an analytic
@@ -442,6 +479,9 @@ def test_cuda_graph_replay_of_prepared_forward():
     prepared = model.prepare_ids(ei, torch.from_numpy(rel).to(DEV), list(names), N)
     want = model.forward_prepared(x, prepared).clone()
     replay, static_in, static_out = model.capture_prepared(x, prepared)
+    del prepared                                         # the replay closure keeps the graph tables alive
+    prepared = model.prepare_ids(ei, torch.from_numpy(rel).to(DEV), list(names), N)
+    torch.cuda.empty_cache()
     replay()
     torch.cuda.synchronize()
     assert_close(static_out.cpu().numpy(), want.cpu().numpy(), 1e-4, 5e-5, "graph replay")
