@@ -42,6 +42,9 @@ WORKLOADS = {
     # one eighth of BASELINE config 5 (50M nodes, 500M edges over 8 GPUs): the hidden-64 kernels at a rank's edge count
     "c5s": dict(name="large-shape-1/8", N=6_250_000, E=62_500_000, R=1000, d=64, L=2, T=64, F=64),
     "c4": dict(name="zero-shot-20k-rel", N=100_000, E=2_000_000, R=20_000, d=256, L=2, T=64, F=256),
+    # BASELINE config 5: dst-partitioned across the GPUs of one box; every rank generates its own shard (features of
+    # its rows, the edges pointing into them) and goes in through the ids-in entry - no global edge list exists
+    "c5": dict(name="large-50M-500M", N=50_000_000, E=500_000_000, R=1000, d=64, L=2, T=64, F=64, sharded_inputs=True),
 }
 NAME_LEN = 14  # len("relation_00000")
 
@@ -130,6 +133,18 @@ def make_device_inputs(w, device, seed=0, skew=False):
     return x, edge_index, rel, utf8, offsets
 
 
+def make_shard_inputs(w, device, lo, hi, n_edges, seed):
+    """One rank's shard of a pre-sharded workload: features of rows [lo, hi), `n_edges` edges with uniform sources
+    over all N nodes and uniform destinations in [lo, hi), uniform relation ids.  Seeded per shard, so any rank can
+    regenerate any shard (the parity check on rank 0 does)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    src = torch.randint(0, w["N"], (n_edges,), generator=g, device=device, dtype=torch.int64)
+    dst = torch.randint(lo, max(hi, lo + 1), (n_edges,), generator=g, device=device, dtype=torch.int64)
+    rel = torch.randint(0, w["R"], (n_edges,), generator=g, device=device, dtype=torch.int32)
+    x = torch.randn(hi - lo, w["F"], generator=g, device=device, dtype=torch.float32)
+    return x, torch.stack([src, dst]), rel
+
+
 def build_model(w, device, precision):
     from graph_hypernetwork_forge import HyperGNN
     torch.manual_seed(0)
@@ -168,7 +183,8 @@ def make_config(w, world, skew):
             "l2": (f"inputs larger than L2 (h {N * d * 4 / 1e9:.2f} GB, edges {E * 16 / 1e9:.2f} GB); "
                    "no explicit flush") if N * d * 4 > 256e6 else
                   "workload smaller than L2: 256 MB scratch written between steps",
-            "parallelism": "single GPU" if world == 1 else f"dst-range x{world} + all-gather(h) per layer"}
+            "parallelism": "single GPU" if world == 1 else
+                           f"dst-range x{world}; fp16 rows of h exchanged per layer over NVLink; output stays sharded"}
 
 
 def sampled_workload(w, edges, seed=0):
@@ -296,6 +312,10 @@ def main():
                     help="enqueue the stages from Python (prepare_packed + forward_prepared) instead of one native call")
     ap.add_argument("--train", action="store_true",
                     help="also time a training step (forward + backward on a prepared graph) -> key 'train_step'")
+    ap.add_argument("--chunks", type=int, default=2, help="multi-GPU: pieces of a rank's rows whose exchange overlaps the next piece")
+    ap.add_argument("--transport", default=None, choices=["p2p", "collective"], help="multi-GPU row exchange")
+    ap.add_argument("--balance", default="nodes", choices=["nodes", "edges"], help="multi-GPU: destination ranges by node count or by edges")
+    ap.add_argument("--no-check", action="store_true", help="multi-GPU: skip the comparison with a single-GPU forward")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the tf32 / fp32 engines (precision_alt)")
@@ -318,7 +338,15 @@ def main():
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
     dist = None
+    nccl_env = {}
     if world > 1:
+        # NVLink only (north_star): no InfiniBand, P2P through NVLink; NCCL's INFO lines go to a file that rank 0
+        # summarises in the JSON line (stdout must stay one JSON line)
+        for k, v in (("NCCL_IB_DISABLE", "1"), ("NCCL_P2P_LEVEL", "NVL"), ("NCCL_DEBUG", "INFO"),
+                     ("NCCL_DEBUG_SUBSYS", "INIT,GRAPH"),
+                     ("NCCL_DEBUG_FILE", f"/tmp/ghf_nccl_{os.getpid()}.log")):
+            os.environ.setdefault(k, v)
+        nccl_env = {k: os.environ[k] for k in ("NCCL_IB_DISABLE", "NCCL_P2P_LEVEL", "NCCL_DEBUG", "NCCL_DEBUG_FILE")}
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
 
@@ -328,23 +356,46 @@ def main():
     if w["d"] not in (32, 64, 128, 256):
         precision = "fp32"
     model = build_model(w, device, precision)
-    x, edge_index, _rel, utf8, offsets = make_device_inputs(w, device, skew=args.skew)
     N, E, L, d = w["N"], w["E"], w["L"], w["d"]
+    pre_sharded = bool(w.get("sharded_inputs"))
+    names = [f"relation_{r:05d}" for r in range(w["R"])]
+    if not pre_sharded:
+        x, edge_index, _rel, utf8, offsets = make_device_inputs(w, device, skew=args.skew)
 
-    if world == 1:
+    sharded = None
+    if world == 1 and not pre_sharded:
         def step():
             if args.python_path:    # the same stages enqueued one by one from Python (~60 native calls per forward)
                 with torch.no_grad():
                     return model.forward_prepared(x, model.prepare_packed(edge_index, utf8, offsets, N))
             return model.forward_packed(x, edge_index, utf8, offsets)   # one native call per forward
         n_local = N
-    else:
-        from graph_hypernetwork_forge.distributed import ShardedForward
-        sharded = ShardedForward(model, N, dist.group.WORLD)
-        n_local = sharded.hi - sharded.lo
+    elif world == 1:
+        # a pre-sharded workload on one GPU: the single shard is the whole graph, through the ids-in entry
+        x, edge_index, rel_ids = make_shard_inputs(w, device, 0, N, E, seed=1000)
+        n_local = N
 
         def step():
-            return sharded.forward_packed(x, edge_index, utf8, offsets)
+            return model.forward_prepared(x, model.prepare_ids(edge_index, rel_ids, names, N))
+    else:
+        from graph_hypernetwork_forge.distributed import ShardedForward, plan_partition, plan_partition_by_edges
+        ranges = None
+        if args.balance == "edges" and not pre_sharded:
+            indeg = torch.bincount(edge_index[1], minlength=N)
+            rowptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
+            rowptr[1:] = torch.cumsum(indeg, 0)
+            ranges = plan_partition_by_edges(rowptr, world)
+        sharded = ShardedForward(model, N, dist.group.WORLD, ranges=ranges, transport=args.transport, chunks=args.chunks)
+        n_local = sharded.hi - sharded.lo
+        if pre_sharded:
+            per = [E // world + (1 if r < E % world else 0) for r in range(world)]
+            x, edge_index, rel_ids = make_shard_inputs(w, device, sharded.lo, sharded.hi, per[rank], seed=1000 + rank)
+
+            def step():
+                return sharded.forward_ids(x, edge_index, rel_ids, names)
+        else:
+            def step():
+                return sharded.forward_packed(x, edge_index, utf8, offsets)
 
     def barrier():
         if dist is not None:
@@ -396,10 +447,12 @@ def main():
     value = E * L / (ms / 1e3)
 
     hbm_peak, peak_src = peaks()
-    local_edges = E if world == 1 else sharded.num_kept
-    b_contr, b_layer = algorithmic_bytes(w, local_edges, n_local, N)
+    local_edges = E if sharded is None else sharded.num_kept
+    # a rank's layer may be several launches (chunks whose row exchange overlaps the next chunk's compute)
+    per_layer = max(1, round(n_layers_timed / max(1, L * args.steps)))
+    b_contr, b_layer = algorithmic_bytes(w, local_edges / per_layer, n_local / per_layer, N)
     fused = precision == "f16" and d == 128 and os.environ.get("GHF_MP_FUSED", "0") == "1"
-    r_contr, r_layer = bytes_as_read(w, local_edges, n_local, precision, fused)
+    r_contr, r_layer = bytes_as_read(w, local_edges / per_layer, n_local / per_layer, precision, fused)
     t_contr = prof["contraction_ms"] / max(n_layers_timed, 1)
     t_layer = (prof["contraction_ms"] + prof["epilogue_ms"] + prof["prep_ms"]) / max(n_layers_timed, 1)
     # the dominant kernel: the fused layer kernel does the whole layer, so it is charged the layer's bytes
@@ -427,15 +480,114 @@ def main():
                 "layer": {"algorithmic_bytes": b_layer, "ms": t_layer, "achieved": gbs(b_layer, t_layer),
                           "frac": gbs(b_layer, t_layer) / hbm_peak,
                           "what": "weight-image packing + layer kernel(s), per layer"},
-                "step": {"algorithmic_bytes": b_layer * L, "ms": ms, "achieved": gbs(b_layer * L, ms),
-                         "frac": gbs(b_layer * L, ms) / hbm_peak,
+                "step": {"algorithmic_bytes": algorithmic_bytes(w, E, N, N)[1] * L, "ms": ms,
+                         "achieved": gbs(algorithmic_bytes(w, E, N, N)[1] * L, ms),
+                         "frac": gbs(algorithmic_bytes(w, E, N, N)[1] * L, ms) / (hbm_peak * world),
                          "what": "the whole forward (dedup, text encoder, projection, graph build, generators, L "
                                  "layers) charged only the L layers' algorithmic bytes: value / (E / (B_layer / "
                                  "peak)); the north-star target is 0.60 of this"}}
 
+    # ---- multi-GPU: parity against a single-GPU forward, stage split, transport, end to end
+    multi = None
+    if sharded is not None:
+        out_local = step()
+        parity = None
+        if not args.no_check:
+            # every rank holds the model; rank 0 (any rank for the replicated workloads) runs the same inputs on ONE
+            # GPU and compares its own rows.  Pre-sharded: rank 0 regenerates every shard.
+            err = torch.zeros(1, device=device, dtype=torch.float64)
+            rows = torch.zeros(1, device=device, dtype=torch.float64)
+            if not pre_sharded:
+                single = model.forward_packed(x, edge_index, utf8, offsets)
+                if n_local:
+                    err[0] = float((single[sharded.lo:sharded.hi] - out_local).abs().max())
+                rows[0] = n_local
+                del single
+            elif rank == 0:
+                from graph_hypernetwork_forge.distributed import plan_partition as _pp
+                per = [E // world + (1 if r < E % world else 0) for r in range(world)]
+                shards = [make_shard_inputs(w, device, lo_r, hi_r, per[r], seed=1000 + r)
+                          for r, (lo_r, hi_r) in enumerate(sharded.ranges)]
+                xf = torch.cat([t[0] for t in shards])
+                eif = torch.cat([t[1] for t in shards], dim=1)
+                relf = torch.cat([t[2] for t in shards])
+                del shards
+                single = model.forward_prepared(xf, model.prepare_ids(eif, relf, names, N))
+                err[0] = float((single[sharded.lo:sharded.hi] - out_local).abs().max())
+                rows[0] = n_local
+                del single, xf, eif, relf
+                torch.cuda.empty_cache()
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            dist.all_reduce(rows)
+            parity = {"max_abs_diff": float(err.item()), "rows_compared": int(rows.item()),
+                      "against": "the single-GPU forward of the same inputs" +
+                                 (" (rank 0 regenerates all shards; its own rows)" if pre_sharded else " (every rank, its own rows)"),
+                      "tolerance": 1.5e-4, "ok": bool(err.item() <= 1.5e-4)}
+        pushed = None
+        if sharded._sym is not None:
+            sharded._sym.bytes_pushed = 0
+            out_local = step()
+            pushed = sharded._sym.bytes_pushed
+        sharded.profile = True
+        for _ in range(3):
+            out_local = step()
+        stages = {k: v / 3 for k, v in sharded.stage_ms().items()}
+        sharded.profile = False
+        st = torch.tensor([stages["prep"], stages["compute"], stages["wait"]], device=device, dtype=torch.float64)
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        # end to end: the rank's inputs in pinned host memory -> device, forward, own rows back to the host
+        e2e_multi = None
+        if not args.no_e2e:
+            host = [t.cpu().pin_memory() for t in ((x, edge_index, rel_ids) if pre_sharded else
+                                                     (x[sharded.lo:sharded.hi], edge_index, utf8, offsets))]
+            hout = torch.empty(n_local, d, dtype=torch.float32).pin_memory()
+
+            def e2e_step():
+                dev_in = [t.to(device, non_blocking=True) for t in host]
+                if pre_sharded:
+                    o = sharded.forward_ids(dev_in[0], dev_in[1], dev_in[2], names)
+                else:
+                    o = sharded.forward_packed(dev_in[0], dev_in[1], dev_in[2], dev_in[3])
+                hout.copy_(o, non_blocking=True)
+                torch.cuda.synchronize(device)
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            k = max(1, min(args.steps, 3))
+            for _ in range(k):
+                e2e_step()
+            barrier()
+            tt = torch.tensor([1e3 * (time.perf_counter() - t0) / k], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            h2d = sum(t.numel() * t.element_size() for t in host)
+            e2e_multi = {"value": E * L / (float(tt.item()) / 1e3), "unit": "edges/s/layer", "ms_per_step": float(tt.item()),
+                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(hout.numel() * 4),
+                         "api": "ShardedForward.forward_" + ("ids" if pre_sharded else "packed") +
+                                " per rank, pinned host buffers, own rows back; bytes are per rank"}
+        transport_lines = []
+        try:
+            with open(os.environ.get("NCCL_DEBUG_FILE", "")) as f:
+                keep = [ln.strip() for ln in f if any(t in ln for t in ("via P2P", "NVLS", "via NET", "via SHM", "Connected", "NCCL version"))]
+            transport_lines = keep[:3] + keep[-5:]
+        except Exception:
+            pass
+        multi = {"transport": sharded.transport, "chunks": len(sharded._chunk_ranges()), "balance": args.balance,
+                 "ranges_rows": [hi_r - lo_r for lo_r, hi_r in sharded.ranges],
+                 "edges_per_rank_max": int(local_edges), "parity": parity,
+                 "stage_ms_max_over_ranks": {"prep": float(st[0]), "compute": float(st[1]), "exposed_exchange": float(st[2])},
+                 "bytes_pushed_per_step_per_rank": pushed,
+                 "output": "sharded: every rank keeps its own rows (SURVEY 8e)",
+                 "nccl_env": nccl_env, "nccl_log": transport_lines}
+        if rank == 0:
+            for ln in transport_lines:
+                print("[nccl] " + ln, file=sys.stderr)
+        e2e_override = e2e_multi
+    else:
+        e2e_override = None
+
     # ---- end to end through the C ABI with host buffers (rank 0 of a 1-GPU run)
-    e2e = None
-    if world == 1 and not args.no_e2e:
+    e2e = e2e_override
+    if world == 1 and not pre_sharded and not args.no_e2e:
         from graph_hypernetwork_forge import _native as nat
         hx = x.cpu().pin_memory()
         hei = edge_index.cpu().pin_memory()
@@ -490,7 +642,7 @@ def main():
 
     # ---- the same step on the other engines (fp32-tolerance context of an f16 / tf32 headline)
     alt = None
-    if world == 1 and not args.no_alt and precision != "fp32":
+    if world == 1 and not pre_sharded and not args.no_alt and precision != "fp32":
         alt = {}
         try:
             del out
@@ -535,7 +687,8 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": precision,
                 "data": "synthetic",
                 "config": make_config(w, world, args.skew),
-                "roofline": roofline, "precision_alt": alt, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "precision_alt": alt, "cpu_baseline": cpu, "e2e": e2e, "multi_gpu": multi,
+                "gpu_launches": launches,
                 "ms_each_step": [round(v, 3) for v in each],
                 "clocks": clocks.summary()}
         if train is not None:

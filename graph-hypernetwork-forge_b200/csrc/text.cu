@@ -3,7 +3,7 @@
 // Strings arrive packed: UTF-8 bytes + int64 offsets.  Dedup keys are whole byte strings (UTF-8 is
 // injective on Python strings, so this equals the reference's dict-key equality); ids are ranks in
 // first-occurrence order, bit-exact with `list(dict.fromkeys(edge_texts))`.
-#include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 #include "ghf_b200.h"
@@ -69,16 +69,23 @@ __device__ __forceinline__ bool same_string(const uint8_t* __restrict__ data,
 // a smaller id in the slot skips the atomic: with few distinct strings almost every edge does.
 // Work item j is string `subset[j]` (ascending ids) or string j itself; the table holds work-item indices, so
 // "smallest index" is "first occurrence" either way.
+// The table is SMALL by default (2^20 slots, 4 MiB: it lives in L2 and needs no 100 MB clear): a thread that probes
+// more than `max_probes` slots raises `overflow` and the host retries with a table of 2 n slots.
 __global__ void dedup_insert_kernel(const uint8_t* __restrict__ data, const int64_t* __restrict__ off,
                                     int64_t E, const uint32_t* __restrict__ subset, int64_t n,
-                                    uint32_t* __restrict__ table, uint64_t mask, uint32_t* __restrict__ slot_of) {
+                                    uint32_t* __restrict__ table, uint64_t mask, uint32_t* __restrict__ slot_of,
+                                    uint32_t max_probes, int32_t* __restrict__ overflow) {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int64_t e = subset ? subset[j] : j;
   const int64_t total = off[E], limit = total & ~(int64_t)3;
   const int64_t s0 = off[e];
   uint64_t slot = hash_string(data, s0, off[e + 1] - s0, limit, total) & mask;
-  for (;;) {
+  for (uint32_t probes = 0;; ++probes) {
+    if (probes > max_probes) {
+      *overflow = 1;
+      break;
+    }
     uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&table[slot]);
     if (cur == kEmpty) {
       cur = atomicCAS(&table[slot], kEmpty, (uint32_t)j);
@@ -94,24 +101,34 @@ __global__ void dedup_insert_kernel(const uint8_t* __restrict__ data, const int6
   slot_of[j] = (uint32_t)slot;
 }
 
-__global__ void dedup_flag_kernel(const uint32_t* __restrict__ table, const uint32_t* __restrict__ slot_of,
-                                  int64_t E, int32_t* __restrict__ flag) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e < E) flag[e] = table[slot_of[e]] == (uint32_t)e;
+// Occupied slots -> (representative work item, slot) pairs, in any order; *count = number of distinct strings.
+__global__ void dedup_compact_kernel(const uint32_t* __restrict__ table, uint64_t cap, uint32_t* __restrict__ reps,
+                                     uint32_t* __restrict__ slots, int32_t* __restrict__ count, int64_t max_out) {
+  const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (s >= cap) return;
+  const uint32_t rep = table[s];
+  if (rep == kEmpty) return;
+  const int i = atomicAdd(count, 1);
+  if (i < max_out) {
+    reps[i] = rep;
+    slots[i] = (uint32_t)s;
+  }
 }
 
-__global__ void dedup_assign_kernel(const uint32_t* __restrict__ table, const uint32_t* __restrict__ slot_of,
-                                    const int32_t* __restrict__ rank, const uint32_t* __restrict__ subset,
-                                    int64_t n, int32_t* __restrict__ rel_ids, int64_t* __restrict__ first_edge,
-                                    int64_t* __restrict__ num_unique) {
+// Pairs sorted by representative = first-occurrence order: rank i goes to slot slots[i], first_edge[i] = that string.
+__global__ void dedup_rank_kernel(const uint32_t* __restrict__ reps, const uint32_t* __restrict__ slots, int64_t U,
+                                  const uint32_t* __restrict__ subset, int32_t* __restrict__ rank_of_slot,
+                                  int64_t* __restrict__ first_edge) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= U) return;
+  rank_of_slot[slots[i]] = (int32_t)i;
+  if (first_edge) first_edge[i] = subset ? (int64_t)subset[reps[i]] : (int64_t)reps[i];
+}
+
+__global__ void dedup_assign_kernel(const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ rank_of_slot,
+                                    int64_t n, int32_t* __restrict__ rel_ids) {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const uint32_t rep = table[slot_of[j]];
-  rel_ids[j] = rank[rep];
-  if (rep == (uint32_t)j) {
-    if (first_edge) first_edge[rank[j]] = subset ? (int64_t)subset[j] : j;
-  }
-  if (j == n - 1) *num_unique = rank[j] + (rep == (uint32_t)j ? 1 : 0);
+  if (j < n) rel_ids[j] = rank_of_slot[slot_of[j]];
 }
 
 // One block per unique string: mean-pool character embeddings, project, tanh.
@@ -208,7 +225,7 @@ extern "C" int ghf_dedup_texts(const uint8_t* d_utf8, const int64_t* d_offsets, 
                                const uint32_t* d_subset, int64_t n_subset, int32_t* d_rel_ids,
                                int64_t* d_first_edge, int64_t* h_num_unique, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  GHF_REQUIRE(E >= 0 && E < (int64_t)0xFFFFFFFE, "ghf_dedup_texts: E=%lld out of range", (long long)E);
+  GHF_REQUIRE(E >= 0 && E <= (int64_t)0x7FFFFFFF, "ghf_dedup_texts: E=%lld out of range", (long long)E);
   GHF_REQUIRE(reinterpret_cast<uintptr_t>(d_utf8) % 4 == 0, "ghf_dedup_texts: d_utf8 must be 4-byte aligned");
   GHF_REQUIRE(d_subset == nullptr || (n_subset >= 0 && n_subset <= E), "ghf_dedup_texts: bad subset size");
   const int64_t n = d_subset ? n_subset : E;   // work items: the strings of the subset, or all of them
@@ -216,39 +233,55 @@ extern "C" int ghf_dedup_texts(const uint8_t* d_utf8, const int64_t* d_offsets, 
     if (h_num_unique) *h_num_unique = 0;
     return 0;
   }
-  uint64_t cap = 64;
-  while (cap < (uint64_t)n * 2) cap <<= 1;
-  TempBuf table, slot_of, flag, rank, scan_tmp, count;
-  GHF_CUDA(table.alloc(cap * sizeof(uint32_t), stream));
+  // Knowledge graphs have few distinct relation strings (BASELINE: 7 ... 20k), so the hash table starts small enough
+  // to stay in L2; a graph with more than 2^19 distinct strings (e.g. the reference-shaped _message_passing entry,
+  // where every edge is its own relation) is detected and redone with the worst-case table.
+  uint64_t full = 64;
+  while (full < (uint64_t)n * 2) full <<= 1;
+  constexpr uint64_t kSmall = 1ull << 20;
+  TempBuf slot_of, words;
   GHF_CUDA(slot_of.alloc(n * sizeof(uint32_t), stream));
-  GHF_CUDA(flag.alloc(n * sizeof(int32_t), stream));
-  GHF_CUDA(rank.alloc(n * sizeof(int32_t), stream));
-  GHF_CUDA(count.alloc(sizeof(int64_t), stream));
-  GHF_CUDA(cudaMemsetAsync(table.p, 0xFF, cap * sizeof(uint32_t), stream));
+  GHF_CUDA(words.alloc(2 * sizeof(int32_t), stream));          // [0] distinct strings, [1] overflow
   const int threads = 256;
   const unsigned blocks = (unsigned)cdiv(n, threads);
-  dedup_insert_kernel<<<blocks, threads, 0, stream>>>(d_utf8, d_offsets, E, d_subset, n, table.as<uint32_t>(),
-                                                      cap - 1, slot_of.as<uint32_t>());
-  GHF_LAUNCH_CHECK();
-  dedup_flag_kernel<<<blocks, threads, 0, stream>>>(table.as<uint32_t>(), slot_of.as<uint32_t>(), n,
-                                                    flag.as<int32_t>());
-  GHF_LAUNCH_CHECK();
-  size_t tmp_bytes = 0;
-  GHF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag.as<int32_t>(), rank.as<int32_t>(),
-                                         (int)n, stream));
-  GHF_CUDA(scan_tmp.alloc(tmp_bytes, stream));
-  GHF_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, flag.as<int32_t>(), rank.as<int32_t>(),
-                                         (int)n, stream));
-  g_launches.fetch_add(2, std::memory_order_relaxed);
-  dedup_assign_kernel<<<blocks, threads, 0, stream>>>(table.as<uint32_t>(), slot_of.as<uint32_t>(),
-                                                      rank.as<int32_t>(), d_subset, n, d_rel_ids, d_first_edge,
-                                                      count.as<int64_t>());
-  GHF_LAUNCH_CHECK();
-  if (h_num_unique) {
-    GHF_CUDA(cudaMemcpyAsync(h_num_unique, count.p, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  for (uint64_t cap = full < kSmall ? full : kSmall;; cap = full) {
+    const int64_t max_u = (int64_t)(cap / 2 < (uint64_t)n ? cap / 2 : (uint64_t)n);   // load factor <= 1/2
+    TempBuf table, reps, slots, rank_of_slot;
+    GHF_CUDA(table.alloc(cap * sizeof(uint32_t), stream));
+    GHF_CUDA(reps.alloc(2 * max_u * sizeof(uint32_t), stream));    // double buffers of the pair sort
+    GHF_CUDA(slots.alloc(2 * max_u * sizeof(uint32_t), stream));
+    GHF_CUDA(rank_of_slot.alloc(cap * sizeof(int32_t), stream));
+    GHF_CUDA(cudaMemsetAsync(table.p, 0xFF, cap * sizeof(uint32_t), stream));
+    GHF_CUDA(cudaMemsetAsync(words.p, 0, 2 * sizeof(int32_t), stream));
+    dedup_insert_kernel<<<blocks, threads, 0, stream>>>(d_utf8, d_offsets, E, d_subset, n, table.as<uint32_t>(),
+                                                        cap - 1, slot_of.as<uint32_t>(),
+                                                        cap == full ? 0xFFFFFFFFu : 4096u, words.as<int32_t>() + 1);
+    GHF_LAUNCH_CHECK();
+    dedup_compact_kernel<<<(unsigned)cdiv((int64_t)cap, threads), threads, 0, stream>>>(
+        table.as<uint32_t>(), cap, reps.as<uint32_t>(), slots.as<uint32_t>(), words.as<int32_t>(), max_u);
+    GHF_LAUNCH_CHECK();
+    int32_t h_words[2] = {0, 0};
+    GHF_CUDA(cudaMemcpyAsync(h_words, words.p, sizeof(h_words), cudaMemcpyDeviceToHost, stream));
     GHF_CUDA(cudaStreamSynchronize(stream));
+    if ((h_words[1] != 0 || h_words[0] > max_u) && cap != full) continue;   // too many distinct strings: full table
+    const int64_t U = h_words[0];
+    cub::DoubleBuffer<uint32_t> kbuf(reps.as<uint32_t>(), reps.as<uint32_t>() + max_u);
+    cub::DoubleBuffer<uint32_t> vbuf(slots.as<uint32_t>(), slots.as<uint32_t>() + max_u);
+    size_t tmp_bytes = 0;
+    TempBuf tmp;
+    GHF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kbuf, vbuf, (int)U, 0, 32, stream));
+    GHF_CUDA(tmp.alloc(tmp_bytes, stream));
+    GHF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, kbuf, vbuf, (int)U, 0, 32, stream));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    dedup_rank_kernel<<<(unsigned)cdiv(U, threads), threads, 0, stream>>>(kbuf.Current(), vbuf.Current(), U, d_subset,
+                                                                         rank_of_slot.as<int32_t>(), d_first_edge);
+    GHF_LAUNCH_CHECK();
+    dedup_assign_kernel<<<blocks, threads, 0, stream>>>(slot_of.as<uint32_t>(), rank_of_slot.as<int32_t>(), n,
+                                                        d_rel_ids);
+    GHF_LAUNCH_CHECK();
+    if (h_num_unique) *h_num_unique = U;
+    return 0;
   }
-  return 0;
 }
 
 extern "C" int ghf_text_encode(const uint8_t* d_utf8, const int64_t* d_offsets, const int64_t* d_string_index,

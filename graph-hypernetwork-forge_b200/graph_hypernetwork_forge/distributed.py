@@ -1,26 +1,41 @@
-"""Multi-GPU forward: 1-D destination-range partition + one all-gather of h per layer.
+"""Multi-GPU forward: 1-D destination-range partition, one exchange of h per layer.
 
-The reference is single-process; this is the scaling design BASELINE.json's
-north_star prescribes.  One process per GPU.  Rank k owns destination rows [lo_k, hi_k): it keeps
-every edge whose destination falls in that range (sources are arbitrary, so each rank holds all
-of h), runs the message-passing layer for its rows, writes them into its slice of the next h and
-all-gathers the slices (NCCL over NVLink; gloo in the CPU tests of the host logic).  Generated
-relation weights are replicated: every rank runs the text encoder and the generators itself.
+The reference is single-process; this is the scaling design BASELINE.json's north_star prescribes
+(SURVEY 8e).  One process per GPU.  Rank k owns destination rows [lo_k, hi_k): it keeps every edge whose destination
+falls in that range (sources are arbitrary, so each rank needs all of h as gather source), runs the layers for its
+rows and makes the new rows visible to every rank.  Generated relation weights are replicated: every rank runs the
+text encoder and the generators itself.
 
-`plan_partition` is pure host logic (unit-tested on CPU with gloo, world_size 2).
+What travels, and how:
+
+  * On the f16 engine (hidden 64 / 128) the kernels gather from the fp16 SHADOW of h and read fp32 h only at a rank's
+    own rows (residual).  So a rank keeps fp32 rows for its own range only, and only fp16 rows travel - half the bytes.
+  * transport "p2p" (default on CUDA): the shadow lives in torch symmetric memory, [N, d] fp16 on every rank, two
+    buffers (read layer l / write layer l + 1).  A rank's epilogue kernel writes the new rows into its own copy;
+    a side stream then pushes them into every peer's copy with plain device-to-device copies over NVLink (copy
+    engines - the persistent contraction kernel owns every SM, a collective kernel could not run beside it), chunk
+    by chunk while the next chunk of rows is still being computed, and a device-side barrier closes the layer.
+    No staging buffer, no equal-size constraint: ranges may be balanced by EDGES (`plan_partition_by_edges`).
+  * transport "collective" (gloo on CPU, or NCCL when symmetric memory is unavailable): an in-place all-gather of
+    padded equal slices, or one broadcast per rank when the ranges are uneven.
+  * The result stays sharded - `forward*` return the rank's own rows [hi - lo, d] ("the last layer's
+    output can stay sharded"); `gather_output=True` all-gathers the fp32 rows for callers that want the reference's
+    full [N, d] return value on every rank.
+
+`plan_partition`, `plan_partition_by_edges` and the collective transport are host logic, unit-tested on CPU with gloo
+(world_size 2, tests/test_distributed_cpu.py); the p2p transport needs GPUs (tests/test_gpu_multi.py, bench.py).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
 
 def plan_partition(num_nodes: int, world_size: int) -> Tuple[int, List[Tuple[int, int]]]:
-    """Equal destination ranges, padded so every rank contributes the same number of rows to the
-    all-gather.  -> (rows_per_rank, [(lo, hi)] * world_size); hi - lo may be < rows_per_rank (even 0)
-    on trailing ranks."""
+    """Equal destination ranges, padded so every rank contributes the same number of rows to an all-gather.
+    -> (rows_per_rank, [(lo, hi)] * world_size); hi - lo may be < rows_per_rank (even 0) on trailing ranks."""
     if world_size < 1 or num_nodes < 0:
         raise ValueError("world_size must be >= 1 and num_nodes >= 0")
     rows = -(-num_nodes // world_size) if num_nodes else 0
@@ -31,127 +46,383 @@ def plan_partition(num_nodes: int, world_size: int) -> Tuple[int, List[Tuple[int
     return rows, ranges
 
 
+def plan_partition_by_edges(rowptr, world_size: int, node_weight: float = 1.0) -> List[Tuple[int, int]]:
+    """Contiguous destination ranges balanced by WORK instead of by node count (power-law in-degree makes
+    equal-node ranges unbalanced).  `rowptr` [N + 1] is the exclusive scan of the in-degrees of all nodes (the
+    dst-CSR row pointer).  Work of a range = its edges + node_weight * its nodes (the per-node epilogue is not free);
+    boundary k is the first node where the cumulative work reaches k / world_size of the total.  Deterministic:
+    every rank computes the same ranges from the same rowptr."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    rp = torch.as_tensor(rowptr).to(torch.float64).cpu()
+    n = rp.numel() - 1
+    if n < 0:
+        raise ValueError("rowptr must have at least one entry")
+    work = rp + node_weight * torch.arange(n + 1, dtype=torch.float64)
+    targets = work[-1] * torch.arange(1, world_size, dtype=torch.float64) / world_size
+    cuts = torch.searchsorted(work, targets, right=False).clamp_(0, n).tolist()
+    bounds = [0] + [int(c) for c in cuts] + [n]
+    for i in range(1, len(bounds)):                      # monotone even with empty ranges
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
 def gather_rows(buf: torch.Tensor, rows: int, rank: int, group, async_op: bool = False):
     """In-place all-gather: rank r has filled buf[r*rows:(r+1)*rows]; afterwards every rank has all of buf.
     async_op: returns the work handle; kernels enqueued before `.wait()` overlap the transfer."""
     return dist.all_gather_into_tensor(buf, buf[rank * rows:(rank + 1) * rows], group=group, async_op=async_op)
 
 
+def exchange_rows(buf: torch.Tensor, ranges: Sequence[Tuple[int, int]], rank: int, group, async_op: bool = False):
+    """Every rank has filled buf[lo_r:hi_r] of its own range; afterwards every rank has all rows.  Equal padded
+    ranges (plan_partition) go through one in-place all-gather; uneven ranges (plan_partition_by_edges) through one
+    broadcast per rank.  -> list of work handles (empty when not async)."""
+    world = len(ranges)
+    rows = ranges[0][1] - ranges[0][0]
+    equal = all(lo == r * rows for r, (lo, _) in enumerate(ranges)) and buf.shape[0] >= rows * world
+    if equal and rows > 0:
+        w = gather_rows(buf, rows, rank, group, async_op)
+        return [w] if async_op else []
+    works = []
+    for r, (lo, hi) in enumerate(ranges):
+        if hi > lo:
+            src = dist.get_global_rank(group, r) if group is not None else r
+            w = dist.broadcast(buf[lo:hi], src=src, group=group, async_op=async_op)
+            if async_op:
+                works.append(w)
+    return works
+
+
+class _SymmetricRows:
+    """[N, d] fp16 table replicated on every rank in torch symmetric memory (two buffers).  A rank writes its own
+    rows locally and pushes them into the peers' copies with device-to-device copies on a side stream."""
+
+    def __init__(self, num_rows: int, d: int, group, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _native
+        self._native = _native
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        name = group.group_name if hasattr(group, "group_name") else dist.group.WORLD.group_name
+        try:                                            # older torch needs the group enabled explicitly
+            if hasattr(symm, "is_symm_mem_enabled_for_group") and not symm.is_symm_mem_enabled_for_group(name):
+                symm.enable_symm_mem_for_group(name)
+        except Exception:  # noqa: BLE001
+            pass
+        self.bufs, self.handles, self.peers = [], [], []
+        for _ in range(2):
+            t = symm.empty((max(num_rows, 1), d), dtype=torch.float16, device=device)
+            hdl = symm.rendezvous(t, name)
+            self.bufs.append(t)
+            self.handles.append(hdl)
+            self.peers.append([t if r == self.rank else hdl.get_buffer(r, tuple(t.shape), torch.float16)
+                               for r in range(self.world)])
+        self.comm = torch.cuda.Stream(device=device)
+        self.bytes_pushed = 0
+
+    def push(self, b: int, lo: int, hi: int) -> None:
+        """Rows [lo, hi) of buffer b, already written locally by work enqueued on the CURRENT stream, go to every
+        peer (enqueued on the side stream, after that work)."""
+        if hi <= lo or self.world == 1:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.comm.wait_event(ev)
+        src = self.bufs[b][lo:hi]
+        with torch.cuda.stream(self.comm):
+            for k in range(1, self.world):              # start with the next rank: the pushes of all ranks interleave
+                r = (self.rank + k) % self.world
+                self._native.copy_async(self.peers[b][r][lo:hi], src)
+        self.bytes_pushed += (self.world - 1) * src.numel() * 2
+
+    def close_layer(self, b: int) -> None:
+        """All pushes of every rank into buffer b have landed everywhere before anything enqueued on the CURRENT stream
+        after this call runs (device-side barrier on the side stream; the host does not wait)."""
+        if self.world == 1:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))   # peers must not be signalled before our own compute
+        self.comm.wait_event(ev)
+        with torch.cuda.stream(self.comm):
+            self.handles[b].barrier(channel=0)
+            done = torch.cuda.Event()
+            done.record(self.comm)
+        torch.cuda.current_stream(self.device).wait_event(done)
+
+
 class ShardedForward:
-    """HyperGNN forward over a destination-partitioned graph (one instance per rank)."""
+    """HyperGNN forward over a destination-partitioned graph (one instance per rank).
 
-    def __init__(self, model, num_nodes: int, group=None):
-        self.model, self.group = model, group
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
+    ranges: optional [(lo, hi)] per rank (e.g. from `plan_partition_by_edges`); default equal node counts.
+    transport: "p2p" | "collective" | None (p2p on CUDA when symmetric memory works, else collective).
+    chunks: the rank's range is processed in this many pieces so that the rows of a finished piece travel while the
+    next one is computed (p2p transport, f16 engine)."""
+
+    def __init__(self, model, num_nodes: int, group=None, ranges=None, transport: Optional[str] = None,
+                 chunks: int = 1):
+        self.model = model
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
         self.num_nodes = num_nodes
-        self.rows, ranges = plan_partition(num_nodes, self.world)
-        self.lo, self.hi = ranges[self.rank]
+        self.rows, equal = plan_partition(num_nodes, self.world)
+        self.ranges = [tuple(map(int, r)) for r in (ranges if ranges is not None else equal)]
+        if len(self.ranges) != self.world or self.ranges[0][0] != 0 or self.ranges[-1][1] != num_nodes or \
+                any(a[1] != b[0] for a, b in zip(self.ranges, self.ranges[1:])):
+            raise ValueError("ranges must tile [0, num_nodes) in rank order")
+        self.lo, self.hi = self.ranges[self.rank]
+        self.transport = transport
+        self.chunks = max(1, int(chunks))
         self.num_kept = 0
+        self.profile = False          # True: CUDA events on the main stream between the stages (read with `stage_ms`)
+        self._marks: List[Tuple[str, torch.cuda.Event]] = []
         self._bufs: Optional[List[torch.Tensor]] = None
+        self._sym: Optional[_SymmetricRows] = None
 
-    def _buffers(self, device, d):
-        if self._bufs is None:
-            shape = (self.rows * self.world, d)
-            self._bufs = [torch.zeros(shape, dtype=torch.float32, device=device) for _ in range(2)]
-        return self._bufs
+    def _mark(self, label: str) -> None:
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((label, ev))
 
-    def _buffers16(self, device, d):
-        if getattr(self, "_bufs16", None) is None:
-            from . import _native
-            shape = (self.rows * self.world, d)
-            self._bufs16 = [_native.Shadow(torch.zeros(shape, dtype=torch.float16, device=device)) for _ in range(2)]
-        return self._bufs16
+    def stage_ms(self) -> dict:
+        """Main-stream time per stage of the profiled forwards since the last call (synchronises): `prep` (projection
+        of the own rows, edge selection, dedup, graph build, text encoder, first generator), `compute` (layer kernels
+        + generators), `wait` (the main stream waiting for rows to arrive = exposed exchange time)."""
+        out = {"prep": 0.0, "compute": 0.0, "wait": 0.0}
+        if self._marks:
+            self._marks[-1][1].synchronize()
+        for (_, a), (label, b) in zip(self._marks, self._marks[1:]):
+            if label != "start":
+                out[label] += a.elapsed_time(b)
+        self._marks = []
+        return out
 
-    def forward_packed(self, node_features, edge_index, utf8, offsets) -> torch.Tensor:
-        # the projection of this rank's rows and the all-gather of their fp16 shadow do not depend on the graph:
-        # they are enqueued first, and the rows travel over NVLink while edge selection, dedup and graph build run
+    # ------------------------------------------------------------------ helpers
+    def _f16_engine(self) -> bool:
+        from . import _native
+        m = self.model
+        return m._precision_code() == _native.PREC_F16 and m.hidden_dim in (64, 128)
+
+    def _symmetric(self, device) -> Optional[_SymmetricRows]:
+        if self.transport == "collective" or device.type != "cuda":
+            return None
+        if self._sym is None:
+            try:
+                self._sym = _SymmetricRows(self.num_nodes, self.model.hidden_dim, self.group, device)
+            except Exception as e:  # noqa: BLE001
+                if self.transport == "p2p":
+                    raise RuntimeError(f"p2p transport unavailable: {e!r}") from e
+                self.transport = "collective"
+                return None
+            self.transport = "p2p"
+        return self._sym
+
+    def _chunk_ranges(self) -> List[Tuple[int, int]]:
+        n, c = self.hi - self.lo, self.chunks
+        if n <= 0 or c == 1:
+            return [(self.lo, self.hi)]
+        step = -(-n // c)
+        step = -(-step // 64) * 64                       # whole 64-row groups: 8/16 KiB-aligned row blocks
+        return [(lo, min(lo + step, self.hi)) for lo in range(self.lo, self.hi, step)]
+
+    def _local_rows(self, node_features: torch.Tensor) -> torch.Tensor:
+        """Features of this rank's own rows: accepts all [N, F] rows or just the [hi - lo, F] local ones."""
+        if node_features.shape[0] == self.num_nodes:
+            return node_features[self.lo:self.hi]
+        if node_features.shape[0] == self.hi - self.lo:
+            return node_features
+        raise RuntimeError(f"node_features must have {self.num_nodes} or {self.hi - self.lo} rows")
+
+    def _gather_output(self, local: torch.Tensor) -> torch.Tensor:
+        """[hi - lo, d] on each rank -> [N, d] on every rank (fp32 rows over the collective)."""
+        d = local.shape[1]
+        full = torch.empty((max(self.rows * self.world, self.num_nodes), d), dtype=local.dtype, device=local.device)
+        full[self.lo:self.hi] = local
+        exchange_rows(full, self.ranges, self.rank, self.group)
+        return full[:self.num_nodes]
+
+    # ------------------------------------------------------------------ entries
+    def forward_packed(self, node_features, edge_index, utf8, offsets, gather_output: bool = False) -> torch.Tensor:
+        """Full edge list + packed relation strings on every rank; the rank selects its own edges."""
+        from . import _native
+        from .models.hypergnn import PackedTexts
+        m = self.model
+        self._mark("start")
+        started = self._start_h0(node_features)          # the rows travel while edge selection and graph build run
+        device = _native.require_cuda(edge_index, utf8, offsets, m.input_proj.weight)
+        subset = None
+        if (self.lo, self.hi) != (0, self.num_nodes):
+            subset = _native.select_edges(edge_index, self.lo, self.hi)
+        packed = PackedTexts(None, device, utf8, offsets, subset)
+        return self._run(node_features, edge_index, packed, started, gather_output)
+
+    def forward(self, node_features, edge_index, edge_texts, gather_output: bool = False) -> torch.Tensor:
+        """The reference's call shape (List[str]); every rank holds the full edge list."""
+        from . import _native
+        from .models.hypergnn import PackedTexts
+        if edge_index.size(1) != len(edge_texts):
+            raise ValueError(f"edge_index has {edge_index.size(1)} edges but edge_texts has {len(edge_texts)} entries")
+        self._mark("start")
         started = self._start_h0(node_features)
-        prepared = self.model.prepare_packed(edge_index, utf8, offsets, self.num_nodes, dst_range=(self.lo, self.hi))
-        return self.forward_prepared(node_features, prepared, _started=started)
+        device = _native.require_cuda(edge_index, self.model.input_proj.weight)
+        packed = PackedTexts(edge_texts, device)
+        return self._run(node_features, edge_index, packed, started, gather_output)
 
-    def forward(self, node_features, edge_index, edge_texts) -> torch.Tensor:
-        prepared = self.model.prepare(edge_index, edge_texts, self.num_nodes, dst_range=(self.lo, self.hi))
-        return self.forward_prepared(node_features, prepared)
+    def forward_ids(self, node_features, edge_index, rel_ids, unique_texts, gather_output: bool = False) -> torch.Tensor:
+        """ids-in entry for PRE-SHARDED edge lists: `edge_index` holds only edges whose destination
+        lies in this rank's range (edges outside it are ignored), `rel_ids[e]` indexes `unique_texts`, the same
+        vocabulary on every rank.  The way in for graphs whose global edge list fits no single GPU (BASELINE config 5)."""
+        from . import _native
+        from .models.hypergnn import RelationIds
+        if edge_index.size(1) != rel_ids.numel():
+            raise ValueError(f"edge_index has {edge_index.size(1)} edges but rel_ids has {rel_ids.numel()} entries")
+        self._mark("start")
+        started = self._start_h0(node_features)
+        device = _native.require_cuda(edge_index, self.model.input_proj.weight)
+        packed = RelationIds(rel_ids, unique_texts, device)
+        return self._run(node_features, edge_index, packed, started, gather_output)
 
-    def forward_prepared(self, node_features, prepared, _started=None) -> torch.Tensor:
-        """-> [num_nodes, hidden] on every rank (the last layer's slices are gathered as well)."""
+    def forward_prepared(self, node_features, prepared, _started=None, gather_output: bool = True) -> torch.Tensor:
+        """Round-1 entry kept for callers that built the rank's graph themselves (`model.prepare*(dst_range=...)`):
+        full [N, d] result on every rank by default."""
+        graph, packed = prepared.graph, prepared.packed
+        if (graph.dst_lo, graph.dst_hi) != (self.lo, self.hi):
+            raise RuntimeError("the prepared graph covers another destination range")
+        started = _started if _started is not None else self._start_h0(node_features)
+        return self._layers(node_features, [graph], packed, started, gather_output)
+
+    # ------------------------------------------------------------------ the forward
+    def _run(self, node_features, edge_index, packed, started, gather_output):
+        import os
         from . import _native
         m = self.model
         if m.training and m.dropout > 0.0:
             raise NotImplementedError("the multi-GPU path is inference-only (no dropout, no gradients)")
-        graph, packed = prepared.graph, prepared.packed
-        self.num_kept = graph.num_kept
+        graphs = []
+        chunks = self._chunk_ranges() if (started is not None and self._sym is not None) else [(self.lo, self.hi)]
+        for lo, hi in chunks:
+            graphs.append(_native.Graph(edge_index, packed.rel_ids, self.num_nodes, max(packed.num_unique, 1),
+                                        m.hidden_dim, dst_lo=lo, dst_hi=hi,
+                                        sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
+                                        unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset))
+        return self._layers(node_features, graphs, packed, started, gather_output)
+
+    def _layers(self, node_features, graphs, packed, started, gather_output):
+        self.num_kept = sum(g.num_kept for g in graphs)
+        if started is not None:
+            local = self._layers_f16(graphs, packed, started)
+        else:
+            local = self._layers_generic(node_features, graphs[0], packed)
+        return self._gather_output(local) if gather_output else local
+
+    def _layers_generic(self, node_features, graph, packed) -> torch.Tensor:
+        """fp32 / tf32 engines (and hidden sizes without an f16 engine): fp32 rows of h travel, over the collective."""
+        from . import _native
+        m = self.model
         N, d = self.num_nodes, m.hidden_dim
         prec = m._precision_code()
-        cur, nxt = self._buffers(node_features.device, d)
-        if prec == _native.PREC_F16 and d == 128:
-            return self._forward_f16(graph, packed, _started or self._start_h0(node_features))
+        if self._bufs is None:
+            shape = (max(self.rows * self.world, N), d)
+            self._bufs = [torch.zeros(shape, dtype=torch.float32, device=node_features.device) for _ in range(2)]
+        cur, nxt = self._bufs
         with torch.no_grad():
-            # every rank projects all nodes (h is needed in full as the gather source)
-            cur[:N] = _native.linear(node_features, m.input_proj.weight, m.input_proj.bias, relu=True)
+            if node_features.shape[0] == N:               # every rank projects all nodes: nothing to exchange
+                cur[:N] = _native.linear(node_features, m.input_proj.weight, m.input_proj.bias, relu=True)
+            else:
+                if self.hi > self.lo:
+                    cur[self.lo:self.hi] = _native.linear(self._local_rows(node_features), m.input_proj.weight,
+                                                          m.input_proj.bias, relu=True)
+                exchange_rows(cur, self.ranges, self.rank, self.group)
             text_embs = m.text_encoder.encode_packed(packed)
+            out = None
             for l in range(m.num_layers):
                 w = m._generate(l, text_embs, packed.num_unique)
                 ln = m.layer_norms[l]
-                out = nxt[self.lo:self.hi] if self.hi > self.lo else None
-                if out is not None:
-                    graph.mp_layer(cur[:N], w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
-                                   out=out)
-                gather_rows(nxt, self.rows, self.rank, self.group)
+                last = l + 1 == m.num_layers
+                if self.hi > self.lo:
+                    out = nxt[self.lo:self.hi]
+                    graph.mp_layer(cur[:N], w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec, out=out)
+                if not last:
+                    exchange_rows(nxt, self.ranges, self.rank, self.group)
                 cur, nxt = nxt, cur
         self._bufs = [cur, nxt]
-        return cur[:N]
+        d_out = cur[self.lo:self.hi] if self.hi > self.lo else cur[:0]
+        return d_out.clone()                              # the buffers are reused by the next call
 
     def _start_h0(self, node_features):
-        """PREC_F16, layer-0 input: project this rank's rows, agree on one scale, convert, start the all-gather of
-        the fp16 rows.  -> (cur, nxt, cur16, nxt16, pending work) or None when the path is not the f16 one."""
+        """f16 engine, layer-0 input: project this rank's rows, agree on one scale, convert, start the exchange of the
+        fp16 rows.  -> state for `_layers_f16`, or None when the path is not the f16 one."""
+        from . import _native
+        m = self.model
+        if not self._f16_engine():
+            return None
+        device = _native.require_cuda(node_features, m.input_proj.weight)
+        N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
+        sym = self._symmetric(device)
+        if sym is not None:
+            tables = sym.bufs
+        else:
+            if getattr(self, "_bufs16", None) is None:
+                shape = (max(self.rows * self.world, N, 1), d)
+                self._bufs16 = [torch.zeros(shape, dtype=torch.float16, device=device) for _ in range(2)]
+            tables = self._bufs16
+        scales = [torch.zeros(2, dtype=torch.float32, device=device) for _ in range(2)]
+        cur16 = _native.Shadow(tables[0][:N] if N else tables[0][:0], scales[0])
+        with torch.no_grad():
+            h_local = torch.empty((hi - lo, d), dtype=torch.float32, device=device)
+            if hi > lo:
+                _native.linear(self._local_rows(node_features), m.input_proj.weight, m.input_proj.bias, relu=True,
+                               out=h_local)
+                _native.absmax(h_local, cur16)
+            # one scale for the whole shadow: the ranks agree on max |h0| first (4 bytes, stream-ordered).  This
+            # collective also orders this forward after every rank's previous one (the tables are reused).
+            dist.all_reduce(cur16.scale[1:2], op=dist.ReduceOp.MAX, group=self.group)
+            _native.to_f16(h_local, cur16.rows(lo, hi), have_amax=True)      # writes the scale even with no rows
+            pending = []
+            if sym is not None:
+                sym.push(0, lo, hi)
+            else:
+                pending = exchange_rows(tables[0], self.ranges, self.rank, self.group, async_op=True)
+        return {"tables": tables, "scales": scales, "h_local": h_local, "pending": pending, "sym": sym}
+
+    def _layers_f16(self, graphs, packed, st) -> torch.Tensor:
+        """f16 engine: fp32 rows stay local, the fp16 shadow is what every rank reads and what travels."""
         from . import _native
         m = self.model
         N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
-        if m._precision_code() != _native.PREC_F16 or d != 128:      # fp16 shadows are chained at hidden 128 only
-            return None
-        cur, nxt = self._buffers(node_features.device, d)
-        cur16, nxt16 = self._buffers16(node_features.device, d)
-        with torch.no_grad():
-            cur16.scale.zero_()
-            if hi > lo:
-                cur[lo:hi] = _native.linear(node_features[lo:hi], m.input_proj.weight, m.input_proj.bias, relu=True)
-                _native.absmax(cur[lo:hi], cur16)
-            # one scale for the whole shadow: the ranks agree on max |h0| first (4 bytes, stream-ordered)
-            dist.all_reduce(cur16.scale[1:2], op=dist.ReduceOp.MAX, group=self.group)
-            if hi > lo:
-                _native.to_f16(cur[lo:hi], cur16.rows(lo, hi), have_amax=True)
-            else:
-                _native.to_f16(cur[:0], cur16.rows(0, 0), have_amax=True)   # still writes the scale
-            # every all-gather is asynchronous: kernels enqueued before the wait (graph preparation here, the
-            # generator of the next layer later) run while the rows travel over NVLink
-            pending = gather_rows(cur16.data, self.rows, self.rank, self.group, async_op=True)
-        return cur, nxt, cur16, nxt16, pending
-
-    def _forward_f16(self, graph, packed, started) -> torch.Tensor:
-        """PREC_F16: a rank needs fp32 h only for its own rows (residual), and the fp16 shadow of h in full (gather
-        source).  So every rank projects only its own rows, and what travels between layers is the fp16 copy -
-        half the all-gather bytes; the fp32 rows are gathered once, after the last layer, for the return value."""
-        from . import _native
-        m = self.model
-        N, lo, hi = self.num_nodes, self.lo, self.hi
-        cur, nxt, cur16, nxt16, pending = started
+        tables, scales, sym = st["tables"], st["scales"], st["sym"]
+        h_cur, pending = st["h_local"], st["pending"]
         with torch.no_grad():
             text_embs = m.text_encoder.encode_packed(packed)
             w = m._generate(0, text_embs, packed.num_unique)
+            self._mark("prep")
             for l in range(m.num_layers):
                 ln = m.layer_norms[l]
                 last = l + 1 == m.num_layers
-                pending.wait()
-                if hi > lo:
-                    graph.mp_layer(cur[:N], w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps,
-                                   _native.PREC_F16, out=nxt[lo:hi], h16=cur16.rows(0, N),
-                                   out16=None if last else nxt16.rows(lo, hi))
-                pending = gather_rows(nxt if last else nxt16.data, self.rows, self.rank, self.group, async_op=True)
+                cb, nb = l % 2, (l + 1) % 2
+                # the rows of h_l are complete everywhere
+                if sym is not None:
+                    sym.close_layer(cb)
+                else:
+                    for work in pending:
+                        work.wait()
+                self._mark("wait")
+                h_nxt = torch.empty_like(h_cur)
+                h16 = _native.Shadow(tables[cb][:N], scales[cb])
+                for g in graphs:
+                    if g.num_local == 0:
+                        continue
+                    out16 = None if last else _native.Shadow(tables[nb][g.dst_lo:g.dst_hi], scales[nb])
+                    g.mp_layer(h_cur, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, _native.PREC_F16,
+                               out=h_nxt[g.dst_lo - lo:g.dst_hi - lo], h16=h16, out16=out16, h_row0=lo)
+                    if not last and sym is not None:
+                        sym.push(nb, g.dst_lo, g.dst_hi)  # these rows travel while the next chunk is computed
                 if not last:
+                    if sym is None:
+                        pending = exchange_rows(tables[nb], self.ranges, self.rank, self.group, async_op=True)
+                    # the next layer's generator runs while the rows travel
                     w = m._generate(l + 1, text_embs, packed.num_unique)
-                cur, nxt, cur16, nxt16 = nxt, cur, nxt16, cur16
-            pending.wait()
-        self._bufs, self._bufs16 = [cur, nxt], [cur16, nxt16]
-        return cur[:N]
+                self._mark("compute")
+                h_cur = h_nxt
+        return h_cur

@@ -29,6 +29,56 @@ def test_plan_partition_covers_nodes_once():
         plan_partition(5, 0)
 
 
+def test_plan_partition_by_edges_balances_work():
+    from graph_hypernetwork_forge.distributed import plan_partition_by_edges
+    rng = np.random.default_rng(0)
+    n = 5000
+    indeg = (rng.zipf(1.3, n) - 1).clip(0, 20000)            # power-law in-degree: a few hubs
+    rowptr = np.concatenate([[0], np.cumsum(indeg)])
+    for world in (1, 2, 3, 8):
+        ranges = plan_partition_by_edges(rowptr, world)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:])) and all(lo <= hi for lo, hi in ranges)
+        work = [rowptr[hi] - rowptr[lo] + (hi - lo) for lo, hi in ranges]
+        heaviest_node = indeg.max() + 1
+        assert max(work) <= sum(work) / world + heaviest_node   # no range exceeds its share by more than one node
+    assert plan_partition_by_edges(np.array([0]), 4) == [(0, 0)] * 4          # no nodes at all
+    equal = plan_partition_by_edges(np.arange(0, 81, 1) * 7, 4)               # uniform degrees -> equal node counts
+    assert [hi - lo for lo, hi in equal] == [20, 20, 20, 20]
+
+
+def _exchange_worker(rank, world, port, ret):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "graph-hypernetwork-forge_b200")]
+    from graph_hypernetwork_forge.distributed import exchange_rows, plan_partition
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, d = 11, 3
+    want = torch.arange(n * d, dtype=torch.float32).reshape(n, d)
+    results = []
+    rows, equal = plan_partition(n, world)
+    for ranges, size in ((equal, rows * world), ([(0, 7), (7, 11)], n), ([(0, 0), (0, 11)], n)):
+        buf = torch.full((size, d), -1.0)
+        lo, hi = ranges[rank]
+        buf[lo:hi] = want[lo:hi]
+        for work in exchange_rows(buf, ranges, rank, None, async_op=True):
+            work.wait()
+        results.append(bool(torch.equal(buf[:n], want)))
+    ret[rank] = results
+    dist.destroy_process_group()
+
+
+def test_exchange_rows_even_and_uneven_ranges_gloo():
+    """The collective transport: in-place all-gather for equal padded ranges, one broadcast per rank otherwise
+    (edge-balanced ranges, empty ranges)."""
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_exchange_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        assert all(all(ret[r]) for r in range(world)), dict(ret)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -217,6 +217,26 @@ def test_dedup_and_text_encoder_edge_cases():
     assert [big[i] for i in first.cpu().numpy()] == u3
 
 
+def test_dedup_many_distinct_strings_takes_the_full_table():
+    """More than 2^19 distinct strings overflow the small (L2-resident) hash table: the retry with the worst-case
+    table must give the same first-occurrence ranking (bit-exact against a host ranking)."""
+    from graph_hypernetwork_forge import _native
+    rng = np.random.default_rng(3)
+    n, distinct = 2_000_000, 700_000
+    value = rng.integers(0, distinct, n)
+    digits = ((value[:, None] // 10 ** np.arange(7, -1, -1)) % 10 + 48).astype(np.uint8)      # "00012345"
+    utf8 = torch.from_numpy(digits.reshape(-1).copy()).to(DEV)
+    offsets = (torch.arange(n + 1, dtype=torch.int64) * 8).to(DEV)
+    rel, first = _native.dedup_texts(utf8, offsets)
+    values, first_idx = np.unique(value, return_index=True)
+    order = np.argsort(first_idx, kind="stable")
+    rank = np.empty(distinct, dtype=np.int64)
+    rank[values[order]] = np.arange(order.size)
+    assert first.numel() == values.size
+    assert np.array_equal(rel.cpu().numpy().astype(np.int64), rank[value])
+    assert np.array_equal(first.cpu().numpy(), first_idx[order])
+
+
 def test_empty_graph_and_isolated_nodes():
     from graph_hypernetwork_forge import HyperGNN
     torch.manual_seed(0)

@@ -19,6 +19,9 @@ x, ei, rel, utf8, offsets = bench.make_device_inputs(w, dev)
 torch.cuda.synchronize()
 for i in range(2):
     _native.launch_count(reset=True)
-    out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, w["N"]))
+    if os.environ.get("GHF_ONE_FORWARD_STAGED"):       # stage by stage from Python
+        out = model.forward_prepared(x, model.prepare_packed(ei, utf8, offsets, w["N"]))
+    else:                                               # the benched entry: one native call
+        out = model.forward_packed(x, ei, utf8, offsets)
     torch.cuda.synchronize()
     print(f"forward {i}: {_native.launch_count()} library launches", flush=True)
