@@ -345,7 +345,10 @@ def main():
         for k, v in (("NCCL_IB_DISABLE", "1"), ("NCCL_P2P_LEVEL", "NVL"), ("NCCL_DEBUG", "INFO"),
                      ("NCCL_DEBUG_SUBSYS", "INIT,GRAPH"),
                      ("NCCL_DEBUG_FILE", f"/tmp/ghf_nccl_{os.getpid()}.log")):
-            os.environ.setdefault(k, v)
+            if k.startswith("NCCL_DEBUG") and not os.environ.get("GHF_KEEP_NCCL_DEBUG"):
+                os.environ[k] = v                         # the image presets NCCL_DEBUG=VERSION
+            else:
+                os.environ.setdefault(k, v)
         nccl_env = {k: os.environ[k] for k in ("NCCL_IB_DISABLE", "NCCL_P2P_LEVEL", "NCCL_DEBUG", "NCCL_DEBUG_FILE")}
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
@@ -571,7 +574,7 @@ def main():
             transport_lines = keep[:3] + keep[-5:]
         except Exception:
             pass
-        multi = {"transport": sharded.transport, "chunks": len(sharded._chunk_ranges()), "balance": args.balance,
+        multi = {"transport": sharded.transport, "chunks": per_layer, "balance": args.balance,
                  "ranges_rows": [hi_r - lo_r for lo_r, hi_r in sharded.ranges],
                  "edges_per_rank_max": int(local_edges), "parity": parity,
                  "stage_ms_max_over_ranks": {"prep": float(st[0]), "compute": float(st[1]), "exposed_exchange": float(st[2])},

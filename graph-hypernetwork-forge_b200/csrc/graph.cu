@@ -139,6 +139,7 @@ extern "C" void ghf_graph_free(ghf_graph* g) {
                   g->unit_rel, g->unit_phase, g->phase_units, g->phase_tiles};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, s);
+  delete[] g->h_phase_unit_begin;
   delete g;
 }
 
@@ -215,6 +216,10 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uin
   GHF_CUDA(cudaMemcpyAsync(&bad_ids, bad.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaMemcpyAsync(&totals[0], gstart.as<int32_t>() + groups, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   GHF_CUDA(cudaMemcpyAsync(&totals[1], ubase.as<int32_t>() + groups, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  // first unit of every super-block = unit_base of its first group (groups are ordered super-block, relation)
+  g->h_phase_unit_begin = new int32_t[n_sb + 1]();
+  GHF_CUDA(cudaMemcpy2DAsync(g->h_phase_unit_begin, sizeof(int32_t), ubase.as<int32_t>(), (size_t)R * sizeof(int32_t),
+                             sizeof(int32_t), (size_t)n_sb + 1, cudaMemcpyDeviceToHost, stream));
 
   cub::DoubleBuffer<Key> kbuf(keys_a.as<Key>(), keys_b.as<Key>());
   cub::DoubleBuffer<uint32_t> vbuf(vals_a.as<uint32_t>(), vals_b.as<uint32_t>());
@@ -332,6 +337,8 @@ extern "C" int ghf_graph_build(const int64_t* d_edge_index, int64_t E, const uin
   *out = g;
   return 0;
 }
+
+extern "C" int64_t ghf_graph_num_phases(const ghf_graph* g) { return g ? g->num_phases : -1; }
 
 extern "C" int ghf_graph_info(const ghf_graph* g, int64_t info[6]) {
   GHF_REQUIRE(g && info, "ghf_graph_info: NULL argument");

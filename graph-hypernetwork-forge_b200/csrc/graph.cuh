@@ -22,6 +22,8 @@ struct ghf_graph {
   int32_t* unit_phase = nullptr;   // [units] super-block ("phase") of the unit's destinations
   int32_t* phase_units = nullptr;  // [phases] number of units per super-block
   int32_t* phase_tiles = nullptr;  // [phases] number of 128-edge tiles per super-block (sum over its units)
+  int32_t* h_phase_unit_begin = nullptr;   // HOST, [phases + 1]: first unit of each super-block (units are ordered by
+                                           // super-block, then relation); lets a layer run on a range of super-blocks
   int64_t num_phases = 0;          // ceil(num_local / sb_nodes), at least 1
   int64_t bytes = 0;
   mutable void* stream = nullptr;  // stream the tables were allocated on / last used on (freed there)

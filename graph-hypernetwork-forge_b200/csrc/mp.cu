@@ -332,10 +332,22 @@ extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim
   return bytes + 256;
 }
 
-static int launch_epilogue(const ghf_graph* g, const float* acc, const float* d_h, const float* d_ln_w,
+// rows [r0, r1) of the graph's local rows (all of them by default); acc / out / upd / out16 are indexed by local row
+static int launch_epilogue(const ghf_graph* g_full, const float* acc, const float* d_h, const float* d_ln_w,
                            const float* d_ln_b, float eps, float* d_out, float* d_upd, void* d_out16,
-                           float* d_out16_scale, cudaStream_t stream) {
-  const int d = g->hidden_dim;
+                           float* d_out16_scale, cudaStream_t stream, int64_t r0 = 0, int64_t r1 = -1) {
+  const int d = g_full->hidden_dim;
+  if (r1 < 0) r1 = g_full->num_local;
+  if (r1 <= r0) return 0;
+  ghf_graph view = *g_full;                              // the same tables, seen from row r0 on
+  view.indeg = g_full->indeg + r0;
+  view.dst_lo = g_full->dst_lo + r0;
+  view.num_local = r1 - r0;
+  const ghf_graph* g = &view;
+  acc += r0 * d;
+  d_out += r0 * d;
+  if (d_upd) d_upd += r0 * d;
+  if (d_out16) d_out16 = reinterpret_cast<char*>(d_out16) + r0 * d * 2;
   const int64_t nl = g->num_local;
   const int threads = 256;
   const bool aligned = (reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(d_h) |
@@ -380,13 +392,31 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
                            const float* d_W_msg, const float* d_W_self, const float* d_bias, int precision,
                            float* acc_ext, bool accumulate, bool transposed, void* d_workspace, cudaStream_t stream,
                            float** acc_used, ProfRec* rec, const void* prepacked = nullptr,
-                           const FusedEpilogue* fe = nullptr, bool* fused_done = nullptr) {
+                           const FusedEpilogue* fe = nullptr, bool* fused_done = nullptr, int phase_lo = 0,
+                           int phase_hi = -1) {
+  // A range of super-blocks [phase_lo, phase_hi): the units of those super-blocks are contiguous, so the kernels see
+  // a view of the graph that starts at the first of them; accumulator rows keep their local row index.
+  const ghf_graph* g_whole = g;
+  ghf_graph view = *g;
+  if (phase_hi < 0) phase_hi = (int)g->num_phases;
+  const bool ranged = phase_lo != 0 || phase_hi != (int)g->num_phases;
+  if (ranged) {
+    GHF_REQUIRE(0 <= phase_lo && phase_lo <= phase_hi && phase_hi <= g->num_phases && g->h_phase_unit_begin,
+                "ghf_mp_layer: bad super-block range [%d, %d) of %lld", phase_lo, phase_hi, (long long)g->num_phases);
+    const int64_t u0 = g->h_phase_unit_begin[phase_lo], u1 = g->h_phase_unit_begin[phase_hi];
+    view.unit_start += u0; view.unit_count += u0; view.unit_rel += u0; view.unit_phase += u0;
+    view.num_units = u1 - u0;
+    g = &view;
+  }
+  const int64_t row0 = (int64_t)phase_lo * g_whole->sb_nodes;
+  const int64_t row1 = phase_hi * (int64_t)g_whole->sb_nodes < g_whole->num_local ? phase_hi * (int64_t)g_whole->sb_nodes
+                                                                                    : g_whole->num_local;
   const int d = g->hidden_dim;
   const int64_t nl = g->num_local;
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
   // (the f16 kernel clears the accumulator itself and keeps per-phase sync words next to the counter)
   const bool f16_ss = precision == GHF_PREC_F16 && mp_f16ss_supported(d);   // hidden 256: streamed weights
-  const bool fused = fe != nullptr && precision == GHF_PREC_F16 && !f16_ss && mp_f16_supported(d) &&
+  const bool fused = fe != nullptr && !ranged && precision == GHF_PREC_F16 && !f16_ss && mp_f16_supported(d) &&
                      mp_f16_fused_enabled(g) && fe->ln_w != nullptr && fe->ln_b != nullptr &&
                      (reinterpret_cast<uintptr_t>(fe->ln_w) | reinterpret_cast<uintptr_t>(fe->ln_b) |
                       reinterpret_cast<uintptr_t>(fe->h) | reinterpret_cast<uintptr_t>(fe->out) |
@@ -394,20 +424,17 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
   const bool self_clearing = precision == GHF_PREC_F16 && !f16_ss && g->num_units > 0;
   int* counter = reinterpret_cast<int*>(align_up(reinterpret_cast<int64_t>(d_workspace), 256));
   float* acc_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(counter) +
-                                           (precision == GHF_PREC_F16 ? mp_f16_sync_bytes(g) : 256));
-  const int64_t acc_bytes = acc_region_bytes(g, d, precision);
+                                           (precision == GHF_PREC_F16 ? mp_f16_sync_bytes(g_whole) : 256));
+  const int64_t acc_bytes = acc_region_bytes(g_whole, d, precision);
   void* pack = reinterpret_cast<char*>(acc_ws) + acc_bytes;
   float* acc = acc_ext ? acc_ext : acc_ws;
   *acc_used = acc;
   if (rec) GHF_CUDA(cudaEventRecord(rec->e[0], stream));
   if (!self_clearing) {
     const size_t head = reinterpret_cast<char*>(acc_ws) - reinterpret_cast<char*>(counter);
-    if (acc_ext) {
-      GHF_CUDA(cudaMemsetAsync(counter, 0, head, stream));
-      if (!accumulate) GHF_CUDA(cudaMemsetAsync(acc_ext, 0, nl * (size_t)d * 4, stream));
-    } else {
-      GHF_CUDA(cudaMemsetAsync(counter, 0, head + nl * (size_t)d * 4, stream));
-    }
+    GHF_CUDA(cudaMemsetAsync(counter, 0, head, stream));
+    if (!(acc_ext && accumulate) && row1 > row0)         // only the rows of the super-blocks in range
+      GHF_CUDA(cudaMemsetAsync((acc_ext ? acc_ext : acc_ws) + row0 * d, 0, (size_t)(row1 - row0) * d * 4, stream));
   }
   // gradient contractions (ghf_mp_contract): transposed relation matrices and an absent (NULL) half are understood
   // by the f16 engine only; the host side materialises them for the other engines
@@ -454,7 +481,8 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
                                fe->out, fe->upd, fe->out16, fe->out16_scale, stream);
       if (fused_done) *fused_done = true;
     } else if (precision == GHF_PREC_F16) {
-      rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream, accumulate, skip_half);
+      rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream, accumulate, skip_half, phase_lo,
+                         phase_hi);
     } else if (d <= 32) {
       rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
     } else if (d <= 64) {
@@ -478,16 +506,20 @@ static int check_layer_args(const ghf_graph* g, const void* d_workspace, int pre
   return 0;
 }
 
-extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
-                                const float* d_W_msg, const float* d_W_self, const float* d_bias,
-                                const float* d_ln_w, const float* d_ln_b, float eps, int precision, float* d_out,
-                                void* d_out16, float* d_out16_scale, float* d_upd, void* d_workspace,
-                                void* stream_) {
+static int mp_layer_impl(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                         const float* d_W_msg, const float* d_W_self, const float* d_bias, const float* d_ln_w,
+                         const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
+                         float* d_out16_scale, float* d_upd, void* d_workspace, int phase_lo, int phase_hi,
+                         void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_layer_args(g, d_workspace, precision, d_h16, d_h16_scale)) return rc;
   GHF_REQUIRE(d_out16 == nullptr || d_out16_scale != nullptr, "ghf_mp_layer: d_out16 needs d_out16_scale (float[2])");
   g->stream = stream_;
   if (g->num_local == 0) return 0;
+  if (phase_hi < 0) phase_hi = (int)g->num_phases;
+  GHF_REQUIRE(0 <= phase_lo && phase_lo <= phase_hi && phase_hi <= g->num_phases,
+              "ghf_mp_layer: bad super-block range [%d, %d) of %lld", phase_lo, phase_hi, (long long)g->num_phases);
+  if (phase_lo == phase_hi) return 0;
   ProfRec rec{};
   const bool prof = g_prof_on;
   if (prof)
@@ -497,16 +529,37 @@ extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void
   bool fused_done = false;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
                                false, false, d_workspace, stream, &acc, prof ? &rec : nullptr, nullptr, &fe,
-                               &fused_done))
+                               &fused_done, phase_lo, phase_hi))
     return rc;
-  if (!fused_done)
-    if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream))
+  if (!fused_done) {
+    const int64_t r0 = (int64_t)phase_lo * g->sb_nodes;
+    const int64_t r1 = phase_hi * (int64_t)g->sb_nodes < g->num_local ? phase_hi * (int64_t)g->sb_nodes : g->num_local;
+    if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream, r0, r1))
       return rc;
+  }
   if (prof) {
     GHF_CUDA(cudaEventRecord(rec.e[3], stream));
     g_prof.push_back(rec);
   }
   return 0;
+}
+
+extern "C" int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                                const float* d_W_msg, const float* d_W_self, const float* d_bias,
+                                const float* d_ln_w, const float* d_ln_b, float eps, int precision, float* d_out,
+                                void* d_out16, float* d_out16_scale, float* d_upd, void* d_workspace,
+                                void* stream_) {
+  return mp_layer_impl(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out,
+                       d_out16, d_out16_scale, d_upd, d_workspace, 0, -1, stream_);
+}
+
+extern "C" int ghf_mp_layer_f16_range(const ghf_graph* g, const float* d_h, const void* d_h16,
+                                      const float* d_h16_scale, const float* d_W_msg, const float* d_W_self,
+                                      const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
+                                      int precision, float* d_out, void* d_out16, float* d_out16_scale, float* d_upd,
+                                      void* d_workspace, int32_t phase_lo, int32_t phase_hi, void* stream_) {
+  return mp_layer_impl(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out,
+                       d_out16, d_out16_scale, d_upd, d_workspace, phase_lo, phase_hi, stream_);
 }
 
 namespace ghf {

@@ -47,7 +47,8 @@ int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool 
 int64_t mp_f16_sync_bytes(const ghf_graph* g);
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
                   const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc = false,
-                  int skip_half = 0);   // skip_half: 1 = no source term (W_msg NULL), 2 = no destination term
+                  int skip_half = 0,    // skip_half: 1 = no source term (W_msg NULL), 2 = no destination term
+                  int phase_lo = 0, int phase_hi = -1);   // super-blocks the given units lie in (clearing covers them)
 
 // The whole layer in one kernel (mp_f16_fused.cu, hidden_dim 128): the contraction reduces into a ring of L2-resident
 // accumulator windows and the row epilogue (mean, residual, ReLU, LayerNorm, fp16 shadow) runs per super-block inside

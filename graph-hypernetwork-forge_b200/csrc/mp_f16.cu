@@ -213,8 +213,8 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
               const float* __restrict__ h_scale, const __half* __restrict__ wpack,
               const float* __restrict__ w_inv_scale,
               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter,
-              const int32_t* __restrict__ unit_phase, int* __restrict__ zero_done, int num_phases, int sb_nodes,
-              int64_t num_local, uint32_t flags, long long* __restrict__ trace) {
+              const int32_t* __restrict__ unit_phase, int* __restrict__ zero_done, int num_phases, int phase_lo,
+              int sb_nodes, int64_t num_local, uint32_t flags, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sA = (raw + 1023u) & ~1023u;
@@ -481,7 +481,8 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
     // lines are created in L2 by full-line stores, so the reductions never fetch accumulator lines from HBM and
     // there is no separate 1.28 GB clear pass.  (All CTAs are co-resident: 1 CTA / SM, grid <= SM count.)
     uint32_t qi = 0, wb = 0;
-    int my_zeroed = -1, ready_phase = -1;
+    // this launch covers super-blocks [phase_lo, num_phases) of the graph (the units it was given lie in them)
+    int my_zeroed = phase_lo - 1, ready_phase = -1;
     auto publish = [&](int start, int rows, int rel, uint32_t tf) {
       if (lane == 0) {
         mbar_wait(q_empty0 + 8u * (qi % kQueue), ((qi / kQueue) & 1u) ^ 1u);
@@ -651,7 +652,10 @@ int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool 
 }
 
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
-                  const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc, int skip_half) {
+                  const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc, int skip_half,
+                  int phase_lo, int phase_hi) {
+  if (phase_hi < 0) phase_hi = (int)g->num_phases;
+  GHF_REQUIRE(0 <= phase_lo && phase_lo <= phase_hi && phase_hi <= g->num_phases, "mp_f16: bad super-block range");
   GHF_REQUIRE(h16_scale != nullptr, "mp_f16: the fp16 shadow needs its scale words");
   GHF_REQUIRE(g->hidden_dim == kD, "mp_f16: hidden_dim must be %d", kD);
   GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_f16: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
@@ -686,7 +690,7 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
   mp_f16_kernel<P, T><<<(unsigned)grid, threads_for(P), kSmem, stream>>>(                                        \
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,                    \
       reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, \
-      zero_done, (int)g->num_phases, g->sb_nodes, g->num_local, env_flags() | (keep_acc ? kFlagNoClear : 0u) | (skip_half == 1 ? kFlagSkipSrc : skip_half == 2 ? kFlagSkipDst : 0u), trace)
+      zero_done, phase_hi, phase_lo, g->sb_nodes, g->num_local, env_flags() | (keep_acc ? kFlagNoClear : 0u) | (skip_half == 1 ? kFlagSkipSrc : skip_half == 2 ? kFlagSkipDst : 0u), trace)
   if (trace) GHF_F16_LAUNCH(4, true);
   else if (prod == 8) GHF_F16_LAUNCH(8, false);
   else GHF_F16_LAUNCH(4, false);

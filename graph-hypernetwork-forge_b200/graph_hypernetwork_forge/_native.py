@@ -62,6 +62,8 @@ def lib():
         "ghf_mp_workspace_bytes": (c_int64, [P, c_int32, c_int]),
         "ghf_mp_layer": (c_int, [P, P, P, P, P, P, P, c_float, c_int, P, P, P, P]),
         "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
+        "ghf_mp_layer_f16_range": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, c_int32, c_int32, P]),
+        "ghf_graph_num_phases": (c_int64, [P]),
         "ghf_mp_contract": (c_int, [P, P, P, P, P, P, P, c_int, P, c_int, c_int, P, P]),
         "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P, P]),
         "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, P]),
@@ -96,7 +98,7 @@ EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
     "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
+    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_layer_f16_range", "ghf_graph_num_phases", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
     "ghf_text_encode_backward", "ghf_weight_images_bytes", "ghf_weight_images_f16", "ghf_mp_layer_images",
     "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_copy_async", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
@@ -370,6 +372,7 @@ class Graph:
         info = (c_int64 * 6)()
         _check(lib().ghf_graph_info(self._h, info), "ghf_graph_info")
         (self.num_kept, self.num_units, self.sb_nodes, self.unit_edges, self.num_local, self.bytes) = map(int, info)
+        self.num_phases = int(lib().ghf_graph_num_phases(self._h))
         self._workspace = {}
 
     def __del__(self):
@@ -410,14 +413,20 @@ class Graph:
             self._workspace[key] = ws
         return ws
 
+    def phase_rows(self, phase_lo: int, phase_hi: int):
+        """Local row range [r0, r1) of the super-blocks [phase_lo, phase_hi)."""
+        return min(phase_lo * self.sb_nodes, self.num_local), min(phase_hi * self.sb_nodes, self.num_local)
+
     def mp_layer(self, h, W_msg, W_self, bias, ln_w, ln_b, eps: float, precision: int, out=None,
-                 want_upd: bool = False, h16=None, out16=None, h_row0=None):
+                 want_upd: bool = False, h16=None, out16=None, h_row0=None, phases=None):
         """One message-passing layer on this graph's destination range -> (out, upd or None).
 
         `h16` (Shadow of [N, d], optional) is the fp16 shadow of `h` the PREC_F16 contraction gathers from (made
         inside when absent); `out16` (Shadow of [local nodes, d], optional) receives the shadow of `out`.
         `h_row0` (PREC_F16 with `h16` only): `h` holds just the rows [h_row0, h_row0 + len(h)) of the fp32 features
-        - enough, because with a shadow the fp32 rows are read only at this graph's own destinations (residual)."""
+        - enough, because with a shadow the fp32 rows are read only at this graph's own destinations (residual).
+        `phases` = (lo, hi): only the super-blocks [lo, hi) of the graph; `out`, `out16`, `upd` still cover all local
+        rows, of which `phase_rows(lo, hi)` are written."""
         dev = self.device
         h, W_msg, W_self, bias = _f32(h), _f32(W_msg), _f32(W_self), _f32(bias)
         ln_w, ln_b = _f32(ln_w), _f32(ln_b)
@@ -443,12 +452,14 @@ class Graph:
             if t is not None and (not isinstance(t, Shadow) or t.data.shape != (rows, d)):
                 raise RuntimeError(f"{name} must be a Shadow of a [{rows},{d}] matrix")
         ws = self.workspace(precision)
+        p_lo, p_hi = (0, self.num_phases) if phases is None else phases
         with torch.cuda.device(dev):
-            _check(lib().ghf_mp_layer_f16(self._h, h_ptr, _ptr(h16.data) if h16 else None,
-                                          _ptr(h16.scale) if h16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
-                                          _ptr(ln_w), _ptr(ln_b), float(eps), precision, _ptr(out),
-                                          _ptr(out16.data) if out16 else None, _ptr(out16.scale) if out16 else None,
-                                          _ptr(upd), _ptr(ws), _stream(dev)), "ghf_mp_layer_f16")
+            _check(lib().ghf_mp_layer_f16_range(self._h, h_ptr, _ptr(h16.data) if h16 else None,
+                                                _ptr(h16.scale) if h16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
+                                                _ptr(ln_w), _ptr(ln_b), float(eps), precision, _ptr(out),
+                                                _ptr(out16.data) if out16 else None,
+                                                _ptr(out16.scale) if out16 else None, _ptr(upd), _ptr(ws), int(p_lo),
+                                                int(p_hi), _stream(dev)), "ghf_mp_layer_f16_range")
         return out, upd
 
     def mp_layer_images(self, h, images, bias, ln_w, ln_b, eps: float, h16=None, out16=None) -> torch.Tensor:

@@ -78,10 +78,9 @@ def exchange_rows(buf: torch.Tensor, ranges: Sequence[Tuple[int, int]], rank: in
     ranges (plan_partition) go through one in-place all-gather; uneven ranges (plan_partition_by_edges) through one
     broadcast per rank.  -> list of work handles (empty when not async)."""
     world = len(ranges)
-    rows = ranges[0][1] - ranges[0][0]
-    equal = all(lo == r * rows for r, (lo, _) in enumerate(ranges)) and buf.shape[0] >= rows * world
-    if equal and rows > 0:
-        w = gather_rows(buf, rows, rank, group, async_op)
+    rows, equal_ranges = plan_partition(ranges[-1][1], world)
+    if [tuple(r) for r in ranges] == equal_ranges and rows > 0 and buf.shape[0] >= rows * world:
+        w = gather_rows(buf[:rows * world], rows, rank, group, async_op)
         return [w] if async_op else []
     works = []
     for r, (lo, hi) in enumerate(ranges):
@@ -155,8 +154,8 @@ class ShardedForward:
 
     ranges: optional [(lo, hi)] per rank (e.g. from `plan_partition_by_edges`); default equal node counts.
     transport: "p2p" | "collective" | None (p2p on CUDA when symmetric memory works, else collective).
-    chunks: the rank's range is processed in this many pieces so that the rows of a finished piece travel while the
-    next one is computed (p2p transport, f16 engine)."""
+    chunks: the rank's super-blocks are processed in this many pieces (`ghf_mp_layer_f16_range`) so that the rows of a
+    finished piece travel while the next one is computed (p2p transport, f16 engine)."""
 
     def __init__(self, model, num_nodes: int, group=None, ranges=None, transport: Optional[str] = None,
                  chunks: int = 1):
@@ -218,13 +217,12 @@ class ShardedForward:
             self.transport = "p2p"
         return self._sym
 
-    def _chunk_ranges(self) -> List[Tuple[int, int]]:
-        n, c = self.hi - self.lo, self.chunks
-        if n <= 0 or c == 1:
-            return [(self.lo, self.hi)]
-        step = -(-n // c)
-        step = -(-step // 64) * 64                       # whole 64-row groups: 8/16 KiB-aligned row blocks
-        return [(lo, min(lo + step, self.hi)) for lo in range(self.lo, self.hi, step)]
+    def _phase_chunks(self, graph) -> List[Tuple[int, int]]:
+        """The graph's super-blocks in `chunks` contiguous pieces (a piece is one launch of the layer kernels)."""
+        n = graph.num_phases
+        c = max(1, min(self.chunks, n))
+        cuts = [round(i * n / c) for i in range(c + 1)]
+        return [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
 
     def _local_rows(self, node_features: torch.Tensor) -> torch.Tensor:
         """Features of this rank's own rows: accepts all [N, F] rows or just the [hi - lo, F] local ones."""
@@ -290,7 +288,7 @@ class ShardedForward:
         if (graph.dst_lo, graph.dst_hi) != (self.lo, self.hi):
             raise RuntimeError("the prepared graph covers another destination range")
         started = _started if _started is not None else self._start_h0(node_features)
-        return self._layers(node_features, [graph], packed, started, gather_output)
+        return self._layers(node_features, graph, packed, started, gather_output)
 
     # ------------------------------------------------------------------ the forward
     def _run(self, node_features, edge_index, packed, started, gather_output):
@@ -299,21 +297,17 @@ class ShardedForward:
         m = self.model
         if m.training and m.dropout > 0.0:
             raise NotImplementedError("the multi-GPU path is inference-only (no dropout, no gradients)")
-        graphs = []
-        chunks = self._chunk_ranges() if (started is not None and self._sym is not None) else [(self.lo, self.hi)]
-        for lo, hi in chunks:
-            graphs.append(_native.Graph(edge_index, packed.rel_ids, self.num_nodes, max(packed.num_unique, 1),
-                                        m.hidden_dim, dst_lo=lo, dst_hi=hi,
-                                        sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
-                                        unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset))
-        return self._layers(node_features, graphs, packed, started, gather_output)
+        graph = _native.Graph(edge_index, packed.rel_ids, self.num_nodes, max(packed.num_unique, 1), m.hidden_dim,
+                              dst_lo=self.lo, dst_hi=self.hi, sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
+                              unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset)
+        return self._layers(node_features, graph, packed, started, gather_output)
 
-    def _layers(self, node_features, graphs, packed, started, gather_output):
-        self.num_kept = sum(g.num_kept for g in graphs)
+    def _layers(self, node_features, graph, packed, started, gather_output):
+        self.num_kept = graph.num_kept
         if started is not None:
-            local = self._layers_f16(graphs, packed, started)
+            local = self._layers_f16(graph, packed, started)
         else:
-            local = self._layers_generic(node_features, graphs[0], packed)
+            local = self._layers_generic(node_features, graph, packed)
         return self._gather_output(local) if gather_output else local
 
     def _layers_generic(self, node_features, graph, packed) -> torch.Tensor:
@@ -386,19 +380,36 @@ class ShardedForward:
                 pending = exchange_rows(tables[0], self.ranges, self.rank, self.group, async_op=True)
         return {"tables": tables, "scales": scales, "h_local": h_local, "pending": pending, "sym": sym}
 
-    def _layers_f16(self, graphs, packed, st) -> torch.Tensor:
-        """f16 engine: fp32 rows stay local, the fp16 shadow is what every rank reads and what travels."""
+    def _layers_f16(self, graph, packed, st) -> torch.Tensor:
+        """f16 engine: fp32 rows stay local, the fp16 shadow is what every rank reads and what travels.  The rank's
+        super-blocks are run in `chunks` pieces; the finished rows of a piece are pushed while the next one runs.
+        The generators of all layers run on a side stream (they depend on the text embeddings only)."""
         from . import _native
         m = self.model
         N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
         tables, scales, sym = st["tables"], st["scales"], st["sym"]
         h_cur, pending = st["h_local"], st["pending"]
+        device = h_cur.device
+        main = torch.cuda.current_stream(device)
+        if getattr(self, "_gen_stream", None) is None:
+            self._gen_stream = torch.cuda.Stream(device=device)
         with torch.no_grad():
             text_embs = m.text_encoder.encode_packed(packed)
-            w = m._generate(0, text_embs, packed.num_unique)
+            self._gen_stream.wait_stream(main)
+            weights, ready = [], []
+            with torch.cuda.stream(self._gen_stream):
+                for l in range(m.num_layers):
+                    weights.append(m._generate(l, text_embs, packed.num_unique))
+                    ready.append(torch.cuda.Event())
+                    ready[-1].record(self._gen_stream)
+            for w in weights:                             # the tensors are consumed on the main stream
+                for t in w.values():
+                    t.record_stream(main)
+            text_embs.record_stream(self._gen_stream)
+            chunks = self._phase_chunks(graph) if graph.num_local else []
             self._mark("prep")
             for l in range(m.num_layers):
-                ln = m.layer_norms[l]
+                ln, w = m.layer_norms[l], weights[l]
                 last = l + 1 == m.num_layers
                 cb, nb = l % 2, (l + 1) % 2
                 # the rows of h_l are complete everywhere
@@ -407,22 +418,19 @@ class ShardedForward:
                 else:
                     for work in pending:
                         work.wait()
+                main.wait_event(ready[l])
                 self._mark("wait")
                 h_nxt = torch.empty_like(h_cur)
                 h16 = _native.Shadow(tables[cb][:N], scales[cb])
-                for g in graphs:
-                    if g.num_local == 0:
-                        continue
-                    out16 = None if last else _native.Shadow(tables[nb][g.dst_lo:g.dst_hi], scales[nb])
-                    g.mp_layer(h_cur, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, _native.PREC_F16,
-                               out=h_nxt[g.dst_lo - lo:g.dst_hi - lo], h16=h16, out16=out16, h_row0=lo)
-                    if not last and sym is not None:
-                        sym.push(nb, g.dst_lo, g.dst_hi)  # these rows travel while the next chunk is computed
-                if not last:
-                    if sym is None:
-                        pending = exchange_rows(tables[nb], self.ranges, self.rank, self.group, async_op=True)
-                    # the next layer's generator runs while the rows travel
-                    w = m._generate(l + 1, text_embs, packed.num_unique)
+                out16 = None if last or hi <= lo else _native.Shadow(tables[nb][lo:hi], scales[nb])
+                for p_lo, p_hi in chunks:
+                    graph.mp_layer(h_cur, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, _native.PREC_F16,
+                                   out=h_nxt, h16=h16, out16=out16, h_row0=lo, phases=(p_lo, p_hi))
+                    if not last and sym is not None:      # these rows travel while the next piece is computed
+                        r0, r1 = graph.phase_rows(p_lo, p_hi)
+                        sym.push(nb, lo + r0, lo + r1)
+                if not last and sym is None:
+                    pending = exchange_rows(tables[nb], self.ranges, self.rank, self.group, async_op=True)
                 self._mark("compute")
                 h_cur = h_nxt
         return h_cur

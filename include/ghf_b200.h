@@ -133,6 +133,18 @@ int ghf_mp_layer_f16(const ghf_graph* g, const float* d_h, const void* d_h16, co
                      const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
                      float* d_out16_scale, float* d_upd, void* d_workspace, void* stream);
 
+/* The same layer restricted to the super-blocks [phase_lo, phase_hi) of the graph (ghf_graph_num_phases of them, each
+ * ghf_graph_info()[2] = sb_nodes destination rows): only rows [phase_lo * sb_nodes, min(phase_hi * sb_nodes, local
+ * nodes)) of d_out / d_out16 / d_upd are written (the pointers still address row 0 of the local range).  A multi-GPU
+ * caller runs a rank's rows in a few such pieces and sends the finished rows of one piece to the peers while the next
+ * one is computed ("chunk the shard and overlap gather of finished dst tiles with remaining compute"). */
+int64_t ghf_graph_num_phases(const ghf_graph* g);
+int ghf_mp_layer_f16_range(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                           const float* d_W_msg, const float* d_W_self, const float* d_bias, const float* d_ln_w,
+                           const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
+                           float* d_out16_scale, float* d_upd, void* d_workspace, int32_t phase_lo, int32_t phase_hi,
+                           void* stream);
+
 /* Building a shadow by hand (layer 0 of a multi-GPU run, where max|h| must be agreed between ranks first):
  * ghf_absmax writes d_scale[1] = max |x|; ghf_convert_f16 picks the scale from d_scale[1] (computing it first when
  * have_amax == 0), writes d_scale[0] and d_y16 = fp16(x * 2^k).  elems % 8 == 0, 16-byte aligned pointers. */

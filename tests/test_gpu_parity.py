@@ -416,6 +416,39 @@ def test_fused_layer_kernel_matches_oracle_over_several_ring_turns(monkeypatch):
         assert_close(packed, ref, 0.0, TC_H_ATOL_SCALE1["f16"], f"out f16 fused forward_packed slots={slots}")
 
 
+@pytest.mark.parametrize("d,prec", [(128, "f16"), (64, "f16"), (128, "tf32"), (48, "fp32")])
+def test_layer_on_ranges_of_super_blocks_equals_the_whole_layer(d, prec):
+    """ghf_mp_layer_f16_range: a layer run as several pieces of consecutive super-blocks (what the multi-GPU path does
+    to overlap the row exchange with the next piece) writes exactly the rows of each piece and gives the layer's
+    result; a piece without edges still gets its epilogue (LN(relu(h)))."""
+    from graph_hypernetwork_forge import _native
+    rng = np.random.default_rng(d)
+    N, E, R = 9000, 70000, 13
+    src = rng.integers(0, N, E)
+    dst = rng.integers(0, N, E)
+    dst[dst // 1024 == 5] = 17                           # super-block 5 of the local range gets no edges at all
+    rel = rng.integers(0, R, E).astype(np.int32)
+    ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+    g = _native.Graph(ei, torch.from_numpy(rel).to(DEV), N, R, d, sb_nodes=1024)
+    assert g.num_phases == 9
+    gen = torch.Generator(device=DEV).manual_seed(d)
+    h = torch.randn(N, d, generator=gen, device=DEV)
+    Wm = torch.randn(R, d, d, generator=gen, device=DEV) * 0.05
+    Ws = torch.randn(R, d, d, generator=gen, device=DEV) * 0.05
+    b = torch.randn(R, d, generator=gen, device=DEV) * 0.1
+    lw, lb = torch.rand(d, generator=gen, device=DEV) + 0.5, torch.randn(d, generator=gen, device=DEV) * 0.1
+    code = _native.precision_code(prec)
+    whole, upd_whole = g.mp_layer(h, Wm, Ws, b, lw, lb, 1e-5, code, want_upd=True)
+    out = torch.full((N, d), float("nan"), device=DEV)
+    for p_lo, p_hi in ((0, 2), (2, 3), (3, 9)):
+        r0, r1 = g.phase_rows(p_lo, p_hi)
+        piece, _ = g.mp_layer(h, Wm, Ws, b, lw, lb, 1e-5, code, out=out, phases=(p_lo, p_hi))
+        assert bool(torch.isnan(out[r1:]).all()), "a piece wrote rows beyond its super-blocks"
+        assert bool(torch.isfinite(out[:r1]).all())
+    assert_close(out.cpu().numpy(), whole.cpu().numpy(), 1e-4, 2e-5, f"layer in three pieces d={d} {prec}")
+    assert bool((upd_whole[5 * 1024:6 * 1024] == 0).all())     # the edge-less super-block: mean over nothing
+
+
 def test_generator_written_operand_images_match_the_packed_path():
     """Hidden 64 / 256 on the f16 engine, enough relations and generator width 128: the one-call forward lets the
     generator's last Linear write the fp16 operand images itself (no fp32 W_msg / W_self, scales from an analytic
