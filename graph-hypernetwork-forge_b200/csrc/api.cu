@@ -266,7 +266,8 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
                     (int64_t)U * d * d >= (1 << 21) && !getenv("GHF_NO_FUSED_GENERATOR");
   // Hidden 128 on the f16 engine: fp32 weights are generated (70 MB at c3), and their fp16 operand images are packed
   // on the generator's stream too, so the layers on the main stream start with their operands ready.
-  const bool prepack = !fuse && prec == GHF_PREC_F16 && mp_f16_supported(d) && U > 0;
+  const char* det_env = getenv("GHF_DETERMINISTIC");   // the deterministic layer wants the fp32 matrices (a bound)
+  const bool prepack = !fuse && prec == GHF_PREC_F16 && mp_f16_supported(d) && U > 0 && !(det_env && det_env[0] == '1');
   const size_t img_bytes = fuse ? (size_t)mp_f16ss_pack_bytes((int)Un, d) : prepack ? (size_t)mp_f16_pack_bytes((int)Un) : 0;
   const size_t w_layer = fuse ? Arena::padded(img_bytes) + Arena::padded(Un * 4) + Arena::padded(Un * d * 4)
                               : 2 * Arena::padded(Un * d * d * 4) + Arena::padded(Un * d * 4);

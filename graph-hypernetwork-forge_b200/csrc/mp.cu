@@ -175,8 +175,9 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
                        const float* __restrict__ h, int64_t dst_lo, int64_t num_local,
                        const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
                        float* __restrict__ out, float* __restrict__ upd, __half* __restrict__ out16,
-                       float* __restrict__ out16_scale) {
+                       float* __restrict__ out16_scale, const int32_t* __restrict__ det_words) {
   using namespace fuse;
+  const int det_eB = det_words ? det_words[2] : 0;     // deterministic mode: acc holds int32 fixed point (mp.cuh)
   constexpr int V = D / 32;
   constexpr int kRows = 4;
   const int lane = threadIdx.x & 31;
@@ -217,7 +218,13 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
     for (int k = 0; k < kRows; ++k) {
       const int64_t r = num_local - 1 - (r0 + k * warps);
       if (r < 0) break;
-      const float inv = 1.f / (float)max(deg[k], 1);
+      float inv = 1.f / (float)max(deg[k], 1);
+      if (det_words) {                                   // integers * 2^-k_v, then the mean
+        const int kv = 30 - (32 - __clz(max(deg[k], 1))) - det_eB;
+        const float unscale = __int_as_float((uint32_t)(127 - max(-126, min(127, kv))) << 23);
+#pragma unroll
+        for (int j = 0; j < V; ++j) a[k][j] = (float)__float_as_int(a[k][j]) * unscale;
+      }
       float x[V], u[V], sum = 0.f;
 #pragma unroll
       for (int j = 0; j < V; ++j) {
@@ -335,7 +342,8 @@ extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim
 // rows [r0, r1) of the graph's local rows (all of them by default); acc / out / upd / out16 are indexed by local row
 static int launch_epilogue(const ghf_graph* g_full, const float* acc, const float* d_h, const float* d_ln_w,
                            const float* d_ln_b, float eps, float* d_out, float* d_upd, void* d_out16,
-                           float* d_out16_scale, cudaStream_t stream, int64_t r0 = 0, int64_t r1 = -1) {
+                           float* d_out16_scale, cudaStream_t stream, int64_t r0 = 0, int64_t r1 = -1,
+                           const int32_t* det_words = nullptr) {
   const int d = g_full->hidden_dim;
   if (r1 < 0) r1 = g_full->num_local;
   if (r1 <= r0) return 0;
@@ -361,14 +369,15 @@ static int launch_epilogue(const ghf_graph* g_full, const float* acc, const floa
     __half* o16 = reinterpret_cast<__half*>(d_out16);
     if (d == 32)
       mp_epilogue_vec_kernel<32><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16, d_out16_scale);
+                                                               d_out, d_upd, o16, d_out16_scale, det_words);
     else if (d == 64)
       mp_epilogue_vec_kernel<64><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16, d_out16_scale);
+                                                               d_out, d_upd, o16, d_out16_scale, det_words);
     else
       mp_epilogue_vec_kernel<128><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b,
-                                                                eps, d_out, d_upd, o16, d_out16_scale);
+                                                                eps, d_out, d_upd, o16, d_out16_scale, det_words);
   } else {
+    GHF_REQUIRE(det_words == nullptr, "ghf_mp_layer: the deterministic mode needs hidden_dim 128 and aligned buffers");
     GHF_REQUIRE(d_out16 == nullptr, "ghf_mp_layer: fp16 output needs hidden_dim 32/64/128 and 16-byte alignment");
     mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(
         acc, g->indeg, d_h, g->dst_lo, nl, d, d_ln_w, d_ln_b, eps, d_out, d_upd);
@@ -393,7 +402,7 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
                            float* acc_ext, bool accumulate, bool transposed, void* d_workspace, cudaStream_t stream,
                            float** acc_used, ProfRec* rec, const void* prepacked = nullptr,
                            const FusedEpilogue* fe = nullptr, bool* fused_done = nullptr, int phase_lo = 0,
-                           int phase_hi = -1) {
+                           int phase_hi = -1, const int32_t** det_words_out = nullptr) {
   // A range of super-blocks [phase_lo, phase_hi): the units of those super-blocks are contiguous, so the kernels see
   // a view of the graph that starts at the first of them; accumulator rows keep their local row index.
   const ghf_graph* g_whole = g;
@@ -476,13 +485,20 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
               : mp_umma_launch(g, d_h, d_bias, acc, pack, counter, stream);
     } else if (f16_ss) {
       rc = mp_f16ss_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream);
-    } else if (fused) {    // contraction + row epilogue in one kernel; the accumulator region is its ring
+    } else if (fused && !(getenv("GHF_DETERMINISTIC") && getenv("GHF_DETERMINISTIC")[0] == '1')) {
+      // contraction + row epilogue in one kernel; the accumulator region is its ring
       rc = mp_f16_fused_launch(g, h16, h16_scale, d_bias, pack, acc_ws, counter, fe->h, fe->ln_w, fe->ln_b, fe->eps,
                                fe->out, fe->upd, fe->out16, fe->out16_scale, stream);
       if (fused_done) *fused_done = true;
     } else if (precision == GHF_PREC_F16) {
+      // GHF_DETERMINISTIC=1 (layer entries only): fixed-point per-destination sums, bit-identical from run to run
+      const char* denv = getenv("GHF_DETERMINISTIC");
+      const bool det = det_words_out != nullptr && denv && denv[0] == '1';
+      GHF_REQUIRE(!det || (d_W_msg && d_W_self && !transposed && !accumulate && !prepacked),
+                  "GHF_DETERMINISTIC=1 needs the fp32 relation matrices of a plain layer");
       rc = mp_f16_launch(g, h16, h16_scale, d_bias, acc, pack, counter, stream, accumulate, skip_half, phase_lo,
-                         phase_hi);
+                         phase_hi, det ? d_W_msg : nullptr, det ? d_W_self : nullptr);
+      if (det) *det_words_out = mp_f16_det_words(counter);
     } else if (d <= 32) {
       rc = launch_mp_fp32<32>(g, d_h, d_W_msg, d_W_self, d_bias, acc, stream);
     } else if (d <= 64) {
@@ -525,16 +541,18 @@ static int mp_layer_impl(const ghf_graph* g, const float* d_h, const void* d_h16
   if (prof)
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
   float* acc = nullptr;
+  const int32_t* det_words = nullptr;
   const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale};
   bool fused_done = false;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
                                false, false, d_workspace, stream, &acc, prof ? &rec : nullptr, nullptr, &fe,
-                               &fused_done, phase_lo, phase_hi))
+                               &fused_done, phase_lo, phase_hi, &det_words))
     return rc;
   if (!fused_done) {
     const int64_t r0 = (int64_t)phase_lo * g->sb_nodes;
     const int64_t r1 = phase_hi * (int64_t)g->sb_nodes < g->num_local ? phase_hi * (int64_t)g->sb_nodes : g->num_local;
-    if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream, r0, r1))
+    if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream, r0, r1,
+                                 det_words))
       return rc;
   }
   if (prof) {

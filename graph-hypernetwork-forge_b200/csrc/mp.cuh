@@ -48,7 +48,12 @@ int64_t mp_f16_sync_bytes(const ghf_graph* g);
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
                   const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc = false,
                   int skip_half = 0,    // skip_half: 1 = no source term (W_msg NULL), 2 = no destination term
-                  int phase_lo = 0, int phase_hi = -1);   // super-blocks the given units lie in (clearing covers them)
+                  int phase_lo = 0, int phase_hi = -1,    // super-blocks the given units lie in (clearing covers them)
+                  const float* det_W_msg = nullptr, const float* det_W_self = nullptr);
+// Deterministic mode (both det_W_* given: the fp32 relation matrices, for a bound on the messages): per-destination
+// sums are accumulated as int32 fixed point - `acc` then holds integers, scaled per destination by 2^k_v with
+// k_v = 30 - bits(indeg_v) - eB, eB = mp_f16_det_words(sync_words)[2] (device) - and the epilogue converts back.
+const int32_t* mp_f16_det_words(const int* sync_words);
 
 // The whole layer in one kernel (mp_f16_fused.cu, hidden_dim 128): the contraction reduces into a ring of L2-resident
 // accumulator windows and the row epilogue (mean, residual, ReLU, LayerNorm, fp16 shadow) runs per super-block inside

@@ -205,7 +205,46 @@ to_f16_kernel(const float* __restrict__ h, int64_t n8, __half* __restrict__ h16,
   }
 }
 
-template <int kProdWarps, bool kTrace>
+// ---- deterministic mode: a bound on |message| -----------------------------------------------------------------
+// words[0] = max over relations r and output columns j of sum_k (|W_msg[r][k][j]| + |W_self[r][k][j]|) (float bits),
+// words[1] = max |bias| (float bits); non-negative floats order like their bit patterns, so atomicMax on ints works
+// and the result does not depend on the order of the atomics.
+__global__ void __launch_bounds__(kD)
+det_wnorm_kernel(const float* __restrict__ W_msg, const float* __restrict__ W_self, const float* __restrict__ bias,
+                 int32_t* __restrict__ words) {
+  __shared__ float s_max[kD / 32], s_bmax[kD / 32];
+  const int64_t r = blockIdx.x;
+  const int j = threadIdx.x;
+  float sum = 0.f;
+  for (int k = 0; k < kD; ++k)
+    sum += fabsf(W_msg[(r * kD + k) * kD + j]) + fabsf(W_self[(r * kD + k) * kD + j]);
+  float b = bias ? fabsf(bias[r * kD + j]) : 0.f;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    sum = fmaxf(sum, __shfl_xor_sync(0xffffffffu, sum, s));
+    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, s));
+  }
+  if ((j & 31) == 0) { s_max[j >> 5] = sum; s_bmax[j >> 5] = b; }
+  __syncthreads();
+  if (j == 0) {
+    for (int i = 1; i < kD / 32; ++i) { sum = fmaxf(sum, s_max[i]); b = fmaxf(b, s_bmax[i]); }
+    atomicMax(words, __float_as_int(sum));
+    atomicMax(words + 1, __float_as_int(b));
+  }
+}
+// words[2] = eB with |message| < 2^eB: |h_u W_msg + h_v W_self + bias| <= max|h| * column sum + max|bias|, one more
+// bit for the rounding of the fp16 operands
+__global__ void det_exponent_kernel(const float* __restrict__ h_scale, int32_t* __restrict__ words) {
+  const float bound = h_scale[1] * __int_as_float(words[0]) + __int_as_float(words[1]);
+  int e = -100;
+  if (bound > 0.f && isfinite(bound)) {
+    frexpf(bound, &e);        // bound = f * 2^e, f in [0.5, 1): bound < 2^e
+    e += 1;
+  }
+  words[2] = e > 60 ? 60 : (e < -100 ? -100 : e);
+}
+
+template <int kProdWarps, bool kTrace, bool kDet>
 __global__ void __launch_bounds__(threads_for(kProdWarps), 1)
 mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict__ unit_count,
               const int32_t* __restrict__ unit_rel, int64_t num_units, const int32_t* __restrict__ src_sorted,
@@ -214,7 +253,8 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
               const float* __restrict__ w_inv_scale,
               const float* __restrict__ bias, float* __restrict__ acc, int* __restrict__ unit_counter,
               const int32_t* __restrict__ unit_phase, int* __restrict__ zero_done, int num_phases, int phase_lo,
-              int sb_nodes, int64_t num_local, uint32_t flags, long long* __restrict__ trace) {
+              int sb_nodes, int64_t num_local, uint32_t flags, long long* __restrict__ trace,
+              const int32_t* __restrict__ indeg, const int32_t* __restrict__ det_words) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sA = (raw + 1023u) & ~1023u;
@@ -298,15 +338,24 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
     // Everything a tile's reductions need from global memory (the destination id of edge e0 + lane, the relation's
     // bias entry and scale) is fetched one tile ahead, so that no load latency sits between "accumulator ready" and
     // the first red.  (Loaded values are kept raw - arithmetic on them here would wait for the load right away.)
-    struct TileRegs { int dst; float bias_n, w_inv; };
+    struct TileRegs { int dst; float bias_n, w_inv; int deg; };
     auto fetch = [&](const int4& t) -> TileRegs {
-      TileRegs x{-1, 0.f, 1.f};
+      TileRegs x{-1, 0.f, 1.f, 1};
       if (t.x < 0) return x;
-      if (e0 + lane < t.y) x.dst = dst_sorted[t.x + e0 + lane];
+      if (e0 + lane < t.y) {
+        x.dst = dst_sorted[t.x + e0 + lane];
+        if constexpr (kDet) x.deg = indeg[x.dst];
+      }
       x.bias_n = bias ? bias[(int64_t)t.z * kD + col] : 0.f;
       x.w_inv = w_inv_scale[t.z];
       return x;
     };
+    // Deterministic mode: every contribution is rounded to fixed point BEFORE it is added - integer additions
+    // commute, so neither the order of the atomics nor the order of the edges inside a run matters.  The scale of
+    // destination v is 2^k_v, k_v = 30 - bits(indeg_v) - eB with |message| < 2^eB (det_words[2], from a bound on
+    // |h| and on the column sums of the relation matrices): |sum_v| 2^k_v < 2^30 cannot overflow an int32.
+    int det_eB = 0;
+    if constexpr (kDet) det_eB = det_words[2];
     int4 cur = q_acquire(0);
     TileRegs cr = fetch(cur);
     for (uint32_t it = 0; cur.x >= 0; ++it) {
@@ -326,7 +375,24 @@ mp_f16_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restrict_
         tmem_ld_wait();
         t1 = tick();
         tadd(2, t1 - t2);
-        if (!(flags & kDbgNoRed)) {
+        if constexpr (kDet) {
+          int run = 0, run_dst = -1;
+          int* acc_i = reinterpret_cast<int*>(acc_col);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int dsti = __shfl_sync(0xffffffffu, cr.dst, e);
+            const int degi = __shfl_sync(0xffffffffu, cr.deg, e);
+            if (dsti != run_dst) {
+              if (run_dst >= 0) atomicAdd(acc_i + (int64_t)run_dst * kD, run);
+              run = 0;
+              run_dst = dsti;
+            }
+            const int k = 30 - (32 - __clz(max(degi, 1))) - det_eB;
+            const float scale = __int_as_float((uint32_t)(127 + max(-126, min(127, k))) << 23);
+            run += __float2int_rn(fmaf(__uint_as_float(r[e]), inv, cr.bias_n) * scale);
+          }
+          if (run_dst >= 0) atomicAdd(acc_i + (int64_t)run_dst * kD, run);
+        } else if (!(flags & kDbgNoRed)) {
           // Segmented sum along the sorted order: edges of one (destination, relation) pair are adjacent, so their
           // contributions are added in a register and leave as ONE red (multigraphs, hub destinations); with all
           // destinations distinct this is one red per edge.
@@ -596,6 +662,10 @@ uint32_t env_flags() {
 
 bool mp_f16_supported(int d) { return d == kD; }
 
+// the three words of the deterministic mode inside the sync words (ints 8..10: clear of the unit counter's line)
+constexpr int kDetWordsAt = 8;
+const int32_t* mp_f16_det_words(const int* sync_words) { return sync_words + kDetWordsAt; }
+
 // [0, 256): counters | then two int32 per super-block (mp_f16_kernel uses one, mp_f16_fused_kernel both)
 int64_t mp_f16_sync_bytes(const ghf_graph* g) { return align_up(256 + g->num_phases * 8, 256); }
 
@@ -653,7 +723,9 @@ int mp_f16_convert(const float* h, int64_t elems, void* h16, float* scale, bool 
 
 int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias, float* acc,
                   const void* pack_scratch, int* sync_words, cudaStream_t stream, bool keep_acc, int skip_half,
-                  int phase_lo, int phase_hi) {
+                  int phase_lo, int phase_hi, const float* det_W_msg, const float* det_W_self) {
+  const bool det = det_W_msg != nullptr && det_W_self != nullptr;
+  GHF_REQUIRE(!det || (!keep_acc && skip_half == 0), "mp_f16: the deterministic mode covers the plain layer only");
   if (phase_hi < 0) phase_hi = (int)g->num_phases;
   GHF_REQUIRE(0 <= phase_lo && phase_lo <= phase_hi && phase_hi <= g->num_phases, "mp_f16: bad super-block range");
   GHF_REQUIRE(h16_scale != nullptr, "mp_f16: the fp16 shadow needs its scale words");
@@ -664,9 +736,10 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
               "mp_f16: h16 / acc / scratch must be 16-byte aligned");
   static bool configured = false;
   if (!configured) {
-    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   const char* penv = getenv("GHF_F16_PROD");
@@ -686,14 +759,22 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
   GHF_CUDA(cudaMemsetAsync(sync_words, 0, mp_f16_sync_bytes(g), stream));
   int* unit_counter = sync_words;
   int* zero_done = sync_words + 64;
-#define GHF_F16_LAUNCH(P, T)                                                                                      \
-  mp_f16_kernel<P, T><<<(unsigned)grid, threads_for(P), kSmem, stream>>>(                                        \
+  int32_t* det_words = sync_words + kDetWordsAt;        // [0] column-sum max, [1] |bias| max, [2] eB (mp_f16_det_words)
+  if (det) {
+    det_wnorm_kernel<<<(unsigned)g->num_rel, kD, 0, stream>>>(det_W_msg, det_W_self, bias, det_words);
+    GHF_LAUNCH_CHECK();
+    det_exponent_kernel<<<1, 1, 0, stream>>>(h16_scale, det_words);
+    GHF_LAUNCH_CHECK();
+  }
+#define GHF_F16_LAUNCH(P, T, D)                                                                                   \
+  mp_f16_kernel<P, T, D><<<(unsigned)grid, threads_for(P), kSmem, stream>>>(                                     \
       g->unit_start, g->unit_count, g->unit_rel, g->num_units, g->src_sorted, g->dst_sorted,                    \
       reinterpret_cast<const __half*>(h16), g->dst_lo, h16_scale, img, inv, bias, acc, unit_counter, g->unit_phase, \
-      zero_done, phase_hi, phase_lo, g->sb_nodes, g->num_local, env_flags() | (keep_acc ? kFlagNoClear : 0u) | (skip_half == 1 ? kFlagSkipSrc : skip_half == 2 ? kFlagSkipDst : 0u), trace)
-  if (trace) GHF_F16_LAUNCH(4, true);
-  else if (prod == 8) GHF_F16_LAUNCH(8, false);
-  else GHF_F16_LAUNCH(4, false);
+      zero_done, phase_hi, phase_lo, g->sb_nodes, g->num_local, env_flags() | (keep_acc ? kFlagNoClear : 0u) | (skip_half == 1 ? kFlagSkipSrc : skip_half == 2 ? kFlagSkipDst : 0u), trace, g->indeg, det_words)
+  if (det) GHF_F16_LAUNCH(4, false, true);
+  else if (trace) GHF_F16_LAUNCH(4, true, false);
+  else if (prod == 8) GHF_F16_LAUNCH(8, false, false);
+  else GHF_F16_LAUNCH(4, false, false);
 #undef GHF_F16_LAUNCH
   GHF_LAUNCH_CHECK();
   if (trace) {

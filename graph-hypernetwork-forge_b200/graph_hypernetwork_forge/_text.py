@@ -38,9 +38,37 @@ def pack_utf8(texts: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
     return np.frombuffer(blob, dtype=np.uint8), offsets
 
 
+_pyhost = None
+
+
+def _pyhost_lib():
+    """lib/libghf_pyhost.so (csrc/pyhost.c): one C pass over the list, keyed on object identity.  None when the
+    helper was not built - the numpy formulation below gives the same result, only slower."""
+    global _pyhost
+    if _pyhost is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_pyhost.so")
+        try:
+            lib = ctypes.PyDLL(path)
+            lib.ghf_collapse_pylist.restype = ctypes.c_int64
+            lib.ghf_collapse_pylist.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+            _pyhost = lib
+        except OSError:
+            _pyhost = False
+    return _pyhost or None
+
+
 def collapse_by_identity(texts: List[str]):
     """-> (distinct objects in first-occurrence order, int32 map edge -> position in that list)."""
     n = len(texts)
+    lib = _pyhost_lib() if type(texts) is list else None
+    if lib is not None:
+        edge_map = np.empty(n, dtype=np.int32)
+        first = np.empty(min(n, 1 << 22), dtype=np.int64)
+        k = int(lib.ghf_collapse_pylist(texts, edge_map.ctypes.data, first.ctypes.data, first.size))
+        if k >= 0:
+            return [texts[i] for i in first[:k]], edge_map
     ids = np.fromiter(map(id, texts), dtype=np.int64, count=n)
     _, first, inverse = np.unique(ids, return_index=True, return_inverse=True)
     order = np.argsort(first, kind="stable")          # distinct objects by first occurrence

@@ -166,3 +166,28 @@ def test_fusion_eligibility_and_autograd_routing_are_host_logic():
         assert not autograd.wants_grad(x)
     assert m128._precision_code() == _native.PREC_F16 and HyperGNN(8, 8, 32, 1)._precision_code() == _native.PREC_TF32
     assert HyperGNN(8, 8, 24, 1)._precision_code() == _native.PREC_FP32
+
+
+def test_list_collapse_in_c_equals_the_numpy_formulation():
+    """csrc/pyhost.c (one C pass over the Python list, keyed on object identity) against the numpy formulation it
+    replaces: same distinct objects in first-occurrence order, same edge map; tuples and huge vocabularies fall back."""
+    from graph_hypernetwork_forge import _text
+    if _text._pyhost_lib() is None:
+        pytest.skip("lib/libghf_pyhost.so not built")
+    names = [f"relation_{r:05d}" for r in range(300)]
+    rng = np.random.default_rng(0)
+    texts = [names[i] for i in rng.integers(0, 300, 50_000)]
+    texts[17] = "relation_00005x"[:-1]                   # equal content, different object
+    objs_c, map_c = _text.collapse_by_identity(texts)
+    saved, _text._pyhost = _text._pyhost, False
+    try:
+        objs_np, map_np = _text.collapse_by_identity(texts)
+    finally:
+        _text._pyhost = saved
+    assert all(a is b for a, b in zip(objs_c, objs_np)) and len(objs_c) == len(objs_np) == 301
+    assert np.array_equal(map_c, map_np) and map_c.dtype == np.int32
+    objs_t, map_t = _text.collapse_by_identity(tuple(texts))      # not a list: the numpy path
+    assert np.array_equal(map_t, map_c)
+    many = [str(i) for i in range(5000)]                 # every element its own object: the table grows
+    objs_m, map_m = _text.collapse_by_identity(many)
+    assert objs_m == many and np.array_equal(map_m, np.arange(5000))
