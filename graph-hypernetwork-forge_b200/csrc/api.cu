@@ -271,12 +271,11 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   const size_t img_bytes = fuse ? (size_t)mp_f16ss_pack_bytes((int)Un, d) : prepack ? (size_t)mp_f16_pack_bytes((int)Un) : 0;
   const size_t w_layer = fuse ? Arena::padded(img_bytes) + Arena::padded(Un * 4) + Arena::padded(Un * d * 4)
                               : 2 * Arena::padded(Un * d * d * 4) + Arena::padded(Un * d * 4);
+  const size_t gen_scratch_bytes = (size_t)ghf_weight_generators_scratch_bytes((int64_t)Un, H, depth, L);
   GHF_CUDA(B.reserve(Arena::padded(Un * T * 4) + (size_t)L * (w_layer + (prepack ? Arena::padded(img_bytes) : 0)) +
-                     4 * Arena::padded(Un * Hn * 4) + 8192));
+                     Arena::padded(gen_scratch_bytes) + 8192));
   float* temb = B.take<float>(Un * T);
-  float* hid_a = B.take<float>(Un * Hn);
-  float* hid_b = B.take<float>(Un * Hn);
-  float* zfin[2] = {B.take<float>(Un * Hn), B.take<float>(Un * Hn)};   // inputs of the two last Linears (fused path)
+  char* gen_scratch = B.take<char>(gen_scratch_bytes);
   float* words = B.take<float>(16);
   std::vector<std::array<float*, 3>> outs(L);
   std::vector<void*> images(L, nullptr);
@@ -291,52 +290,56 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
       if (prepack) images[l] = B.take<char>(img_bytes);
     }
   }
-  const int n_out[3] = {d * d, d * d, d};
   if (int rc = ghf_text_encode(d_utf8, d_offs, first, U, emb, C, Wp, bp, T, temb, stream)) return rc;
 
-  // WG:137-141 for the U distinct relations, every layer: on the side stream, beside graph build and projection
+  // WG:137-141 for the U distinct relations, EVERY layer at once (ghf_weight_generators: the hidden Linears of all
+  // 3 L MLPs are one grouped launch per depth level), on the side stream, beside graph build and projection
   cudaStream_t gen_stream = use_side ? side.stream : stream;
   if (use_side) {
     GHF_CUDA(cudaEventRecord(side.text_ready, stream));
     GHF_CUDA(cudaStreamWaitEvent(side.stream, side.text_ready, 0));
   }
-  auto generate = [&](int l) -> int {
-    for (int m = 0; m < 3 && U > 0; ++m) {
-      const float* in = temb;
-      int in_dim = T;
-      for (int i = 0; i < depth; ++i) {
-        float* o = (fuse && m < 2 && i == depth - 1) ? zfin[m] : ((i & 1) ? hid_b : hid_a);
-        if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][i], layers[l].b[m][i], H, 1, nullptr, o, gen_stream))
-          return rc;
-        in = o;
-        in_dim = H;
+  auto generate_all = [&]() -> int {
+    if (U == 0) return 0;
+    std::vector<const float*> gp, gls;
+    std::vector<float*> gout;
+    for (int l = 0; l < L; ++l)
+      for (int m = 0; m < 3; ++m) {
+        for (int i = 0; i <= depth; ++i) {
+          gp.push_back(layers[l].w[m][i]);
+          gp.push_back(layers[l].b[m][i]);
+        }
+        gls.push_back(layers[l].log_scale[m]);
+        gout.push_back(outs[l][m]);
       }
-      if (fuse && m < 2) continue;                         // the two big Linears follow, once both inputs exist
-      if (int rc = ghf_linear(in, U, in_dim, layers[l].w[m][depth], layers[l].b[m][depth], n_out[m], 0,
-                              layers[l].log_scale[m], outs[l][m], gen_stream))
-        return rc;
-    }
-    if (prepack)
-      if (int rc = mp_f16_pack_rel((int)U, outs[l][0], outs[l][1], images[l], gen_stream, false)) return rc;
-    if (fuse && U > 0) {
-      if (int rc = mp_f16ss_image_scales(zfin[0], zfin[1], H, U, layers[l].w[0][depth], layers[l].b[0][depth],
-                                         layers[l].w[1][depth], layers[l].b[1][depth], d, layers[l].log_scale[0],
-                                         layers[l].log_scale[1], words, img_scale[l], images[l], gen_stream))
-        return rc;
-      for (int m = 0; m < 2; ++m)
-        if (int rc = linear_umma_to_images(zfin[m], U, layers[l].w[m][depth], layers[l].b[m][depth], d, m,
-                                           layers[l].log_scale[m], img_scale[l], images[l],
-                                           mp_f16ss_image_bytes(d), gen_stream))
+    if (int rc = ghf_weight_generators(temb, U, T, H, depth, L, d, d, gp.data(), gls.data(), gout.data(), gen_scratch,
+                                       fuse ? 1 : 0, gen_stream))
+      return rc;
+    for (int l = 0; l < L; ++l) {
+      if (prepack)
+        if (int rc = mp_f16_pack_rel((int)U, outs[l][0], outs[l][1], images[l], gen_stream, false)) return rc;
+      if (fuse) {
+        // inputs of the two big heads of generator l (layout documented in ghf_b200.h)
+        const float* base = reinterpret_cast<const float*>(gen_scratch) + (size_t)((depth - 1) & 1) * 3 * L * U * H;
+        const float* zm = base + (size_t)(3 * l + 0) * U * H;
+        const float* zs = base + (size_t)(3 * l + 1) * U * H;
+        if (int rc = mp_f16ss_image_scales(zm, zs, H, U, layers[l].w[0][depth], layers[l].b[0][depth],
+                                           layers[l].w[1][depth], layers[l].b[1][depth], d, layers[l].log_scale[0],
+                                           layers[l].log_scale[1], words, img_scale[l], images[l], gen_stream))
           return rc;
+        const float* z[2] = {zm, zs};
+        for (int m = 0; m < 2; ++m)
+          if (int rc = linear_umma_to_images(z[m], U, layers[l].w[m][depth], layers[l].b[m][depth], d, m,
+                                             layers[l].log_scale[m], img_scale[l], images[l],
+                                             mp_f16ss_image_bytes(d), gen_stream))
+            return rc;
+      }
+      if (use_side) GHF_CUDA(cudaEventRecord(side.weights_ready[l], side.stream));
     }
     return 0;
   };
-  // only layer 0's generator is enqueued before graph build: the host spends ~10 us per launch, and the main
-  // stream should not wait for 27 of them; the other layers follow while graph build's tail and the projection run
-  if (use_side) {
-    if (int rc = generate(0)) return rc;
-    GHF_CUDA(cudaEventRecord(side.weights_ready[0], side.stream));
-  }
+  if (use_side)
+    if (int rc = generate_all()) return rc;
 
   ghf_graph* g = nullptr;
   if (int rc = ghf_graph_build(d_ei, E, nullptr, 0, rel, num_nodes, (int32_t)(U > 0 ? U : 1), d, 0, num_nodes, 0, 0,
@@ -358,11 +361,8 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
     return rc;
   }
   trace.mark("proj-join");
-  if (use_side)
-    for (int l = 1; l < L; ++l) {
-      if (int rc = generate(l)) return rc;
-      GHF_CUDA(cudaEventRecord(side.weights_ready[l], side.stream));
-    }
+  if (!use_side)
+    if (int rc = generate_all()) return rc;
 
   float* cur = h0;
   float* nxt = h1;
@@ -371,11 +371,7 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   float* cur_sc = scales;
   float* nxt_sc = scales + 2;
   for (int l = 0; l < L; ++l) {
-    if (use_side) {
-      GHF_CUDA(cudaStreamWaitEvent(stream, side.weights_ready[l], 0));
-    } else if (int rc = generate(l)) {
-      return rc;
-    }
+    if (use_side && U > 0) GHF_CUDA(cudaStreamWaitEvent(stream, side.weights_ready[l], 0));
     // HG:286-296
     void* out16 = (want_f16 && l + 1 < L) ? nxt16 : nullptr;
     float* dst = l + 1 < L ? nxt : d_out;                // the last layer writes the caller's buffer

@@ -80,6 +80,9 @@ def lib():
         "ghf_hypergnn_forward_device": (c_int, [POINTER(ModelDesc), POINTER(c_void_p), c_int64, P, c_int64, P,
                                                 c_int64, P, P, P, P]),
         "ghf_copy_async": (c_int, [P, P, c_int64, P]),
+        "ghf_weight_generators_scratch_bytes": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
+        "ghf_weight_generators": (c_int, [P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                          POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), P, c_int32, P]),
         "ghf_launch_count": (c_int64, [c_int]),
         "ghf_profile_enable": (c_int, [c_int]),
         "ghf_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
@@ -100,7 +103,8 @@ EXPORTED_SYMBOLS = (
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
     "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_layer_f16_range", "ghf_graph_num_phases", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
     "ghf_text_encode_backward", "ghf_weight_images_bytes", "ghf_weight_images_f16", "ghf_mp_layer_images",
-    "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_copy_async", "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
+    "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_copy_async", "ghf_weight_generators_scratch_bytes", "ghf_weight_generators",
+    "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
 )
 
 
@@ -202,6 +206,44 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_
                                        _ptr(y), _ptr(y16.data) if y16 else None, _ptr(y16.scale) if y16 else None,
                                        _stream(dev)), "ghf_linear_f16out")
     return (y, y16) if want_f16 else y
+
+
+def weight_generators(text_emb: torch.Tensor, mlps, log_scales, d_in: int, d_out: int):
+    """WG:120-143 for several generators in ONE native call (ghf_weight_generators: the hidden Linears of all their
+    MLPs are one grouped launch per depth level).  `mlps`: per generator, the Linears of its three MLPs (W_msg,
+    W_self, bias order) as lists of (weight, bias); `log_scales`: per generator three [1] tensors.
+    -> per generator {"W_msg" [U,d_in,d_out], "W_self", "bias" [U,d_out]}."""
+    text_emb = _f32(text_emb)
+    dev = text_emb.device
+    U, T = text_emb.shape
+    n_gen = len(mlps)
+    depth = len(mlps[0][0]) - 1
+    H = mlps[0][0][0][0].shape[0] if depth > 0 else 0
+    flat, keep = [], []
+    for gen in mlps:
+        if len(gen) != 3 or any(len(m) != depth + 1 for m in gen):
+            raise RuntimeError("weight_generators: every generator needs three MLPs of equal depth")
+        for m in gen:
+            for i, (w, b) in enumerate(m):
+                w, b = _f32(w), _f32(b)
+                want = (H, T if i == 0 else H) if i < depth else None
+                if want is not None and tuple(w.shape) != want:
+                    raise RuntimeError(f"weight_generators: hidden Linear {i} is {tuple(w.shape)}, expected {want}")
+                keep += [w, b]
+                flat += [w.data_ptr(), b.data_ptr()]
+    ls = [_f32(t) for g in log_scales for t in g]
+    outs = [{"W_msg": torch.empty((U, d_in, d_out), dtype=torch.float32, device=dev),
+             "W_self": torch.empty((U, d_in, d_out), dtype=torch.float32, device=dev),
+             "bias": torch.empty((U, d_out), dtype=torch.float32, device=dev)} for _ in range(n_gen)]
+    n_scr = int(lib().ghf_weight_generators_scratch_bytes(U, H, depth, n_gen))
+    scratch = torch.empty(n_scr, dtype=torch.uint8, device=dev)
+    params = (c_void_p * len(flat))(*flat)
+    lsp = (c_void_p * len(ls))(*[t.data_ptr() for t in ls])
+    outp = (c_void_p * (3 * n_gen))(*[o[k].data_ptr() for o in outs for k in ("W_msg", "W_self", "bias")])
+    with torch.cuda.device(dev):
+        _check(lib().ghf_weight_generators(_ptr(text_emb), U, T, H, depth, n_gen, d_in, d_out, params, lsp, outp,
+                                           _ptr(scratch), 0, _stream(dev)), "ghf_weight_generators")
+    return outs
 
 
 def copy_async(dst: torch.Tensor, src: torch.Tensor) -> None:

@@ -330,8 +330,9 @@ class ShardedForward:
                 exchange_rows(cur, self.ranges, self.rank, self.group)
             text_embs = m.text_encoder.encode_packed(packed)
             out = None
+            all_w = m._generate_all(text_embs, packed.num_unique)
             for l in range(m.num_layers):
-                w = m._generate(l, text_embs, packed.num_unique)
+                w = all_w[l]
                 ln = m.layer_norms[l]
                 last = l + 1 == m.num_layers
                 if self.hi > self.lo:
@@ -396,12 +397,11 @@ class ShardedForward:
         with torch.no_grad():
             text_embs = m.text_encoder.encode_packed(packed)
             self._gen_stream.wait_stream(main)
-            weights, ready = [], []
-            with torch.cuda.stream(self._gen_stream):
-                for l in range(m.num_layers):
-                    weights.append(m._generate(l, text_embs, packed.num_unique))
-                    ready.append(torch.cuda.Event())
-                    ready[-1].record(self._gen_stream)
+            with torch.cuda.stream(self._gen_stream):    # every layer's weights in one native call
+                weights = m._generate_all(text_embs, packed.num_unique)
+                done = torch.cuda.Event()
+                done.record(self._gen_stream)
+            ready = [done] * m.num_layers
             for w in weights:                             # the tensors are consumed on the main stream
                 for t in w.values():
                     t.record_stream(main)

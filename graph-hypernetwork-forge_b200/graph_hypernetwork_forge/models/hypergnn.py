@@ -252,6 +252,7 @@ class HyperGNN(nn.Module):
                 taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
                 taps["in_degree"] = graph.export()["indeg"]
             fuse = taps is None and self._can_fuse_generator(prec, packed.num_unique, text_embs)
+            all_w = None if fuse else self._generate_all(text_embs, packed.num_unique)
             for l in range(self.num_layers):
                 ln = self.layer_norms[l]
                 out16 = None
@@ -267,7 +268,7 @@ class HyperGNN(nn.Module):
                     h = graph.mp_layer_images(h, images, bias, ln.weight, ln.bias, ln.eps, h16=h16, out16=out16)
                     h16 = out16
                     continue
-                w = self._generate(l, text_embs, packed.num_unique)
+                w = all_w[l]
                 h, upd = graph.mp_layer(h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, prec,
                                         want_upd=taps is not None, h16=h16, out16=out16)
                 h16 = out16
@@ -360,6 +361,19 @@ class HyperGNN(nn.Module):
             return {"W_msg": torch.zeros(1, d, d, device=dev), "W_self": torch.zeros(1, d, d, device=dev),
                     "bias": torch.zeros(1, d, device=dev)}
         return self.weight_generators[layer](text_embs)
+
+    def _generate_all(self, text_embs: torch.Tensor, num_unique: int) -> List[dict]:
+        """The generated weights of EVERY layer in one native call (they depend on the text embeddings only):
+        `ghf_weight_generators` batches the hidden Linears of all 3 L MLPs into one launch per depth level.
+        Inference only; falls back to layer-by-layer generation when autograd or dropout is in play."""
+        gens = list(self.weight_generators)
+        if num_unique == 0 or (self.training and self.dropout > 0.0) or \
+                autograd.wants_grad(text_embs, *self.parameters()) or len(gens) > 16:
+            return [self._generate(l, text_embs, num_unique) for l in range(self.num_layers)]
+        mlps = [[[(m.weight, m.bias) for m in gen.generators[kind] if isinstance(m, nn.Linear)]
+                 for kind in ("W_msg", "W_self", "bias")] for gen in gens]
+        scales = [[gen.log_scales[k] for k in ("W_msg", "W_self", "bias")] for gen in gens]
+        return _native.weight_generators(text_embs, mlps, scales, self.hidden_dim, self.hidden_dim)
 
     def forward_packed(self, node_features: torch.Tensor, edge_index: torch.Tensor, utf8: torch.Tensor,
                        offsets: torch.Tensor) -> torch.Tensor:

@@ -230,6 +230,23 @@ int ghf_hypergnn_forward_device(const ghf_model_desc* desc, const float* const* 
                                 const int64_t* d_edge_index, int64_t E, const uint8_t* d_utf8,
                                 const int64_t* d_offsets, float* d_out, void* stream);
 
+/* ---- a8 for several generators at once (WG:120-143; north_star item 2: "the three per-layer MLPs run as batched
+ * GEMMs over the R unique relations") ---------------------------------------------------------------------------
+ * The L generators of a HyperGNN depend on the text embeddings only, so their hidden Linears are ONE grouped launch
+ * per depth level (3 n_gen equally shaped problems), the bias heads another one, and the two [U, d_in*d_out] heads of
+ * each generator go through ghf_linear (tcgen05 when large enough).
+ * h_params: HOST array of n_gen x 3 x (depth+1) x {weight, bias} DEVICE pointers (MLP order W_msg, W_self, bias - the
+ * flat order of INTEGRATION.md); h_log_scales: n_gen x 3 device pointers; h_out: n_gen x 3 device output pointers
+ * (W_msg [U,d_in,d_out], W_self likewise, bias [U,d_out]).  d_scratch: ghf_weight_generators_scratch_bytes bytes; it
+ * holds the hidden activations, the input of head m of generator g starting at float offset
+ * ((depth-1)&1) * 3 n_gen U H + (3 g + m) U H.  skip_big != 0: the W_msg / W_self heads are left to the caller (who
+ * writes operand images from those inputs, ghf_weight_images_f16). */
+int64_t ghf_weight_generators_scratch_bytes(int64_t U, int32_t H, int32_t depth, int32_t n_gen);
+int ghf_weight_generators(const float* d_text_emb, int64_t U, int32_t T, int32_t H, int32_t depth, int32_t n_gen,
+                          int32_t d_in, int32_t d_out, const float* const* h_params,
+                          const float* const* h_log_scales, float* const* h_out, void* d_scratch, int32_t skip_big,
+                          void* stream);
+
 /* ---- multi-GPU plumbing --------------------------------------------------------------------------
  * Stream-ordered copy between device buffers that may live on different GPUs of one box (peer-mapped / symmetric
  * memory): a rank pushes the fp16 rows it has just computed into every peer's copy of h16 over NVLink with the copy

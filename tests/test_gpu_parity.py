@@ -103,6 +103,31 @@ def test_weight_generator_standalone_matches_reference_golden():
             assert_close(single[k].cpu().numpy(), want_s, FP32_RTOL, 2e-6 * wmax, f"{tag} single {k}")
 
 
+@pytest.mark.parametrize("U,T,H,depth,d,L", [(535, 64, 128, 2, 128, 3), (37, 16, 64, 2, 24, 2), (200, 32, 64, 0, 32, 2),
+                                             (3, 64, 128, 1, 64, 1)])
+def test_grouped_weight_generators_equal_the_modules(U, T, H, depth, d, L):
+    """ghf_weight_generators (every layer's three MLPs in one native call, hidden Linears grouped per depth level)
+    against the per-module WeightGenerator.forward, which is pinned to the reference's golden outputs above."""
+    from graph_hypernetwork_forge import WeightGenerator, _native
+    import torch.nn as nn
+    torch.manual_seed(U + d)
+    gens = [WeightGenerator(T, d, d, hidden_dim=H, num_hidden=depth).eval().to(DEV) for _ in range(L)]
+    with torch.no_grad():
+        for i, g in enumerate(gens):
+            for p in g.log_scales.values():
+                p.fill_(-1.0 - 0.1 * i)
+    emb = torch.randn(U, T, device=DEV)
+    mlps = [[[(m.weight, m.bias) for m in g.generators[k] if isinstance(m, nn.Linear)] for k in ("W_msg", "W_self", "bias")]
+            for g in gens]
+    scales = [[g.log_scales[k] for k in ("W_msg", "W_self", "bias")] for g in gens]
+    got = _native.weight_generators(emb, mlps, scales, d, d)
+    for g, out in zip(gens, got):
+        want = g(emb)
+        for k in ("W_msg", "W_self", "bias"):
+            wmax = float(want[k].abs().max())
+            assert_close(out[k].cpu().numpy(), want[k].cpu().numpy(), FP32_RTOL, 2e-6 * wmax, f"grouped generator {k}")
+
+
 def test_forward_call_is_drop_in(toy_kg):
     """model(node_features, edge_index, edge_texts) exactly as the reference is called."""
     case = load_case("toy_c1")
