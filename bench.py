@@ -312,7 +312,9 @@ def main():
                     help="enqueue the stages from Python (prepare_packed + forward_prepared) instead of one native call")
     ap.add_argument("--train", action="store_true",
                     help="also time a training step (forward + backward on a prepared graph) -> key 'train_step'")
-    ap.add_argument("--chunks", type=int, default=2, help="multi-GPU: pieces of a rank's rows whose exchange overlaps the next piece")
+    ap.add_argument("--chunks", type=int, default=0, help="multi-GPU, --push copy: pieces of a rank's rows whose exchange overlaps the next piece (0 = auto)")
+    ap.add_argument("--push", default="kernel", choices=["kernel", "copy"],
+                    help="multi-GPU p2p: epilogue kernel stores rows to the peers that read them | whole ranges by copy engines")
     ap.add_argument("--transport", default=None, choices=["p2p", "collective"], help="multi-GPU row exchange")
     ap.add_argument("--balance", default="nodes", choices=["nodes", "edges"], help="multi-GPU: destination ranges by node count or by edges")
     ap.add_argument("--no-check", action="store_true", help="multi-GPU: skip the comparison with a single-GPU forward")
@@ -388,7 +390,8 @@ def main():
             rowptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
             rowptr[1:] = torch.cumsum(indeg, 0)
             ranges = plan_partition_by_edges(rowptr, world)
-        sharded = ShardedForward(model, N, dist.group.WORLD, ranges=ranges, transport=args.transport, chunks=args.chunks)
+        sharded = ShardedForward(model, N, dist.group.WORLD, ranges=ranges, transport=args.transport, chunks=args.chunks,
+                                 push=args.push)
         n_local = sharded.hi - sharded.lo
         if pre_sharded:
             per = [E // world + (1 if r < E % world else 0) for r in range(world)]
@@ -574,7 +577,11 @@ def main():
             transport_lines = keep[:3] + keep[-5:]
         except Exception:
             pass
-        multi = {"transport": sharded.transport, "chunks": per_layer, "balance": args.balance,
+        sel = sharded.rows_needed_by_peers
+        multi = {"transport": sharded.transport, "push": args.push if sharded.transport == "p2p" else None,
+                 "rows_sent_fraction": (float((sel.float().sum() - sel[rank].float().sum()) /
+                                              max(1, sel.numel() - sel.shape[1])) if sel is not None else None),
+                 "chunks": per_layer, "balance": args.balance,
                  "ranges_rows": [hi_r - lo_r for lo_r, hi_r in sharded.ranges],
                  "edges_per_rank_max": int(local_edges), "parity": parity,
                  "stage_ms_max_over_ranks": {"prep": float(st[0]), "compute": float(st[1]), "exposed_exchange": float(st[2])},

@@ -169,13 +169,25 @@ mp_epilogue_kernel(const float* __restrict__ acc, const int32_t* __restrict__ in
 // The same epilogue for hidden_dim 32 / 64 / 128: a lane owns D/32 CONSECUTIVE columns (one vector access per row
 // and operand), four rows in flight per warp, and an optional fp16 copy of the output row for the next layer's
 // gathers (GHF_PREC_F16).
+// Multi-GPU: the fp16 rows the epilogue produces are also stored straight into the peers' copies of the shadow table
+// (peer-mapped symmetric memory, NVLink stores) - but only into the copies of the ranks that READ the row: rank q
+// gathers row v only if one of its edges has source v (`mask[q * mask_stride + local row]`, exchanged once per
+// graph).  No staging copy, no collective kernel, ~half the bytes of an all-gather at in-degree 6.
+struct PeerPush {
+  const uint8_t* mask = nullptr;      // [world][mask_stride] bytes; nullptr: no push
+  int64_t mask_stride = 0;
+  __half* const* tables = nullptr;    // device array [world]: base of every rank's [N, D] fp16 table
+  int world = 0, me = 0;
+  int64_t table_row0 = 0;             // global row of local row 0
+};
+
 template <int D>
 __global__ void __launch_bounds__(256)
 mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict__ indeg,
                        const float* __restrict__ h, int64_t dst_lo, int64_t num_local,
                        const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
                        float* __restrict__ out, float* __restrict__ upd, __half* __restrict__ out16,
-                       float* __restrict__ out16_scale, const int32_t* __restrict__ det_words) {
+                       float* __restrict__ out16_scale, const int32_t* __restrict__ det_words, const PeerPush push) {
   using namespace fuse;
   const int det_eB = det_words ? det_words[2] : 0;     // deterministic mode: acc holds int32 fixed point (mp.cuh)
   constexpr int V = D / 32;
@@ -250,10 +262,19 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
         __half* o = out16 + r * D + lane * V;
         if constexpr (V == 4) {
           const __half2 p0 = __floats2half2_rn(y[0] * s16, y[1] * s16), p1 = __floats2half2_rn(y[2] * s16, y[3] * s16);
-          *reinterpret_cast<uint2*>(o) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+          const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+          *reinterpret_cast<uint2*>(o) = packed;
+          if (push.mask)
+            for (int q = 0; q < push.world; ++q)
+              if (q != push.me && push.mask[q * push.mask_stride + r])
+                *reinterpret_cast<uint2*>(push.tables[q] + (push.table_row0 + r) * D + lane * V) = packed;
         } else if constexpr (V == 2) {
-          *reinterpret_cast<__half2*>(o) = __floats2half2_rn(y[0] * s16, y[1] * s16);
+          const __half2 packed = __floats2half2_rn(y[0] * s16, y[1] * s16);
+          *reinterpret_cast<__half2*>(o) = packed;
+          if (push.mask)
+            for (int q = 0; q < push.world; ++q)
+              if (q != push.me && push.mask[q * push.mask_stride + r])
+                *reinterpret_cast<__half2*>(push.tables[q] + (push.table_row0 + r) * D + lane * V) = packed;
         } else {
           *o = __float2half_rn(y[0] * s16);
         }
@@ -343,7 +364,7 @@ extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim
 static int launch_epilogue(const ghf_graph* g_full, const float* acc, const float* d_h, const float* d_ln_w,
                            const float* d_ln_b, float eps, float* d_out, float* d_upd, void* d_out16,
                            float* d_out16_scale, cudaStream_t stream, int64_t r0 = 0, int64_t r1 = -1,
-                           const int32_t* det_words = nullptr) {
+                           const int32_t* det_words = nullptr, PeerPush push = PeerPush()) {
   const int d = g_full->hidden_dim;
   if (r1 < 0) r1 = g_full->num_local;
   if (r1 <= r0) return 0;
@@ -356,6 +377,11 @@ static int launch_epilogue(const ghf_graph* g_full, const float* acc, const floa
   d_out += r0 * d;
   if (d_upd) d_upd += r0 * d;
   if (d_out16) d_out16 = reinterpret_cast<char*>(d_out16) + r0 * d * 2;
+  if (push.mask) {
+    GHF_REQUIRE(d_out16 != nullptr && (d == 64 || d == 128), "ghf_mp_layer: the peer push needs the fp16 output, hidden 64/128");
+    push.mask += r0;
+    push.table_row0 = g->dst_lo;                         // the view's first row
+  }
   const int64_t nl = g->num_local;
   const int threads = 256;
   const bool aligned = (reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(d_h) |
@@ -369,14 +395,15 @@ static int launch_epilogue(const ghf_graph* g_full, const float* acc, const floa
     __half* o16 = reinterpret_cast<__half*>(d_out16);
     if (d == 32)
       mp_epilogue_vec_kernel<32><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16, d_out16_scale, det_words);
+                                                               d_out, d_upd, o16, d_out16_scale, det_words, push);
     else if (d == 64)
       mp_epilogue_vec_kernel<64><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16, d_out16_scale, det_words);
+                                                               d_out, d_upd, o16, d_out16_scale, det_words, push);
     else
       mp_epilogue_vec_kernel<128><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b,
-                                                                eps, d_out, d_upd, o16, d_out16_scale, det_words);
+                                                                eps, d_out, d_upd, o16, d_out16_scale, det_words, push);
   } else {
+    GHF_REQUIRE(push.mask == nullptr, "ghf_mp_layer: the peer push needs hidden_dim 64/128 and aligned buffers");
     GHF_REQUIRE(det_words == nullptr, "ghf_mp_layer: the deterministic mode needs hidden_dim 128 and aligned buffers");
     GHF_REQUIRE(d_out16 == nullptr, "ghf_mp_layer: fp16 output needs hidden_dim 32/64/128 and 16-byte alignment");
     mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(
@@ -393,6 +420,7 @@ struct FusedEpilogue {
   float *out, *upd;
   void* out16;
   float* out16_scale;
+  bool no_fusion = false;    // the caller needs the separate epilogue kernel (peer push)
 };
 
 // The contraction of one layer: acc[v] = sum over in-edges of [h_u | h_v] @ [W_msg[r] ; W_self[r]] + bias[r].
@@ -425,7 +453,7 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
   // (the f16 kernel clears the accumulator itself and keeps per-phase sync words next to the counter)
   const bool f16_ss = precision == GHF_PREC_F16 && mp_f16ss_supported(d);   // hidden 256: streamed weights
-  const bool fused = fe != nullptr && !ranged && precision == GHF_PREC_F16 && !f16_ss && mp_f16_supported(d) &&
+  const bool fused = fe != nullptr && !ranged && !fe->no_fusion && precision == GHF_PREC_F16 && !f16_ss && mp_f16_supported(d) &&
                      mp_f16_fused_enabled(g) && fe->ln_w != nullptr && fe->ln_b != nullptr &&
                      (reinterpret_cast<uintptr_t>(fe->ln_w) | reinterpret_cast<uintptr_t>(fe->ln_b) |
                       reinterpret_cast<uintptr_t>(fe->h) | reinterpret_cast<uintptr_t>(fe->out) |
@@ -526,7 +554,7 @@ static int mp_layer_impl(const ghf_graph* g, const float* d_h, const void* d_h16
                          const float* d_W_msg, const float* d_W_self, const float* d_bias, const float* d_ln_w,
                          const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
                          float* d_out16_scale, float* d_upd, void* d_workspace, int phase_lo, int phase_hi,
-                         void* stream_) {
+                         void* stream_, PeerPush push = PeerPush()) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_layer_args(g, d_workspace, precision, d_h16, d_h16_scale)) return rc;
   GHF_REQUIRE(d_out16 == nullptr || d_out16_scale != nullptr, "ghf_mp_layer: d_out16 needs d_out16_scale (float[2])");
@@ -542,7 +570,7 @@ static int mp_layer_impl(const ghf_graph* g, const float* d_h, const void* d_h16
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
   float* acc = nullptr;
   const int32_t* det_words = nullptr;
-  const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale};
+  const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, push.mask != nullptr};
   bool fused_done = false;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
                                false, false, d_workspace, stream, &acc, prof ? &rec : nullptr, nullptr, &fe,
@@ -552,7 +580,7 @@ static int mp_layer_impl(const ghf_graph* g, const float* d_h, const void* d_h16
     const int64_t r0 = (int64_t)phase_lo * g->sb_nodes;
     const int64_t r1 = phase_hi * (int64_t)g->sb_nodes < g->num_local ? phase_hi * (int64_t)g->sb_nodes : g->num_local;
     if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream, r0, r1,
-                                 det_words))
+                                 det_words, push))
       return rc;
   }
   if (prof) {
@@ -578,6 +606,45 @@ extern "C" int ghf_mp_layer_f16_range(const ghf_graph* g, const float* d_h, cons
                                       void* d_workspace, int32_t phase_lo, int32_t phase_hi, void* stream_) {
   return mp_layer_impl(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out,
                        d_out16, d_out16_scale, d_upd, d_workspace, phase_lo, phase_hi, stream_);
+}
+
+extern "C" int ghf_mp_layer_f16_push(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                                     const float* d_W_msg, const float* d_W_self, const float* d_bias,
+                                     const float* d_ln_w, const float* d_ln_b, float eps, int precision, float* d_out,
+                                     void* d_out16, float* d_out16_scale, float* d_upd, void* d_workspace,
+                                     int32_t phase_lo, int32_t phase_hi, const uint8_t* d_peer_mask,
+                                     int64_t mask_stride, void* const* d_peer_tables, int32_t world, int32_t rank,
+                                     void* stream_) {
+  GHF_REQUIRE(g != nullptr, "ghf_mp_layer_f16_push: graph is NULL");
+  GHF_REQUIRE(d_peer_mask && d_peer_tables && world >= 1 && rank >= 0 && rank < world && mask_stride >= g->num_local,
+              "ghf_mp_layer_f16_push: bad peer arguments");
+  PeerPush push;
+  push.mask = d_peer_mask;
+  push.mask_stride = mask_stride;
+  push.tables = reinterpret_cast<__half* const*>(d_peer_tables);
+  push.world = world;
+  push.me = rank;
+  return mp_layer_impl(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out,
+                       d_out16, d_out16_scale, d_upd, d_workspace, phase_lo, phase_hi, stream_, push);
+}
+
+static __global__ void mark_rows_kernel(const int64_t* __restrict__ ids, const uint32_t* __restrict__ subset, int64_t n,
+                                 int64_t num_rows, uint8_t* __restrict__ mask) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t v = ids[subset ? subset[j] : j];
+  if (v >= 0 && v < num_rows) mask[v] = 1;               // every writer stores the same byte
+}
+
+extern "C" int ghf_mark_rows(const int64_t* d_ids, const uint32_t* d_subset, int64_t n, int64_t num_rows,
+                             uint8_t* d_mask, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHF_REQUIRE(n >= 0 && num_rows >= 0 && (n == 0 || (d_ids && d_mask)), "ghf_mark_rows: bad arguments");
+  GHF_CUDA(cudaMemsetAsync(d_mask, 0, (size_t)num_rows, stream));
+  if (n == 0) return 0;
+  mark_rows_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(d_ids, d_subset, n, num_rows, d_mask);
+  GHF_LAUNCH_CHECK();
+  return 0;
 }
 
 namespace ghf {

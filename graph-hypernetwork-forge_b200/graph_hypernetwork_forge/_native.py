@@ -64,6 +64,9 @@ def lib():
         "ghf_mp_layer_f16": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, P]),
         "ghf_mp_layer_f16_range": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, c_int32, c_int32, P]),
         "ghf_graph_num_phases": (c_int64, [P]),
+        "ghf_mp_layer_f16_push": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, P, c_int32, c_int32,
+                                          P, c_int64, P, c_int32, c_int32, P]),
+        "ghf_mark_rows": (c_int, [P, P, c_int64, c_int64, P, P]),
         "ghf_mp_contract": (c_int, [P, P, P, P, P, P, P, c_int, P, c_int, c_int, P, P]),
         "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P, P]),
         "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, P]),
@@ -101,7 +104,7 @@ EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
     "ghf_linear_f16out",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
-    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_layer_f16_range", "ghf_graph_num_phases", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
+    "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_layer_f16_range", "ghf_graph_num_phases", "ghf_mp_layer_f16_push", "ghf_mark_rows", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
     "ghf_text_encode_backward", "ghf_weight_images_bytes", "ghf_weight_images_f16", "ghf_mp_layer_images",
     "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_copy_async", "ghf_weight_generators_scratch_bytes", "ghf_weight_generators",
     "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
@@ -244,6 +247,32 @@ def weight_generators(text_emb: torch.Tensor, mlps, log_scales, d_in: int, d_out
         _check(lib().ghf_weight_generators(_ptr(text_emb), U, T, H, depth, n_gen, d_in, d_out, params, lsp, outp,
                                            _ptr(scratch), 0, _stream(dev)), "ghf_weight_generators")
     return outs
+
+
+def mark_rows(ids: torch.Tensor, num_rows: int, subset=None) -> torch.Tensor:
+    """uint8 [num_rows]: 1 where the row id occurs in `ids` (int64; only the entries listed in `subset` when given):
+    the rows of the node table a rank gathers from."""
+    dev = ids.device
+    if ids.dtype != torch.int64 or not ids.is_contiguous():
+        raise RuntimeError("mark_rows: ids must be a contiguous int64 tensor")
+    mask = torch.empty(max(num_rows, 1), dtype=torch.uint8, device=dev)
+    n = ids.numel() if subset is None else subset.numel()
+    with torch.cuda.device(dev):
+        _check(lib().ghf_mark_rows(_ptr(ids), _ptr(subset), n, num_rows, _ptr(mask), _stream(dev)), "ghf_mark_rows")
+    return mask[:num_rows]
+
+
+class PeerPush:
+    """Arguments of the epilogue's stores into the peers' tables (`Graph.mp_layer(push=...)`): `mask` uint8
+    [world, local rows] (which peer reads which of my rows), `tables` int64 [world] device array of table base
+    pointers, this rank's index."""
+
+    def __init__(self, mask: torch.Tensor, tables: torch.Tensor, rank: int):
+        if mask.dtype != torch.uint8 or mask.dim() != 2 or not mask.is_contiguous():
+            raise RuntimeError("PeerPush: mask must be a contiguous uint8 [world, local rows] tensor")
+        if tables.dtype != torch.int64 or tables.numel() != mask.shape[0]:
+            raise RuntimeError("PeerPush: tables must hold one int64 pointer per rank")
+        self.mask, self.tables, self.rank, self.world = mask, tables, int(rank), int(mask.shape[0])
 
 
 def copy_async(dst: torch.Tensor, src: torch.Tensor) -> None:
@@ -460,7 +489,7 @@ class Graph:
         return min(phase_lo * self.sb_nodes, self.num_local), min(phase_hi * self.sb_nodes, self.num_local)
 
     def mp_layer(self, h, W_msg, W_self, bias, ln_w, ln_b, eps: float, precision: int, out=None,
-                 want_upd: bool = False, h16=None, out16=None, h_row0=None, phases=None):
+                 want_upd: bool = False, h16=None, out16=None, h_row0=None, phases=None, push=None):
         """One message-passing layer on this graph's destination range -> (out, upd or None).
 
         `h16` (Shadow of [N, d], optional) is the fp16 shadow of `h` the PREC_F16 contraction gathers from (made
@@ -468,7 +497,8 @@ class Graph:
         `h_row0` (PREC_F16 with `h16` only): `h` holds just the rows [h_row0, h_row0 + len(h)) of the fp32 features
         - enough, because with a shadow the fp32 rows are read only at this graph's own destinations (residual).
         `phases` = (lo, hi): only the super-blocks [lo, hi) of the graph; `out`, `out16`, `upd` still cover all local
-        rows, of which `phase_rows(lo, hi)` are written."""
+        rows, of which `phase_rows(lo, hi)` are written.  `push` (PeerPush, with `out16`): the epilogue kernel also
+        stores each fp16 row into the tables of the peers that read it."""
         dev = self.device
         h, W_msg, W_self, bias = _f32(h), _f32(W_msg), _f32(W_self), _f32(bias)
         ln_w, ln_b = _f32(ln_w), _f32(ln_b)
@@ -495,6 +525,18 @@ class Graph:
                 raise RuntimeError(f"{name} must be a Shadow of a [{rows},{d}] matrix")
         ws = self.workspace(precision)
         p_lo, p_hi = (0, self.num_phases) if phases is None else phases
+        if push is not None:
+            if out16 is None or push.mask.shape[1] < self.num_local:
+                raise RuntimeError("push needs out16 and a mask row per local node")
+            with torch.cuda.device(dev):
+                _check(lib().ghf_mp_layer_f16_push(self._h, h_ptr, _ptr(h16.data) if h16 else None,
+                                                   _ptr(h16.scale) if h16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
+                                                   _ptr(ln_w), _ptr(ln_b), float(eps), precision, _ptr(out),
+                                                   _ptr(out16.data), _ptr(out16.scale), _ptr(upd), _ptr(ws), int(p_lo),
+                                                   int(p_hi), _ptr(push.mask), int(push.mask.shape[1]),
+                                                   _ptr(push.tables), push.world, push.rank, _stream(dev)),
+                       "ghf_mp_layer_f16_push")
+            return out, upd
         with torch.cuda.device(dev):
             _check(lib().ghf_mp_layer_f16_range(self._h, h_ptr, _ptr(h16.data) if h16 else None,
                                                 _ptr(h16.scale) if h16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),

@@ -118,6 +118,9 @@ class _SymmetricRows:
                                for r in range(self.world)])
         self.comm = torch.cuda.Stream(device=device)
         self.bytes_pushed = 0
+        # base pointers of every rank's tables, on the device (the epilogue kernel stores through them)
+        self.table_ptrs = [torch.tensor([t.data_ptr() for t in self.peers[b]], dtype=torch.int64, device=device)
+                           for b in range(2)]
 
     def push(self, b: int, lo: int, hi: int) -> None:
         """Rows [lo, hi) of buffer b, already written locally by work enqueued on the CURRENT stream, go to every
@@ -155,10 +158,15 @@ class ShardedForward:
     ranges: optional [(lo, hi)] per rank (e.g. from `plan_partition_by_edges`); default equal node counts.
     transport: "p2p" | "collective" | None (p2p on CUDA when symmetric memory works, else collective).
     chunks: the rank's super-blocks are processed in this many pieces (`ghf_mp_layer_f16_range`) so that the rows of a
-    finished piece travel while the next one is computed (p2p transport, f16 engine)."""
+    finished piece travel while the next one is computed (p2p transport, f16 engine, push="copy"); 0 = one piece per
+    ~8 super-blocks, at most 4.
+    push (p2p transport): "kernel" (default) - the epilogue kernel stores each new fp16 row straight into the tables
+    of the peers that READ it (the sources of their edges; one all-to-all of byte masks per graph), about half the
+    bytes of an all-gather at in-degree 6; "copy" - whole row ranges go to every peer with device-to-device copies
+    on a side stream (copy engines), overlapping the next chunk's compute."""
 
     def __init__(self, model, num_nodes: int, group=None, ranges=None, transport: Optional[str] = None,
-                 chunks: int = 1):
+                 chunks: int = 0, push: str = "kernel"):
         self.model = model
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -171,7 +179,11 @@ class ShardedForward:
             raise ValueError("ranges must tile [0, num_nodes) in rank order")
         self.lo, self.hi = self.ranges[self.rank]
         self.transport = transport
-        self.chunks = max(1, int(chunks))
+        self.chunks = max(0, int(chunks))
+        if push not in ("kernel", "copy"):
+            raise ValueError("push must be 'kernel' or 'copy'")
+        self.push = push
+        self.rows_needed_by_peers = None
         self.num_kept = 0
         self.profile = False          # True: CUDA events on the main stream between the stages (read with `stage_ms`)
         self._marks: List[Tuple[str, torch.cuda.Event]] = []
@@ -220,7 +232,7 @@ class ShardedForward:
     def _phase_chunks(self, graph) -> List[Tuple[int, int]]:
         """The graph's super-blocks in `chunks` contiguous pieces (a piece is one launch of the layer kernels)."""
         n = graph.num_phases
-        c = max(1, min(self.chunks, n))
+        c = max(1, min(self.chunks, n)) if self.chunks else max(1, min(4, n // 8))
         cuts = [round(i * n / c) for i in range(c + 1)]
         return [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
 
@@ -300,7 +312,21 @@ class ShardedForward:
         graph = _native.Graph(edge_index, packed.rel_ids, self.num_nodes, max(packed.num_unique, 1), m.hidden_dim,
                               dst_lo=self.lo, dst_hi=self.hi, sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
                               unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset)
+        if started is not None and self._sym is not None and self.push == "kernel" and self.world > 1:
+            started["peer_mask"] = self._peer_mask(edge_index, packed.subset)
         return self._layers(node_features, graph, packed, started, gather_output)
+
+    def _peer_mask(self, edge_index, subset) -> torch.Tensor:
+        """uint8 [world, local rows]: entry [q, r] says rank q gathers this rank's row r (it is the source of one of
+        q's edges).  Every rank marks the sources of its own edges and one all-to-all hands each range to its owner."""
+        from . import _native
+        need = _native.mark_rows(edge_index[0], self.num_nodes, subset)
+        sizes = [hi - lo for lo, hi in self.ranges]
+        n_local = self.hi - self.lo
+        got = torch.empty(self.world * n_local, dtype=torch.uint8, device=need.device)
+        dist.all_to_all_single(got, need, output_split_sizes=[n_local] * self.world, input_split_sizes=sizes,
+                               group=self.group)
+        return got.view(self.world, n_local)
 
     def _layers(self, node_features, graph, packed, started, gather_output):
         self.num_kept = graph.num_kept
@@ -423,10 +449,15 @@ class ShardedForward:
                 h_nxt = torch.empty_like(h_cur)
                 h16 = _native.Shadow(tables[cb][:N], scales[cb])
                 out16 = None if last or hi <= lo else _native.Shadow(tables[nb][lo:hi], scales[nb])
-                for p_lo, p_hi in chunks:
+                mask = st.get("peer_mask")
+                push = None
+                if not last and sym is not None and mask is not None and hi > lo:
+                    push = _native.PeerPush(mask, sym.table_ptrs[nb], self.rank)
+                    self.rows_needed_by_peers = mask
+                for p_lo, p_hi in ([(0, graph.num_phases)] if push is not None else chunks):
                     graph.mp_layer(h_cur, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps, _native.PREC_F16,
-                                   out=h_nxt, h16=h16, out16=out16, h_row0=lo, phases=(p_lo, p_hi))
-                    if not last and sym is not None:      # these rows travel while the next piece is computed
+                                   out=h_nxt, h16=h16, out16=out16, h_row0=lo, phases=(p_lo, p_hi), push=push)
+                    if not last and sym is not None and push is None:   # these rows travel while the next piece runs
                         r0, r1 = graph.phase_rows(p_lo, p_hi)
                         sym.push(nb, lo + r0, lo + r1)
                 if not last and sym is None:

@@ -145,6 +145,23 @@ int ghf_mp_layer_f16_range(const ghf_graph* g, const float* d_h, const void* d_h
                            float* d_out16_scale, float* d_upd, void* d_workspace, int32_t phase_lo, int32_t phase_hi,
                            void* stream);
 
+/* Multi-GPU, fused with the exchange: the same ranged layer whose epilogue kernel ALSO stores each fp16 result row
+ * straight into the peers' copies of the shadow table (peer-mapped symmetric memory, NVLink stores from the kernel),
+ * but only for the peers that read the row.  d_peer_mask[q * mask_stride + r] != 0 <=> rank q has an edge whose
+ * source is this rank's local row r (ghf_mark_rows on rank q + one all-to-all of the byte masks per graph);
+ * d_peer_tables: device array of `world` pointers, entry q = base of rank q's [num_nodes, d] fp16 table; d_out16 is
+ * this rank's own rows of its own table (as in ghf_mp_layer_f16).  hidden_dim 64 / 128. */
+int ghf_mp_layer_f16_push(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                          const float* d_W_msg, const float* d_W_self, const float* d_bias, const float* d_ln_w,
+                          const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
+                          float* d_out16_scale, float* d_upd, void* d_workspace, int32_t phase_lo, int32_t phase_hi,
+                          const uint8_t* d_peer_mask, int64_t mask_stride, void* const* d_peer_tables, int32_t world,
+                          int32_t rank, void* stream);
+/* d_mask[v] = 1 for every v = d_ids[j] (j over all n entries, or over d_subset[0..n) when given), 0 elsewhere:
+ * the rows of the node table a rank gathers from (sources of its edges). */
+int ghf_mark_rows(const int64_t* d_ids, const uint32_t* d_subset, int64_t n, int64_t num_rows, uint8_t* d_mask,
+                  void* stream);
+
 /* Building a shadow by hand (layer 0 of a multi-GPU run, where max|h| must be agreed between ranks first):
  * ghf_absmax writes d_scale[1] = max |x|; ghf_convert_f16 picks the scale from d_scale[1] (computing it first when
  * have_amax == 0), writes d_scale[0] and d_y16 = fp16(x * 2^k).  elems % 8 == 0, 16-byte aligned pointers. */
