@@ -313,7 +313,7 @@ def main():
     ap.add_argument("--train", action="store_true",
                     help="also time a training step (forward + backward on a prepared graph) -> key 'train_step'")
     ap.add_argument("--chunks", type=int, default=0, help="multi-GPU, --push copy: pieces of a rank's rows whose exchange overlaps the next piece (0 = auto)")
-    ap.add_argument("--push", default="kernel", choices=["kernel", "copy"],
+    ap.add_argument("--push", default="auto", choices=["auto", "kernel", "copy"],
                     help="multi-GPU p2p: epilogue kernel stores rows to the peers that read them | whole ranges by copy engines")
     ap.add_argument("--transport", default=None, choices=["p2p", "collective"], help="multi-GPU row exchange")
     ap.add_argument("--balance", default="nodes", choices=["nodes", "edges"], help="multi-GPU: destination ranges by node count or by edges")
@@ -578,7 +578,7 @@ def main():
         except Exception:
             pass
         sel = sharded.rows_needed_by_peers
-        multi = {"transport": sharded.transport, "push": args.push if sharded.transport == "p2p" else None,
+        multi = {"transport": sharded.transport, "push": sharded.push_used if sharded.transport == "p2p" else None,
                  "rows_sent_fraction": (float((sel.float().sum() - sel[rank].float().sum()) /
                                               max(1, sel.numel() - sel.shape[1])) if sel is not None else None),
                  "chunks": per_layer, "balance": args.balance,

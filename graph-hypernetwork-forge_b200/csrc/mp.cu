@@ -169,18 +169,6 @@ mp_epilogue_kernel(const float* __restrict__ acc, const int32_t* __restrict__ in
 // The same epilogue for hidden_dim 32 / 64 / 128: a lane owns D/32 CONSECUTIVE columns (one vector access per row
 // and operand), four rows in flight per warp, and an optional fp16 copy of the output row for the next layer's
 // gathers (GHF_PREC_F16).
-// Multi-GPU: the fp16 rows the epilogue produces are also stored straight into the peers' copies of the shadow table
-// (peer-mapped symmetric memory, NVLink stores) - but only into the copies of the ranks that READ the row: rank q
-// gathers row v only if one of its edges has source v (`mask[q * mask_stride + local row]`, exchanged once per
-// graph).  No staging copy, no collective kernel, ~half the bytes of an all-gather at in-degree 6.
-struct PeerPush {
-  const uint8_t* mask = nullptr;      // [world][mask_stride] bytes; nullptr: no push
-  int64_t mask_stride = 0;
-  __half* const* tables = nullptr;    // device array [world]: base of every rank's [N, D] fp16 table
-  int world = 0, me = 0;
-  int64_t table_row0 = 0;             // global row of local row 0
-};
-
 template <int D>
 __global__ void __launch_bounds__(256)
 mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict__ indeg,
@@ -420,7 +408,7 @@ struct FusedEpilogue {
   float *out, *upd;
   void* out16;
   float* out16_scale;
-  bool no_fusion = false;    // the caller needs the separate epilogue kernel (peer push)
+  const PeerPush* push = nullptr;   // multi-GPU: rows also go to the peers' tables (either kernel can do it)
 };
 
 // The contraction of one layer: acc[v] = sum over in-edges of [h_u | h_v] @ [W_msg[r] ; W_self[r]] + bias[r].
@@ -453,8 +441,13 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
   // (the f16 kernel clears the accumulator itself and keeps per-phase sync words next to the counter)
   const bool f16_ss = precision == GHF_PREC_F16 && mp_f16ss_supported(d);   // hidden 256: streamed weights
-  const bool fused = fe != nullptr && !ranged && !fe->no_fusion && precision == GHF_PREC_F16 && !f16_ss && mp_f16_supported(d) &&
-                     mp_f16_fused_enabled(g) && fe->ln_w != nullptr && fe->ln_b != nullptr &&
+  // With a peer push the fused kernel is the default: its row epilogue runs per super-block WHILE later super-blocks
+  // are still being contracted, so the NVLink stores overlap the contraction (GHF_PUSH_FUSED=0: separate epilogue).
+  const char* pf_env = getenv("GHF_PUSH_FUSED");
+  const bool push_fused = fe != nullptr && fe->push != nullptr && fe->push->mask != nullptr && g->num_units > 0 &&
+                          !(pf_env && pf_env[0] == '0');
+  const bool fused = fe != nullptr && !ranged && precision == GHF_PREC_F16 && !f16_ss && mp_f16_supported(d) &&
+                     (mp_f16_fused_enabled(g) || push_fused) && fe->ln_w != nullptr && fe->ln_b != nullptr &&
                      (reinterpret_cast<uintptr_t>(fe->ln_w) | reinterpret_cast<uintptr_t>(fe->ln_b) |
                       reinterpret_cast<uintptr_t>(fe->h) | reinterpret_cast<uintptr_t>(fe->out) |
                       reinterpret_cast<uintptr_t>(fe->upd) | reinterpret_cast<uintptr_t>(fe->out16)) % 16 == 0;
@@ -516,7 +509,7 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
     } else if (fused && !(getenv("GHF_DETERMINISTIC") && getenv("GHF_DETERMINISTIC")[0] == '1')) {
       // contraction + row epilogue in one kernel; the accumulator region is its ring
       rc = mp_f16_fused_launch(g, h16, h16_scale, d_bias, pack, acc_ws, counter, fe->h, fe->ln_w, fe->ln_b, fe->eps,
-                               fe->out, fe->upd, fe->out16, fe->out16_scale, stream);
+                               fe->out, fe->upd, fe->out16, fe->out16_scale, stream, fe->push);
       if (fused_done) *fused_done = true;
     } else if (precision == GHF_PREC_F16) {
       // GHF_DETERMINISTIC=1 (layer entries only): fixed-point per-destination sums, bit-identical from run to run
@@ -570,7 +563,8 @@ static int mp_layer_impl(const ghf_graph* g, const float* d_h, const void* d_h16
     for (auto& e : rec.e) GHF_CUDA(cudaEventCreate(&e));
   float* acc = nullptr;
   const int32_t* det_words = nullptr;
-  const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, push.mask != nullptr};
+  push.table_row0 = g->dst_lo;
+  const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, push.mask ? &push : nullptr};
   bool fused_done = false;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
                                false, false, d_workspace, stream, &acc, prof ? &rec : nullptr, nullptr, &fe,

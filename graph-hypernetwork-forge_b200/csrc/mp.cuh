@@ -1,12 +1,25 @@
 // mp.cuh — interface between ghf_mp_layer (mp.cu) and the tcgen05 contraction engine (mp_umma.cu).
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "graph.cuh"
 
 namespace ghf {
+
+// Multi-GPU: the fp16 rows the epilogue produces are also stored straight into the peers' copies of the shadow table
+// (peer-mapped symmetric memory, NVLink stores) - but only into the copies of the ranks that READ the row: rank q
+// gathers row v only if one of its edges has source v (`mask[q * mask_stride + local row]`, exchanged once per
+// graph).  No staging copy, no collective kernel, ~half the bytes of an all-gather at in-degree 6.
+struct PeerPush {
+  const uint8_t* mask = nullptr;      // [world][mask_stride] bytes; nullptr: no push
+  int64_t mask_stride = 0;
+  __half* const* tables = nullptr;    // device array [world]: base of every rank's [N, D] fp16 table
+  int world = 0, me = 0;
+  int64_t table_row0 = 0;             // global row of local row 0
+};
 
 bool mp_umma_supported(int hidden_dim);
 // bytes of scratch for the per-relation operand images [R][2d x d] (tf32, UMMA K-major SW128 layout)
@@ -64,7 +77,7 @@ int64_t mp_f16_fused_ring_rows(const ghf_graph* g);
 int mp_f16_fused_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias,
                         const void* pack_scratch, float* ring, int* sync_words, const float* h, const float* ln_w,
                         const float* ln_b, float eps, float* out, float* upd, void* out16, float* out16_scale,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const PeerPush* push = nullptr);
 
 // hidden_dim 256 / 64 with streamed fp16 weights (mp_f16_ss.cu): operand images [R][256 KiB / 16 KiB] + inverse
 // scales [R]; acc must be zero at entry, `unit_counter` one zeroed int

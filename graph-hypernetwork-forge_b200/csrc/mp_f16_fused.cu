@@ -115,6 +115,7 @@ struct FusedParams {
   float* out16_scale;
   uint32_t flags;
   long long* trace;     // GHF_FUSED_TRACE: cycle accounting of CTA 0 (kTrace instantiation)
+  PeerPush push;        // multi-GPU: result rows also go to the tables of the peers that read them (mp.cuh)
 };
 
 // Rows [r0, r1) of phase a that this CTA finishes: out = LN(relu(acc / max(indeg, 1) + h)), slot rows back to zero.
@@ -201,8 +202,12 @@ __device__ __forceinline__ void row_epilogue(const FusedParams& p, int a, int wa
       __stcs(reinterpret_cast<float4*>(p.out + r * kD) + lane, y);
       if (p.out16) {
         const __half2 p0 = __floats2half2_rn(y.x * s16, y.y * s16), p1 = __floats2half2_rn(y.z * s16, y.w * s16);
-        *reinterpret_cast<uint2*>(p.out16 + r * kD + lane * 4) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+        const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+        *reinterpret_cast<uint2*>(p.out16 + r * kD + lane * 4) = packed;
+        if (p.push.mask)                                 // NVLink stores, while later super-blocks are contracted
+          for (int q = 0; q < p.push.world; ++q)
+            if (q != p.push.me && p.push.mask[q * p.push.mask_stride + r])
+              *reinterpret_cast<uint2*>(p.push.tables[q] + (p.push.table_row0 + r) * kD + lane * 4) = packed;
       }
     }
   }
@@ -622,7 +627,7 @@ bool mp_f16_fused_enabled(const ghf_graph* g) {
 int mp_f16_fused_launch(const ghf_graph* g, const void* h16, const float* h16_scale, const float* bias,
                         const void* pack_scratch, float* ring, int* sync_words, const float* h, const float* ln_w,
                         const float* ln_b, float eps, float* out, float* upd, void* out16, float* out16_scale,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const PeerPush* push) {
   GHF_REQUIRE(h16_scale != nullptr, "mp_f16_fused: the fp16 shadow needs its scale words");
   GHF_REQUIRE(g->hidden_dim == kD && g->num_units > 0, "mp_f16_fused: hidden_dim must be %d and the graph non-empty", kD);
   GHF_REQUIRE(g->unit_edges % kTile == 0, "mp_f16_fused: unit_edges=%d must be a multiple of %d", g->unit_edges, kTile);
@@ -652,6 +657,10 @@ int mp_f16_fused_launch(const ghf_graph* g, const void* h16, const float* h16_sc
   p.num_local = g->num_local; p.num_phases = (int)g->num_phases; p.sync = sync_words; p.indeg = g->indeg; p.h = h;
   p.ln_w = ln_w; p.ln_b = ln_b; p.eps = eps; p.out = out; p.upd = upd; p.out16 = reinterpret_cast<__half*>(out16);
   p.out16_scale = out16_scale;
+  if (push) {
+    GHF_REQUIRE(out16 != nullptr, "mp_f16_fused: the peer push needs the fp16 output");
+    p.push = *push;
+  }
   const char* fenv = getenv("GHF_FUSED_FLAGS");
   p.flags = fenv ? (uint32_t)atoi(fenv) : kDefaultFlags;
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();

@@ -160,13 +160,18 @@ class ShardedForward:
     chunks: the rank's super-blocks are processed in this many pieces (`ghf_mp_layer_f16_range`) so that the rows of a
     finished piece travel while the next one is computed (p2p transport, f16 engine, push="copy"); 0 = one piece per
     ~8 super-blocks, at most 4.
-    push (p2p transport): "kernel" (default) - the epilogue kernel stores each new fp16 row straight into the tables
-    of the peers that READ it (the sources of their edges; one all-to-all of byte masks per graph), about half the
-    bytes of an all-gather at in-degree 6; "copy" - whole row ranges go to every peer with device-to-device copies
-    on a side stream (copy engines), overlapping the next chunk's compute."""
+    push (p2p transport): "kernel" - the layer kernel's row epilogue stores each new fp16 row straight into the tables
+    of the peers that READ it (the sources of their edges; one all-to-all of byte masks per graph): about half the
+    bytes of an all-gather at in-degree 6, and the NVLink stores of one super-block overlap the contraction of the
+    next ones; "copy" - whole row ranges go to every peer with device-to-device copies on a side stream (copy
+    engines), overlapping the next chunk's compute; "auto" (default) picks per graph from a two-line cost model
+    (`_pick_push`)."""
+
+    # cost model of `_pick_push`: seconds per edge and layer of the contraction at hidden 128, NVLink bytes per second
+    _T_EDGE_128, _NVLINK_BPS = 1.9e-10, 7.0e11
 
     def __init__(self, model, num_nodes: int, group=None, ranges=None, transport: Optional[str] = None,
-                 chunks: int = 0, push: str = "kernel"):
+                 chunks: int = 0, push: str = "auto"):
         self.model = model
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -180,9 +185,10 @@ class ShardedForward:
         self.lo, self.hi = self.ranges[self.rank]
         self.transport = transport
         self.chunks = max(0, int(chunks))
-        if push not in ("kernel", "copy"):
-            raise ValueError("push must be 'kernel' or 'copy'")
+        if push not in ("kernel", "copy", "auto"):
+            raise ValueError("push must be 'kernel', 'copy' or 'auto'")
         self.push = push
+        self.push_used = None
         self.rows_needed_by_peers = None
         self.num_kept = 0
         self.profile = False          # True: CUDA events on the main stream between the stages (read with `stage_ms`)
@@ -312,9 +318,24 @@ class ShardedForward:
         graph = _native.Graph(edge_index, packed.rel_ids, self.num_nodes, max(packed.num_unique, 1), m.hidden_dim,
                               dst_lo=self.lo, dst_hi=self.hi, sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
                               unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset)
-        if started is not None and self._sym is not None and self.push == "kernel" and self.world > 1:
-            started["peer_mask"] = self._peer_mask(edge_index, packed.subset)
+        if started is not None and self._sym is not None and self.world > 1:
+            self.push_used = self._pick_push(graph) if self.push == "auto" else self.push
+            if self.push_used == "kernel":
+                started["peer_mask"] = self._peer_mask(edge_index, packed.subset)
         return self._layers(node_features, graph, packed, started, gather_output)
+
+    def _pick_push(self, graph) -> str:
+        """Per layer: "kernel" costs compute + f X, "copy" costs max(compute, X) + min(compute, X) / chunks, with
+        X = time to receive everybody's rows, f = share of rows a peer really reads ~ 1 - exp(-edges per rank / N)
+        (uniform sources), compute ~ edges per rank x t_edge.  c3 on 8 GPUs: 0.38 + 0.55 x 0.80 < 0.80 + 0.38 -> kernel;
+        c5 on 8 GPUs: 5.9 + 0.71 x 8.0 > 8.0 + 5.9 / 4 -> copy."""
+        import math
+        d, n = self.model.hidden_dim, max(self.num_nodes, 1)
+        compute = graph.num_kept * self._T_EDGE_128 * d / 128.0
+        x = (self.world - 1) / self.world * n * d * 2 / self._NVLINK_BPS
+        f = 1.0 - math.exp(-graph.num_kept / n)
+        chunks = len(self._phase_chunks(graph))
+        return "kernel" if compute + f * x < max(compute, x) + min(compute, x) / chunks else "copy"
 
     def _peer_mask(self, edge_index, subset) -> torch.Tensor:
         """uint8 [world, local rows]: entry [q, r] says rank q gathers this rank's row r (it is the source of one of

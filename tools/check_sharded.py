@@ -32,7 +32,8 @@ for prec, tol in (("f16", 1.5e-4), ("tf32", 1.5e-4), ("fp32", 1e-4)):
     errs = []
     variants = [dict(), dict(transport="collective")]
     if prec == "f16":
-        variants += [dict(push="copy", chunks=3), dict(push="copy", balance=True, chunks=2), dict(balance=True),
+        variants += [dict(push="kernel"), dict(push="copy", chunks=3), dict(push="copy", balance=True, chunks=2),
+                     dict(push="kernel", balance=True),
                      dict(transport="collective", balance=True)]
     for kw in variants:
         kw = dict(kw)
