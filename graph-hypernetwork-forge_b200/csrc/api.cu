@@ -20,16 +20,16 @@ char* err_buf() {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+  static int cached[64] = {0};
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached[dev] = n;
     else
       return 148;
   }
-  return cached;
+  return cached[dev];
 }
 
 }  // namespace ghf
@@ -254,9 +254,15 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
   int64_t U = 0;
   if (int rc = ghf_dedup_texts(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream)) return rc;
   trace.mark("dedup");
-  const int prec = (desc->precision == GHF_PREC_F16 && (d == 64 || d == 128 || d == 256)) ? GHF_PREC_F16
-                   : (desc->precision != GHF_PREC_FP32 && (d == 32 || d == 64 || d == 128)) ? GHF_PREC_TF32
-                                                                                           : GHF_PREC_FP32;
+  // the same rule as the staged entries (ghf_mp_layer_f16): an engine that does not cover this hidden size is an
+  // error, not a silent change of arithmetic
+  GHF_REQUIRE(desc->precision != GHF_PREC_F16 || d == 64 || d == 128 || d == 256,
+              "ghf_hypergnn_forward: the f16 engine covers hidden_dim 64, 128 and 256, got %d", d);
+  GHF_REQUIRE(desc->precision != GHF_PREC_TF32 || d == 32 || d == 64 || d == 128,
+              "ghf_hypergnn_forward: the tf32 engine covers hidden_dim 32, 64 and 128, got %d", d);
+  GHF_REQUIRE(desc->precision == GHF_PREC_FP32 || desc->precision == GHF_PREC_TF32 || desc->precision == GHF_PREC_F16,
+              "ghf_hypergnn_forward: precision=%d", desc->precision);
+  const int prec = desc->precision;
   // second arena: everything whose size depends on the number of distinct relations
   const size_t Un = (size_t)(U > 0 ? U : 1), Hn = (size_t)(H > 0 ? H : 1);
   // Hidden 64 / 256 on the f16 engine: the generator's last Linear writes the fp16 operand images of the contraction

@@ -46,7 +46,17 @@ inline int fail(const char* fmt, ...) {
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t align_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 
-int sm_count();  // SMs of the current device (cached; api.cu)
+int sm_count();  // SMs of the current device (cached per device; api.cu)
+
+// cudaFuncSetAttribute is per DEVICE: kernels that opt in to large shared memory configure themselves on first use
+// on each device of the process.  -> true the first time it is called with these flags on the current device.
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;   // unknown device: configure again
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
 
 // ---- fp16 shadow of h (GHF_PREC_F16) ------------------------------------------------------------------------
 // A shadow is (h16, scale) with scale = float[2] in device memory: h = h16 * scale[0] (scale[0] is an exact power of

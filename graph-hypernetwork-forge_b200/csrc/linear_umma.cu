@@ -329,10 +329,9 @@ static int64_t pick_gx(int64_t tiles, int nblocks) {
 
 int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b, int N, int relu,
                        const float* log_scale, float* Y, void* Y16, float* y16_scale, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
   }
   const int64_t tiles = (M + kTile - 1) / kTile;
   const int nblocks = N / kD;
@@ -348,10 +347,9 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
 int linear_umma_to_images(const float* X, int64_t M, const float* W, const float* b, int d, int which,
                           const float* log_scale, const float* row_scale, void* images, int64_t image_bytes,
                           cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
   }
   const int N = d * d;
   GHF_REQUIRE(N % kD == 0 && d % 4 == 0 && N / kD <= 65535, "linear_umma_to_images: hidden_dim %d", d);

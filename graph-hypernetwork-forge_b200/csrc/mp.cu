@@ -441,11 +441,12 @@ static int run_contraction(const ghf_graph* g, const float* d_h, const void* d_h
   // workspace: [work counter, 256 B][accumulator rows][operand images (tensor-core paths)][fp16 h (f16 path)]
   // (the f16 kernel clears the accumulator itself and keeps per-phase sync words next to the counter)
   const bool f16_ss = precision == GHF_PREC_F16 && mp_f16ss_supported(d);   // hidden 256: streamed weights
-  // With a peer push the fused kernel is the default: its row epilogue runs per super-block WHILE later super-blocks
-  // are still being contracted, so the NVLink stores overlap the contraction (GHF_PUSH_FUSED=0: separate epilogue).
+  // GHF_PUSH_FUSED=1: with a peer push, use the fused kernel - its row epilogue runs per super-block WHILE later
+  // super-blocks are still being contracted, so the NVLink stores overlap the contraction.  Measured equal to the
+  // separate epilogue kernel at c3 on 8 GPUs (3.82 ms both, profiles/r02_multi_gpu_8.txt), so it stays opt-in.
   const char* pf_env = getenv("GHF_PUSH_FUSED");
   const bool push_fused = fe != nullptr && fe->push != nullptr && fe->push->mask != nullptr && g->num_units > 0 &&
-                          !(pf_env && pf_env[0] == '0');
+                          pf_env && pf_env[0] == '1';
   const bool fused = fe != nullptr && !ranged && precision == GHF_PREC_F16 && !f16_ss && mp_f16_supported(d) &&
                      (mp_f16_fused_enabled(g) || push_fused) && fe->ln_w != nullptr && fe->ln_b != nullptr &&
                      (reinterpret_cast<uintptr_t>(fe->ln_w) | reinterpret_cast<uintptr_t>(fe->ln_b) |

@@ -734,13 +734,12 @@ int mp_f16_launch(const ghf_graph* g, const void* h16, const float* h16_scale, c
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(h16) | reinterpret_cast<uintptr_t>(acc) |
                reinterpret_cast<uintptr_t>(pack_scratch)) % 16 == 0,
               "mp_f16: h16 / acc / scratch must be 16-byte aligned");
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     GHF_CUDA(cudaFuncSetAttribute(mp_f16_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
   }
   const char* penv = getenv("GHF_F16_PROD");
   const int prod = penv ? atoi(penv) : 4;

@@ -638,13 +638,10 @@ int mp_f16_fused_launch(const ghf_graph* g, const void* h16, const float* h16_sc
               "mp_f16_fused: buffers must be 16-byte aligned");
   GHF_REQUIRE(g->num_phases < (1 << 23), "mp_f16_fused: too many super-blocks");
   static bool configured[64] = {false};
-  int dev = 0;
-  GHF_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
+  if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(mp_f16_fused_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     GHF_CUDA(cudaFuncSetAttribute(mp_f16_fused_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     GHF_CUDA(cudaFuncSetAttribute(mp_f16_fused_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured[dev] = true;
   }
   FusedParams p{};
   p.unit_start = g->unit_start; p.unit_count = g->unit_count; p.unit_rel = g->unit_rel; p.unit_phase = g->unit_phase;

@@ -388,10 +388,9 @@ int64_t mp_f16ss_pack_bytes(int num_rel, int d) {
 template <int D>
 static int pack_impl(const ghf_graph* g, const float* W_msg, const float* W_self, uint8_t* img, float* inv,
                      cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(pack_f16_ss_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackSmem));
-    configured = true;
   }
   const int grid = g->num_rel < sm_count() ? g->num_rel : sm_count();
   pack_f16_ss_kernel<D><<<(unsigned)grid, kPackThreads, kPackSmem, stream>>>(W_msg, W_self, img, inv, g->num_rel);
@@ -414,10 +413,9 @@ int mp_f16ss_pack(const ghf_graph* g, const float* W_msg, const float* W_self, v
 template <int D>
 static int launch_impl(const ghf_graph* g, const __half* h16, const float* h16_scale, const float* bias, float* acc,
                        const uint8_t* img, const float* inv, int* unit_counter, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(mp_f16_ss_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::kSmem));
-    configured = true;
   }
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
   mp_f16_ss_kernel<D><<<(unsigned)grid, kThreads, Cfg<D>::kSmem, stream>>>(

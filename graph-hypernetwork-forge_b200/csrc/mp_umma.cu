@@ -301,10 +301,9 @@ template <int D>
 int launch(const ghf_graph* g, const float* h, const uint8_t* wpack, const float* bias, float* acc,
            int* unit_counter, cudaStream_t stream) {
   using C = Cfg<D>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(mp_umma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    configured = true;
   }
   const int64_t grid = g->num_units < sm_count() ? g->num_units : sm_count();
   mp_umma_kernel<D><<<(unsigned)grid, C::kThreads, C::kSmem, stream>>>(

@@ -325,10 +325,9 @@ int mp_wgrad_f16_launch(const ghf_graph* g, const void* h16, const float* h_scal
   GHF_REQUIRE((reinterpret_cast<uintptr_t>(h16) | reinterpret_cast<uintptr_t>(g16) |
                reinterpret_cast<uintptr_t>(gW_msg) | reinterpret_cast<uintptr_t>(gW_self)) % 16 == 0,
               "mp_wgrad_f16: buffers must be 16-byte aligned");
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(mp_wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
   }
   GHF_CUDA(cudaMemsetAsync(unit_counter, 0, sizeof(int), stream));
   const char* fenv = getenv("GHF_WGRAD_FLAGS");

@@ -138,7 +138,10 @@ class HyperGNN(nn.Module):
     of the node features and runs the per-edge contraction on tcgen05 kind::f16 with fp32 accumulation
     (hidden_dim 128, and 64 / 256 with streamed weights; same 11-bit operand significand as TF32), ``"tf32"`` runs it on tcgen05 kind::tf32
     (hidden_dim 32/64/128), ``"fp32"`` on CUDA cores; ``None``/"auto" picks f16, then tf32, then fp32 as
-    the shape allows (env ``GHF_PRECISION`` overrides).
+    the shape allows (env ``GHF_PRECISION`` fills in when no precision is given).  NOTE: the default is therefore
+    NOT the reference's fp32 arithmetic at hidden 32/64/128/256 - tensor-core engines round the operands of the
+    per-edge contraction to an 11-bit significand (measured error and tolerances: tests/_util.py); pass
+    ``precision="fp32"`` for fp32 end to end.
     """
 
     def __init__(self, text_dim: int, node_feat_dim: int, hidden_dim: int, num_layers: int = 2,
@@ -160,7 +163,8 @@ class HyperGNN(nn.Module):
 
     # ------------------------------------------------------------------
     def _precision_code(self) -> int:
-        name = os.environ.get("GHF_PRECISION") or self.precision or "auto"
+        # an explicit constructor argument wins; the environment variable only fills in for precision=None/"auto"
+        name = self.precision if self.precision not in (None, "auto") else (os.environ.get("GHF_PRECISION") or "auto")
         if name == "auto":
             name = "f16" if self.hidden_dim in (64, 128, 256) else "tf32" if self.hidden_dim == 32 else "fp32"
         return _native.precision_code(name)
