@@ -301,8 +301,8 @@ def cpu_baseline_subprocess(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)    # 20 x ~12 ms at c3: single slow steps (allocator, clocks) average out
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "tf32", "fp32"])
@@ -650,6 +650,28 @@ def main():
                  "peak_memory_gib": torch.cuda.max_memory_allocated(device) / 2**30,
                  "what": "prepared graph reused; loss = (out * W).sum(); gradients of every parameter"}
 
+    # ---- the graph reused ("edges are sorted once", north_star item 3): dedup + graph build done once, every timed
+    # step = input projection + text encoder + generators + L layers on the prepared graph.  A second figure, NOT the
+    # headline: `value` above rebuilds everything every step.
+    prepared_fig = None
+    if world == 1 and not pre_sharded and not args.no_alt:
+        prep = model.prepare_packed(edge_index, utf8, offsets, N)
+        for _ in range(3):
+            o3 = model.forward_prepared(x, prep)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        p0.record()
+        for _ in range(args.steps):
+            o3 = model.forward_prepared(x, prep)
+        p1.record()
+        torch.cuda.synchronize(device)
+        pms = p0.elapsed_time(p1) / args.steps
+        prepared_fig = {"ms_per_step": pms, "value": E * L / (pms / 1e3), "unit": "edges/s/layer",
+                        "step_frac": gbs(algorithmic_bytes(w, E, N, N)[1] * L, pms) / hbm_peak,
+                        "what": "HyperGNN.forward_prepared on a graph prepared once (relation dedup + graph build "
+                                "outside the timed region); projection, text encoder, generators and layers inside"}
+        del prep, o3
+
     # ---- the same step on the other engines (fp32-tolerance context of an f16 / tf32 headline)
     alt = None
     if world == 1 and not pre_sharded and not args.no_alt and precision != "fp32":
@@ -697,7 +719,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": precision,
                 "data": "synthetic",
                 "config": make_config(w, world, args.skew),
-                "roofline": roofline, "precision_alt": alt, "cpu_baseline": cpu, "e2e": e2e, "multi_gpu": multi,
+                "roofline": roofline, "prepared_graph": prepared_fig, "precision_alt": alt, "cpu_baseline": cpu, "e2e": e2e, "multi_gpu": multi,
                 "gpu_launches": launches,
                 "ms_each_step": [round(v, 3) for v in each],
                 "clocks": clocks.summary()}

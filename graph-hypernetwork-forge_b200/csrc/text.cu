@@ -64,6 +64,35 @@ __device__ __forceinline__ bool same_string(const uint8_t* __restrict__ data,
   return true;
 }
 
+// Strings of at most 16 bytes (relation names usually are) are held in four registers: five aligned word loads cover
+// [s0, s0 + 16) at any alignment, bytes beyond the string are zeroed.  -> false when the fast path does not apply.
+__device__ __forceinline__ bool load_short(const uint8_t* __restrict__ data, int64_t s0, int64_t n, int64_t limit,
+                                           uint32_t (&w)[4]) {
+  const int64_t a = s0 & ~(int64_t)3;
+  if (n > 16 || a + 20 > limit) return false;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(data + a);
+  const uint32_t x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3), x4 = __ldg(p + 4);
+  const int sh = 8 * (int)(s0 & 3);
+  w[0] = __funnelshift_r(x0, x1, sh); w[1] = __funnelshift_r(x1, x2, sh);
+  w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rem = (int)n - 4 * i;
+    w[i] = rem >= 4 ? w[i] : (rem <= 0 ? 0u : (w[i] & ((1u << (8 * rem)) - 1u)));
+  }
+  return true;
+}
+__device__ __forceinline__ uint64_t hash_short(const uint32_t (&w)[4], int64_t n) {   // == hash_string on the same bytes
+  uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)n;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (4 * i < n) h = (h ^ w[i]) * 0x100000001b3ull;
+  h ^= h >> 33; h *= 0xff51afd7ed558ccdull;
+  h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull;
+  h ^= h >> 33;
+  return h;
+}
+
 // Open-addressing table of representative edge ids.  Equal strings meet in one slot; the slot keeps
 // the smallest edge id that ever arrived (atomicMin), i.e. the first occurrence.  A thread that already sees
 // a smaller id in the slot skips the atomic: with few distinct strings almost every edge does.
@@ -79,8 +108,10 @@ __global__ void dedup_insert_kernel(const uint8_t* __restrict__ data, const int6
   if (j >= n) return;
   const int64_t e = subset ? subset[j] : j;
   const int64_t total = off[E], limit = total & ~(int64_t)3;
-  const int64_t s0 = off[e];
-  uint64_t slot = hash_string(data, s0, off[e + 1] - s0, limit, total) & mask;
+  const int64_t s0 = off[e], len = off[e + 1] - s0;
+  uint32_t mine[4];
+  const bool is_short = load_short(data, s0, len, limit, mine);
+  uint64_t slot = (is_short ? hash_short(mine, len) : hash_string(data, s0, len, limit, total)) & mask;
   for (uint32_t probes = 0;; ++probes) {
     if (probes > max_probes) {
       *overflow = 1;
@@ -92,7 +123,15 @@ __global__ void dedup_insert_kernel(const uint8_t* __restrict__ data, const int6
       if (cur == kEmpty) break;  // claimed
     }
     if (cur == (uint32_t)j) break;
-    if (same_string(data, off, e, subset ? subset[cur] : cur, limit, total)) {
+    const int64_t other = subset ? subset[cur] : cur;
+    bool same;
+    uint32_t theirs[4];
+    const int64_t o0 = off[other], olen = off[other + 1] - o0;
+    if (is_short && olen == len && load_short(data, o0, olen, limit, theirs))
+      same = mine[0] == theirs[0] && mine[1] == theirs[1] && mine[2] == theirs[2] && mine[3] == theirs[3];
+    else
+      same = same_string(data, off, e, other, limit, total);
+    if (same) {
       if (cur > (uint32_t)j) atomicMin(&table[slot], (uint32_t)j);   // entries only ever decrease
       break;
     }

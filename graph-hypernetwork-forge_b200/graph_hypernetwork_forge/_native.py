@@ -17,7 +17,7 @@ PREC_FP32 = 0
 PREC_TF32 = 1
 PREC_F16 = 2
 _PREC = {"fp32": PREC_FP32, "tf32": PREC_TF32, "f16": PREC_F16}
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _LIB_PATH = os.environ.get("GHF_LIB") or os.path.join(
     os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")

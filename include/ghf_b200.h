@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GHF_ABI_VERSION 4
+#define GHF_ABI_VERSION 5
 
 /* precision of the relation-typed contraction in ghf_mp_layer */
 #define GHF_PREC_FP32 0 /* CUDA-core FFMA, fp32 end to end (rtol 1e-5 vs reference)          */
