@@ -237,7 +237,15 @@ extern "C" int ghf_weight_generators(const float* d_text_emb, int64_t U, int32_t
       grp.log_scale[p] = nullptr;
       grp.Y[p] = hid[i & 1] + (int64_t)p * U * H;
     }
-    if (int rc = linear_group(grp, n_prob, U, i == 0 ? T : H, H, 1, stream)) return rc;
+    // many relations (zero-shot vocabularies, BASELINE config 4: U = 20k): a hidden Linear is large enough to fill
+    // the machine by itself and goes to the tcgen05 Linear (3xTF32) problem by problem; otherwise one grouped launch
+    const int in_i = i == 0 ? T : H;
+    if (linear_umma_eligible(U, in_i, H, 1, nullptr, grp.X[0], grp.W[0], grp.Y[0])) {
+      for (int p = 0; p < n_prob; ++p)
+        if (int rc = ghf_linear(grp.X[p], U, in_i, grp.W[p], grp.b[p], H, 1, nullptr, grp.Y[p], stream_)) return rc;
+    } else if (int rc = linear_group(grp, n_prob, U, in_i, H, 1, stream)) {
+      return rc;
+    }
   }
   const int in_dim = depth > 0 ? H : T;
   auto last_in = [&](int p) { return depth > 0 ? hid[(depth - 1) & 1] + (int64_t)p * U * H : d_text_emb; };

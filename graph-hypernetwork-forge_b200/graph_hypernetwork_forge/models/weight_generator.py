@@ -65,7 +65,7 @@ class WeightGenerator(nn.Module):
         mods = list(self.generators[kind])
         linears = [i for i, m in enumerate(mods) if isinstance(m, nn.Linear)]
         ls = self.log_scales[kind]
-        grad = autograd.wants_grad(x, ls, *self.generators[kind].parameters())
+        grad = torch.is_grad_enabled() and autograd.wants_grad(x, ls, *self.generators[kind].parameters())
         for pos, i in enumerate(linears):
             last = pos == len(linears) - 1
             if grad:
