@@ -22,6 +22,7 @@
 #include "umma.cuh"
 
 namespace ghf {
+int mp_f16_absmax(const float* x, int64_t elems, float* scale, cudaStream_t stream);   // mp_f16.cu
 namespace {
 
 using namespace ptx;
@@ -299,6 +300,239 @@ linear128_umma_kernel(const float* __restrict__ X, int64_t M, const float* __res
   if (warp == kWarpMma) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ================================================================================================================
+// Image mode on fp16 operands (round 2).  The tf32 image kernel above re-stages the fp32 activations of every row
+// tile for every feature block (64 KiB in per 32 KiB out: ncu showed 18 % tensor pipe, 19 % DRAM - the SM <-> L2
+// interface again).  The result is rounded to fp16 anyway, so the operands can be fp16 too (the same 11-bit
+// significand TF32 keeps, power-of-two scales): the activations are converted ONCE into the swizzled tile layout
+// the tensor core reads (32 KiB per tile, one bulk copy), the weight block sits in 64 TMEM columns, kind::f16.
+// ================================================================================================================
+constexpr int kXTileBytes = 2 * kSub;          // 128 rows x 128 k fp16: two 128-byte swizzle atoms of 64 k
+constexpr int kFStages = 4;
+constexpr int kFSmem = 1024 + kFStages * kXTileBytes + 2 * kStaging + 512;
+constexpr uint32_t kFWCol = 256;               // weight block: TMEM columns [256, 320)
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kD >> 4) << 24);
+
+// X [M,128] fp32 -> fp16 tiles in operand order: tile t, k-half s, row r, 16-byte chunk c at chunk (c ^ (r & 7));
+// rows >= M are zero.  scale[0] = 1 / s with s the power of two chosen from scale[1] = max |X| (mp_f16_absmax).
+__global__ void __launch_bounds__(256)
+x16_tiles_kernel(const float* __restrict__ X, int64_t M, int64_t tiles, __half* __restrict__ out,
+                 float* __restrict__ scale) {
+  const float s = f16_scale_for(scale[1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale[0] = 1.f / s;
+  const int64_t total = tiles * kTile * 16;    // 16-byte chunks
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i >> 4;
+    const int c = (int)(i & 15);               // chunk of 8 k
+    const int64_t t = row / kTile;
+    const int r = (int)(row % kTile);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (row < M) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(X + row * kD + 8 * c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(X + row * kD + 8 * c + 4));
+      const __half2 p0 = __floats2half2_rn(a.x * s, a.y * s), p1 = __floats2half2_rn(a.z * s, a.w * s);
+      const __half2 p2 = __floats2half2_rn(b.x * s, b.y * s), p3 = __floats2half2_rn(b.z * s, b.w * s);
+      o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
+      o.z = *reinterpret_cast<const uint32_t*>(&p2); o.w = *reinterpret_cast<const uint32_t*>(&p3);
+    }
+    const int sub = c >> 3, cc = c & 7;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(out) + t * kXTileBytes + sub * kSub + r * 128 + ((cc ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
+// W [N,128] fp32 -> fp16 in TMEM-load order per 128-feature block: block b | lane quarter q | 16-byte group j (8 k) |
+// lane l | 8 halfs, so that loader warp q reads 512 contiguous bytes per instruction and lane l's 16 loads are its
+// row's 128 k = 64 TMEM columns.  scale as above (scale[1] = max |W| given).
+__global__ void __launch_bounds__(256)
+w16_blocks_kernel(const float* __restrict__ W, int64_t N, __half* __restrict__ out, float* __restrict__ scale) {
+  const float s = f16_scale_for(scale[1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale[0] = 1.f / s;
+  const int64_t total = N * 16;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i >> 4;
+    const int j = (int)(i & 15);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(W + n * kD + 8 * j));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(W + n * kD + 8 * j + 4));
+    const __half2 p0 = __floats2half2_rn(a.x * s, a.y * s), p1 = __floats2half2_rn(a.z * s, a.w * s);
+    const __half2 p2 = __floats2half2_rn(b.x * s, b.y * s), p3 = __floats2half2_rn(b.z * s, b.w * s);
+    uint4 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&p0); o.y = *reinterpret_cast<const uint32_t*>(&p1);
+    o.z = *reinterpret_cast<const uint32_t*>(&p2); o.w = *reinterpret_cast<const uint32_t*>(&p3);
+    const int64_t blk = n / kD;
+    const int nn = (int)(n % kD);
+    const int64_t idx = (((blk * 4 + (nn >> 5)) * 16 + j) * 32 + (nn & 31));   // in 16-byte units
+    reinterpret_cast<uint4*>(out)[idx] = o;
+  }
+}
+
+__device__ __forceinline__ void umma_f16_ts_l(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Yt[128 features, 128 rows] = W16_block[128, 128 k] * X16_tile^T, written as fp16 operand images (ImageOut).
+// Warp roles (320 threads, 1 CTA / SM): 0-7 epilogue (warps 0-3 load the weight block into TMEM first) | 8 bulk-copy
+// producer (one lane) | 9 MMA issuer + TMEM allocator.
+constexpr int kFThreads = 32 * 10;
+__global__ void __launch_bounds__(kFThreads, 1)
+linear128_f16_images_kernel(const __half* __restrict__ X16, int64_t M, const __half* __restrict__ W16,
+                            const float* __restrict__ bias, const float* __restrict__ log_scale,
+                            const float* __restrict__ x_scale, const float* __restrict__ w_scale, ImageOut io) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sA = (raw + 1023u) & ~1023u;
+  const uint32_t sStg = sA + kFStages * kXTileBytes;
+  const uint32_t sBar = sStg + 2 * kStaging;
+  auto full = [&](int s) { return sBar + 8u * s; };
+  auto empty = [&](int s) { return sBar + 8u * (kFStages + s); };
+  auto acc_full = [&](int a) { return sBar + 8u * (2 * kFStages + a); };
+  auto acc_empty = [&](int a) { return sBar + 8u * (2 * kFStages + 2 + a); };
+  const uint32_t tmem_slot = sBar + 8u * (2 * kFStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (M + kTile - 1) / kTile;
+  if (bias) bias += (int64_t)blockIdx.y * kD;
+  // exp(log_scale) and the two operand scales (exact powers of two) in one factor
+  const float alpha = (log_scale ? expf(*log_scale) : 1.f) * x_scale[0] * w_scale[0];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFStages; ++s) {
+      mbar_init(full(s), 1);     // the producer's expect_tx arrival; the bulk copy completes the transaction bytes
+      mbar_init(empty(s), 1);    // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 256);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {   // the weight block -> 64 TMEM columns (lane = feature, column = k pair)
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(W16) + ((int64_t)blockIdx.y * 4 + warp) * (16 * 32 * 16) + lane * 16;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + kFWCol;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 v = ldg_nc_v4(src + (half * 8 + j) * (32 * 16));
+        r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+      }
+      tmem_st_32x32(t_row + 32u * half, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue (as in the tf32 image kernel)
+    const int grp = warp >> 2, q = warp & 3;
+    float* stg = reinterpret_cast<float*>(smem_raw + (sStg - raw) + grp * kStaging);
+    const float4* stg4 = reinterpret_cast<const float4*>(stg);
+    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float eb = log_scale ? expf(*log_scale) : 1.f;     // the bias is in real units: only exp(log_scale) applies
+    const int j0 = (int)blockIdx.y * kD + 4 * lane;          // flat output feature = k * d + n
+    const int kk = j0 / io.d + io.which * io.d, n = j0 % io.d;
+    const int64_t img_off = (int64_t)(kk >> 6) * (io.d * 128) + (int64_t)(n >> 6) * (64 * 128) + (kk & 63) * 128 +
+                            (((((n & 63) >> 3) ^ (kk & 7))) << 4) + (n & 7) * 2;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int64_t row0 = tile * kTile;
+      mbar_wait(acc_full(a), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int bb = 0; bb < 2; ++bb) {
+        const int e0 = 64 * grp + 32 * bb;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kTile + e0), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) stg[e * kD + q * 32 + lane] = __uint_as_float(r[e]);
+        float sc8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = row0 + e0 + 8 * q + i;
+          sc8[i] = row < M ? __ldg(io.row_scale + row) : 0.f;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = 8 * q + i;
+          const int64_t row = row0 + e0 + e;
+          const float4 v = stg4[e * (kD / 4) + lane];
+          if (row < M) {
+            const float sc = sc8[i];
+            const float y0 = (v.x * alpha + b4.x * eb) * sc, y1 = (v.y * alpha + b4.y * eb) * sc;
+            const float y2 = (v.z * alpha + b4.z * eb) * sc, y3 = (v.w * alpha + b4.w * eb) * sc;
+            const __half2 p0 = __floats2half2_rn(y0, y1), p1 = __floats2half2_rn(y2, y3);
+            *reinterpret_cast<uint2*>(io.img + row * io.image_bytes + img_off) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(a));
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ producer: one bulk copy per row tile
+    if (lane == 0) {
+      int64_t cc = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++cc) {
+        const int stage = (int)(cc % kFStages);
+        mbar_wait(empty(stage), (uint32_t)(((cc / kFStages) & 1) ^ 1));
+        mbar_arrive_expect_tx(full(stage), kXTileBytes);
+        bulk_g2s(sA + stage * kXTileBytes, reinterpret_cast<const uint8_t*>(X16) + tile * kXTileBytes, kXTileBytes,
+                 full(stage));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    int64_t cc = 0;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it, ++cc) {
+      const int a = it & 1;
+      mbar_wait(acc_empty(a), ((it >> 1) & 1) ^ 1u);
+      const int stage = (int)(cc % kFStages);
+      mbar_wait(full(stage), (uint32_t)((cc / kFStages) & 1));
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(a * kTile);
+      const uint32_t addr = sA + stage * kXTileBytes;
+      if (elect_one()) {
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const uint64_t bdesc = umma_desc_k128(addr + sub * kSub);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            umma_f16_ts_l(d_tmem, tmem_base + kFWCol + (uint32_t)(32 * sub + 8 * j), bdesc + 2 * j, kIdescF16,
+                          (uint32_t)(sub | j));
+        }
+        umma_commit(empty(stage));
+        umma_commit(acc_full(a));
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
 }  // namespace
 
 bool linear_umma_eligible(int64_t M, int K, int N, int relu, const void* log_scale, const void* X, const void* W,
@@ -344,9 +578,50 @@ int linear_umma_launch(const float* X, int64_t M, const float* W, const float* b
 
 // The last Linear of a weight generator written as fp16 operand images: image[m] entry (k + which * d, n) =
 // fp16( exp(log_scale) * (X[m] . W[k * d + n] + b[k * d + n]) * row_scale[m] ).   K = 128, N = d * d.
+// the same through fp16 operands (linear128_f16_images_kernel); GHF_IMAGES_TF32=1 keeps the tf32 kernel
+static int linear_f16_to_images(const float* X, int64_t M, const float* W, const float* b, int d, int which,
+                                const float* log_scale, const float* row_scale, void* images, int64_t image_bytes,
+                                cudaStream_t stream) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
+    GHF_CUDA(cudaFuncSetAttribute(linear128_f16_images_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+  }
+  const int N = d * d;
+  const int64_t tiles = (M + kTile - 1) / kTile;
+  const int nblocks = N / kD;
+  TempBuf x16, w16, scales;
+  GHF_CUDA(x16.alloc((size_t)tiles * kXTileBytes, stream));
+  GHF_CUDA(w16.alloc((size_t)N * kD * sizeof(__half), stream));
+  GHF_CUDA(scales.alloc(4 * sizeof(float), stream));
+  float* xs = scales.as<float>();
+  float* ws = xs + 2;
+  if (int rc = mp_f16_absmax(X, M * (int64_t)kD, xs, stream)) return rc;
+  if (int rc = mp_f16_absmax(W, (int64_t)N * kD, ws, stream)) return rc;
+  const unsigned cap = (unsigned)sm_count() * 8;
+  const int64_t xc = tiles * kTile * 16, wc = (int64_t)N * 16;
+  x16_tiles_kernel<<<(unsigned)(cdiv(xc, 256) < cap ? cdiv(xc, 256) : cap), 256, 0, stream>>>(X, M, tiles,
+                                                                                            x16.as<__half>(), xs);
+  GHF_LAUNCH_CHECK();
+  w16_blocks_kernel<<<(unsigned)(cdiv(wc, 256) < cap ? cdiv(wc, 256) : cap), 256, 0, stream>>>(W, N, w16.as<__half>(), ws);
+  GHF_LAUNCH_CHECK();
+  const int64_t gx = pick_gx(tiles, nblocks);
+  ImageOut io{reinterpret_cast<uint8_t*>(images), row_scale, image_bytes, d, which};
+  linear128_f16_images_kernel<<<dim3((unsigned)gx, (unsigned)nblocks), kFThreads, kFSmem, stream>>>(
+      x16.as<__half>(), M, w16.as<__half>(), b, log_scale, xs, ws, io);
+  GHF_LAUNCH_CHECK();
+  return 0;
+}
+
 int linear_umma_to_images(const float* X, int64_t M, const float* W, const float* b, int d, int which,
                           const float* log_scale, const float* row_scale, void* images, int64_t image_bytes,
                           cudaStream_t stream) {
+  {
+    const char* env = getenv("GHF_IMAGES_TF32");
+    const int N = d * d;
+    if (!(env && env[0] == '1') && N % kD == 0 && d % 4 == 0 && N / kD <= 65535 && M > 0 &&
+        (reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) % 16 == 0)
+      return linear_f16_to_images(X, M, W, b, d, which, log_scale, row_scale, images, image_bytes, stream);
+  }
   static bool configured[64] = {false};
   if (first_use_on_device(configured)) {
     GHF_CUDA(cudaFuncSetAttribute(linear128_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
