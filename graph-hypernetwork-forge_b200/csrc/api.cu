@@ -1,6 +1,7 @@
 // api.cu — library-wide state and ghf_hypergnn_forward_host, the end-to-end entry point that takes
 // HOST buffers (the shape of the reference's HyperGNN.forward, HG:236-298, at a C boundary).
 #include <array>
+#include <functional>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -240,19 +241,33 @@ static int forward_device_impl(const ghf_model_desc* desc, const float* const* d
     return ghf_linear_f16out(d_x, num_nodes, F, Win, bin, d, 1, nullptr, h0, h16_0, want_f16 ? scales : nullptr,
                              proj_stream);
   };
-  if (use_side) {
-    GHF_CUDA(cudaEventRecord(side.entry, stream));
+  // It is enqueued from inside dedup, right before the host waits for the number of distinct strings: the projection
+  // (HBM-bound, persistent CTAs) then runs through that round trip and beside the small sort / scan kernels that
+  // follow, instead of in front of the dedup kernels.
+  const bool entry_early = getenv("GHF_PROJ_ENTRY_LATE") == nullptr;   // experiment knob
+  if (use_side && entry_early) GHF_CUDA(cudaEventRecord(side.entry, stream));
+  const std::function<int()> enqueue_projection = [&]() -> int {
+    if (!use_side) return 0;
+    if (!entry_early) GHF_CUDA(cudaEventRecord(side.entry, stream));
     GHF_CUDA(cudaStreamWaitEvent(proj_stream, side.entry, 0));
     if (int rc = project()) return rc;
     GHF_CUDA(cudaEventRecord(side.proj_done, proj_stream));
-  }
+    return 0;
+  };
 
   StageTrace trace;
   trace.stream = stream;
   trace.mark("start");
   // HG:264-268  dedup (first-occurrence order), HG:270 text encoder on the distinct strings
   int64_t U = 0;
-  if (int rc = ghf_dedup_texts(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream)) return rc;
+  bool projected = false;
+  const std::function<int()> hook = [&]() -> int {
+    projected = true;
+    return enqueue_projection();
+  };
+  if (int rc = dedup_texts_hooked(d_utf8, d_offs, E, nullptr, 0, rel, first, &U, stream, &hook)) return rc;
+  if (!projected)                                        // no strings at all: dedup returned before its hook
+    if (int rc = enqueue_projection()) return rc;
   trace.mark("dedup");
   // the same rule as the staged entries (ghf_mp_layer_f16): an engine that does not cover this hidden size is an
   // error, not a silent change of arithmetic

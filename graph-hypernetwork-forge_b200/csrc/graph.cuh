@@ -28,3 +28,15 @@ struct ghf_graph {
   int64_t bytes = 0;
   mutable void* stream = nullptr;  // stream the tables were allocated on / last used on (freed there)
 };
+
+#ifdef __cplusplus
+#include <cuda_runtime.h>
+
+#include <functional>
+namespace ghf {
+// ghf_dedup_texts with a hook that runs after the first kernels are enqueued and before the host waits (text.cu)
+int dedup_texts_hooked(const uint8_t* d_utf8, const int64_t* d_offsets, int64_t E, const uint32_t* d_subset,
+                       int64_t n_subset, int32_t* d_rel_ids, int64_t* d_first_edge, int64_t* h_num_unique,
+                       cudaStream_t stream, const std::function<int()>* before_sync);
+}  // namespace ghf
+#endif

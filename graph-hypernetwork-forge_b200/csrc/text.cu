@@ -5,8 +5,11 @@
 // first-occurrence order, bit-exact with `list(dict.fromkeys(edge_texts))`.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <functional>
+
 #include "common.cuh"
 #include "ghf_b200.h"
+#include "graph.cuh"
 
 namespace ghf {
 namespace {
@@ -263,7 +266,15 @@ using namespace ghf;
 extern "C" int ghf_dedup_texts(const uint8_t* d_utf8, const int64_t* d_offsets, int64_t E,
                                const uint32_t* d_subset, int64_t n_subset, int32_t* d_rel_ids,
                                int64_t* d_first_edge, int64_t* h_num_unique, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+  return ghf::dedup_texts_hooked(d_utf8, d_offsets, E, d_subset, n_subset, d_rel_ids, d_first_edge, h_num_unique,
+                                 (cudaStream_t)stream_, nullptr);
+}
+
+// `before_sync` (optional) is called once, after the insert + compaction kernels are enqueued and before the host
+// waits for the number of distinct strings: work enqueued there (on another stream) fills the GPU during the round trip.
+int ghf::dedup_texts_hooked(const uint8_t* d_utf8, const int64_t* d_offsets, int64_t E, const uint32_t* d_subset,
+                            int64_t n_subset, int32_t* d_rel_ids, int64_t* d_first_edge, int64_t* h_num_unique,
+                            cudaStream_t stream, const std::function<int()>* before_sync) {
   GHF_REQUIRE(E >= 0 && E <= (int64_t)0x7FFFFFFF, "ghf_dedup_texts: E=%lld out of range", (long long)E);
   GHF_REQUIRE(reinterpret_cast<uintptr_t>(d_utf8) % 4 == 0, "ghf_dedup_texts: d_utf8 must be 4-byte aligned");
   GHF_REQUIRE(d_subset == nullptr || (n_subset >= 0 && n_subset <= E), "ghf_dedup_texts: bad subset size");
@@ -301,6 +312,10 @@ extern "C" int ghf_dedup_texts(const uint8_t* d_utf8, const int64_t* d_offsets, 
     GHF_LAUNCH_CHECK();
     int32_t h_words[2] = {0, 0};
     GHF_CUDA(cudaMemcpyAsync(h_words, words.p, sizeof(h_words), cudaMemcpyDeviceToHost, stream));
+    if (before_sync && *before_sync) {
+      if (int rc = (*before_sync)()) return rc;
+      before_sync = nullptr;                             // once, not again on the retry with the full table
+    }
     GHF_CUDA(cudaStreamSynchronize(stream));
     if ((h_words[1] != 0 || h_words[0] > max_u) && cap != full) continue;   // too many distinct strings: full table
     const int64_t U = h_words[0];
