@@ -17,7 +17,7 @@ PREC_FP32 = 0
 PREC_TF32 = 1
 PREC_F16 = 2
 _PREC = {"fp32": PREC_FP32, "tf32": PREC_TF32, "f16": PREC_F16}
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _LIB_PATH = os.environ.get("GHF_LIB") or os.path.join(
     os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")
@@ -54,6 +54,7 @@ def lib():
         "ghf_text_encode": (c_int, [P, P, P, c_int64, P, c_int, P, P, c_int, P, P]),
         "ghf_linear": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P, P]),
         "ghf_linear_f16out": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P, P, P, P]),
+        "ghf_linear_backward": (c_int, [P, c_int64, c_int, P, c_int, c_int, P, P, P, P, P, P, P, P]),
         "ghf_graph_build": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int32, c_int32, c_int64, c_int64,
                                     c_int32, c_int32, POINTER(c_void_p), P]),
         "ghf_graph_free": (None, [P]),
@@ -102,7 +103,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
-    "ghf_linear_f16out",
+    "ghf_linear_f16out", "ghf_linear_backward",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
     "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_layer_f16_range", "ghf_graph_num_phases", "ghf_mp_layer_f16_push", "ghf_mark_rows", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
     "ghf_text_encode_backward", "ghf_weight_images_bytes", "ghf_weight_images_f16", "ghf_mp_layer_images",
@@ -209,6 +210,29 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False, log_
                                        _ptr(y), _ptr(y16.data) if y16 else None, _ptr(y16.scale) if y16 else None,
                                        _stream(dev)), "ghf_linear_f16out")
     return (y, y16) if want_f16 else y
+
+
+def linear_backward(x, weight, log_scale, y, g_y, relu: bool, need_x: bool = True, need_w: bool = True,
+                    need_b: bool = True, need_ls: bool = False):
+    """Gradients of `linear` (ghf_linear_backward): -> (g_x, g_w, g_b, g_log_scale), None where not asked for.
+    x [M,K], weight [N,K], y = the forward result [M,N], g_y = dL/dy."""
+    x, weight, y, g_y = _f32(x), _f32(weight), _f32(y), _f32(g_y)
+    dev = x.device
+    M, K = x.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K or y.shape != (M, N) or g_y.shape != (M, N):
+        raise RuntimeError(f"linear_backward: x {tuple(x.shape)}, weight {tuple(weight.shape)}, y {tuple(y.shape)}, "
+                           f"g_y {tuple(g_y.shape)} do not fit")
+    log_scale = None if log_scale is None else _f32(log_scale)
+    g_x = torch.empty((M, K), dtype=torch.float32, device=dev) if need_x else None
+    g_w = torch.empty((N, K), dtype=torch.float32, device=dev) if need_w else None
+    g_b = torch.empty((N,), dtype=torch.float32, device=dev) if need_b else None
+    g_ls = torch.empty((1,), dtype=torch.float32, device=dev) if need_ls and log_scale is not None else None
+    with torch.cuda.device(dev):
+        _check(lib().ghf_linear_backward(_ptr(x), M, K, _ptr(weight), N, int(relu), _ptr(log_scale), _ptr(y),
+                                         _ptr(g_y), _ptr(g_x), _ptr(g_w), _ptr(g_b), _ptr(g_ls), _stream(dev)),
+               "ghf_linear_backward")
+    return g_x, g_w, g_b, g_ls
 
 
 def weight_generators(text_emb: torch.Tensor, mlps, log_scales, d_in: int, d_out: int):

@@ -1,5 +1,5 @@
 """Autograd for the B200 path: `torch.autograd.Function`s whose forward is the native kernel and whose backward
-is the native gradient kernel (message passing, text encoder) or a plain library GEMM (the Linear layers).
+is the native gradient kernel (message passing, text encoder, Linear layers).
 
 The reference trains through `HyperGNN.forward` (tests/test_hypergnn.py:183-226, demo.py:79-101);
 with these the drop-in does too: when gradients are enabled and something requires them, `HyperGNN.forward`,
@@ -18,13 +18,13 @@ def wants_grad(*tensors) -> bool:
 
 
 class LinearFn(torch.autograd.Function):
-    """y = exp(log_scale) * act(x W^T + b) (ghf_linear).  Backward: three GEMMs through torch.matmul (library
-    GEMMs) - in TF32 when `tf32` is set, i.e. when the model runs a tensor-core precision mode anyway, else fp32.
-    `shadow` (a list, optional) receives the fp16 Shadow of y made by the same kernel (the input projection)."""
+    """y = exp(log_scale) * act(x W^T + b) (ghf_linear).  Backward: `ghf_linear_backward` - two fp32 kernels
+    (dL/dx; dL/dW with the bias and log-scale gradients summed from the same tiles), the ReLU mask applied while the
+    tiles are loaded.  `shadow` (a list, optional) receives the fp16 Shadow of y made by the same kernel (the input
+    projection).  `tf32` is kept for callers of round 1 (the library GEMMs it selected are gone) and ignored."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, log_scale, relu: bool, shadow, tf32: bool):
-        ctx.tf32 = bool(tf32)
         if shadow is not None:
             y, y16 = _native.linear(x, weight, bias, relu=relu, log_scale=log_scale, want_f16=True)
             shadow.append(y16)
@@ -36,26 +36,15 @@ class LinearFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_y):
         x, weight, log_scale, y = ctx.saved_tensors
-        g_pre = g_y
-        if ctx.relu:      # exp(log_scale) > 0: y and the pre-activation share their sign; one fused pass
-            g_pre = torch.ops.aten.threshold_backward(g_y.contiguous(), y, 0.0)
-        g_ls = alpha = None
-        if log_scale is not None:
-            if ctx.needs_input_grad[3]:
-                g_ls = (g_y * y).sum().reshape(log_scale.shape)
-            alpha = log_scale.exp()                     # a scalar: applied to the (small) products, not to g_pre
-        allow = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = ctx.tf32
-        try:
-            g_x = g_pre @ weight if ctx.needs_input_grad[0] else None
-            g_w = g_pre.t() @ x if ctx.needs_input_grad[1] else None
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = allow
-        g_b = g_pre.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        if alpha is not None:
-            g_x, g_w, g_b = (None if t is None else t * alpha for t in (g_x, g_w, g_b))
+        need = ctx.needs_input_grad
+        g_x, g_w, g_b, g_ls = _native.linear_backward(
+            x, weight, log_scale, y, g_y.contiguous(), ctx.relu, need_x=need[0], need_w=need[1],
+            need_b=ctx.has_bias and need[2], need_ls=log_scale is not None and need[3])
+        if g_ls is not None:
+            g_ls = g_ls.reshape(log_scale.shape)
         return g_x, g_w, g_b, g_ls, None, None, None
 
 

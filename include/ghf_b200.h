@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GHF_ABI_VERSION 5
+#define GHF_ABI_VERSION 6
 
 /* precision of the relation-typed contraction in ghf_mp_layer */
 #define GHF_PREC_FP32 0 /* CUDA-core FFMA, fp32 end to end (rtol 1e-5 vs reference)          */
@@ -81,6 +81,17 @@ int ghf_linear(const float* d_X, int64_t M, int K, const float* d_W, const float
 int ghf_linear_f16out(const float* d_X, int64_t M, int K, const float* d_W, const float* d_b, int N,
                       int relu, const float* d_log_scale, float* d_Y, void* d_Y16, float* d_Y16_scale,
                       void* stream);
+
+/* ---- f3: gradients of ghf_linear (what loss.backward() needs of HG:261, WG:97-107, WG:138-140) ------------------
+ * For Y = alpha * act(X W^T + b) and gY = dL/dY, with g_pre = gY * [Y > 0] under ReLU (g_pre = gY otherwise):
+ *   d_gX [M,K] = alpha * g_pre W          d_gW [N,K] = alpha * g_pre^T X
+ *   d_gb [N]   = alpha * sum_m g_pre      d_gls [1]  = sum gY * Y   (the gradient of log_scale)
+ * Any output may be NULL (not computed).  d_Y is needed under ReLU and for d_gls, d_X for d_gW, d_W for d_gX.
+ * fp32 FFMA tiles; the ReLU mask is applied while tiles are loaded (no g_pre tensor), sums over rows and split
+ * contractions are reduced with fp32 atomics (outputs are zeroed here).  Replaces the library GEMMs of round 1. */
+int ghf_linear_backward(const float* d_X, int64_t M, int K, const float* d_W, int N, int relu,
+                        const float* d_log_scale, const float* d_Y, const float* d_gY, float* d_gX, float* d_gW,
+                        float* d_gb, float* d_gls, void* stream);
 
 /* ---- graph preprocessing (replaces the per-call gathers HG:281-283, scatter index HG:207-219)
  * Builds, for destinations dst in [dst_lo, dst_hi):

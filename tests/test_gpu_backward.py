@@ -180,6 +180,51 @@ class TestWeightGeneratorGradients:
             assert_rel_to_max(got[n].cpu().numpy(), p.grad.cpu().numpy(), 1e-4, f"grad {n}")
 
 
+@pytest.mark.parametrize("M,K,N,relu,scaled", [
+    (1000, 64, 128, True, False),       # generator hidden Linear
+    (535, 128, 16384, False, True),     # generator head: long contraction for dL/dx (split + atomics), log_scale
+    (37, 24, 50, True, True),           # nothing divisible by 4: scalar loaders
+    (3, 7, 5, False, False),
+    (200_000, 128, 128, True, False),   # input projection: the sum over rows split across CTAs
+    (4096, 48, 32, True, False),
+])
+def test_native_linear_backward_matches_float64(M, K, N, relu, scaled):
+    """ghf_linear_backward (dL/dx, dL/dW, dL/db, dL/dlog_scale of y = exp(s) act(x W^T + b)) against float64
+    autograd of the same expression; 2e-5 of each gradient's largest entry (fp32 sums in another order)."""
+    from graph_hypernetwork_forge import _native
+    g = torch.Generator(device=DEV).manual_seed(M + 3 * K + 7 * N)
+    x = torch.randn(M, K, generator=g, device=DEV)
+    w = torch.randn(N, K, generator=g, device=DEV) / K ** 0.5
+    b = torch.randn(N, generator=g, device=DEV)
+    ls = torch.tensor([-0.7], device=DEV) if scaled else None
+    g_y = torch.randn(M, N, generator=g, device=DEV)
+    y = _native.linear(x, w, b, relu=relu, log_scale=ls)
+    g_x, g_w, g_b, g_ls = _native.linear_backward(x, w, ls, y, g_y, relu, need_ls=scaled)
+
+    x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+    ls64 = ls.double().requires_grad_(True) if scaled else None
+    z = x64 @ w64.t() + b64
+    if relu:
+        # the mask must be the kernel's own (y > 0): a pre-activation within rounding of zero may fall either side
+        z = z * (y > 0).double()
+    y64 = z * ls64.exp() if scaled else z
+    (y64 * g_y.double()).sum().backward()
+    assert_rel_to_max(g_x.cpu().numpy(), x64.grad.cpu().numpy(), 2e-5, "g_x")
+    assert_rel_to_max(g_w.cpu().numpy(), w64.grad.cpu().numpy(), 2e-5, "g_w")
+    assert_rel_to_max(g_b.cpu().numpy(), b64.grad.cpu().numpy(), 2e-5, "g_b")
+    if scaled:
+        # the kernel sums g_y * y with the fp32 y of the forward
+        want = (g_y.double() * y.double()).sum().reshape(1)
+        assert_rel_to_max(g_ls.cpu().numpy(), want.cpu().numpy(), 2e-5, "g_log_scale")
+        assert abs(float(ls64.grad) - float(g_ls)) <= 1e-4 * max(1.0, abs(float(ls64.grad)))
+    # subsets of outputs
+    only_w = _native.linear_backward(x, w, ls, y, g_y, relu, need_x=False, need_b=False)
+    assert only_w[0] is None and only_w[2] is None
+    assert_rel_to_max(only_w[1].cpu().numpy(), w64.grad.cpu().numpy(), 2e-5, "g_w alone")
+    only_b = _native.linear_backward(x, w, ls, y, g_y, relu, need_x=False, need_w=False)
+    assert_rel_to_max(only_b[2].cpu().numpy(), b64.grad.cpu().numpy(), 2e-5, "g_b alone")
+
+
 def test_dropout_in_training_mode_matches_torch_stream():
     """Training mode with dropout > 0 (HG:293-294, WG:103-104): the drop-in draws its masks with F.dropout in the
     reference's call order, so with the same CUDA seed it reproduces the oracle's forward and gradients."""

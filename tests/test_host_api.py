@@ -22,7 +22,7 @@ def test_header_symbols_are_exported():
     L = ctypes.CDLL(_native.lib_path())
     for name in declared:
         assert hasattr(L, name), name
-    assert _native.lib().ghf_abi_version() == _native.ABI_VERSION == 5
+    assert _native.lib().ghf_abi_version() == _native.ABI_VERSION == 6
 
 
 def test_state_dict_and_init_stream_match_reference():
