@@ -108,10 +108,11 @@ __global__ void __launch_bounds__(256)
 mp_epilogue_kernel(const float* __restrict__ acc, const int32_t* __restrict__ indeg,
                    const float* __restrict__ h, int64_t dst_lo, int64_t num_local, int d,
                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
-                   float* __restrict__ out, float* __restrict__ upd) {
+                   float* __restrict__ out, float* __restrict__ upd, const DropoutArgs da) {
   const int lane = threadIdx.x & 31;
   const int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (v >= num_local) return;
+  const uint64_t e_row = (uint64_t)(dst_lo + v) * (uint64_t)d;   // index of the row's first element in [num_nodes, d]
   const float inv = 1.f / (float)max(indeg[v], 1);
   const float* a = acc + v * d;
   const float* hv = h + (dst_lo + v) * d;
@@ -129,6 +130,7 @@ mp_epilogue_kernel(const float* __restrict__ acc, const int32_t* __restrict__ in
         const float u = a[c] * inv;
         if (up) up[c] = u;
         x[i] = fmaxf(u + hv[c], 0.f);
+        if (da.keep > 0.f) x[i] *= fuse::dropout_mult1(da, e_row + c);
         sum += x[i];
       }
     }
@@ -136,7 +138,8 @@ mp_epilogue_kernel(const float* __restrict__ acc, const int32_t* __restrict__ in
     for (int c = lane; c < d; c += 32) {
       const float u = a[c] * inv;
       if (up) up[c] = u;
-      const float xv = fmaxf(u + hv[c], 0.f);
+      float xv = fmaxf(u + hv[c], 0.f);
+      if (da.keep > 0.f) xv *= fuse::dropout_mult1(da, e_row + c);
       o[c] = xv;  // parked in the output row, normalised in place below
       sum += xv;
     }
@@ -169,13 +172,14 @@ mp_epilogue_kernel(const float* __restrict__ acc, const int32_t* __restrict__ in
 // The same epilogue for hidden_dim 32 / 64 / 128: a lane owns D/32 CONSECUTIVE columns (one vector access per row
 // and operand), four rows in flight per warp, and an optional fp16 copy of the output row for the next layer's
 // gathers (GHF_PREC_F16).
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(256)
 mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict__ indeg,
                        const float* __restrict__ h, int64_t dst_lo, int64_t num_local,
                        const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
                        float* __restrict__ out, float* __restrict__ upd, __half* __restrict__ out16,
-                       float* __restrict__ out16_scale, const int32_t* __restrict__ det_words, const PeerPush push) {
+                       float* __restrict__ out16_scale, const int32_t* __restrict__ det_words, const PeerPush push,
+                       const DropoutArgs da) {
   using namespace fuse;
   const int det_eB = det_words ? det_words[2] : 0;     // deterministic mode: acc holds int32 fixed point (mp.cuh)
   constexpr int V = D / 32;
@@ -230,8 +234,15 @@ mp_epilogue_vec_kernel(const float* __restrict__ acc, const int32_t* __restrict_
       for (int j = 0; j < V; ++j) {
         u[j] = a[k][j] * inv;
         x[j] = fmaxf(u[j] + hv[k][j], 0.f);
-        sum += x[j];
       }
+      if constexpr (DROP) {                              // training-mode dropout (HG:293-294), torch's Philox stream
+        float m[V];
+        dropout_multv<V>(da, (uint64_t)(dst_lo + r) * D + lane * V, m);
+#pragma unroll
+        for (int j = 0; j < V; ++j) x[j] *= m[j];
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) sum += x[j];
       if (upd) vstore<V>(upd + r * D + lane * V, u);
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
@@ -352,7 +363,8 @@ extern "C" int64_t ghf_mp_workspace_bytes(const ghf_graph* g, int32_t hidden_dim
 static int launch_epilogue(const ghf_graph* g_full, const float* acc, const float* d_h, const float* d_ln_w,
                            const float* d_ln_b, float eps, float* d_out, float* d_upd, void* d_out16,
                            float* d_out16_scale, cudaStream_t stream, int64_t r0 = 0, int64_t r1 = -1,
-                           const int32_t* det_words = nullptr, PeerPush push = PeerPush()) {
+                           const int32_t* det_words = nullptr, PeerPush push = PeerPush(),
+                           DropoutArgs da = DropoutArgs()) {
   const int d = g_full->hidden_dim;
   if (r1 < 0) r1 = g_full->num_local;
   if (r1 <= r0) return 0;
@@ -381,21 +393,20 @@ static int launch_epilogue(const ghf_graph* g_full, const float* acc, const floa
     const int64_t cap = (int64_t)sm_count() * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     __half* o16 = reinterpret_cast<__half*>(d_out16);
-    if (d == 32)
-      mp_epilogue_vec_kernel<32><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16, d_out16_scale, det_words, push);
-    else if (d == 64)
-      mp_epilogue_vec_kernel<64><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps,
-                                                               d_out, d_upd, o16, d_out16_scale, det_words, push);
-    else
-      mp_epilogue_vec_kernel<128><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b,
-                                                                eps, d_out, d_upd, o16, d_out16_scale, det_words, push);
+#define GHF_EPI_VEC(D, DROP)                                                                                       \
+  mp_epilogue_vec_kernel<D, DROP><<<grid, threads, 0, stream>>>(acc, g->indeg, d_h, g->dst_lo, nl, d_ln_w, d_ln_b, eps, \
+                                                                d_out, d_upd, o16, d_out16_scale, det_words, push, da)
+    const bool drop = da.keep > 0.f;   // a separate instantiation: the inference kernel keeps its registers
+    if (d == 32) { if (drop) GHF_EPI_VEC(32, true); else GHF_EPI_VEC(32, false); }
+    else if (d == 64) { if (drop) GHF_EPI_VEC(64, true); else GHF_EPI_VEC(64, false); }
+    else { if (drop) GHF_EPI_VEC(128, true); else GHF_EPI_VEC(128, false); }
+#undef GHF_EPI_VEC
   } else {
     GHF_REQUIRE(push.mask == nullptr, "ghf_mp_layer: the peer push needs hidden_dim 64/128 and aligned buffers");
     GHF_REQUIRE(det_words == nullptr, "ghf_mp_layer: the deterministic mode needs hidden_dim 128 and aligned buffers");
     GHF_REQUIRE(d_out16 == nullptr, "ghf_mp_layer: fp16 output needs hidden_dim 32/64/128 and 16-byte alignment");
     mp_epilogue_kernel<<<(unsigned)cdiv(nl * 32, threads), threads, 0, stream>>>(
-        acc, g->indeg, d_h, g->dst_lo, nl, d, d_ln_w, d_ln_b, eps, d_out, d_upd);
+        acc, g->indeg, d_h, g->dst_lo, nl, d, d_ln_w, d_ln_b, eps, d_out, d_upd, da);
   }
   GHF_LAUNCH_CHECK();
   return 0;
@@ -548,7 +559,7 @@ static int mp_layer_impl(const ghf_graph* g, const float* d_h, const void* d_h16
                          const float* d_W_msg, const float* d_W_self, const float* d_bias, const float* d_ln_w,
                          const float* d_ln_b, float eps, int precision, float* d_out, void* d_out16,
                          float* d_out16_scale, float* d_upd, void* d_workspace, int phase_lo, int phase_hi,
-                         void* stream_, PeerPush push = PeerPush()) {
+                         void* stream_, PeerPush push = PeerPush(), DropoutArgs da = DropoutArgs()) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_layer_args(g, d_workspace, precision, d_h16, d_h16_scale)) return rc;
   GHF_REQUIRE(d_out16 == nullptr || d_out16_scale != nullptr, "ghf_mp_layer: d_out16 needs d_out16_scale (float[2])");
@@ -568,14 +579,15 @@ static int mp_layer_impl(const ghf_graph* g, const float* d_h, const void* d_h16
   const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, push.mask ? &push : nullptr};
   bool fused_done = false;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, precision, nullptr,
-                               false, false, d_workspace, stream, &acc, prof ? &rec : nullptr, nullptr, &fe,
+                               false, false, d_workspace, stream, &acc, prof ? &rec : nullptr, nullptr,
+                               da.keep > 0.f ? nullptr : &fe,   // dropout lives in the separate row epilogue only
                                &fused_done, phase_lo, phase_hi, &det_words))
     return rc;
   if (!fused_done) {
     const int64_t r0 = (int64_t)phase_lo * g->sb_nodes;
     const int64_t r1 = phase_hi * (int64_t)g->sb_nodes < g->num_local ? phase_hi * (int64_t)g->sb_nodes : g->num_local;
     if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, d_upd, d_out16, d_out16_scale, stream, r0, r1,
-                                 det_words, push))
+                                 det_words, push, da))
       return rc;
   }
   if (prof) {
@@ -621,6 +633,51 @@ extern "C" int ghf_mp_layer_f16_push(const ghf_graph* g, const float* d_h, const
   push.me = rank;
   return mp_layer_impl(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out,
                        d_out16, d_out16_scale, d_upd, d_workspace, phase_lo, phase_hi, stream_, push);
+}
+
+namespace ghf {
+int make_dropout_args(float p, uint64_t seed, uint64_t offset, int64_t numel, DropoutArgs* out, int64_t* advance) {
+  GHF_REQUIRE(p > 0.f && p < 1.f, "dropout probability must lie in (0, 1), got %g", (double)p);
+  GHF_REQUIRE(numel > 0 && numel % 4 == 0 && offset % 4 == 0,
+              "native dropout follows torch's vectorised kernel: numel %% 4 == 0 and a generator offset %% 4 == 0");
+  int dev = 0, max_threads = 0;
+  GHF_CUDA(cudaGetDevice(&dev));
+  GHF_CUDA(cudaDeviceGetAttribute(&max_threads, cudaDevAttrMaxThreadsPerMultiProcessor, dev));
+  // torch's launch for this tensor: blocks of 256 threads, min(SMs * (max threads per SM / 256), ceil(numel / 256))
+  const int64_t blocks_full = (int64_t)sm_count() * (max_threads / 256);
+  const int64_t blocks = blocks_full < cdiv(numel, 256) ? blocks_full : cdiv(numel, 256);
+  const int64_t threads = 256 * blocks;
+  if (out) {
+    const double keep = 1.0 - (double)p;                 // torch: p1m = 1. - p (double), compared and inverted as float
+    out->keep = (float)keep;
+    out->scale = (float)(1.0 / (double)out->keep);
+    out->key0 = (uint32_t)seed;
+    out->key1 = (uint32_t)(seed >> 32);
+    out->ctr0 = offset / 4;
+    out->threads = (uint32_t)threads;
+  }
+  if (advance) *advance = 4 * cdiv(numel, 4 * threads);  // ((numel - 1) / (256 * blocks * 4) + 1) * 4
+  return 0;
+}
+}  // namespace ghf
+
+extern "C" int64_t ghf_dropout_offset_advance(int64_t numel) {
+  int64_t adv = -1;
+  if (numel <= 0 || numel % 4 != 0) return -1;
+  if (make_dropout_args(0.5f, 0, 0, numel, nullptr, &adv)) return -1;
+  return adv;
+}
+
+extern "C" int ghf_mp_layer_dropout(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                                    const float* d_W_msg, const float* d_W_self, const float* d_bias,
+                                    const float* d_ln_w, const float* d_ln_b, float eps, int precision, float p_drop,
+                                    uint64_t seed, uint64_t offset, float* d_out, void* d_out16, float* d_out16_scale,
+                                    float* d_upd, void* d_workspace, void* stream_) {
+  GHF_REQUIRE(g != nullptr, "ghf_mp_layer_dropout: graph is NULL");
+  DropoutArgs da;
+  if (int rc = make_dropout_args(p_drop, seed, offset, g->num_nodes * (int64_t)g->hidden_dim, &da, nullptr)) return rc;
+  return mp_layer_impl(g, d_h, d_h16, d_h16_scale, d_W_msg, d_W_self, d_bias, d_ln_w, d_ln_b, eps, precision, d_out,
+                       d_out16, d_out16_scale, d_upd, d_workspace, 0, -1, stream_, PeerPush(), da);
 }
 
 static __global__ void mark_rows_kernel(const int64_t* __restrict__ ids, const uint32_t* __restrict__ subset, int64_t n,

@@ -21,6 +21,21 @@ struct PeerPush {
   int64_t table_row0 = 0;             // global row of local row 0
 };
 
+// Training-mode dropout between the ReLU and the LayerNorm of a layer (HG:293-294), applied inside the row epilogue on
+// the SAME Philox stream torch's CUDA dropout would use for the [num_nodes, d] tensor (tools/dropout_stream_probe.py
+// restates and checks the mapping): element i belongs to "thread" t = (i / 4) % threads at step s = (i / 4) / threads;
+// it is kept iff uniform(Philox4x32-10(key = seed, counter = (offset / 4 + s, subsequence t))[i % 4]) < keep, and kept
+// values are multiplied by `scale` = float(1 / keep).  keep == 0: no dropout.
+struct DropoutArgs {
+  float keep = 0.f, scale = 1.f;
+  uint32_t key0 = 0, key1 = 0;   // the generator's seed
+  uint64_t ctr0 = 0;             // the generator's offset / 4 at the time of the call
+  uint32_t threads = 1;          // threads of the launch torch would make for this tensor
+};
+// fills `out` for dropout probability p on a tensor of `numel` elements (numel % 4 == 0) on the current device;
+// *advance = how far the call moves the generator's offset
+int make_dropout_args(float p, uint64_t seed, uint64_t offset, int64_t numel, DropoutArgs* out, int64_t* advance);
+
 bool mp_umma_supported(int hidden_dim);
 // bytes of scratch for the per-relation operand images [R][2d x d] (tf32, UMMA K-major SW128 layout)
 int64_t mp_umma_pack_bytes(int num_rel, int hidden_dim);

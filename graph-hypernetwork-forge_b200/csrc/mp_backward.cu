@@ -27,7 +27,7 @@ mp_epilogue_bwd_kernel(const float* __restrict__ g_out, const float* __restrict_
                        const int32_t* __restrict__ indeg, const float* __restrict__ h, int64_t dst_lo,
                        int64_t num_local, int d, const float* __restrict__ ln_w, float eps,
                        float* __restrict__ g_pre, float* __restrict__ g_acc, float* __restrict__ g_lnw,
-                       float* __restrict__ g_lnb) {
+                       float* __restrict__ g_lnb, const DropoutArgs da) {
   extern __shared__ float red[];  // [2][d] block partials of the LayerNorm parameter gradients
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -47,14 +47,16 @@ mp_epilogue_bwd_kernel(const float* __restrict__ g_out, const float* __restrict_
     const float* up = upd + v * d;
     const float* hv = h + (dst_lo + v) * d;
     const float* go = g_out + v * d;
-    float x[kBwdMaxV], gy[kBwdMaxV];
+    float x[kBwdMaxV], gy[kBwdMaxV], dm[kBwdMaxV];   // dm: dropout multiplier (0 or 1 / keep; 1 without dropout)
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < kBwdMaxV; ++i) {
       const int c = lane + 32 * i;
       x[i] = gy[i] = 0.f;
+      dm[i] = 1.f;
       if (c < d) {
-        x[i] = fmaxf(up[c] + hv[c], 0.f);
+        if (da.keep > 0.f) dm[i] = fuse::dropout_mult1(da, (uint64_t)(dst_lo + v) * (uint64_t)d + c);
+        x[i] = fmaxf(up[c] + hv[c], 0.f) * dm[i];        // what the LayerNorm saw
         gy[i] = go[c];
         sum += x[i];
       }
@@ -93,8 +95,8 @@ mp_epilogue_bwd_kernel(const float* __restrict__ g_out, const float* __restrict_
     for (int i = 0; i < kBwdMaxV; ++i) {
       const int c = lane + 32 * i;
       if (c < d) {
-        const float gx = rstd * (gy[i] * lw[i] - s1 - xh[i] * s2);
-        const float gp = x[i] > 0.f ? gx : 0.f;  // relu'(0) = 0, as torch
+        const float gx = rstd * (gy[i] * lw[i] - s1 - xh[i] * s2) * dm[i];
+        const float gp = x[i] > 0.f ? gx : 0.f;  // relu'(0) = 0, as torch (x > 0 iff kept and relu input > 0)
         g_pre[v * d + c] = gp;
         g_acc[v * d + c] = gp * inv_cnt;
       }
@@ -117,13 +119,13 @@ mp_epilogue_bwd_kernel(const float* __restrict__ g_out, const float* __restrict_
 
 // The same for hidden_dim 32 / 64 / 128: a lane owns D/32 CONSECUTIVE columns (one vector access per row and
 // operand), four rows in flight per warp; optionally max |g_acc| for the fp16 shadow the next kernels gather from.
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(256)
 mp_epilogue_bwd_vec_kernel(const float* __restrict__ g_out, const float* __restrict__ upd,
                            const int32_t* __restrict__ indeg, const float* __restrict__ h, int64_t dst_lo,
                            int64_t num_local, const float* __restrict__ ln_w, float eps, float* __restrict__ g_pre,
                            float* __restrict__ g_acc, float* __restrict__ g_lnw, float* __restrict__ g_lnb,
-                           float* __restrict__ g_acc_scale) {
+                           float* __restrict__ g_acc_scale, const DropoutArgs da) {
   using namespace fuse;
   constexpr int V = D / 32;
   constexpr int kRows = 4;
@@ -157,10 +159,13 @@ mp_epilogue_bwd_vec_kernel(const float* __restrict__ g_out, const float* __restr
       const int64_t r = r0 + k * warps;
       if (r >= num_local) break;
       const float inv_cnt = 1.f / (float)max(deg[k], 1);
-      float x[V], sum = 0.f;
+      float x[V], dm[V], sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) dm[j] = 1.f;
+      if constexpr (DROP) dropout_multv<V>(da, (uint64_t)(dst_lo + r) * D + lane * V, dm);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        x[j] = fmaxf(up[k][j] + hv[k][j], 0.f);
+        x[j] = fmaxf(up[k][j] + hv[k][j], 0.f) * dm[j];  // what the LayerNorm saw
         sum += x[j];
       }
 #pragma unroll
@@ -192,7 +197,7 @@ mp_epilogue_bwd_vec_kernel(const float* __restrict__ g_out, const float* __restr
       float gp[V], ga[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const float gx = rstd * (gy[k][j] * lw[j] - s1 - xh[j] * s2);
+        const float gx = rstd * (gy[k][j] * lw[j] - s1 - xh[j] * s2) * dm[j];
         gp[j] = x[j] > 0.f ? gx : 0.f;
         ga[j] = gp[j] * inv_cnt;
         amax = fmaxf(amax, fabsf(ga[j]));
@@ -297,10 +302,9 @@ mp_wgrad_kernel(const int32_t* __restrict__ unit_start, const int32_t* __restric
 
 using namespace ghf;
 
-extern "C" int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out, const float* d_upd,
-                                        const float* d_h, const float* d_ln_w, float eps, float* d_g_pre,
-                                        float* d_g_acc, float* d_g_ln_w, float* d_g_ln_b, float* d_g_acc_scale,
-                                        void* stream_) {
+static int epilogue_backward_impl(const ghf_graph* g, const float* d_g_out, const float* d_upd, const float* d_h,
+                                  const float* d_ln_w, float eps, float* d_g_pre, float* d_g_acc, float* d_g_ln_w,
+                                  float* d_g_ln_b, float* d_g_acc_scale, const DropoutArgs da, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(g != nullptr, "ghf_mp_epilogue_backward: graph is NULL");
   const int d = g->hidden_dim;
@@ -317,21 +321,43 @@ extern "C" int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out
   const bool aligned = (reinterpret_cast<uintptr_t>(d_g_out) | reinterpret_cast<uintptr_t>(d_upd) |
                         reinterpret_cast<uintptr_t>(d_h) | reinterpret_cast<uintptr_t>(d_ln_w) |
                         reinterpret_cast<uintptr_t>(d_g_pre) | reinterpret_cast<uintptr_t>(d_g_acc)) % 16 == 0;
-#define GHF_BWD_VEC(D)                                                                                              \
-  mp_epilogue_bwd_vec_kernel<D><<<grid, 256, 0, stream>>>(d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local,   \
-                                                          d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b,        \
-                                                          d_g_acc_scale)
-  if (aligned && d == 128) GHF_BWD_VEC(128);
-  else if (aligned && d == 64) GHF_BWD_VEC(64);
-  else if (aligned && d == 32) GHF_BWD_VEC(32);
+#define GHF_BWD_VEC(D, DROP)                                                                                        \
+  mp_epilogue_bwd_vec_kernel<D, DROP><<<grid, 256, 0, stream>>>(d_g_out, d_upd, g->indeg, d_h, g->dst_lo,           \
+                                                                g->num_local, d_ln_w, eps, d_g_pre, d_g_acc,        \
+                                                                d_g_ln_w, d_g_ln_b, d_g_acc_scale, da)
+  const bool drop = da.keep > 0.f;
+  if (aligned && d == 128) { if (drop) GHF_BWD_VEC(128, true); else GHF_BWD_VEC(128, false); }
+  else if (aligned && d == 64) { if (drop) GHF_BWD_VEC(64, true); else GHF_BWD_VEC(64, false); }
+  else if (aligned && d == 32) { if (drop) GHF_BWD_VEC(32, true); else GHF_BWD_VEC(32, false); }
   else {
     GHF_REQUIRE(d_g_acc_scale == nullptr, "ghf_mp_epilogue_backward: max|g_acc| needs hidden_dim 32/64/128");
     mp_epilogue_bwd_kernel<<<grid, 256, 2 * d * sizeof(float), stream>>>(
-        d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local, d, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b);
+        d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local, d, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b,
+        da);
   }
 #undef GHF_BWD_VEC
   GHF_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out, const float* d_upd,
+                                        const float* d_h, const float* d_ln_w, float eps, float* d_g_pre,
+                                        float* d_g_acc, float* d_g_ln_w, float* d_g_ln_b, float* d_g_acc_scale,
+                                        void* stream_) {
+  return epilogue_backward_impl(g, d_g_out, d_upd, d_h, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b,
+                                d_g_acc_scale, DropoutArgs(), stream_);
+}
+
+extern "C" int ghf_mp_epilogue_backward_dropout(const ghf_graph* g, const float* d_g_out, const float* d_upd,
+                                                const float* d_h, const float* d_ln_w, float eps, float p_drop,
+                                                uint64_t seed, uint64_t offset, float* d_g_pre, float* d_g_acc,
+                                                float* d_g_ln_w, float* d_g_ln_b, float* d_g_acc_scale,
+                                                void* stream_) {
+  GHF_REQUIRE(g != nullptr, "ghf_mp_epilogue_backward_dropout: graph is NULL");
+  DropoutArgs da;
+  if (int rc = make_dropout_args(p_drop, seed, offset, g->num_nodes * (int64_t)g->hidden_dim, &da, nullptr)) return rc;
+  return epilogue_backward_impl(g, d_g_out, d_upd, d_h, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b,
+                                d_g_acc_scale, da, stream_);
 }
 
 extern "C" int ghf_mp_weight_grad(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -70,6 +70,11 @@ def lib():
         "ghf_mark_rows": (c_int, [P, P, c_int64, c_int64, P, P]),
         "ghf_mp_contract": (c_int, [P, P, P, P, P, P, P, c_int, P, c_int, c_int, P, P]),
         "ghf_mp_epilogue_backward": (c_int, [P, P, P, P, P, c_float, P, P, P, P, P, P]),
+        "ghf_dropout_offset_advance": (c_int64, [c_int64]),
+        "ghf_mp_layer_dropout": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, c_float, c_uint64, c_uint64,
+                                         P, P, P, P, P, P]),
+        "ghf_mp_epilogue_backward_dropout": (c_int, [P, P, P, P, P, c_float, c_float, c_uint64, c_uint64,
+                                                     P, P, P, P, P, P]),
         "ghf_mp_weight_grad": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, P]),
         "ghf_text_encode_backward": (c_int, [P, P, P, c_int64, P, c_int, P, c_int, P, P, P, P, P, P]),
         "ghf_weight_images_bytes": (c_int64, [c_int64, c_int32]),
@@ -106,6 +111,7 @@ EXPORTED_SYMBOLS = (
     "ghf_linear_f16out", "ghf_linear_backward",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
     "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_layer_f16_range", "ghf_graph_num_phases", "ghf_mp_layer_f16_push", "ghf_mark_rows", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
+    "ghf_dropout_offset_advance", "ghf_mp_layer_dropout", "ghf_mp_epilogue_backward_dropout",
     "ghf_text_encode_backward", "ghf_weight_images_bytes", "ghf_weight_images_f16", "ghf_mp_layer_images",
     "ghf_score_pairs", "ghf_score_pairs_backward", "ghf_absmax", "ghf_convert_f16", "ghf_hypergnn_forward_host", "ghf_hypergnn_forward_device", "ghf_copy_async", "ghf_weight_generators_scratch_bytes", "ghf_weight_generators",
     "ghf_launch_count", "ghf_profile_enable", "ghf_profile_read",
@@ -171,6 +177,35 @@ def profile_read():
 
 
 # ----------------------------------------------------------------------------- ops
+class DropoutState:
+    """What one `F.dropout(t, p)` call on a CUDA tensor of `numel` elements would take from torch's default CUDA
+    generator: (p, seed, offset).  `draw` reads the generator and advances it exactly as that call would
+    (ghf_dropout_offset_advance), so native dropout and torch's own dropout calls share one random stream."""
+
+    __slots__ = ("p", "seed", "offset")
+
+    def __init__(self, p: float, seed: int, offset: int):
+        self.p, self.seed, self.offset = float(p), int(seed), int(offset)
+
+    @staticmethod
+    def supported(numel: int) -> bool:
+        return numel > 0 and numel % 4 == 0     # torch's vectorised kernel; anything else keeps the torch-op path
+
+    @staticmethod
+    def draw(p: float, numel: int, device) -> "DropoutState":
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("native dropout reads the generator state on the host: not capturable")
+        device = torch.device(device)
+        gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        with torch.cuda.device(device):
+            adv = int(lib().ghf_dropout_offset_advance(int(numel)))
+        if adv < 0 or offset % 4:
+            raise RuntimeError(f"native dropout: unsupported tensor size {numel} or generator offset {offset}")
+        gen.set_offset(offset + adv)
+        return DropoutState(p, seed & 0xFFFFFFFFFFFFFFFF, offset)
+
+
 class Shadow:
     """fp16 shadow of a float32 feature matrix: `data` (float16) and `scale` (float32[2] on the device) with
     features = data * scale[0]; scale[0] is an exact power of two chosen on the device, scale[1] = max |features|."""
@@ -513,7 +548,7 @@ class Graph:
         return min(phase_lo * self.sb_nodes, self.num_local), min(phase_hi * self.sb_nodes, self.num_local)
 
     def mp_layer(self, h, W_msg, W_self, bias, ln_w, ln_b, eps: float, precision: int, out=None,
-                 want_upd: bool = False, h16=None, out16=None, h_row0=None, phases=None, push=None):
+                 want_upd: bool = False, h16=None, out16=None, h_row0=None, phases=None, push=None, dropout=None):
         """One message-passing layer on this graph's destination range -> (out, upd or None).
 
         `h16` (Shadow of [N, d], optional) is the fp16 shadow of `h` the PREC_F16 contraction gathers from (made
@@ -522,7 +557,8 @@ class Graph:
         - enough, because with a shadow the fp32 rows are read only at this graph's own destinations (residual).
         `phases` = (lo, hi): only the super-blocks [lo, hi) of the graph; `out`, `out16`, `upd` still cover all local
         rows, of which `phase_rows(lo, hi)` are written.  `push` (PeerPush, with `out16`): the epilogue kernel also
-        stores each fp16 row into the tables of the peers that read it."""
+        stores each fp16 row into the tables of the peers that read it.  `dropout` (DropoutState): training-mode
+        dropout between the ReLU and the LayerNorm, inside the row epilogue (whole graph, no `phases` / `push`)."""
         dev = self.device
         h, W_msg, W_self, bias = _f32(h), _f32(W_msg), _f32(W_self), _f32(bias)
         ln_w, ln_b = _f32(ln_w), _f32(ln_b)
@@ -550,6 +586,8 @@ class Graph:
         ws = self.workspace(precision)
         p_lo, p_hi = (0, self.num_phases) if phases is None else phases
         if push is not None:
+            if dropout is not None:
+                raise RuntimeError("dropout runs on the whole graph of one GPU")
             if out16 is None or push.mask.shape[1] < self.num_local:
                 raise RuntimeError("push needs out16 and a mask row per local node")
             with torch.cuda.device(dev):
@@ -560,6 +598,18 @@ class Graph:
                                                    int(p_hi), _ptr(push.mask), int(push.mask.shape[1]),
                                                    _ptr(push.tables), push.world, push.rank, _stream(dev)),
                        "ghf_mp_layer_f16_push")
+            return out, upd
+        if dropout is not None:
+            if phases is not None or h_row0 is not None:
+                raise RuntimeError("dropout runs on the whole graph of one GPU")
+            with torch.cuda.device(dev):
+                _check(lib().ghf_mp_layer_dropout(self._h, h_ptr, _ptr(h16.data) if h16 else None,
+                                                  _ptr(h16.scale) if h16 else None, _ptr(W_msg), _ptr(W_self),
+                                                  _ptr(bias), _ptr(ln_w), _ptr(ln_b), float(eps), precision,
+                                                  dropout.p, dropout.seed, dropout.offset, _ptr(out),
+                                                  _ptr(out16.data) if out16 else None,
+                                                  _ptr(out16.scale) if out16 else None, _ptr(upd), _ptr(ws),
+                                                  _stream(dev)), "ghf_mp_layer_dropout")
             return out, upd
         with torch.cuda.device(dev):
             _check(lib().ghf_mp_layer_f16_range(self._h, h_ptr, _ptr(h16.data) if h16 else None,
@@ -626,8 +676,9 @@ class Graph:
                                          _stream(dev)), "ghf_mp_contract")
         return out
 
-    def epilogue_backward(self, g_out, upd, h, ln_w, eps: float, want_shadow: bool = False):
-        """-> (g_pre, g_acc, g_ln_w, g_ln_b, Shadow of g_acc or None); see ghf_mp_epilogue_backward."""
+    def epilogue_backward(self, g_out, upd, h, ln_w, eps: float, want_shadow: bool = False, dropout=None):
+        """-> (g_pre, g_acc, g_ln_w, g_ln_b, Shadow of g_acc or None); see ghf_mp_epilogue_backward.  `dropout`: the
+        DropoutState of the forward call (the mask is regenerated from it)."""
         dev, d = self.device, self.hidden_dim
         g_out, upd, h, ln_w = _f32(g_out), _f32(upd), _f32(h), _f32(ln_w)
         if g_out.shape != (self.num_local, d) or upd.shape != g_out.shape or h.shape != (self.num_nodes, d):
@@ -636,10 +687,16 @@ class Graph:
         g_w, g_b = torch.empty_like(ln_w), torch.empty_like(ln_w)
         g16 = Shadow(torch.empty(g_acc.shape, dtype=torch.float16, device=dev)) if want_shadow else None
         with torch.cuda.device(dev):
-            _check(lib().ghf_mp_epilogue_backward(self._h, _ptr(g_out), _ptr(upd), _ptr(h), _ptr(ln_w), float(eps),
-                                                  _ptr(g_pre), _ptr(g_acc), _ptr(g_w), _ptr(g_b),
-                                                  _ptr(g16.scale) if g16 else None, _stream(dev)),
-                   "ghf_mp_epilogue_backward")
+            if dropout is not None:
+                _check(lib().ghf_mp_epilogue_backward_dropout(
+                    self._h, _ptr(g_out), _ptr(upd), _ptr(h), _ptr(ln_w), float(eps), dropout.p, dropout.seed,
+                    dropout.offset, _ptr(g_pre), _ptr(g_acc), _ptr(g_w), _ptr(g_b), _ptr(g16.scale) if g16 else None,
+                    _stream(dev)), "ghf_mp_epilogue_backward_dropout")
+            else:
+                _check(lib().ghf_mp_epilogue_backward(self._h, _ptr(g_out), _ptr(upd), _ptr(h), _ptr(ln_w),
+                                                      float(eps), _ptr(g_pre), _ptr(g_acc), _ptr(g_w), _ptr(g_b),
+                                                      _ptr(g16.scale) if g16 else None, _stream(dev)),
+                       "ghf_mp_epilogue_backward")
         if g16 is not None:
             to_f16(g_acc, g16, have_amax=True)
         return g_pre, g_acc, g_w, g_b, g16

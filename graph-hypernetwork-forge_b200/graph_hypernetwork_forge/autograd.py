@@ -105,10 +105,10 @@ class MPLayerFn(torch.autograd.Function):
     and the LayerNorm parameters."""
 
     @staticmethod
-    def forward(ctx, h, W_msg, W_self, bias, ln_w, ln_b, graph, eps: float, precision: int, h16, out16):
+    def forward(ctx, h, W_msg, W_self, bias, ln_w, ln_b, graph, eps: float, precision: int, h16, out16, dropout=None):
         out, upd = graph.mp_layer(h, W_msg, W_self, bias, ln_w, ln_b, eps, precision, want_upd=True, h16=h16,
-                                  out16=out16)
-        ctx.graph, ctx.eps, ctx.precision, ctx.h16 = graph, eps, precision, h16
+                                  out16=out16, dropout=dropout)
+        ctx.graph, ctx.eps, ctx.precision, ctx.h16, ctx.dropout = graph, eps, precision, h16, dropout
         ctx.save_for_backward(h, W_msg, W_self, ln_w, upd)
         return out
 
@@ -121,20 +121,23 @@ class MPLayerFn(torch.autograd.Function):
         # g_acc travels as ONE fp16 shadow to the two contractions and to the weight gradients (its max comes out
         # of the epilogue kernel itself); g_pre, the residual's share of dL/dh, is the buffer the others add to
         g_pre, g_acc, g_ln_w, g_ln_b, g16 = graph.epilogue_backward(g_out.contiguous(), upd, h, ln_w, ctx.eps,
-                                                                    want_shadow=f16 and graph.hidden_dim == 128)
+                                                                    want_shadow=f16 and graph.hidden_dim == 128,
+                                                                    dropout=ctx.dropout)
         g_h, g_wm, g_ws, g_b = _contraction_backward(graph, prec, h, W_msg, W_self, g_acc, g16, ctx.h16,
                                                      ctx.needs_input_grad, g_pre)
-        return g_h, g_wm, g_ws, g_b, g_ln_w, g_ln_b, None, None, None, None, None
+        return g_h, g_wm, g_ws, g_b, g_ln_w, g_ln_b, None, None, None, None, None, None
 
 
-def mp_layer(graph, h, W_msg, W_self, bias, ln_w, ln_b, eps, precision, h16=None, out16=None):
-    return MPLayerFn.apply(h, W_msg, W_self, bias, ln_w, ln_b, graph, eps, precision, h16, out16)
+def mp_layer(graph, h, W_msg, W_self, bias, ln_w, ln_b, eps, precision, h16=None, out16=None, dropout=None):
+    """`dropout` (_native.DropoutState): training-mode dropout inside the row epilogue (HG:293-294)."""
+    return MPLayerFn.apply(h, W_msg, W_self, bias, ln_w, ln_b, graph, eps, precision, h16, out16, dropout)
 
 
 class MPUpdateFn(torch.autograd.Function):
     """Only the pre-residual update of a layer, upd_v = acc_v / max(indeg_v, 1) (HG:160-230, what the reference's
-    `_message_passing` returns).  Used when something sits between the update and the LayerNorm that the fused
-    epilogue does not do - dropout in training mode (HG:293-294) - so that the rest of the layer runs as torch ops."""
+    `_message_passing` returns).  Used by the reference-shaped `_message_passing` entry, and for training-mode dropout
+    (HG:293-294) on tensors whose size torch's vectorised dropout kernel does not cover (numel % 4 != 0), where the rest
+    of the layer runs as torch ops; otherwise dropout happens inside the native row epilogue (MPLayerFn)."""
 
     @staticmethod
     def forward(ctx, h, W_msg, W_self, bias, graph, precision: int, h16):

@@ -298,12 +298,19 @@ class HyperGNN(nn.Module):
         work as they do on the reference (tests/test_hypergnn.py:183-226, demo.py:79-101).
 
         `dropping` (training mode with dropout > 0, HG:293-294): the dropout sits between the ReLU and the
-        LayerNorm, inside what the fused epilogue computes, so the layer is split - the contraction and the mean
-        stay native (`autograd.MPUpdateFn`), residual + ReLU + `F.dropout` + LayerNorm run as torch ops on the
-        device.  `F.dropout` draws from torch's CUDA generator in the reference's call order."""
+        LayerNorm, i.e. inside the row epilogue, and that is where it happens (`ghf_mp_layer_dropout`): the kernel
+        regenerates the mask `F.dropout` would draw from torch's CUDA generator at this point of the reference's call
+        order (Philox counters restated in tools/dropout_stream_probe.py), so the drop-in follows the reference's
+        random stream without a mask tensor; the generator is advanced as `F.dropout` would.  Only when the tensor
+        size is outside torch's vectorised kernel (N d % 4 != 0) is the layer split - contraction and mean native
+        (`autograd.MPUpdateFn`), residual + ReLU + `F.dropout` + LayerNorm as torch ops."""
         graph, packed = prepared.graph, prepared.packed
         N, d = graph.num_nodes, self.hidden_dim
-        chain = prec == _native.PREC_F16 and d in (64, 128) and not dropping   # fp16 shadows chained layer to layer
+        # dropout inside the native row epilogue, on torch's own Philox stream, whenever torch's vectorised dropout
+        # kernel would handle the [N, d] tensor; otherwise the layer is split and F.dropout itself runs
+        native_drop = dropping and _native.DropoutState.supported(N * d) and not os.environ.get("GHF_TORCH_DROPOUT")
+        split = dropping and not native_drop
+        chain = prec == _native.PREC_F16 and d in (64, 128) and not split   # fp16 shadows chained layer to layer
         made = [] if chain else None
         fast = prec != _native.PREC_FP32             # tensor-core precision mode: the backward GEMMs may use TF32
         for gen in self.weight_generators:
@@ -320,13 +327,14 @@ class HyperGNN(nn.Module):
             out16 = None
             if chain and l + 1 < self.num_layers:
                 out16 = _native.Shadow(torch.empty((graph.num_local, d), dtype=torch.float16, device=h.device))
-            if dropping:
+            if split:
                 upd = autograd.mp_update(graph, h, w["W_msg"], w["W_self"], w["bias"], prec, h16=h16)
                 x = nn.functional.dropout(torch.relu(upd + h), p=self.dropout)
                 h = nn.functional.layer_norm(x, (d,), ln.weight, ln.bias, ln.eps)
             else:
+                drop = _native.DropoutState.draw(self.dropout, N * d, h.device) if native_drop else None
                 h = autograd.mp_layer(graph, h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, ln.eps,
-                                      prec, h16=h16, out16=out16)
+                                      prec, h16=h16, out16=out16, dropout=drop)
             h16 = out16
             if taps is not None:
                 taps[f"W_msg.{l}"], taps[f"W_self.{l}"], taps[f"bias.{l}"] = w["W_msg"], w["W_self"], w["bias"]

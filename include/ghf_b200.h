@@ -202,6 +202,24 @@ int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void* d_x16, con
 int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out, const float* d_upd, const float* d_h,
                              const float* d_ln_w, float eps, float* d_g_pre, float* d_g_acc, float* d_g_ln_w,
                              float* d_g_ln_b, float* d_g_acc_scale, void* stream);
+/* ---- f4: training-mode dropout inside the row epilogue (HG:293-294: F.dropout between the ReLU and the LayerNorm) --
+ * ghf_mp_layer_f16 with x = dropout(relu(upd + h), p_drop) before the LayerNorm.  The mask is the one torch's CUDA
+ * dropout draws for the [num_nodes, hidden] tensor from generator state (seed, offset): element i is kept iff
+ * uniform(Philox4x32-10(seed; counter offset/4 + (i/4)/T, subsequence (i/4) % T)[i % 4]) < 1 - p_drop, with T the
+ * thread count of torch's launch (tools/dropout_stream_probe.py checks this mapping against F.dropout); kept
+ * values are scaled by 1 / (1 - p_drop).  Needs num_nodes * hidden % 4 == 0 and offset % 4 == 0 (torch's vectorised
+ * kernel).  The caller advances its generator by ghf_dropout_offset_advance(num_nodes * hidden), as torch would.
+ * ghf_mp_epilogue_backward_dropout regenerates the same mask from (seed, offset): no mask tensor is stored. */
+int64_t ghf_dropout_offset_advance(int64_t numel);
+int ghf_mp_layer_dropout(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
+                         const float* d_W_msg, const float* d_W_self, const float* d_bias, const float* d_ln_w,
+                         const float* d_ln_b, float eps, int precision, float p_drop, uint64_t seed, uint64_t offset,
+                         float* d_out, void* d_out16, float* d_out16_scale, float* d_upd, void* d_workspace,
+                         void* stream);
+int ghf_mp_epilogue_backward_dropout(const ghf_graph* g, const float* d_g_out, const float* d_upd, const float* d_h,
+                                     const float* d_ln_w, float eps, float p_drop, uint64_t seed, uint64_t offset,
+                                     float* d_g_pre, float* d_g_acc, float* d_g_ln_w, float* d_g_ln_b,
+                                     float* d_g_acc_scale, void* stream);
 /* Gradients of the generated relation tensors (overwritten): g_W_msg[r] = sum_{e in r} h_u^T g_acc_v,
  * g_W_self[r] = sum_{e in r} h_v^T g_acc_v, g_bias[r] = sum_{e in r} g_acc_v  ([R,d,d], [R,d,d], [R,d]).
  * (d_h16, d_h16_scale), (d_g16, d_g16_scale): optional fp16 shadows of h and g_acc for the tensor-core path

@@ -261,6 +261,58 @@ def test_dropout_in_training_mode_matches_torch_stream():
     assert torch.equal(a, b) or float((a - b).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("d,precision,N", [(32, "fp32", 500), (64, "tf32", 700), (128, "f16", 3000), (24, "fp32", 333),
+                                           (128, "fp32", 2500)])
+def test_native_dropout_follows_torch_generator(d, precision, N, monkeypatch):
+    """Dropout inside the native row epilogue (ghf_mp_layer_dropout) against the split path that calls F.dropout
+    itself: same seed -> the same elements dropped (outputs and every gradient agree to rounding), and the CUDA
+    generator ends at the same offset, so whatever draws next sees the reference's stream.  Covers the three vector
+    kernels (hidden 32 / 64 / 128), the generic one (hidden 24) and more elements than one step of torch's launch."""
+    from graph_hypernetwork_forge import HyperGNN
+    E, R, L, T, F, p = 8 * N, 7, 2, 16, 12, 0.3
+    g = torch.Generator(device=DEV).manual_seed(d + N)
+    ei = torch.randint(0, N, (2, E), generator=g, device=DEV)
+    rel = torch.randint(0, R, (E,), generator=g, device=DEV)
+    x = torch.randn(N, F, generator=g, device=DEV)
+    loss_w = torch.randn(N, d, generator=g, device=DEV)
+    names = [f"r{r}" for r in range(R)]
+    torch.manual_seed(3)
+    model = HyperGNN(T, F, d, L, dropout=p, precision=precision)
+    with torch.no_grad():
+        for gen in model.weight_generators:
+            for q in gen.log_scales.values():
+                q.fill_(-1.0)
+    model = model.to(DEV).train()
+    prepared = model.prepare_ids(ei, rel, names, N)
+    gen = torch.cuda.default_generators[0]
+
+    def run(torch_dropout):
+        if torch_dropout:
+            monkeypatch.setenv("GHF_TORCH_DROPOUT", "1")
+        else:
+            monkeypatch.delenv("GHF_TORCH_DROPOUT", raising=False)
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(77)
+        torch.rand(8, device=DEV)                       # the stream does not start at offset 0
+        out = model.forward_prepared(x, prepared)
+        (out * loss_w).sum().backward()
+        return out.detach().clone(), {k: q.grad.clone() for k, q in model.named_parameters()}, gen.get_offset()
+
+    out_n, grads_n, off_n = run(False)
+    out_t, grads_t, off_t = run(True)
+    assert off_n == off_t, f"generator offsets differ: native {off_n}, torch {off_t}"
+    tol = 2e-5 if precision == "fp32" else 2e-3     # tensor-core paths: the two variants chain different fp16 shadows
+    assert_rel_to_max(out_n.cpu().numpy(), out_t.cpu().numpy(), tol, "out, native dropout vs F.dropout")
+    for k in grads_t:
+        assert_rel_to_max(grads_n[k].cpu().numpy(), grads_t[k].cpu().numpy(), 5e-4 if precision == "fp32" else 2e-2,
+                          f"grad {k}, native dropout vs F.dropout")
+    # one flipped mask element would move a whole LayerNorm row by O(1); also compare against no dropout at all
+    model.eval()
+    with torch.no_grad():
+        out_e = model.forward_prepared(x, prepared)
+    assert float((out_e - out_n).abs().max()) > 0.1
+
+
 def test_score_edges_matches_score_triple_and_its_gradient():
     """`score_edges(embs, heads, tails)` = `score_triple(embs[heads], embs[tails])` (HG:304-318), forward and
     gradient, with repeated ids; out-of-range ids raise."""
