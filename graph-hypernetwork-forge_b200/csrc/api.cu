@@ -33,9 +33,41 @@ int sm_count() {
   return cached[dev];
 }
 
+namespace {
+thread_local int (*t_presync_fn)(void*) = nullptr;
+thread_local void* t_presync_arg = nullptr;
+}  // namespace
+
+int readback_wait(cudaStream_t stream, const std::function<int()>* first) {
+  static thread_local cudaEvent_t ev[64] = {nullptr};
+  int dev = 0;
+  GHF_CUDA(cudaGetDevice(&dev));
+  GHF_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  if (!ev[dev]) GHF_CUDA(cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming));
+  GHF_CUDA(cudaEventRecord(ev[dev], stream));            // the read-back copy is the last thing enqueued so far
+  if (first && *first)
+    if (int rc = (*first)()) return rc;
+  if (t_presync_fn) {
+    int (*fn)(void*) = t_presync_fn;
+    void* arg = t_presync_arg;
+    t_presync_fn = nullptr;                              // one shot: consumed by the first entry point that waits
+    t_presync_arg = nullptr;
+    const int rc = fn(arg);
+    if (rc != 0) return fail("the pre-sync hook failed (%d)", rc);
+  }
+  GHF_CUDA(cudaEventSynchronize(ev[dev]));
+  return 0;
+}
+
 }  // namespace ghf
 
 using namespace ghf;
+
+extern "C" int ghf_set_presync_hook(int (*fn)(void*), void* arg) {
+  t_presync_fn = fn;
+  t_presync_arg = arg;
+  return 0;
+}
 
 extern "C" int ghf_abi_version(void) { return GHF_ABI_VERSION; }
 extern "C" const char* ghf_last_error(void) { return err_buf(); }

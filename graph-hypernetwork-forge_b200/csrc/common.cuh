@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 
@@ -47,6 +48,14 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t align_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 
 int sm_count();  // SMs of the current device (cached per device; api.cu)
+
+// ghf_set_presync_hook (api.cu): a host callback the NEXT blocking entry point of this thread (ghf_select_edges,
+// ghf_dedup_texts, ghf_graph_build) calls once, after its kernels are enqueued and right before it waits for a size
+// to come back from the device.  Work the callback enqueues (on any stream) fills the GPU during the round trip.
+// The wait itself is for an EVENT recorded right after the read-back copy, not for the stream: work the hook puts on
+// the same stream does not delay the host.
+// readback_wait: record the event on `stream`, run `first` (an internal hook, may be NULL) and the caller's hook, wait.
+int readback_wait(cudaStream_t stream, const std::function<int()>* first = nullptr);
 
 // cudaFuncSetAttribute is per DEVICE: kernels that opt in to large shared memory configure themselves on first use
 // on each device of the process.  -> true the first time it is called with these flags on the current device.

@@ -230,7 +230,7 @@ static int graph_build_impl(ghf_graph* g, const int64_t* d_edge_index, const uin
     GHF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kbuf, vbuf, (int)n, 0, end_bit, stream));
     g_launches.fetch_add((end_bit + 7) / 8 + 2, std::memory_order_relaxed);
   }
-  GHF_CUDA(cudaStreamSynchronize(stream));
+  if (int rc = readback_wait(stream)) return rc;         // runs the caller's one-shot hook (ghf_set_presync_hook)
   GHF_REQUIRE((bad_ids & 1) == 0, "ghf_graph_build: edge_index holds node ids outside [0, %lld)",
               (long long)g->num_nodes);
   GHF_REQUIRE((bad_ids & 2) == 0, "ghf_graph_build: relation ids outside [0, %d)", g->num_rel);
@@ -278,7 +278,7 @@ extern "C" int ghf_select_edges(const int64_t* d_edge_index, int64_t E, int64_t 
   GHF_CUDA(cub::DeviceSelect::If(tmp.p, bytes, ids, d_edge_ids, count.as<int64_t>(), (int)E, pred, stream));
   g_launches.fetch_add(2, std::memory_order_relaxed);
   GHF_CUDA(cudaMemcpyAsync(h_count, count.p, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-  GHF_CUDA(cudaStreamSynchronize(stream));
+  if (int rc = readback_wait(stream)) return rc;         // runs the caller's one-shot hook (ghf_set_presync_hook)
   return 0;
 }
 

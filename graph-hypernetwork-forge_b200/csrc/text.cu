@@ -312,11 +312,10 @@ int ghf::dedup_texts_hooked(const uint8_t* d_utf8, const int64_t* d_offsets, int
     GHF_LAUNCH_CHECK();
     int32_t h_words[2] = {0, 0};
     GHF_CUDA(cudaMemcpyAsync(h_words, words.p, sizeof(h_words), cudaMemcpyDeviceToHost, stream));
-    if (before_sync && *before_sync) {
-      if (int rc = (*before_sync)()) return rc;
-      before_sync = nullptr;                             // once, not again on the retry with the full table
-    }
-    GHF_CUDA(cudaStreamSynchronize(stream));
+    // wait for the two words only (an event after the copy), with the hooks run in between: `before_sync` and the
+    // caller's one-shot hook (ghf_set_presync_hook) - both once, not again on the retry with the full table
+    if (int rc = readback_wait(stream, before_sync)) return rc;
+    before_sync = nullptr;
     if ((h_words[1] != 0 || h_words[0] > max_u) && cap != full) continue;   // too many distinct strings: full table
     const int64_t U = h_words[0];
     cub::DoubleBuffer<uint32_t> kbuf(reps.as<uint32_t>(), reps.as<uint32_t>() + max_u);

@@ -22,6 +22,7 @@ ABI_VERSION = 6
 _LIB_PATH = os.environ.get("GHF_LIB") or os.path.join(
     os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libghf_b200.so")
 _lib = None
+_HOOK_T = ctypes.CFUNCTYPE(c_int, c_void_p)
 
 
 class ModelDesc(ctypes.Structure):
@@ -49,6 +50,7 @@ def lib():
         "ghf_abi_version": (c_int, []),
         "ghf_last_error": (c_char_p, []),
         "ghf_device_ok": (c_int, []),
+        "ghf_set_presync_hook": (c_int, [_HOOK_T, P]),
         "ghf_dedup_texts": (c_int, [P, P, c_int64, P, c_int64, P, P, POINTER(c_int64), P]),
         "ghf_select_edges": (c_int, [P, c_int64, c_int64, c_int64, P, POINTER(c_int64), P]),
         "ghf_text_encode": (c_int, [P, P, P, c_int64, P, c_int, P, P, c_int, P, P]),
@@ -107,7 +109,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
+    "ghf_abi_version", "ghf_last_error", "ghf_device_ok", "ghf_set_presync_hook", "ghf_dedup_texts", "ghf_select_edges", "ghf_text_encode", "ghf_linear",
     "ghf_linear_f16out", "ghf_linear_backward",
     "ghf_graph_build", "ghf_graph_free", "ghf_graph_info", "ghf_graph_export", "ghf_mp_workspace_bytes",
     "ghf_mp_layer", "ghf_mp_layer_f16", "ghf_mp_layer_f16_range", "ghf_graph_num_phases", "ghf_mp_layer_f16_push", "ghf_mark_rows", "ghf_mp_contract", "ghf_mp_epilogue_backward", "ghf_mp_weight_grad",
@@ -144,6 +146,39 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
     with torch.cuda.device(dev):
         _check(lib().ghf_device_ok(), "ghf_device_ok")
     return dev
+
+
+def _call_with_presync(call, before_sync):
+    """Run `call()` (a wrapper around ghf_select_edges / ghf_dedup_texts / ghf_graph_build) with `before_sync` set as
+    the one-shot pre-sync hook (ghf_set_presync_hook): the native side invokes it after its kernels are enqueued and
+    right before it waits for a size from the device, so whatever `before_sync` enqueues runs through that round
+    trip.  `before_sync` runs exactly once - here, afterwards, if the entry point never reached its wait."""
+    if before_sync is None:
+        return call()
+    state = {"ran": False, "exc": None}
+
+    def hook(_arg):
+        state["ran"] = True
+        try:
+            before_sync()
+        except BaseException as e:  # noqa: BLE001 - re-raised below, outside the foreign frame
+            state["exc"] = e
+            return 1
+        return 0
+
+    c_hook = _HOOK_T(hook)
+    lib().ghf_set_presync_hook(c_hook, None)
+    try:
+        result = call()
+    except RuntimeError:
+        if state["exc"] is not None:
+            raise state["exc"]
+        raise
+    finally:
+        lib().ghf_set_presync_hook(_HOOK_T(0), None)
+    if not state["ran"]:
+        before_sync()
+    return result
 
 
 def _ptr(t):
@@ -364,9 +399,10 @@ def to_f16(x: torch.Tensor, shadow: Shadow, have_amax: bool = False) -> Shadow:
     return shadow
 
 
-def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor, subset=None):
+def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor, subset=None, before_sync=None):
     """-> (rel_ids int32, first_edge int64 [U]) for packed strings on the device.  rel_ids has one entry per
-    string, or per entry of `subset` (ascending string ids, int32 storage read as uint32) when given."""
+    string, or per entry of `subset` (ascending string ids, int32 storage read as uint32) when given.
+    `before_sync`: see `_call_with_presync`."""
     dev = utf8.device
     E = offsets.numel() - 1
     n = E if subset is None else subset.numel()
@@ -376,13 +412,15 @@ def dedup_texts(utf8: torch.Tensor, offsets: torch.Tensor, subset=None):
     first = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     nu = c_int64(0)
     with torch.cuda.device(dev):
-        _check(lib().ghf_dedup_texts(_ptr(utf8), _ptr(offsets), E, _ptr(subset), n if subset is not None else 0,
-                                     _ptr(rel), _ptr(first), ctypes.byref(nu), _stream(dev)), "ghf_dedup_texts")
+        _call_with_presync(lambda: _check(
+            lib().ghf_dedup_texts(_ptr(utf8), _ptr(offsets), E, _ptr(subset), n if subset is not None else 0,
+                                  _ptr(rel), _ptr(first), ctypes.byref(nu), _stream(dev)), "ghf_dedup_texts"), before_sync)
     return rel, first[: nu.value]
 
 
-def select_edges(edge_index: torch.Tensor, dst_lo: int, dst_hi: int) -> torch.Tensor:
-    """Ascending ids (int32 storage, uint32 values) of the edges whose destination lies in [dst_lo, dst_hi)."""
+def select_edges(edge_index: torch.Tensor, dst_lo: int, dst_hi: int, before_sync=None) -> torch.Tensor:
+    """Ascending ids (int32 storage, uint32 values) of the edges whose destination lies in [dst_lo, dst_hi).
+    `before_sync`: see `_call_with_presync`."""
     dev = edge_index.device
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
         raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
@@ -391,8 +429,9 @@ def select_edges(edge_index: torch.Tensor, dst_lo: int, dst_hi: int) -> torch.Te
     ids = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
     n = c_int64(0)
     with torch.cuda.device(dev):
-        _check(lib().ghf_select_edges(_ptr(edge_index), E, int(dst_lo), int(dst_hi), _ptr(ids), ctypes.byref(n),
-                                      _stream(dev)), "ghf_select_edges")
+        _call_with_presync(lambda: _check(
+            lib().ghf_select_edges(_ptr(edge_index), E, int(dst_lo), int(dst_hi), _ptr(ids), ctypes.byref(n),
+                                   _stream(dev)), "ghf_select_edges"), before_sync)
     return ids[: n.value]
 
 
@@ -476,8 +515,9 @@ class Graph:
 
     def __init__(self, edge_index: torch.Tensor, rel_ids: torch.Tensor, num_nodes: int, num_rel: int,
                  hidden_dim: int, dst_lo: int = 0, dst_hi=None, sb_nodes: int = 0, unit_edges: int = 0,
-                 edge_ids=None):
-        """`edge_ids` (from `select_edges`): build from those edges only; rel_ids is then indexed like edge_ids."""
+                 edge_ids=None, before_sync=None):
+        """`edge_ids` (from `select_edges`): build from those edges only; rel_ids is then indexed like edge_ids.
+        `before_sync`: see `_call_with_presync`."""
         dev = edge_index.device
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
@@ -493,11 +533,13 @@ class Graph:
         n_sub = 0 if edge_ids is None else edge_ids.numel()
         if rel_ids.numel() != (E if edge_ids is None else n_sub):
             raise RuntimeError("rel_ids must have one entry per edge (or per selected edge)")
+        rel_c = rel_ids.contiguous()
         with torch.cuda.device(dev):
-            _check(lib().ghf_graph_build(_ptr(edge_index), E, _ptr(edge_ids), n_sub, _ptr(rel_ids.contiguous()),
-                                         self.num_nodes, self.num_rel, self.hidden_dim, self.dst_lo, self.dst_hi,
-                                         int(sb_nodes), int(unit_edges), ctypes.byref(self._h), _stream(dev)),
-                   "ghf_graph_build")
+            _call_with_presync(lambda: _check(
+                lib().ghf_graph_build(_ptr(edge_index), E, _ptr(edge_ids), n_sub, _ptr(rel_c), self.num_nodes,
+                                      self.num_rel, self.hidden_dim, self.dst_lo, self.dst_hi, int(sb_nodes),
+                                      int(unit_edges), ctypes.byref(self._h), _stream(dev)), "ghf_graph_build"),
+                before_sync)
         self._inputs = (edge_index, edge_ids, rel_ids.contiguous())   # export() recomputes the permutation from them
         info = (c_int64 * 6)()
         _check(lib().ghf_graph_info(self._h, info), "ghf_graph_info")

@@ -265,13 +265,20 @@ class ShardedForward:
         from .models.hypergnn import PackedTexts
         m = self.model
         self._mark("start")
-        started = self._start_h0(node_features)          # the rows travel while edge selection and graph build run
         device = _native.require_cuda(edge_index, utf8, offsets, m.input_proj.weight)
+        box = {}
+
+        def start_h0():                                  # the rows travel while edge selection and graph build run
+            box["started"] = self._start_h0(node_features)
         subset = None
         if (self.lo, self.hi) != (0, self.num_nodes):
-            subset = _native.select_edges(edge_index, self.lo, self.hi)
+            # the selection kernels go first; the projection of the own rows, the scale agreement and the push of
+            # the fp16 rows are enqueued while the host would otherwise just wait for the number of selected edges
+            subset = _native.select_edges(edge_index, self.lo, self.hi, before_sync=start_h0)
+        else:
+            start_h0()
         packed = PackedTexts(None, device, utf8, offsets, subset)
-        return self._run(node_features, edge_index, packed, started, gather_output)
+        return self._run(node_features, edge_index, packed, box["started"], gather_output)
 
     def forward(self, node_features, edge_index, edge_texts, gather_output: bool = False) -> torch.Tensor:
         """The reference's call shape (List[str]); every rank holds the full edge list."""
@@ -315,9 +322,20 @@ class ShardedForward:
         m = self.model
         if m.training and m.dropout > 0.0:
             raise NotImplementedError("the multi-GPU path is inference-only (no dropout, no gradients)")
+        hook = None
+        if started is not None:
+            # text encoder + the generators of every layer need only the dedup result.  They are enqueued (on the side
+            # stream, ~0.3 ms of host time) from inside graph build, after its kernels are in the queue and before it
+            # waits for the table sizes: they run beside the sort instead of after it, and cost no time on the host.
+            dedup_done = torch.cuda.Event()
+            dedup_done.record(torch.cuda.current_stream(node_features.device))
+
+            def hook():
+                started["weights"] = self._start_generators(packed, node_features.device, after=dedup_done)
         graph = _native.Graph(edge_index, packed.rel_ids, self.num_nodes, max(packed.num_unique, 1), m.hidden_dim,
                               dst_lo=self.lo, dst_hi=self.hi, sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
-                              unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset)
+                              unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset,
+                              before_sync=hook)
         if started is not None and self._sym is not None and self.world > 1:
             self.push_used = self._pick_push(graph) if self.push == "auto" else self.push
             if self.push_used == "kernel":
@@ -428,10 +446,33 @@ class ShardedForward:
                 pending = exchange_rows(tables[0], self.ranges, self.rank, self.group, async_op=True)
         return {"tables": tables, "scales": scales, "h_local": h_local, "pending": pending, "sym": sym}
 
+    def _start_generators(self, packed, device, after=None):
+        """Text encoder + every layer's generated weights in one native call on the side stream (they depend on the
+        relation texts only).  `after`: event the side stream waits for (default: everything enqueued on the current
+        stream so far).  -> (weights per layer, event after the last of them)."""
+        m = self.model
+        main = torch.cuda.current_stream(device)
+        if getattr(self, "_gen_stream", None) is None:
+            self._gen_stream = torch.cuda.Stream(device=device)
+        with torch.no_grad():
+            if after is not None:
+                self._gen_stream.wait_event(after)
+            else:
+                self._gen_stream.wait_stream(main)
+            with torch.cuda.stream(self._gen_stream):
+                text_embs = m.text_encoder.encode_packed(packed)
+                weights = m._generate_all(text_embs, packed.num_unique)
+                done = torch.cuda.Event()
+                done.record(self._gen_stream)
+            for w in weights:                             # the tensors are consumed on the main stream
+                for t in w.values():
+                    t.record_stream(main)
+        return weights, done
+
     def _layers_f16(self, graph, packed, st) -> torch.Tensor:
         """f16 engine: fp32 rows stay local, the fp16 shadow is what every rank reads and what travels.  The rank's
         super-blocks are run in `chunks` pieces; the finished rows of a piece are pushed while the next one runs.
-        The generators of all layers run on a side stream (they depend on the text embeddings only)."""
+        The generators of all layers run on a side stream (`_start_generators`, enqueued before graph build)."""
         from . import _native
         m = self.model
         N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
@@ -439,20 +480,9 @@ class ShardedForward:
         h_cur, pending = st["h_local"], st["pending"]
         device = h_cur.device
         main = torch.cuda.current_stream(device)
-        if getattr(self, "_gen_stream", None) is None:
-            self._gen_stream = torch.cuda.Stream(device=device)
         with torch.no_grad():
-            text_embs = m.text_encoder.encode_packed(packed)
-            self._gen_stream.wait_stream(main)
-            with torch.cuda.stream(self._gen_stream):    # every layer's weights in one native call
-                weights = m._generate_all(text_embs, packed.num_unique)
-                done = torch.cuda.Event()
-                done.record(self._gen_stream)
+            weights, done = st["weights"] if "weights" in st else self._start_generators(packed, device)
             ready = [done] * m.num_layers
-            for w in weights:                             # the tensors are consumed on the main stream
-                for t in w.values():
-                    t.record_stream(main)
-            text_embs.record_stream(self._gen_stream)
             chunks = self._phase_chunks(graph) if graph.num_local else []
             self._mark("prep")
             for l in range(m.num_layers):

@@ -39,9 +39,9 @@ class PackedTexts:
     """Relation strings on the device: bytes, offsets, per-edge relation ids, distinct-string index."""
 
     def __init__(self, texts: Optional[List[str]], device: torch.device, utf8: Optional[torch.Tensor] = None,
-                 offsets: Optional[torch.Tensor] = None, subset: Optional[torch.Tensor] = None):
+                 offsets: Optional[torch.Tensor] = None, subset: Optional[torch.Tensor] = None, before_sync=None):
         """`subset` (packed path only): ids of the strings to consider (a rank's own edges); `rel_ids` is then
-        indexed like `subset`."""
+        indexed like `subset`.  `before_sync`: called once while dedup waits for its host round trip."""
         self.subset = subset
         if texts is None:   # already packed on the device (UTF-8 bytes + int64 offsets[E+1])
             if utf8.dtype != torch.uint8 or offsets.dtype != torch.int64:
@@ -53,7 +53,7 @@ class PackedTexts:
             self.num_edges = len(texts)
             self.utf8 = _to_device(data, device) if data.size else torch.zeros(1, dtype=torch.uint8, device=device)
             self.offsets = _to_device(offs, device)
-        ids, first = _native.dedup_texts(self.utf8, self.offsets, subset)   # over the packed strings
+        ids, first = _native.dedup_texts(self.utf8, self.offsets, subset, before_sync=before_sync)   # packed strings
         self.first = first                                          # packed-string index of each distinct text
         self.num_unique = int(first.numel())
         if edge_map is None:

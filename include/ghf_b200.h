@@ -93,6 +93,14 @@ int ghf_linear_backward(const float* d_X, int64_t M, int K, const float* d_W, in
                         const float* d_log_scale, const float* d_Y, const float* d_gY, float* d_gX, float* d_gW,
                         float* d_gb, float* d_gls, void* stream);
 
+/* ---- overlap of host round trips ---------------------------------------------------------------------------------
+ * ghf_select_edges, ghf_dedup_texts and ghf_graph_build each wait once for a size to come back from the device.
+ * A hook set here is called ONCE by the next of those calls on this thread, after its kernels are enqueued and right
+ * before it waits: whatever the hook enqueues (the input projection, the weight generators - on any stream) runs
+ * through the round trip instead of after it.  The hook returns 0; anything else fails the entry point.  A hook
+ * that is never consumed (an early error, an empty input) stays set: clear it with (NULL, NULL). */
+int ghf_set_presync_hook(int (*fn)(void*), void* arg);
+
 /* ---- graph preprocessing (replaces the per-call gathers HG:281-283, scatter index HG:207-219)
  * Builds, for destinations dst in [dst_lo, dst_hi):
  *   in-degree, dst-CSR rowptr, and the edge order (super-block of dst, relation, dst), stable,
