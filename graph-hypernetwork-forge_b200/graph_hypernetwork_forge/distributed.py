@@ -236,8 +236,9 @@ class ShardedForward:
         return self._sym
 
     def _phase_chunks(self, graph) -> List[Tuple[int, int]]:
-        """The graph's super-blocks in `chunks` contiguous pieces (a piece is one launch of the layer kernels)."""
-        n = graph.num_phases
+        """The graph's super-blocks (a Graph, or their number) in `chunks` contiguous pieces (a piece is one launch
+        of the layer kernels)."""
+        n = graph if isinstance(graph, int) else graph.num_phases
         c = max(1, min(self.chunks, n)) if self.chunks else max(1, min(4, n // 8))
         cuts = [round(i * n / c) for i in range(c + 1)]
         return [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
@@ -277,7 +278,16 @@ class ShardedForward:
             subset = _native.select_edges(edge_index, self.lo, self.hi, before_sync=start_h0)
         else:
             start_h0()
-        packed = PackedTexts(None, device, utf8, offsets, subset)
+
+        def start_peer_mask():
+            # who reads which of this rank's rows needs only the selected edges: marked and exchanged while dedup
+            # waits for its count, instead of between graph build and the first layer
+            st = box["started"]
+            if st is not None and self._sym is not None and self.world > 1:
+                kept = int(subset.numel()) if subset is not None else int(edge_index.shape[1])
+                sb = max(1024, (48 << 20) // (8 * m.hidden_dim))          # graph build's default super-block
+                self._decide_push(st, kept, -(-max(self.hi - self.lo, 1) // sb), edge_index, subset)
+        packed = PackedTexts(None, device, utf8, offsets, subset, before_sync=start_peer_mask)
         return self._run(node_features, edge_index, packed, box["started"], gather_output)
 
     def forward(self, node_features, edge_index, edge_texts, gather_output: bool = False) -> torch.Tensor:
@@ -336,23 +346,28 @@ class ShardedForward:
                               dst_lo=self.lo, dst_hi=self.hi, sb_nodes=int(os.environ.get("GHF_SB_NODES", "0")),
                               unit_edges=int(os.environ.get("GHF_UNIT_EDGES", "0")), edge_ids=packed.subset,
                               before_sync=hook)
-        if started is not None and self._sym is not None and self.world > 1:
-            self.push_used = self._pick_push(graph) if self.push == "auto" else self.push
-            if self.push_used == "kernel":
-                started["peer_mask"] = self._peer_mask(edge_index, packed.subset)
+        if started is not None and self._sym is not None and self.world > 1 and "push" not in started:
+            self._decide_push(started, graph.num_kept, graph.num_phases, edge_index, packed.subset)
         return self._layers(node_features, graph, packed, started, gather_output)
 
-    def _pick_push(self, graph) -> str:
+    def _decide_push(self, started, num_kept: int, num_phases: int, edge_index, subset) -> None:
+        """Pick the push mode of this forward (once) and, for "kernel", exchange the read masks."""
+        self.push_used = self._pick_push(num_kept, num_phases) if self.push == "auto" else self.push
+        started["push"] = self.push_used
+        if self.push_used == "kernel":
+            started["peer_mask"] = self._peer_mask(edge_index, subset)
+
+    def _pick_push(self, num_kept: int, num_phases: int) -> str:
         """Per layer: "kernel" costs compute + f X, "copy" costs max(compute, X) + min(compute, X) / chunks, with
         X = time to receive everybody's rows, f = share of rows a peer really reads ~ 1 - exp(-edges per rank / N)
         (uniform sources), compute ~ edges per rank x t_edge.  c3 on 8 GPUs: 0.38 + 0.55 x 0.80 < 0.80 + 0.38 -> kernel;
         c5 on 8 GPUs: 5.9 + 0.71 x 8.0 > 8.0 + 5.9 / 4 -> copy."""
         import math
         d, n = self.model.hidden_dim, max(self.num_nodes, 1)
-        compute = graph.num_kept * self._T_EDGE_128 * d / 128.0
+        compute = num_kept * self._T_EDGE_128 * d / 128.0
         x = (self.world - 1) / self.world * n * d * 2 / self._NVLINK_BPS
-        f = 1.0 - math.exp(-graph.num_kept / n)
-        chunks = len(self._phase_chunks(graph))
+        f = 1.0 - math.exp(-num_kept / n)
+        chunks = len(self._phase_chunks(num_phases))
         return "kernel" if compute + f * x < max(compute, x) + min(compute, x) / chunks else "copy"
 
     def _peer_mask(self, edge_index, subset) -> torch.Tensor:

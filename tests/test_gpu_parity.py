@@ -594,3 +594,50 @@ def test_out_of_range_node_ids_are_reported():
         bad[row, 17] = val
         with pytest.raises(RuntimeError, match="outside"):
             _native.Graph(bad, rel, N, 1, 32)
+
+
+def test_presync_hook_runs_once_inside_the_blocking_entries():
+    """`before_sync` (ghf_set_presync_hook): select_edges, dedup_texts and the graph build call it exactly once, from
+    inside the native call (after their kernels are enqueued, before the wait), the results are unchanged, work it
+    enqueues on the same stream is ordered correctly, an exception in it surfaces, and it still runs when the entry
+    point returns before waiting (no edges)."""
+    from graph_hypernetwork_forge import _native, _text
+    N, E, R = 300, 5000, 11
+    rng = np.random.default_rng(3)
+    ei = torch.from_numpy(rng.integers(0, N, (2, E))).to(DEV)
+    texts = [f"rel_{int(r)}" for r in rng.integers(0, R, E)]
+    data, offs = _text.pack_utf8(texts)
+    utf8, offsets = torch.from_numpy(data).to(DEV), torch.from_numpy(offs).to(DEV)
+    calls = []
+    probe = torch.zeros(4, device=DEV)
+
+    def hook(tag):
+        def run():
+            calls.append(tag)
+            probe.add_(1.0)                              # enqueued on the entry's own stream, from inside the call
+        return run
+
+    sel0 = _native.select_edges(ei, 50, 200)
+    sel1 = _native.select_edges(ei, 50, 200, before_sync=hook("select"))
+    assert torch.equal(sel0, sel1)
+    rel0, first0 = _native.dedup_texts(utf8, offsets)
+    rel1, first1 = _native.dedup_texts(utf8, offsets, before_sync=hook("dedup"))
+    assert torch.equal(rel0, rel1) and torch.equal(first0, first1)
+    g0 = _native.Graph(ei, rel0, N, int(first0.numel()), 32)
+    g1 = _native.Graph(ei, rel0, N, int(first0.numel()), 32, before_sync=hook("graph"))
+    a, b = g0.export(), g1.export()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert calls == ["select", "dedup", "graph"]
+    # never reaches its wait (no edges): the hook still runs, afterwards
+    empty = torch.zeros((2, 0), dtype=torch.int64, device=DEV)
+    _native.select_edges(empty, 0, 10, before_sync=hook("empty"))
+    assert calls[-1] == "empty" and float(probe[0]) == 4.0
+
+    def boom():
+        raise KeyError("from the hook")
+    with pytest.raises(KeyError, match="from the hook"):
+        _native.dedup_texts(utf8, offsets, before_sync=boom)
+    rel2, _ = _native.dedup_texts(utf8, offsets)         # the library is still usable, no stale hook
+    assert torch.equal(rel0, rel2)
+    _native.select_edges(ei, 0, N)                       # nothing left set: this must not call anything
+    assert len(calls) == 4
