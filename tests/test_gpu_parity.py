@@ -607,7 +607,7 @@ def test_presync_hook_runs_once_inside_the_blocking_entries():
     ei = torch.from_numpy(rng.integers(0, N, (2, E))).to(DEV)
     texts = [f"rel_{int(r)}" for r in rng.integers(0, R, E)]
     data, offs = _text.pack_utf8(texts)
-    utf8, offsets = torch.from_numpy(data).to(DEV), torch.from_numpy(offs).to(DEV)
+    utf8, offsets = torch.from_numpy(data.copy()).to(DEV), torch.from_numpy(offs.copy()).to(DEV)
     calls = []
     probe = torch.zeros(4, device=DEV)
 
