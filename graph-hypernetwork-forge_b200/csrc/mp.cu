@@ -702,12 +702,18 @@ extern "C" int ghf_mark_rows(const int64_t* d_ids, const uint32_t* d_subset, int
 namespace ghf {
 int mp_layer_prepacked(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
                        const void* images, const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
-                       float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace, cudaStream_t stream) {
+                       float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace, cudaStream_t stream,
+                       int phase_lo, int phase_hi) {
   if (int rc = check_layer_args(g, d_workspace, GHF_PREC_F16, d_h16, d_h16_scale)) return rc;
   GHF_REQUIRE(images != nullptr && (mp_f16ss_supported(g->hidden_dim) || mp_f16_supported(g->hidden_dim)),
               "mp_layer_prepacked: hidden_dim 64 / 128 / 256 only");
   g->stream = stream;
   if (g->num_local == 0) return 0;
+  if (phase_hi < 0) phase_hi = (int)g->num_phases;
+  GHF_REQUIRE(0 <= phase_lo && phase_lo <= phase_hi && phase_hi <= g->num_phases,
+              "mp_layer_prepacked: bad super-block range [%d, %d) of %lld", phase_lo, phase_hi, (long long)g->num_phases);
+  if (phase_lo == phase_hi) return 0;
+
   ProfRec rec{};
   const bool prof = g_prof_on;
   if (prof)
@@ -716,11 +722,15 @@ int mp_layer_prepacked(const ghf_graph* g, const float* d_h, const void* d_h16, 
   const FusedEpilogue fe{d_h, d_ln_w, d_ln_b, eps, d_out, nullptr, d_out16, d_out16_scale};
   bool fused_done = false;
   if (int rc = run_contraction(g, d_h, d_h16, d_h16_scale, nullptr, nullptr, d_bias, GHF_PREC_F16, nullptr, false,
-                               false, d_workspace, stream, &acc, prof ? &rec : nullptr, images, &fe, &fused_done))
+                               false, d_workspace, stream, &acc, prof ? &rec : nullptr, images, &fe, &fused_done,
+                               phase_lo, phase_hi))
     return rc;
-  if (!fused_done)
-    if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, nullptr, d_out16, d_out16_scale, stream))
+  if (!fused_done) {
+    const int64_t r0 = (int64_t)phase_lo * g->sb_nodes;
+    const int64_t r1 = phase_hi * (int64_t)g->sb_nodes < g->num_local ? phase_hi * (int64_t)g->sb_nodes : g->num_local;
+    if (int rc = launch_epilogue(g, acc, d_h, d_ln_w, d_ln_b, eps, d_out, nullptr, d_out16, d_out16_scale, stream, r0, r1))
       return rc;
+  }
   if (prof) {
     GHF_CUDA(cudaEventRecord(rec.e[3], stream));
     g_prof.push_back(rec);

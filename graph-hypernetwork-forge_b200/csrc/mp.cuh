@@ -112,9 +112,11 @@ int linear_umma_to_images(const float* X, int64_t M, const float* W, const float
                           const float* log_scale, const float* row_scale, void* images, int64_t image_bytes,
                           cudaStream_t stream);
 // ghf_mp_layer_f16 for hidden 64 / 256 with the operand images already built (`images`: mp_f16ss_pack_bytes layout)
+// phase_lo / phase_hi: only the super-blocks [phase_lo, phase_hi) (default: all), as ghf_mp_layer_f16_range
 int mp_layer_prepacked(const ghf_graph* g, const float* d_h, const void* d_h16, const float* d_h16_scale,
                        const void* images, const float* d_bias, const float* d_ln_w, const float* d_ln_b, float eps,
-                       float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace, cudaStream_t stream);
+                       float* d_out, void* d_out16, float* d_out16_scale, void* d_workspace, cudaStream_t stream,
+                       int phase_lo = 0, int phase_hi = -1);
 
 // gradients of the generated relation tensors on tcgen05 (mp_wgrad_f16.cu, hidden_dim 128): g_W_msg[r] / g_W_self[r] /
 // g_bias[r] += sums over the edges of r (buffers zero at entry); h16 / g16 are fp16 shadows with their scale words.

@@ -290,6 +290,37 @@ def test_c_abi_host_forward_matches():
     assert_close(out.numpy(), case["taps"]["out"], 1e-4, 2e-5, "host forward")
 
 
+@pytest.mark.parametrize("precision,d", [("f16", 128), ("fp32", 32), ("f16", 64)])
+def test_host_forward_sends_the_last_layer_in_pieces(precision, d, monkeypatch):
+    """ghf_hypergnn_forward_host runs the last layer in pieces of super-blocks and copies each piece's rows to the
+    host while the next one is computed: with many small super-blocks (GHF_SB_NODES) every piece boundary and the
+    ragged last super-block are exercised; the result must equal the device entry's, row for row."""
+    from graph_hypernetwork_forge import HyperGNN, _native, _text
+    N, E, R, L, T, F = 20_011, 150_000, 13, 2, 16, 24
+    rng = np.random.default_rng(d)
+    ei = torch.from_numpy(rng.integers(0, N, (2, E)))
+    texts = [f"relation/{int(r)}" for r in rng.integers(0, R, E)]
+    data, off = _text.pack_utf8(texts)
+    x = torch.from_numpy(rng.standard_normal((N, F)).astype(np.float32))
+    torch.manual_seed(d)
+    model = HyperGNN(T, F, d, L, precision=precision).eval().to(DEV)
+    monkeypatch.setenv("GHF_SB_NODES", "1024")                   # 20 super-blocks -> 4 pieces of 5
+    utf8, offsets = torch.from_numpy(data.copy()), torch.from_numpy(off.copy())
+    with torch.no_grad():
+        want = model.forward_packed(x.to(DEV), ei.to(DEV), utf8.to(DEV), offsets.to(DEV)).cpu()
+    desc = _native.ModelDesc(T, F, d, L, 32, max(64, 2 * T), 2, _native.precision_code(precision), 1e-5)
+    out = torch.full((N, d), float("nan")).pin_memory()
+    _native.forward_host(desc, model.flat_parameters(), x.pin_memory(), ei.pin_memory(), utf8, offsets, out,
+                         torch.device(DEV))
+    assert not torch.isnan(out).any(), "rows never copied back"
+    assert_close(out.numpy(), want.numpy(), 1e-4, 1e-4, f"host forward in pieces vs device entry ({precision}, d={d})")
+    monkeypatch.setenv("GHF_NO_OUTPUT_PIPE", "1")                # the plain whole-layer path still works
+    out2 = torch.full((N, d), float("nan")).pin_memory()
+    _native.forward_host(desc, model.flat_parameters(), x.pin_memory(), ei.pin_memory(), utf8, offsets, out2,
+                         torch.device(DEV))
+    assert_close(out2.numpy(), want.numpy(), 1e-4, 1e-4, f"host forward, one piece ({precision}, d={d})")
+
+
 def test_message_passing_reference_signature():
     """_message_passing(h, edge_index, rel_weights) with per-edge weights, as the reference exposes it."""
     from graph_hypernetwork_forge import HyperGNN
