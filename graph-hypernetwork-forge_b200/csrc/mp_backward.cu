@@ -117,6 +117,78 @@ mp_epilogue_bwd_kernel(const float* __restrict__ g_out, const float* __restrict_
   }
 }
 
+// Any hidden_dim beyond 32 * kBwdMaxV: the row lives in shared memory instead of registers (one warp per row, four
+// warps per CTA: 8 d floats of row buffers + 2 d of LayerNorm-gradient partials), four passes over it.
+__global__ void __launch_bounds__(128)
+mp_epilogue_bwd_big_kernel(const float* __restrict__ g_out, const float* __restrict__ upd,
+                           const int32_t* __restrict__ indeg, const float* __restrict__ h, int64_t dst_lo,
+                           int64_t num_local, int d, const float* __restrict__ ln_w, float eps,
+                           float* __restrict__ g_pre, float* __restrict__ g_acc, float* __restrict__ g_lnw,
+                           float* __restrict__ g_lnb, const DropoutArgs da) {
+  extern __shared__ float sm[];  // red[2][d] | per warp: x[d], gy[d]
+  float* red = sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* xs = sm + 2 * d + (size_t)warp * 2 * d;
+  float* gys = xs + d;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) red[c] = 0.f;
+  __syncthreads();
+  const float inv_d = 1.f / (float)d;
+  for (int64_t v = w0; v < num_local; v += warps) {
+    const float inv_cnt = 1.f / (float)max(indeg[v], 1);
+    const float* up = upd + v * d;
+    const float* hv = h + (dst_lo + v) * d;
+    const float* go = g_out + v * d;
+    const uint64_t e_row = (uint64_t)(dst_lo + v) * (uint64_t)d;
+    float sum = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      float x = fmaxf(up[c] + hv[c], 0.f);
+      if (da.keep > 0.f) x *= fuse::dropout_mult1(da, e_row + c);   // what the LayerNorm saw
+      xs[c] = x;
+      gys[c] = go[c];
+      sum += x;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    const float mean = sum * inv_d;
+    float var = 0.f;
+    for (int c = lane; c < d; c += 32) var += (xs[c] - mean) * (xs[c] - mean);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+    const float rstd = rsqrtf(var * inv_d + eps);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float xh = (xs[c] - mean) * rstd, gh = gys[c] * ln_w[c];
+      s1 += gh;
+      s2 += gh * xh;
+      atomicAdd(&red[c], gys[c] * xh);
+      atomicAdd(&red[d + c], gys[c]);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, s);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, s);
+    }
+    s1 *= inv_d;
+    s2 *= inv_d;
+    for (int c = lane; c < d; c += 32) {
+      const float xh = (xs[c] - mean) * rstd;
+      float gx = rstd * (gys[c] * ln_w[c] - s1 - xh * s2);
+      if (da.keep > 0.f) gx *= fuse::dropout_mult1(da, e_row + c);
+      const float gp = xs[c] > 0.f ? gx : 0.f;
+      g_pre[v * d + c] = gp;
+      g_acc[v * d + c] = gp * inv_cnt;
+    }
+    __syncwarp();                                        // the row buffers are reused by this warp's next row
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    atomicAdd(&g_lnw[c], red[c]);
+    atomicAdd(&g_lnb[c], red[d + c]);
+  }
+}
+
 // The same for hidden_dim 32 / 64 / 128: a lane owns D/32 CONSECUTIVE columns (one vector access per row and
 // operand), four rows in flight per warp; optionally max |g_acc| for the fp16 shadow the next kernels gather from.
 template <int D, bool DROP>
@@ -308,7 +380,6 @@ static int epilogue_backward_impl(const ghf_graph* g, const float* d_g_out, cons
   cudaStream_t stream = (cudaStream_t)stream_;
   GHF_REQUIRE(g != nullptr, "ghf_mp_epilogue_backward: graph is NULL");
   const int d = g->hidden_dim;
-  GHF_REQUIRE(d <= 32 * kBwdMaxV, "ghf_mp_epilogue_backward: hidden_dim %d > %d", d, 32 * kBwdMaxV);
   GHF_REQUIRE(d_g_out && d_upd && d_h && d_ln_w && d_g_pre && d_g_acc && d_g_ln_w && d_g_ln_b,
               "ghf_mp_epilogue_backward: NULL argument");
   GHF_CUDA(cudaMemsetAsync(d_g_ln_w, 0, d * sizeof(float), stream));
@@ -329,7 +400,18 @@ static int epilogue_backward_impl(const ghf_graph* g, const float* d_g_out, cons
   if (aligned && d == 128) { if (drop) GHF_BWD_VEC(128, true); else GHF_BWD_VEC(128, false); }
   else if (aligned && d == 64) { if (drop) GHF_BWD_VEC(64, true); else GHF_BWD_VEC(64, false); }
   else if (aligned && d == 32) { if (drop) GHF_BWD_VEC(32, true); else GHF_BWD_VEC(32, false); }
-  else {
+  else if (d > 32 * kBwdMaxV) {                          // the row does not fit in registers: shared-memory variant
+    GHF_REQUIRE(d_g_acc_scale == nullptr, "ghf_mp_epilogue_backward: max|g_acc| needs hidden_dim 32/64/128");
+    const size_t smem = (size_t)(2 + 2 * 4) * d * sizeof(float);
+    GHF_REQUIRE(smem <= 200 * 1024, "ghf_mp_epilogue_backward: hidden_dim %d needs %zu bytes of shared memory", d, smem);
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured))
+      GHF_CUDA(cudaFuncSetAttribute(mp_epilogue_bwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const int64_t want_big = cdiv(g->num_local, 4);
+    mp_epilogue_bwd_big_kernel<<<(unsigned)(want_big < cap ? want_big : cap), 128, smem, stream>>>(
+        d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local, d, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b,
+        da);
+  } else {
     GHF_REQUIRE(d_g_acc_scale == nullptr, "ghf_mp_epilogue_backward: max|g_acc| needs hidden_dim 32/64/128");
     mp_epilogue_bwd_kernel<<<grid, 256, 2 * d * sizeof(float), stream>>>(
         d_g_out, d_upd, g->indeg, d_h, g->dst_lo, g->num_local, d, d_ln_w, eps, d_g_pre, d_g_acc, d_g_ln_w, d_g_ln_b,

@@ -204,7 +204,8 @@ int ghf_mp_contract(const ghf_graph* g, const float* d_x, const void* d_x16, con
 /* Undo LayerNorm, ReLU and the mean (HG:212-213, 289-296) for rows [dst_lo, dst_hi): from d_g_out = dL/d out,
  * the saved pre-residual update d_upd (ghf_mp_layer's tap) and d_h:
  *   d_g_pre = dL/d(upd + h)  (also the residual's share of dL/dh),  d_g_acc = d_g_pre / max(indeg, 1),
- *   d_g_ln_w[d], d_g_ln_b[d] = LayerNorm parameter gradients (overwritten).  hidden_dim <= 256.
+ *   d_g_ln_w[d], d_g_ln_b[d] = LayerNorm parameter gradients (overwritten).  Any hidden_dim (rows beyond 256
+ *   columns are staged in shared memory).
  *   d_g_acc_scale (float[2], optional, hidden_dim 32/64/128): [1] = max |g_acc|, ready for ghf_convert_f16 with
  *   have_amax = 1 - the fp16 shadow of g_acc the gradient contractions gather from. */
 int ghf_mp_epilogue_backward(const ghf_graph* g, const float* d_g_out, const float* d_upd, const float* d_h,

@@ -82,6 +82,48 @@ def test_medium_graph_against_float64_oracle(precision, tol):
         assert_rel_to_max(p.grad.cpu().numpy(), params[k].grad.cpu().numpy(), tol, f"grad {k}")
 
 
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_wide_hidden_dim_trains(dropout):
+    """hidden_dim 288 (> 256: the epilogue gradient stages rows in shared memory instead of registers), fp32 engine,
+    against float64 autograd of the torch oracle - with and without training-mode dropout (same seed, same stream)."""
+    from graph_hypernetwork_forge import HyperGNN
+    from oracle import hypergnn_torch as OT
+    N, E, R, d, L, T, F = 700, 6000, 5, 288, 2, 16, 20
+    g = torch.Generator(device=DEV).manual_seed(288)
+    ei = torch.randint(0, N, (2, E), generator=g, device=DEV)
+    rel = torch.randint(0, R, (E,), generator=g, device=DEV)
+    x = torch.randn(N, F, generator=g, device=DEV)
+    loss_w = torch.randn(N, d, generator=g, device=DEV)
+    names = [f"wide_{r}" for r in range(R)]
+    torch.manual_seed(288)
+    model = HyperGNN(T, F, d, L, dropout=dropout, precision="fp32")
+    with torch.no_grad():
+        for gen in model.weight_generators:
+            for q in gen.log_scales.values():
+                q.fill_(-2.0)
+    model = model.to(DEV).train()
+    prepared = model.prepare_ids(ei, rel, names, N)
+    xg = x.clone().requires_grad_(True)
+    torch.manual_seed(4321)
+    out = model.forward_prepared(xg, prepared)
+    (out * loss_w).sum().backward()
+    if dropout:
+        # dropout: float32 oracle on the device (F.dropout has no float64 stream of its own to compare masks with)
+        params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        xr, lw, tol = x.clone().requires_grad_(True), loss_w, 1e-3
+    else:
+        params = {k: v.detach().double().requires_grad_(True) for k, v in model.state_dict().items()}
+        xr, lw, tol = x.double().requires_grad_(True), loss_w.double(), FP32_GRAD_REL
+    torch.manual_seed(4321)
+    ref = OT.hypergnn_forward(params, xr, ei, rel, names, d, L, dropout=dropout)
+    (ref * lw).sum().backward()
+    assert_rel_to_max(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), 1e-4, "out, hidden 288")
+    assert_rel_to_max(xg.grad.cpu().numpy(), xr.grad.cpu().numpy(), tol, "grad node_features, hidden 288")
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert_rel_to_max(p.grad.cpu().numpy(), params[k].grad.cpu().numpy(), tol, f"grad {k}, hidden 288")
+
+
 # ---- the reference's training tests, on CUDA tensors (tests/test_hypergnn.py:183-226) ----
 @pytest.fixture
 def toy_kg():
