@@ -191,3 +191,44 @@ def test_list_collapse_in_c_equals_the_numpy_formulation():
     many = [str(i) for i in range(5000)]                 # every element its own object: the table grows
     objs_m, map_m = _text.collapse_by_identity(many)
     assert objs_m == many and np.array_equal(map_m, np.arange(5000))
+
+
+def test_presync_wrapper_runs_the_hook_exactly_once_on_the_host_side():
+    """`_call_with_presync`: when the native entry point never reaches its wait (here: a stand-in call that does not
+    touch the device) the hook still runs, once, after the call; nothing stays registered in the library."""
+    from graph_hypernetwork_forge import _native
+    ran = []
+    assert _native._call_with_presync(lambda: "result", lambda: ran.append(1)) == "result"
+    assert ran == [1]
+    assert _native._call_with_presync(lambda: 7, None) == 7          # no hook: a plain call
+
+    def failing_call():
+        raise RuntimeError("native failure")
+    with pytest.raises(RuntimeError, match="native failure"):
+        _native._call_with_presync(failing_call, lambda: ran.append(2))
+    assert ran == [1]                                                # the entry failed: its hook is not run afterwards
+    # an edge-less selection returns before any device call: loadable and callable without a GPU
+    n = ctypes.c_int64(-1)
+    rc = _native.lib().ghf_select_edges(None, 0, 0, 10, None, ctypes.byref(n), None)
+    assert rc == 0 and n.value == 0
+
+
+def test_dropout_stream_restatement_is_pinned_to_philox_known_answers():
+    """tools/dropout_stream_probe.py restates torch's dropout counters with a numpy Philox4x32-10; the generator is
+    held to the published known-answer vectors of Philox4x32-10 (Random123 kat_vectors) here, on the CPU."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dropout_probe", os.path.join(ROOT, "tools", "dropout_stream_probe.py"))
+    probe = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(probe)
+    u64 = lambda v: np.array([v], dtype=np.uint64)   # noqa: E731
+    kat = [((0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffffffffffff, 0xffffffffffffffff, 0xffffffffffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd))]
+    for (seed, ctr, sub), want in kat:
+        got = probe.philox(seed, u64(ctr), u64(sub))[:, 0]
+        assert tuple(int(x) for x in got) == want
+    # the mapping of elements to (thread, step, component) used by the kernel (mp_fuse.cuh: dropout_mult4)
+    keep, adv = probe.predicted_keep(4096, 0.25, 1234, 8, sms=148, max_threads_per_sm=2048)
+    assert keep.shape == (4096,) and adv == 4 and 0.70 < keep.mean() < 0.80
+    from graph_hypernetwork_forge import _native
+    assert _native.DropoutState.supported(4096) and not _native.DropoutState.supported(4097)
+    assert not _native.DropoutState.supported(0)
