@@ -697,9 +697,17 @@ class Graph:
         `accumulate` they are added to `out`.  PREC_F16 at hidden 128 only: `transposed` uses W[r]^T, and W_msg,
         W_self or bias may be None (zeros; the rows of an absent half are not even gathered)."""
         dev, d = self.device, self.hidden_dim
-        x = _f32(x)
-        if x.shape != (self.num_nodes, d):
-            raise RuntimeError(f"x must be [{self.num_nodes},{d}], got {tuple(x.shape)}")
+        if x is None:                                        # PREC_F16 with a shadow: the fp32 rows are never read
+            if x16 is None or precision != PREC_F16:
+                raise RuntimeError("contract: x may be omitted only with precision f16 and its fp16 shadow x16")
+            x_ptr = _ptr(x16.data)                           # any valid pointer
+        else:
+            x = _f32(x)
+            if x.shape != (self.num_nodes, d):
+                raise RuntimeError(f"x must be [{self.num_nodes},{d}], got {tuple(x.shape)}")
+            x_ptr = _ptr(x)
+        if x16 is not None and (not isinstance(x16, Shadow) or x16.data.shape != (self.num_nodes, d)):
+            raise RuntimeError(f"x16 must be a Shadow of a [{self.num_nodes},{d}] matrix")
         W_msg, W_self, bias = (None if t is None else _f32(t) for t in (W_msg, W_self, bias))
         for t, shape in ((W_msg, (self.num_rel, d, d)), (W_self, (self.num_rel, d, d)), (bias, (self.num_rel, d))):
             if t is not None and t.shape != shape:
@@ -712,30 +720,45 @@ class Graph:
             raise RuntimeError("contract: out must be a contiguous float32 [local nodes, d] tensor")
         ws = self.workspace(precision)
         with torch.cuda.device(dev):
-            _check(lib().ghf_mp_contract(self._h, _ptr(x), _ptr(x16.data) if x16 else None,
+            _check(lib().ghf_mp_contract(self._h, x_ptr, _ptr(x16.data) if x16 else None,
                                          _ptr(x16.scale) if x16 else None, _ptr(W_msg), _ptr(W_self), _ptr(bias),
                                          precision, _ptr(out), int(accumulate), int(transposed), _ptr(ws),
                                          _stream(dev)), "ghf_mp_contract")
         return out
 
-    def epilogue_backward(self, g_out, upd, h, ln_w, eps: float, want_shadow: bool = False, dropout=None):
+    def epilogue_backward(self, g_out, upd, h, ln_w, eps: float, want_shadow: bool = False, dropout=None,
+                          h_row0=None, shadow_out=None):
         """-> (g_pre, g_acc, g_ln_w, g_ln_b, Shadow of g_acc or None); see ghf_mp_epilogue_backward.  `dropout`: the
-        DropoutState of the forward call (the mask is regenerated from it)."""
+        DropoutState of the forward call (the mask is regenerated from it).  `h_row0`: `h` holds only the rows
+        [h_row0, h_row0 + len(h)) of the features (they are read at this graph's own destinations only).
+        `shadow_out` (a Shadow of [local nodes, d], e.g. the local rows of a full table): receives the shadow of g_acc."""
         dev, d = self.device, self.hidden_dim
         g_out, upd, h, ln_w = _f32(g_out), _f32(upd), _f32(h), _f32(ln_w)
-        if g_out.shape != (self.num_local, d) or upd.shape != g_out.shape or h.shape != (self.num_nodes, d):
+        if g_out.shape != (self.num_local, d) or upd.shape != g_out.shape:
+            raise RuntimeError("epilogue_backward: shape mismatch")
+        h_ptr = _ptr(h)
+        if h_row0 is not None:
+            if h.dim() != 2 or h.shape[1] != d or h_row0 > self.dst_lo or h_row0 + h.shape[0] < self.dst_hi:
+                raise RuntimeError(f"h rows [{h_row0},{h_row0 + h.shape[0]}) must cover [{self.dst_lo},{self.dst_hi})")
+            h_ptr = c_void_p(h.data_ptr() - int(h_row0) * d * 4)
+        elif h.shape != (self.num_nodes, d):
             raise RuntimeError("epilogue_backward: shape mismatch")
         g_pre, g_acc = torch.empty_like(g_out), torch.empty_like(g_out)
         g_w, g_b = torch.empty_like(ln_w), torch.empty_like(ln_w)
-        g16 = Shadow(torch.empty(g_acc.shape, dtype=torch.float16, device=dev)) if want_shadow else None
+        if shadow_out is not None:
+            if not isinstance(shadow_out, Shadow) or shadow_out.data.shape != g_acc.shape:
+                raise RuntimeError("epilogue_backward: shadow_out must shadow a [local nodes, d] matrix")
+            g16 = shadow_out
+        else:
+            g16 = Shadow(torch.empty(g_acc.shape, dtype=torch.float16, device=dev)) if want_shadow else None
         with torch.cuda.device(dev):
             if dropout is not None:
                 _check(lib().ghf_mp_epilogue_backward_dropout(
-                    self._h, _ptr(g_out), _ptr(upd), _ptr(h), _ptr(ln_w), float(eps), dropout.p, dropout.seed,
+                    self._h, _ptr(g_out), _ptr(upd), h_ptr, _ptr(ln_w), float(eps), dropout.p, dropout.seed,
                     dropout.offset, _ptr(g_pre), _ptr(g_acc), _ptr(g_w), _ptr(g_b), _ptr(g16.scale) if g16 else None,
                     _stream(dev)), "ghf_mp_epilogue_backward_dropout")
             else:
-                _check(lib().ghf_mp_epilogue_backward(self._h, _ptr(g_out), _ptr(upd), _ptr(h), _ptr(ln_w),
+                _check(lib().ghf_mp_epilogue_backward(self._h, _ptr(g_out), _ptr(upd), h_ptr, _ptr(ln_w),
                                                       float(eps), _ptr(g_pre), _ptr(g_acc), _ptr(g_w), _ptr(g_b),
                                                       _ptr(g16.scale) if g16 else None, _stream(dev)),
                        "ghf_mp_epilogue_backward")
@@ -746,8 +769,16 @@ class Graph:
     def weight_grad(self, h, g_acc, precision: int, h16=None, g16=None):
         """-> (g_W_msg [R,d,d], g_W_self [R,d,d], g_bias [R,d]); see ghf_mp_weight_grad."""
         dev, d = self.device, self.hidden_dim
-        h, g_acc = _f32(h), _f32(g_acc)
-        if h.shape != (self.num_nodes, d) or g_acc.shape != (self.num_local, d):
+        g_acc = _f32(g_acc)
+        if h is None:                                        # PREC_F16 with shadows: the fp32 rows are never read
+            if h16 is None or precision != PREC_F16:
+                raise RuntimeError("weight_grad: h may be omitted only with precision f16 and its fp16 shadow h16")
+            h = h16.data
+        else:
+            h = _f32(h)
+            if h.shape != (self.num_nodes, d):
+                raise RuntimeError("weight_grad: shape mismatch")
+        if g_acc.shape != (self.num_local, d):
             raise RuntimeError("weight_grad: shape mismatch")
         gm = torch.empty((self.num_rel, d, d), dtype=torch.float32, device=dev)
         gs = torch.empty_like(gm)

@@ -152,6 +152,65 @@ class _SymmetricRows:
         torch.cuda.current_stream(self.device).wait_event(done)
 
 
+class _ShardedLayerFn(torch.autograd.Function):
+    """One message-passing layer of a rank (f16 engine, hidden 128) with its gradients.
+
+    Forward: `ghf_mp_layer_f16` on the rank's graph - fp32 rows `h_local` of the own range (residual), the fp16 table
+    `h16` of ALL rows (gather source; a non-differentiable carrier: every rank holds the same values).  Backward, given
+    dL/d out for the own rows: the epilogue gradient and the self-loop term are local; the weight gradients are this
+    rank's share (summed over ranks at the end, `ShardedForward.allreduce_gradients`); the message term
+    `g_acc_v W_msg[r]^T` lands on the SOURCE u of every edge (u -> v) with v in the own range - any row of the graph -
+    so it is contracted over the rank's reversed edges into a partial [N, d] and summed across ranks, each owner
+    keeping its rows (reduce-scatter; the one collective of a layer's backward)."""
+
+    @staticmethod
+    def forward(ctx, h_local, W_msg, W_self, bias, ln_w, ln_b, sf, graph, rev_graph, eps, h16, out16):
+        from . import _native
+        out, upd = graph.mp_layer(h_local, W_msg, W_self, bias, ln_w, ln_b, eps, _native.PREC_F16, want_upd=True,
+                                  h16=h16, out16=out16, h_row0=sf.lo)
+        ctx.sf, ctx.graph, ctx.rev_graph, ctx.eps, ctx.h16 = sf, graph, rev_graph, eps, h16
+        ctx.save_for_backward(h_local, W_msg, W_self, ln_w, upd)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        from . import _native
+        h_local, W_msg, W_self, ln_w, upd = ctx.saved_tensors
+        sf, graph, rev, prec = ctx.sf, ctx.graph, ctx.rev_graph, _native.PREC_F16
+        N, d, lo, hi = sf.num_nodes, graph.hidden_dim, sf.lo, sf.hi
+        dev = g_out.device
+        # fp16 table of g_acc over ALL rows; only the own rows are ever read (destinations of the own edges, sources
+        # of the reversed ones), so the rest stays unwritten
+        g16 = _native.Shadow(torch.empty((N, d), dtype=torch.float16, device=dev))
+        g_pre, g_acc, g_ln_w, g_ln_b, _ = graph.epilogue_backward(g_out.contiguous(), upd, h_local, ln_w, ctx.eps,
+                                                                  h_row0=lo, shadow_out=g16.rows(lo, hi))
+        needs = ctx.needs_input_grad
+        g_wm = g_ws = g_b = None
+        if any(needs[1:4]):
+            g_wm, g_ws, g_b = graph.weight_grad(None, g_acc, prec, h16=ctx.h16, g16=g16.rows(lo, hi))
+        g_h = None
+        if needs[0]:
+            # self-loop term: stays at the own rows, added to the residual's share
+            graph.contract(None, None, W_self, None, prec, x16=g16, out=g_pre, accumulate=True, transposed=True)
+            # message term: partial sums for every row of the graph from the own (reversed) edges ...
+            partial = rev.contract(None, W_msg, None, None, prec, x16=g16, transposed=True)
+            # ... summed over ranks; each owner keeps its rows
+            g_h = g_pre
+            if sf.world > 1:
+                equal = all(b - a == sf.rows for a, b in sf.ranges) and sf.rows * sf.world == N
+                if equal and dev.type == "cuda":
+                    mine = torch.empty((hi - lo, d), dtype=partial.dtype, device=dev)
+                    dist.reduce_scatter_tensor(mine, partial, group=sf.group)
+                    g_h += mine
+                else:
+                    dist.all_reduce(partial, group=sf.group)
+                    g_h += partial[lo:hi]
+            else:
+                g_h += partial[lo:hi]
+        return g_h, g_wm, g_ws, g_b, g_ln_w, g_ln_b, None, None, None, None, None, None
+
+
 class ShardedForward:
     """HyperGNN forward over a destination-partitioned graph (one instance per rank).
 
@@ -267,6 +326,12 @@ class ShardedForward:
         m = self.model
         self._mark("start")
         device = _native.require_cuda(edge_index, utf8, offsets, m.input_proj.weight)
+        if m._wants_grad(node_features):                 # training: the autograd path (no overlap tricks)
+            subset = None
+            if (self.lo, self.hi) != (0, self.num_nodes):
+                subset = _native.select_edges(edge_index, self.lo, self.hi)
+            return self._run_autograd(node_features, edge_index, PackedTexts(None, device, utf8, offsets, subset),
+                                      gather_output)
         box = {}
 
         def start_h0():                                  # the rows travel while edge selection and graph build run
@@ -297,8 +362,10 @@ class ShardedForward:
         if edge_index.size(1) != len(edge_texts):
             raise ValueError(f"edge_index has {edge_index.size(1)} edges but edge_texts has {len(edge_texts)} entries")
         self._mark("start")
-        started = self._start_h0(node_features)
         device = _native.require_cuda(edge_index, self.model.input_proj.weight)
+        if self.model._wants_grad(node_features):
+            return self._run_autograd(node_features, edge_index, PackedTexts(edge_texts, device), gather_output)
+        started = self._start_h0(node_features)
         packed = PackedTexts(edge_texts, device)
         return self._run(node_features, edge_index, packed, started, gather_output)
 
@@ -311,8 +378,11 @@ class ShardedForward:
         if edge_index.size(1) != rel_ids.numel():
             raise ValueError(f"edge_index has {edge_index.size(1)} edges but rel_ids has {rel_ids.numel()} entries")
         self._mark("start")
-        started = self._start_h0(node_features)
         device = _native.require_cuda(edge_index, self.model.input_proj.weight)
+        if self.model._wants_grad(node_features):
+            return self._run_autograd(node_features, edge_index, RelationIds(rel_ids, unique_texts, device),
+                                      gather_output)
+        started = self._start_h0(node_features)
         packed = RelationIds(rel_ids, unique_texts, device)
         return self._run(node_features, edge_index, packed, started, gather_output)
 
@@ -331,7 +401,7 @@ class ShardedForward:
         from . import _native
         m = self.model
         if m.training and m.dropout > 0.0:
-            raise NotImplementedError("the multi-GPU path is inference-only (no dropout, no gradients)")
+            raise NotImplementedError("the multi-GPU path has no dropout")
         hook = None
         if started is not None:
             # text encoder + the generators of every layer need only the dedup result.  They are enqueued (on the side
@@ -349,6 +419,57 @@ class ShardedForward:
         if started is not None and self._sym is not None and self.world > 1 and "push" not in started:
             self._decide_push(started, graph.num_kept, graph.num_phases, edge_index, packed.subset)
         return self._layers(node_features, graph, packed, started, gather_output)
+
+    def _run_autograd(self, node_features, edge_index, packed, gather_output):
+        """The sharded forward with the autograd graph recorded (f16 engine, hidden 128): `loss.backward()` on a loss
+        over the rank's own rows leaves this rank's SHARE of every parameter gradient in `.grad`;
+        `allreduce_gradients()` sums the shares.  Layers exchange fp16 rows over the collective transport (training
+        keeps one fp16 table per layer for the backward instead of the two ping-pong tables of inference)."""
+        from . import _native, autograd
+        m = self.model
+        N, d, lo, hi = self.num_nodes, m.hidden_dim, self.lo, self.hi
+        if m.training and m.dropout > 0.0:
+            raise NotImplementedError("the multi-GPU path has no dropout")
+        if m._precision_code() != _native.PREC_F16 or d != 128:
+            raise NotImplementedError("gradients on the multi-GPU path need the f16 engine at hidden_dim 128")
+        if gather_output:
+            raise NotImplementedError("gradients on the multi-GPU path: the loss is taken over the rank's own rows")
+        device = node_features.device
+        graph = _native.Graph(edge_index, packed.rel_ids, N, max(packed.num_unique, 1), d, dst_lo=lo, dst_hi=hi,
+                              edge_ids=packed.subset)
+        # the rank's edges reversed (destination = the original source, any row of the graph): the graph the message
+        # term of dL/dh is contracted over
+        ei_own = edge_index if packed.subset is None else edge_index[:, packed.subset.long()]
+        rev = _native.Graph(ei_own.flip(0).contiguous(), packed.rel_ids, N, max(packed.num_unique, 1), d)
+        x_local = self._local_rows(node_features)
+        h = autograd.linear(x_local, m.input_proj.weight, m.input_proj.bias, relu=True)
+        text_embs = m.text_encoder.encode_packed(packed)
+        rows_pad = max(self.rows * self.world, N, 1)
+        for l in range(m.num_layers):
+            # fp16 table of h_l: own rows converted with a scale all ranks agree on, then exchanged
+            table = torch.zeros((rows_pad, d), dtype=torch.float16, device=device)
+            h16 = _native.Shadow(table[:N], torch.zeros(2, dtype=torch.float32, device=device))
+            with torch.no_grad():
+                if hi > lo:
+                    _native.absmax(h.detach(), h16)
+                dist.all_reduce(h16.scale[1:2], op=dist.ReduceOp.MAX, group=self.group)
+                _native.to_f16(h.detach(), h16.rows(lo, hi), have_amax=True)
+                exchange_rows(table, self.ranges, self.rank, self.group)
+            w = m._generate(l, text_embs, packed.num_unique)
+            ln = m.layer_norms[l]
+            h = _ShardedLayerFn.apply(h, w["W_msg"], w["W_self"], w["bias"], ln.weight, ln.bias, self, graph, rev,
+                                      ln.eps, h16, None)
+        self.num_kept = graph.num_kept
+        return h
+
+    def allreduce_gradients(self) -> None:
+        """Sum every parameter's `.grad` over the ranks (each rank's backward leaves its share; parameters a rank's
+        graph never touched contribute zeros)."""
+        for p in self.model.parameters():
+            if p.requires_grad:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                dist.all_reduce(p.grad, group=self.group)
 
     def _decide_push(self, started, num_kept: int, num_phases: int, edge_index, subset) -> None:
         """Pick the push mode of this forward (once) and, for "kernel", exchange the read masks."""

@@ -17,3 +17,13 @@ def test_sharded_forward_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "check_sharded.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_gradients_match_single_gpu():
+    """loss.backward() through the destination-partitioned forward + allreduce_gradients() against the single-GPU
+    model: every parameter gradient and the node-feature gradient (tools/check_sharded_grad.py)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29518", os.path.join(ROOT, "tools", "check_sharded_grad.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
