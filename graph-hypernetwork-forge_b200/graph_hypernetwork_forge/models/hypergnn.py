@@ -27,6 +27,9 @@ from .. import _native, _text, autograd
 from .weight_generator import WeightGenerator
 
 
+_SIDE_STREAMS = {}   # device -> side stream of forward_prepared (the generators run beside the input projection)
+
+
 def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
     arr = np.ascontiguousarray(arr)
     t = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
@@ -246,17 +249,35 @@ class HyperGNN(nn.Module):
         with torch.no_grad():
             h16 = None   # fp16 shadow of h, chained from layer to layer on the f16 path
             chain = prec == _native.PREC_F16 and self.hidden_dim in (64, 128)   # shadows chained layer to layer
+            # The text encoder and the generators of every layer depend on the relation texts only: on a side stream
+            # they run beside the input projection instead of between it and the first layer (as in the one-call
+            # native forward).  Forked from and joined back into the current stream, so CUDA-graph capture sees one graph.
+            dev = node_features.device
+            main = torch.cuda.current_stream(dev)
+            side = None
+            if taps is None and not os.environ.get("GHF_NO_SIDE_GENERATORS"):
+                side = _SIDE_STREAMS.get(dev)
+                if side is None:
+                    side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+                side.wait_stream(main)
+            with torch.cuda.stream(side if side is not None else main):
+                text_embs = self.text_encoder.encode_packed(packed)
+                fuse = taps is None and self._can_fuse_generator(prec, packed.num_unique, text_embs)
+                all_w = None if fuse else self._generate_all(text_embs, packed.num_unique)
             if chain:
                 h, h16 = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True,
                                         want_f16=True)
             else:
                 h = _native.linear(node_features, self.input_proj.weight, self.input_proj.bias, relu=True)
-            text_embs = self.text_encoder.encode_packed(packed)
+            if side is not None:
+                main.wait_stream(side)
+                text_embs.record_stream(main)                # allocated on the side stream, consumed on this one
+                for w in all_w or ():
+                    for t in w.values():
+                        t.record_stream(main)
             if taps is not None:
                 taps["edge_rel_ids"], taps["text_embs"], taps["h0"] = packed.rel_ids, text_embs, h
                 taps["in_degree"] = graph.export()["indeg"]
-            fuse = taps is None and self._can_fuse_generator(prec, packed.num_unique, text_embs)
-            all_w = None if fuse else self._generate_all(text_embs, packed.num_unique)
             for l in range(self.num_layers):
                 ln = self.layer_norms[l]
                 out16 = None
