@@ -53,20 +53,27 @@ def _pyhost_lib():
             lib = ctypes.PyDLL(path)
             lib.ghf_collapse_pylist.restype = ctypes.c_int64
             lib.ghf_collapse_pylist.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+            lib.ghf_collapse_pylist_mt.restype = ctypes.c_int64
+            lib.ghf_collapse_pylist_mt.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                   ctypes.c_int]
             _pyhost = lib
         except OSError:
             _pyhost = False
     return _pyhost or None
 
 
-def collapse_by_identity(texts: List[str]):
-    """-> (distinct objects in first-occurrence order, int32 map edge -> position in that list)."""
+def collapse_by_identity(texts: List[str], out: np.ndarray = None, threads: int = 0):
+    """-> (distinct objects in first-occurrence order, int32 map edge -> position in that list).
+    `out`: int32 [len(texts)] buffer for the map (e.g. pinned memory, so that it goes to the device without another
+    host copy); `threads`: worker threads of the C pass (0 = one per 1M entries, at most 16)."""
     n = len(texts)
     lib = _pyhost_lib() if type(texts) is list else None
+    if out is not None and (out.dtype != np.int32 or out.shape != (n,) or not out.flags.c_contiguous):
+        raise ValueError("collapse_by_identity: out must be a contiguous int32 array with one entry per text")
     if lib is not None:
-        edge_map = np.empty(n, dtype=np.int32)
+        edge_map = np.empty(n, dtype=np.int32) if out is None else out
         first = np.empty(min(n, 1 << 22), dtype=np.int64)
-        k = int(lib.ghf_collapse_pylist(texts, edge_map.ctypes.data, first.ctypes.data, first.size))
+        k = int(lib.ghf_collapse_pylist_mt(texts, edge_map.ctypes.data, first.ctypes.data, first.size, int(threads)))
         if k >= 0:
             return [texts[i] for i in first[:k]], edge_map
     ids = np.fromiter(map(id, texts), dtype=np.int64, count=n)
@@ -75,18 +82,21 @@ def collapse_by_identity(texts: List[str]):
     rank = np.empty_like(order)
     rank[order] = np.arange(order.size)
     objs = [texts[i] for i in first[order]]
+    if out is not None:
+        out[:] = rank[inverse]
+        return objs, out
     return objs, rank[inverse].astype(np.int32)
 
 
-def pack_texts(texts: List[str]):
+def pack_texts(texts: List[str], edge_map_out: np.ndarray = None):
     """-> (utf8 bytes, offsets, edge_to_string or None).
 
     `edge_to_string[e]` indexes the packed strings; None means the identity map
-    (every edge has its own packed string).
+    (every edge has its own packed string).  `edge_map_out`: buffer for the map (see `collapse_by_identity`).
     """
     if len(texts) < _IDENTITY_THRESHOLD:
         data, offsets = pack_utf8(texts)
         return data, offsets, None
-    objs, edge_map = collapse_by_identity(texts)
+    objs, edge_map = collapse_by_identity(texts, out=edge_map_out)
     data, offsets = pack_utf8(objs)
     return data, offsets, edge_map

@@ -52,7 +52,14 @@ class PackedTexts:
             self.num_edges = offsets.numel() - 1
             self.utf8, self.offsets, edge_map = utf8.contiguous(), offsets.contiguous(), None
         else:
-            data, offs, edge_map = _text.pack_texts(texts)
+            # the edge -> distinct-object map is written straight into pinned memory: one copy to the device, no
+            # staging copy on the host (64 MB at 16M edges)
+            pinned = None
+            if len(texts) >= (1 << 16) and torch.device(device).type == "cuda":
+                pinned = torch.empty(len(texts), dtype=torch.int32, pin_memory=True)
+            data, offs, edge_map = _text.pack_texts(texts, None if pinned is None else pinned.numpy())
+            if edge_map is not None and pinned is not None:
+                edge_map = pinned                                     # (a tensor: _to_device below takes it as is)
             self.num_edges = len(texts)
             self.utf8 = _to_device(data, device) if data.size else torch.zeros(1, dtype=torch.uint8, device=device)
             self.offsets = _to_device(offs, device)
@@ -62,7 +69,11 @@ class PackedTexts:
         if edge_map is None:
             self.rel_ids = ids
         else:                                                       # edges -> packed strings -> relation ids
-            self.rel_ids = ids[_to_device(edge_map, device).long()].contiguous()
+            if isinstance(edge_map, torch.Tensor):
+                emap = edge_map.to(device, non_blocking=True)
+            else:
+                emap = _to_device(edge_map, device)
+            self.rel_ids = ids[emap.long()].contiguous()
 
 
 class RelationIds(PackedTexts):

@@ -193,6 +193,37 @@ def test_list_collapse_in_c_equals_the_numpy_formulation():
     assert objs_m == many and np.array_equal(map_m, np.arange(5000))
 
 
+@pytest.mark.parametrize("threads", [1, 2, 3, 7, 16])
+def test_threaded_list_collapse_equals_the_single_pass(threads):
+    """The multi-threaded walk (chunk-local ranks, merged in chunk order, rewritten to global ranks) gives exactly
+    the single-threaded result: objects that first appear in a late chunk, chunks with disjoint vocabularies,
+    every element its own object, an output buffer supplied by the caller."""
+    from graph_hypernetwork_forge import _text
+    if _text._pyhost_lib() is None:
+        pytest.skip("lib/libghf_pyhost.so not built")
+    rng = np.random.default_rng(threads)
+    names = [f"rel-{r}" for r in range(97)]
+    n = 40_001
+    ids = rng.integers(0, 60, n)
+    ids[n // 2:] = rng.integers(40, 97, n - n // 2)      # names 60..96 first appear in the second half
+    ids[n - 5] = 96
+    texts = [names[i] for i in ids]
+    objs_1, map_1 = _text.collapse_by_identity(texts, threads=1)
+    out = np.full(n, -1, dtype=np.int32)
+    objs_t, map_t = _text.collapse_by_identity(texts, out=out, threads=threads)
+    assert map_t is out and np.array_equal(map_t, map_1)
+    assert len(objs_t) == len(objs_1) and all(a is b for a, b in zip(objs_t, objs_1))
+    want = list(dict.fromkeys(texts))                    # the reference's own dedup (HG:264-265)
+    assert all(a is b for a, b in zip(objs_t, want)) and len(want) == len(objs_t)
+    assert all(texts[i] is objs_t[map_t[i]] for i in range(0, n, 997))
+    many = [str(i) for i in range(3000)]                 # every element its own object
+    objs_m, map_m = _text.collapse_by_identity(many, threads=threads)
+    assert objs_m == many and np.array_equal(map_m, np.arange(3000))
+    assert _text.collapse_by_identity([], threads=threads)[0] == []
+    with pytest.raises(ValueError):
+        _text.collapse_by_identity(texts, out=np.zeros(3, dtype=np.int32))
+
+
 def test_presync_wrapper_runs_the_hook_exactly_once_on_the_host_side():
     """`_call_with_presync`: when the native entry point never reaches its wait (here: a stand-in call that does not
     touch the device) the hook still runs, once, after the call; nothing stays registered in the library."""

@@ -7,6 +7,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "graph-hypernetwork-forge_b200")]
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 torch.set_grad_enabled(False)
@@ -43,4 +44,12 @@ print(f"forward_packed (strings packed on the device)      : {ms_packed:8.2f} ms
 print(f"model(x, edge_index, List[str]) - the drop-in call  : {ms_list:8.2f} ms   max|diff| {float((a - b).abs().max()):.2e}")
 print(f"  of which list -> distinct objects + edge map in C : {ms_c:8.2f} ms   ({len(objs)} distinct objects)")
 print(f"  (the numpy formulation it replaces                : {ms_np:8.2f} ms)")
+import os  # noqa: E402
+buf = np.zeros(len(texts), dtype=np.int32)
+for th in (1, 2, 4, 8, 16):
+    t = time.perf_counter()
+    for _ in range(3):
+        _text.collapse_by_identity(texts, out=buf, threads=th)
+    print(f"  C pass with {th:2d} thread(s) into a touched buffer       : {1e3 * (time.perf_counter() - t) / 3:8.2f} ms"
+          f"   ({os.cpu_count()} host cores)")
 print(f"  edge map host -> device: {emap.nbytes / 1e6:.0f} MB")
