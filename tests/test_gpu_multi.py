@@ -27,3 +27,20 @@ def test_sharded_gradients_match_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29518", os.path.join(ROOT, "tools", "check_sharded_grad.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _torchrun(script, nproc, port, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", script)]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+
+
+def test_sharded_paths_on_one_gpu_world_size_1():
+    """The same two checks with a world-size-1 process group on ONE GPU: no row crosses a link, but the whole host
+    side of `ShardedForward` runs - symmetric-memory tables, pre-sync hooks, range views of the graph, the autograd
+    layer with its reversed-edge contraction - so a 1-GPU box still exercises it (the 2-GPU tests above skip there)."""
+    r = _torchrun("check_sharded.py", 1, 29519)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = _torchrun("check_sharded_grad.py", 1, 29520)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "world 1" in r.stdout
