@@ -439,8 +439,14 @@ class ShardedForward:
                               edge_ids=packed.subset)
         # the rank's edges reversed (destination = the original source, any row of the graph): the graph the message
         # term of dL/dh is contracted over
-        ei_own = edge_index if packed.subset is None else edge_index[:, packed.subset.long()]
-        rev = _native.Graph(ei_own.flip(0).contiguous(), packed.rel_ids, N, max(packed.num_unique, 1), d)
+        if packed.subset is not None:                    # forward_packed: the selected edges, relation ids alike
+            ei_own, rel_own = edge_index[:, packed.subset.long()], packed.rel_ids
+        elif (lo, hi) != (0, N):                         # forward / forward_ids: one relation id per edge of the list
+            own = ((edge_index[1] >= lo) & (edge_index[1] < hi)).nonzero().squeeze(1)
+            ei_own, rel_own = edge_index[:, own], packed.rel_ids[own].contiguous()
+        else:
+            ei_own, rel_own = edge_index, packed.rel_ids
+        rev = _native.Graph(ei_own.flip(0).contiguous(), rel_own, N, max(packed.num_unique, 1), d)
         x_local = self._local_rows(node_features)
         h = autograd.linear(x_local, m.input_proj.weight, m.input_proj.bias, relu=True)
         text_embs = m.text_encoder.encode_packed(packed)

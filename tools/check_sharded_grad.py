@@ -22,7 +22,8 @@ dist.init_process_group("nccl", device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
 # N divisible by the world size (reduce-scatter of the message term) and not (all-reduce), node- and edge-balanced
-for N, balance in ((60_000, False), (60_003, False), (60_003, True)):
+for N, balance, entry in ((60_000, False, "packed"), (60_003, False, "packed"), (60_003, True, "packed"),
+                          (60_003, False, "ids"), (60_000, False, "list")):
     w = dict(bench.WORKLOADS["c3"], N=N, E=400_000, R=23, L=2)
     model = bench.build_model(w, dev, "f16").train()
     with torch.no_grad():                      # O(1) generated weights so that the update matters
@@ -45,7 +46,13 @@ for N, balance in ((60_000, False), (60_003, False), (60_003, True)):
         ranges = plan_partition_by_edges(rowptr, world)
     sf = ShardedForward(model, N, dist.group.WORLD, ranges=ranges)
     x_sh = x.clone().requires_grad_(True)
-    out = sf.forward_packed(x_sh, ei, utf8, offsets)
+    names = [f"relation_{r:05d}" for r in range(w["R"])]
+    if entry == "ids":                         # the ids-in entry: relation ids + vocabulary, whole edge list
+        out = sf.forward_ids(x_sh, ei, _rel, names)
+    elif entry == "list":                      # the reference's call shape
+        out = sf.forward(x_sh, ei, [names[r] for r in _rel.tolist()])
+    else:
+        out = sf.forward_packed(x_sh, ei, utf8, offsets)
     (out * loss_w[sf.lo:sf.hi]).sum().backward()
     sf.allreduce_gradients()
     gx = x_sh.grad.clone()
@@ -61,7 +68,7 @@ for N, balance in ((60_000, False), (60_003, False), (60_003, True)):
     good = rel <= 2e-3 and all(v[0] == v[0] for v in errs.values())
     ok = ok and good
     if rank == 0:
-        print(f"N={N} ranges={'edges' if balance else 'nodes'} world {world}: worst {worst[0]}: |diff| {worst[1][0]:.3e} "
+        print(f"N={N} ranges={'edges' if balance else 'nodes'} entry={entry} world {world}: worst {worst[0]}: |diff| {worst[1][0]:.3e} "
               f"of max {worst[1][1]:.3e} = {rel:.2e} (bound 2e-3)  out diff {errs['out'][0]:.2e}  "
               f"{'ok' if good else 'MISMATCH'}", flush=True)
 flag = torch.tensor([0 if ok else 1], device=dev)
