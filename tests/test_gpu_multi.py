@@ -44,3 +44,13 @@ def test_sharded_paths_on_one_gpu_world_size_1():
     r = _torchrun("check_sharded_grad.py", 1, 29520)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "world 1" in r.stdout
+
+
+def test_sharded_training_example_runs_on_one_gpu():
+    """examples/train_sharded.py under torchrun with one process: the loss over all rows falls, the script's own
+    checks (replicas identical, loss decreased) pass."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
+           "--master-addr", "127.0.0.1", "--master-port", "29521", os.path.join(ROOT, "examples", "train_sharded.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "step  10" in r.stdout
